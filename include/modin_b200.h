@@ -1,0 +1,248 @@
+/*
+ * modin_b200.h — C ABI of libmodin_b200.so: the sm_100a kernels behind Modin's
+ * partition-execution hot path (Map / Binary / TreeReduce / GroupByReduce /
+ * broadcast-merge operator templates).
+ *
+ * The reference (modin-project/modin) is pure Python and has NO native/FFI
+ * boundary on this path: the per-partition arithmetic is a Python closure
+ * around a pandas method, invoked by
+ *   PandasDataframePartition.apply(func)            modin/core/dataframe/pandas/partitioning/partition.py:77-140
+ *   PandasOnPythonDataframePartition.apply          modin/core/execution/python/implementations/pandas_on_python/partitioning/partition.py:76-123
+ *   PandasDataframeAxisPartition.deploy_axis_func   modin/core/dataframe/pandas/partitioning/axis_partition.py:396-499
+ * Each entry point below therefore names the *pandas call site in the
+ * reference* whose per-block work it replaces.  INTEGRATION.md shows the
+ * ctypes binding (modin_b200/_lib.py) a Modin maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from mb200_last_error() (thread-local, valid until the next
+ *     failing call on the same thread);
+ *   - all column pointers are DEVICE pointers (one contiguous buffer per column,
+ *     Arrow fixed-width layout: float64 / int64 / uint8-bool; float64 nulls are
+ *     NaN as in pandas, so no validity bitmap is carried on this path);
+ *   - pointer *arrays* (`const void* const* cols`) and scalar arrays are HOST
+ *     arrays of length ncols; they are copied into kernel parameters;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous with respect to the host unless stated;
+ *   - no global state besides the CUDA context; no CPU fallback: on a machine
+ *     without a usable sm_100 device every compute call fails with an error.
+ */
+#ifndef MODIN_B200_H
+#define MODIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_ABI_VERSION 1
+#define MB200_MAX_COLS 32 /* max columns per launch == Modin's MinColumnPartitionSize (envvars.py:1149-1190) */
+
+typedef void* mb200_stream_t;
+
+/* ---- column element types ------------------------------------------------ */
+enum mb200_dtype {
+  MB200_F64 = 0, /* pandas float64 (NaN == null) */
+  MB200_I64 = 1, /* pandas int64 */
+  MB200_U8 = 2   /* pandas bool (0/1 bytes) */
+};
+
+/* ---- Map / Binary elementwise opcodes ------------------------------------
+ * Replaces the per-block pandas call of
+ *   Map.register(pandas.DataFrame.abs)          qc.py:2036      (MB200_OP_ABS)
+ *   Map.register(pandas.DataFrame.isna/notna)   qc.py:2063-2106 (ISNA/NOTNA)
+ *   qc.fillna scalar branch                      qc.py:2710-2813 (FILLNA)
+ *   Binary.register(pandas.DataFrame.<op>)       qc.py:535-624   (ADD..GE, scalar and frame forms)
+ * `*_S` forms take the right operand from the per-column scalar s0[col];
+ * R* forms are the reflected versions (scalar OP x).
+ * AFFINE  : out = (x * s0[col]) + s1[col]   -- two IEEE roundings, like pandas `df * b + c`
+ * FMA3    : out = (a * b) + c  on three frames -- two roundings, NOT a fused multiply-add
+ * Comparison ops write uint8 0/1.
+ */
+enum mb200_map_op {
+  MB200_OP_ABS = 0,
+  MB200_OP_NEG = 1,
+  MB200_OP_ISNA = 2,
+  MB200_OP_NOTNA = 3,
+  MB200_OP_FILLNA_S = 4,
+  MB200_OP_AFFINE = 5,
+  MB200_OP_ADD_S = 6,
+  MB200_OP_SUB_S = 7,
+  MB200_OP_RSUB_S = 8,
+  MB200_OP_MUL_S = 9,
+  MB200_OP_DIV_S = 10,
+  MB200_OP_RDIV_S = 11,
+  MB200_OP_EQ_S = 12,
+  MB200_OP_NE_S = 13,
+  MB200_OP_LT_S = 14,
+  MB200_OP_LE_S = 15,
+  MB200_OP_GT_S = 16,
+  MB200_OP_GE_S = 17,
+  MB200_OP_CLIP_S = 18, /* min(max(x, s0), s1), NaN preserved */
+  MB200_OP_COPY = 19,
+  /* two-frame ops (in0 OP in1) */
+  MB200_OP_ADD = 32,
+  MB200_OP_SUB = 33,
+  MB200_OP_MUL = 34,
+  MB200_OP_DIV = 35,
+  MB200_OP_EQ = 36,
+  MB200_OP_NE = 37,
+  MB200_OP_LT = 38,
+  MB200_OP_LE = 39,
+  MB200_OP_GT = 40,
+  MB200_OP_GE = 41,
+  MB200_OP_FILLNA = 42, /* isnan(in0) ? in1 : in0 */
+  /* three-frame op */
+  MB200_OP_FMA3 = 64
+};
+
+/* ---- TreeReduce opcodes ---------------------------------------------------
+ * Replaces the map-phase pandas call of TreeReduce.register(pandas.DataFrame.sum / count /
+ * max / min / mean) qc.py:976-1096 (per block: nanops.nansum etc.).
+ */
+enum mb200_reduce_op {
+  MB200_RED_SUM = 0,  /* out_val = sum (NaN skipped iff skipna), out_cnt = #non-NaN */
+  MB200_RED_MIN = 1,  /* out_val = min over non-NaN, out_cnt = #non-NaN             */
+  MB200_RED_MAX = 2,
+  MB200_RED_COUNT = 3 /* out_cnt only */
+};
+
+/* ---- groupby aggregate selection (bit flags) ------------------------------ */
+enum mb200_gb_flags {
+  MB200_GB_SUM = 1,   /* acc[g][v]  += x   (NaN skipped, pandas min_count=0)       */
+  MB200_GB_COUNT = 2, /* cnt[g][v]  += !isnan(x)                                     */
+  MB200_GB_SIZE = 4   /* size[g]    += 1                                             */
+};
+
+/* ======================= runtime / memory ================================== */
+int mb200_abi_version(void);
+const char* mb200_last_error(void);
+/* Fails unless a CUDA device of compute capability 10.x is present. */
+int mb200_device_check(int device);
+int mb200_device_info(int device, int* sm_count, size_t* l2_bytes, size_t* total_mem,
+                      int* cc_major, int* cc_minor);
+int mb200_set_device(int device);
+int mb200_alloc(void** ptr, size_t bytes, mb200_stream_t stream);
+int mb200_free(void* ptr, mb200_stream_t stream);
+int mb200_alloc_host(void** ptr, size_t bytes); /* pinned */
+int mb200_free_host(void* ptr);
+int mb200_h2d(void* dst, const void* src, size_t bytes, mb200_stream_t stream);
+int mb200_d2h(void* dst, const void* src, size_t bytes, mb200_stream_t stream);
+int mb200_d2d(void* dst, const void* src, size_t bytes, mb200_stream_t stream);
+int mb200_memset(void* dst, int byte, size_t bytes, mb200_stream_t stream);
+int mb200_stream_sync(mb200_stream_t stream);
+/* number of kernels launched by this library in this process (bench `gpu_launches`) */
+int64_t mb200_launch_count(void);
+
+/* ======================= Map / Binary ====================================== */
+/* One launch sweeps all `ncols` columns of a block (partition).
+ * in1/in2 may be NULL for unary ops; s0/s1 are per-column scalar bit patterns
+ * (double or int64 according to `dtype`), may be NULL when the op takes none.
+ * `out_dtype` must be MB200_U8 for predicates, else equal `dtype`
+ * (MB200_OP_DIV on int64 inputs writes float64).
+ * Reference: pm.map_partitions pm.py:708-769, pm.n_ary_operation pm.py:1725-1788.
+ */
+int mb200_map(int op, int dtype, int ncols, const void* const* in0, const void* const* in1,
+              const void* const* in2, void* const* out, int64_t nrows, const uint64_t* s0,
+              const uint64_t* s1, mb200_stream_t stream);
+
+/* Streaming form of mb200_map for HOST-resident blocks: chunks of rows are staged through
+ * pinned buffers, H2D / kernel / D2H overlapped on three streams.  Host pointers in, host
+ * pointers out.  Synchronous.  Used by the e2e measurement and by from_pandas->op->to_pandas. */
+int mb200_map_host(int op, int dtype, int ncols, const void* const* in0_host,
+                   const void* const* in1_host, const void* const* in2_host, void* const* out_host,
+                   int64_t nrows, const uint64_t* s0, const uint64_t* s1, int64_t chunk_rows);
+
+/* ======================= TreeReduce ======================================== */
+/* Scratch size (bytes) needed by mb200_reduce_columns for `ncols` columns. */
+size_t mb200_reduce_scratch_bytes(int ncols);
+/* Column-wise reduction of one block: out_val[ncols] (double or int64 by dtype) and
+ * out_cnt[ncols] (int64) are DEVICE arrays.  Deterministic (fixed tile->CTA map, fixed
+ * combine order).  Float sums are Kahan-compensated per thread.
+ * variant: 0 = TMA (cp.async.bulk) staged shared-memory tiles, 1 = direct 256-bit loads.
+ * Reference: PandasDataframe.tree_reduce map phase df.py:2208-2250.
+ */
+int mb200_reduce_columns(int op, int dtype, int ncols, const void* const* in, int64_t nrows,
+                         int skipna, void* out_val, int64_t* out_cnt, void* scratch,
+                         int variant, mb200_stream_t stream);
+
+/* ======================= GroupByReduce ===================================== */
+typedef struct mb200_gb_table mb200_gb_table; /* opaque, device resident */
+
+/* Create an empty open-addressed table with room for `group_capacity` distinct keys and
+ * `nvals` float64 accumulator columns.  flags = mb200_gb_flags. */
+int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags,
+                    mb200_stream_t stream);
+int mb200_gb_destroy(mb200_gb_table* table, mb200_stream_t stream);
+/* Hash-aggregate one block: keys[nrows] int64, vals[nvals][nrows] float64 (device).
+ * May be called repeatedly (one call per row partition resident on this GPU);
+ * replaces GroupByReduce.map alg/groupby.py:124-208 (df.groupby(by).sum() per block).
+ * If the table overflows, the call succeeds but mb200_gb_ngroups reports overflow. */
+int mb200_gb_accumulate(mb200_gb_table* table, const int64_t* keys, const void* const* vals,
+                        int64_t nrows, mb200_stream_t stream);
+/* Merge partial tables (keys + partial sums/counts/sizes as produced by mb200_gb_emit) into
+ * `table`: replaces GroupByReduce.reduce alg/groupby.py:211-300 (groupby(level=0).sum()). */
+int mb200_gb_merge_partial(mb200_gb_table* table, const int64_t* keys,
+                           const void* const* sums, const void* const* cnts,
+                           const int64_t* sizes, int64_t npartial, mb200_stream_t stream);
+/* Synchronises `stream`; returns number of groups and whether capacity was exceeded. */
+int mb200_gb_ngroups(mb200_gb_table* table, int64_t* ngroups, int* overflow,
+                     mb200_stream_t stream);
+/* Scratch bytes needed by mb200_gb_emit for `ngroups` groups. */
+size_t mb200_gb_emit_scratch_bytes(int64_t ngroups);
+/* Write the result block: out_keys[ngroups] (ascending iff sort), out_sums[nvals][ngroups],
+ * out_cnts[nvals][ngroups] (int64, may be NULL), out_sizes[ngroups] (may be NULL). */
+int mb200_gb_emit(mb200_gb_table* table, int64_t ngroups, int sort, int64_t* out_keys,
+                  void* const* out_sums, void* const* out_cnts, int64_t* out_sizes,
+                  void* scratch, mb200_stream_t stream);
+
+/* ======================= broadcast hash join =============================== */
+typedef struct mb200_join_table mb200_join_table;
+/* Build a hash table over the (broadcast) right/dim key column.
+ * Replaces the right side of pandas.merge in MergeImpl.row_axis_merge merge.py:104-252. */
+int mb200_join_build(mb200_join_table** table, const int64_t* dim_keys, int64_t ndim,
+                     mb200_stream_t stream);
+int mb200_join_destroy(mb200_join_table* table, mb200_stream_t stream);
+/* 1 if every dim key is distinct (many-to-one probe is valid), else 0. Synchronises. */
+int mb200_join_is_unique(mb200_join_table* table, int* unique, mb200_stream_t stream);
+/* many-to-one probe: out_idx[i] = row of fact_keys[i] in dim, or -1. Also counts matches. */
+int mb200_join_probe(mb200_join_table* table, const int64_t* fact_keys, int64_t nfact,
+                     int64_t* out_idx, int64_t* out_nmatch_dev, mb200_stream_t stream);
+/* fused left-join payload gather for unique dim keys:
+ * out[c][i] = hit ? dim_cols[c][idx] : NaN  (float64 payload; int64 payload promoted by caller) */
+int mb200_join_probe_gather(mb200_join_table* table, const int64_t* fact_keys, int64_t nfact,
+                            int ncols, const void* const* dim_cols, int dim_dtype,
+                            void* const* out_cols, int64_t* out_nmatch_dev,
+                            mb200_stream_t stream);
+/* take: out[c][i] = idx[i] >= 0 ? src[c][idx[i]] : null_value (gather rows). */
+int mb200_take(int dtype, int ncols, const void* const* src, const int64_t* idx, int64_t nidx,
+               void* const* out, mb200_stream_t stream);
+/* stream compaction of rows where idx >= 0: writes positions; returns count via device ptr. */
+int mb200_compact_hits(const int64_t* idx, int64_t n, int64_t* out_pos, int64_t* out_count_dev,
+                       void* scratch, size_t scratch_bytes, mb200_stream_t stream);
+
+/* ======================= synthetic data (from_map-style generators) ======== */
+/* Counter-based generators, reproducible for any row range; the numpy twin lives in
+ * modin_b200/synth.py.  value(row, col) depends only on (seed, col, row_offset + i).
+ * gen_f64: approx N(0,1) (Irwin-Hall of 4 exact uniforms); nan_per_64k of every 65536
+ * values are NaN.  gen_i64: uniform integer in [0, modulus). */
+int mb200_gen_f64(double* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                  int nan_per_64k, mb200_stream_t stream);
+int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                  uint64_t modulus, mb200_stream_t stream);
+
+/* ======================= utilities ========================================= */
+/* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.
+ * scratch_bytes >= mb200_sort_scratch_bytes(n). */
+size_t mb200_sort_scratch_bytes(int64_t n);
+int mb200_sort_pairs_i64(int64_t* keys, int64_t* payload, int64_t n, void* scratch,
+                         size_t scratch_bytes, mb200_stream_t stream);
+/* Write >= L2-sized buffer to evict L2 between timed iterations. */
+int mb200_flush_l2(void* buf, size_t bytes, mb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODIN_B200_H */

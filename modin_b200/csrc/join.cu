@@ -1,0 +1,415 @@
+// join.cu — broadcast hash join: build once over the (broadcast) dim key column, probe with
+// every fact row block, gather the dim payload.
+//
+// Reference path: MergeImpl.row_axis_merge (modin/core/storage_formats/pandas/merge.py:104-252)
+// collapses the right frame into one partition (`right._modin_frame.combine()`, merge.py:178),
+// broadcasts it to every left row partition (broadcast_apply_full_axis, df.py:3483-3676) and
+// calls pandas.merge(left_block, right, how, on, sort=False) per block (merge.py:166-168);
+// pandas factorizes both key columns, builds hash-join indexers and `take`s the payload.
+//
+// Here: slots[cap] {int64 key, int32 row} (cap = pow2 >= 2 * ndim).  For the many-to-one case
+// (distinct dim keys; star-schema fact x dim) a fact row needs one probe and the output keeps
+// the fact's row order, so `how="left"` only has to materialise the dim payload columns; the
+// fact columns are shared by reference with the input frame (blocks are immutable values).
+// Algorithmic traffic for the fused probe+gather: 8 B key read + 8 B per payload column written
+// per fact row; the slot / payload reads hit the L2-resident dim table.
+#include "common.cuh"
+
+namespace mb200 {
+
+struct __align__(16) JSlot {
+  long long key;
+  int row;  // -1 empty, -2 being inserted, >= 0 dim row index
+  int pad;
+};
+struct JMeta {
+  int duplicate;  // some dim key occurs twice
+  int pad;
+};
+
+}  // namespace mb200
+
+struct mb200_join_table {
+  mb200::JSlot* slots;
+  long long cap;
+  long long ndim;
+  mb200::JMeta* meta;
+};
+
+namespace mb200 {
+
+__device__ __forceinline__ void ld_jslot(const JSlot* s, long long& key, int& row) {
+  unsigned long long a, b;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s) : "memory");
+  key = (long long)a;
+  row = (int)(unsigned int)(b & 0xffffffffULL);
+}
+
+__global__ void join_init_kernel(JSlot* slots, long long cap, JMeta* meta) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) {
+    JSlot s;
+    s.key = 0;
+    s.row = -1;
+    s.pad = 0;
+    slots[i] = s;
+  }
+  if (i == 0) {
+    meta->duplicate = 0;
+    meta->pad = 0;
+  }
+}
+
+__global__ void join_build_kernel(JSlot* slots, unsigned int mask, const long long* __restrict__ keys, long long n,
+                                  JMeta* meta) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long k = keys[i];
+    unsigned int slot = hash_key(k) & mask;
+    for (;;) {
+      long long sk;
+      int r;
+      ld_jslot(&slots[slot], sk, r);
+      if (r >= 0) {
+        if (sk == k) {  // duplicate dim key: keep the first row seen, flag it
+          meta->duplicate = 1;
+          break;
+        }
+        slot = (slot + 1) & mask;
+        continue;
+      }
+      if (r == -1) {
+        const int old = atomicCAS(&slots[slot].row, -1, -2);
+        if (old == -1) {
+          *reinterpret_cast<volatile long long*>(&slots[slot].key) = k;
+          __threadfence();
+          *reinterpret_cast<volatile int*>(&slots[slot].row) = (int)i;
+          break;
+        }
+      }
+      // slot is being published by another thread: look again
+    }
+  }
+}
+
+__device__ __forceinline__ int join_lookup(const JSlot* slots, unsigned int mask, long long k) {
+  unsigned int slot = hash_key(k) & mask;
+  for (;;) {
+    long long sk;
+    int r;
+    ld_jslot(&slots[slot], sk, r);
+    if (r < 0) return -1;  // table is read-only during probing: empty slot terminates the chain
+    if (sk == k) return r;
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) join_probe_kernel(const JSlot* __restrict__ slots, unsigned int mask,
+                                                         const long long* __restrict__ fact_keys, long long n,
+                                                         long long* __restrict__ out_idx,
+                                                         unsigned long long* nmatch) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint64_t pol = l2_policy_evict_first();
+  unsigned long long hits = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = join_lookup(slots, mask, ldg_stream_i64(fact_keys + i, pol));
+    out_idx[i] = (long long)r;
+    hits += (r >= 0);
+  }
+  // one atomic per warp
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, m);
+  if ((threadIdx.x & 31) == 0 && hits && nmatch) atomicAdd(nmatch, hits);
+}
+
+struct GatherParams {
+  const void* dim_cols[MB200_MAX_COLS];
+  void* out_cols[MB200_MAX_COLS];
+  int ncols;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) join_probe_gather_kernel(const JSlot* __restrict__ slots, unsigned int mask,
+                                                                const long long* __restrict__ fact_keys, long long n,
+                                                                const __grid_constant__ GatherParams g,
+                                                                unsigned long long* nmatch, T null_value) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint64_t pol = l2_policy_evict_first();
+  unsigned long long hits = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = join_lookup(slots, mask, ldg_stream_i64(fact_keys + i, pol));
+    hits += (r >= 0);
+    for (int c = 0; c < g.ncols; ++c) {
+      const T v = r >= 0 ? static_cast<const T*>(g.dim_cols[c])[r] : null_value;
+      static_cast<T*>(g.out_cols[c])[i] = v;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, m);
+  if ((threadIdx.x & 31) == 0 && hits && nmatch) atomicAdd(nmatch, hits);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) take_kernel(const __grid_constant__ GatherParams g,
+                                                   const long long* __restrict__ idx, long long n, T null_value) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long r = idx[i];
+    for (int c = 0; c < g.ncols; ++c)
+      static_cast<T*>(g.out_cols[c])[i] = r >= 0 ? static_cast<const T*>(g.dim_cols[c])[r] : null_value;
+  }
+}
+
+// ---- compaction of hit positions: block counts -> scan -> ranked scatter
+constexpr int kCompBlock = 256;
+constexpr int kCompItems = 2048;  // per block
+
+__global__ void __launch_bounds__(kCompBlock) compact_count_kernel(const long long* __restrict__ idx, long long n,
+                                                                   unsigned int* __restrict__ counts) {
+  __shared__ unsigned int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * kCompItems;
+  unsigned int c = 0;
+  for (int j = threadIdx.x; j < kCompItems; j += kCompBlock) {
+    const long long i = base + j;
+    c += (i < n && idx[i] >= 0);
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s;
+}
+
+// exclusive scan of counts[nblocks] into 64-bit offsets; single block; also writes the total.
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned int* __restrict__ counts, long long nblocks,
+                                                            long long* __restrict__ offsets, long long* total) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const long long per = (nblocks + 1023) / 1024;
+  const long long lo = (long long)t * per;
+  long long hi = lo + per;
+  if (hi > nblocks) hi = nblocks;
+  long long s = 0;
+  for (long long i = lo; i < hi; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = t ? part[t - 1] : 0;
+  for (long long i = lo; i < hi; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+  if (t == 1023 && total) *total = part[1023];
+}
+
+__global__ void __launch_bounds__(kCompBlock) compact_scatter_kernel(const long long* __restrict__ idx, long long n,
+                                                                     const long long* __restrict__ offsets,
+                                                                     long long* __restrict__ out_pos) {
+  __shared__ unsigned int warp_base[kCompBlock / 32];
+  __shared__ unsigned int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * kCompItems;
+  const long long off = offsets[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < kCompItems; j0 += kCompBlock) {
+    const long long i = base + j0 + threadIdx.x;
+    const bool hit = (i < n) && idx[i] >= 0;
+    const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+    const unsigned int rank = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_base[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // serial prefix over 8 warps keeps row order
+      unsigned int run = running;
+      for (int w = 0; w < kCompBlock / 32; ++w) {
+        const unsigned int c = warp_base[w];
+        warp_base[w] = run;
+        run += c;
+      }
+      running = run;
+    }
+    __syncthreads();
+    if (hit) out_pos[off + warp_base[warp] + rank] = i;
+    __syncthreads();
+  }
+}
+
+static long long jnext_pow2(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static int launch_grid(long long n, int threads, int per_sm, int* grid) {
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long g = (n + threads - 1) / threads;
+  const long long cap = (long long)dp.sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  *grid = (int)g;
+  return 0;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int mb200_join_build(mb200_join_table** table, const int64_t* dim_keys, int64_t ndim,
+                                mb200_stream_t stream) {
+  if (!table) return fail("mb200_join_build", "null out pointer");
+  if (ndim < 0 || ndim > 0x7fffffffLL) return fail("mb200_join_build", "dim rows must be in [0, 2^31)");
+  if (ndim > 0 && !dim_keys) return fail("mb200_join_build", "null keys");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  mb200_join_table* t = new mb200_join_table();
+  t->ndim = ndim;
+  t->cap = jnext_pow2(2 * ndim < 1024 ? 1024 : 2 * ndim);
+  t->slots = nullptr;
+  t->meta = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&t->slots, (size_t)t->cap * sizeof(JSlot), st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->meta, sizeof(JMeta), st);
+  if (e != cudaSuccess) {
+    mb200_join_destroy(t, stream);
+    return cuda_fail("mb200_join_build", e);
+  }
+  join_init_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->meta);
+  MB_LAUNCH_CHECK("join_init_kernel");
+  if (ndim > 0) {
+    int grid;
+    if (int rc = launch_grid(ndim, 256, 8, &grid)) return rc;
+    join_build_kernel<<<grid, 256, 0, st>>>(t->slots, (unsigned int)(t->cap - 1),
+                                            reinterpret_cast<const long long*>(dim_keys), ndim, t->meta);
+    MB_LAUNCH_CHECK("join_build_kernel");
+  }
+  *table = t;
+  return 0;
+}
+
+extern "C" int mb200_join_destroy(mb200_join_table* t, mb200_stream_t stream) {
+  if (!t) return 0;
+  if (t->slots) cudaFreeAsync(t->slots, (cudaStream_t)stream);
+  if (t->meta) cudaFreeAsync(t->meta, (cudaStream_t)stream);
+  delete t;
+  return 0;
+}
+
+extern "C" int mb200_join_is_unique(mb200_join_table* t, int* unique, mb200_stream_t stream) {
+  if (!t || !unique) return fail("mb200_join_is_unique", "null argument");
+  JMeta m;
+  MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  MB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *unique = m.duplicate ? 0 : 1;
+  return 0;
+}
+
+extern "C" int mb200_join_probe(mb200_join_table* t, const int64_t* fact_keys, int64_t nfact, int64_t* out_idx,
+                                int64_t* out_nmatch_dev, mb200_stream_t stream) {
+  if (!t) return fail("mb200_join_probe", "null table");
+  if (nfact < 0) return fail("mb200_join_probe", "negative nfact");
+  if (nfact == 0) return 0;
+  if (!fact_keys || !out_idx) return fail("mb200_join_probe", "null argument");
+  int grid;
+  if (int rc = launch_grid(nfact, 256, 8, &grid)) return rc;
+  join_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      t->slots, (unsigned int)(t->cap - 1), reinterpret_cast<const long long*>(fact_keys), nfact,
+      reinterpret_cast<long long*>(out_idx), reinterpret_cast<unsigned long long*>(out_nmatch_dev));
+  MB_LAUNCH_CHECK("join_probe_kernel");
+  return 0;
+}
+
+extern "C" int mb200_join_probe_gather(mb200_join_table* t, const int64_t* fact_keys, int64_t nfact, int ncols,
+                                       const void* const* dim_cols, int dim_dtype, void* const* out_cols,
+                                       int64_t* out_nmatch_dev, mb200_stream_t stream) {
+  if (!t) return fail("mb200_join_probe_gather", "null table");
+  if (ncols < 0 || ncols > MB200_MAX_COLS) return fail("mb200_join_probe_gather", "ncols out of range (0..32)");
+  if (nfact < 0) return fail("mb200_join_probe_gather", "negative nfact");
+  if (nfact == 0) return 0;
+  if (!fact_keys || (ncols > 0 && (!dim_cols || !out_cols))) return fail("mb200_join_probe_gather", "null argument");
+  GatherParams g;
+  memset(&g, 0, sizeof(g));
+  g.ncols = ncols;
+  for (int c = 0; c < ncols; ++c) {
+    g.dim_cols[c] = dim_cols[c];
+    g.out_cols[c] = out_cols[c];
+    if (!out_cols[c] || (!dim_cols[c] && t->ndim > 0)) return fail("mb200_join_probe_gather", "null column pointer");
+  }
+  int grid;
+  if (int rc = launch_grid(nfact, 256, 8, &grid)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned int mask = (unsigned int)(t->cap - 1);
+  unsigned long long* nm = reinterpret_cast<unsigned long long*>(out_nmatch_dev);
+  const long long* fk = reinterpret_cast<const long long*>(fact_keys);
+  if (dim_dtype == MB200_F64) {
+    join_probe_gather_kernel<double><<<grid, 256, 0, st>>>(t->slots, mask, fk, nfact, g, nm,
+                                                           (double)__builtin_nan(""));
+  } else if (dim_dtype == MB200_I64) {
+    join_probe_gather_kernel<long long><<<grid, 256, 0, st>>>(t->slots, mask, fk, nfact, g, nm, 0LL);
+  } else {
+    return fail("mb200_join_probe_gather", "unsupported payload dtype");
+  }
+  MB_LAUNCH_CHECK("join_probe_gather_kernel");
+  return 0;
+}
+
+extern "C" int mb200_take(int dtype, int ncols, const void* const* src, const int64_t* idx, int64_t nidx,
+                          void* const* out, mb200_stream_t stream) {
+  if (ncols < 0 || ncols > MB200_MAX_COLS) return fail("mb200_take", "ncols out of range (0..32)");
+  if (nidx < 0) return fail("mb200_take", "negative nidx");
+  if (nidx == 0 || ncols == 0) return 0;
+  if (!src || !idx || !out) return fail("mb200_take", "null argument");
+  GatherParams g;
+  memset(&g, 0, sizeof(g));
+  g.ncols = ncols;
+  for (int c = 0; c < ncols; ++c) {
+    g.dim_cols[c] = src[c];
+    g.out_cols[c] = out[c];
+    if (!out[c]) return fail("mb200_take", "null column pointer");
+  }
+  int grid;
+  if (int rc = launch_grid(nidx, 256, 8, &grid)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* ix = reinterpret_cast<const long long*>(idx);
+  if (dtype == MB200_F64)
+    take_kernel<double><<<grid, 256, 0, st>>>(g, ix, nidx, (double)__builtin_nan(""));
+  else if (dtype == MB200_I64)
+    take_kernel<long long><<<grid, 256, 0, st>>>(g, ix, nidx, 0LL);
+  else if (dtype == MB200_U8)
+    take_kernel<unsigned char><<<grid, 256, 0, st>>>(g, ix, nidx, (unsigned char)0);
+  else
+    return fail("mb200_take", "unsupported dtype");
+  MB_LAUNCH_CHECK("take_kernel");
+  return 0;
+}
+
+extern "C" int mb200_compact_hits(const int64_t* idx, int64_t n, int64_t* out_pos, int64_t* out_count_dev,
+                                  void* scratch, size_t scratch_bytes, mb200_stream_t stream) {
+  if (n < 0) return fail("mb200_compact_hits", "negative n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    if (out_count_dev) MB_CUDA(cudaMemsetAsync(out_count_dev, 0, 8, st));
+    return 0;
+  }
+  if (!idx || !out_pos || !scratch) return fail("mb200_compact_hits", "null argument");
+  const long long nblocks = (n + kCompItems - 1) / kCompItems;
+  const size_t need = (size_t)nblocks * 12 + 256;
+  if (scratch_bytes < need) return fail("mb200_compact_hits", "scratch too small (need 12 B per 2048 rows + 256)");
+  long long* offsets = static_cast<long long*>(scratch);
+  unsigned int* counts = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + (size_t)nblocks * 8);
+  const long long* ix = reinterpret_cast<const long long*>(idx);
+  compact_count_kernel<<<(unsigned)nblocks, kCompBlock, 0, st>>>(ix, n, counts);
+  MB_LAUNCH_CHECK("compact_count_kernel");
+  compact_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, offsets, reinterpret_cast<long long*>(out_count_dev));
+  MB_LAUNCH_CHECK("compact_scan_kernel");
+  compact_scatter_kernel<<<(unsigned)nblocks, kCompBlock, 0, st>>>(ix, n, offsets, reinterpret_cast<long long*>(out_pos));
+  MB_LAUNCH_CHECK("compact_scatter_kernel");
+  return 0;
+}

@@ -1,0 +1,97 @@
+// synth.cu — counter-based synthetic column generators (from_map-style on-device ingest,
+// cf. BaseIO.from_map modin/core/io/io.py:184-209) and the L2 flush used between timed runs.
+//
+// value(seed, col, row) is a pure function, so any row range of any partition on any GPU is
+// reproducible; modin_b200/synth.py holds the bit-identical numpy twin used by the tests.
+//   z1 = mix64(seed * K1 + col * K2 + row + 1),  z2 = mix64(z1 + K3)
+//   f64: four exact uniforms u = (32-bit piece) * 2^-32 ; x = ((u0+u1)+(u2+u3) - 2) * sqrt(3)
+//        (Irwin-Hall(4), mean 0, variance 1; every operation is a single IEEE rounding, so
+//        numpy reproduces it bit for bit);  NaN when (z2 >> 48) < nan_per_64k... uses z1 low bits.
+//   i64: ((z1 >> 32) * modulus) >> 32   (uniform in [0, modulus), modulus < 2^32)
+#include "common.cuh"
+
+namespace mb200 {
+
+constexpr unsigned long long K1 = 0x9E3779B97F4A7C15ULL;
+constexpr unsigned long long K2 = 0xD1B54A32D192ED03ULL;
+constexpr unsigned long long K3 = 0x8CB92BA72F3D8DD7ULL;
+
+__device__ __forceinline__ double synth_f64(unsigned long long seed, unsigned long long col, long long row,
+                                            int nan_per_64k) {
+  const unsigned long long z1 = mix64(seed * K1 + col * K2 + (unsigned long long)row + 1ULL);
+  const unsigned long long z2 = mix64(z1 + K3);
+  const double s = 2.3283064365386963e-10;  // 2^-32
+  const double u0 = (double)(unsigned int)(z1 >> 32) * s;
+  const double u1 = (double)(unsigned int)(z1 & 0xffffffffULL) * s;
+  const double u2 = (double)(unsigned int)(z2 >> 32) * s;
+  const double u3 = (double)(unsigned int)(z2 & 0xffffffffULL) * s;
+  const double x = __dmul_rn(__dsub_rn(__dadd_rn(__dadd_rn(u0, u1), __dadd_rn(u2, u3)), 2.0), 1.7320508075688772);
+  const unsigned long long z3 = mix64(z2 + K3);
+  if ((int)(z3 & 0xffffULL) < nan_per_64k) return __longlong_as_double(0x7ff8000000000000LL);
+  return x;
+}
+
+__global__ void gen_f64_kernel(double* __restrict__ out, long long n, unsigned long long seed,
+                               unsigned long long col, long long row_offset, int nan_per_64k) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = synth_f64(seed, col, row_offset + i, nan_per_64k);
+}
+
+__global__ void gen_i64_kernel(long long* __restrict__ out, long long n, unsigned long long seed,
+                               unsigned long long col, long long row_offset, unsigned long long modulus) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long z1 = mix64(seed * K1 + col * K2 + (unsigned long long)(row_offset + i) + 1ULL);
+    out[i] = (long long)(((z1 >> 32) * modulus) >> 32);
+  }
+}
+
+__global__ void flush_kernel(unsigned long long* __restrict__ buf, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (unsigned long long)i;
+}
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" int mb200_gen_f64(double* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                             int nan_per_64k, mb200_stream_t stream) {
+  if (nrows < 0) return fail("mb200_gen_f64", "negative nrows");
+  if (nrows == 0) return 0;
+  if (!out) return fail("mb200_gen_f64", "null output");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long grid = (nrows + 255) / 256;
+  if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
+  gen_f64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(out, nrows, seed, col, row_offset, nan_per_64k);
+  MB_LAUNCH_CHECK("gen_f64_kernel");
+  return 0;
+}
+
+extern "C" int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                             uint64_t modulus, mb200_stream_t stream) {
+  if (nrows < 0) return fail("mb200_gen_i64", "negative nrows");
+  if (modulus == 0 || modulus > 0xffffffffULL) return fail("mb200_gen_i64", "modulus must be in [1, 2^32)");
+  if (nrows == 0) return 0;
+  if (!out) return fail("mb200_gen_i64", "null output");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long grid = (nrows + 255) / 256;
+  if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
+  gen_i64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, seed, col,
+                                                                   row_offset, modulus);
+  MB_LAUNCH_CHECK("gen_i64_kernel");
+  return 0;
+}
+
+extern "C" int mb200_flush_l2(void* buf, size_t bytes, mb200_stream_t stream) {
+  if (!buf || bytes < 8) return fail("mb200_flush_l2", "need a buffer");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  flush_kernel<<<dp.sm_count * 8, 256, 0, (cudaStream_t)stream>>>(static_cast<unsigned long long*>(buf),
+                                                                  (long long)(bytes / 8));
+  MB_LAUNCH_CHECK("flush_kernel");
+  return 0;
+}
