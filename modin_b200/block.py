@@ -1,0 +1,338 @@
+"""DeviceBlock: the payload of one partition -- a device-resident columnar (Arrow-layout) block.
+
+In the reference a block partition wraps a ``pandas.DataFrame``
+(modin/core/dataframe/pandas/partitioning/partition.py:33-76; the Python engine keeps it in
+``self._data``, pandas_on_python/partitioning/partition.py:49-60).  Here the payload is one
+contiguous fixed-width device buffer per column (float64 / int64 / bool-as-uint8; float64
+nulls are NaN exactly as in pandas), plus host-side labels:
+
+* ``columns``  pandas.Index of column labels (host, O(W));
+* ``index``    either a ``pandas.RangeIndex`` (O(1), the 1e9-row case) or device "index
+  columns" (groupby keys) that become the pandas index on ``to_pandas``; never a host
+  object array of n labels.
+
+Blocks are immutable values (same contract as the reference: "Objects of this class are
+treated as immutable", pandas_on_python/partitioning/partition.py:43-44), so column buffers
+are shared by reference between blocks (``mask`` of whole columns, merge pass-through
+columns) instead of being deep-copied at every boundary like PandasOnPython does.
+
+torch is used only as the allocator / stream owner (``torch.empty`` on the device,
+``torch.cuda.current_stream()``); all arithmetic goes through libmodin_b200.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import pandas
+
+from . import _lib
+
+_TORCH = None
+
+
+def torch_mod():
+    global _TORCH
+    if _TORCH is None:
+        import torch
+
+        _TORCH = torch
+    return _TORCH
+
+
+def device_ready() -> bool:
+    """True when a CUDA device is visible to torch (the only way device blocks can exist)."""
+    t = torch_mod()
+    return bool(t.cuda.is_available())
+
+
+def current_device():
+    t = torch_mod()
+    if not t.cuda.is_available():
+        raise _lib.B200Error(
+            "no CUDA device visible: modin_b200 executes partitions on B200 GPUs only (no CPU fallback)"
+        )
+    return t.device("cuda", t.cuda.current_device())
+
+
+def current_stream() -> int:
+    return torch_mod().cuda.current_stream().cuda_stream
+
+
+_NP2CODE = {np.dtype("float64"): _lib.F64, np.dtype("int64"): _lib.I64, np.dtype("bool"): _lib.U8,
+            np.dtype("uint8"): _lib.U8}  # fmt: skip
+
+
+def dtype_code(np_dtype) -> int:
+    try:
+        return _NP2CODE[np.dtype(np_dtype)]
+    except KeyError:
+        raise TypeError(
+            f"dtype {np_dtype} is not supported on the B200 partition path (float64 / int64 / bool only)"
+        ) from None
+
+
+def _torch_dtype(np_dtype):
+    t = torch_mod()
+    np_dtype = np.dtype(np_dtype)
+    if np_dtype == np.float64:
+        return t.float64
+    if np_dtype == np.int64:
+        return t.int64
+    if np_dtype in (np.dtype("bool"), np.dtype("uint8")):
+        return t.uint8
+    raise TypeError(f"dtype {np_dtype} is not supported on the B200 partition path")
+
+
+class DeviceColumn:
+    """One fixed-width column: a 1-D device tensor plus the pandas dtype it stands for."""
+
+    __slots__ = ("data", "dtype")
+
+    def __init__(self, data, dtype):
+        self.data = data  # torch tensor, 1-D, contiguous
+        self.dtype = np.dtype(dtype)
+
+    def __len__(self):
+        return int(self.data.shape[0])
+
+    @property
+    def ptr(self) -> int:
+        return self.data.data_ptr()
+
+    @property
+    def code(self) -> int:
+        return dtype_code(self.dtype)
+
+    @classmethod
+    def empty(cls, n: int, dtype) -> "DeviceColumn":
+        t = torch_mod()
+        return cls(t.empty(int(n), dtype=_torch_dtype(dtype), device=current_device()), dtype)
+
+    @classmethod
+    def from_numpy(cls, arr: np.ndarray) -> "DeviceColumn":
+        t = torch_mod()
+        arr = np.ascontiguousarray(arr)
+        dtype = arr.dtype
+        dtype_code(dtype)
+        host = arr.view(np.uint8) if dtype == np.bool_ else arr
+        dev = t.from_numpy(host).to(current_device(), non_blocking=False)
+        return cls(dev, dtype)
+
+    def to_numpy(self) -> np.ndarray:
+        host = self.data.cpu().numpy()
+        if self.dtype == np.bool_:
+            return host.view(np.bool_)
+        return host
+
+    def slice(self, start: int, stop: int) -> "DeviceColumn":
+        return DeviceColumn(self.data[start:stop], self.dtype)
+
+
+class DeviceBlock:
+    """Columnar device block = payload of one block partition."""
+
+    __slots__ = ("cols", "columns", "index_cols", "index_names", "range_start", "nrows", "index_host", "replicated")
+
+    def __init__(
+        self,
+        cols: Sequence[DeviceColumn],
+        columns,
+        nrows: Optional[int] = None,
+        range_start: int = 0,
+        index_cols: Optional[Sequence[DeviceColumn]] = None,
+        index_names: Optional[list] = None,
+        index_host: Optional[pandas.Index] = None,
+        replicated: bool = False,
+    ):
+        # replicated: under torch.distributed, True when every rank holds this same block (results of
+        # collectives); False when the block is this rank's row shard of a larger frame
+        self.replicated = bool(replicated)
+        self.cols: List[DeviceColumn] = list(cols)
+        self.columns = columns if isinstance(columns, pandas.Index) else pandas.Index(list(columns))
+        if len(self.cols) != len(self.columns):
+            raise ValueError(f"{len(self.cols)} device columns for {len(self.columns)} labels")
+        if nrows is None:
+            if self.cols:
+                nrows = len(self.cols[0])
+            elif index_cols:
+                nrows = len(index_cols[0])
+            elif index_host is not None:
+                nrows = len(index_host)
+            else:
+                nrows = 0
+        self.nrows = int(nrows)
+        for c in self.cols:
+            if len(c) != self.nrows:
+                raise ValueError("ragged device block")
+        self.range_start = int(range_start)
+        self.index_cols = list(index_cols) if index_cols else None
+        self.index_names = list(index_names) if index_names else None
+        self.index_host = index_host  # only for small blocks (reduction results etc.)
+
+    # ---- pandas-like surface used by the partition layer ---------------------------------
+    def __len__(self):
+        return self.nrows
+
+    @property
+    def shape(self):
+        return (self.nrows, len(self.cols))
+
+    @property
+    def dtypes(self) -> pandas.Series:
+        return pandas.Series([c.dtype for c in self.cols], index=self.columns)
+
+    @property
+    def index(self) -> pandas.Index:
+        """Materialise the row labels on the host (only sensible for small blocks)."""
+        if self.index_host is not None:
+            return self.index_host
+        if self.index_cols:
+            arrays = [c.to_numpy() for c in self.index_cols]
+            names = self.index_names or [None] * len(arrays)
+            if len(arrays) == 1:
+                return pandas.Index(arrays[0], name=names[0])
+            return pandas.MultiIndex.from_arrays(arrays, names=names)
+        return pandas.RangeIndex(self.range_start, self.range_start + self.nrows)
+
+    def has_range_index(self) -> bool:
+        return self.index_cols is None and self.index_host is None
+
+    # ---- construction / egress --------------------------------------------------------------
+    @classmethod
+    def from_pandas(cls, df: pandas.DataFrame) -> "DeviceBlock":
+        """H2D ingest of one pandas block (pm.from_pandas -> partition.put, pm.py:1029-1066)."""
+        if isinstance(df, pandas.Series):
+            df = df.to_frame()
+        cols = []
+        for i in range(df.shape[1]):
+            s = df.iloc[:, i]
+            arr = s.to_numpy()
+            if arr.dtype == object or arr.dtype.kind not in "fib":
+                raise TypeError(
+                    f"column {df.columns[i]!r} has dtype {s.dtype}; the B200 partition path carries "
+                    "float64 / int64 / bool columns only"
+                )
+            if arr.dtype.kind == "f" and arr.dtype != np.float64:
+                arr = arr.astype(np.float64)
+            if arr.dtype.kind == "i" and arr.dtype != np.int64:
+                arr = arr.astype(np.int64)
+            cols.append(DeviceColumn.from_numpy(arr))
+        idx = df.index
+        if isinstance(idx, pandas.RangeIndex) and idx.step == 1 and idx.name is None:
+            return cls(cols, df.columns, nrows=len(df), range_start=idx.start)
+        if not isinstance(idx, pandas.MultiIndex) and idx.dtype.kind in "if" and len(idx) > 0:
+            arr = idx.to_numpy()
+            arr = arr.astype(np.int64) if arr.dtype.kind == "i" else arr.astype(np.float64)
+            return cls(cols, df.columns, nrows=len(df), index_cols=[DeviceColumn.from_numpy(arr)],
+                       index_names=[idx.name])  # fmt: skip
+        return cls(cols, df.columns, nrows=len(df), index_host=idx)
+
+    def to_pandas(self) -> pandas.DataFrame:
+        """D2H egress (partition.to_pandas, part.py:330-350)."""
+        data = {i: c.to_numpy() for i, c in enumerate(self.cols)}
+        df = pandas.DataFrame(data, index=self.index, copy=False)
+        df.columns = self.columns
+        if not self.cols:
+            df = pandas.DataFrame(index=self.index, columns=self.columns)
+        return df
+
+    def to_numpy(self) -> np.ndarray:
+        return self.to_pandas().to_numpy()
+
+    # ---- structural ops (no arithmetic) -------------------------------------------------------
+    def with_cols(self, cols, columns=None) -> "DeviceBlock":
+        return DeviceBlock(
+            cols,
+            self.columns if columns is None else columns,
+            nrows=self.nrows,
+            range_start=self.range_start,
+            index_cols=self.index_cols,
+            index_names=self.index_names,
+            index_host=self.index_host,
+            replicated=self.replicated,
+        )
+
+    def select_columns(self, positions: Sequence[int]) -> "DeviceBlock":
+        """Column subset sharing the buffers (mask along axis 1)."""
+        return self.with_cols([self.cols[i] for i in positions], self.columns[list(positions)])
+
+    def slice_rows(self, start: int, stop: int) -> "DeviceBlock":
+        """Contiguous row range as views of the same buffers (mask along axis 0)."""
+        start = max(0, min(start, self.nrows))
+        stop = max(start, min(stop, self.nrows))
+        cols = [c.slice(start, stop) for c in self.cols]
+        icols = [c.slice(start, stop) for c in self.index_cols] if self.index_cols else None
+        ihost = self.index_host[start:stop] if self.index_host is not None else None
+        return DeviceBlock(cols, self.columns, nrows=stop - start, range_start=self.range_start + start,
+                           index_cols=icols, index_names=self.index_names, index_host=ihost)  # fmt: skip
+
+    def column(self, label) -> DeviceColumn:
+        loc = self.columns.get_loc(label)
+        if not isinstance(loc, (int, np.integer)):
+            raise KeyError(f"column label {label!r} is not unique")
+        return self.cols[int(loc)]
+
+    def __repr__(self):
+        return f"DeviceBlock(nrows={self.nrows}, columns={list(self.columns)!r})"
+
+
+def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
+    """Row-wise concatenation of blocks with identical columns (pandas.concat in
+    deploy_axis_func, axpart.py:445-452) -- a D2D copy into fresh column buffers."""
+    t = torch_mod()
+    blocks = [b for b in blocks]
+    if len(blocks) == 1:
+        return blocks[0]
+    first = blocks[0]
+    ncols = len(first.cols)
+    cols = []
+    for j in range(ncols):
+        dts = {b.cols[j].dtype for b in blocks}
+        dtype = first.cols[j].dtype
+        if len(dts) > 1:  # int + float partials (count next to sum) promote like pandas.concat
+            dtype = np.result_type(*dts)
+            parts = [b.cols[j].data.to(_torch_dtype(dtype)) if b.cols[j].dtype != dtype else b.cols[j].data
+                     for b in blocks]  # fmt: skip
+        else:
+            parts = [b.cols[j].data for b in blocks]
+        cols.append(DeviceColumn(t.cat(parts), dtype))
+    nrows = sum(b.nrows for b in blocks)
+    if all(b.index_cols for b in blocks):
+        k = len(first.index_cols)
+        icols = [DeviceColumn(t.cat([b.index_cols[i].data for b in blocks]), first.index_cols[i].dtype)
+                 for i in range(k)]  # fmt: skip
+        return DeviceBlock(cols, first.columns, nrows=nrows, index_cols=icols, index_names=first.index_names)
+    if all(b.index_host is not None for b in blocks):
+        ih = blocks[0].index_host
+        for b in blocks[1:]:
+            ih = ih.append(b.index_host)
+        return DeviceBlock(cols, first.columns, nrows=nrows, index_host=ih)
+    contiguous = all(b.has_range_index() for b in blocks)
+    if contiguous:
+        pos = first.range_start
+        for b in blocks:
+            if b.range_start != pos:
+                contiguous = False
+                break
+            pos += b.nrows
+    if contiguous:
+        return DeviceBlock(cols, first.columns, nrows=nrows, range_start=first.range_start)
+    ih = blocks[0].index
+    for b in blocks[1:]:
+        ih = ih.append(b.index)
+    return DeviceBlock(cols, first.columns, nrows=nrows, index_host=ih)
+
+
+def concat_cols(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
+    """Column-wise concatenation (shares buffers; no copy)."""
+    first = blocks[0]
+    cols = []
+    labels = []
+    for b in blocks:
+        if b.nrows != first.nrows:
+            raise ValueError("column concat of blocks with different row counts")
+        cols.extend(b.cols)
+        labels.extend(list(b.columns))
+    return first.with_cols(cols, pandas.Index(labels))

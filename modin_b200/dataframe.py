@@ -1,0 +1,330 @@
+"""B200Dataframe: the core dataframe over a 2-D grid of device partitions.
+
+Mirror of ``PandasDataframe`` (modin/core/dataframe/pandas/dataframe/dataframe.py) for the
+methods on the hot path: ``map`` (:2253-2319), ``tree_reduce`` (:2208-2250) with
+``_build_treereduce_func`` (:2081-2123) and ``_compute_tree_reduce_metadata`` (:2125-2168),
+``n_ary_op`` (:3851-3950) with the ``_check_if_axes_identical`` fast path (:3678-3707),
+``broadcast_apply`` (:3233-3335), ``broadcast_apply_full_axis`` (:3483-3676),
+``groupby_reduce`` (:4530-4589), ``from_pandas`` / ``from_arrow`` / ``to_pandas``
+(:4592-4722), ``combine``, ``finalize`` / ``wait_computations`` (:4780-4791).
+
+Metadata (index, columns, dtypes, row lengths, column widths) lives on the host and is O(W) or
+a ``RangeIndex``; a 1e9-row index is never materialised.  Under torch.distributed every rank
+holds the row shard it owns: ``_partitions`` is the LOCAL grid, ``index`` the local labels, and
+``global_nrows`` the job-wide row count.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import pandas
+
+from . import dist
+from .block import DeviceBlock
+from .functors import MODIN_UNNAMED_SERIES_LABEL
+from .partitioning import B200PartitionManager
+
+
+class B200Dataframe:
+    _partition_mgr_cls = B200PartitionManager
+    engine = "B200"
+    storage_format = "Arrow"
+
+    def __init__(self, partitions, index=None, columns=None, row_lengths=None, column_widths=None, dtypes=None,
+                 pandas_backend=None):  # fmt: skip
+        self._partitions = np.asarray(partitions, dtype=object)
+        if self._partitions.ndim != 2:
+            raise ValueError("partitions must be a 2-D grid")
+        self._index_cache = index
+        self._columns_cache = columns
+        self._row_lengths_cache = list(row_lengths) if row_lengths is not None else None
+        self._column_widths_cache = list(column_widths) if column_widths is not None else None
+        self._dtypes = dtypes
+        self._pandas_backend = pandas_backend
+        self._filter_empties()
+
+    @property
+    def __constructor__(self):
+        return type(self)
+
+    # ---- metadata ----------------------------------------------------------------------------
+    def _filter_empties(self):
+        """Drop zero-length row / column partitions (df.py:582-640), keeping at least a 1x1 grid."""
+        if self._partitions.size == 0:
+            return
+        rl = self.row_lengths
+        cw = self.column_widths
+        keep_r = [i for i, n in enumerate(rl) if n > 0] or [0]
+        keep_c = [j for j, n in enumerate(cw) if n > 0] or [0]
+        if len(keep_r) != len(rl) or len(keep_c) != len(cw):
+            self._partitions = self._partitions[np.ix_(keep_r, keep_c)]
+            self._row_lengths_cache = [rl[i] for i in keep_r]
+            self._column_widths_cache = [cw[j] for j in keep_c]
+
+    @property
+    def row_lengths(self) -> List[int]:
+        if self._row_lengths_cache is None:
+            self._row_lengths_cache = [row[0].length() for row in self._partitions] if self._partitions.size else []
+        return self._row_lengths_cache
+
+    @property
+    def column_widths(self) -> List[int]:
+        if self._column_widths_cache is None:
+            self._column_widths_cache = [p.width() for p in self._partitions[0]] if self._partitions.size else []
+        return self._column_widths_cache
+
+    @property
+    def index(self) -> pandas.Index:
+        if self._index_cache is None:
+            self._index_cache, _ = self._partition_mgr_cls.get_indices(0, self._partitions)
+        return self._index_cache
+
+    @property
+    def columns(self) -> pandas.Index:
+        if self._columns_cache is None:
+            self._columns_cache, _ = self._partition_mgr_cls.get_indices(1, self._partitions)
+        return self._columns_cache
+
+    @property
+    def dtypes(self) -> pandas.Series:
+        if self._dtypes is None:
+            series = [p.get().dtypes for p in self._partitions[0]]
+            self._dtypes = pandas.concat(series) if series else pandas.Series(dtype=object)
+        return self._dtypes
+
+    @property
+    def has_materialized_dtypes(self):
+        return self._dtypes is not None
+
+    @property
+    def has_materialized_index(self):
+        return self._index_cache is not None
+
+    @property
+    def has_materialized_columns(self):
+        return self._columns_cache is not None
+
+    def __len__(self):
+        return sum(self.row_lengths)
+
+    @property
+    def global_nrows(self) -> int:
+        """Job-wide row count (sum over ranks of the local shard lengths)."""
+        n = len(self)
+        if dist.is_distributed() and not self._is_replicated():
+            import torch
+
+            t = torch.tensor([n], dtype=torch.int64, device=self._any_device())
+            dist.all_reduce_values([t], ["sum"])
+            n = int(t.item())
+        return n
+
+    def _any_device(self):
+        for p in self._partitions.flatten():
+            b = p.get()
+            if b.cols:
+                return b.cols[0].data.device
+        from .block import current_device
+
+        return current_device()
+
+    def _is_replicated(self) -> bool:
+        return all(p.get().replicated for p in self._partitions.flatten())
+
+    def copy_index_cache(self, copy_lengths=False):
+        return self._index_cache
+
+    def copy_columns_cache(self, copy_lengths=False):
+        return self._columns_cache
+
+    def copy_dtypes_cache(self):
+        return self._dtypes
+
+    def copy(self):
+        return self.__constructor__(self._partitions, self._index_cache, self._columns_cache,
+                                    self._row_lengths_cache, self._column_widths_cache, self._dtypes)  # fmt: skip
+
+    # ---- Map ------------------------------------------------------------------------------------
+    def map(self, func: Callable, dtypes=None, new_columns=None, func_args=None, func_kwargs=None, lazy=False):
+        """df.py:2253-2319."""
+        map_fn = self._partition_mgr_cls.lazy_map_partitions if lazy else self._partition_mgr_cls.map_partitions
+        new_partitions = map_fn(self._partitions, func, func_args, func_kwargs)
+        if new_columns is not None and self.has_materialized_columns:
+            assert len(new_columns) == len(self.columns), \
+                "New column's length must be identical to the previous columns"  # fmt: skip
+        elif new_columns is None:
+            new_columns = self.copy_columns_cache(copy_lengths=True)
+        if isinstance(dtypes, str) and dtypes == "copy":
+            dtypes = self.copy_dtypes_cache()
+        elif dtypes is not None and not isinstance(dtypes, pandas.Series):
+            dtypes = pandas.Series([pandas.api.types.pandas_dtype(dtypes)] * len(self.columns), index=new_columns)
+        return self.__constructor__(new_partitions, self.copy_index_cache(copy_lengths=True), new_columns,
+                                    self._row_lengths_cache, self._column_widths_cache, dtypes=dtypes)  # fmt: skip
+
+    # ---- TreeReduce -------------------------------------------------------------------------------
+    def _build_treereduce_func(self, axis, func):
+        """df.py:2081-2123.  Device reduce functors already return the 1 x W block labelled
+        ``__reduced__`` that the reference builds from the pandas Series, so this is the identity
+        for them; anything else is rejected (no pandas on this path)."""
+        return func
+
+    def _compute_tree_reduce_metadata(self, axis, new_parts, dtypes=None):
+        """df.py:2125-2168."""
+        new_axes, new_axes_lengths = [0, 0], [0, 0]
+        new_axes[axis] = pandas.Index([MODIN_UNNAMED_SERIES_LABEL])
+        new_axes[axis ^ 1] = self.columns if axis == 0 else self.index
+        new_axes_lengths[axis] = [1]
+        new_axes_lengths[axis ^ 1] = self.column_widths if axis == 0 else self.row_lengths
+        if dtypes == "copy":
+            dtypes = self.copy_dtypes_cache()
+        elif dtypes is not None:
+            dtypes = pandas.Series([pandas.api.types.pandas_dtype(dtypes)] * len(new_axes[1]), index=new_axes[1])
+        return self.__constructor__(new_parts, *new_axes, *new_axes_lengths, dtypes)
+
+    def tree_reduce(self, axis, map_func: Callable, reduce_func: Optional[Callable] = None, dtypes=None):
+        """df.py:2208-2250: map every block to a 1 x W partial, then reduce each column partition's
+        partials (plus an all_reduce across GPUs, issued by the reduce functor's collective hook)."""
+        if axis != 0:
+            raise NotImplementedError("tree_reduce along axis=1 is not on the B200 path")
+        map_func = self._build_treereduce_func(axis, map_func)
+        reduce_func = map_func if reduce_func is None else self._build_treereduce_func(axis, reduce_func)
+        map_parts = self._partition_mgr_cls.map_partitions(self._partitions, map_func)
+        reduce_parts = self._partition_mgr_cls.map_axis_partitions(axis, map_parts, reduce_func, num_splits=1)
+        return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
+
+    # ---- Binary -----------------------------------------------------------------------------------
+    def _check_if_axes_identical(self, other: "B200Dataframe", axis: int = 0) -> bool:
+        """df.py:3678-3707."""
+        if axis == 0:
+            return self.index.equals(other.index) and self.row_lengths == other.row_lengths
+        return self.columns.equals(other.columns) and self.column_widths == other.column_widths
+
+    def n_ary_op(self, op, right_frames: list, join_type="outer", copartition_along_columns=True, labels="replace",
+                 dtypes=None, sort=None):  # fmt: skip
+        """df.py:3851-3950, fast path only: operands must already be co-partitioned (identical labels
+        and partition lengths, df.py:3750-3758 -- no data movement).  The general ``_copartition``
+        reindex (df.py:3799-3840) is a "next" row."""
+        for other in right_frames:
+            if not (self._check_if_axes_identical(other, 0) and self._check_if_axes_identical(other, 1)):
+                raise NotImplementedError(
+                    "binary op between differently partitioned / labelled frames needs _copartition, "
+                    "which is not on the B200 path yet"
+                )
+        new_frame = self._partition_mgr_cls.n_ary_operation(
+            self._partitions, op, [other._partitions for other in right_frames]
+        )
+        return self.__constructor__(new_frame, self._index_cache, self._columns_cache, self._row_lengths_cache,
+                                    self._column_widths_cache, dtypes)  # fmt: skip
+
+    def broadcast_apply(self, axis, func, other, join_type="left", copartition=True, labels="keep", dtypes=None):
+        """df.py:3233-3335: every block gets the matching slice of ``other`` along ``axis``."""
+        if not self._check_if_axes_identical(other, axis):
+            raise NotImplementedError("broadcast_apply needs co-partitioned operands on the B200 path")
+        new_frame = self._partition_mgr_cls.broadcast_apply(axis, func, self._partitions, other._partitions)
+        return self.__constructor__(new_frame, self._index_cache, self._columns_cache, self._row_lengths_cache,
+                                    self._column_widths_cache, dtypes)  # fmt: skip
+
+    def broadcast_apply_full_axis(self, axis, func, other, new_index=None, new_columns=None, apply_indices=None,
+                                  enumerate_partitions=False, dtypes=None, keep_partitioning=True, num_splits=None,
+                                  sync_labels=True, pass_axis_lengths_to_partitions=False):  # fmt: skip
+        """df.py:3483-3676: apply ``func(full_axis_block, other_frame_block)`` to every row (axis=1) or
+        column (axis=0) of the grid with ``other`` broadcast whole."""
+        if other is not None:
+            others = other if isinstance(other, list) else [other]
+            other_parts = [o._partitions for o in others]
+        else:
+            other_parts = None
+        new_partitions = self._partition_mgr_cls.broadcast_axis_partitions(
+            axis=axis, left=self._partitions, right=other_parts[0] if other_parts else None, apply_func=func,
+            apply_indices=apply_indices, enumerate_partitions=enumerate_partitions, keep_partitioning=keep_partitioning,
+            num_splits=1 if num_splits is None else num_splits,
+        )  # fmt: skip
+        return self.__constructor__(new_partitions, new_index, new_columns, None, None, dtypes)
+
+    # ---- GroupByReduce ----------------------------------------------------------------------------
+    def groupby_reduce(self, axis, by, map_func, reduce_func, new_index=None, new_columns=None, apply_indices=None):
+        """df.py:4530-4589."""
+        by_parts = by if by is None else by._partitions
+        if by is not None and self.row_lengths != by.row_lengths:
+            raise NotImplementedError("`by` must be co-partitioned with the frame on the B200 path")
+        new_partitions = self._partition_mgr_cls.groupby_reduce(axis, self._partitions, by_parts, map_func, reduce_func,
+                                                                apply_indices)  # fmt: skip
+        return self.__constructor__(new_partitions, new_index, new_columns)
+
+    # ---- structure ---------------------------------------------------------------------------------
+    def combine(self):
+        """pm.combine (pm.py:1328-1373): one partition holding the whole frame (all ranks' rows)."""
+        parts = self._partition_mgr_cls.combine(self._partitions)
+        return self.__constructor__(parts, None, self._columns_cache, None, None, self._dtypes)
+
+    def take_2d_labels_or_positional(self, row_positions=None, col_positions=None):
+        """Column selection by position (subset of df.py:1188-1389): buffers are shared."""
+        if row_positions is not None:
+            raise NotImplementedError("row selection is not on the B200 path")
+        cols = list(col_positions)
+        widths = self.column_widths
+        bounds = np.cumsum([0] + widths)
+        new_rows = []
+        for row in self._partitions:
+            blocks = [p.get() for p in row]
+            picked = []
+            for c in cols:
+                j = int(np.searchsorted(bounds, c, side="right") - 1)
+                picked.append(blocks[j].select_columns([c - bounds[j]]))
+            from .block import concat_cols
+
+            blk = concat_cols(picked) if len(picked) > 1 else picked[0]
+            new_rows.append([self._partition_mgr_cls._partition_class(blk)])
+        new_cols = self.columns[cols]
+        dt = self._dtypes.iloc[cols] if self._dtypes is not None else None
+        return self.__constructor__(np.array(new_rows), self._index_cache, new_cols, self._row_lengths_cache,
+                                    [len(cols)], dt)  # fmt: skip
+
+    # ---- ingest / egress ----------------------------------------------------------------------------
+    @classmethod
+    def from_pandas(cls, df: pandas.DataFrame):
+        """df.py:4592-4620."""
+        new_index = df.index
+        new_columns = df.columns
+        new_dtypes = df.dtypes
+        parts, _, row_lengths, col_widths = cls._partition_mgr_cls.from_pandas(df, return_dims=True)
+        if dist.is_distributed():
+            lo, hi = dist.shard_bounds(len(df))
+            new_index = new_index[lo:hi]
+        return cls(parts, new_index, new_columns, row_lengths, col_widths, dtypes=new_dtypes)
+
+    @classmethod
+    def from_arrow(cls, at):
+        """df.py:4622-4654."""
+        parts, _, row_lengths, col_widths = cls._partition_mgr_cls.from_arrow(at, return_dims=True)
+        return cls(parts, None, pandas.Index(at.column_names), row_lengths, col_widths)
+
+    @classmethod
+    def from_blocks(cls, blocks: List[DeviceBlock]):
+        """Frame from device blocks already resident on this rank (from_map-style ingest,
+        modin/core/io/io.py:184-209): one row partition per block."""
+        pc = cls._partition_mgr_cls._partition_class
+        parts = np.array([[pc.put(b)] for b in blocks], dtype=object)
+        first = blocks[0]
+        index = None
+        if all(b.has_range_index() for b in blocks):
+            index = pandas.RangeIndex(first.range_start, first.range_start + sum(b.nrows for b in blocks))
+        return cls(parts, index, first.columns, [b.nrows for b in blocks], [len(first.cols)], dtypes=first.dtypes)
+
+    def to_pandas(self) -> pandas.DataFrame:
+        """df.py:4691-4722."""
+        df = self._partition_mgr_cls.to_pandas(self._partitions)
+        if len(df.columns) == 0 and self._columns_cache is not None and len(self._columns_cache):
+            df = pandas.DataFrame(columns=self._columns_cache, index=df.index)
+        return df
+
+    def to_numpy(self, **kwargs):
+        return self._partition_mgr_cls.to_numpy(self._partitions, **kwargs)
+
+    def finalize(self):
+        self._partition_mgr_cls.finalize(self._partitions)
+
+    def wait_computations(self):
+        self._partition_mgr_cls.wait_partitions(self._partitions.flatten())

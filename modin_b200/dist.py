@@ -1,0 +1,204 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) collectives.
+
+The reference never issues a collective; its data-movement primitives are "gather all blocks
+of an axis into one task" (axis_partition.apply, axpart.py:445-452), "hand one future to many
+tasks" (pm.base_broadcast_apply, pm.py:443-494) and the range-partition shuffle
+(pm.shuffle_partitions, pm.py:1937-2052).  Their B200 equivalents:
+
+* TreeReduce combine   -> ``all_reduce`` of the W-vector partial (sum / min / max);
+* GroupByReduce reduce -> range-partitioned all-to-all of the PRE-AGGREGATED partial tables
+  (<= G rows per GPU, never raw rows), pivots picked TeraSort-style from samples of the
+  per-rank sorted keys (cf. ShuffleSortFunctions, dfutils.py:163-332);
+* broadcast merge      -> ``all_gather`` of the dim shard columns.
+
+Rows are sharded across ranks (rank r owns a contiguous row range); Map / Binary never
+communicate.  Everything here works on plain torch tensors so the same code runs under
+``gloo`` on CPU tensors (tests, world_size 2) and ``nccl`` on device tensors.
+"""
+
+from __future__ import annotations
+
+import os
+from typing import List, Sequence
+
+_T = None
+
+
+def _torch():
+    global _T
+    if _T is None:
+        import torch
+
+        _T = torch
+    return _T
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def is_distributed() -> bool:
+    d = _dist()
+    return d.is_available() and d.is_initialized() and d.get_world_size() > 1
+
+
+def world_size() -> int:
+    d = _dist()
+    return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+
+def rank() -> int:
+    d = _dist()
+    return d.get_rank() if d.is_available() and d.is_initialized() else 0
+
+
+def init_from_env(backend: str | None = None) -> bool:
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / MASTER_*).
+    Returns True when running with world_size > 1."""
+    t = _torch()
+    d = _dist()
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws <= 1:
+        return False
+    if not d.is_initialized():
+        if backend is None:
+            backend = "nccl" if t.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+            t.cuda.set_device(local)
+            d.init_process_group(backend, device_id=t.device("cuda", local))
+        else:
+            d.init_process_group(backend)
+    return True
+
+
+def barrier():
+    if is_distributed():
+        _dist().barrier()
+
+
+def shard_bounds(nrows: int, r: int | None = None, ws: int | None = None):
+    """Contiguous row range [lo, hi) owned by rank r: even split, remainder to the low ranks."""
+    ws = world_size() if ws is None else ws
+    r = rank() if r is None else r
+    base, rem = divmod(int(nrows), ws)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+_REDUCE_OPS = {"sum": "SUM", "min": "MIN", "max": "MAX"}
+
+
+def all_reduce_values(tensors: Sequence, ops: Sequence[str]) -> None:
+    """In-place all_reduce of many 1-element tensors: one collective per (dtype, op) bucket.
+
+    TreeReduce combine: W x 8 B per bucket -- latency-bound, so the W scalars are packed."""
+    if not is_distributed() or not tensors:
+        return
+    t = _torch()
+    d = _dist()
+    buckets = {}
+    for i, (x, op) in enumerate(zip(tensors, ops)):
+        buckets.setdefault((x.dtype, op), []).append(i)
+    for (dtype, op), idxs in buckets.items():
+        packed = t.cat([tensors[i].reshape(-1) for i in idxs])
+        d.all_reduce(packed, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
+        off = 0
+        for i in idxs:
+            n = tensors[i].numel()
+            tensors[i].copy_(packed[off : off + n].reshape(tensors[i].shape))
+            off += n
+
+
+def all_gather_rows(cols: Sequence) -> List:
+    """all_gather of row shards (different lengths per rank) -> concatenated columns."""
+    if not is_distributed():
+        return list(cols)
+    t = _torch()
+    d = _dist()
+    ws = world_size()
+    n_local = int(cols[0].shape[0]) if cols else 0
+    dev = cols[0].device if cols else "cpu"
+    counts = t.zeros(ws, dtype=t.int64, device=dev)
+    counts[rank()] = n_local
+    d.all_reduce(counts)
+    counts = [int(c) for c in counts.tolist()]
+    out = []
+    for c in cols:
+        pieces = [t.empty(k, dtype=c.dtype, device=c.device) for k in counts]
+        m = max(counts)
+        # all_gather needs equal shapes: pad to the longest shard
+        padded = t.zeros(m, dtype=c.dtype, device=c.device)
+        padded[:n_local] = c
+        gathered = [t.empty(m, dtype=c.dtype, device=c.device) for _ in range(ws)]
+        d.all_gather(gathered, padded)
+        pieces = [g[:k] for g, k in zip(gathered, counts)]
+        out.append(t.cat(pieces))
+    return out
+
+
+def choose_pivots(sorted_keys, nsamples: int = 256):
+    """ws-1 range pivots, identical on every rank, from evenly spaced samples of each rank's
+    ascending unique keys (TeraSort-style; reference: pick_pivots_from_samples_for_sort,
+    dfutils.py:288-332).  Keys k go to destination  #(pivots <= k)."""
+    t = _torch()
+    d = _dist()
+    ws = world_size()
+    g = int(sorted_keys.shape[0])
+    dev = sorted_keys.device
+    samp = t.full((nsamples,), t.iinfo(t.int64).max, dtype=t.int64, device=dev)
+    k = min(nsamples, g)
+    if k > 0:
+        pos = (t.arange(k, device=dev, dtype=t.float64) + 0.5) * (g / k)
+        samp[:k] = sorted_keys[pos.to(t.int64).clamp_(max=g - 1)]
+    cnt = t.tensor([k], dtype=t.int64, device=dev)
+    all_s = [t.empty_like(samp) for _ in range(ws)]
+    all_c = [t.empty_like(cnt) for _ in range(ws)]
+    d.all_gather(all_s, samp)
+    d.all_gather(all_c, cnt)
+    pool = t.cat([s[: int(c.item())] for s, c in zip(all_s, all_c)])
+    if pool.numel() == 0:
+        return t.zeros(ws - 1, dtype=t.int64, device=dev)
+    pool, _ = t.sort(pool)
+    q = (t.arange(1, ws, device=dev, dtype=t.float64) * (pool.numel() / ws)).to(t.int64).clamp_(max=pool.numel() - 1)
+    return pool[q]
+
+
+def exchange_by_key_range(sorted_keys, columns: Sequence):
+    """Range-partitioned all-to-all of a key-sorted partial table.
+
+    ``sorted_keys``: int64 [g] ascending; ``columns``: tensors [g] (8-byte dtypes).  Every rank
+    receives, for its key range, the segments of all ranks (each ascending), concatenated in
+    rank order.  Returns (keys, columns).  Message size <= g * 8 * (1 + len(columns)) bytes."""
+    if not is_distributed():
+        return sorted_keys, list(columns)
+    t = _torch()
+    d = _dist()
+    ws = world_size()
+    dev = sorted_keys.device
+    pivots = choose_pivots(sorted_keys)
+    # destination of key k = number of pivots <= k  -> split points via searchsorted(right=False on pivots)
+    cuts = t.searchsorted(sorted_keys, pivots, right=False)  # first index with key >= pivot
+    bounds = t.cat([t.zeros(1, dtype=t.int64, device=dev), cuts.to(t.int64),
+                    t.tensor([sorted_keys.shape[0]], dtype=t.int64, device=dev)])  # fmt: skip
+    send_counts = (bounds[1:] - bounds[:-1]).to(t.int64)
+    recv_counts = t.empty_like(send_counts)
+    d.all_to_all_single(recv_counts, send_counts)
+    sc = [int(x) for x in send_counts.tolist()]
+    rc = [int(x) for x in recv_counts.tolist()]
+    ncols = 1 + len(columns)
+    # pack keys + columns as int64 bit patterns: one collective for the whole table
+    packed = t.empty((int(sorted_keys.shape[0]), ncols), dtype=t.int64, device=dev)
+    packed[:, 0] = sorted_keys
+    for j, c in enumerate(columns):
+        packed[:, j + 1] = c.view(t.int64) if c.dtype != t.int64 else c
+    recv = t.empty((sum(rc), ncols), dtype=t.int64, device=dev)
+    d.all_to_all_single(recv, packed, output_split_sizes=rc, input_split_sizes=sc)
+    keys = recv[:, 0].contiguous()
+    outs = []
+    for j, c in enumerate(columns):
+        col = recv[:, j + 1].contiguous()
+        outs.append(col.view(c.dtype) if c.dtype != t.int64 else col)
+    return keys, outs

@@ -1,0 +1,479 @@
+"""Tagged device functors: what the operator templates hand to the partitions.
+
+The reference's templates wrap *pandas methods* in closures (``lambda x: function(x, *args,
+**kwargs)``, alg/map.py:64-66, alg/tree_reduce.py:76-77, alg/binary.py:399-401, 422) and the
+partition calls them on a ``pandas.DataFrame``.  The B200 query compiler registers these
+functors through the same templates instead: each is a callable with the
+pandas method's calling convention that takes ``DeviceBlock`` operands and launches
+libmodin_b200 kernels.  They carry an ``op`` tag so that the partition call-queue can fuse
+adjacent ones (``x*b`` then ``+c`` -> one AFFINE sweep; ``a*b`` then ``+c`` -> one FMA3 sweep).
+
+Anything a functor cannot do on the device raises ``NotImplementedError`` -- there is no
+silent pandas fallback on this path.
+"""
+
+from __future__ import annotations
+
+import numbers
+from typing import Optional
+
+import numpy as np
+import pandas
+
+from . import _lib, ops
+from .block import DeviceBlock, DeviceColumn, concat_rows
+from .config import ReduceVariant
+
+MODIN_UNNAMED_SERIES_LABEL = "__reduced__"  # modin/utils.py:98
+
+_BINARY_TO_SCALAR = {
+    "add": "add_s", "radd": "add_s", "sub": "sub_s", "rsub": "rsub_s", "mul": "mul_s", "rmul": "mul_s",
+    "truediv": "div_s", "rtruediv": "rdiv_s", "eq": "eq_s", "ne": "ne_s", "lt": "lt_s", "le": "le_s",
+    "gt": "gt_s", "ge": "ge_s",
+}  # fmt: skip
+_BINARY_TO_FRAME = {
+    "add": "add", "radd": "add", "sub": "sub", "mul": "mul", "rmul": "mul", "truediv": "div",
+    "eq": "eq", "ne": "ne", "lt": "lt", "le": "le", "gt": "gt", "ge": "ge",
+}  # fmt: skip
+_REFLECTED_FRAME = {"rsub": "sub", "rtruediv": "div"}
+
+
+class DevFn:
+    """Base of all device functors."""
+
+    op: str = ""
+    fusable: bool = False
+
+    def __call__(self, block, *args, **kwargs):  # pragma: no cover - interface
+        raise NotImplementedError
+
+
+def _is_scalar(x) -> bool:
+    return isinstance(x, (numbers.Number, np.number, np.bool_)) and not isinstance(x, bool) or isinstance(x, bool)
+
+
+def _check_block(x, who):
+    if not isinstance(x, DeviceBlock):
+        raise TypeError(f"{who} expects a DeviceBlock partition payload, got {type(x).__name__}")
+
+
+class DevMap(DevFn):
+    """Unary elementwise map: abs / neg / isna / notna (qc.py:2036, 2063-2106)."""
+
+    def __init__(self, op: str):
+        if op not in ("abs", "neg", "isna", "notna", "copy"):
+            raise ValueError(op)
+        self.op = op
+
+    def __call__(self, block, *args, **kwargs):
+        _check_block(block, f"DevMap({self.op})")
+        if not block.cols or block.nrows == 0:
+            return self._empty(block)
+        if self.op in ("isna", "notna"):
+            # int64 columns hold no nulls: constant answer, computed by the compare kernel (x == x)
+            cols = []
+            for c in block.cols:
+                if c.dtype == np.float64:
+                    cols.extend(ops.map_columns(self.op, [c]))
+                else:
+                    cols.extend(ops.map_columns("ne" if self.op == "isna" else "eq", [c], [c]))
+            return block.with_cols(cols)
+        return block.with_cols(ops.map_columns(self.op, block.cols))
+
+    def _empty(self, block):
+        if self.op in ("isna", "notna"):
+            return block.with_cols([DeviceColumn.empty(block.nrows, np.bool_) for _ in block.cols])
+        return block
+
+
+class DevFillna(DevFn):
+    """``df.fillna(value=scalar|dict)`` -- the Map branch of qc.fillna (qc.py:2710-2813)."""
+
+    op = "fillna"
+
+    def __call__(self, block, *args, value=None, method=None, axis=None, inplace=False, limit=None, **kwargs):
+        _check_block(block, "DevFillna")
+        if args:
+            value = args[0]
+        if method is not None or limit is not None:
+            raise NotImplementedError("fillna(method=/limit=) is a Fold in the reference; not on the B200 path")
+        if value is None:
+            raise ValueError("Must specify a fill 'value' or 'method'.")
+        if isinstance(value, dict) or isinstance(value, pandas.Series):
+            lookup = dict(value)
+        elif _is_scalar(value):
+            lookup = None
+        else:
+            raise NotImplementedError("fillna with a frame value goes through broadcast_apply; use DevBinary('fillna')")
+        out = []
+        for label, c in zip(block.columns, block.cols):
+            v = value if lookup is None else lookup.get(label)
+            if v is None or c.dtype != np.float64 or block.nrows == 0:
+                out.append(c)  # nothing to fill: share the buffer
+            else:
+                out.extend(ops.map_columns("fillna_s", [c], s0=[float(v)]))
+        return block.with_cols(out)
+
+
+class DevBinary(DevFn):
+    """Binary operator against a scalar, a row vector (list / Series along axis=1) or another
+    block -- the three shapes Binary.caller produces (alg/binary.py:334-458)."""
+
+    fusable = True
+
+    def __init__(self, op: str):
+        if op not in _BINARY_TO_SCALAR and op not in _REFLECTED_FRAME and op != "fillna":
+            raise ValueError(f"binary op {op!r} is not implemented on the B200 path")
+        self.op = op
+
+    # -- helpers -------------------------------------------------------------------------------
+    @staticmethod
+    def _promote(cols, scalar_is_float):
+        """pandas type promotion for arithmetic: int64 (op) float -> float64."""
+        if scalar_is_float and any(c.dtype == np.int64 for c in cols):
+            return ops.cast_columns_f64(cols)
+        return list(cols)
+
+    def _scalar(self, block, scalars):
+        """`scalars`: one python scalar per column."""
+        kop = _BINARY_TO_SCALAR[self.op]
+        is_pred = kop in _lib.PREDICATES
+        any_float = any(isinstance(s, (float, np.floating)) for s in scalars)
+        cols = self._promote(block.cols, any_float and not is_pred) if not is_pred else list(block.cols)
+        out = [None] * len(cols)
+        # group by dtype handled inside map_columns; scalars must match the column dtype
+        svals = []
+        for c, s in zip(cols, scalars):
+            if c.dtype == np.int64 and isinstance(s, (float, np.floating)):
+                # predicate of int column vs float scalar: compare in float64
+                raise NotImplementedError("comparison of int64 columns with a float scalar is not on the B200 path")
+            svals.append(float(s) if c.dtype == np.float64 else int(s))
+        out = ops.map_columns(kop, cols, s0=svals)
+        return block.with_cols(out)
+
+    def _frame(self, left, right):
+        if self.op == "fillna":
+            kop, a, b = "fillna", left.cols, right.cols
+        elif self.op in _REFLECTED_FRAME:
+            kop, a, b = _REFLECTED_FRAME[self.op], right.cols, left.cols
+        else:
+            kop, a, b = _BINARY_TO_FRAME[self.op], left.cols, right.cols
+        if len(a) != len(b) or left.nrows != right.nrows:
+            raise ValueError("device binary op needs identically shaped, co-partitioned operands")
+        if not left.columns.equals(right.columns):
+            raise NotImplementedError("binary op between blocks with different column labels (needs copartition)")
+        if kop not in _lib.PREDICATES and kop != "div":
+            mixed = any(x.dtype != y.dtype for x, y in zip(a, b))
+            if mixed:
+                a, b = ops.cast_columns_f64(a), ops.cast_columns_f64(b)
+        return left.with_cols(ops.map_columns(kop, a, b))
+
+    def __call__(self, block, other, *args, axis=None, level=None, fill_value=None, **kwargs):
+        _check_block(block, f"DevBinary({self.op})")
+        if level is not None or fill_value is not None:
+            raise NotImplementedError("level= / fill_value= are not implemented on the B200 path")
+        if block.nrows == 0 or not block.cols:
+            return block
+        if isinstance(other, DeviceBlock):
+            return self._frame(block, other)
+        if _is_scalar(other):
+            return self._scalar(block, [other] * len(block.cols))
+        if isinstance(other, pandas.Series):
+            if axis in (0, "index"):
+                raise NotImplementedError("column-vector broadcast (axis=0) is not on the B200 path")
+            other = other.reindex(block.columns)
+            if other.isna().any():
+                raise NotImplementedError("row vector does not cover every column label")
+            other = other.to_list()
+        if isinstance(other, (list, tuple, np.ndarray)):
+            if len(other) != len(block.cols):
+                raise ValueError(f"Unable to coerce to Series, length must be {len(block.cols)}: given {len(other)}")
+            return self._scalar(block, list(other))
+        raise NotImplementedError(f"binary op with {type(other).__name__} operand is not on the B200 path")
+
+
+class DevAffine(DevFn):
+    """Fused ``x * s + t`` (two roundings) produced by the call-queue fusion pass."""
+
+    op = "affine"
+
+    def __init__(self, mul, add):
+        self.mul, self.add = mul, add  # per-column lists or scalars
+
+    def __call__(self, block, *args, **kwargs):
+        _check_block(block, "DevAffine")
+        W = len(block.cols)
+        mul = list(self.mul) if isinstance(self.mul, (list, tuple, np.ndarray)) else [self.mul] * W
+        add = list(self.add) if isinstance(self.add, (list, tuple, np.ndarray)) else [self.add] * W
+        if any(c.dtype != np.float64 for c in block.cols):
+            raise NotImplementedError("fused affine map needs float64 columns")
+        return block.with_cols(ops.map_columns("affine", block.cols, s0=[float(m) for m in mul],
+                                               s1=[float(a) for a in add]))  # fmt: skip
+
+
+class DevFma3(DevFn):
+    """Fused ``a * b + c`` over three co-partitioned blocks (two roundings)."""
+
+    op = "fma3"
+
+    def __call__(self, a, b, c, *args, **kwargs):
+        for x in (a, b, c):
+            _check_block(x, "DevFma3")
+        if not (a.nrows == b.nrows == c.nrows and len(a.cols) == len(b.cols) == len(c.cols)):
+            raise ValueError("fma3 needs identically shaped operands")
+        if any(x.dtype != np.float64 for blk in (a, b, c) for x in blk.cols):
+            raise NotImplementedError("fused a*b+c needs float64 columns")
+        return a.with_cols(ops.map_columns("fma3", a.cols, b.cols, c.cols))
+
+
+# ------------------------------------------------------------------ TreeReduce functors
+def _reduced_block(cols, columns, label=MODIN_UNNAMED_SERIES_LABEL):
+    return DeviceBlock(cols, columns, nrows=1, index_host=pandas.Index([label]))
+
+
+class DevReduce(DevFn):
+    """``pandas.DataFrame.sum/count/min/max(axis=0)`` of one block -> 1 x W block.
+
+    Used both as map and as reduce function of TreeReduce (qc.py:976-1035): the reduce phase
+    sees the row-concatenation of the per-partition 1 x W partials.
+    """
+
+    def __init__(self, op: str, phase: str = "map"):
+        if op not in ("sum", "count", "min", "max"):
+            raise ValueError(op)
+        self.op = op
+        self.phase = phase  # "map" | "reduce"
+
+    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+        _check_block(block, f"DevReduce({self.op})")
+        if axis not in (0, "index", None):
+            raise NotImplementedError("row-wise (axis=1) reductions are not on the B200 path")
+        if min_count and min_count > 1:
+            raise NotImplementedError("sum(min_count>1) is a full-axis Reduce in the reference; not on the B200 path")
+        W = len(block.cols)
+        if W == 0:
+            return _reduced_block([], block.columns)
+        kop = self.op
+        if self.phase == "reduce" and self.op == "count":
+            kop = "sum"  # counts add up (qc.py:976: TreeReduce.register(count, sum))
+        variant = ReduceVariant.get()
+        vals, cnts = ops.reduce_columns(kop if kop != "count" else "count", block.cols, skipna=bool(skipna),
+                                        variant=variant)  # fmt: skip
+        out = []
+        for j, c in enumerate(block.cols):
+            if kop == "count":
+                out.append(DeviceColumn(cnts[j], np.int64))
+            elif kop == "sum" and min_count == 1 and c.dtype == np.float64 and skipna:
+                # all-NaN column -> NaN: 0/0 * 0 trick avoided; patch on host-free path via where(count==0)
+                out.append(_nan_where_empty(vals[j], cnts[j]))
+            else:
+                out.append(DeviceColumn(vals[j], c.dtype))
+        return _reduced_block(out, block.columns)
+
+
+def _nan_where_empty(val, cnt):
+    """val if cnt > 0 else NaN, on device, for a 1-element tensor (min_count=1 semantics)."""
+    v = DeviceColumn(val, np.float64)
+    c = DeviceColumn(cnt, np.int64)
+    cf = ops.cast_columns_f64([c])[0]
+    # cf/cf is 1.0 when count > 0 and NaN when count == 0 ; multiply keeps val or makes NaN
+    one_or_nan = ops.map_columns("div", [cf], [cf])[0]
+    return ops.map_columns("mul", [v], [one_or_nan])[0]
+
+
+class DevMeanMap(DevFn):
+    """Map phase of mean: per-column (sum, count) -- qc.py:1046-1058 builds a 2-row frame with
+    rows "sum"/"count"; here the partial is 1 x 2W: W float sums followed by W int64 counts."""
+
+    op = "mean_map"
+
+    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, **kwargs):
+        _check_block(block, "DevMeanMap")
+        if axis not in (0, "index", None):
+            raise NotImplementedError("row-wise mean is not on the B200 path")
+        cols = ops.cast_columns_f64(block.cols)
+        vals, cnts = ops.reduce_columns("sum", cols, skipna=bool(skipna), variant=ReduceVariant.get())
+        out = [DeviceColumn(v, np.float64) for v in vals]
+        if skipna:
+            out += [DeviceColumn(c, np.int64) for c in cnts]
+        else:  # count of rows, NaNs included (qc.py:1049-1053 uses len when skipna=False)
+            import torch
+
+            n = block.nrows
+            out += [DeviceColumn(torch.full((1,), n, dtype=torch.int64, device=vals[0].device), np.int64)
+                    for _ in cnts]  # fmt: skip
+        labels = pandas.MultiIndex.from_tuples([("sum", c) for c in block.columns] + [("count", c) for c in block.columns])
+        return _reduced_block(out, labels)
+
+
+class DevMeanReduce(DevFn):
+    """Reduce phase of mean: add the partial sums and counts, divide (qc.py:1060-1075)."""
+
+    op = "mean_reduce"
+
+    def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
+        _check_block(block, "DevMeanReduce")
+        W = len(block.cols) // 2
+        sums, _ = ops.reduce_columns("sum", block.cols[:W], skipna=False, variant=1)
+        cnts, _ = ops.reduce_columns("sum", block.cols[W:], skipna=False, variant=1)
+        s = [DeviceColumn(v, np.float64) for v in sums]
+        c = ops.cast_columns_f64([DeviceColumn(v, np.int64) for v in cnts])
+        labels = pandas.Index([t[1] for t in block.columns]) if isinstance(block.columns, pandas.MultiIndex) else \
+            block.columns[:W]  # fmt: skip
+        return _reduced_block(ops.map_columns("div", s, c), labels)
+
+
+# ------------------------------------------------------------------ GroupByReduce functors
+_GB_FLAGS = {
+    "sum": _lib.GB_SUM,
+    "count": _lib.GB_COUNT,
+    "size": _lib.GB_SIZE,
+    "mean": _lib.GB_SUM | _lib.GB_COUNT,
+}
+
+
+def _split_key_values(block: DeviceBlock, by_block: Optional[DeviceBlock]):
+    """Key column + value columns of one row block (alg/groupby.py:186-206: with drop=True the
+    `by` column is taken out of the data, or concatenated in when it lives in another frame)."""
+    if by_block is None:
+        raise NotImplementedError("groupby needs a `by` block on the B200 path")
+    if len(by_block.cols) != 1:
+        raise NotImplementedError("multi-column `by` is not on the B200 path yet")
+    key = by_block.cols[0]
+    key_label = by_block.columns[0]
+    keep = [i for i, lab in enumerate(block.columns) if lab != key_label]
+    vals = [block.cols[i] for i in keep]
+    labels = block.columns[keep]
+    if key.dtype != np.int64:
+        raise NotImplementedError("device groupby needs an int64 key column")
+    return key, key_label, vals, labels
+
+
+class DevGroupbyMap(DevFn):
+    """GroupByReduce.map (alg/groupby.py:124-208): hash-aggregate one row block against its
+    slice of `by` into a partial table (index = keys, ascending)."""
+
+    def __init__(self, agg: str, capacity_hint: int = 1 << 20):
+        if agg not in _GB_FLAGS:
+            raise NotImplementedError(f"groupby.{agg} is not on the B200 path")
+        self.agg = agg
+        self.op = f"groupby_{agg}_map"
+        self.capacity_hint = capacity_hint
+
+    def __call__(self, block, by_block=None, *args, **kwargs):
+        _check_block(block, self.op)
+        key, key_label, vals, labels = _split_key_values(block, by_block)
+        flags = _GB_FLAGS[self.agg]
+        if self.agg == "size":
+            vals, labels = [], labels[:0]
+        else:
+            vals = ops.cast_columns_f64(vals) if self.agg in ("count", "mean") else vals
+            if any(v.dtype != np.float64 for v in vals):
+                raise NotImplementedError("device groupby.sum aggregates float64 value columns only")
+        keys, sums, cnts, sizes = ops.hash_aggregate([(key, vals)], flags, self.capacity_hint)
+        return _partial_block(self.agg, keys, key_label, sums, cnts, sizes, labels)
+
+
+def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels):
+    if agg == "sum":
+        cols, cl = sums, labels
+    elif agg == "count":
+        cols, cl = cnts, labels
+    elif agg == "size":
+        cols, cl = [sizes], pandas.Index(["size"])
+    else:  # mean: sums then counts
+        cols = list(sums) + list(cnts)
+        cl = pandas.MultiIndex.from_tuples([("sum", c) for c in labels] + [("count", c) for c in labels])
+    return DeviceBlock(cols, cl, nrows=len(keys), index_cols=[keys], index_names=[key_label])
+
+
+class DevGroupbyReduce(DevFn):
+    """GroupByReduce.reduce (alg/groupby.py:211-300): regroup the concatenated partial tables by
+    key (level 0) with the reduce aggregation (sum of sums / counts / sizes; mean = sum/count)."""
+
+    def __init__(self, agg: str):
+        self.agg = agg
+        self.op = f"groupby_{agg}_reduce"
+
+    def __call__(self, block, *args, partition_idx=0, **kwargs):
+        _check_block(block, self.op)
+        if not block.index_cols:
+            raise ValueError("groupby reduce expects partial tables keyed by device index columns")
+        keys = block.index_cols[0]
+        key_label = block.index_names[0] if block.index_names else None
+        agg = self.agg
+        if agg == "sum":
+            k, s, _, _ = ops.hash_aggregate([(keys, block.cols, None, None)], _lib.GB_SUM, len(keys), partial=True)
+            return DeviceBlock(s, block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
+        if agg == "count":
+            # counts are int64 partials: merged through the count accumulators
+            zeros = [ops.cast_columns_f64([c])[0] for c in block.cols]
+            k, _, c, _ = ops.hash_aggregate([(keys, zeros, block.cols, None)], _lib.GB_COUNT, len(keys), partial=True)
+            return DeviceBlock(c, block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
+        if agg == "size":
+            k, _, _, z = ops.hash_aggregate([(keys, [], None, block.cols[0])], _lib.GB_SIZE, len(keys), partial=True)
+            return DeviceBlock([z], block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
+        # mean
+        W = len(block.cols) // 2
+        k, s, c, _ = ops.hash_aggregate([(keys, block.cols[:W], block.cols[W:], None)], _lib.GB_SUM | _lib.GB_COUNT,
+                                        len(keys), partial=True)  # fmt: skip
+        cf = ops.cast_columns_f64(c)
+        labels = pandas.Index([t[1] for t in block.columns[:W]])
+        return DeviceBlock(ops.map_columns("div", s, cf), labels, nrows=len(k), index_cols=[k],
+                           index_names=[key_label])  # fmt: skip
+
+
+# ------------------------------------------------------------------ broadcast merge functor
+class DevMerge(DevFn):
+    """Per-row-partition ``pandas.merge(left_block, right, how, on, sort=False)`` of
+    MergeImpl.row_axis_merge (merge.py:139-168) as a hash-join probe + payload gather."""
+
+    op = "merge"
+
+    def __init__(self, on, how="left", suffixes=("_x", "_y")):
+        if how not in ("left", "inner"):
+            raise NotImplementedError("device merge supports how='left' and how='inner'")
+        self.on, self.how, self.suffixes = on, how, suffixes
+        self._cache = {}
+
+    def _table(self, right: DeviceBlock):
+        key = id(right)
+        ent = self._cache.get(key)
+        if ent is None or ent[0] is not right:
+            table = ops.JoinTable(right.column(self.on))
+            if not table.is_unique():
+                table.close()
+                raise NotImplementedError("device merge needs distinct keys on the right (many-to-one join)")
+            ent = (right, table)
+            self._cache.clear()
+            self._cache[key] = ent
+        return ent[1]
+
+    def __call__(self, left, right, *args, **kwargs):
+        _check_block(left, "DevMerge")
+        _check_block(right, "DevMerge")
+        table = self._table(right)
+        fact_keys = left.column(self.on)
+        pay_pos = [i for i, lab in enumerate(right.columns) if lab != self.on]
+        pay_cols = [right.cols[i] for i in pay_pos]
+        pay_labels = [right.columns[i] for i in pay_pos]
+        left_labels = list(left.columns)
+        # suffixes for overlapping non-key labels (pandas.merge semantics)
+        overlap = set(left_labels) & set(pay_labels)
+        ll = [f"{x}{self.suffixes[0]}" if x in overlap else x for x in left_labels]
+        rl = [f"{x}{self.suffixes[1]}" if x in overlap else x for x in pay_labels]
+        if self.how == "left":
+            gathered, nmatch = table.probe_gather(fact_keys, pay_cols)
+            if any(c.dtype == np.int64 for c in pay_cols):
+                if int(nmatch.item()) != left.nrows:  # misses: pandas promotes int payload to float64 NaN
+                    idx, _ = table.probe(fact_keys)
+                    pay_f = ops.cast_columns_f64(pay_cols)
+                    gathered = ops.take_columns(pay_f, idx)
+            cols = list(left.cols) + gathered  # fact columns shared by reference
+            return DeviceBlock(cols, pandas.Index(ll + rl), nrows=left.nrows, range_start=left.range_start)
+        idx, _ = table.probe(fact_keys)
+        pos, k = ops.compact_hits(idx)
+        lcols = ops.take_columns(left.cols, pos)
+        hit_idx = ops.take_columns([idx], pos)[0]
+        rcols = ops.take_columns(pay_cols, hit_idx)
+        return DeviceBlock(lcols + rcols, pandas.Index(ll + rl), nrows=k, range_start=0)

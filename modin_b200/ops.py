@@ -1,0 +1,345 @@
+"""Block-level operations: DeviceBlock in, DeviceBlock out, every one a libmodin_b200 call.
+
+These are the bodies that replace the per-block pandas calls of the reference
+(``func(self._data.copy())`` in pandas_on_python/partitioning/partition.py:76-123).
+No function here touches a host copy of the data, and none has a CPU branch.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import pandas
+
+from . import _lib
+from .block import DeviceBlock, DeviceColumn, current_stream, torch_mod, current_device
+
+_scratch_cache = {}
+
+
+def _scratch(nbytes: int, tag: str = "default"):
+    """Per-device reusable scratch buffer (grown geometrically)."""
+    t = torch_mod()
+    key = (t.cuda.current_device(), tag)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = t.empty(max(int(nbytes), 1 << 20), dtype=t.uint8, device=current_device())
+        _scratch_cache[key] = buf
+    return buf
+
+
+def f64_bits(x: float) -> int:
+    return int(np.float64(x).view(np.uint64))
+
+
+def i64_bits(x: int) -> int:
+    return int(np.int64(x).view(np.uint64))
+
+
+def _scalar_bits(vals, code):
+    if vals is None:
+        return None
+    conv = f64_bits if code == _lib.F64 else i64_bits
+    return _lib.u64_array([conv(v) for v in vals])
+
+
+# ------------------------------------------------------------------ Map / Binary
+def map_columns(
+    op: str,
+    in0: Sequence[DeviceColumn],
+    in1: Optional[Sequence[DeviceColumn]] = None,
+    in2: Optional[Sequence[DeviceColumn]] = None,
+    s0: Optional[Sequence] = None,
+    s1: Optional[Sequence] = None,
+) -> List[DeviceColumn]:
+    """Elementwise op over W columns of equal dtype with ONE kernel launch per dtype group."""
+    lib = _lib.load()
+    n = len(in0[0]) if in0 else 0
+    out: List[Optional[DeviceColumn]] = [None] * len(in0)
+    groups = {}
+    for j, c in enumerate(in0):
+        groups.setdefault(c.code, []).append(j)
+    for code, idxs in groups.items():
+        if code == _lib.U8:
+            raise TypeError(f"elementwise {op!r} on bool columns is not on the B200 path")
+        if op in _lib.PREDICATES:
+            odt = np.dtype("bool")
+        elif op in ("div", "div_s", "rdiv_s"):
+            odt = np.dtype("float64")
+        else:
+            odt = in0[idxs[0]].dtype
+        for k in range(0, len(idxs), 32):
+            sel = idxs[k : k + 32]
+            outs = [DeviceColumn.empty(n, odt) for _ in sel]
+            a = _lib.ptr_array([in0[j].ptr for j in sel])
+            b = _lib.ptr_array([in1[j].ptr for j in sel]) if in1 is not None else None
+            c = _lib.ptr_array([in2[j].ptr for j in sel]) if in2 is not None else None
+            if in1 is not None and any(in1[j].code != code for j in sel):
+                raise TypeError("mixed dtypes between operands of a device binary op")
+            if in2 is not None and any(in2[j].code != code for j in sel):
+                raise TypeError("mixed dtypes between operands of a device ternary op")
+            o = _lib.ptr_array([x.ptr for x in outs])
+            s0a = _scalar_bits([s0[j] for j in sel], code) if s0 is not None else None
+            s1a = _scalar_bits([s1[j] for j in sel], code) if s1 is not None else None
+            _lib.check(lib.mb200_map(_lib.OP[op], code, len(sel), a, b, c, o, n, s0a, s1a, current_stream()))
+            for j, x in zip(sel, outs):
+                out[j] = x
+    return out  # type: ignore[return-value]
+
+
+def cast_columns_f64(cols: Sequence[DeviceColumn]) -> List[DeviceColumn]:
+    """int64 -> float64 promotion (x / 1.0 through the division kernel)."""
+    res = []
+    for c in cols:
+        if c.dtype == np.float64:
+            res.append(c)
+        elif c.dtype == np.int64:
+            res.extend(map_columns("div_s", [c], s0=[1]))
+        else:
+            raise TypeError(f"cannot promote {c.dtype} to float64 on device")
+    return res
+
+
+# ------------------------------------------------------------------ TreeReduce
+def reduce_columns(op: str, cols: Sequence[DeviceColumn], skipna: bool = True, variant: int = 0):
+    """Column-wise reduction.  Returns (values DeviceColumn-per-dtype-group arrays, counts).
+
+    Output: list of (value_tensor_1elem_view, count_tensor_1elem_view) is avoided; instead two
+    device tensors of length W are returned per dtype group, mapped back to column order:
+    ``vals[j]`` is a 0-d device view (float64 or int64), ``cnts[j]`` a 0-d int64 view.
+    """
+    lib = _lib.load()
+    t = torch_mod()
+    n = len(cols[0]) if cols else 0
+    vals: list = [None] * len(cols)
+    cnts: list = [None] * len(cols)
+    groups = {}
+    for j, c in enumerate(cols):
+        groups.setdefault(c.code, []).append(j)
+    for code, idxs in groups.items():
+        if code == _lib.U8:
+            raise TypeError("reductions over bool columns are not on the B200 path")
+        for k in range(0, len(idxs), 32):
+            sel = idxs[k : k + 32]
+            odt = t.float64 if code == _lib.F64 else t.int64
+            oval = t.empty(len(sel), dtype=odt, device=current_device())
+            ocnt = t.empty(len(sel), dtype=t.int64, device=current_device())
+            scratch = _scratch(lib.mb200_reduce_scratch_bytes(len(sel)), "reduce")
+            ptrs = _lib.ptr_array([cols[j].ptr for j in sel])
+            _lib.check(
+                lib.mb200_reduce_columns(
+                    _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, oval.data_ptr(), ocnt.data_ptr(),
+                    scratch.data_ptr(), variant, current_stream(),
+                )
+            )  # fmt: skip
+            for pos, j in enumerate(sel):
+                vals[j] = oval[pos : pos + 1]
+                cnts[j] = ocnt[pos : pos + 1]
+    return vals, cnts
+
+
+# ------------------------------------------------------------------ GroupByReduce
+class GroupTable:
+    """Owner of one device hash table (mb200_gb_table)."""
+
+    def __init__(self, group_capacity: int, nvals: int, flags: int):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self.capacity = int(group_capacity)
+        self.nvals = int(nvals)
+        self.flags = int(flags)
+        _lib.check(self.lib.mb200_gb_create(C.byref(self.handle), self.capacity, self.nvals, self.flags,
+                                            current_stream()))  # fmt: skip
+
+    def accumulate(self, keys: DeviceColumn, vals: Sequence[DeviceColumn]):
+        if keys.dtype != np.int64:
+            raise TypeError("device groupby needs an int64 key column")
+        for v in vals:
+            if v.dtype != np.float64:
+                raise TypeError("device groupby aggregates float64 value columns")
+        ptrs = _lib.ptr_array([v.ptr for v in vals])
+        _lib.check(self.lib.mb200_gb_accumulate(self.handle, keys.ptr, ptrs, len(keys), current_stream()))
+
+    def merge_partial(self, keys: DeviceColumn, sums, cnts=None, sizes: Optional[DeviceColumn] = None):
+        ps = _lib.ptr_array([v.ptr for v in sums]) if sums else None
+        pc = _lib.ptr_array([v.ptr for v in cnts]) if cnts else None
+        _lib.check(
+            self.lib.mb200_gb_merge_partial(self.handle, keys.ptr, ps, pc, sizes.ptr if sizes is not None else None,
+                                            len(keys), current_stream())
+        )  # fmt: skip
+
+    def ngroups(self):
+        ng = C.c_int64()
+        ov = C.c_int()
+        _lib.check(self.lib.mb200_gb_ngroups(self.handle, C.byref(ng), C.byref(ov), current_stream()))
+        return int(ng.value), bool(ov.value)
+
+    def emit(self, ngroups: int, sort: bool = True):
+        keys = DeviceColumn.empty(ngroups, np.int64)
+        sums = [DeviceColumn.empty(ngroups, np.float64) for _ in range(self.nvals)] if self.flags & _lib.GB_SUM else None
+        cnts = [DeviceColumn.empty(ngroups, np.int64) for _ in range(self.nvals)] if self.flags & _lib.GB_COUNT else None
+        sizes = DeviceColumn.empty(ngroups, np.int64) if self.flags & _lib.GB_SIZE else None
+        scratch = _scratch(self.lib.mb200_gb_emit_scratch_bytes(ngroups), "gb_emit")
+        _lib.check(
+            self.lib.mb200_gb_emit(
+                self.handle, ngroups, 1 if sort else 0, keys.ptr,
+                _lib.ptr_array([c.ptr for c in sums]) if sums else None,
+                _lib.ptr_array([c.ptr for c in cnts]) if cnts else None,
+                sizes.ptr if sizes is not None else None, scratch.data_ptr(), current_stream(),
+            )
+        )  # fmt: skip
+        return keys, sums, cnts, sizes
+
+    def close(self):
+        if self.handle:
+            self.lib.mb200_gb_destroy(self.handle, current_stream())
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool = False, sort: bool = True):
+    """Run the hash aggregation over a list of (keys, vals[, cnts, sizes]) inputs, growing the
+    table when it overflows.  Returns (keys, sums, cnts, sizes) device columns."""
+    cap = max(int(capacity_hint), 1024)
+    nvals = len(key_cols_vals[0][1]) if key_cols_vals[0][1] else 0
+    while True:
+        table = GroupTable(cap, nvals, flags)
+        try:
+            for item in key_cols_vals:
+                if partial:
+                    table.merge_partial(*item)
+                else:
+                    table.accumulate(item[0], item[1])
+            ng, overflow = table.ngroups()
+            if not overflow:
+                return table.emit(ng, sort=sort)
+        finally:
+            table.close()
+        total_rows = sum(len(item[0]) for item in key_cols_vals)
+        if cap >= max(total_rows, 1024):
+            raise _lib.B200Error("group table overflow even with capacity == number of rows")
+        cap = min(max(cap * 4, 1024), max(total_rows, 1024))
+
+
+# ------------------------------------------------------------------ broadcast hash join
+class JoinTable:
+    def __init__(self, dim_keys: DeviceColumn):
+        if dim_keys.dtype != np.int64:
+            raise TypeError("device merge needs an int64 key column")
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self.keys = dim_keys
+        _lib.check(self.lib.mb200_join_build(C.byref(self.handle), dim_keys.ptr, len(dim_keys), current_stream()))
+
+    def is_unique(self) -> bool:
+        u = C.c_int()
+        _lib.check(self.lib.mb200_join_is_unique(self.handle, C.byref(u), current_stream()))
+        return bool(u.value)
+
+    def probe(self, fact_keys: DeviceColumn):
+        t = torch_mod()
+        idx = DeviceColumn.empty(len(fact_keys), np.int64)
+        nm = t.zeros(1, dtype=t.int64, device=current_device())
+        _lib.check(self.lib.mb200_join_probe(self.handle, fact_keys.ptr, len(fact_keys), idx.ptr, nm.data_ptr(),
+                                             current_stream()))  # fmt: skip
+        return idx, nm
+
+    def probe_gather(self, fact_keys: DeviceColumn, dim_cols: Sequence[DeviceColumn]):
+        """Left-join payload: float64 out (NaN on miss); int64 payload is promoted like pandas does
+        when a left join has misses -- decided by the caller from the returned match count."""
+        t = torch_mod()
+        n = len(fact_keys)
+        nm = t.zeros(1, dtype=t.int64, device=current_device())
+        outs: list = [None] * len(dim_cols)
+        groups = {}
+        for j, c in enumerate(dim_cols):
+            groups.setdefault(c.code, []).append(j)
+        for code, idxs in groups.items():
+            if code == _lib.U8:
+                raise TypeError("bool payload columns are not on the device merge path")
+            sel_out = [DeviceColumn.empty(n, dim_cols[j].dtype) for j in idxs]
+            _lib.check(
+                self.lib.mb200_join_probe_gather(
+                    self.handle, fact_keys.ptr, n, len(idxs), _lib.ptr_array([dim_cols[j].ptr for j in idxs]), code,
+                    _lib.ptr_array([c.ptr for c in sel_out]), nm.data_ptr() if code == list(groups)[0] else None,
+                    current_stream(),
+                )
+            )  # fmt: skip
+            for j, c in zip(idxs, sel_out):
+                outs[j] = c
+        return outs, nm
+
+    def close(self):
+        if self.handle:
+            self.lib.mb200_join_destroy(self.handle, current_stream())
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def take_columns(cols: Sequence[DeviceColumn], idx: DeviceColumn) -> List[DeviceColumn]:
+    lib = _lib.load()
+    n = len(idx)
+    outs: list = [None] * len(cols)
+    groups = {}
+    for j, c in enumerate(cols):
+        groups.setdefault(c.code, []).append(j)
+    for code, idxs in groups.items():
+        for k in range(0, len(idxs), 32):
+            sel = idxs[k : k + 32]
+            o = [DeviceColumn.empty(n, cols[j].dtype) for j in sel]
+            _lib.check(lib.mb200_take(code, len(sel), _lib.ptr_array([cols[j].ptr for j in sel]), idx.ptr, n,
+                                      _lib.ptr_array([c.ptr for c in o]), current_stream()))  # fmt: skip
+            for j, c in zip(sel, o):
+                outs[j] = c
+    return outs
+
+
+def compact_hits(idx: DeviceColumn):
+    """Positions (ascending) of idx >= 0 and their count (host int; synchronises)."""
+    lib = _lib.load()
+    t = torch_mod()
+    n = len(idx)
+    pos = DeviceColumn.empty(n, np.int64)
+    cnt = t.zeros(1, dtype=t.int64, device=current_device())
+    nb = (n + 2047) // 2048
+    sb = nb * 12 + 256
+    scratch = _scratch(sb, "compact")
+    _lib.check(lib.mb200_compact_hits(idx.ptr, n, pos.ptr, cnt.data_ptr(), scratch.data_ptr(), sb, current_stream()))
+    k = int(cnt.item())
+    return pos.slice(0, k), k
+
+
+# ------------------------------------------------------------------ synthetic columns
+def gen_f64(nrows: int, seed: int, col: int, row_offset: int = 0, nan_per_64k: int = 0) -> DeviceColumn:
+    lib = _lib.load()
+    c = DeviceColumn.empty(nrows, np.float64)
+    _lib.check(lib.mb200_gen_f64(c.ptr, nrows, seed, col, row_offset, nan_per_64k, current_stream()))
+    return c
+
+
+def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0) -> DeviceColumn:
+    lib = _lib.load()
+    c = DeviceColumn.empty(nrows, np.int64)
+    _lib.check(lib.mb200_gen_i64(c.ptr, nrows, seed, col, row_offset, modulus, current_stream()))
+    return c
+
+
+def sort_pairs(keys: DeviceColumn, payload: DeviceColumn):
+    """In-place stable sort of (keys, payload) by key."""
+    lib = _lib.load()
+    n = len(keys)
+    sb = lib.mb200_sort_scratch_bytes(n)
+    scratch = _scratch(sb, "sort")
+    _lib.check(lib.mb200_sort_pairs_i64(keys.ptr, payload.ptr, n, scratch.data_ptr(), sb, current_stream()))

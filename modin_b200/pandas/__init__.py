@@ -1,0 +1,349 @@
+"""``modin_b200.pandas``: the pandas-API layer over the B200 query compiler.
+
+A thin mirror of ``modin.pandas`` for the operations on the hot path, written the way the
+reference's API layer is: every method validates arguments, forwards to
+``self._query_compiler.<op>`` and wraps the resulting query compiler
+(modin/pandas/base.py:485-542 ``_binary_op``, :660-665 ``abs``; modin/pandas/dataframe.py:2188-2247
+``sum``, :484-603 ``groupby``, :1365-1403 ``merge``; modin/pandas/groupby.py:1330-1345, 1829-1886).
+
+With real Modin installed, ``modin_b200.modin_plugin.register()`` plugs the same execution in
+behind ``modin.pandas`` itself; this module is what runs where Modin is absent (the GPU box).
+"""
+
+from __future__ import annotations
+
+import numbers
+from typing import Optional
+
+import numpy as np
+import pandas
+
+from ..functors import MODIN_UNNAMED_SERIES_LABEL
+from ..query_compiler import B200QueryCompiler
+
+
+def _is_scalar(x):
+    return isinstance(x, (numbers.Number, np.number)) or np.isscalar(x)
+
+
+class BasePandasDataset:
+    _query_compiler: B200QueryCompiler
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def _create_or_update_from_compiler(self, new_query_compiler):
+        return type(self)(query_compiler=new_query_compiler)
+
+    def _validate_other(self, other):
+        if isinstance(other, BasePandasDataset):
+            return other._query_compiler
+        return other
+
+    def _binary_op(self, op, other, **kwargs):
+        """modin/pandas/base.py:485-542."""
+        other_qc = self._validate_other(other)
+        broadcast = isinstance(other, Series) and isinstance(self, DataFrame)
+        if broadcast:
+            # frame (op) Series along columns == per-column scalars: hand the values over as a row vector
+            other_qc = other._to_pandas()
+        new_qc = getattr(self._query_compiler, op)(other_qc, **kwargs)
+        return self._create_or_update_from_compiler(new_qc)
+
+    def _reduce_dimension(self, query_compiler):
+        """1 x W frame -> pandas.Series (modin/pandas/dataframe.py ``_reduce_dimension``): the result of
+        a reduction is small, so it is returned as a host ``pandas.Series``."""
+        df = query_compiler.to_pandas()
+        ser = df.iloc[0] if len(df) else pandas.Series(dtype="float64", index=df.columns)
+        ser.name = None
+        if len(set(df.dtypes)) == 1:
+            ser = ser.astype(df.dtypes.iloc[0])
+        return ser
+
+    # ---- Map -------------------------------------------------------------------------------------
+    def abs(self):
+        return self._create_or_update_from_compiler(self._query_compiler.abs())
+
+    def __abs__(self):
+        return self.abs()
+
+    def __neg__(self):
+        return self._create_or_update_from_compiler(self._query_compiler.negative())
+
+    def isna(self):
+        return self._create_or_update_from_compiler(self._query_compiler.isna())
+
+    isnull = isna
+
+    def notna(self):
+        return self._create_or_update_from_compiler(self._query_compiler.notna())
+
+    notnull = notna
+
+    def fillna(self, value=None, *, method=None, axis=None, inplace=False, limit=None, downcast=None):
+        if value is None and method is None:
+            raise ValueError("Must specify a fill 'value' or 'method'.")
+        if isinstance(value, (list, tuple)):
+            raise TypeError(f'"value" parameter must be a scalar or dict, but you passed a "{type(value).__name__}"')
+        if inplace:
+            raise NotImplementedError("inplace=True is not supported by modin_b200.pandas")
+        if isinstance(value, BasePandasDataset):
+            value = value._query_compiler
+        return self._create_or_update_from_compiler(
+            self._query_compiler.fillna(value=value, method=method, axis=axis, limit=limit)
+        )
+
+    # ---- Binary ----------------------------------------------------------------------------------
+    def add(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("add", other, axis=axis, level=level, fill_value=fill_value)
+
+    def radd(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("radd", other, axis=axis, level=level, fill_value=fill_value)
+
+    def sub(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("sub", other, axis=axis, level=level, fill_value=fill_value)
+
+    def rsub(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("rsub", other, axis=axis, level=level, fill_value=fill_value)
+
+    def mul(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("mul", other, axis=axis, level=level, fill_value=fill_value)
+
+    def rmul(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("rmul", other, axis=axis, level=level, fill_value=fill_value)
+
+    def truediv(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("truediv", other, axis=axis, level=level, fill_value=fill_value)
+
+    def rtruediv(self, other, axis="columns", level=None, fill_value=None):
+        return self._binary_op("rtruediv", other, axis=axis, level=level, fill_value=fill_value)
+
+    div = divide = truediv
+    multiply = mul
+    subtract = sub
+
+    def eq(self, other, axis="columns", level=None):
+        return self._binary_op("eq", other, axis=axis, level=level)
+
+    def ne(self, other, axis="columns", level=None):
+        return self._binary_op("ne", other, axis=axis, level=level)
+
+    def lt(self, other, axis="columns", level=None):
+        return self._binary_op("lt", other, axis=axis, level=level)
+
+    def le(self, other, axis="columns", level=None):
+        return self._binary_op("le", other, axis=axis, level=level)
+
+    def gt(self, other, axis="columns", level=None):
+        return self._binary_op("gt", other, axis=axis, level=level)
+
+    def ge(self, other, axis="columns", level=None):
+        return self._binary_op("ge", other, axis=axis, level=level)
+
+    __add__ = lambda self, o: self.add(o)  # noqa: E731
+    __radd__ = lambda self, o: self.radd(o)  # noqa: E731
+    __sub__ = lambda self, o: self.sub(o)  # noqa: E731
+    __rsub__ = lambda self, o: self.rsub(o)  # noqa: E731
+    __mul__ = lambda self, o: self.mul(o)  # noqa: E731
+    __rmul__ = lambda self, o: self.rmul(o)  # noqa: E731
+    __truediv__ = lambda self, o: self.truediv(o)  # noqa: E731
+    __rtruediv__ = lambda self, o: self.rtruediv(o)  # noqa: E731
+    __eq__ = lambda self, o: self.eq(o)  # noqa: E731
+    __ne__ = lambda self, o: self.ne(o)  # noqa: E731
+    __lt__ = lambda self, o: self.lt(o)  # noqa: E731
+    __le__ = lambda self, o: self.le(o)  # noqa: E731
+    __gt__ = lambda self, o: self.gt(o)  # noqa: E731
+    __ge__ = lambda self, o: self.ge(o)  # noqa: E731
+    __hash__ = None
+
+    # ---- TreeReduce --------------------------------------------------------------------------------
+    def _stat(self, name, axis=0, skipna=True, numeric_only=False, **kwargs):
+        if axis not in (0, "index", None):
+            raise NotImplementedError(f"{name}(axis=1) is not on the B200 path")
+        qc = getattr(self._query_compiler, name)(axis=0, skipna=skipna, numeric_only=numeric_only, **kwargs)
+        return self._reduce_dimension(qc)
+
+    def sum(self, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+        return self._stat("sum", axis, skipna, numeric_only, min_count=min_count)
+
+    def mean(self, axis=0, skipna=True, numeric_only=False, **kwargs):
+        return self._stat("mean", axis, skipna, numeric_only)
+
+    def min(self, axis=0, skipna=True, numeric_only=False, **kwargs):
+        return self._stat("min", axis, skipna, numeric_only)
+
+    def max(self, axis=0, skipna=True, numeric_only=False, **kwargs):
+        return self._stat("max", axis, skipna, numeric_only)
+
+    def count(self, axis=0, numeric_only=False):
+        if axis not in (0, "index", None):
+            raise NotImplementedError("count(axis=1) is not on the B200 path")
+        return self._reduce_dimension(self._query_compiler.count(axis=0, numeric_only=numeric_only))
+
+    # ---- misc --------------------------------------------------------------------------------------
+    def _to_pandas(self):
+        return self._query_compiler.to_pandas()
+
+    def to_numpy(self, **kwargs):
+        return self._query_compiler.to_numpy(**kwargs)
+
+    def execute(self):
+        """modin.utils.execute (modin/utils.py:740-753): drain call queues and wait for the device."""
+        self._query_compiler.execute()
+        return self
+
+    @property
+    def dtypes(self):
+        return self._query_compiler.dtypes
+
+
+class DataFrame(BasePandasDataset):
+    """modin.pandas.DataFrame for the hot path (modin/pandas/dataframe.py:147-266 constructor)."""
+
+    def __init__(self, data=None, index=None, columns=None, dtype=None, copy=None, query_compiler=None):
+        if query_compiler is not None:
+            self._query_compiler = query_compiler
+            return
+        if isinstance(data, DataFrame):
+            self._query_compiler = data._query_compiler
+            return
+        if not isinstance(data, pandas.DataFrame) or index is not None or columns is not None or dtype is not None:
+            data = pandas.DataFrame(data=data, index=index, columns=columns, dtype=dtype)
+        self._query_compiler = B200QueryCompiler.from_pandas(data)
+
+    # metadata
+    columns = property(lambda self: self._query_compiler.columns)
+    index = property(lambda self: self._query_compiler.index)
+    shape = property(lambda self: (self._query_compiler.get_axis_len(0), len(self.columns)))
+
+    def __len__(self):
+        return self._query_compiler.get_axis_len(0)
+
+    def __getitem__(self, key):
+        if isinstance(key, (list, pandas.Index, np.ndarray)):
+            return DataFrame(query_compiler=self._query_compiler.getitem_column_array(list(key)))
+        if key not in self.columns:
+            raise KeyError(key)
+        qc = self._query_compiler.getitem_column_array([key])
+        return Series(query_compiler=qc)
+
+    def groupby(self, by=None, axis=0, level=None, as_index=True, sort=True, group_keys=True, observed=True,
+                dropna=True):  # fmt: skip
+        """modin/pandas/dataframe.py:484-603: a column label resolves to ``self[by]``'s query compiler
+        with ``drop=True``."""
+        if axis not in (0, "index"):
+            raise NotImplementedError("groupby(axis=1) is not on the B200 path")
+        if level is not None:
+            raise NotImplementedError("groupby(level=) is not on the B200 path")
+        if isinstance(by, (list, tuple)):
+            if len(by) != 1:
+                raise NotImplementedError("multi-column groupby is not on the B200 path yet")
+            by = by[0]
+        drop = False
+        if isinstance(by, Series):
+            by_qc = by._query_compiler
+        elif isinstance(by, str) or not callable(by):
+            if by not in self.columns:
+                raise KeyError(by)
+            by_qc = self[by]._query_compiler
+            drop = True
+        else:
+            raise NotImplementedError("callable `by` is not on the B200 path")
+        return DataFrameGroupBy(self, by_qc, drop=drop,
+                                groupby_kwargs=dict(as_index=as_index, sort=sort, group_keys=group_keys,
+                                                    observed=observed, dropna=dropna, level=level))  # fmt: skip
+
+    def merge(self, right, how="inner", on=None, left_on=None, right_on=None, left_index=False, right_index=False,
+              sort=False, suffixes=("_x", "_y"), copy=None, indicator=False, validate=None):  # fmt: skip
+        """modin/pandas/dataframe.py:1365-1403."""
+        if isinstance(right, Series):
+            raise NotImplementedError("merging with a Series is not on the B200 path")
+        if not isinstance(right, DataFrame):
+            raise TypeError(f"Can only merge Series or DataFrame objects, a {type(right)} was passed")
+        if indicator or validate is not None or sort:
+            raise NotImplementedError("merge(indicator=/validate=/sort=True) is not on the B200 path")
+        return DataFrame(
+            query_compiler=self._query_compiler.merge(
+                right._query_compiler, how=how, on=on, left_on=left_on, right_on=right_on, left_index=left_index,
+                right_index=right_index, sort=sort, suffixes=suffixes,
+            )
+        )  # fmt: skip
+
+    def __repr__(self):
+        return f"<modin_b200.pandas.DataFrame shape={self.shape} columns={list(self.columns)!r}>"
+
+
+class Series(BasePandasDataset):
+    """One-column frame viewed as a Series (modin/pandas/series.py keeps a 1-column query compiler)."""
+
+    def __init__(self, data=None, index=None, name=None, query_compiler=None):
+        if query_compiler is not None:
+            self._query_compiler = query_compiler
+            return
+        ser = data if isinstance(data, pandas.Series) else pandas.Series(data, index=index, name=name)
+        label = ser.name if ser.name is not None else MODIN_UNNAMED_SERIES_LABEL
+        self._query_compiler = B200QueryCompiler.from_pandas(ser.to_frame(label))
+
+    @property
+    def name(self):
+        label = self._query_compiler.columns[0]
+        return None if label == MODIN_UNNAMED_SERIES_LABEL else label
+
+    def __len__(self):
+        return self._query_compiler.get_axis_len(0)
+
+    def _to_pandas(self):
+        df = self._query_compiler.to_pandas()
+        ser = df.iloc[:, 0]
+        ser.name = self.name
+        return ser
+
+    def _reduce_dimension(self, query_compiler):
+        res = super()._reduce_dimension(query_compiler)
+        return res.iloc[0]
+
+
+class DataFrameGroupBy:
+    """modin/pandas/groupby.py (``_wrap_aggregation`` :1829-1886)."""
+
+    def __init__(self, df: DataFrame, by_qc, drop, groupby_kwargs):
+        self._df = df
+        self._query_compiler = df._query_compiler
+        self._by = by_qc
+        self._drop = drop
+        self._kwargs = groupby_kwargs
+        if not groupby_kwargs.get("as_index", True):
+            raise NotImplementedError("groupby(as_index=False) is not on the B200 path")
+
+    def _wrap_aggregation(self, qc_method, numeric_only=False, agg_args=None, agg_kwargs=None):
+        qc = self._query_compiler
+        if self._drop:
+            # the key column lives in the frame: value columns are all the others (alg/groupby.py:186-199)
+            pass
+        result_qc = qc_method(qc, by=self._by, axis=0, groupby_kwargs=self._kwargs, agg_args=agg_args or [],
+                              agg_kwargs=agg_kwargs or {}, drop=self._drop)  # fmt: skip
+        return DataFrame(query_compiler=result_qc)
+
+    def sum(self, numeric_only=False, min_count=0):
+        if min_count:
+            raise NotImplementedError("groupby.sum(min_count>0) is not on the B200 path")
+        return self._wrap_aggregation(type(self._query_compiler).groupby_sum, numeric_only)
+
+    def count(self):
+        return self._wrap_aggregation(type(self._query_compiler).groupby_count)
+
+    def mean(self, numeric_only=False):
+        return self._wrap_aggregation(type(self._query_compiler).groupby_mean, numeric_only)
+
+    def size(self):
+        res = self._wrap_aggregation(type(self._query_compiler).groupby_size)
+        return Series(query_compiler=res._query_compiler)
+
+    def agg(self, func, *args, **kwargs):
+        if isinstance(func, str) and func in ("sum", "count", "mean", "size"):
+            return getattr(self, func)()
+        raise NotImplementedError(f"groupby.agg({func!r}) is not on the B200 path")
+
+    aggregate = agg
+
+
+def concat(*args, **kwargs):  # pragma: no cover - signature placeholder
+    raise NotImplementedError("concat is not on the B200 path")

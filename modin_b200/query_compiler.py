@@ -1,0 +1,217 @@
+"""B200QueryCompiler: the hot-path subset of PandasQueryCompiler with device functors registered
+through the operator templates.
+
+Reference registrations being mirrored (modin/core/storage_formats/pandas/query_compiler.py):
+Binary ops ``:535-624``; ``count/sum/max/min/mean`` TreeReduce ``:976-1096``; ``abs`` ``:2036``;
+``isna/notna/negative`` ``:2063-2106``; ``fillna`` ``:2710-2813``; ``groupby_*`` ``:3741-3748``
+with GroupbyReduceImpl (storage_formats/pandas/groupby.py:26-248); ``merge`` ``:657-667`` with
+MergeImpl.row_axis_merge (merge.py:104-252).
+
+Operations outside this list raise ``NotImplementedError`` instead of defaulting to pandas: the
+north-star forbids a CPU fallback on this path, and a silent D2H -> pandas -> H2D round trip would
+hide exactly the cost this backend exists to remove.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pandas
+
+from .algebra import Binary, GroupByReduce, Map, TreeReduce
+from .dataframe import B200Dataframe
+from .functors import (
+    DevBinary,
+    DevFillna,
+    DevGroupbyMap,
+    DevGroupbyReduce,
+    DevMap,
+    DevMeanMap,
+    DevMeanReduce,
+    DevMerge,
+    DevReduce,
+)
+from .partitioning import Bound
+
+
+def _dtypes_sum(dtypes: pandas.Series, *func_args, **func_kwargs):
+    """qc.py:961-974: result dtype of sum = common type of the columns."""
+    return np.result_type(*dtypes.values) if len(dtypes) else np.dtype("float64")
+
+
+class B200QueryCompiler:
+    """Query compiler holding a ``B200Dataframe`` (qc.py:279-302)."""
+
+    _modin_frame: B200Dataframe
+    _shape_hint = None
+
+    def __init__(self, modin_frame: B200Dataframe, shape_hint=None):
+        self._modin_frame = modin_frame
+        self._shape_hint = shape_hint
+
+    @property
+    def __constructor__(self):
+        return type(self)
+
+    storage_format = property(lambda self: self._modin_frame.storage_format)
+    engine = property(lambda self: self._modin_frame.engine)
+
+    # ---- metadata ----------------------------------------------------------------------------------
+    index = property(lambda self: self._modin_frame.index)
+    columns = property(lambda self: self._modin_frame.columns)
+    dtypes = property(lambda self: self._modin_frame.dtypes)
+    frame_has_materialized_dtypes = property(lambda self: self._modin_frame.has_materialized_dtypes)
+    frame_has_materialized_columns = property(lambda self: self._modin_frame.has_materialized_columns)
+
+    def get_axis_len(self, axis):
+        return len(self._modin_frame) if axis == 0 else len(self.columns)
+
+    # ---- lifecycle (qc.py:366-387) ------------------------------------------------------------------
+    def finalize(self):
+        self._modin_frame.finalize()
+
+    def execute(self):
+        self.finalize()
+        self._modin_frame.wait_computations()
+
+    def free(self):
+        pass
+
+    @classmethod
+    def from_pandas(cls, df, data_cls=B200Dataframe):
+        return cls(data_cls.from_pandas(df))
+
+    @classmethod
+    def from_arrow(cls, at, data_cls=B200Dataframe):
+        return cls(data_cls.from_arrow(at))
+
+    def to_pandas(self):
+        return self._modin_frame.to_pandas()
+
+    def to_numpy(self, **kwargs):
+        return self._modin_frame.to_numpy(**kwargs)
+
+    def default_to_pandas(self, pandas_op, *args, **kwargs):
+        name = getattr(pandas_op, "__name__", str(pandas_op))
+        raise NotImplementedError(
+            f"`{name}` has no device implementation in modin_b200 and this execution never defaults to pandas"
+        )
+
+    def getitem_column_array(self, key, numeric=False, ignore_order=False):
+        """qc.py:2885-2905."""
+        if numeric:
+            positions = list(key)
+        else:
+            positions = [int(p) for p in self.columns.get_indexer_for(list(key))]
+            if any(p < 0 for p in positions):
+                missing = [k for k, p in zip(key, positions) if p < 0]
+                raise KeyError(f"{missing} not in index")
+        return self.__constructor__(self._modin_frame.take_2d_labels_or_positional(col_positions=positions))
+
+    # ---- Map (qc.py:2036-2106) ----------------------------------------------------------------------
+    abs = Map.register(DevMap("abs"), dtypes="copy")
+    negative = Map.register(DevMap("neg"), dtypes="copy")
+    isna = Map.register(DevMap("isna"), dtypes=np.bool_)
+    notna = Map.register(DevMap("notna"), dtypes=np.bool_)
+    copy_data = Map.register(DevMap("copy"), dtypes="copy")
+
+    def fillna(self, **kwargs):
+        """qc.py:2710-2813: scalar / dict values are a Map; ``method``/``limit`` would be a Fold."""
+        value = kwargs.get("value")
+        if isinstance(value, type(self)):
+            if kwargs.get("method") is not None:
+                raise NotImplementedError("fillna(method=) is not on the B200 path")
+            return self.__constructor__(
+                self._modin_frame.n_ary_op(Bound(DevBinary("fillna")), [value._modin_frame], join_type="left")
+            )
+        return self.__constructor__(self._modin_frame.map(Bound(DevFillna(), (), kwargs), dtypes=None))
+
+    # ---- Binary (qc.py:535-624) ---------------------------------------------------------------------
+    add = Binary.register(DevBinary("add"), infer_dtypes="try_sample")
+    radd = Binary.register(DevBinary("radd"), infer_dtypes="try_sample")
+    sub = Binary.register(DevBinary("sub"), infer_dtypes="try_sample")
+    rsub = Binary.register(DevBinary("rsub"), infer_dtypes="try_sample")
+    mul = Binary.register(DevBinary("mul"), infer_dtypes="try_sample")
+    rmul = Binary.register(DevBinary("rmul"), infer_dtypes="try_sample")
+    truediv = Binary.register(DevBinary("truediv"), infer_dtypes="try_sample")
+    rtruediv = Binary.register(DevBinary("rtruediv"), infer_dtypes="try_sample")
+    eq = Binary.register(DevBinary("eq"), infer_dtypes="bool")
+    ne = Binary.register(DevBinary("ne"), infer_dtypes="bool")
+    lt = Binary.register(DevBinary("lt"), infer_dtypes="bool")
+    le = Binary.register(DevBinary("le"), infer_dtypes="bool")
+    gt = Binary.register(DevBinary("gt"), infer_dtypes="bool")
+    ge = Binary.register(DevBinary("ge"), infer_dtypes="bool")
+
+    # ---- TreeReduce (qc.py:976-1096) ----------------------------------------------------------------
+    count = TreeReduce.register(DevReduce("count"), DevReduce("count", phase="reduce"))
+    sum = TreeReduce.register(DevReduce("sum"), DevReduce("sum", phase="reduce"), compute_dtypes=_dtypes_sum)
+    max = TreeReduce.register(DevReduce("max"), DevReduce("max", phase="reduce"))
+    min = TreeReduce.register(DevReduce("min"), DevReduce("min", phase="reduce"))
+    mean = TreeReduce.register(DevMeanMap(), DevMeanReduce(), compute_dtypes=lambda *a, **k: np.dtype("float64"))
+
+    # ---- GroupByReduce (qc.py:3741-3748; impl table storage_formats/pandas/groupby.py:237-248) ------
+    groupby_sum = GroupByReduce.register(DevGroupbyMap("sum"), DevGroupbyReduce("sum"))
+    groupby_count = GroupByReduce.register(DevGroupbyMap("count"), DevGroupbyReduce("count"))
+    groupby_size = GroupByReduce.register(DevGroupbyMap("size"), DevGroupbyReduce("size"))
+    groupby_mean = GroupByReduce.register(DevGroupbyMap("mean"), DevGroupbyReduce("mean"))
+
+    # ---- merge (qc.py:657-667 -> MergeImpl.row_axis_merge merge.py:104-252) --------------------------
+    def merge(self, right, **kwargs):
+        how = kwargs.get("how", "inner")
+        on = kwargs.get("on")
+        left_on, right_on = kwargs.get("left_on"), kwargs.get("right_on")
+        if kwargs.get("left_index") or kwargs.get("right_index"):
+            raise NotImplementedError("index joins default to pandas in the reference (merge.py:129-136)")
+        if how not in ("left", "inner"):
+            raise NotImplementedError(f"merge(how={how!r}) defaults to pandas in the reference; not on the B200 path")
+        if on is None and left_on is not None and left_on == right_on:
+            on = left_on
+        if on is None or isinstance(on, (list, tuple)) and len(on) != 1:
+            raise NotImplementedError("device merge joins on exactly one int64 key column given by `on`")
+        if isinstance(on, (list, tuple)):
+            on = on[0]
+        suffixes = kwargs.get("suffixes", ("_x", "_y"))
+        # merge.py:178 -- all dim partitions collapsed into one and broadcast to every row partition
+        right_to_broadcast = right._modin_frame.combine()
+        func = DevMerge(on=on, how=how, suffixes=suffixes)
+        right_labels = [c for c in right.columns if c != on]
+        overlap = set(self.columns) & set(right_labels)
+        new_columns = pandas.Index(
+            [f"{c}{suffixes[0]}" if c in overlap else c for c in self.columns]
+            + [f"{c}{suffixes[1]}" if c in overlap else c for c in right_labels]
+        )
+        new_frame = self._modin_frame.broadcast_apply_full_axis(
+            axis=1, func=func, other=right_to_broadcast, keep_partitioning=True, new_columns=new_columns,
+            sync_labels=False,
+        )  # fmt: skip
+        # merge.py:236-250: the result index is reset to a fresh RangeIndex
+        return self.__constructor__(_reset_row_index(new_frame))
+
+
+def _reset_row_index(frame: B200Dataframe) -> B200Dataframe:
+    """``reset_index(drop=True)`` on range-indexed device blocks: renumber ``range_start`` so that
+    the row partitions of this rank form one contiguous RangeIndex (metadata only, no kernel)."""
+    from . import dist
+    from .block import DeviceBlock
+
+    lengths = frame.row_lengths
+    offset = 0
+    if dist.is_distributed():
+        import torch
+
+        dev = frame._any_device()
+        mine = torch.zeros(dist.world_size(), dtype=torch.int64, device=dev)
+        mine[dist.rank()] = sum(lengths)
+        dist.all_reduce_values([mine], ["sum"])
+        offset = int(mine[: dist.rank()].sum().item())
+    pc = frame._partition_mgr_cls._partition_class
+    rows = []
+    for row, n in zip(frame._partitions, lengths):
+        new_row = []
+        for p in row:
+            b = p.get()
+            new_row.append(pc(DeviceBlock(b.cols, b.columns, nrows=b.nrows, range_start=offset)))
+        rows.append(new_row)
+        offset += n
+    start = offset - sum(lengths)
+    return type(frame)(np.array(rows, dtype=object), pandas.RangeIndex(start, offset), frame._columns_cache,
+                       lengths, frame._column_widths_cache, frame._dtypes)  # fmt: skip

@@ -1,0 +1,246 @@
+"""CPU restatement of the reference's partition-execution hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import this package; nothing under ``modin_b200/`` does (the product path
+has no CPU branch).
+
+What is restated: Modin's *partitioning + operator-template* logic -- the part of the algorithm
+that lives in /root/reference -- with the per-block arithmetic delegated to pandas exactly as the
+reference does (the arithmetic itself is the third-party dependency ``pandas`` pinned
+``>=2.2,<2.4`` in /root/reference/setup.py:49; this image has pandas 3.0.2).  Each function cites
+the reference code it follows.  Parity is PINNED: ``tests/golden/*.npz`` were produced by running
+the unmodified reference (PandasOnPython engine, NPartitions=4, five pandas-3 import shims, see
+``tests/golden/make_golden.py``) in the build container, and ``tests/test_oracle.py`` checks this
+restatement against them bit for bit.
+"""
+
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import pandas
+
+MODIN_UNNAMED_SERIES_LABEL = "__reduced__"  # modin/utils.py:98
+MIN_ROW_PARTITION_SIZE = 32  # modin/config/envvars.py:1149-1190
+MIN_COLUMN_PARTITION_SIZE = 32
+
+
+# ------------------------------------------------------------------ partition grid
+def compute_chunksize(axis_len: int, num_splits: int, min_block_size: int) -> int:
+    """modin/core/storage_formats/pandas/utils.py:28-58."""
+    chunksize = axis_len // num_splits
+    if axis_len % num_splits:
+        chunksize += 1
+    return max(chunksize, min_block_size)
+
+
+def split_into_partitions(df: pandas.DataFrame, npartitions: int) -> List[List[pandas.DataFrame]]:
+    """pm.from_pandas / split_pandas_df_into_partitions (partition_manager.py:1029-1149): a 2-D grid
+    of ``iloc`` slices, chunk = max(ceil(n / NPartitions), 32) along both axes."""
+    row_chunk = compute_chunksize(df.shape[0], npartitions, MIN_ROW_PARTITION_SIZE)
+    col_chunk = compute_chunksize(df.shape[1], npartitions, MIN_COLUMN_PARTITION_SIZE)
+    grid = []
+    for i in range(0, max(len(df), 1), row_chunk):
+        grid.append([df.iloc[i : i + row_chunk, j : j + col_chunk].copy()  # python engine copies on put, partition.py:52
+                     for j in range(0, max(len(df.columns), 1), col_chunk)])  # fmt: skip
+    return grid
+
+
+def _pmap(fn: Callable, items: Sequence, threads: int):
+    if threads <= 1 or len(items) <= 1:
+        return [fn(x) for x in items]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(fn, items))
+
+
+def to_pandas(grid) -> pandas.DataFrame:
+    """pm.to_pandas (partition_manager.py:989-1005): concat columns within a row, then rows."""
+    rows = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
+    return pandas.concat(rows, axis=0) if len(rows) > 1 else rows[0]
+
+
+# ------------------------------------------------------------------ Map (alg/map.py:32-70, df.py:2253-2319)
+def map_partitions(grid, func: Callable, threads: int = 1):
+    """pm.map_partitions (partition_manager.py:708-769): ``func`` on a copy of every block
+    (pandas_on_python/partitioning/partition.py:110)."""
+    flat = [(i, j, blk) for i, row in enumerate(grid) for j, blk in enumerate(row)]
+    outs = _pmap(lambda t: func(t[2].copy()), flat, threads)
+    new = [[None] * len(row) for row in grid]
+    for (i, j, _), o in zip(flat, outs):
+        new[i][j] = o
+    return new
+
+
+def df_abs(df: pandas.DataFrame, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """qc.abs = Map.register(pandas.DataFrame.abs) (query_compiler.py:2036)."""
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), pandas.DataFrame.abs, threads))
+
+
+def df_fillna(df, value, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """qc.fillna scalar/dict branch -> frame.map (query_compiler.py:2710-2813)."""
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), lambda b: b.fillna(value=value), threads))
+
+
+def df_isna(df, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), pandas.DataFrame.isna, threads))
+
+
+# ------------------------------------------------------------------ Binary (alg/binary.py:334-458)
+def binary_scalar(df, op: str, other, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """Scalar / list operand: ``frame.map(func, func_args=(other,), lazy=True)`` (binary.py:449-455)."""
+    fn = getattr(pandas.DataFrame, op)
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), lambda b: fn(b, other), threads))
+
+
+def n_ary_op(frames: Sequence[pandas.DataFrame], func: Callable, npartitions: int, threads: int = 1):
+    """PandasDataframe.n_ary_op fast path (dataframe.py:3851-3950 with identical axes, :3750-3758) ->
+    pm.n_ary_operation (partition_manager.py:1725-1788): ``out[i,j] = func(left[i,j], *right[i,j])``."""
+    grids = [split_into_partitions(f, npartitions) for f in frames]
+    left = grids[0]
+    flat = [(i, j) for i, row in enumerate(left) for j in range(len(row))]
+    outs = _pmap(lambda ij: func(*[g[ij[0]][ij[1]].copy() for g in grids]), flat, threads)
+    new = [[None] * len(row) for row in left]
+    for (i, j), o in zip(flat, outs):
+        new[i][j] = o
+    return new
+
+
+def a_mul_b_add_c(a, b, c, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """``a * b + c`` the way the reference executes it: two Binary passes with a materialised
+    temporary (``mul`` then ``add``, each an n_ary_op or a scalar map)."""
+
+    def one(x, op, y):
+        if isinstance(y, pandas.DataFrame):
+            return to_pandas(n_ary_op([x, y], lambda l, r: getattr(pandas.DataFrame, op)(l, r), npartitions, threads))
+        return binary_scalar(x, op, y, npartitions, threads)
+
+    return one(one(a, "mul", b), "add", c)
+
+
+# ------------------------------------------------------------------ TreeReduce (alg/tree_reduce.py:33-82)
+def _build_treereduce_func(func: Callable) -> Callable:
+    """PandasDataframe._build_treereduce_func, axis=0 (dataframe.py:2081-2123): Series -> 1-row frame
+    labelled ``__reduced__`` so partials stack along the reduced axis."""
+
+    def _tree_reduce_func(df):
+        series_result = func(df)
+        if isinstance(series_result, pandas.Series):
+            result = pandas.DataFrame(series_result).T
+            result.index = [MODIN_UNNAMED_SERIES_LABEL]
+        else:
+            result = pandas.DataFrame(series_result)
+        return result
+
+    return _tree_reduce_func
+
+
+def tree_reduce(df, map_func: Callable, reduce_func: Optional[Callable], npartitions: int, threads: int = 1):
+    """PandasDataframe.tree_reduce (dataframe.py:2208-2250): map every block, then per column partition
+    ``pandas.concat`` the partials (deploy_axis_func, axis_partition.py:445-452) and reduce once."""
+    grid = split_into_partitions(df, npartitions)
+    mfn = _build_treereduce_func(map_func)
+    rfn = mfn if reduce_func is None else _build_treereduce_func(reduce_func)
+    mapped = map_partitions(grid, mfn, threads)
+    ncolparts = len(mapped[0])
+    reduced = []
+    for j in range(ncolparts):
+        stacked = pandas.concat([row[j] for row in mapped], axis=0)
+        reduced.append(rfn(stacked))
+    out = pandas.concat(reduced, axis=1) if len(reduced) > 1 else reduced[0]
+    ser = out.iloc[0]
+    ser.name = None
+    return ser
+
+
+def df_sum(df, npartitions, skipna=True, min_count=0, threads: int = 1):
+    """qc.sum = TreeReduce.register(pandas.DataFrame.sum) (query_compiler.py:978-984)."""
+    f = lambda x: x.sum(axis=0, skipna=skipna, min_count=min_count)  # noqa: E731
+    return tree_reduce(df, f, None, npartitions, threads)
+
+
+def df_count(df, npartitions, threads: int = 1):
+    """qc.count = TreeReduce.register(pandas.DataFrame.count, pandas.DataFrame.sum) (query_compiler.py:976)."""
+    return tree_reduce(df, lambda x: x.count(axis=0), lambda x: x.sum(axis=0), npartitions, threads)
+
+
+def df_min(df, npartitions, skipna=True, threads: int = 1):
+    return tree_reduce(df, lambda x: x.min(axis=0, skipna=skipna), None, npartitions, threads)  # query_compiler.py:1013-1035
+
+
+def df_max(df, npartitions, skipna=True, threads: int = 1):
+    return tree_reduce(df, lambda x: x.max(axis=0, skipna=skipna), None, npartitions, threads)
+
+
+def df_mean(df, npartitions, skipna=True, threads: int = 1):
+    """qc.mean (query_compiler.py:1037-1096): map = {"sum","count"} rows; reduce = sum both, divide."""
+
+    def map_fn(x):
+        return pandas.DataFrame(
+            {"sum": x.sum(axis=0, skipna=skipna), "count": x.count(axis=0) if skipna else len(x)}
+        ).T
+
+    grid = split_into_partitions(df, npartitions)
+    mapped = map_partitions(grid, map_fn, threads)
+    outs = []
+    for j in range(len(mapped[0])):
+        stacked = pandas.concat([row[j] for row in mapped], axis=0)
+        sums = stacked.loc["sum"].sum(axis=0, skipna=False) if stacked.loc[["sum"]].shape[0] > 1 else stacked.loc["sum"]
+        cnts = stacked.loc["count"].sum(axis=0, skipna=False) if stacked.loc[["count"]].shape[0] > 1 else stacked.loc["count"]
+        outs.append(sums / cnts)
+    res = pandas.concat(outs) if len(outs) > 1 else outs[0]
+    res.name = None
+    return res.astype("float64")
+
+
+# ------------------------------------------------------------------ GroupByReduce (alg/groupby.py)
+def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """``df.groupby(by).<agg>()`` through GroupByReduce: map = per row block
+    ``df.groupby(by, as_index=True, sort=True).<map_agg>()`` (alg/groupby.py:124-208); reduce =
+    concat of the partial tables + ``groupby(level=0).<reduce_agg>()`` (alg/groupby.py:211-300).
+    Aggregation table: storage_formats/pandas/groupby.py:237-248 (sum->sum, count->sum, size->sum,
+    mean -> sum & count then divide :184-234)."""
+    grid = split_into_partitions(df, npartitions)
+    row_blocks = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
+
+    def map_fn(block):
+        g = block.groupby(by, as_index=True, sort=True, observed=True)
+        if agg == "sum":
+            return g.sum()
+        if agg == "count":
+            return g.count()
+        if agg == "size":
+            return g.size().to_frame("size")
+        if agg == "mean":
+            return pandas.concat({"sum": g.sum(), "count": g.count()}, axis=1)
+        raise ValueError(agg)
+
+    partials = _pmap(lambda b: map_fn(b.copy()), row_blocks, threads)
+    stacked = pandas.concat(partials, axis=0)
+    regrouped = stacked.groupby(level=0, sort=True).sum()
+    if agg == "mean":
+        return regrouped["sum"] / regrouped["count"]
+    if agg == "size":
+        return regrouped["size"]
+    return regrouped
+
+
+# ------------------------------------------------------------------ broadcast merge (merge.py:104-252)
+def broadcast_merge(left, right, on: str, how: str, npartitions: int, threads: int = 1, suffixes=("_x", "_y")):
+    """MergeImpl.row_axis_merge: the right frame collapsed to one partition (merge.py:178) and handed to
+    every left ROW partition, ``pandas.merge(left_block, right, how=how, on=on, sort=False)``
+    (merge.py:139-168), results concatenated, index reset (merge.py:236-250)."""
+    assert how in ("left", "inner")
+    grid = split_into_partitions(left, npartitions)
+    row_blocks = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
+    right_full = right.copy()
+    outs = _pmap(lambda b: pandas.merge(b.copy(), right_full, how=how, on=on, sort=False, suffixes=suffixes),
+                 row_blocks, threads)  # fmt: skip
+    res = pandas.concat(outs, axis=0)
+    return res.reset_index(drop=True)
+
+
+def cpu_threads() -> int:
+    return os.cpu_count() or 1

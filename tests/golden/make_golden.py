@@ -1,0 +1,144 @@
+"""Generate the golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    MODIN_ENGINE=python python tests/golden/make_golden.py
+
+Imports modin from /root/reference (read-only mount) with the PandasOnPython engine and
+NPartitions=4, after applying the five pandas-3 import shims listed in SURVEY.md §8(c) (the
+image ships pandas 3.0.2, the reference pins pandas<2.4; the shims only restore removed pandas
+names / swallow removed keyword arguments -- no reference source is modified or copied).  Inputs
+are the seeded synthetic frames of ``modin_b200.synth`` (host twin) at small sizes; outputs are
+what ``modin.pandas`` returns.  Everything is stored in one ``.npz`` per case under
+tests/golden/.  /root/reference does not exist on the GPU box, which is why the vectors are
+committed.
+"""
+
+import functools
+import os
+import sys
+
+import numpy as np
+import pandas
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def apply_pandas3_shims():
+    import pandas.core.series as pcs
+    import pandas.io.parsers.base_parser as bp
+
+    def _stub(*a, **k):
+        """stub"""
+        raise NotImplementedError
+
+    if not hasattr(pandas, "read_gbq"):
+        pandas.read_gbq = _stub
+    if not hasattr(pcs, "_coerce_method"):
+        def _coerce_method(converter):
+            def wrapper(self):
+                if len(self) == 1:
+                    return converter(self.iloc[0])
+                raise TypeError(f"cannot convert the series to {converter}")
+            wrapper.__name__ = f"__{converter.__name__}__"
+            return wrapper
+        pcs._coerce_method = _coerce_method
+    if not hasattr(bp.ParserBase, "_validate_usecols_arg"):
+        bp.ParserBase._validate_usecols_arg = lambda self, usecols: (usecols, None)
+    for cls in (pandas.DataFrame, pandas.Series):
+        g = cls.groupby
+        cls.groupby = functools.wraps(g)(lambda self, *a, axis=0, _g=g, **k: _g(self, *a, **k))
+        f = cls.fillna
+        cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: _f(self, *a, **k))
+
+
+def main():
+    os.environ["MODIN_ENGINE"] = "python"
+    apply_pandas3_shims()
+    sys.path.insert(0, "/root/reference")
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    import modin.config as cfg
+    import modin.pandas as mpd
+
+    cfg.NPartitions.put(4)
+    from modin_b200 import synth
+
+    def save(name, **arrays):
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+        print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrays.items()})
+
+    def P(x):  # modin -> pandas
+        return x._to_pandas() if hasattr(x, "_to_pandas") else x
+
+    # ---- C1-like: Map / TreeReduce on n x 4 float64 with NaNs
+    for n, W, nan in ((1000, 4, 0), (4099, 5, 2000)):
+        pdf = synth.host_frame(n, W, seed=42, nan_per_64k=nan)
+        mdf = mpd.DataFrame(pdf)
+        tag = f"frame_n{n}_w{W}_nan{nan}"
+        save(
+            tag,
+            meta=np.array([n, W, 42, nan]),
+            abs=P(mdf.abs()).to_numpy(),
+            neg=P(-mdf).to_numpy(),
+            isna=P(mdf.isna()).to_numpy(),
+            fillna=P(mdf.fillna(1.5)).to_numpy(),
+            affine=P(mdf * 1.25 + 0.5).to_numpy(),
+            rowvec=P(mdf * list(np.arange(1, W + 1) * 0.5) + list(np.arange(W) * 0.25)).to_numpy(),
+            sum=P(mdf.sum()).to_numpy(),
+            sum_noskip=P(mdf.sum(skipna=False)).to_numpy(),
+            sum_mc1=P(mdf.sum(min_count=1)).to_numpy(),
+            mean=P(mdf.mean()).to_numpy(),
+            min=P(mdf.min()).to_numpy(),
+            max=P(mdf.max()).to_numpy(),
+            count=P(mdf.count()).to_numpy(),
+            lt0=P(mdf < 0.0).to_numpy(),
+        )
+        # 3-frame a*b+c
+        b = synth.host_frame(n, W, seed=7, nan_per_64k=0)
+        c = synth.host_frame(n, W, seed=9, nan_per_64k=0)
+        mb, mc = mpd.DataFrame(b), mpd.DataFrame(c)
+        save(tag + "_fma3", meta=np.array([n, W, 42, nan, 7, 9]), out=P(mdf * mb + mc).to_numpy(),
+             sub=P(mdf - mb).to_numpy(), div=P(mdf / mb).to_numpy(), ge=P(mdf >= mb).to_numpy())
+
+    # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
+    for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):
+        pdf = synth.host_frame(n, V, seed=42, nan_per_64k=nan, key_modulus=G, key_seed=43)
+        mdf = mpd.DataFrame(pdf)
+        g = mdf.groupby("key")
+        s, c, m, z = P(g.sum()), P(g.count()), P(g.mean()), P(g.size())
+        save(
+            f"groupby_n{n}_g{G}_v{V}_nan{nan}",
+            meta=np.array([n, G, V, nan, 42, 43]),
+            keys=s.index.to_numpy(),
+            sum=s.to_numpy(),
+            count=c.to_numpy(),
+            mean=m.to_numpy(),
+            size=z.to_numpy(),
+        )
+
+    # ---- C5-like: broadcast merge fact x dim on int64 key
+    for n, nd, hit in ((6000, 500, 1.0), (6000, 500, 0.8)):
+        fact = synth.host_frame(n, 3, seed=42, key_modulus=nd, key_seed=43)
+        rng = np.random.RandomState(5)
+        dim_keys = rng.permutation(nd).astype(np.int64)
+        if hit < 1.0:
+            dim_keys = dim_keys[: int(nd * hit)]
+        dim = pandas.DataFrame({"key": dim_keys, "d0": synth.gen_f64(len(dim_keys), 11, 0),
+                                "d1": np.arange(len(dim_keys), dtype=np.int64) * 3})
+        mf, md = mpd.DataFrame(fact), mpd.DataFrame(dim)
+        left = P(mf.merge(md, on="key", how="left"))
+        inner = P(mf.merge(md, on="key", how="inner"))
+        save(
+            f"merge_n{n}_d{nd}_hit{int(hit * 100)}",
+            meta=np.array([n, nd, int(hit * 100)]),
+            dim_keys=dim_keys,
+            left=left.to_numpy(dtype=np.float64),
+            left_cols=np.array(list(left.columns)),
+            inner=inner.to_numpy(dtype=np.float64),
+        )
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""The CPU oracle (oracle/reference_path.py) pinned against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py: Modin PandasOnPython, NPartitions=4).
+
+The oracle restates Modin's partition/template logic and delegates block arithmetic to pandas like
+the reference does, on the same partition grid -- so elementwise results AND partition-ordered
+float sums must match the reference bit for bit.
+"""
+
+import glob
+import os
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import synth
+from oracle import reference_path as orc
+
+NP = 4  # NPartitions used when the golden vectors were generated
+
+
+def _load(golden_dir, pattern):
+    files = sorted(glob.glob(os.path.join(golden_dir, pattern)))
+    assert files, f"no golden files match {pattern}"
+    return [(os.path.basename(f), np.load(f, allow_pickle=False)) for f in files]
+
+
+def _bits(a):
+    a = np.asarray(a)
+    if a.dtype == np.float64:
+        return a.view(np.uint64)
+    return a
+
+
+def assert_bit_equal(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
+    if got.dtype != want.dtype:
+        got = got.astype(want.dtype)
+    assert np.array_equal(_bits(got), _bits(want)), f"{what}: not bit-identical"
+
+
+def _frame_cases(golden_dir):
+    return [(n, z) for n, z in _load(golden_dir, "frame_*.npz") if not n.endswith("_fma3.npz")]
+
+
+def test_golden_inventory(golden_dir):
+    assert len(_load(golden_dir, "frame_*.npz")) == 4
+    assert len(_load(golden_dir, "groupby_*.npz")) == 2
+    assert len(_load(golden_dir, "merge_*.npz")) == 2
+
+
+def test_map_and_binary_against_reference(golden_dir):
+    for name, z in _frame_cases(golden_dir):
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        assert_bit_equal(orc.df_abs(df, NP).to_numpy(), z["abs"], f"{name}:abs")
+        neg = orc.to_pandas(orc.map_partitions(orc.split_into_partitions(df, NP), pandas.DataFrame.__neg__))
+        assert_bit_equal(neg.to_numpy(), z["neg"], f"{name}:neg")
+        assert_bit_equal(orc.df_isna(df, NP).to_numpy(), z["isna"], f"{name}:isna")
+        assert_bit_equal(orc.df_fillna(df, 1.5, NP).to_numpy(), z["fillna"], f"{name}:fillna")
+        assert_bit_equal(orc.a_mul_b_add_c(df, 1.25, 0.5, NP).to_numpy(), z["affine"], f"{name}:affine")
+        mul = list(np.arange(1, W + 1) * 0.5)
+        add = list(np.arange(W) * 0.25)
+        assert_bit_equal(orc.a_mul_b_add_c(df, mul, add, NP).to_numpy(), z["rowvec"], f"{name}:rowvec")
+        assert_bit_equal(orc.binary_scalar(df, "lt", 0.0, NP).to_numpy(), z["lt0"], f"{name}:lt0")
+
+
+def test_three_frame_fma_against_reference(golden_dir):
+    for name, z in _load(golden_dir, "frame_*_fma3.npz"):
+        n, W, seed, nan, sb, sc = (int(x) for x in z["meta"])
+        a = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        b = synth.host_frame(n, W, seed=sb)
+        c = synth.host_frame(n, W, seed=sc)
+        assert_bit_equal(orc.a_mul_b_add_c(a, b, c, NP).to_numpy(), z["out"], f"{name}:a*b+c")
+        sub = orc.to_pandas(orc.n_ary_op([a, b], lambda l, r: l.sub(r), NP))
+        assert_bit_equal(sub.to_numpy(), z["sub"], f"{name}:sub")
+        div = orc.to_pandas(orc.n_ary_op([a, b], lambda l, r: l.truediv(r), NP))
+        assert_bit_equal(div.to_numpy(), z["div"], f"{name}:div")
+        ge = orc.to_pandas(orc.n_ary_op([a, b], lambda l, r: l.ge(r), NP))
+        assert_bit_equal(ge.to_numpy(), z["ge"], f"{name}:ge")
+
+
+def test_tree_reduce_against_reference(golden_dir):
+    for name, z in _frame_cases(golden_dir):
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        assert_bit_equal(orc.df_sum(df, NP).to_numpy(), z["sum"], f"{name}:sum")
+        assert_bit_equal(orc.df_sum(df, NP, skipna=False).to_numpy(), z["sum_noskip"], f"{name}:sum skipna=False")
+        assert_bit_equal(orc.df_sum(df, NP, min_count=1).to_numpy(), z["sum_mc1"], f"{name}:sum min_count=1")
+        assert_bit_equal(orc.df_mean(df, NP).to_numpy(), z["mean"], f"{name}:mean")
+        assert_bit_equal(orc.df_min(df, NP).to_numpy(), z["min"], f"{name}:min")
+        assert_bit_equal(orc.df_max(df, NP).to_numpy(), z["max"], f"{name}:max")
+        assert_bit_equal(orc.df_count(df, NP).to_numpy(), z["count"], f"{name}:count")
+
+
+def test_groupby_against_reference(golden_dir):
+    for name, z in _load(golden_dir, "groupby_*.npz"):
+        n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, V, seed=seed, nan_per_64k=nan, key_modulus=G, key_seed=kseed)
+        s = orc.groupby_reduce(df, "key", "sum", NP)
+        assert_bit_equal(s.index.to_numpy(), z["keys"], f"{name}:keys")
+        assert_bit_equal(s.to_numpy(), z["sum"], f"{name}:sum")
+        assert_bit_equal(orc.groupby_reduce(df, "key", "count", NP).to_numpy(), z["count"], f"{name}:count")
+        assert_bit_equal(orc.groupby_reduce(df, "key", "size", NP).to_numpy(), z["size"], f"{name}:size")
+        assert_bit_equal(orc.groupby_reduce(df, "key", "mean", NP).to_numpy(), z["mean"], f"{name}:mean")
+
+
+def test_merge_against_reference(golden_dir):
+    for name, z in _load(golden_dir, "merge_*.npz"):
+        n, nd, hit = (int(x) for x in z["meta"])
+        fact = synth.host_frame(n, 3, seed=42, key_modulus=nd, key_seed=43)
+        dim_keys = z["dim_keys"]
+        dim = pandas.DataFrame({"key": dim_keys, "d0": synth.gen_f64(len(dim_keys), 11, 0),
+                                "d1": np.arange(len(dim_keys), dtype=np.int64) * 3})  # fmt: skip
+        left = orc.broadcast_merge(fact, dim, "key", "left", NP)
+        assert list(left.columns) == [str(c) for c in z["left_cols"]]
+        assert_bit_equal(left.to_numpy(dtype=np.float64), z["left"], f"{name}:left")
+        inner = orc.broadcast_merge(fact, dim, "key", "inner", NP)
+        assert_bit_equal(inner.to_numpy(dtype=np.float64), z["inner"], f"{name}:inner")
+
+
+def test_oracle_threads_do_not_change_results():
+    df = synth.host_frame(5000, 4, seed=1, nan_per_64k=500)
+    a = orc.df_sum(df, 8, threads=1).to_numpy()
+    b = orc.df_sum(df, 8, threads=4).to_numpy()
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_partition_grid_matches_reference_rule():
+    # modin/core/storage_formats/pandas/utils.py:28-58: chunk = max(ceil(n / NPartitions), 32)
+    assert orc.compute_chunksize(1_000_000, 8, 32) == 125_000
+    assert orc.compute_chunksize(100, 8, 32) == 32
+    grid = orc.split_into_partitions(synth.host_frame(1000, 4), 4)
+    assert [len(r[0]) for r in grid] == [250, 250, 250, 250] and all(len(r) == 1 for r in grid)
