@@ -22,6 +22,7 @@ torch is used only as the allocator / stream owner (``torch.empty`` on the devic
 
 from __future__ import annotations
 
+import warnings
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -116,8 +117,12 @@ class DeviceColumn:
         arr = np.ascontiguousarray(arr)
         dtype = arr.dtype
         dtype_code(dtype)
+        target = current_device()  # raises (no CPU fallback) before any host work
         host = arr.view(np.uint8) if dtype == np.bool_ else arr
-        dev = t.from_numpy(host).to(current_device(), non_blocking=False)
+        with warnings.catch_warnings():
+            # pandas copy-on-write hands out read-only arrays; they are only read for the H2D copy
+            warnings.simplefilter("ignore", UserWarning)
+            dev = t.from_numpy(host).to(target, non_blocking=False)
         return cls(dev, dtype)
 
     def to_numpy(self) -> np.ndarray:

@@ -61,7 +61,8 @@ __device__ __forceinline__ TO apply(TI a, TI b, TI c, TI s0, TI s1) {
     if constexpr (F) return (TO)fabs(a);
     else return (TO)(a < 0 ? (TI)(0ULL - (unsigned long long)a) : a);
   } else if constexpr (OP == MB200_OP_NEG) {
-    if constexpr (F) return (TO)(-a);
+    // sign-bit flip (like numpy/x86 xorpd): `-a` as arithmetic would not flip the sign of a NaN
+    if constexpr (F) return (TO)__longlong_as_double(__double_as_longlong(a) ^ (long long)0x8000000000000000ULL);
     else return (TO)(TI)(0ULL - (unsigned long long)a);
   } else if constexpr (OP == MB200_OP_ISNA) {
     return (TO)(a != a);

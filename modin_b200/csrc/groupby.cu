@@ -138,6 +138,21 @@ __device__ __forceinline__ int probe_insert(const GbParams& p, long long k) {
   }
 }
 
+// Read-only lookup: dense group id of `k`, or -1 if the probe chain ends at an empty or
+// in-flight slot (the caller then takes the serialized insert path).
+__device__ __forceinline__ int probe_find(const GbParams& p, long long k) {
+  unsigned int slot = hash_key(k) & p.mask;
+  for (long long probes = 0; probes <= p.cap; ++probes) {
+    long long sk;
+    int g;
+    ld_slot(&p.slots[slot], sk, g);
+    if (g < 0) return -1;
+    if (sk == k) return g;
+    slot = (slot + 1) & p.mask;
+  }
+  return -1;
+}
+
 template <int VARIANT, bool PARTIAL>
 __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
   __shared__ double s_tile[kGbWarps][8 * kColStride];
@@ -160,11 +175,28 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
         x[c] = (c < nc && valid) ? ldg_stream_f64(static_cast<const double*>(p.vals[c]) + row, pol) : 0.0;
     }
     // ---- probe (one lane per distinct key in the warp)
-    k = valid ? k : __shfl_sync(0xffffffffu, k, 0);
+    {
+      // rows past the end borrow lane 0's key (lane 0 is always valid in a live chunk) so that they join
+      // its peer group and never become leaders; the shuffle is executed by ALL lanes.
+      const long long k0 = __shfl_sync(0xffffffffu, k, 0);
+      k = valid ? k : k0;
+    }
     const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
     const int leader = __ffs(peers) - 1;
-    int gid = 0;
-    if (lane == leader) gid = probe_insert(p, k);
+    const bool is_leader = (lane == leader);
+    // fast path: read-only lookup by every leader in parallel (the steady state once the table is warm)
+    int gid = -1;
+    if (is_leader) gid = probe_find(p, k);
+    // slow path: leaders that met an empty / in-flight slot insert ONE LANE AT A TIME, so a lane that
+    // spins on a slot lock can only be waiting for another warp (which makes progress independently),
+    // never for a diverged lane of its own warp.
+    unsigned int need = __ballot_sync(0xffffffffu, is_leader && gid < 0);
+    while (need) {
+      const int l = __ffs(need) - 1;
+      if (lane == l) gid = probe_insert(p, k);
+      need &= need - 1;
+      __syncwarp();
+    }
     gid = __shfl_sync(0xffffffffu, gid, leader);
     const bool live = valid && gid < gcap;
 

@@ -244,31 +244,80 @@ class DevReduce(DevFn):
         self.op = op
         self.phase = phase  # "map" | "reduce"
 
-    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+    def _kernel_op(self):
+        if self.phase == "reduce" and self.op == "count":
+            return "sum"  # counts add up (qc.py:976: TreeReduce.register(count, sum))
+        return self.op
+
+    def _check(self, block, axis, min_count):
         _check_block(block, f"DevReduce({self.op})")
         if axis not in (0, "index", None):
             raise NotImplementedError("row-wise (axis=1) reductions are not on the B200 path")
         if min_count and min_count > 1:
             raise NotImplementedError("sum(min_count>1) is a full-axis Reduce in the reference; not on the B200 path")
-        W = len(block.cols)
-        if W == 0:
+
+    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+        self._check(block, axis, min_count)
+        if not block.cols:
             return _reduced_block([], block.columns)
-        kop = self.op
-        if self.phase == "reduce" and self.op == "count":
-            kop = "sum"  # counts add up (qc.py:976: TreeReduce.register(count, sum))
-        variant = ReduceVariant.get()
-        vals, cnts = ops.reduce_columns(kop if kop != "count" else "count", block.cols, skipna=bool(skipna),
-                                        variant=variant)  # fmt: skip
+        kop = self._kernel_op()
+        vals, cnts = ops.reduce_columns(kop, block.cols, skipna=bool(skipna), variant=ReduceVariant.get())
         out = []
         for j, c in enumerate(block.cols):
             if kop == "count":
                 out.append(DeviceColumn(cnts[j], np.int64))
             elif kop == "sum" and min_count == 1 and c.dtype == np.float64 and skipna:
-                # all-NaN column -> NaN: 0/0 * 0 trick avoided; patch on host-free path via where(count==0)
+                # pandas min_count=1: no valid value -> NaN.  Works through the tree exactly like the
+                # reference: an all-NaN block yields a NaN partial, which the reduce phase skips.
                 out.append(_nan_where_empty(vals[j], cnts[j]))
             else:
                 out.append(DeviceColumn(vals[j], c.dtype))
         return _reduced_block(out, block.columns)
+
+    def run_distributed(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+        """Reduce-phase body when rows are sharded over several GPUs: local reduction of this rank's
+        partials, then ONE packed all_reduce of the W-vector (sum / min / max) -- the collective that
+        replaces the reference's gather-to-one-task (axis_partition.py:445-452)."""
+        from . import dist
+
+        self._check(block, axis, min_count)
+        if not block.cols:
+            return _reduced_block([], block.columns)
+        t = ops.torch_mod()
+        kop = self._kernel_op()
+        vals, cnts = ops.reduce_columns(kop, block.cols, skipna=bool(skipna), variant=ReduceVariant.get())
+        W = len(block.cols)
+        if kop == "count":
+            dist.all_reduce_values(cnts, ["sum"] * W)
+            out = [DeviceColumn(c, np.int64) for c in cnts]
+        elif kop == "sum":
+            dist.all_reduce_values(vals, ["sum"] * W)
+            if min_count == 1 and skipna:
+                dist.all_reduce_values(cnts, ["sum"] * W)
+                vals = [t.where(n == 0, t.full_like(v, float("nan")), v) if v.dtype == t.float64 else v
+                        for v, n in zip(vals, cnts)]  # fmt: skip
+            out = [DeviceColumn(v, c.dtype) for v, c in zip(vals, block.cols)]
+        else:
+            # min / max: a shard without valid values must not poison the others -> +-inf locally,
+            # NaN decided from the job-wide counts (pandas: all-NaN -> NaN; skipna=False & any NaN -> NaN)
+            nrows = t.full((1,), block.nrows, dtype=t.int64, device=vals[0].device)
+            rows = [nrows.clone() for _ in range(W)]
+            for j, c in enumerate(block.cols):
+                if c.dtype == np.float64:
+                    inf = float("inf") if kop == "min" else float("-inf")
+                    vals[j] = t.where(cnts[j] > 0, t.nan_to_num(vals[j], nan=inf), t.full_like(vals[j], inf))
+            dist.all_reduce_values(vals, [kop] * W)
+            dist.all_reduce_values(cnts + rows, ["sum"] * (2 * W))
+            out = []
+            for j, c in enumerate(block.cols):
+                v = vals[j]
+                if c.dtype == np.float64:
+                    bad = (cnts[j] == 0) if skipna else ((cnts[j] == 0) | (cnts[j] < rows[j]))
+                    v = t.where(bad, t.full_like(v, float("nan")), v)
+                out.append(DeviceColumn(v, c.dtype))
+        res = _reduced_block(out, block.columns)
+        res.replicated = True
+        return res
 
 
 def _nan_where_empty(val, cnt):
@@ -311,16 +360,34 @@ class DevMeanReduce(DevFn):
 
     op = "mean_reduce"
 
-    def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
-        _check_block(block, "DevMeanReduce")
+    def _local(self, block):
         W = len(block.cols) // 2
         sums, _ = ops.reduce_columns("sum", block.cols[:W], skipna=False, variant=1)
         cnts, _ = ops.reduce_columns("sum", block.cols[W:], skipna=False, variant=1)
+        labels = pandas.Index([t[1] for t in block.columns[:W]]) if isinstance(block.columns, pandas.MultiIndex) \
+            else block.columns[:W]  # fmt: skip
+        return sums, cnts, labels
+
+    @staticmethod
+    def _divide(sums, cnts, labels):
         s = [DeviceColumn(v, np.float64) for v in sums]
         c = ops.cast_columns_f64([DeviceColumn(v, np.int64) for v in cnts])
-        labels = pandas.Index([t[1] for t in block.columns]) if isinstance(block.columns, pandas.MultiIndex) else \
-            block.columns[:W]  # fmt: skip
         return _reduced_block(ops.map_columns("div", s, c), labels)
+
+    def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
+        _check_block(block, "DevMeanReduce")
+        return self._divide(*self._local(block))
+
+    def run_distributed(self, block, *args, axis=0, skipna=True, **kwargs):
+        """Sums and counts are all_reduced BEFORE the division (mean of shard means would be wrong)."""
+        from . import dist
+
+        _check_block(block, "DevMeanReduce")
+        sums, cnts, labels = self._local(block)
+        dist.all_reduce_values(sums + cnts, ["sum"] * (len(sums) + len(cnts)))
+        res = self._divide(sums, cnts, labels)
+        res.replicated = True
+        return res
 
 
 # ------------------------------------------------------------------ GroupByReduce functors
@@ -395,32 +462,64 @@ class DevGroupbyReduce(DevFn):
         self.agg = agg
         self.op = f"groupby_{agg}_reduce"
 
-    def __call__(self, block, *args, partition_idx=0, **kwargs):
+    def _merge(self, keys, cols):
+        """Regroup partial rows by key -> ascending unique keys + merged partial columns (same layout
+        as the input: sums | counts | size, depending on the aggregation)."""
+        agg = self.agg
+        n = len(keys)
+        if agg == "sum":
+            k, s, _, _ = ops.hash_aggregate([(keys, cols, None, None)], _lib.GB_SUM, n, partial=True)
+            return k, list(s)
+        if agg == "count":
+            # int64 partial counts are merged through the count accumulators (values are ignored)
+            dummy = [ops.cast_columns_f64([c])[0] for c in cols]
+            k, _, c, _ = ops.hash_aggregate([(keys, dummy, cols, None)], _lib.GB_COUNT, n, partial=True)
+            return k, list(c)
+        if agg == "size":
+            k, _, _, z = ops.hash_aggregate([(keys, [], None, cols[0])], _lib.GB_SIZE, n, partial=True)
+            return k, [z]
+        W = len(cols) // 2
+        k, s, c, _ = ops.hash_aggregate([(keys, cols[:W], cols[W:], None)], _lib.GB_SUM | _lib.GB_COUNT, n,
+                                        partial=True)  # fmt: skip
+        return k, list(s) + list(c)
+
+    def _finalize(self, k, cols, columns, key_label):
+        if self.agg == "mean":
+            W = len(cols) // 2
+            cf = ops.cast_columns_f64(cols[W:])
+            labels = pandas.Index([t[1] for t in columns[:W]])
+            return DeviceBlock(ops.map_columns("div", cols[:W], cf) if len(k) else cols[:W], labels, nrows=len(k),
+                               index_cols=[k], index_names=[key_label])  # fmt: skip
+        return DeviceBlock(cols, columns, nrows=len(k), index_cols=[k], index_names=[key_label])
+
+    def _unpack(self, block):
         _check_block(block, self.op)
         if not block.index_cols:
             raise ValueError("groupby reduce expects partial tables keyed by device index columns")
-        keys = block.index_cols[0]
-        key_label = block.index_names[0] if block.index_names else None
-        agg = self.agg
-        if agg == "sum":
-            k, s, _, _ = ops.hash_aggregate([(keys, block.cols, None, None)], _lib.GB_SUM, len(keys), partial=True)
-            return DeviceBlock(s, block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
-        if agg == "count":
-            # counts are int64 partials: merged through the count accumulators
-            zeros = [ops.cast_columns_f64([c])[0] for c in block.cols]
-            k, _, c, _ = ops.hash_aggregate([(keys, zeros, block.cols, None)], _lib.GB_COUNT, len(keys), partial=True)
-            return DeviceBlock(c, block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
-        if agg == "size":
-            k, _, _, z = ops.hash_aggregate([(keys, [], None, block.cols[0])], _lib.GB_SIZE, len(keys), partial=True)
-            return DeviceBlock([z], block.columns, nrows=len(k), index_cols=[k], index_names=[key_label])
-        # mean
-        W = len(block.cols) // 2
-        k, s, c, _ = ops.hash_aggregate([(keys, block.cols[:W], block.cols[W:], None)], _lib.GB_SUM | _lib.GB_COUNT,
-                                        len(keys), partial=True)  # fmt: skip
-        cf = ops.cast_columns_f64(c)
-        labels = pandas.Index([t[1] for t in block.columns[:W]])
-        return DeviceBlock(ops.map_columns("div", s, cf), labels, nrows=len(k), index_cols=[k],
-                           index_names=[key_label])  # fmt: skip
+        return block.index_cols[0], (block.index_names[0] if block.index_names else None)
+
+    def __call__(self, block, *args, partition_idx=0, **kwargs):
+        keys, key_label = self._unpack(block)
+        k, cols = self._merge(keys, block.cols)
+        return self._finalize(k, cols, block.columns, key_label)
+
+    def run_distributed(self, block, *args, partition_idx=0, **kwargs):
+        """The groupby shuffle: merge this rank's partial tables, range-partition the merged table by
+        key over the ranks (all-to-all of <= G pre-aggregated rows per GPU, never raw rows), merge
+        what arrives.  Rank r ends up owning the r-th key range, ascending -- the concatenation over
+        ranks is the reference's key-sorted result."""
+        from . import dist
+
+        keys, key_label = self._unpack(block)
+        k, cols = self._merge(keys, block.cols)
+        rk, rcols = dist.exchange_by_key_range(k.data, [c.data for c in cols])
+        rkeys = DeviceColumn(rk, np.int64)
+        rc = [DeviceColumn(t_, c.dtype) for t_, c in zip(rcols, cols)]
+        if len(rkeys):
+            k2, cols2 = self._merge(rkeys, rc)
+        else:
+            k2, cols2 = rkeys, rc
+        return self._finalize(k2, cols2, block.columns, key_label)
 
 
 # ------------------------------------------------------------------ broadcast merge functor

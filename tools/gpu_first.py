@@ -68,9 +68,9 @@ def check(name, ok, detail=""):
 
 
 # ------------------------------------------------------------------ parity (small, odd sizes)
-def parity():
+def parity(only_groupby=False):
     rng = np.random.RandomState(0)
-    for n in (1, 7, 4096, 4097, 100003):
+    for n in (() if only_groupby else (1, 7, 4096, 4097, 100003)):
         W = 3
         A = rng.randn(W, n)
         B = rng.randn(W, n)
@@ -151,7 +151,7 @@ def parity():
             check(f"reduce i64 min v{variant} n={n}", np.array_equal(oi.cpu().numpy(), I.min(axis=1)))
 
     # sort
-    for n in (2, 255, 256, 5000, 300001):
+    for n in (() if only_groupby else (2, 255, 256, 5000, 300001)):
         k = rng.randint(-2**62, 2**62, size=n).astype(np.int64)
         k[: n // 3] = rng.randint(-5, 5, size=n // 3)
         pl = np.arange(n, dtype=np.int64)
@@ -247,8 +247,16 @@ def bandwidth(log2n):
     ref = torch.stack([c.sum() for c in cols]).cpu().numpy()
     f()
     got = oval.cpu().numpy()
-    # groupby: G = 1e6 keys, V = 8
     del out
+
+
+def bandwidth_groupby(log2n):
+    n = 1 << log2n
+    W = 8
+    cols = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(W)]
+    for i, c in enumerate(cols):
+        _lib.check(lib.mb200_gen_f64(c.data_ptr(), n, 42, i, 0, 0, st))
+    cp = cols_ptr(cols)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     for G in (1000, 1_000_000):
         _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, G, st))
@@ -273,7 +281,11 @@ if __name__ == "__main__":
     what = sys.argv[2] if len(sys.argv) > 2 else "all"
     if what in ("all", "parity"):
         parity()
+    if what == "gbparity":
+        parity(only_groupby=True)
     if what in ("all", "bw"):
         bandwidth(log2n)
+    if what in ("all", "gbbw"):
+        bandwidth_groupby(log2n)
     report(done=True, failures=FAIL, launches=lib.mb200_launch_count())
     sys.exit(1 if FAIL else 0)
