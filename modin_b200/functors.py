@@ -205,10 +205,20 @@ class DevAffine(DevFn):
         W = len(block.cols)
         mul = list(self.mul) if isinstance(self.mul, (list, tuple, np.ndarray)) else [self.mul] * W
         add = list(self.add) if isinstance(self.add, (list, tuple, np.ndarray)) else [self.add] * W
-        if any(c.dtype != np.float64 for c in block.cols):
-            raise NotImplementedError("fused affine map needs float64 columns")
-        return block.with_cols(ops.map_columns("affine", block.cols, s0=[float(m) for m in mul],
-                                               s1=[float(a) for a in add]))  # fmt: skip
+        if block.nrows == 0 or not block.cols:
+            return block
+        is_int = lambda v: isinstance(v, (int, np.integer)) and not isinstance(v, bool)  # noqa: E731
+        cols, s0, s1 = [], [], []
+        for c, m, a in zip(block.cols, mul, add):
+            if c.dtype == np.int64 and is_int(m) and is_int(a):
+                cols.append(c)  # int64 * int + int stays int64 (wrapping), like pandas
+                s0.append(int(m))
+                s1.append(int(a))
+            else:
+                cols.append(ops.cast_columns_f64([c])[0])
+                s0.append(float(m))
+                s1.append(float(a))
+        return block.with_cols(ops.map_columns("affine", cols, s0=s0, s1=s1))
 
 
 class DevFma3(DevFn):
@@ -437,7 +447,8 @@ class DevGroupbyMap(DevFn):
             vals = ops.cast_columns_f64(vals) if self.agg in ("count", "mean") else vals
             if any(v.dtype != np.float64 for v in vals):
                 raise NotImplementedError("device groupby.sum aggregates float64 value columns only")
-        keys, sums, cnts, sizes = ops.hash_aggregate([(key, vals)], flags, self.capacity_hint)
+        cap = max(1024, min(self.capacity_hint, block.nrows))
+        keys, sums, cnts, sizes = ops.hash_aggregate([(key, vals)], flags, cap)
         return _partial_block(self.agg, keys, key_label, sums, cnts, sizes, labels)
 
 

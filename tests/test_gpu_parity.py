@@ -1,0 +1,269 @@
+"""GPU parity tests (``-m gpu``): the B200 execution, driven through its public pandas-style API
+(modin_b200.pandas -> query compiler -> templates -> partitions -> C ABI -> sm_100a kernels),
+against (1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on
+fresh seeded inputs.
+
+Tolerances: elementwise / predicates / min / max / count / size / keys / merge are
+BIT-EXACT (NaN == NaN); float sums and means satisfy
+``|got - ref| <= 4 * log2(n) * 2**-53 * sum|x|`` per output value.
+"""
+
+import glob
+import math
+import os
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import synth
+from oracle import reference_path as orc
+
+pytestmark = pytest.mark.gpu
+
+EPS = 2.0**-53
+
+
+def bpd():
+    import modin_b200.pandas as m
+
+    return m
+
+
+@pytest.fixture(autouse=True)
+def _four_partitions():
+    """The reference's own tests force NPartitions=4 (modin/tests/pandas/dataframe/test_reduce.py:41)."""
+    from modin_b200 import config
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    yield
+    config.NPartitions.put(old)
+
+
+def _load(golden_dir, pattern):
+    files = sorted(glob.glob(os.path.join(golden_dir, pattern)))
+    assert files
+    return [(os.path.basename(f), np.load(f, allow_pickle=False)) for f in files]
+
+
+def assert_exact(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
+    if want.dtype.kind == "f" or got.dtype.kind == "f":
+        g, w = got.astype(np.float64), want.astype(np.float64)
+        both_nan = np.isnan(g) & np.isnan(w)
+        same = (g.view(np.uint64) == w.view(np.uint64)) | both_nan
+        assert same.all(), f"{what}: {np.count_nonzero(~same)} elements differ (bit-exact, NaN==NaN)"
+    else:
+        assert np.array_equal(got, want), f"{what}: integer/bool mismatch"
+
+
+def sum_tolerance(abs_sum, n):
+    return 4.0 * max(1.0, math.log2(max(n, 2))) * EPS * abs_sum + 1e-300
+
+
+def assert_sum_close(got, want, abs_sums, n, what):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{what}: shape"
+    tol = np.array([sum_tolerance(a, n) for a in np.asarray(abs_sums, dtype=np.float64).ravel()]).reshape(got.shape)
+    both_nan = np.isnan(got) & np.isnan(want)
+    ok = both_nan | (np.abs(got - want) <= tol) | (got == want)
+    assert ok.all(), f"{what}: max err {np.nanmax(np.abs(got - want))} vs tol {tol.max()}"
+
+
+# ---------------------------------------------------------------------------------------------
+def test_device_generators_match_numpy_twin():
+    from modin_b200 import ops
+
+    for n, off in ((1, 0), (1000, 0), (4097, 12345)):
+        a = ops.gen_f64(n, 42, 3, off, 1000).to_numpy()
+        assert_exact(a, synth.gen_f64(n, 42, 3, off, 1000), f"gen_f64 n={n}")
+        k = ops.gen_i64(n, 43, 0, 1000, off).to_numpy()
+        assert np.array_equal(k, synth.gen_i64(n, 43, 0, 1000, off))
+
+
+def test_map_binary_vs_reference_golden(golden_dir):
+    m = bpd()
+    for name, z in [(n, z) for n, z in _load(golden_dir, "frame_*.npz") if not n.endswith("_fma3.npz")]:
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        df = m.DataFrame(pdf)
+        assert_exact(df.abs()._to_pandas().to_numpy(), z["abs"], f"{name}:abs")
+        assert_exact((-df)._to_pandas().to_numpy(), z["neg"], f"{name}:neg")
+        assert_exact(df.isna()._to_pandas().to_numpy(), z["isna"], f"{name}:isna")
+        assert_exact(df.fillna(1.5)._to_pandas().to_numpy(), z["fillna"], f"{name}:fillna")
+        assert_exact((df * 1.25 + 0.5)._to_pandas().to_numpy(), z["affine"], f"{name}:affine (fused)")
+        mul = list(np.arange(1, W + 1) * 0.5)
+        add = list(np.arange(W) * 0.25)
+        assert_exact((df * mul + add)._to_pandas().to_numpy(), z["rowvec"], f"{name}:row-vector affine")
+        assert_exact((df < 0.0)._to_pandas().to_numpy(), z["lt0"], f"{name}:lt0")
+
+
+def test_three_frame_fma_vs_reference_golden(golden_dir):
+    m = bpd()
+    for name, z in _load(golden_dir, "frame_*_fma3.npz"):
+        n, W, seed, nan, sb, sc = (int(x) for x in z["meta"])
+        a = m.DataFrame(synth.host_frame(n, W, seed=seed, nan_per_64k=nan))
+        b = m.DataFrame(synth.host_frame(n, W, seed=sb))
+        c = m.DataFrame(synth.host_frame(n, W, seed=sc))
+        assert_exact((a * b + c)._to_pandas().to_numpy(), z["out"], f"{name}:a*b+c (fused, two roundings)")
+        assert_exact((a - b)._to_pandas().to_numpy(), z["sub"], f"{name}:sub")
+        assert_exact((a / b)._to_pandas().to_numpy(), z["div"], f"{name}:div")
+        assert_exact((a >= b)._to_pandas().to_numpy(), z["ge"], f"{name}:ge")
+
+
+def test_tree_reduce_vs_reference_golden(golden_dir):
+    m = bpd()
+    for name, z in [(n, z) for n, z in _load(golden_dir, "frame_*.npz") if not n.endswith("_fma3.npz")]:
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        abs_sums = np.nansum(np.abs(pdf.to_numpy()), axis=0)
+        df = m.DataFrame(pdf)
+        assert_sum_close(df.sum().to_numpy(), z["sum"], abs_sums, n, f"{name}:sum")
+        assert_sum_close(df.sum(skipna=False).to_numpy(), z["sum_noskip"], abs_sums, n, f"{name}:sum skipna=False")
+        assert_sum_close(df.sum(min_count=1).to_numpy(), z["sum_mc1"], abs_sums, n, f"{name}:sum min_count=1")
+        cnt = np.maximum(z["count"], 1)
+        assert_sum_close(df.mean().to_numpy(), z["mean"], abs_sums / cnt, n, f"{name}:mean")
+        assert_exact(df.min().to_numpy(), z["min"], f"{name}:min")
+        assert_exact(df.max().to_numpy(), z["max"], f"{name}:max")
+        assert_exact(df.count().to_numpy(), z["count"], f"{name}:count")
+        assert df.count().dtype == np.int64
+
+
+def test_groupby_vs_reference_golden(golden_dir):
+    m = bpd()
+    for name, z in _load(golden_dir, "groupby_*.npz"):
+        n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, V, seed=seed, nan_per_64k=nan, key_modulus=G, key_seed=kseed)
+        df = m.DataFrame(pdf)
+        g = df.groupby("key")
+        s = g.sum()._to_pandas()
+        assert_exact(s.index.to_numpy(), z["keys"], f"{name}:keys sorted")
+        assert s.index.name == "key" and list(s.columns) == [f"c{i}" for i in range(V)]
+        abs_by_group = pdf.drop(columns="key").abs().groupby(pdf["key"]).sum().to_numpy()
+        assert_sum_close(s.to_numpy(), z["sum"], abs_by_group, n, f"{name}:sum")
+        assert_exact(g.count()._to_pandas().to_numpy(), z["count"], f"{name}:count")
+        assert_exact(g.size()._to_pandas().to_numpy(), z["size"], f"{name}:size")
+        cnt = np.maximum(z["count"], 1)
+        assert_sum_close(g.mean()._to_pandas().to_numpy(), z["mean"], abs_by_group / cnt, n, f"{name}:mean")
+
+
+def test_merge_vs_reference_golden(golden_dir):
+    m = bpd()
+    for name, z in _load(golden_dir, "merge_*.npz"):
+        n, nd, hit = (int(x) for x in z["meta"])
+        fact = synth.host_frame(n, 3, seed=42, key_modulus=nd, key_seed=43)
+        dim_keys = z["dim_keys"]
+        dim = pandas.DataFrame({"key": dim_keys, "d0": synth.gen_f64(len(dim_keys), 11, 0),
+                                "d1": np.arange(len(dim_keys), dtype=np.int64) * 3})  # fmt: skip
+        left = m.DataFrame(fact).merge(m.DataFrame(dim), on="key", how="left")._to_pandas()
+        assert list(left.columns) == [str(c) for c in z["left_cols"]]
+        assert_exact(left.to_numpy(dtype=np.float64), z["left"], f"{name}:left")
+        assert isinstance(left.index, pandas.RangeIndex) and len(left) == n
+        inner = m.DataFrame(fact).merge(m.DataFrame(dim), on="key", how="inner")._to_pandas()
+        assert_exact(inner.to_numpy(dtype=np.float64), z["inner"], f"{name}:inner")
+
+
+# ------------------------------------------------------------------ fresh inputs vs the oracle
+@pytest.mark.parametrize("n,W,nan", [(1, 1, 0), (31, 3, 0), (33, 2, 30000), (100003, 8, 500), (262144, 16, 0)])
+def test_against_oracle_various_shapes(n, W, nan):
+    m = bpd()
+    pdf = synth.host_frame(n, W, seed=5, nan_per_64k=nan)
+    df = m.DataFrame(pdf)
+    NPART = 4
+    assert_exact(df.abs()._to_pandas().to_numpy(), orc.df_abs(pdf, NPART).to_numpy(), "abs")
+    assert_exact((df * 0.75 + 2.0)._to_pandas().to_numpy(), orc.a_mul_b_add_c(pdf, 0.75, 2.0, NPART).to_numpy(), "affine")
+    abs_sums = np.nansum(np.abs(pdf.to_numpy()), axis=0)
+    assert_sum_close(df.sum().to_numpy(), orc.df_sum(pdf, NPART).to_numpy(), abs_sums, n, "sum")
+    assert_exact(df.count().to_numpy(), orc.df_count(pdf, NPART).to_numpy(), "count")
+    assert_exact(df.min().to_numpy(), orc.df_min(pdf, NPART).to_numpy(), "min")
+    assert_exact(df.max().to_numpy(), orc.df_max(pdf, NPART).to_numpy(), "max")
+
+
+def test_reduce_variants_agree():
+    """TMA-staged and direct-load reductions are two schedules of the same arithmetic."""
+    from modin_b200 import config
+
+    m = bpd()
+    pdf = synth.host_frame(300007, 5, seed=9, nan_per_64k=100)
+    abs_sums = np.nansum(np.abs(pdf.to_numpy()), axis=0)
+    res = []
+    for v in (0, 1):
+        config.ReduceVariant.put(v)
+        res.append(m.DataFrame(pdf).sum().to_numpy())
+    config.ReduceVariant.put(0)
+    assert_sum_close(res[0], res[1], abs_sums, len(pdf), "variants")
+
+
+def test_int64_columns_are_exact():
+    m = bpd()
+    rng = np.random.RandomState(3)
+    pdf = pandas.DataFrame({"a": rng.randint(-10**12, 10**12, 70001), "b": rng.randint(-5, 5, 70001)}).astype("int64")
+    df = m.DataFrame(pdf)
+    assert_exact(df.sum().to_numpy(), pdf.sum().to_numpy(), "int sum")
+    assert_exact(df.min().to_numpy(), pdf.min().to_numpy(), "int min")
+    assert_exact(df.abs()._to_pandas().to_numpy(), pdf.abs().to_numpy(), "int abs")
+    assert_exact((df * 3 + 1)._to_pandas().to_numpy(), (pdf * 3 + 1).to_numpy(), "int affine (unfused)")
+    assert_exact((df == 0)._to_pandas().to_numpy(), (pdf == 0).to_numpy(), "int eq")
+
+
+def test_edge_cases_and_errors():
+    m = bpd()
+    # all-NaN column, +-inf, -0.0
+    pdf = pandas.DataFrame({"a": [np.nan, np.nan, np.nan], "b": [np.inf, 1.0, -0.0], "c": [-np.inf, np.inf, 2.0]})
+    df = m.DataFrame(pdf)
+    assert_exact(df.sum().to_numpy(), pdf.sum().to_numpy(), "sum with inf / all-NaN")
+    assert_exact(df.sum(min_count=1).to_numpy(), pdf.sum(min_count=1).to_numpy(), "min_count=1 all-NaN -> NaN")
+    assert_exact(df.min().to_numpy(), pdf.min().to_numpy(), "min all-NaN -> NaN")
+    assert_exact(df.max(skipna=False).to_numpy(), pdf.max(skipna=False).to_numpy(), "max skipna=False")
+    assert_exact(df.abs()._to_pandas().to_numpy(), pdf.abs().to_numpy(), "abs(-0.0) = +0.0")
+    # errors surface like pandas / the reference does
+    with pytest.raises(ValueError):
+        df.fillna()
+    with pytest.raises(KeyError):
+        df.groupby("nope")
+    with pytest.raises(TypeError):
+        m.DataFrame(pandas.DataFrame({"s": ["x", "y"]}))
+    with pytest.raises(NotImplementedError):
+        df.merge(df, how="outer", on="a")
+
+
+def test_groupby_with_empty_and_skewed_partitions():
+    """cf. test_groupby_with_empty_partition (modin/tests/core/storage_formats/pandas/test_internals.py:863)."""
+    m = bpd()
+    n = 9001
+    keys = np.zeros(n, dtype=np.int64)
+    keys[-3:] = [7, 7, -2]  # one giant group + tiny ones, all in the last partition
+    pdf = pandas.DataFrame({"key": keys, "v": synth.gen_f64(n, 1, 0)})
+    got = m.DataFrame(pdf).groupby("key").sum()._to_pandas()
+    want = orc.groupby_reduce(pdf, "key", "sum", 4)
+    assert_exact(got.index.to_numpy(), want.index.to_numpy(), "keys")
+    assert_sum_close(got.to_numpy(), want.to_numpy(), pdf["v"].abs().groupby(pdf["key"]).sum().to_numpy()[:, None], n, "sum")
+
+
+def test_large_scale_invariants():
+    """Properties that do not need a CPU pass over the data (SURVEY.md §8d "parity at scale")."""
+    m = bpd()
+    from modin_b200 import config
+
+    config.NPartitions.put(2)
+    n, W, G = 1 << 24, 8, 100_000
+    df = synth.device_frame(n, W, key_modulus=G, npartitions=2)
+    vals = df[[f"c{i}" for i in range(W)]]
+    col_sum = vals.sum().to_numpy()
+    col_abs = vals.abs().sum().to_numpy()
+    g = df.groupby("key")
+    gs = g.sum()._to_pandas()
+    assert len(gs) == G and gs.index.is_monotonic_increasing and gs.index[0] == 0 and gs.index[-1] == G - 1
+    assert_sum_close(gs.sum().to_numpy(), col_sum, col_abs, n, "sum of group sums == column sums")
+    sz = g.size()._to_pandas()
+    assert int(sz.sum()) == n
+    # sampled elementwise equality against the numpy twin of the generator
+    out = (vals * 1.5 + 0.25)._to_pandas()
+    rows = np.array([0, 1, 4095, 4096, n // 2, n - 1])
+    for j in range(W):
+        ref = np.array([synth.gen_f64(1, 42, j, int(r))[0] for r in rows]) * 1.5 + 0.25
+        assert_exact(out.iloc[rows, j].to_numpy(), ref, f"sampled affine col {j}")
+    mean = vals.mean().to_numpy()
+    assert np.all(np.abs(mean - col_sum / n) <= 1e-15 + 4 * EPS * col_abs / n)
