@@ -155,7 +155,9 @@ __device__ __forceinline__ int probe_find(const GbParams& p, long long k) {
 
 template <int VARIANT, bool PARTIAL>
 __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
-  __shared__ double s_tile[kGbWarps][8 * kColStride];
+  // variant 0: [8 cols][34] column tiles; variant 2: [32 rows][10] row tiles (80-byte stride: 16-byte
+  // aligned rows, conflict-free 128-bit stores)
+  __shared__ __align__(16) double s_tile[kGbWarps][32 * 10];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long nchunks = (p.nrows + 31) >> 5;
   const long long wstride = (long long)gridDim.x * kGbWarps;
@@ -211,7 +213,30 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
         for (int c = 0; c < 8; ++c)
           x[c] = (c < nc && valid) ? ldg_stream_f64(static_cast<const double*>(p.vals[c0 + c]) + row, pol) : 0.0;
       }
-      if (VARIANT == 1) {
+      if (VARIANT == 2) {
+        // One TMA bulk reduction per row: the row's (<= 8) values are laid out contiguously in shared
+        // memory and added to the group's 64-byte accumulator row by the copy engine
+        // (cp.reduce.async.bulk ... .add.f64 -> UBLKRED), i.e. ONE async op per row instead of 8 RED
+        // lanes through the LSU.  NaNs are replaced by +0.0 (adding zero == skipping).
+        double* myrow = s_tile[warp] + lane * 10;
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // my previous row has been read
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          double2 d;
+          d.x = (c < nc && x[c] == x[c]) ? x[c] : 0.0;
+          d.y = (c + 1 < nc && x[c + 1] == x[c + 1]) ? x[c + 1] : 0.0;
+          *reinterpret_cast<double2*>(myrow + c) = d;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (live) {
+          const unsigned int bytes = (unsigned int)(((nc + 1) >> 1) * 16);
+          double* dst = p.acc + (size_t)gid * p.vstride + c0;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst),
+                       "r"(smem_u32(myrow)), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      } else if (VARIANT == 1) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < nc && live) {
@@ -252,6 +277,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
       }
     }
   }
+  if (VARIANT == 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void gb_init_kernel(Slot* slots, long long cap, GbMeta* meta) {
@@ -319,7 +345,9 @@ static long long next_pow2(long long v) {
 
 static int gb_variant_from_env() {
   const char* e = getenv("MB200_GB_VARIANT");  // read per call: lets one process compare variants
-  return (e && e[0] == '1') ? 1 : 0;
+  if (e && e[0] == '1') return 1;
+  if (e && e[0] == '2') return 2;
+  return 0;
 }
 
 static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const* vals, const void* const* pcnt,
@@ -350,7 +378,9 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   p.psize = psize;
   if (partial && (t->flags & MB200_GB_SIZE) && !psize) return fail("groupby", "null partial size column");
   p.nrows = nrows;
-  const int variant = gb_variant_from_env();
+  int variant = gb_variant_from_env();
+  // the bulk-reduce variant covers plain sums of raw rows; counts / partial merges use variant 0
+  if (variant == 2 && (partial || (t->flags & MB200_GB_COUNT) || !(t->flags & MB200_GB_SUM))) variant = 0;
   int occ = 0;
   const long long nchunks = (nrows + 31) / 32;
 #define MB_GB_LAUNCH(V, P)                                                                                  \
@@ -361,7 +391,9 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
     if (grid > need) grid = need;                                                                           \
     gb_accumulate_kernel<V, P><<<(unsigned)grid, kGbThreads, 0, st>>>(p);                                   \
   } while (0)
-  if (variant == 0) {
+  if (variant == 2) {
+    MB_GB_LAUNCH(2, false);
+  } else if (variant == 0) {
     if (partial) MB_GB_LAUNCH(0, true);
     else MB_GB_LAUNCH(0, false);
   } else {

@@ -6,9 +6,10 @@
 //
 // Layout: grid = (ctas_per_col, ncols); CTA (x, c) owns row tiles x, x+gridDim.x, ... of
 // column c (fixed map => deterministic result).  Two variants:
-//   variant 0 (default): 4-stage ring of 16 KiB shared-memory tiles filled by 1-D TMA bulk
-//       copies (cp.async.bulk + mbarrier complete_tx; UBLKCP in SASS), consumed with
-//       conflict-free 128-bit LDS, warp-shuffle + shared-memory block reduction;
+//   variant 0: 6-stage ring of 16 KiB shared-memory tiles filled by 1-D TMA bulk copies
+//       (cp.async.bulk + mbarrier complete_tx; UBLKCP in SASS) issued by a dedicated producer
+//       warp, consumed by 8 warps with conflict-free 128-bit LDS, warp-shuffle + shared-memory
+//       block reduction;
 //   variant 1: direct 256-bit streaming loads (LDG.E.256), same reduction tree.
 // Per-thread float sums are Kahan-compensated (error O(eps)*sum|x| independent of n; the
 // compensation is reset when it becomes NaN so +-inf inputs behave like pandas/numpy).
@@ -24,7 +25,7 @@ namespace mb200 {
 constexpr int kRThreads = 256;
 constexpr int kMaxCtasPerCol = 2048;
 // TMA ring
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kTmaTileElems = 2048;  // 16 KiB
 constexpr int kTmaTileBytes = kTmaTileElems * 8;
 // direct-load variant
@@ -173,28 +174,30 @@ __device__ __forceinline__ T shfl_xor(T v, int m) {
 }
 
 // block-wide combine of (value, count); result valid in thread 0.  Fixed tree => deterministic.
+// Works for any block of <= 32 warps (the TMA variant carries a 9th, producer-only warp that
+// contributes the identity).
 template <int OP, typename T>
 __device__ __forceinline__ void block_combine(T& val, long long& cnt) {
-  __shared__ T s_val[kRThreads / 32];
-  __shared__ long long s_cnt[kRThreads / 32];
+  __shared__ T s_val[32];
+  __shared__ long long s_cnt[32];
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) {
     val = Acc<OP, T>::combine(val, shfl_xor(val, m));
     cnt += shfl_xor(cnt, m);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = (blockDim.x + 31) >> 5;
   if (lane == 0) {
     s_val[warp] = val;
     s_cnt[warp] = cnt;
   }
   __syncthreads();
   if (warp == 0) {
-    constexpr int NW = kRThreads / 32;
-    T v = lane < NW ? s_val[lane] : s_val[0];
-    long long n = lane < NW ? s_cnt[lane] : 0;
-    // lanes >= NW hold a duplicate of warp 0's value: neutralise by only combining lanes < NW
+    Acc<OP, T> ident;
+    T v = lane < nw ? s_val[lane] : ident.value();
+    long long n = lane < nw ? s_cnt[lane] : 0;
 #pragma unroll
-    for (int m = NW / 2; m >= 1; m >>= 1) {
+    for (int m = 16; m >= 1; m >>= 1) {
       v = Acc<OP, T>::combine(v, shfl_xor(v, m));
       n += shfl_xor(n, m);
     }
@@ -261,81 +264,95 @@ __global__ void __launch_bounds__(kRThreads) reduce_ldg_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------- variant 0: TMA-staged tiles
+// Warp-specialised: warps 0..7 consume, warp 8 (one elected lane) is the TMA producer.  A ring of
+// kStages 16 KiB tiles with a full[] (TMA complete_tx) and an empty[] (one arrive per consumer
+// warp) mbarrier per stage lets the producer run kStages tiles ahead without any block-wide sync.
+constexpr int kTmaThreads = kRThreads + 32;
+constexpr int kConsumerWarps = kRThreads / 32;
+
 template <int OP, typename T>
-__global__ void __launch_bounds__(kRThreads) reduce_tma_kernel(const __grid_constant__ RedParams p) {
+__global__ void __launch_bounds__(kTmaThreads) reduce_tma_kernel(const __grid_constant__ RedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* tiles = reinterpret_cast<T*>(smem_raw);                                      // kStages x 16 KiB
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTmaTileBytes);  // kStages barriers
+  T* tiles = reinterpret_cast<T*>(smem_raw);  // kStages x 16 KiB
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTmaTileBytes);
+  uint64_t* empty = full + kStages;
 
   const T* __restrict__ a = static_cast<const T*>(p.in[blockIdx.y]);
   const long long n = p.nrows;
   const long long ntiles = (n + kTmaTileElems - 1) / kTmaTileElems;
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   // tiles owned by this CTA: blockIdx.x + k * gridDim.x
   const long long first = blockIdx.x;
   const long long nmine = first < ntiles ? (ntiles - first + gridDim.x - 1) / gridDim.x : 0;
 
-  uint64_t policy = 0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
     mbar_fence_init();
-    policy = l2_policy_evict_first();
   }
   __syncthreads();
 
-  // elements of tile k that arrive through the bulk copy (even count: 16-byte granularity)
   auto tile_elems = [&](long long k) -> int {
     const long long base = (first + k * gridDim.x) * kTmaTileElems;
     const long long rem = n - base;
     return rem >= kTmaTileElems ? kTmaTileElems : (int)rem;
   };
-  auto issue = [&](long long k) {  // thread 0 only
-    const int s = (int)(k % kStages);
-    const long long base = (first + k * gridDim.x) * kTmaTileElems;
-    const uint32_t bytes = (uint32_t)((tile_elems(k) & ~1) * 8);
-    mbar_expect_tx(&full[s], bytes);
-    if (bytes) tma_bulk_g2s(tiles + (size_t)s * kTmaTileElems, a + base, bytes, &full[s], policy);
-  };
 
-  if (tid == 0) {
-    const long long pre = nmine < kStages ? nmine : kStages;
-    for (long long k = 0; k < pre; ++k) issue(k);
-  }
-
-  Acc<OP, T> acc[2];
-  for (long long k = 0; k < nmine; ++k) {
-    const int s = (int)(k % kStages);
-    const uint32_t parity = (uint32_t)((k / kStages) & 1);
-    mbar_wait(&full[s], parity);
-    const T* tile = tiles + (size_t)s * kTmaTileElems;
-    const int ne = tile_elems(k);
-    const int ne_even = ne & ~1;
-    if (ne == kTmaTileElems) {
-#pragma unroll
-      for (int j = 0; j < kTmaTileElems / (2 * kRThreads); ++j) {
-        const int e = (j * kRThreads + tid) * 2;
-        if constexpr (std::is_same<T, double>::value) {
-          const double2 v = *reinterpret_cast<const double2*>(tile + e);
-          acc[0].add(v.x, p.skipna);
-          acc[1].add(v.y, p.skipna);
-        } else {
-          const longlong2 v = *reinterpret_cast<const longlong2*>(tile + e);
-          acc[0].add(v.x, p.skipna);
-          acc[1].add(v.y, p.skipna);
-        }
-      }
-    } else {
-      for (int e = tid; e < ne_even; e += kRThreads) acc[0].add(tile[e], p.skipna);
-      if ((ne & 1) && tid == 0) {  // odd tail element never went through the 16-byte bulk copy
+  Acc<OP, T> acc[4];
+  if (warp == kConsumerWarps) {
+    // ---------------- producer warp
+    if (lane == 0) {
+      const uint64_t policy = l2_policy_evict_first();
+      for (long long k = 0; k < nmine; ++k) {
+        const int s = (int)(k % kStages);
+        if (k >= kStages) mbar_wait(&empty[s], (uint32_t)(((k / kStages) - 1) & 1));
         const long long base = (first + k * gridDim.x) * kTmaTileElems;
-        acc[1].add(a[base + ne - 1], p.skipna);
+        // elements that arrive through the bulk copy: even count (16-byte granularity)
+        const uint32_t bytes = (uint32_t)((tile_elems(k) & ~1) * 8);
+        mbar_expect_tx(&full[s], bytes);
+        if (bytes) tma_bulk_g2s(tiles + (size_t)s * kTmaTileElems, a + base, bytes, &full[s], policy);
       }
     }
-    __syncthreads();  // every thread is done with stage s before it is refilled
-    if (tid == 0 && k + kStages < nmine) issue(k + kStages);
+  } else {
+    // ---------------- consumer warps
+    for (long long k = 0; k < nmine; ++k) {
+      const int s = (int)(k % kStages);
+      mbar_wait(&full[s], (uint32_t)((k / kStages) & 1));
+      const T* tile = tiles + (size_t)s * kTmaTileElems;
+      const int ne = tile_elems(k);
+      if (ne == kTmaTileElems) {
+#pragma unroll
+        for (int j = 0; j < kTmaTileElems / (2 * kRThreads); ++j) {
+          const int e = (j * kRThreads + tid) * 2;
+          if constexpr (std::is_same<T, double>::value) {
+            const double2 v = *reinterpret_cast<const double2*>(tile + e);
+            acc[(2 * j) & 3].add(v.x, p.skipna);
+            acc[(2 * j + 1) & 3].add(v.y, p.skipna);
+          } else {
+            const longlong2 v = *reinterpret_cast<const longlong2*>(tile + e);
+            acc[(2 * j) & 3].add(v.x, p.skipna);
+            acc[(2 * j + 1) & 3].add(v.y, p.skipna);
+          }
+        }
+      } else {
+        const int ne_even = ne & ~1;
+        for (int e = tid; e < ne_even; e += kRThreads) acc[0].add(tile[e], p.skipna);
+        if ((ne & 1) && tid == 0) {  // odd tail element never went through the 16-byte bulk copy
+          const long long base = (first + k * gridDim.x) * kTmaTileElems;
+          acc[1].add(a[base + ne - 1], p.skipna);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done reading stage s
+    }
   }
   acc[0].merge(acc[1]);
+  acc[2].merge(acc[3]);
+  acc[0].merge(acc[2]);
   T val = acc[0].value();
   long long cnt = acc[0].n;
   block_combine<OP, T>(val, cnt);
@@ -396,12 +413,12 @@ static int run_reduce(const RedParams& p0, int variant, void* out_val, long long
   }
   if (variant == 0 && !a16) variant = 1;  // bulk copies need 16-byte aligned sources
 
-  const size_t smem = (size_t)kStages * kTmaTileBytes + kStages * sizeof(uint64_t);
+  const size_t smem = (size_t)kStages * kTmaTileBytes + 2 * kStages * sizeof(uint64_t);
   int occ = 0;
   long long ntiles;
   if (variant == 0) {
     MB_CUDA(cudaFuncSetAttribute(reduce_tma_kernel<OP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tma_kernel<OP, T>, kRThreads, smem));
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_tma_kernel<OP, T>, kTmaThreads, smem));
     ntiles = (p.nrows + kTmaTileElems - 1) / kTmaTileElems;
   } else {
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reduce_ldg_kernel<OP, T, true>, kRThreads, 0));
@@ -419,7 +436,7 @@ static int run_reduce(const RedParams& p0, int variant, void* out_val, long long
                                             (size_t)MB200_MAX_COLS * kMaxCtasPerCol * 8);
   dim3 grid((unsigned)per_col, (unsigned)p.ncols);
   if (variant == 0) {
-    reduce_tma_kernel<OP, T><<<grid, kRThreads, smem, st>>>(p);
+    reduce_tma_kernel<OP, T><<<grid, kTmaThreads, smem, st>>>(p);
     MB_LAUNCH_CHECK("reduce_tma_kernel");
   } else {
     if (a32)

@@ -1,0 +1,137 @@
+"""world_size-2 ``gloo`` tests (CPU tensors) of the multi-GPU plumbing in modin_b200/dist.py:
+row sharding, the packed all_reduce of TreeReduce partials, the all_gather of row shards and the
+range-partitioned all-to-all of groupby partial tables.  The local compute that the GPU kernels
+do is stood in for by the CPU oracle / numpy -- only the exchange logic is under test here.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from modin_b200 import dist as bdist
+from modin_b200 import synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, ws, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        ret[rank] = fn(rank, ws)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, ws=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(ws, _free_port(), fn, ret), nprocs=ws, join=True)
+    return [ret[r] for r in range(ws)]
+
+
+def test_shard_bounds_cover_all_rows():
+    for n in (0, 1, 7, 8, 1_000_000_007):
+        for ws in (1, 2, 3, 8):
+            b = [bdist.shard_bounds(n, r, ws) for r in range(ws)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _tree_reduce_job(rank, ws):
+    # every rank reduces its shard (numpy stands in for reduce_columns), then the packed all_reduce
+    n, W = 10_001, 5
+    lo, hi = bdist.shard_bounds(n, rank, ws)
+    cols = [synth.gen_f64(hi - lo, 42, j, lo) for j in range(W)]
+    sums = [torch.tensor([c.sum()], dtype=torch.float64) for c in cols]
+    mins = [torch.tensor([c.min()], dtype=torch.float64) for c in cols]
+    cnts = [torch.tensor([len(c)], dtype=torch.int64) for c in cols]
+    bdist.all_reduce_values(sums + mins + cnts, ["sum"] * W + ["min"] * W + ["sum"] * W)
+    return [float(x) for x in sums], [float(x) for x in mins], [int(x) for x in cnts]
+
+
+def test_tree_reduce_combine_matches_single_process():
+    out = _run(_tree_reduce_job)
+    n, W = 10_001, 5
+    full = [synth.gen_f64(n, 42, j) for j in range(W)]
+    for sums, mins, cnts in out:  # replicated on every rank
+        assert np.allclose(sums, [c.sum() for c in full], rtol=0, atol=1e-10)
+        assert mins == [c.min() for c in full]
+        assert cnts == [n] * W
+    assert out[0] == out[1]
+
+
+def _gather_job(rank, ws):
+    n = 1001
+    lo, hi = bdist.shard_bounds(n, rank, ws)
+    a = torch.from_numpy(synth.gen_f64(hi - lo, 1, 0, lo))
+    k = torch.from_numpy(synth.gen_i64(hi - lo, 2, 0, 50, lo))
+    ga, gk = bdist.all_gather_rows([a, k])
+    return ga.numpy(), gk.numpy()
+
+
+def test_all_gather_rows_restores_global_order():
+    out = _run(_gather_job)
+    for ga, gk in out:
+        assert np.array_equal(ga.view(np.uint64), synth.gen_f64(1001, 1, 0).view(np.uint64))
+        assert np.array_equal(gk, synth.gen_i64(1001, 2, 0, 50))
+
+
+def _groupby_job(rank, ws):
+    """Local partial table (pandas groupby of the shard = stand-in for the hash-aggregate kernel),
+    range exchange, local merge of what arrives."""
+    import pandas
+
+    n, G, V = 40_000, 3_000, 3
+    lo, hi = bdist.shard_bounds(n, rank, ws)
+    pdf = synth.host_frame(hi - lo, V, seed=42, row_offset=lo, key_modulus=G, key_seed=43)
+    part = pdf.groupby("key").sum()  # ascending unique keys
+    keys = torch.from_numpy(part.index.to_numpy().copy())
+    cols = [torch.from_numpy(part.iloc[:, j].to_numpy().copy()) for j in range(V)]
+    rk, rc = bdist.exchange_by_key_range(keys, cols)
+    got = pandas.DataFrame({f"c{j}": rc[j].numpy() for j in range(V)}, index=rk.numpy()).groupby(level=0).sum()
+    return got.index.to_numpy(), got.to_numpy()
+
+
+def test_groupby_range_exchange_equals_global_groupby():
+    out = _run(_groupby_job)
+    n, G, V = 40_000, 3_000, 3
+    pdf = synth.host_frame(n, V, seed=42, key_modulus=G, key_seed=43)
+    want = pdf.groupby("key").sum()
+    keys = np.concatenate([o[0] for o in out])
+    vals = np.concatenate([o[1] for o in out])
+    # rank r owns the r-th key range: concatenation in rank order is globally sorted and complete
+    assert np.array_equal(keys, want.index.to_numpy())
+    assert np.allclose(vals, want.to_numpy(), rtol=0, atol=1e-9)
+    assert len(out[0][0]) > 0 and len(out[1][0]) > 0
+    assert out[0][0].max() < out[1][0].min()
+    # balanced within a factor of two (sampled pivots)
+    assert 0.5 < len(out[0][0]) / len(out[1][0]) < 2.0
+
+
+def _empty_rank_job(rank, ws):
+    keys = torch.arange(10, dtype=torch.int64) if rank == 0 else torch.empty(0, dtype=torch.int64)
+    vals = [keys.to(torch.float64) * 2.0]
+    rk, rc = bdist.exchange_by_key_range(keys, vals)
+    return rk.numpy(), rc[0].numpy()
+
+
+def test_exchange_with_an_empty_rank():
+    out = _run(_empty_rank_job)
+    keys = np.concatenate([o[0] for o in out])
+    vals = np.concatenate([o[1] for o in out])
+    assert np.array_equal(np.sort(keys), np.arange(10))
+    assert np.array_equal(vals, keys * 2.0)
