@@ -138,7 +138,8 @@ class DeviceColumn:
 class DeviceBlock:
     """Columnar device block = payload of one block partition."""
 
-    __slots__ = ("cols", "columns", "index_cols", "index_names", "range_start", "nrows", "index_host", "replicated")
+    __slots__ = ("cols", "columns", "index_cols", "index_names", "range_start", "nrows", "index_host", "replicated",
+                 "keys_sorted_unique")
 
     def __init__(
         self,
@@ -154,6 +155,8 @@ class DeviceBlock:
         # replicated: under torch.distributed, True when every rank holds this same block (results of
         # collectives); False when the block is this rank's row shard of a larger frame
         self.replicated = bool(replicated)
+        # True for a group table straight out of the hash aggregate: device index keys ascending and distinct
+        self.keys_sorted_unique = False
         self.cols: List[DeviceColumn] = list(cols)
         self.columns = columns if isinstance(columns, pandas.Index) else pandas.Index(list(columns))
         if len(self.cols) != len(self.columns):

@@ -462,7 +462,9 @@ def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels):
     else:  # mean: sums then counts
         cols = list(sums) + list(cnts)
         cl = pandas.MultiIndex.from_tuples([("sum", c) for c in labels] + [("count", c) for c in labels])
-    return DeviceBlock(cols, cl, nrows=len(keys), index_cols=[keys], index_names=[key_label])
+    blk = DeviceBlock(cols, cl, nrows=len(keys), index_cols=[keys], index_names=[key_label])
+    blk.keys_sorted_unique = True
+    return blk
 
 
 class DevGroupbyReduce(DevFn):
@@ -509,9 +511,16 @@ class DevGroupbyReduce(DevFn):
             raise ValueError("groupby reduce expects partial tables keyed by device index columns")
         return block.index_cols[0], (block.index_names[0] if block.index_names else None)
 
+    def _local_merge(self, block, keys):
+        # a single partial table (one row partition on this GPU) is already one row per key, ascending:
+        # nothing to regroup -- the reference would re-run groupby(level=0) on it to the same effect
+        if block.keys_sorted_unique:
+            return keys, list(block.cols)
+        return self._merge(keys, block.cols)
+
     def __call__(self, block, *args, partition_idx=0, **kwargs):
         keys, key_label = self._unpack(block)
-        k, cols = self._merge(keys, block.cols)
+        k, cols = self._local_merge(block, keys)
         return self._finalize(k, cols, block.columns, key_label)
 
     def run_distributed(self, block, *args, partition_idx=0, **kwargs):
@@ -522,7 +531,7 @@ class DevGroupbyReduce(DevFn):
         from . import dist
 
         keys, key_label = self._unpack(block)
-        k, cols = self._merge(keys, block.cols)
+        k, cols = self._local_merge(block, keys)
         rk, rcols = dist.exchange_by_key_range(k.data, [c.data for c in cols])
         rkeys = DeviceColumn(rk, np.int64)
         rc = [DeviceColumn(t_, c.dtype) for t_, c in zip(rcols, cols)]

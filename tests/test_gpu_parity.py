@@ -213,10 +213,15 @@ def test_edge_cases_and_errors():
     # all-NaN column, +-inf, -0.0
     pdf = pandas.DataFrame({"a": [np.nan, np.nan, np.nan], "b": [np.inf, 1.0, -0.0], "c": [-np.inf, np.inf, 2.0]})
     df = m.DataFrame(pdf)
-    assert_exact(df.sum().to_numpy(), pdf.sum().to_numpy(), "sum with inf / all-NaN")
-    assert_exact(df.sum(min_count=1).to_numpy(), pdf.sum(min_count=1).to_numpy(), "min_count=1 all-NaN -> NaN")
-    assert_exact(df.min().to_numpy(), pdf.min().to_numpy(), "min all-NaN -> NaN")
-    assert_exact(df.max(skipna=False).to_numpy(), pdf.max(skipna=False).to_numpy(), "max skipna=False")
+    # The truth is the REFERENCE (restated by the oracle), not plain pandas: Modin's tree reduce returns 0.0 for
+    # the sum of [-inf, inf, 2.0] (the NaN partial of the map phase is skipped by the skipna reduce phase) where
+    # pandas returns NaN -- checked against the unmodified reference in the build container.
+    assert_exact(df.sum().to_numpy(), orc.df_sum(pdf, 4).to_numpy(), "sum with inf / all-NaN")
+    assert_exact(df.sum().to_numpy(), np.array([0.0, np.inf, 0.0]), "sum quirk reproduced")
+    assert_exact(df.sum(min_count=1).to_numpy(), orc.df_sum(pdf, 4, min_count=1).to_numpy(), "min_count=1 all-NaN -> NaN")
+    assert_exact(df.mean().to_numpy(), orc.df_mean(pdf, 4).to_numpy(), "mean with inf / all-NaN")
+    assert_exact(df.min().to_numpy(), orc.df_min(pdf, 4).to_numpy(), "min all-NaN -> NaN")
+    assert_exact(df.max(skipna=False).to_numpy(), orc.df_max(pdf, 4, skipna=False).to_numpy(), "max skipna=False")
     assert_exact(df.abs()._to_pandas().to_numpy(), pdf.abs().to_numpy(), "abs(-0.0) = +0.0")
     # errors surface like pandas / the reference does
     with pytest.raises(ValueError):

@@ -165,7 +165,7 @@ def parity(only_groupby=False):
 
     # groupby
     import pandas as pd
-    for variant in ("0", "1"):
+    for variant in ("0", "1", "2"):
         os.environ["MB200_GB_VARIANT"] = variant
         for n, G, V in ((1, 1, 1), (1000, 10, 3), (100003, 5000, 8), (200000, 150000, 11)):
             keys = rng.randint(-G // 2, G - G // 2, size=n).astype(np.int64)
@@ -260,7 +260,7 @@ def bandwidth_groupby(log2n):
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     for G in (1000, 1_000_000):
         _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, G, st))
-        for variant in ("0", "1"):
+        for variant in ("0", "1", "2"):
             os.environ["MB200_GB_VARIANT"] = variant
             tab = C.c_void_p()
             _lib.check(lib.mb200_gb_create(C.byref(tab), G + 16, W, _lib.GB_SUM, st))
