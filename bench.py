@@ -107,10 +107,22 @@ def best_thread_count(cols: int) -> int:
     return best
 
 
+_MALLOC_ENV = {
+    # keep big numpy buffers inside the heap and never trim it: without this every pandas temporary is a
+    # fresh mmap whose first touch page-faults, which would sandbag the CPU arm by 2-10x
+    "MALLOC_MMAP_THRESHOLD_": str(1 << 25),
+    "MALLOC_TRIM_THRESHOLD_": str(1 << 40),
+    "MALLOC_TOP_PAD_": str(1 << 28),
+}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.environ.get("MB200_REF_CHILD") != "1":
+        env = dict(os.environ, MB200_REF_CHILD="1", **_MALLOC_ENV)
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     threads = best_thread_count(args.cols)
     rows = int(args.cpu_rows)
     for _ in range(max(args.warmup, 1)):
@@ -348,13 +360,19 @@ def run_b200_arm(args):
     # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
     cpu = None
     if rank == 0 and not args.skip_cpu and ws == 1:
-        threads = best_thread_count(W)
-        crow = int(args.cpu_rows)
-        cpu_reference_pass(min(crow, 1_000_000), W, threads)
-        dts = [cpu_reference_pass(crow, W, threads) for _ in range(2)]
-        cpu = {"value": crow / min(dts), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{crow} rows x {W} cols, best of 2 (oracle port of Modin-on-pandas, "
-                         f"{threads} partitions on {threads} threads)"}  # fmt: skip
+        # the CPU leg runs in its own process (own malloc tuning, no CUDA context): the reference arm itself
+        env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+        for k in ("LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "MB200_REF_CHILD"):
+            env.pop(k, None)
+        try:
+            res = subprocess.run(
+                [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                 "--cpu-rows", str(int(args.cpu_rows)), "--cols", str(W)],
+                capture_output=True, text=True, timeout=600, env=env)  # fmt: skip
+            ref = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+            cpu = ref["cpu_baseline"]
+        except Exception as e:  # the GPU numbers stand on their own; say why the CPU leg is missing
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
         line = {

@@ -9,23 +9,35 @@
 //
 // Data structure (all device resident):
 //   slots[cap]   16-byte {int64 key, int32 gid, pad}; cap = pow2 >= 2 * group_capacity.
-//                gid: -1 empty, -2 being inserted, [0, gcap) dense group id, gcap = overflowed.
+//                gid: -1 empty, -2 claimed (being published), [0, gcap) dense id, gcap = overflowed.
+//                A slot is published with ONE 128-bit store {key, gid} and read with ONE 128-bit load.
 //   acc[gcap][vstride]  float64 sums, row-major so one group's V sums share 64-byte segments.
 //   cnt[gcap][vstride]  int64 non-NaN counts (optional), size[gcap] int64 rows (optional).
-// For G = 1e6, V = 8 the table is 32 MiB of slots + 64 MiB of sums: it lives in the 126 MB L2
-// while the 72 B/row input streams past it with L2 evict-first loads.
+// For G = 1e6, V = 8 the table is 32 MiB of slots + 64 MiB of sums: it is kept in the 126 MB L2
+// (table accesses carry an L2 evict-last policy, the streamed 72 B/row input an evict-first one).
 //
-// Kernel (one warp = 32 consecutive rows per iteration):
-//   1. coalesced loads of the key and the V values of the 32 rows (all issued up front);
-//   2. warp-cooperative probe: __match_any_sync groups lanes holding the same key, the lowest
-//      lane of each group probes / inserts (linear probing, 128-bit slot loads, CAS on gid as
-//      the insertion lock), the gid is broadcast back with __shfl_sync;
-//   3. accumulate with RED.ADD.F64:  variant 0 re-lays the 32x8 value tile through padded
-//      shared memory so that 8 consecutive lanes update the 8 sums of ONE group (one 64-byte
-//      segment per row); variant 1 keeps lane == row (32 different segments per instruction).
+// Kernels
+//   gb_accumulate_tma_kernel (default; V <= 8, 16-byte aligned columns): a producer warp streams
+//     256-row tiles of the key + value columns into a shared-memory ring with 1-D TMA bulk copies
+//     (full/empty mbarriers), so DRAM latency is out of the per-row dependency chain and no
+//     registers hold in-flight rows; 8 consumer warps each take 32 rows of a tile.
+//   gb_accumulate_kernel (fallback: ragged tails, unaligned views, V > 8, partial-table merges):
+//     the same per-warp algorithm with direct coalesced loads.
+// Per warp (32 rows):
+//   1. warp-cooperative probe: __match_any_sync groups lanes holding the same key; the lowest lane
+//      of each group looks the key up (read-only linear probing).  Missing keys are inserted in
+//      warp-convergent ROUNDS: claim the empty slot with a CAS, take dense ids with one atomicAdd
+//      per warp per round, publish {key, gid} with a 128-bit store; a lane that meets a slot
+//      claimed by someone else simply retries next round -- no lane ever spins on another lane;
+//   2. accumulate with RED.ADD.F64, 8 consecutive lanes updating the 8 sums of ONE group (one
+//      64-byte segment, one L2 request per row); the value tile is read transposed from shared memory.
 // Float atomics make the summation order run-dependent: results agree with pandas to the
 // tolerance stated in tests (|err| <= 4 log2(n) eps sum|x|), not bit for bit; counts/sizes
 // and keys are exact.
+//
+// Tried and measured (gpurun_out round 1, 2^27 rows, G = 1e6, V = 8): lane == row REDs (8 segments
+// per instruction) 16.5 G rows/s; 8-lanes-per-row REDs 35.4 G rows/s; one TMA bulk reduction per
+// row (cp.reduce.async.bulk .add.f64 / UBLKRED) 34.7 G rows/s -- no gain, dropped.
 #include "common.cuh"
 
 namespace mb200 {
@@ -43,7 +55,7 @@ struct __align__(16) Slot {
 struct GbMeta {  // device-side bookkeeping
   int ngroups;
   int overflow;
-  long long kmin;
+  long long kmin;  // filled by gb_collect_kernel
   long long kmax;
 };
 
@@ -67,6 +79,12 @@ namespace mb200 {
 constexpr int kGbThreads = 256;
 constexpr int kGbWarps = kGbThreads / 32;
 constexpr int kColStride = 34;  // doubles; 34 = 2 (mod 16) -> conflict-free transposed reads
+// TMA-staged kernel
+constexpr int kTileRows = 256;
+constexpr int kTileColStride = 258;  // doubles; 258 = 2 (mod 16), and 258 * 8 is a multiple of 16 bytes
+constexpr int kGbStages = 3;
+constexpr int kGbTmaThreads = kGbThreads + 32;
+constexpr int kStageBytes = ((9 * kTileColStride * 8 + 127) / 128) * 128;
 
 struct GbParams {
   Slot* slots;
@@ -87,82 +105,96 @@ struct GbParams {
   long long nrows;
 };
 
-__device__ __forceinline__ void red_add_f64(double* p, double v) {
-  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+// ---- table accesses: relaxed GPU-scope, L2 evict-last (keep the table resident under the stream)
+__device__ __forceinline__ void red_add_f64(double* p, double v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void red_add_u64(long long* p, long long v) {
-  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void red_add_u64(long long* p, long long v, uint64_t pol) {
+  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void ld_slot(const Slot* s, long long& key, int& gid) {
+__device__ __forceinline__ void ld_slot(const Slot* s, long long& key, int& gid, uint64_t pol) {
   unsigned long long a, b;
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s) : "memory");
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+               : "=l"(a), "=l"(b)
+               : "l"(s), "l"(pol)
+               : "memory");
   key = (long long)a;
   gid = (int)(unsigned int)(b & 0xffffffffULL);
 }
+__device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_t pol) {
+  const unsigned long long b = (unsigned long long)(unsigned int)gid;
+  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(s),
+               "l"((unsigned long long)key), "l"(b), "l"(pol)
+               : "memory");
+}
 
-// Find or insert `k`; returns the dense group id, or gcap if the table overflowed.
-__device__ __forceinline__ int probe_insert(const GbParams& p, long long k) {
+// Dense group id of every lane's key (gcap = table overflowed).  Must be called by all 32 lanes.
+__device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t pol) {
+  const int lane = threadIdx.x & 31;
+  const int gcap = (int)p.gcap;
+  const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
+  const int leader = __ffs(peers) - 1;
+  const bool is_leader = (lane == leader);
+  int gid = -1;
   unsigned int slot = hash_key(k) & p.mask;
   long long probes = 0;
-  for (;;) {
-    long long sk;
-    int g;
-    ld_slot(&p.slots[slot], sk, g);
-    if (g >= 0) {
-      if (sk == k) return g;
-      slot = (slot + 1) & p.mask;
-      if (++probes > p.cap) {  // table full of other keys
-        p.meta->overflow = 1;
-        return (int)p.gcap;
-      }
-      continue;
-    }
-    if (g == -1) {
-      const int old = atomicCAS(&p.slots[slot].gid, -1, -2);
-      if (old == -1) {  // we own the slot: write the key, take a dense id, publish
-        *reinterpret_cast<volatile long long*>(&p.slots[slot].key) = k;
-        int ng = atomicAdd(&p.meta->ngroups, 1);
-        if (ng >= p.gcap) {
-          p.meta->overflow = 1;
-          ng = (int)p.gcap;
-        } else {
-          atomicMin(&p.meta->kmin, k);
-          atomicMax(&p.meta->kmax, k);
+  unsigned int pending = __ballot_sync(0xffffffffu, is_leader);
+  while (pending) {
+    bool won = false;
+    if (is_leader && gid < 0) {
+      for (;;) {
+        long long sk;
+        int g;
+        ld_slot(&p.slots[slot], sk, g, pol);
+        if (g >= 0) {
+          if (sk == k) {
+            gid = g;
+            break;
+          }
+          slot = (slot + 1) & p.mask;
+          if (++probes > p.cap) {  // table full of other keys
+            p.meta->overflow = 1;
+            gid = gcap;
+            break;
+          }
+          continue;
         }
-        __threadfence();
-        *reinterpret_cast<volatile int*>(&p.slots[slot].gid) = ng;
-        return ng;
+        if (g == -1) won = (atomicCAS(&p.slots[slot].gid, -1, -2) == -1);
+        break;  // claimed it, or someone else is publishing this slot: look again next round
       }
     }
-    // g == -2 (or we lost the CAS): another thread is publishing this slot; look again
+    // dense ids for this round's winners: one atomicAdd per warp
+    const unsigned int winners = __ballot_sync(0xffffffffu, won);
+    if (winners) {
+      const int first = __ffs(winners) - 1;
+      int base = 0;
+      if (lane == first) base = atomicAdd(&p.meta->ngroups, __popc(winners));
+      base = __shfl_sync(0xffffffffu, base, first);
+      if (won) {
+        int ng = base + __popc(winners & ((1u << lane) - 1u));
+        if (ng >= gcap) {
+          p.meta->overflow = 1;
+          ng = gcap;
+        }
+        st_slot(&p.slots[slot], k, ng, pol);
+        gid = ng;
+      }
+    }
+    pending = __ballot_sync(0xffffffffu, is_leader && gid < 0);
   }
+  return __shfl_sync(0xffffffffu, gid, leader);
 }
 
-// Read-only lookup: dense group id of `k`, or -1 if the probe chain ends at an empty or
-// in-flight slot (the caller then takes the serialized insert path).
-__device__ __forceinline__ int probe_find(const GbParams& p, long long k) {
-  unsigned int slot = hash_key(k) & p.mask;
-  for (long long probes = 0; probes <= p.cap; ++probes) {
-    long long sk;
-    int g;
-    ld_slot(&p.slots[slot], sk, g);
-    if (g < 0) return -1;
-    if (sk == k) return g;
-    slot = (slot + 1) & p.mask;
-  }
-  return -1;
-}
-
+// ---------------------------------------------------------------- fallback: direct loads
 template <int VARIANT, bool PARTIAL>
 __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
-  // variant 0: [8 cols][34] column tiles; variant 2: [32 rows][10] row tiles (80-byte stride: 16-byte
-  // aligned rows, conflict-free 128-bit stores)
-  __shared__ __align__(16) double s_tile[kGbWarps][32 * 10];
+  __shared__ double s_tile[kGbWarps][8 * kColStride];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long nchunks = (p.nrows + 31) >> 5;
   const long long wstride = (long long)gridDim.x * kGbWarps;
   const int gcap = (int)p.gcap;
   const uint64_t pol = l2_policy_evict_first();
+  const uint64_t keep = l2_policy_evict_last();
   for (long long ch = (long long)blockIdx.x * kGbWarps + warp; ch < nchunks; ch += wstride) {
     const long long base = ch << 5;
     const long long row = base + lane;
@@ -176,35 +208,16 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
       for (int c = 0; c < 8; ++c)
         x[c] = (c < nc && valid) ? ldg_stream_f64(static_cast<const double*>(p.vals[c]) + row, pol) : 0.0;
     }
-    // ---- probe (one lane per distinct key in the warp)
     {
       // rows past the end borrow lane 0's key (lane 0 is always valid in a live chunk) so that they join
       // its peer group and never become leaders; the shuffle is executed by ALL lanes.
       const long long k0 = __shfl_sync(0xffffffffu, k, 0);
       k = valid ? k : k0;
     }
-    const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
-    const int leader = __ffs(peers) - 1;
-    const bool is_leader = (lane == leader);
-    // fast path: read-only lookup by every leader in parallel (the steady state once the table is warm)
-    int gid = -1;
-    if (is_leader) gid = probe_find(p, k);
-    // slow path: leaders that met an empty / in-flight slot insert ONE LANE AT A TIME, so a lane that
-    // spins on a slot lock can only be waiting for another warp (which makes progress independently),
-    // never for a diverged lane of its own warp.
-    unsigned int need = __ballot_sync(0xffffffffu, is_leader && gid < 0);
-    while (need) {
-      const int l = __ffs(need) - 1;
-      if (lane == l) gid = probe_insert(p, k);
-      need &= need - 1;
-      __syncwarp();
-    }
-    gid = __shfl_sync(0xffffffffu, gid, leader);
+    const int gid = resolve_gid(p, k, keep);
     const bool live = valid && gid < gcap;
 
-    if ((p.flags & MB200_GB_SIZE) && live) {
-      red_add_u64(p.size + gid, PARTIAL ? p.psize[row] : 1LL);
-    }
+    if ((p.flags & MB200_GB_SIZE) && live) red_add_u64(p.size + gid, PARTIAL ? p.psize[row] : 1LL, keep);
     // ---- accumulate, 8 value columns at a time
     for (int c0 = 0; c0 < p.nvals; c0 += 8) {
       const int nc = (p.nvals - c0) < 8 ? (p.nvals - c0) : 8;
@@ -213,40 +226,17 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
         for (int c = 0; c < 8; ++c)
           x[c] = (c < nc && valid) ? ldg_stream_f64(static_cast<const double*>(p.vals[c0 + c]) + row, pol) : 0.0;
       }
-      if (VARIANT == 2) {
-        // One TMA bulk reduction per row: the row's (<= 8) values are laid out contiguously in shared
-        // memory and added to the group's 64-byte accumulator row by the copy engine
-        // (cp.reduce.async.bulk ... .add.f64 -> UBLKRED), i.e. ONE async op per row instead of 8 RED
-        // lanes through the LSU.  NaNs are replaced by +0.0 (adding zero == skipping).
-        double* myrow = s_tile[warp] + lane * 10;
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // my previous row has been read
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          double2 d;
-          d.x = (c < nc && x[c] == x[c]) ? x[c] : 0.0;
-          d.y = (c + 1 < nc && x[c + 1] == x[c + 1]) ? x[c + 1] : 0.0;
-          *reinterpret_cast<double2*>(myrow + c) = d;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (live) {
-          const unsigned int bytes = (unsigned int)(((nc + 1) >> 1) * 16);
-          double* dst = p.acc + (size_t)gid * p.vstride + c0;
-          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst),
-                       "r"(smem_u32(myrow)), "r"(bytes)
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      } else if (VARIANT == 1) {
+      if (VARIANT == 1) {  // lane == row (kept for measurement)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < nc && live) {
             const size_t o = (size_t)gid * p.vstride + c0 + c;
             if (p.flags & MB200_GB_SUM) {
-              if (x[c] == x[c]) red_add_f64(p.acc + o, x[c]);
+              if (x[c] == x[c]) red_add_f64(p.acc + o, x[c], keep);
             }
             if (p.flags & MB200_GB_COUNT) {
-              if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[row]);
-              else if (x[c] == x[c]) red_add_u64(p.cnt + o, 1LL);
+              if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[row], keep);
+              else if (x[c] == x[c]) red_add_u64(p.cnt + o, 1LL, keep);
             }
           }
         }
@@ -265,11 +255,11 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
           if (ok) {
             const size_t o = (size_t)g * p.vstride + c0 + c;
             if (p.flags & MB200_GB_SUM) {
-              if (xv == xv) red_add_f64(p.acc + o, xv);
+              if (xv == xv) red_add_f64(p.acc + o, xv, keep);
             }
             if (p.flags & MB200_GB_COUNT) {
-              if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[base + r]);
-              else if (xv == xv) red_add_u64(p.cnt + o, 1LL);
+              if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[base + r], keep);
+              else if (xv == xv) red_add_u64(p.cnt + o, 1LL, keep);
             }
           }
         }
@@ -277,7 +267,76 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
       }
     }
   }
-  if (VARIANT == 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- default: TMA-staged tiles
+// Handles the first ntiles * 256 rows (full tiles only); nvals <= 8; raw rows (not partial tables).
+__global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const __grid_constant__ GbParams p,
+                                                                          long long ntiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kGbStages * kStageBytes);
+  uint64_t* empty = full + kGbStages;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = p.nvals;
+  const int gcap = (int)p.gcap;
+  const long long first = blockIdx.x;
+  const long long nmine = first < ntiles ? (ntiles - first + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kGbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGbWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kGbWarps) {
+    // ---------------- producer: (1 + nv) bulk copies of 2 KiB per tile
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      for (long long k = 0; k < nmine; ++k) {
+        const int s = (int)(k % kGbStages);
+        if (k >= kGbStages) mbar_wait(&empty[s], (uint32_t)(((k / kGbStages) - 1) & 1));
+        const long long row0 = (first + k * gridDim.x) * kTileRows;
+        double* stage = reinterpret_cast<double*>(smem_raw + (size_t)s * kStageBytes);
+        mbar_expect_tx(&full[s], (uint32_t)((1 + nv) * kTileRows * 8));
+        tma_bulk_g2s(stage, p.keys + row0, kTileRows * 8, &full[s], pol);
+        for (int c = 0; c < nv; ++c)
+          tma_bulk_g2s(stage + (size_t)(1 + c) * kTileColStride, static_cast<const double*>(p.vals[c]) + row0,
+                       kTileRows * 8, &full[s], pol);
+      }
+    }
+    return;
+  }
+  // ---------------- consumers: warp w owns rows [32w, 32w + 32) of every tile
+  const uint64_t keep = l2_policy_evict_last();
+  const int c = lane & 7;
+  for (long long k = 0; k < nmine; ++k) {
+    const int s = (int)(k % kGbStages);
+    mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
+    const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
+    const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
+    const int gid = resolve_gid(p, key, keep);
+    if ((p.flags & MB200_GB_SIZE) && gid < gcap) red_add_u64(p.size + gid, 1LL, keep);
+    const double* vt = stage + kTileColStride + warp * 32;  // value column 0, this warp's rows
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int r = 4 * kk + (lane >> 3);
+      const int g = __shfl_sync(0xffffffffu, gid, r);
+      if (c < nv && g < gcap) {
+        const double xv = vt[c * kTileColStride + r];
+        const size_t o = (size_t)g * p.vstride + c;
+        if (xv == xv) {
+          if (p.flags & MB200_GB_SUM) red_add_f64(p.acc + o, xv, keep);
+          if (p.flags & MB200_GB_COUNT) red_add_u64(p.cnt + o, 1LL, keep);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
 }
 
 __global__ void gb_init_kernel(Slot* slots, long long cap, GbMeta* meta) {
@@ -297,15 +356,41 @@ __global__ void gb_init_kernel(Slot* slots, long long cap, GbMeta* meta) {
   }
 }
 
-// keys_by_gid[gid] = key ; perm[gid] = gid
-__global__ void gb_collect_kernel(const Slot* __restrict__ slots, long long cap, long long gcap,
-                                  long long* __restrict__ keys_by_gid, long long* __restrict__ perm) {
+// keys_by_gid[gid] = key ; perm[gid] = gid ; key range for the sort (one atomic pair per block)
+__global__ void __launch_bounds__(256) gb_collect_kernel(const Slot* __restrict__ slots, long long cap, long long gcap,
+                                                         long long* __restrict__ keys_by_gid,
+                                                         long long* __restrict__ perm, GbMeta* meta) {
+  __shared__ long long s_min[8], s_max[8];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000ULL;
   if (i < cap) {
     const Slot s = slots[i];
     if (s.gid >= 0 && s.gid < gcap) {
       keys_by_gid[s.gid] = s.key;
       perm[s.gid] = s.gid;
+      lo = hi = s.key;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, lo, m), b = __shfl_xor_sync(0xffffffffu, hi, m);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_min[warp] = lo;
+    s_max[warp] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      lo = s_min[w] < lo ? s_min[w] : lo;
+      hi = s_max[w] > hi ? s_max[w] : hi;
+    }
+    if (lo <= hi) {
+      atomicMin(&meta->kmin, lo);
+      atomicMax(&meta->kmax, hi);
     }
   }
 }
@@ -343,10 +428,25 @@ static long long next_pow2(long long v) {
   return p;
 }
 
+// MB200_GB_VARIANT: unset/0 = TMA-staged (default), 1 = direct loads + 8-lanes-per-row REDs,
+// 2 = direct loads + lane == row REDs.  Read per call so one process can compare them.
 static int gb_variant_from_env() {
-  const char* e = getenv("MB200_GB_VARIANT");  // read per call: lets one process compare variants
+  const char* e = getenv("MB200_GB_VARIANT");
   if (e && e[0] == '1') return 1;
   if (e && e[0] == '2') return 2;
+  return 0;
+}
+
+template <int VARIANT, bool PARTIAL>
+static int launch_ldg(const GbParams& p, const DevProps& dp, cudaStream_t st) {
+  int occ = 0;
+  MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_kernel<VARIANT, PARTIAL>, kGbThreads, 0));
+  const long long nchunks = (p.nrows + 31) / 32;
+  long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
+  const long long need = (nchunks + kGbWarps - 1) / kGbWarps;
+  if (grid > need) grid = need;
+  gb_accumulate_kernel<VARIANT, PARTIAL><<<(unsigned)grid, kGbThreads, 0, st>>>(p);
+  MB_LAUNCH_CHECK("gb_accumulate_kernel");
   return 0;
 }
 
@@ -369,40 +469,43 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   p.flags = t->flags;
   p.meta = t->meta;
   p.keys = keys;
+  bool aligned = aligned16(keys);
   for (int c = 0; c < t->nvals; ++c) {
     p.vals[c] = vals ? vals[c] : nullptr;
     p.pcnt[c] = pcnt ? pcnt[c] : nullptr;
     if ((t->flags & (MB200_GB_SUM | MB200_GB_COUNT)) && !p.vals[c]) return fail("groupby", "null value column");
     if (partial && (t->flags & MB200_GB_COUNT) && !p.pcnt[c]) return fail("groupby", "null partial count column");
+    aligned = aligned && aligned16(p.vals[c]);
   }
   p.psize = psize;
   if (partial && (t->flags & MB200_GB_SIZE) && !psize) return fail("groupby", "null partial size column");
   p.nrows = nrows;
-  int variant = gb_variant_from_env();
-  // the bulk-reduce variant covers plain sums of raw rows; counts / partial merges use variant 0
-  if (variant == 2 && (partial || (t->flags & MB200_GB_COUNT) || !(t->flags & MB200_GB_SUM))) variant = 0;
-  int occ = 0;
-  const long long nchunks = (nrows + 31) / 32;
-#define MB_GB_LAUNCH(V, P)                                                                                  \
-  do {                                                                                                      \
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_kernel<V, P>, kGbThreads, 0)); \
-    long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);                                          \
-    const long long need = (nchunks + kGbWarps - 1) / kGbWarps;                                             \
-    if (grid > need) grid = need;                                                                           \
-    gb_accumulate_kernel<V, P><<<(unsigned)grid, kGbThreads, 0, st>>>(p);                                   \
-  } while (0)
-  if (variant == 2) {
-    MB_GB_LAUNCH(2, false);
-  } else if (variant == 0) {
-    if (partial) MB_GB_LAUNCH(0, true);
-    else MB_GB_LAUNCH(0, false);
-  } else {
-    if (partial) MB_GB_LAUNCH(1, true);
-    else MB_GB_LAUNCH(1, false);
+  const int variant = gb_variant_from_env();
+
+  if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
+    const long long ntiles = nrows / kTileRows;
+    const size_t smem = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
+    MB_CUDA(cudaFuncSetAttribute(gb_accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_tma_kernel, kGbTmaThreads, smem));
+    long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
+    if (grid > ntiles) grid = ntiles;
+    gb_accumulate_tma_kernel<<<(unsigned)grid, kGbTmaThreads, smem, st>>>(p, ntiles);
+    MB_LAUNCH_CHECK("gb_accumulate_tma_kernel");
+    const long long done = ntiles * kTileRows;
+    if (done == nrows) return 0;
+    // ragged tail (< 256 rows) goes through the direct-load kernel
+    p.keys = keys + done;
+    for (int c = 0; c < t->nvals; ++c)
+      if (p.vals[c]) p.vals[c] = static_cast<const double*>(p.vals[c]) + done;
+    p.nrows = nrows - done;
   }
-#undef MB_GB_LAUNCH
-  MB_LAUNCH_CHECK("gb_accumulate_kernel");
-  return 0;
+  if (variant == 2) {
+    if (partial) return launch_ldg<1, true>(p, dp, st);
+    return launch_ldg<1, false>(p, dp, st);
+  }
+  if (partial) return launch_ldg<0, true>(p, dp, st);
+  return launch_ldg<0, false>(p, dp, st);
 }
 
 }  // namespace mb200
@@ -516,18 +619,18 @@ extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64
   if (ngroups == 0) return 0;
   if (!scratch) return fail("mb200_gb_emit", "null scratch");
   cudaStream_t st = (cudaStream_t)stream;
-  GbMeta m;
-  MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, st));
-  MB_CUDA(cudaStreamSynchronize(st));
-  if (m.overflow) return fail("mb200_gb_emit", "table overflowed: recreate with a larger group capacity");
-
   char* s = static_cast<char*>(scratch);
   long long* keys_by_gid = reinterpret_cast<long long*>(s);
   long long* perm = reinterpret_cast<long long*>(s + (size_t)ngroups * 8);
   size_t off = ((size_t)ngroups * 16 + 255) & ~(size_t)255;
   char* sort_s = s + off;
-  gb_collect_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->gcap, keys_by_gid, perm);
+  gb_collect_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->gcap, keys_by_gid, perm,
+                                                                      t->meta);
   MB_LAUNCH_CHECK("gb_collect_kernel");
+  GbMeta m;
+  MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, st));
+  MB_CUDA(cudaStreamSynchronize(st));
+  if (m.overflow) return fail("mb200_gb_emit", "table overflowed: recreate with a larger group capacity");
   if (sort) {
     long long* tk = reinterpret_cast<long long*>(sort_s);
     long long* tp = reinterpret_cast<long long*>(sort_s + (size_t)ngroups * 8);

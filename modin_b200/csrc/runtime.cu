@@ -32,6 +32,14 @@ int dev_props(DevProps* out) {
     g_props[dev].cc_major = p.major;
     g_props[dev].cc_minor = p.minor;
     g_props[dev].smem_optin = p.sharedMemPerBlockOptin;
+    // Stream-ordered allocations (group / join tables) come from the device's default pool; keep freed
+    // memory in the pool instead of returning it to the OS at every synchronisation (default threshold 0),
+    // otherwise each groupby step pays for re-mapping ~100 MB of table memory.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g_props_ok[dev] = true;
   }
   *out = g_props[dev];

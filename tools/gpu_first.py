@@ -271,9 +271,19 @@ def bandwidth_groupby(log2n):
             ng = C.c_int64()
             ov = C.c_int()
             _lib.check(lib.mb200_gb_ngroups(tab, C.byref(ng), C.byref(ov), st))
-            report(bench=f"groupby_sum_env{variant}", rows=n, G=G, V=W, ngroups=ng.value, overflow=ov.value,
+            report(bench=f"groupby_sum_warm_env{variant}", rows=n, G=G, V=W, ngroups=ng.value, overflow=ov.value,
                    ms_best=best, ms_med=med, GBps=n * 72 / 1e9 / best * 1e3, rows_per_s=n / best * 1e3)
             _lib.check(lib.mb200_gb_destroy(tab, st))
+
+            # cold: a fresh table per pass (create + memset + all inserts + accumulate), as in a real groupby
+            def cold():
+                t2 = C.c_void_p()
+                _lib.check(lib.mb200_gb_create(C.byref(t2), G + 16, W, _lib.GB_SUM, st))
+                _lib.check(lib.mb200_gb_accumulate(t2, keys.data_ptr(), cp, n, st))
+                _lib.check(lib.mb200_gb_destroy(t2, st))
+            best, med = timeit(cold, iters=3, warm=1)
+            report(bench=f"groupby_sum_cold_env{variant}", rows=n, G=G, V=W, ms_best=best, ms_med=med,
+                   GBps=n * 72 / 1e9 / best * 1e3, rows_per_s=n / best * 1e3)
 
 
 if __name__ == "__main__":
