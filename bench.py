@@ -68,12 +68,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_for(kernel: str):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), if it
-    was taken on this exact configuration; else None."""
+def traffic_for(kernel: str, rows_local: int = 0):
+    """DRAM bytes per launch of `kernel`, from the committed `ncu --set full` capture
+    (profiles/traffic.json, taken at 2^27 rows) scaled linearly to this run's local row count;
+    None when no capture exists for the kernel."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(kernel)
+        t = json.load(open(path))
+        ent = t.get(kernel)
+        if not ent:
+            return None
+        return float(ent["dram_bytes"]) * (rows_local / float(t["rows"]))
     except Exception:
         return None
 
@@ -279,7 +284,7 @@ def run_b200_arm(args):
     achieved = alg_bytes_local / (kernel_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "map_kernel<AFFINE,f64> (256-bit column sweep)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic_for("map_affine"), "peak_source": peak_src,
+                "traffic": traffic_for("map_affine", rows_local), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_local, "launch_ms": kernel_ms}  # fmt: skip
 
     also = []
@@ -296,7 +301,7 @@ def run_b200_arm(args):
                      "unit": UNIT, "ms_per_step": ms_s,
                      "roofline": {"bound": "hbm", "kernel": "reduce_tma_kernel<SUM,f64>", "achieved": ach,
                                   "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                  "traffic": traffic_for("reduce_sum")}})  # fmt: skip
+                                  "traffic": traffic_for("reduce_sum", rows_local)}})  # fmt: skip
         # ---- GroupByReduce: groupby('key').sum(), G = 1e6 int64 keys, 8 float64 values (C4)
         del a
         torch.cuda.empty_cache()
@@ -318,7 +323,7 @@ def run_b200_arm(args):
                      "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
                      "roofline": {"bound": "hbm", "kernel": "gb_accumulate_kernel (L2-resident hash aggregate)",
                                   "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                  "traffic": traffic_for("groupby_sum")}})  # fmt: skip
+                                  "traffic": traffic_for("groupby_sum", rows_local)}})  # fmt: skip
         del g
         torch.cuda.empty_cache()
     else:

@@ -103,64 +103,92 @@ struct GbParams {
   const void* pcnt[MB200_MAX_COLS];   // partial counts (PARTIAL only)
   const long long* psize;             // partial sizes (PARTIAL only)
   long long nrows;
+  int policy_mode;  // unused (kept for experiments)
+  int prefetch;     // TMA kernel: L2-prefetch the next tile's probe slots (MB200_GB_PREFETCH=0 disables)
 };
 
-// ---- table accesses: relaxed GPU-scope, L2 evict-last (keep the table resident under the stream)
-__device__ __forceinline__ void red_add_f64(double* p, double v, uint64_t pol) {
-  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+// ---- table accesses: relaxed GPU-scope.  L2 eviction-priority hints on these (evict_last / evict_normal
+// via createpolicy + .L2::cache_hint) were measured to make no difference at any table size
+// (gpurun_out/gb_probe.log), so the plain forms are used; `pol` is kept in the signatures for experiments.
+__device__ __forceinline__ void red_add_f64(double* p, double v, uint64_t) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ void red_add_u64(long long* p, long long v, uint64_t pol) {
-  asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+__device__ __forceinline__ void red_add_u64(long long* p, long long v, uint64_t) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void ld_slot(const Slot* s, long long& key, int& gid, uint64_t pol) {
+__device__ __forceinline__ void ld_slot(const Slot* s, long long& key, int& gid, uint64_t) {
   unsigned long long a, b;
-  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
-               : "=l"(a), "=l"(b)
-               : "l"(s), "l"(pol)
-               : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s) : "memory");
   key = (long long)a;
   gid = (int)(unsigned int)(b & 0xffffffffULL);
 }
-__device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_t pol) {
+__device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_t) {
   const unsigned long long b = (unsigned long long)(unsigned int)gid;
-  asm volatile("st.relaxed.gpu.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(s),
-               "l"((unsigned long long)key), "l"(b), "l"(pol)
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(s), "l"((unsigned long long)key), "l"(b)
                : "memory");
 }
+__device__ __forceinline__ uint64_t table_policy(int) { return 0; }
 
-// Dense group id of every lane's key (gcap = table overflowed).  Must be called by all 32 lanes.
-__device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t pol) {
+// Probe step shared by the lookup and the insert path.  All probe loops below have WARP-UNIFORM trip
+// counts (the continue condition is a __any_sync vote), so every lane leaves a loop together.  A
+// data-dependent `break` per lane is legal under independent thread scheduling but nvcc then lets
+// the early finishers run ahead: the warp executed the whole accumulate phase in ~1.6 diverged
+// groups (ncu: REDG 54 M warp-instructions instead of 33.5 M, smsp__inst_executed 1.8x; 5.7 ms
+// instead of 3.8 ms per 2^27 rows).
+//
+// Warp-wide lookup: dense group id of each leader's key, or -1 when its probe chain ends at an empty
+// or in-flight slot (`slot` is left at that position).  Read-only: the steady-state path.
+__device__ __forceinline__ int probe_find(const GbParams& p, long long k, bool is_leader, unsigned int& slot) {
+  int found = -1;
+  long long probes = 0;
+  bool active = is_leader;
+  while (__any_sync(0xffffffffu, active)) {
+    if (active) {
+      long long sk;
+      int g;
+      ld_slot(&p.slots[slot], sk, g, 0);
+      const bool hit = (g >= 0) && (sk == k);
+      if (hit) found = g;
+      if (hit || g < 0 || ++probes > p.cap) active = false;
+      else slot = (slot + 1) & p.mask;
+    }
+  }
+  return found;
+}
+
+// Slow path, entered by the WHOLE warp (uniform branch) when some leader's key is not in the table yet.
+// Rounds: every pending leader walks its chain (uniform-trip loop) until it finds its key, claims an
+// empty slot with a CAS, or meets a slot that somebody else is publishing (retry next round); the
+// round's winners take consecutive dense ids from ONE atomicAdd and publish {key, gid} with a 128-bit
+// store.  No lane ever spins on another lane of its own warp.
+__device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool is_leader, int gid,
+                                          unsigned int slot) {
   const int lane = threadIdx.x & 31;
   const int gcap = (int)p.gcap;
-  const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
-  const int leader = __ffs(peers) - 1;
-  const bool is_leader = (lane == leader);
-  int gid = -1;
-  unsigned int slot = hash_key(k) & p.mask;
   long long probes = 0;
-  unsigned int pending = __ballot_sync(0xffffffffu, is_leader);
-  while (pending) {
+  while (__any_sync(0xffffffffu, is_leader && gid < 0)) {
     bool won = false;
-    if (is_leader && gid < 0) {
-      for (;;) {
+    bool walking = is_leader && gid < 0;
+    while (__any_sync(0xffffffffu, walking)) {
+      if (walking) {
         long long sk;
         int g;
-        ld_slot(&p.slots[slot], sk, g, pol);
+        ld_slot(&p.slots[slot], sk, g, 0);
         if (g >= 0) {
           if (sk == k) {
             gid = g;
-            break;
-          }
-          slot = (slot + 1) & p.mask;
-          if (++probes > p.cap) {  // table full of other keys
+            walking = false;
+          } else if (++probes > p.cap) {  // table full of other keys
             p.meta->overflow = 1;
             gid = gcap;
-            break;
+            walking = false;
+          } else {
+            slot = (slot + 1) & p.mask;
           }
-          continue;
+        } else {
+          if (g == -1) won = (atomicCAS(&p.slots[slot].gid, -1, -2) == -1);
+          walking = false;  // claimed it, or someone else is publishing this slot: look again next round
         }
-        if (g == -1) won = (atomicCAS(&p.slots[slot].gid, -1, -2) == -1);
-        break;  // claimed it, or someone else is publishing this slot: look again next round
       }
     }
     // dense ids for this round's winners: one atomicAdd per warp
@@ -176,12 +204,23 @@ __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint6
           p.meta->overflow = 1;
           ng = gcap;
         }
-        st_slot(&p.slots[slot], k, ng, pol);
+        st_slot(&p.slots[slot], k, ng, 0);
         gid = ng;
       }
     }
-    pending = __ballot_sync(0xffffffffu, is_leader && gid < 0);
   }
+  return gid;
+}
+
+// Dense group id of every lane's key (gcap = table overflowed).  Must be called by all 32 lanes.
+__device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
+  const int leader = __ffs(peers) - 1;
+  const bool is_leader = (lane == leader);
+  unsigned int slot = hash_key(k) & p.mask;
+  int gid = probe_find(p, k, is_leader, slot);
+  if (__any_sync(0xffffffffu, is_leader && gid < 0)) gid = insert_rounds(p, k, is_leader, gid, slot);
   return __shfl_sync(0xffffffffu, gid, leader);
 }
 
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_
   const long long wstride = (long long)gridDim.x * kGbWarps;
   const int gcap = (int)p.gcap;
   const uint64_t pol = l2_policy_evict_first();
-  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t keep = table_policy(p.policy_mode);
   for (long long ch = (long long)blockIdx.x * kGbWarps + warp; ch < nchunks; ch += wstride) {
     const long long base = ch << 5;
     const long long row = base + lane;
@@ -311,13 +350,23 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     return;
   }
   // ---------------- consumers: warp w owns rows [32w, 32w + 32) of every tile
-  const uint64_t keep = l2_policy_evict_last();
+  const uint64_t keep = table_policy(p.policy_mode);
   const int c = lane & 7;
   for (long long k = 0; k < nmine; ++k) {
     const int s = (int)(k % kGbStages);
     mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
     const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
     const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
+    if (p.prefetch && k + 1 < nmine) {
+      // the next tile's keys are (normally) already in shared memory: pull the first probe slot of each of
+      // this warp's next 32 rows into L2 now, one tile ahead of the dependent 128-bit slot load
+      const int s1 = (int)((k + 1) % kGbStages);
+      mbar_wait(&full[s1], (uint32_t)(((k + 1) / kGbStages) & 1));
+      const long long nk =
+          reinterpret_cast<const long long*>(smem_raw + (size_t)s1 * kStageBytes)[warp * 32 + lane];
+      const Slot* ns = &p.slots[hash_key(nk) & p.mask];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ns));
+    }
     const int gid = resolve_gid(p, key, keep);
     if ((p.flags & MB200_GB_SIZE) && gid < gcap) red_add_u64(p.size + gid, 1LL, keep);
     const double* vt = stage + kTileColStride + warp * 32;  // value column 0, this warp's rows
@@ -428,13 +477,17 @@ static long long next_pow2(long long v) {
   return p;
 }
 
-// MB200_GB_VARIANT: unset/0 = TMA-staged (default), 1 = direct loads + 8-lanes-per-row REDs,
-// 2 = direct loads + lane == row REDs.  Read per call so one process can compare them.
-static int gb_variant_from_env() {
+// MB200_GB_VARIANT: 0 = TMA-staged tiles, 1 = direct loads + 8-lanes-per-row REDs, 2 = direct loads +
+// lane == row REDs; unset = pick by table footprint.  Read per call so one process can compare them.
+// Measured (2^27 rows, V = 8, fresh table per pass): G = 65536 (6 MB table) TMA 3.41 ms vs direct 3.68 ms;
+// G = 1e6 (96 MB table, only ~35 % L2 hits) TMA 5.03 ms vs direct 4.47 ms -- with a table that misses L2
+// the probe chain is DRAM-latency bound and the direct kernel's 40 resident warps beat the TMA kernel's 32.
+static int gb_variant_from_env(size_t table_bytes, size_t l2_bytes) {
   const char* e = getenv("MB200_GB_VARIANT");
+  if (e && e[0] == '0') return 0;
   if (e && e[0] == '1') return 1;
   if (e && e[0] == '2') return 2;
-  return 0;
+  return table_bytes * 2 <= l2_bytes ? 0 : 1;
 }
 
 template <int VARIANT, bool PARTIAL>
@@ -480,7 +533,16 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   p.psize = psize;
   if (partial && (t->flags & MB200_GB_SIZE) && !psize) return fail("groupby", "null partial size column");
   p.nrows = nrows;
-  const int variant = gb_variant_from_env();
+  {
+    const char* e = getenv("MB200_GB_POLICY");  // none | last | normal
+    p.policy_mode = (e && e[0] == 'l') ? 1 : ((e && e[0] == 'n' && e[1] == 'o' && e[2] == 'r') ? 2 : 0);
+    const char* pf = getenv("MB200_GB_PREFETCH");
+    p.prefetch = (pf && pf[0] == '1') ? 1 : 0;  // measured: no gain (the limiter is random-sector DRAM traffic)
+  }
+  const size_t table_bytes = (size_t)t->cap * sizeof(Slot) + (size_t)t->gcap * t->vstride * 8 *
+                                                                  (((t->flags & MB200_GB_SUM) ? 1 : 0) +
+                                                                   ((t->flags & MB200_GB_COUNT) ? 1 : 0));
+  const int variant = gb_variant_from_env(table_bytes, dp.l2_bytes);
 
   if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
