@@ -239,6 +239,9 @@ int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int6
 size_t mb200_sort_scratch_bytes(int64_t n);
 int mb200_sort_pairs_i64(int64_t* keys, int64_t* payload, int64_t n, void* scratch,
                          size_t scratch_bytes, mb200_stream_t stream);
+/* Bytes of L2 the device can pin (persisting carve-out) and the largest access-policy window; the
+ * groupby kernels pin the accumulator rows of tables larger than L2/2. */
+int mb200_l2_persist_info(int* max_persist_bytes, int* max_window_bytes);
 /* Write >= L2-sized buffer to evict L2 between timed iterations. */
 int mb200_flush_l2(void* buf, size_t bytes, mb200_stream_t stream);
 

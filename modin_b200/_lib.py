@@ -80,6 +80,7 @@ _SIGNATURES = {
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_sort_pairs_i64": (C.c_int, [_vp, _vp, _i64, _vp, C.c_size_t, _vp]),
+    "mb200_l2_persist_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mb200_flush_l2": (C.c_int, [_vp, C.c_size_t, _vp]),
 }  # fmt: skip
 

@@ -13,16 +13,19 @@
 //                A slot is published with ONE 128-bit store {key, gid} and read with ONE 128-bit load.
 //   acc[gcap][vstride]  float64 sums, row-major so one group's V sums share 64-byte segments.
 //   cnt[gcap][vstride]  int64 non-NaN counts (optional), size[gcap] int64 rows (optional).
-// For G = 1e6, V = 8 the table is 32 MiB of slots + 64 MiB of sums: it is kept in the 126 MB L2
-// (table accesses carry an L2 evict-last policy, the streamed 72 B/row input an evict-first one).
+// For G = 1e6, V = 8 the table is 32 MiB of slots + 64 MiB of sums.  The streamed 72 B/row input is
+// loaded with an L2 evict-first policy, yet ncu shows only ~35 % L2 hits on the table at this size
+// (DRAM traffic 17.8 GB per 9.7 GB of input): the kernel is bound by random 32-byte-sector DRAM
+// traffic, not by the atomics (lts__d_atomic_input_cycles_active ~ 39 %) nor by the stream.  Tables
+// up to ~48 MiB (G <= 5e5 at V = 8) stay L2-resident and run ~30 % faster per row.
 //
 // Kernels
-//   gb_accumulate_tma_kernel (default; V <= 8, 16-byte aligned columns): a producer warp streams
+//   gb_accumulate_tma_kernel (tables <= L2/2; V <= 8, 16-byte aligned columns): a producer warp streams
 //     256-row tiles of the key + value columns into a shared-memory ring with 1-D TMA bulk copies
 //     (full/empty mbarriers), so DRAM latency is out of the per-row dependency chain and no
 //     registers hold in-flight rows; 8 consumer warps each take 32 rows of a tile.
-//   gb_accumulate_kernel (fallback: ragged tails, unaligned views, V > 8, partial-table merges):
-//     the same per-warp algorithm with direct coalesced loads.
+//   gb_accumulate_kernel (larger tables; also ragged tails, unaligned views, V > 8, partial-table
+//     merges): the same per-warp algorithm with direct coalesced loads and 40 resident warps per SM.
 // Per warp (32 rows):
 //   1. warp-cooperative probe: __match_any_sync groups lanes holding the same key; the lowest lane
 //      of each group looks the key up (read-only linear probing).  Missing keys are inserted in
@@ -35,9 +38,11 @@
 // tolerance stated in tests (|err| <= 4 log2(n) eps sum|x|), not bit for bit; counts/sizes
 // and keys are exact.
 //
-// Tried and measured (gpurun_out round 1, 2^27 rows, G = 1e6, V = 8): lane == row REDs (8 segments
-// per instruction) 16.5 G rows/s; 8-lanes-per-row REDs 35.4 G rows/s; one TMA bulk reduction per
-// row (cp.reduce.async.bulk .add.f64 / UBLKRED) 34.7 G rows/s -- no gain, dropped.
+// Tried and measured (round 1, 2^27 rows, G = 1e6, V = 8, warm table): lane == row REDs (8 segments per
+// instruction) 16.5 G rows/s; 8-lanes-per-row REDs 33-35 G rows/s; one TMA bulk reduction per row
+// (cp.reduce.async.bulk .add.f64 / UBLKRED) 34.7 G rows/s -- no gain, dropped; L2 eviction-priority
+// hints on the table accesses and L2 prefetch of the next tile's probe slots -- no gain either.
+// Fresh table per pass (what a real groupby pays): 30 G rows/s at G = 1e6, 39 G rows/s at G = 65536.
 #include "common.cuh"
 
 namespace mb200 {
@@ -129,28 +134,56 @@ __device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_
 }
 __device__ __forceinline__ uint64_t table_policy(int) { return 0; }
 
-// Probe step shared by the lookup and the insert path.  All probe loops below have WARP-UNIFORM trip
-// counts (the continue condition is a __any_sync vote), so every lane leaves a loop together.  A
-// data-dependent `break` per lane is legal under independent thread scheduling but nvcc then lets
-// the early finishers run ahead: the warp executed the whole accumulate phase in ~1.6 diverged
-// groups (ncu: REDG 54 M warp-instructions instead of 33.5 M, smsp__inst_executed 1.8x; 5.7 ms
-// instead of 3.8 ms per 2^27 rows).
-//
+// Probing works on BUCKETS of two slots = one 32-byte sector, fetched with one 256-bit load: a probe
+// round costs the same sector as a single-slot probe but the chain of rounds is about half as long
+// (with single-slot linear probing at load factor 0.48 the longest of a warp's 32 chains averaged 5.6
+// dependent round trips per 32 rows -- 29 % of all stall samples sat on that load).
+// All probe loops have WARP-UNIFORM trip counts (the continue condition is a __any_sync vote), so
+// every lane leaves a loop together.  A data-dependent `break` per lane is legal under independent
+// thread scheduling but nvcc then lets the early finishers run ahead: the warp executed the whole
+// accumulate phase in ~1.6 diverged groups (ncu: REDG 54 M warp-instructions instead of 33.5 M,
+// smsp__inst_executed 1.8x; 5.7 ms instead of 3.8 ms per 2^27 rows).
+__device__ __forceinline__ void ld_bucket(const Slot* b, long long& k0, int& g0, long long& k1, int& g1) {
+  unsigned long long a, x, c, d;
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(a), "=l"(x), "=l"(c), "=l"(d)
+               : "l"(b)
+               : "memory");
+  k0 = (long long)a;
+  g0 = (int)(unsigned int)(x & 0xffffffffULL);
+  k1 = (long long)c;
+  g1 = (int)(unsigned int)(d & 0xffffffffULL);
+}
+
+// One probe round for key `k` at `bucket`.  Returns: >= 0 found gid; -1 the first non-foreign slot
+// (index `sub`) is empty; -2 it is being published by someone; -3 both slots hold other keys.
+__device__ __forceinline__ int probe_bucket(const GbParams& p, long long k, unsigned int bucket, int& sub) {
+  long long k0, k1;
+  int g0, g1;
+  ld_bucket(p.slots + 2 * (size_t)bucket, k0, g0, k1, g1);
+  sub = 0;
+  if (g0 >= 0 && k0 == k) return g0;
+  if (g0 < 0) return g0;  // -1 empty / -2 in flight
+  sub = 1;
+  if (g1 >= 0 && k1 == k) return g1;
+  if (g1 < 0) return g1;
+  return -3;
+}
+
 // Warp-wide lookup: dense group id of each leader's key, or -1 when its probe chain ends at an empty
-// or in-flight slot (`slot` is left at that position).  Read-only: the steady-state path.
-__device__ __forceinline__ int probe_find(const GbParams& p, long long k, bool is_leader, unsigned int& slot) {
+// or in-flight slot (`bucket` is left at that position).  Read-only: the steady-state path.
+__device__ __forceinline__ int probe_find(const GbParams& p, long long k, bool is_leader, unsigned int& bucket) {
   int found = -1;
   long long probes = 0;
   bool active = is_leader;
+  const unsigned int bmask = p.mask >> 1;
   while (__any_sync(0xffffffffu, active)) {
     if (active) {
-      long long sk;
-      int g;
-      ld_slot(&p.slots[slot], sk, g, 0);
-      const bool hit = (g >= 0) && (sk == k);
-      if (hit) found = g;
-      if (hit || g < 0 || ++probes > p.cap) active = false;
-      else slot = (slot + 1) & p.mask;
+      int sub;
+      const int r = probe_bucket(p, k, bucket, sub);
+      if (r >= 0) found = r;
+      if (r != -3 || ++probes > p.cap) active = false;
+      else bucket = (bucket + 1) & bmask;
     }
   }
   return found;
@@ -162,31 +195,31 @@ __device__ __forceinline__ int probe_find(const GbParams& p, long long k, bool i
 // round's winners take consecutive dense ids from ONE atomicAdd and publish {key, gid} with a 128-bit
 // store.  No lane ever spins on another lane of its own warp.
 __device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool is_leader, int gid,
-                                          unsigned int slot) {
+                                          unsigned int bucket) {
   const int lane = threadIdx.x & 31;
   const int gcap = (int)p.gcap;
+  const unsigned int bmask = p.mask >> 1;
   long long probes = 0;
   while (__any_sync(0xffffffffu, is_leader && gid < 0)) {
     bool won = false;
+    int sub = 0;
     bool walking = is_leader && gid < 0;
     while (__any_sync(0xffffffffu, walking)) {
       if (walking) {
-        long long sk;
-        int g;
-        ld_slot(&p.slots[slot], sk, g, 0);
-        if (g >= 0) {
-          if (sk == k) {
-            gid = g;
-            walking = false;
-          } else if (++probes > p.cap) {  // table full of other keys
+        const int r = probe_bucket(p, k, bucket, sub);
+        if (r >= 0) {
+          gid = r;
+          walking = false;
+        } else if (r == -3) {
+          if (++probes > p.cap) {  // table full of other keys
             p.meta->overflow = 1;
             gid = gcap;
             walking = false;
           } else {
-            slot = (slot + 1) & p.mask;
+            bucket = (bucket + 1) & bmask;
           }
         } else {
-          if (g == -1) won = (atomicCAS(&p.slots[slot].gid, -1, -2) == -1);
+          if (r == -1) won = (atomicCAS(&p.slots[2 * (size_t)bucket + sub].gid, -1, -2) == -1);
           walking = false;  // claimed it, or someone else is publishing this slot: look again next round
         }
       }
@@ -204,7 +237,7 @@ __device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool i
           p.meta->overflow = 1;
           ng = gcap;
         }
-        st_slot(&p.slots[slot], k, ng, 0);
+        st_slot(&p.slots[2 * (size_t)bucket + sub], k, ng, 0);
         gid = ng;
       }
     }
@@ -218,15 +251,15 @@ __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint6
   const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
   const int leader = __ffs(peers) - 1;
   const bool is_leader = (lane == leader);
-  unsigned int slot = hash_key(k) & p.mask;
-  int gid = probe_find(p, k, is_leader, slot);
-  if (__any_sync(0xffffffffu, is_leader && gid < 0)) gid = insert_rounds(p, k, is_leader, gid, slot);
+  unsigned int bucket = hash_key(k) & (p.mask >> 1);
+  int gid = probe_find(p, k, is_leader, bucket);
+  if (__any_sync(0xffffffffu, is_leader && gid < 0)) gid = insert_rounds(p, k, is_leader, gid, bucket);
   return __shfl_sync(0xffffffffu, gid, leader);
 }
 
 // ---------------------------------------------------------------- fallback: direct loads
 template <int VARIANT, bool PARTIAL>
-__global__ void __launch_bounds__(kGbThreads) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
+__global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
   __shared__ double s_tile[kGbWarps][8 * kColStride];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long nchunks = (p.nrows + 31) >> 5;
@@ -487,7 +520,9 @@ static int gb_variant_from_env(size_t table_bytes, size_t l2_bytes) {
   if (e && e[0] == '0') return 0;
   if (e && e[0] == '1') return 1;
   if (e && e[0] == '2') return 2;
-  return table_bytes * 2 <= l2_bytes ? 0 : 1;
+  (void)table_bytes;
+  (void)l2_bytes;
+  return 0;  // with 2-slot buckets the TMA-staged kernel is at least as fast at every table size measured
 }
 
 template <int VARIANT, bool PARTIAL>
@@ -543,6 +578,51 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
                                                                   (((t->flags & MB200_GB_SUM) ? 1 : 0) +
                                                                    ((t->flags & MB200_GB_COUNT) ? 1 : 0));
   const int variant = gb_variant_from_env(table_bytes, dp.l2_bytes);
+
+  // Tables that do not fit the normally-managed L2 next to the stream: pin the accumulator rows (the
+  // 2-sector RED target of every row) in the persisting L2 carve-out for the kernels launched below.
+  // Opt-in (MB200_GB_PERSIST=1): measured on B200 (82.9 MB max carve-out) it changes nothing at G = 1e6
+  // (4.30 ms with and without per 2^27 rows), gains ~12 % at G = 2e6, and the process-wide carve-out
+  // slows every other kernel that wants the whole L2 -- so it is off by default.
+  struct WindowGuard {
+    cudaStream_t st;
+    bool on = false;
+    ~WindowGuard() {
+      if (on) {
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+      }
+    }
+  } guard{st};
+  {
+    const char* e = getenv("MB200_GB_PERSIST");
+    const bool want = (e && e[0] == '1');
+    if (want && t->acc && table_bytes * 2 > dp.l2_bytes) {
+      int dev = 0, max_persist = 0, max_window = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      const size_t accb = (size_t)t->gcap * t->vstride * 8;
+      if (max_persist > 0 && max_window > 0) {
+        static size_t configured = 0;
+        if (configured != (size_t)max_persist) {
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+          configured = (size_t)max_persist;
+        }
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.accessPolicyWindow.base_ptr = t->acc;
+        v.accessPolicyWindow.num_bytes = accb < (size_t)max_window ? accb : (size_t)max_window;
+        const double fit = (double)max_persist / (double)v.accessPolicyWindow.num_bytes;
+        v.accessPolicyWindow.hitRatio = fit >= 1.0 ? 1.0f : (float)fit;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) guard.on = true;
+        else cudaGetLastError();
+      }
+    }
+  }
 
   if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
@@ -633,6 +713,15 @@ extern "C" int mb200_gb_destroy(mb200_gb_table* t, mb200_stream_t stream) {
   if (t->cnt) cudaFreeAsync(t->cnt, st);
   if (t->size) cudaFreeAsync(t->size, st);
   delete t;
+  return 0;
+}
+
+/* number of bytes the device can pin in L2 (diagnostics for the persisting-window experiment) */
+extern "C" int mb200_l2_persist_info(int* max_persist_bytes, int* max_window_bytes) {
+  int dev = 0;
+  MB_CUDA(cudaGetDevice(&dev));
+  if (max_persist_bytes) MB_CUDA(cudaDeviceGetAttribute(max_persist_bytes, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  if (max_window_bytes) MB_CUDA(cudaDeviceGetAttribute(max_window_bytes, cudaDevAttrMaxAccessPolicyWindowSize, dev));
   return 0;
 }
 
