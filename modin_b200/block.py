@@ -276,6 +276,31 @@ class DeviceBlock:
         return DeviceBlock(cols, self.columns, nrows=stop - start, range_start=self.range_start + start,
                            index_cols=icols, index_names=self.index_names, index_host=ihost)  # fmt: skip
 
+    @property
+    def T(self) -> "DeviceBlock":
+        """Transpose of a VECTOR-shaped block (1 x W or n x 1), on device.  Modin's API layer turns the
+        1 x W result frame of a reduction into a Series through ``qc.transpose()`` -> ``lambda df: df.T``
+        (modin/pandas/dataframe.py ``_reduce_dimension``; df.py:4745-4775).  General 2-D transposes are not
+        on this path."""
+        t = torch_mod()
+        if self.nrows == 1 and self.cols:
+            dts = {c.dtype for c in self.cols}
+            dtype = self.cols[0].dtype if len(dts) == 1 else np.result_type(*dts)
+            parts = [c.data if c.dtype == dtype else c.data.to(_torch_dtype(dtype)) for c in self.cols]
+            col = DeviceColumn(t.cat(parts), dtype)
+            blk = DeviceBlock([col], self.index, nrows=len(self.cols), index_host=self.columns)
+            blk.replicated = self.replicated
+            return blk
+        if len(self.cols) == 1 and self.nrows <= 4096:
+            c = self.cols[0]
+            cols = [DeviceColumn(c.data[i : i + 1], c.dtype) for i in range(self.nrows)]
+            blk = DeviceBlock(cols, self.index, nrows=1, index_host=self.columns)
+            blk.replicated = self.replicated
+            return blk
+        if not self.cols or self.nrows == 0:
+            return DeviceBlock([], self.index, nrows=len(self.cols), index_host=self.columns)
+        raise NotImplementedError("general 2-D transposition is not on the B200 path")
+
     def column(self, label) -> DeviceColumn:
         loc = self.columns.get_loc(label)
         if not isinstance(loc, (int, np.integer)):

@@ -1,0 +1,284 @@
+"""Plug the B200 execution in behind the real ``modin.pandas`` (when Modin is importable).
+
+``register()`` adds an execution ``(storage_format="Arrow", engine="B200")`` to Modin through its
+public hooks only -- no reference file is edited:
+
+* ``StorageFormat.add_option`` / ``Engine.add_option`` / ``Backend.register_backend``
+  (modin/config/envvars.py:271-277, 449-472);
+* a factory class injected as ``factories.ArrowOnB200Factory`` -- the dispatcher looks factories up
+  by exactly that name (modin/core/execution/dispatching/factories/dispatcher.py:143-172);
+* ``BaseIO`` subclass naming the frame and query-compiler classes (modin/core/io/io.py:51-52).
+
+The classes are Modin's OWN ``PandasDataframe`` / ``PandasDataframePartitionManager`` /
+``PandasQueryCompiler`` with this package's device classes mixed in in front, so every non-hot
+method keeps Modin's behaviour while the hot path (Map / Binary / TreeReduce / GroupByReduce /
+broadcast merge) is re-registered with device functors through Modin's unchanged operator
+templates.  ``modin.set_execution(engine="B200", storage_format="Arrow")`` then makes
+``import modin.pandas as pd`` a drop-in.
+
+The image ships pandas 3 while the reference pins pandas<2.4; ``apply_pandas3_shims()`` restores the
+five removed names / keyword arguments Modin's import and hot path need.  It touches
+only pandas attributes, never Modin.
+"""
+
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import pandas
+
+_REGISTERED = None
+
+
+def apply_pandas3_shims() -> None:
+    """Make ``import modin`` and its hot path work under pandas 3 (no-ops on pandas 2.x)."""
+    import pandas.core.series as pcs
+    import pandas.io.parsers.base_parser as bp
+
+    def _stub(*a, **k):
+        """Removed from pandas 3; not on the B200 path."""
+        raise NotImplementedError
+
+    if not hasattr(pandas, "read_gbq"):
+        pandas.read_gbq = _stub
+    if not hasattr(pcs, "_coerce_method"):
+
+        def _coerce_method(converter):
+            def wrapper(self):
+                if len(self) == 1:
+                    return converter(self.iloc[0])
+                raise TypeError(f"cannot convert the series to {converter}")
+
+            wrapper.__name__ = f"__{converter.__name__}__"
+            return wrapper
+
+        pcs._coerce_method = _coerce_method
+    if not hasattr(bp.ParserBase, "_validate_usecols_arg"):
+        bp.ParserBase._validate_usecols_arg = lambda self, usecols: (usecols, None)
+    for cls in (pandas.DataFrame, pandas.Series):
+        if getattr(cls.groupby, "_mb200_shim", False):
+            continue
+        g = cls.groupby
+        wrapped = functools.wraps(g)(lambda self, *a, axis=0, _g=g, **k: _g(self, *a, **k))
+        wrapped._mb200_shim = True
+        cls.groupby = wrapped
+        f = cls.fillna
+        cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: _f(self, *a, **k))
+
+
+def register(shims: bool | None = None):
+    """Register the execution with Modin and return the namespace of generated classes."""
+    global _REGISTERED
+    if _REGISTERED is not None:
+        return _REGISTERED
+    if shims is None:
+        shims = int(pandas.__version__.split(".")[0]) >= 3
+    if shims:
+        apply_pandas3_shims()
+
+    import modin.config as cfg
+    from modin.config.envvars import Execution
+    from modin.core.dataframe.algebra import Binary, GroupByReduce, Map, TreeReduce
+    from modin.core.dataframe.pandas.dataframe.dataframe import PandasDataframe
+    from modin.core.dataframe.pandas.partitioning.partition_manager import PandasDataframePartitionManager
+    from modin.core.execution.dispatching.factories import factories
+    from modin.core.io.io import BaseIO
+    from modin.core.storage_formats.pandas.query_compiler import PandasQueryCompiler
+
+    from . import functors as fx
+    from . import partitioning as bp
+    from .block import DeviceBlock
+    from .query_compiler import _dtypes_sum
+
+    # ---------------------------------------------------------------- partition manager
+    class B200OnModinPartitionManager(bp.B200PartitionManager, PandasDataframePartitionManager):
+        """Device classmethods first in the MRO; indexing / rebalancing helpers stay Modin's."""
+
+        _partition_class = bp.B200Partition
+        _column_partitions_class = bp.B200ColumnPartition
+        _row_partition_class = bp.B200RowPartition
+        _execution_wrapper = bp.B200Wrapper
+
+    # ---------------------------------------------------------------- core dataframe
+    class B200OnModinDataframe(PandasDataframe):
+        _partition_mgr_cls = B200OnModinPartitionManager
+
+        @property
+        def engine(self) -> str:  # df.py:137-148
+            return "B200"
+
+        @property
+        def storage_format(self) -> str:  # df.py:125-135
+            return "Arrow"
+
+        def _build_treereduce_func(self, axis, func):
+            """df.py:2081-2123: device reduce functors already return the 1 x W block labelled
+            ``__reduced__``; only pandas results need the Series -> frame conversion."""
+            pandas_wrapper = super()._build_treereduce_func(axis, func)
+
+            def _tree_reduce_func(df, *args, **kwargs):
+                if isinstance(df, DeviceBlock):
+                    result = func(df, *args, **kwargs)
+                    if isinstance(result, DeviceBlock):
+                        return result
+                    raise NotImplementedError(
+                        "this reduction has no device functor in modin_b200 (no pandas fallback on the B200 path)"
+                    )
+                return pandas_wrapper(df, *args, **kwargs)
+
+            return _tree_reduce_func
+
+        def _compute_dtypes(self, columns=None):
+            """df.py:472-520 runs a pandas lambda tree-reduce; device blocks carry their dtypes as host
+            metadata, so read them directly."""
+            series = [p.get().dtypes for p in self._partitions[0]] if self._partitions.size else []
+            dtypes = pandas.concat(series) if series else pandas.Series([], dtype=object)
+            dtypes.index = self.columns
+            if columns is not None:
+                dtypes = dtypes.loc[list(columns)]
+            return dtypes
+
+    # ---------------------------------------------------------------- GroupByReduce over device blocks
+    class B200GroupByReduce(GroupByReduce):
+        """alg/groupby.py: same template, but the per-block map / reduce bodies are the device functors
+        instead of ``df.groupby(...)`` on pandas blocks (alg/groupby.py:124-300)."""
+
+        @classmethod
+        def register_agg(cls, agg: str):
+            map_f, red_f = fx.DevGroupbyMap(agg), fx.DevGroupbyReduce(agg)
+
+            def caller(query_compiler, by, axis, groupby_kwargs, agg_args, agg_kwargs, drop=False, **kwargs):
+                if axis != 0 or not isinstance(by, type(query_compiler)) or len(by.columns) != 1:
+                    raise NotImplementedError("device groupby: one key column of the same frame, axis=0")
+                if not groupby_kwargs.get("as_index", True) or groupby_kwargs.get("level") is not None:
+                    raise NotImplementedError("device groupby: as_index=True, no level=")
+                new_frame = query_compiler._modin_frame.groupby_reduce(
+                    axis, by._modin_frame, lambda df, other=None, **kw: map_f(df, other),
+                    lambda df, **kw: red_f(df, **kw),
+                )
+                return query_compiler.__constructor__(new_frame)
+
+            return caller
+
+    # ---------------------------------------------------------------- query compiler
+    _f64 = lambda *a, **k: np.dtype("float64")  # noqa: E731
+
+    class B200OnModinQueryCompiler(PandasQueryCompiler):
+        # Map (qc.py:2036-2106)
+        abs = Map.register(fx.DevMap("abs"), dtypes="copy")
+        negative = Map.register(fx.DevMap("neg"), dtypes="copy")
+        isna = Map.register(fx.DevMap("isna"), dtypes=np.bool_)
+        notna = Map.register(fx.DevMap("notna"), dtypes=np.bool_)
+        # Binary (qc.py:535-624)
+        add = Binary.register(fx.DevBinary("add"), infer_dtypes="common_cast")
+        radd = Binary.register(fx.DevBinary("radd"), infer_dtypes="common_cast")
+        sub = Binary.register(fx.DevBinary("sub"), infer_dtypes="common_cast")
+        rsub = Binary.register(fx.DevBinary("rsub"), infer_dtypes="common_cast")
+        mul = Binary.register(fx.DevBinary("mul"), infer_dtypes="common_cast")
+        rmul = Binary.register(fx.DevBinary("rmul"), infer_dtypes="common_cast")
+        truediv = Binary.register(fx.DevBinary("truediv"), infer_dtypes="common_cast")
+        rtruediv = Binary.register(fx.DevBinary("rtruediv"), infer_dtypes="common_cast")
+        eq = Binary.register(fx.DevBinary("eq"), infer_dtypes="bool")
+        ne = Binary.register(fx.DevBinary("ne"), infer_dtypes="bool")
+        lt = Binary.register(fx.DevBinary("lt"), infer_dtypes="bool")
+        le = Binary.register(fx.DevBinary("le"), infer_dtypes="bool")
+        gt = Binary.register(fx.DevBinary("gt"), infer_dtypes="bool")
+        ge = Binary.register(fx.DevBinary("ge"), infer_dtypes="bool")
+        # TreeReduce (qc.py:976-1096)
+        count = TreeReduce.register(fx.DevReduce("count"), fx.DevReduce("count", phase="reduce"),
+                                    compute_dtypes=lambda *a, **k: np.dtype("int64"))  # fmt: skip
+        sum = TreeReduce.register(fx.DevReduce("sum"), fx.DevReduce("sum", phase="reduce"), compute_dtypes=_dtypes_sum)
+        max = TreeReduce.register(fx.DevReduce("max"), fx.DevReduce("max", phase="reduce"))
+        min = TreeReduce.register(fx.DevReduce("min"), fx.DevReduce("min", phase="reduce"))
+        mean = TreeReduce.register(fx.DevMeanMap(), fx.DevMeanReduce(), compute_dtypes=_f64)
+        # GroupByReduce (qc.py:3741-3748)
+        groupby_sum = B200GroupByReduce.register_agg("sum")
+        groupby_count = B200GroupByReduce.register_agg("count")
+        groupby_size = B200GroupByReduce.register_agg("size")
+        groupby_mean = B200GroupByReduce.register_agg("mean")
+
+        def fillna(self, **kwargs):
+            """qc.py:2710-2813."""
+            value = kwargs.get("value")
+            if kwargs.get("method") is not None or kwargs.get("limit") is not None:
+                raise NotImplementedError("fillna(method=/limit=) is a Fold in the reference; not on the B200 path")
+            if isinstance(value, type(self)):
+                return self.__constructor__(
+                    self._modin_frame.n_ary_op(lambda x, y: fx.DevBinary("fillna")(x, y), [value._modin_frame],
+                                               join_type="left", dtypes="copy")
+                )  # fmt: skip
+            kw = {k: v for k, v in kwargs.items() if k in ("value",)}
+            return self.__constructor__(self._modin_frame.map(lambda x: fx.DevFillna()(x, **kw), dtypes="copy"))
+
+        def merge(self, right, **kwargs):
+            """qc.py:657-667 -> MergeImpl.row_axis_merge (merge.py:104-252) with the per-block
+            ``pandas.merge`` replaced by the device hash-join functor."""
+            how = kwargs.get("how", "inner")
+            on = kwargs.get("on")
+            if kwargs.get("left_index") or kwargs.get("right_index") or how not in ("left", "inner"):
+                raise NotImplementedError("device merge: how in {left, inner}, no index joins")
+            if isinstance(on, (list, tuple)):
+                if len(on) != 1:
+                    raise NotImplementedError("device merge joins on exactly one int64 key column")
+                on = on[0]
+            if on is None:
+                raise NotImplementedError("device merge needs `on`")
+            suffixes = kwargs.get("suffixes", ("_x", "_y"))
+            right_to_broadcast = right._modin_frame.combine()  # merge.py:178
+            func = fx.DevMerge(on=on, how=how, suffixes=suffixes)
+            right_labels = [c for c in right.columns if c != on]
+            overlap = set(self.columns) & set(right_labels)
+            new_columns = pandas.Index(
+                [f"{c}{suffixes[0]}" if c in overlap else c for c in self.columns]
+                + [f"{c}{suffixes[1]}" if c in overlap else c for c in right_labels]
+            )
+            new_frame = self._modin_frame.broadcast_apply_full_axis(
+                axis=1, func=func, other=right_to_broadcast, keep_partitioning=True, num_splits=1,
+                new_columns=new_columns, sync_labels=False,
+            )  # fmt: skip
+            # merge.py:236-250 resets the index with a pandas lambda per block; on range-indexed device
+            # blocks that is a renumbering of `range_start` (metadata only)
+            from .query_compiler import _reset_row_index
+
+            return self.__constructor__(_reset_row_index(new_frame))
+
+    # ---------------------------------------------------------------- IO + factory
+    class B200IO(BaseIO):
+        frame_cls = B200OnModinDataframe
+        query_compiler_cls = B200OnModinQueryCompiler
+
+    class ArrowOnB200Factory(factories.BaseFactory):
+        @classmethod
+        def prepare(cls):
+            cls.io_cls = B200IO
+
+    cfg.StorageFormat.add_option("Arrow")
+    cfg.Engine.add_option("B200")
+    if "B200" not in cfg.Backend.get_active_backends() if hasattr(cfg.Backend, "get_active_backends") else True:
+        try:
+            cfg.Backend.register_backend("B200", Execution(storage_format="Arrow", engine="B200"))
+        except ValueError:
+            pass  # already registered in this interpreter
+    setattr(factories, "ArrowOnB200Factory", ArrowOnB200Factory)
+
+    class _NS:
+        pass
+
+    ns = _NS()
+    ns.PartitionManager = B200OnModinPartitionManager
+    ns.Dataframe = B200OnModinDataframe
+    ns.QueryCompiler = B200OnModinQueryCompiler
+    ns.IO = B200IO
+    ns.Factory = ArrowOnB200Factory
+    _REGISTERED = ns
+    return ns
+
+
+def activate():
+    """``register()`` + ``modin.set_execution(engine="B200", storage_format="Arrow")``."""
+    ns = register()
+    import modin
+
+    modin.set_execution(engine="B200", storage_format="Arrow")
+    return ns

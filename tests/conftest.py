@@ -35,3 +35,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def cpu_device():
+    """Host-logic tests without a GPU: swap the kernel wrappers for the numpy test double
+    (tests/cpu_double.py).  Never used by the ``gpu``-marked tests."""
+    from tests import cpu_double
+
+    with cpu_double.installed():
+        yield

@@ -1,0 +1,187 @@
+"""TEST DOUBLE for the device: lets the host-side stack (templates -> frame -> partition manager ->
+partitions -> functors) run in a container without a GPU by swapping the kernel wrappers of
+``modin_b200.ops`` for numpy/pandas stand-ins that work on CPU torch tensors.
+
+This is test infrastructure in the same sense as ``oracle/``: it exists so that the HOST LOGIC
+(partition grid, call-queue fusion, functor argument handling, template wiring, the real-Modin
+plug-in glue) can be exercised by ``pytest -m "not gpu"``.  It is installed by the ``cpu_device``
+fixture only; nothing in ``modin_b200/`` imports it and the product has no CPU path.
+"""
+
+from __future__ import annotations
+
+import contextlib
+
+import numpy as np
+import pandas
+import torch
+
+from modin_b200 import _lib, block, ops
+from modin_b200.block import DeviceColumn
+
+
+def _np(col: DeviceColumn) -> np.ndarray:
+    a = col.data.numpy()
+    return a.view(np.bool_) if col.dtype == np.bool_ else a
+
+
+def _col(arr: np.ndarray) -> DeviceColumn:
+    arr = np.ascontiguousarray(arr)
+    host = arr.view(np.uint8) if arr.dtype == np.bool_ else arr
+    return DeviceColumn(torch.from_numpy(host.copy()), arr.dtype)
+
+
+def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
+    out = []
+    for j, a in enumerate(in0):
+        x = _np(a)
+        y = _np(in1[j]) if in1 is not None else None
+        z = _np(in2[j]) if in2 is not None else None
+        p = s0[j] if s0 is not None else None
+        q = s1[j] if s1 is not None else None
+        if a.dtype == np.bool_:
+            raise TypeError("bool columns")
+        with np.errstate(all="ignore"):
+            r = {
+                "abs": lambda: np.abs(x), "neg": lambda: -x, "isna": lambda: np.isnan(x), "notna": lambda: ~np.isnan(x),
+                "fillna_s": lambda: np.where(np.isnan(x), p, x), "affine": lambda: x * p + q,
+                "add_s": lambda: x + p, "sub_s": lambda: x - p, "rsub_s": lambda: p - x, "mul_s": lambda: x * p,
+                "div_s": lambda: x / np.float64(p), "rdiv_s": lambda: np.float64(p) / x,
+                "eq_s": lambda: x == p, "ne_s": lambda: x != p, "lt_s": lambda: x < p, "le_s": lambda: x <= p,
+                "gt_s": lambda: x > p, "ge_s": lambda: x >= p, "copy": lambda: x.copy(),
+                "add": lambda: x + y, "sub": lambda: x - y, "mul": lambda: x * y, "div": lambda: x / y,
+                "eq": lambda: x == y, "ne": lambda: x != y, "lt": lambda: x < y, "le": lambda: x <= y,
+                "gt": lambda: x > y, "ge": lambda: x >= y, "fillna": lambda: np.where(np.isnan(x), y, x),
+                "fma3": lambda: x * y + z,
+            }[op]()  # fmt: skip
+        if op in ("div", "div_s", "rdiv_s"):
+            r = r.astype(np.float64)
+        out.append(_col(np.asarray(r)))
+    return out
+
+
+def reduce_columns(op, cols, skipna=True, variant=0):
+    vals, cnts = [], []
+    for c in cols:
+        x = _np(c)
+        if c.dtype == np.int64:
+            n = len(x)
+            v = {"sum": x.sum() if n else 0, "min": x.min() if n else np.iinfo(np.int64).max,
+                 "max": x.max() if n else np.iinfo(np.int64).min, "count": 0}[op]  # fmt: skip
+            vals.append(torch.tensor([v], dtype=torch.int64))
+            cnts.append(torch.tensor([n], dtype=torch.int64))
+            continue
+        ok = ~np.isnan(x)
+        n = int(ok.sum())
+        with np.errstate(all="ignore"):
+            if op == "sum":
+                v = x[ok].sum() if skipna else x.sum()
+            elif op == "count":
+                v = 0.0
+            elif n == 0 or (not skipna and n < len(x)):
+                v = np.nan
+            else:
+                v = x[ok].min() if op == "min" else x[ok].max()
+        vals.append(torch.tensor([v], dtype=torch.float64))
+        cnts.append(torch.tensor([n], dtype=torch.int64))
+    return vals, cnts
+
+
+def hash_aggregate(items, flags, capacity_hint, partial=False, sort=True):
+    keys = np.concatenate([_np(it[0]) for it in items])
+    nv = len(items[0][1]) if items[0][1] else 0
+    df = pandas.DataFrame({"k": keys})
+    uniq = np.sort(np.unique(keys))
+    g = df.groupby("k", sort=True)
+    sums = cnts = sizes = None
+    if flags & _lib.GB_SUM:
+        sums = []
+        for v in range(nv):
+            x = np.concatenate([_np(it[1][v]) for it in items])
+            sums.append(_col(pandas.Series(np.where(np.isnan(x), 0.0, x)).groupby(keys, sort=True).sum().to_numpy()))
+    if flags & _lib.GB_COUNT:
+        cnts = []
+        for v in range(nv):
+            if partial:
+                c = np.concatenate([_np(it[2][v]) for it in items])
+            else:
+                c = (~np.isnan(np.concatenate([_np(it[1][v]) for it in items]))).astype(np.int64)
+            cnts.append(_col(pandas.Series(c).groupby(keys, sort=True).sum().to_numpy().astype(np.int64)))
+    if flags & _lib.GB_SIZE:
+        z = np.concatenate([_np(it[3]) for it in items]) if partial else np.ones(len(keys), dtype=np.int64)
+        sizes = _col(pandas.Series(z).groupby(keys, sort=True).sum().to_numpy().astype(np.int64))
+    del g
+    return _col(uniq.astype(np.int64)), sums, cnts, sizes
+
+
+class JoinTable:
+    def __init__(self, dim_keys):
+        self.keys = _np(dim_keys)
+        self.index = pandas.Index(self.keys)
+
+    def is_unique(self):
+        return bool(self.index.is_unique)
+
+    def _idx(self, fact_keys):
+        return self.index.get_indexer(_np(fact_keys)).astype(np.int64)
+
+    def probe(self, fact_keys):
+        idx = self._idx(fact_keys)
+        return _col(idx), torch.tensor([int((idx >= 0).sum())])
+
+    def probe_gather(self, fact_keys, dim_cols):
+        idx = self._idx(fact_keys)
+        outs = []
+        for c in dim_cols:
+            x = _np(c)
+            null = np.nan if c.dtype == np.float64 else 0
+            outs.append(_col(np.where(idx >= 0, x[np.maximum(idx, 0)], null).astype(c.dtype)))
+        return outs, torch.tensor([int((idx >= 0).sum())])
+
+    def close(self):
+        pass
+
+
+def take_columns(cols, idx):
+    i = _np(idx)
+    outs = []
+    for c in cols:
+        x = _np(c)
+        null = np.nan if c.dtype == np.float64 else 0
+        outs.append(_col(np.where(i >= 0, x[np.maximum(i, 0)], null).astype(c.dtype)))
+    return outs
+
+
+def compact_hits(idx):
+    pos = np.nonzero(_np(idx) >= 0)[0].astype(np.int64)
+    return _col(pos), len(pos)
+
+
+def cast_columns_f64(cols):
+    return [c if c.dtype == np.float64 else _col(_np(c).astype(np.float64)) for c in cols]
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap the device for the double (context manager used by the ``cpu_device`` fixture)."""
+    from modin_b200 import synth
+
+    saved = {
+        "current_device": block.current_device,
+        **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
+                                        "compact_hits", "cast_columns_f64", "gen_f64", "gen_i64")},
+    }  # fmt: skip
+    block.current_device = lambda: torch.device("cpu")
+    ops.current_device = block.current_device
+    ops.map_columns, ops.reduce_columns, ops.hash_aggregate = map_columns, reduce_columns, hash_aggregate
+    ops.JoinTable, ops.take_columns, ops.compact_hits, ops.cast_columns_f64 = JoinTable, take_columns, compact_hits, \
+        cast_columns_f64  # fmt: skip
+    ops.gen_f64 = lambda n, seed, col, row_offset=0, nan_per_64k=0: _col(synth.gen_f64(n, seed, col, row_offset, nan_per_64k))
+    ops.gen_i64 = lambda n, seed, col, modulus, row_offset=0: _col(synth.gen_i64(n, seed, col, modulus, row_offset))
+    try:
+        yield
+    finally:
+        block.current_device = saved.pop("current_device")
+        ops.current_device = block.current_device
+        for n, v in saved.items():
+            setattr(ops, n, v)

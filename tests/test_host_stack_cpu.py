@@ -1,0 +1,125 @@
+"""CPU tests of the host-side stack (templates -> frame -> partition manager -> partitions -> functors)
+with the device replaced by the numpy test double (tests/cpu_double.py).  What is under test is the
+HOST LOGIC -- grids, call-queue fusion, argument plumbing, metadata, error behaviour -- against the
+oracle; kernel arithmetic is checked by the ``gpu`` tests."""
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import config, synth
+from oracle import reference_path as orc
+
+
+def _same(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+
+@pytest.fixture(autouse=True)
+def _np4():
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    yield
+    config.NPartitions.put(old)
+
+
+def test_map_binary_tree_reduce_through_the_api(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(1003, 5, seed=3, nan_per_64k=4000)
+    df = bpd.DataFrame(pdf)
+    assert df._query_compiler._modin_frame._partitions.shape == (4, 1)
+    assert _same(df.abs()._to_pandas().to_numpy(), orc.df_abs(pdf, 4).to_numpy())
+    assert _same((df * 1.5 + 2.0)._to_pandas().to_numpy(), orc.a_mul_b_add_c(pdf, 1.5, 2.0, 4).to_numpy())
+    assert _same((-df)._to_pandas().to_numpy(), (-pdf).to_numpy())
+    assert _same(df.fillna(0.25)._to_pandas().to_numpy(), orc.df_fillna(pdf, 0.25, 4).to_numpy())
+    assert np.allclose(df.sum().to_numpy(), orc.df_sum(pdf, 4).to_numpy(), rtol=0, atol=1e-9)
+    assert np.allclose(df.mean().to_numpy(), orc.df_mean(pdf, 4).to_numpy(), rtol=0, atol=1e-12)
+    assert _same(df.count().to_numpy(), orc.df_count(pdf, 4).to_numpy())
+    assert _same(df.min().to_numpy(), orc.df_min(pdf, 4).to_numpy())
+    assert _same(df.max(skipna=False).to_numpy(), orc.df_max(pdf, 4, skipna=False).to_numpy())
+    assert _same(df.sum(min_count=1).to_numpy(), orc.df_sum(pdf, 4, min_count=1).to_numpy()) or \
+        np.allclose(df.sum(min_count=1).to_numpy(), orc.df_sum(pdf, 4, min_count=1).to_numpy(), atol=1e-9, equal_nan=True)
+    res = df.sum()
+    assert isinstance(res, pandas.Series) and list(res.index) == list(pdf.columns) and res.name is None
+
+
+def test_frame_frame_ops_and_fusion(cpu_device):
+    import modin_b200.pandas as bpd
+
+    a, b, c = (synth.host_frame(600, 3, seed=s) for s in (1, 2, 3))
+    A, B, C = bpd.DataFrame(a), bpd.DataFrame(b), bpd.DataFrame(c)
+    out = A * B + C
+    parts = out._query_compiler._modin_frame._partitions
+    assert all(len(p.call_queue) == 2 for p in parts.flatten())  # mul, add queued -> fused at drain
+    assert _same(out._to_pandas().to_numpy(), orc.a_mul_b_add_c(a, b, c, 4).to_numpy())
+    assert _same((A / B)._to_pandas().to_numpy(), (a / b).to_numpy())
+    assert _same((A >= B)._to_pandas().to_numpy(), (a >= b).to_numpy())
+    short = bpd.DataFrame(synth.host_frame(599, 3))
+    with pytest.raises(NotImplementedError):
+        (A + short)._to_pandas()
+
+
+def test_groupby_and_merge_through_the_api(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(5003, 3, seed=42, nan_per_64k=2000, key_modulus=41)
+    df = bpd.DataFrame(pdf)
+    g = df.groupby("key")
+    for agg in ("sum", "count", "mean"):
+        got = getattr(g, agg)()._to_pandas()
+        want = orc.groupby_reduce(pdf, "key", agg, 4)
+        assert list(got.index) == list(want.index) and got.index.name == "key"
+        assert list(got.columns) == list(want.columns)
+        assert np.allclose(got.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+    assert _same(g.size()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "size", 4).to_numpy())
+    # result frame metadata
+    res = g.sum()
+    assert len(res) == 41 and list(res.columns) == ["c0", "c1", "c2"]
+
+    rng = np.random.RandomState(0)
+    dim = pandas.DataFrame({"key": rng.permutation(41)[:35].astype(np.int64), "d0": rng.randn(35),
+                            "c0": np.arange(35, dtype=np.int64)})  # fmt: skip
+    left = df.merge(bpd.DataFrame(dim), on="key", how="left")._to_pandas()
+    wl = orc.broadcast_merge(pdf, dim, "key", "left", 4)
+    assert list(left.columns) == list(wl.columns)  # overlapping "c0" gets _x / _y suffixes
+    assert _same(left.to_numpy(dtype=np.float64), wl.to_numpy(dtype=np.float64))
+    inner = df.merge(bpd.DataFrame(dim), on="key", how="inner")._to_pandas()
+    assert _same(inner.to_numpy(dtype=np.float64),
+                 orc.broadcast_merge(pdf, dim, "key", "inner", 4).to_numpy(dtype=np.float64))
+    dup = pandas.DataFrame({"key": np.array([1, 1, 2], dtype=np.int64), "d": [1.0, 2.0, 3.0]})
+    with pytest.raises(NotImplementedError):
+        df.merge(bpd.DataFrame(dup), on="key", how="left")._to_pandas()
+
+
+def test_errors_match_pandas_types(cpu_device):
+    import modin_b200.pandas as bpd
+
+    df = bpd.DataFrame(synth.host_frame(50, 2))
+    with pytest.raises(ValueError):
+        df.fillna()
+    with pytest.raises(TypeError):
+        df.fillna([1, 2])
+    with pytest.raises(KeyError):
+        df["nope"]
+    with pytest.raises(KeyError):
+        df.groupby("nope")
+    with pytest.raises(NotImplementedError):
+        df.sum(axis=1)
+    with pytest.raises(NotImplementedError):
+        df.merge(df, how="outer", on="c0")
+    with pytest.raises(TypeError):
+        bpd.DataFrame(pandas.DataFrame({"s": ["a", "b"]}))
+
+
+def test_wide_frames_use_a_2d_grid(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = pandas.DataFrame(np.arange(64 * 40, dtype=np.float64).reshape(64, 40))
+    df = bpd.DataFrame(pdf)
+    f = df._query_compiler._modin_frame
+    assert f._partitions.shape == (2, 2) and f.column_widths == [32, 8] and f.row_lengths == [32, 32]
+    assert _same((df * 2.0)._to_pandas().to_numpy(), (pdf * 2.0).to_numpy())
+    assert _same(df.sum().to_numpy(), pdf.sum().to_numpy())
+    assert _same(df[[0, 35]]._to_pandas().to_numpy(), pdf[[0, 35]].to_numpy())

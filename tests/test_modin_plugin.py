@@ -1,0 +1,134 @@
+"""The drop-in boundary under REAL Modin: ``modin_b200.modin_plugin.register()`` plugs the execution
+in behind ``modin.pandas`` and the hot-path operations run through Modin's own API layer, query
+compiler caster, operator templates and ``PandasDataframe`` methods into this package's partition
+classes and device functors.
+
+Modin comes from ``baseline/_ref`` (pip-installed from the read-only reference, git-ignored; it
+travels to the GPU box with the snapshot).  Without it these tests are skipped.  On a box without a
+GPU the device is the numpy test double (host logic only); the ``gpu``-marked variant at the bottom
+runs the same scenarios on the B200.
+"""
+
+import os
+import sys
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import synth
+from oracle import reference_path as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "modin")),
+                                reason="reference Modin not installed under baseline/_ref")  # fmt: skip
+
+
+def _same(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+
+@pytest.fixture(scope="module")
+def modin_b200_execution():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from modin_b200 import modin_plugin
+
+    ns = modin_plugin.register()
+    import modin
+    import modin.config as cfg
+    import modin.pandas as mpd
+
+    modin.set_execution(engine="B200", storage_format="Arrow")
+    cfg.NPartitions.put(4)
+    from modin_b200 import config
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    yield ns, mpd
+    config.NPartitions.put(old)
+
+
+def _scenarios(mpd, ns):
+    pdf = synth.host_frame(2003, 4, seed=11, nan_per_64k=3000, key_modulus=23)
+    vals = pdf.drop(columns="key")
+    mdf = mpd.DataFrame(vals)
+    qc = mdf._query_compiler
+    assert type(qc) is ns.QueryCompiler and type(qc._modin_frame) is ns.Dataframe
+    assert qc.engine == "B200" and qc.storage_format == "Arrow" and qc.get_backend() == "B200"
+    from modin_b200.block import DeviceBlock
+
+    assert all(isinstance(p.get(), DeviceBlock) for p in qc._modin_frame._partitions.flatten())
+    P = lambda x: x._to_pandas()  # noqa: E731
+
+    assert _same(P(mdf.abs()).to_numpy(), orc.df_abs(vals, 4).to_numpy())
+    assert _same(P(mdf * 1.5 + 0.25).to_numpy(), orc.a_mul_b_add_c(vals, 1.5, 0.25, 4).to_numpy())
+    assert _same(P(-mdf).to_numpy(), (-vals).to_numpy())
+    assert _same(P(mdf.isna()).to_numpy().astype(float), vals.isna().to_numpy().astype(float))
+    assert _same(P(mdf.fillna(2.0)).to_numpy(), orc.df_fillna(vals, 2.0, 4).to_numpy())
+    other = synth.host_frame(2003, 4, seed=12)
+    mo = mpd.DataFrame(other)
+    assert _same(P(mdf * mo + mo).to_numpy(), orc.a_mul_b_add_c(vals, other, other, 4).to_numpy())
+    assert _same(P(mdf < mo).to_numpy().astype(float), (vals < other).to_numpy().astype(float))
+
+    s = P(mdf.sum())
+    assert isinstance(s, pandas.Series) and list(s.index) == list(vals.columns)
+    assert np.allclose(s.to_numpy(), orc.df_sum(vals, 4).to_numpy(), rtol=0, atol=1e-9)
+    assert np.allclose(P(mdf.mean()).to_numpy(), orc.df_mean(vals, 4).to_numpy(), rtol=0, atol=1e-12)
+    assert _same(P(mdf.count()).to_numpy(), orc.df_count(vals, 4).to_numpy())
+    assert _same(P(mdf.min()).to_numpy(), orc.df_min(vals, 4).to_numpy())
+    assert _same(P(mdf.max()).to_numpy(), orc.df_max(vals, 4).to_numpy())
+
+    mfull = mpd.DataFrame(pdf)
+    g = P(mfull.groupby("key").sum())
+    want = orc.groupby_reduce(pdf, "key", "sum", 4)
+    assert list(g.index) == list(want.index) and list(g.columns) == list(want.columns)
+    assert np.allclose(g.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9)
+    assert _same(P(mfull.groupby("key").count()).to_numpy(), orc.groupby_reduce(pdf, "key", "count", 4).to_numpy())
+    assert np.allclose(P(mfull.groupby("key").mean()).to_numpy(), orc.groupby_reduce(pdf, "key", "mean", 4).to_numpy(),
+                       rtol=0, atol=1e-12, equal_nan=True)  # fmt: skip
+
+    rng = np.random.RandomState(1)
+    dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
+    left = P(mfull.merge(mpd.DataFrame(dim), on="key", how="left"))
+    wl = orc.broadcast_merge(pdf, dim, "key", "left", 4)
+    assert list(left.columns) == list(wl.columns) and _same(left.to_numpy(), wl.to_numpy())
+    inner = P(mfull.merge(mpd.DataFrame(dim), on="key", how="inner"))
+    assert _same(inner.to_numpy(), orc.broadcast_merge(pdf, dim, "key", "inner", 4).to_numpy())
+
+
+def test_registration_resolves_through_modins_dispatcher(modin_b200_execution):
+    ns, mpd = modin_b200_execution
+    import modin.config as cfg
+    from modin.core.execution.dispatching.factories.dispatcher import FactoryDispatcher
+
+    assert cfg.Engine.get() == "B200" and cfg.StorageFormat.get() == "Arrow"
+    factory = FactoryDispatcher.get_factory()
+    assert factory.io_cls is ns.IO
+    assert ns.IO.frame_cls is ns.Dataframe and ns.IO.query_compiler_cls is ns.QueryCompiler
+
+
+def test_hot_path_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    ns, mpd = modin_b200_execution
+    _scenarios(mpd, ns)
+
+
+@pytest.mark.gpu
+def test_hot_path_under_real_modin_on_b200(modin_b200_execution):
+    ns, mpd = modin_b200_execution
+    from modin_b200 import _lib
+
+    lib = _lib.load()
+    before = lib.mb200_launch_count()
+    _scenarios(mpd, ns)
+    assert lib.mb200_launch_count() > before
