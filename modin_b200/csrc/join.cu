@@ -92,16 +92,30 @@ __global__ void join_build_kernel(JSlot* slots, unsigned int mask, const long lo
   }
 }
 
-__device__ __forceinline__ int join_lookup(const JSlot* slots, unsigned int mask, long long k) {
+// Warp-wide lookup with a vote-controlled (warp-uniform) probe loop: every lane leaves together, so the
+// stores that follow run converged (a per-lane `return` inside the loop lets nvcc run the rest of the
+// iteration in diverged groups -- measured on the groupby kernel, see groupby.cu).  Must be called by
+// all 32 lanes; lanes without a row pass valid = false.
+__device__ __forceinline__ int join_lookup(const JSlot* slots, unsigned int mask, long long k, bool valid) {
   unsigned int slot = hash_key(k) & mask;
-  for (;;) {
-    long long sk;
-    int r;
-    ld_jslot(&slots[slot], sk, r);
-    if (r < 0) return -1;  // table is read-only during probing: empty slot terminates the chain
-    if (sk == k) return r;
-    slot = (slot + 1) & mask;
+  int res = -1;
+  bool active = valid;
+  while (__any_sync(0xffffffffu, active)) {
+    if (active) {
+      long long sk;
+      int r;
+      ld_jslot(&slots[slot], sk, r);
+      if (r < 0) {
+        active = false;  // table is read-only during probing: an empty slot terminates the chain
+      } else if (sk == k) {
+        res = r;
+        active = false;
+      } else {
+        slot = (slot + 1) & mask;
+      }
+    }
   }
+  return res;
 }
 
 __global__ void __launch_bounds__(256) join_probe_kernel(const JSlot* __restrict__ slots, unsigned int mask,
@@ -110,16 +124,21 @@ __global__ void __launch_bounds__(256) join_probe_kernel(const JSlot* __restrict
                                                          unsigned long long* nmatch) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const uint64_t pol = l2_policy_evict_first();
+  const int lane = threadIdx.x & 31;
   unsigned long long hits = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int r = join_lookup(slots, mask, ldg_stream_i64(fact_keys + i, pol));
-    out_idx[i] = (long long)r;
-    hits += (r >= 0);
+  // warp-uniform outer loop: `base` is the row of lane 0
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    const long long k = valid ? ldg_stream_i64(fact_keys + i, pol) : 0;
+    const int r = join_lookup(slots, mask, k, valid);
+    if (valid) out_idx[i] = (long long)r;
+    hits += (valid && r >= 0);
   }
   // one atomic per warp
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, m);
-  if ((threadIdx.x & 31) == 0 && hits && nmatch) atomicAdd(nmatch, hits);
+  if (lane == 0 && hits && nmatch) atomicAdd(nmatch, hits);
 }
 
 struct GatherParams {
@@ -135,18 +154,24 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(const JSlot* __r
                                                                 unsigned long long* nmatch, T null_value) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const uint64_t pol = l2_policy_evict_first();
+  const int lane = threadIdx.x & 31;
   unsigned long long hits = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int r = join_lookup(slots, mask, ldg_stream_i64(fact_keys + i, pol));
-    hits += (r >= 0);
-    for (int c = 0; c < g.ncols; ++c) {
-      const T v = r >= 0 ? static_cast<const T*>(g.dim_cols[c])[r] : null_value;
-      static_cast<T*>(g.out_cols[c])[i] = v;
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    const long long k = valid ? ldg_stream_i64(fact_keys + i, pol) : 0;
+    const int r = join_lookup(slots, mask, k, valid);
+    hits += (valid && r >= 0);
+    if (valid) {
+      for (int c = 0; c < g.ncols; ++c) {
+        const T v = r >= 0 ? static_cast<const T*>(g.dim_cols[c])[r] : null_value;
+        static_cast<T*>(g.out_cols[c])[i] = v;
+      }
     }
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, m);
-  if ((threadIdx.x & 31) == 0 && hits && nmatch) atomicAdd(nmatch, hits);
+  if (lane == 0 && hits && nmatch) atomicAdd(nmatch, hits);
 }
 
 template <typename T>
