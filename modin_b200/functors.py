@@ -158,9 +158,19 @@ class DevBinary(DevFn):
             kop, a, b = _REFLECTED_FRAME[self.op], right.cols, left.cols
         else:
             kop, a, b = _BINARY_TO_FRAME[self.op], left.cols, right.cols
-        if len(a) != len(b) or left.nrows != right.nrows:
+        if left.nrows != right.nrows:
             raise ValueError("device binary op needs identically shaped, co-partitioned operands")
-        if not left.columns.equals(right.columns):
+        if len(right.cols) == 1 and len(left.cols) != 1 and self.op not in _REFLECTED_FRAME:
+            # frame (op) column vector: the broadcast_apply shape of Binary.caller (alg/binary.py:396-408,
+            # `df.mul(series, axis=0)`): the single right column is paired with every left column
+            b = [right.cols[0]] * len(left.cols)
+            a = left.cols
+        elif len(right.cols) == 1 and len(left.cols) != 1:
+            a = [right.cols[0]] * len(left.cols)
+            b = left.cols
+        elif len(a) != len(b):
+            raise ValueError("device binary op needs identically shaped, co-partitioned operands")
+        elif not left.columns.equals(right.columns):
             raise NotImplementedError("binary op between blocks with different column labels (needs copartition)")
         if kop not in _lib.PREDICATES and kop != "div":
             mixed = any(x.dtype != y.dtype for x, y in zip(a, b))

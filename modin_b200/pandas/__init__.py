@@ -41,9 +41,13 @@ class BasePandasDataset:
     def _binary_op(self, op, other, **kwargs):
         """modin/pandas/base.py:485-542."""
         other_qc = self._validate_other(other)
-        broadcast = isinstance(other, Series) and isinstance(self, DataFrame)
-        if broadcast:
-            # frame (op) Series along columns == per-column scalars: hand the values over as a row vector
+        if isinstance(other, Series) and isinstance(self, DataFrame):
+            if kwargs.get("axis") in (0, "index"):
+                # frame (op) Series along the rows: a column vector co-partitioned with the frame -> the
+                # broadcast_apply branch of Binary.caller (alg/binary.py:396-408)
+                new_qc = getattr(self._query_compiler, op)(other_qc, broadcast=True, **kwargs)
+                return self._create_or_update_from_compiler(new_qc)
+            # along the columns == per-column scalars: hand the (W) values over as a row vector
             other_qc = other._to_pandas()
         new_qc = getattr(self._query_compiler, op)(other_qc, **kwargs)
         return self._create_or_update_from_compiler(new_qc)

@@ -123,3 +123,20 @@ def test_wide_frames_use_a_2d_grid(cpu_device):
     assert _same((df * 2.0)._to_pandas().to_numpy(), (pdf * 2.0).to_numpy())
     assert _same(df.sum().to_numpy(), pdf.sum().to_numpy())
     assert _same(df[[0, 35]]._to_pandas().to_numpy(), pdf[[0, 35]].to_numpy())
+
+
+def test_series_operands_both_axes(cpu_device):
+    """frame (op) Series: along columns = row vector (lazy map), along rows = broadcast_apply."""
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(900, 3, seed=6)
+    df = bpd.DataFrame(pdf)
+    col = pdf["c1"]
+    ser = df["c1"]
+    assert isinstance(ser, bpd.Series) and ser.name == "c1" and len(ser) == 900
+    assert _same(df.mul(ser, axis=0)._to_pandas().to_numpy(), pdf.mul(col, axis=0).to_numpy())
+    assert _same(df.sub(ser, axis=0)._to_pandas().to_numpy(), pdf.sub(col, axis=0).to_numpy())
+    assert _same(df.rsub(ser, axis=0)._to_pandas().to_numpy(), pdf.rsub(col, axis=0).to_numpy())
+    rowvec = pandas.Series([1.0, -2.0, 0.5], index=pdf.columns)
+    assert _same((df + bpd.Series(rowvec))._to_pandas().to_numpy(), (pdf + rowvec).to_numpy())
+    assert np.isclose(ser.sum(), col.sum()) and ser.count() == 900
