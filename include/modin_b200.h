@@ -106,7 +106,8 @@ enum mb200_reduce_op {
   MB200_RED_SUM = 0,  /* out_val = sum (NaN skipped iff skipna), out_cnt = #non-NaN */
   MB200_RED_MIN = 1,  /* out_val = min over non-NaN, out_cnt = #non-NaN             */
   MB200_RED_MAX = 2,
-  MB200_RED_COUNT = 3 /* out_cnt only */
+  MB200_RED_COUNT = 3, /* out_cnt only */
+  MB200_RED_PROD = 4   /* out_val = product (NaN skipped iff skipna), out_cnt = #non-NaN */
 };
 
 /* ---- groupby aggregate selection (bit flags) ------------------------------ */

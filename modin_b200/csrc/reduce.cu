@@ -152,6 +152,39 @@ struct Acc<MB200_RED_MAX, long long> {
   static __device__ __forceinline__ long long combine(long long a, long long b) { return a > b ? a : b; }
 };
 template <>
+struct Acc<MB200_RED_PROD, double> {
+  double m = 1.0;
+  long long n = 0;
+  __device__ __forceinline__ void add(double x, int skipna) {
+    const bool ok = (x == x);
+    n += ok;
+    m *= (ok || !skipna) ? x : 1.0;
+  }
+  __device__ __forceinline__ void merge(const Acc& o) {
+    m *= o.m;
+    n += o.n;
+  }
+  __device__ __forceinline__ double value() const { return m; }
+  static __device__ __forceinline__ double combine(double a, double b) { return a * b; }
+};
+template <>
+struct Acc<MB200_RED_PROD, long long> {
+  unsigned long long m = 1;
+  long long n = 0;
+  __device__ __forceinline__ void add(long long x, int) {
+    m *= (unsigned long long)x;
+    n += 1;
+  }
+  __device__ __forceinline__ void merge(const Acc& o) {
+    m *= o.m;
+    n += o.n;
+  }
+  __device__ __forceinline__ long long value() const { return (long long)m; }
+  static __device__ __forceinline__ long long combine(long long a, long long b) {
+    return (long long)((unsigned long long)a * (unsigned long long)b);
+  }
+};
+template <>
 struct Acc<MB200_RED_COUNT, double> {
   long long n = 0;
   __device__ __forceinline__ void add(double x, int) { n += (x == x); }
@@ -485,6 +518,7 @@ extern "C" int mb200_reduce_columns(int op, int dtype, int ncols, const void* co
       case MB200_RED_MIN: MB_RED(MB200_RED_MIN, double)
       case MB200_RED_MAX: MB_RED(MB200_RED_MAX, double)
       case MB200_RED_COUNT: MB_RED(MB200_RED_COUNT, double)
+      case MB200_RED_PROD: MB_RED(MB200_RED_PROD, double)
     }
   } else if (dtype == MB200_I64) {
     switch (op) {
@@ -492,6 +526,7 @@ extern "C" int mb200_reduce_columns(int op, int dtype, int ncols, const void* co
       case MB200_RED_MIN: MB_RED(MB200_RED_MIN, long long)
       case MB200_RED_MAX: MB_RED(MB200_RED_MAX, long long)
       case MB200_RED_COUNT: MB_RED(MB200_RED_COUNT, long long)
+      case MB200_RED_PROD: MB_RED(MB200_RED_PROD, long long)
     }
   }
 #undef MB_RED

@@ -259,7 +259,7 @@ class DevReduce(DevFn):
     """
 
     def __init__(self, op: str, phase: str = "map"):
-        if op not in ("sum", "count", "min", "max"):
+        if op not in ("sum", "count", "min", "max", "prod"):
             raise ValueError(op)
         self.op = op
         self.phase = phase  # "map" | "reduce"
@@ -310,6 +310,10 @@ class DevReduce(DevFn):
         if kop == "count":
             dist.all_reduce_values(cnts, ["sum"] * W)
             out = [DeviceColumn(c, np.int64) for c in cnts]
+        elif kop == "prod":
+            # gather every rank's partial product per column (world_size values) and multiply locally
+            vals = [dist.all_gather_rows([v.reshape(1)])[0].prod().reshape(1) for v in vals]
+            out = [DeviceColumn(v, c.dtype) for v, c in zip(vals, block.cols)]
         elif kop == "sum":
             dist.all_reduce_values(vals, ["sum"] * W)
             if min_count == 1 and skipna:

@@ -168,6 +168,13 @@ class BasePandasDataset:
     def sum(self, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
         return self._stat("sum", axis, skipna, numeric_only, min_count=min_count)
 
+    def prod(self, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
+        if min_count:
+            raise NotImplementedError("prod(min_count>0) is not on the B200 path")
+        return self._stat("prod", axis, skipna, numeric_only)
+
+    product = prod
+
     def mean(self, axis=0, skipna=True, numeric_only=False, **kwargs):
         return self._stat("mean", axis, skipna, numeric_only)
 

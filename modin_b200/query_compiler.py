@@ -144,6 +144,7 @@ class B200QueryCompiler:
     # ---- TreeReduce (qc.py:976-1096) ----------------------------------------------------------------
     count = TreeReduce.register(DevReduce("count"), DevReduce("count", phase="reduce"))
     sum = TreeReduce.register(DevReduce("sum"), DevReduce("sum", phase="reduce"), compute_dtypes=_dtypes_sum)
+    prod = TreeReduce.register(DevReduce("prod"), DevReduce("prod", phase="reduce"), compute_dtypes=_dtypes_sum)
     max = TreeReduce.register(DevReduce("max"), DevReduce("max", phase="reduce"))
     min = TreeReduce.register(DevReduce("min"), DevReduce("min", phase="reduce"))
     mean = TreeReduce.register(DevMeanMap(), DevMeanReduce(), compute_dtypes=lambda *a, **k: np.dtype("float64"))

@@ -161,6 +161,11 @@ def df_sum(df, npartitions, skipna=True, min_count=0, threads: int = 1):
     return tree_reduce(df, f, None, npartitions, threads)
 
 
+def df_prod(df, npartitions, skipna=True, threads: int = 1):
+    """qc.prod = TreeReduce.register(pandas.DataFrame.prod) (query_compiler.py:985)."""
+    return tree_reduce(df, lambda x: x.prod(axis=0, skipna=skipna), None, npartitions, threads)
+
+
 def df_count(df, npartitions, threads: int = 1):
     """qc.count = TreeReduce.register(pandas.DataFrame.count, pandas.DataFrame.sum) (query_compiler.py:976)."""
     return tree_reduce(df, lambda x: x.count(axis=0), lambda x: x.sum(axis=0), npartitions, threads)

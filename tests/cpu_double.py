@@ -67,7 +67,7 @@ def reduce_columns(op, cols, skipna=True, variant=0):
         if c.dtype == np.int64:
             n = len(x)
             v = {"sum": x.sum() if n else 0, "min": x.min() if n else np.iinfo(np.int64).max,
-                 "max": x.max() if n else np.iinfo(np.int64).min, "count": 0}[op]  # fmt: skip
+                 "max": x.max() if n else np.iinfo(np.int64).min, "count": 0, "prod": x.prod() if n else 1}[op]  # fmt: skip
             vals.append(torch.tensor([v], dtype=torch.int64))
             cnts.append(torch.tensor([n], dtype=torch.int64))
             continue
@@ -76,6 +76,8 @@ def reduce_columns(op, cols, skipna=True, variant=0):
         with np.errstate(all="ignore"):
             if op == "sum":
                 v = x[ok].sum() if skipna else x.sum()
+            elif op == "prod":
+                v = x[ok].prod() if skipna else x.prod()
             elif op == "count":
                 v = 0.0
             elif n == 0 or (not skipna and n < len(x)):

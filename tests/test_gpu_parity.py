@@ -181,6 +181,24 @@ def test_against_oracle_various_shapes(n, W, nan):
     assert_exact(df.max().to_numpy(), orc.df_max(pdf, NPART).to_numpy(), "max")
 
 
+def test_prod_tree_reduce():
+    m = bpd()
+    pdf = synth.host_frame(300, 4, seed=21, nan_per_64k=3000) * 1.7
+    got = m.DataFrame(pdf).prod().to_numpy()
+    want = orc.df_prod(pdf, 4).to_numpy()
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    ints = pandas.DataFrame({"a": np.arange(1, 21, dtype=np.int64), "b": np.full(20, -2, dtype=np.int64)})
+    assert_exact(m.DataFrame(ints).prod().to_numpy(), ints.prod().to_numpy(), "int64 prod (wrapping, exact)")
+
+
+def test_series_column_vector_broadcast():
+    m = bpd()
+    pdf = synth.host_frame(5000, 3, seed=6)
+    df = m.DataFrame(pdf)
+    assert_exact(df.mul(df["c1"], axis=0)._to_pandas().to_numpy(), pdf.mul(pdf["c1"], axis=0).to_numpy(), "mul axis=0")
+    assert_exact(df.rsub(df["c2"], axis=0)._to_pandas().to_numpy(), pdf.rsub(pdf["c2"], axis=0).to_numpy(), "rsub axis=0")
+
+
 def test_reduce_variants_agree():
     """TMA-staged and direct-load reductions are two schedules of the same arithmetic."""
     from modin_b200 import config

@@ -43,6 +43,8 @@ def test_map_binary_tree_reduce_through_the_api(cpu_device):
         np.allclose(df.sum(min_count=1).to_numpy(), orc.df_sum(pdf, 4, min_count=1).to_numpy(), atol=1e-9, equal_nan=True)
     res = df.sum()
     assert isinstance(res, pandas.Series) and list(res.index) == list(pdf.columns) and res.name is None
+    small = synth.host_frame(40, 3, seed=9, nan_per_64k=6000) * 1.5
+    assert np.allclose(bpd.DataFrame(small).prod().to_numpy(), orc.df_prod(small, 4).to_numpy(), rtol=1e-12)
 
 
 def test_frame_frame_ops_and_fusion(cpu_device):
