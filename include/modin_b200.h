@@ -114,7 +114,9 @@ enum mb200_reduce_op {
 enum mb200_gb_flags {
   MB200_GB_SUM = 1,   /* acc[g][v]  += x   (NaN skipped, pandas min_count=0)       */
   MB200_GB_COUNT = 2, /* cnt[g][v]  += !isnan(x)                                     */
-  MB200_GB_SIZE = 4   /* size[g]    += 1                                             */
+  MB200_GB_SIZE = 4,  /* size[g]    += 1                                             */
+  MB200_GB_MIN = 8,   /* acc[g][v]   = min(acc, x)  (NaN skipped; exclusive with SUM / MAX) */
+  MB200_GB_MAX = 16   /* acc[g][v]   = max(acc, x)                                          */
 };
 
 /* ======================= runtime / memory ================================== */

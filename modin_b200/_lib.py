@@ -34,7 +34,7 @@ OP = {
 }  # fmt: skip
 PREDICATES = {"isna", "notna", "eq_s", "ne_s", "lt_s", "le_s", "gt_s", "ge_s", "eq", "ne", "lt", "le", "gt", "ge"}
 RED = {"sum": 0, "min": 1, "max": 2, "count": 3, "prod": 4}
-GB_SUM, GB_COUNT, GB_SIZE = 1, 2, 4
+GB_SUM, GB_COUNT, GB_SIZE, GB_MIN, GB_MAX = 1, 2, 4, 8, 16
 
 _vp = C.c_void_p
 _vpp = C.POINTER(C.c_void_p)

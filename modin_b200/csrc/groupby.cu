@@ -134,6 +134,30 @@ __device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_
 }
 __device__ __forceinline__ uint64_t table_policy(int) { return 0; }
 
+// min / max accumulators share the `acc` array: doubles are stored through an order-preserving map to
+// int64 (flip the magnitude bits of negatives) so that RED.MIN.S64 / RED.MAX.S64 order them like
+// floating-point comparison.  NaNs are skipped by the callers; INT64_MAX / INT64_MIN (the images of
+// all-ones NaNs) mark "no value yet" for min / max and decode to NaN.
+__device__ __forceinline__ long long f64_to_ordered(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double ordered_to_f64(long long o) {
+  return __longlong_as_double(o ^ ((o >> 63) & 0x7fffffffffffffffLL));
+}
+__device__ __forceinline__ void red_min_s64(long long* p, long long v) {
+  asm volatile("red.relaxed.gpu.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_s64(long long* p, long long v) {
+  asm volatile("red.relaxed.gpu.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// value accumulator update of one (group, column): sum, or min / max on the ordered image
+__device__ __forceinline__ void acc_update(const GbParams& p, size_t o, double xv, uint64_t keep) {
+  if (p.flags & MB200_GB_SUM) red_add_f64(p.acc + o, xv, keep);
+  else if (p.flags & MB200_GB_MIN) red_min_s64(reinterpret_cast<long long*>(p.acc) + o, f64_to_ordered(xv));
+  else if (p.flags & MB200_GB_MAX) red_max_s64(reinterpret_cast<long long*>(p.acc) + o, f64_to_ordered(xv));
+}
+
 // Probing works on BUCKETS of two slots = one 32-byte sector, fetched with one 256-bit load: a probe
 // round costs the same sector as a single-slot probe but the chain of rounds is about half as long
 // (with single-slot linear probing at load factor 0.48 the longest of a warp's 32 chains averaged 5.6
@@ -303,9 +327,7 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
         for (int c = 0; c < 8; ++c) {
           if (c < nc && live) {
             const size_t o = (size_t)gid * p.vstride + c0 + c;
-            if (p.flags & MB200_GB_SUM) {
-              if (x[c] == x[c]) red_add_f64(p.acc + o, x[c], keep);
-            }
+            if (x[c] == x[c]) acc_update(p, o, x[c], keep);
             if (p.flags & MB200_GB_COUNT) {
               if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[row], keep);
               else if (x[c] == x[c]) red_add_u64(p.cnt + o, 1LL, keep);
@@ -326,9 +348,7 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
           const bool ok = (base + r < p.nrows) && (c < nc) && (g < gcap);
           if (ok) {
             const size_t o = (size_t)g * p.vstride + c0 + c;
-            if (p.flags & MB200_GB_SUM) {
-              if (xv == xv) red_add_f64(p.acc + o, xv, keep);
-            }
+            if (xv == xv) acc_update(p, o, xv, keep);
             if (p.flags & MB200_GB_COUNT) {
               if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[base + r], keep);
               else if (xv == xv) red_add_u64(p.cnt + o, 1LL, keep);
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
         const double xv = vt[c * kTileColStride + r];
         const size_t o = (size_t)g * p.vstride + c;
         if (xv == xv) {
-          if (p.flags & MB200_GB_SUM) red_add_f64(p.acc + o, xv, keep);
+          acc_update(p, o, xv, keep);
           if (p.flags & MB200_GB_COUNT) red_add_u64(p.cnt + o, 1LL, keep);
         }
       }
@@ -419,6 +439,11 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
+}
+
+__global__ void gb_fill_kernel(long long* p, long long n, long long v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
 __global__ void gb_init_kernel(Slot* slots, long long cap, GbMeta* meta) {
@@ -485,6 +510,7 @@ struct EmitParams {
   const long long* size;
   int nvals;
   int vstride;
+  int flags;
   long long ngroups;
   long long* out_keys;
   void* out_sums[MB200_MAX_COLS];
@@ -499,7 +525,15 @@ __global__ void gb_emit_kernel(const __grid_constant__ EmitParams p) {
   if (p.out_keys) p.out_keys[i] = p.keys_sorted[i];
   if (p.out_sizes && p.size) p.out_sizes[i] = p.size[g];
   for (int v = 0; v < p.nvals; ++v) {
-    if (p.out_sums[v] && p.acc) static_cast<double*>(p.out_sums[v])[i] = p.acc[(size_t)g * p.vstride + v];
+    if (p.out_sums[v] && p.acc) {
+      double val = p.acc[(size_t)g * p.vstride + v];
+      if (p.flags & (MB200_GB_MIN | MB200_GB_MAX)) {
+        const long long o = __double_as_longlong(val);
+        const bool empty = (p.flags & MB200_GB_MIN) ? (o == 0x7fffffffffffffffLL) : (o == (long long)0x8000000000000000ULL);
+        val = empty ? __longlong_as_double(0x7ff8000000000000LL) : ordered_to_f64(o);
+      }
+      static_cast<double*>(p.out_sums[v])[i] = val;
+    }
     if (p.out_cnts[v] && p.cnt) static_cast<long long*>(p.out_cnts[v])[i] = p.cnt[(size_t)g * p.vstride + v];
   }
 }
@@ -561,7 +595,8 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   for (int c = 0; c < t->nvals; ++c) {
     p.vals[c] = vals ? vals[c] : nullptr;
     p.pcnt[c] = pcnt ? pcnt[c] : nullptr;
-    if ((t->flags & (MB200_GB_SUM | MB200_GB_COUNT)) && !p.vals[c]) return fail("groupby", "null value column");
+    if ((t->flags & (MB200_GB_SUM | MB200_GB_COUNT | MB200_GB_MIN | MB200_GB_MAX)) && !p.vals[c])
+      return fail("groupby", "null value column");
     if (partial && (t->flags & MB200_GB_COUNT) && !p.pcnt[c]) return fail("groupby", "null partial count column");
     aligned = aligned && aligned16(p.vals[c]);
   }
@@ -575,7 +610,7 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
     p.prefetch = (pf && pf[0] == '1') ? 1 : 0;  // measured: no gain (the limiter is random-sector DRAM traffic)
   }
   const size_t table_bytes = (size_t)t->cap * sizeof(Slot) + (size_t)t->gcap * t->vstride * 8 *
-                                                                  (((t->flags & MB200_GB_SUM) ? 1 : 0) +
+                                                                  (((t->flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX)) ? 1 : 0) +
                                                                    ((t->flags & MB200_GB_COUNT) ? 1 : 0));
   const int variant = gb_variant_from_env(table_bytes, dp.l2_bytes);
 
@@ -683,6 +718,15 @@ extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, i
   if (flags & MB200_GB_SUM) {
     MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     MB_TRY(cudaMemsetAsync(t->acc, 0, accb, st));
+  } else if (flags & (MB200_GB_MIN | MB200_GB_MAX)) {
+    MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
+    // "no value yet": INT64_MAX = bytes ff..ff 7f for min is not a byte pattern; use the fill kernel
+    gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
+                                                             (long long)(accb / 8),
+                                                             (flags & MB200_GB_MIN) ? 0x7fffffffffffffffLL
+                                                                                    : (long long)0x8000000000000000ULL);
+    MB_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
   }
   if (flags & MB200_GB_COUNT) {
     MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
@@ -802,6 +846,7 @@ extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64
   p.size = t->size;
   p.nvals = t->nvals;
   p.vstride = t->vstride;
+  p.flags = t->flags;
   p.ngroups = ngroups;
   p.out_keys = reinterpret_cast<long long*>(out_keys);
   for (int v = 0; v < t->nvals; ++v) {

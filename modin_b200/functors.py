@@ -416,6 +416,8 @@ class DevMeanReduce(DevFn):
 
 # ------------------------------------------------------------------ GroupByReduce functors
 _GB_FLAGS = {
+    "min": _lib.GB_MIN,
+    "max": _lib.GB_MAX,
     "sum": _lib.GB_SUM,
     "count": _lib.GB_COUNT,
     "size": _lib.GB_SIZE,
@@ -467,7 +469,7 @@ class DevGroupbyMap(DevFn):
 
 
 def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels):
-    if agg == "sum":
+    if agg in ("sum", "min", "max"):
         cols, cl = sums, labels
     elif agg == "count":
         cols, cl = cnts, labels
@@ -494,8 +496,8 @@ class DevGroupbyReduce(DevFn):
         as the input: sums | counts | size, depending on the aggregation)."""
         agg = self.agg
         n = len(keys)
-        if agg == "sum":
-            k, s, _, _ = ops.hash_aggregate([(keys, cols, None, None)], _lib.GB_SUM, n, partial=True)
+        if agg in ("sum", "min", "max"):  # partial sums add up; partial minima / maxima reduce with min / max
+            k, s, _, _ = ops.hash_aggregate([(keys, cols, None, None)], _GB_FLAGS[agg], n, partial=True)
             return k, list(s)
         if agg == "count":
             # int64 partial counts are merged through the count accumulators (values are ignored)

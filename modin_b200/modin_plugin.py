@@ -197,6 +197,8 @@ def register(shims: bool | None = None):
         groupby_count = B200GroupByReduce.register_agg("count")
         groupby_size = B200GroupByReduce.register_agg("size")
         groupby_mean = B200GroupByReduce.register_agg("mean")
+        groupby_min = B200GroupByReduce.register_agg("min")
+        groupby_max = B200GroupByReduce.register_agg("max")
 
         def fillna(self, **kwargs):
             """qc.py:2710-2813."""

@@ -178,7 +178,8 @@ class GroupTable:
 
     def emit(self, ngroups: int, sort: bool = True):
         keys = DeviceColumn.empty(ngroups, np.int64)
-        sums = [DeviceColumn.empty(ngroups, np.float64) for _ in range(self.nvals)] if self.flags & _lib.GB_SUM else None
+        has_acc = self.flags & (_lib.GB_SUM | _lib.GB_MIN | _lib.GB_MAX)
+        sums = [DeviceColumn.empty(ngroups, np.float64) for _ in range(self.nvals)] if has_acc else None
         cnts = [DeviceColumn.empty(ngroups, np.int64) for _ in range(self.nvals)] if self.flags & _lib.GB_COUNT else None
         sizes = DeviceColumn.empty(ngroups, np.int64) if self.flags & _lib.GB_SIZE else None
         scratch = _scratch(self.lib.mb200_gb_emit_scratch_bytes(ngroups), "gb_emit")

@@ -344,12 +344,18 @@ class DataFrameGroupBy:
     def mean(self, numeric_only=False):
         return self._wrap_aggregation(type(self._query_compiler).groupby_mean, numeric_only)
 
+    def min(self, numeric_only=False, min_count=-1):
+        return self._wrap_aggregation(type(self._query_compiler).groupby_min, numeric_only)
+
+    def max(self, numeric_only=False, min_count=-1):
+        return self._wrap_aggregation(type(self._query_compiler).groupby_max, numeric_only)
+
     def size(self):
         res = self._wrap_aggregation(type(self._query_compiler).groupby_size)
         return Series(query_compiler=res._query_compiler)
 
     def agg(self, func, *args, **kwargs):
-        if isinstance(func, str) and func in ("sum", "count", "mean", "size"):
+        if isinstance(func, str) and func in ("sum", "count", "mean", "size", "min", "max"):
             return getattr(self, func)()
         raise NotImplementedError(f"groupby.agg({func!r}) is not on the B200 path")
 

@@ -154,6 +154,8 @@ class B200QueryCompiler:
     groupby_count = GroupByReduce.register(DevGroupbyMap("count"), DevGroupbyReduce("count"))
     groupby_size = GroupByReduce.register(DevGroupbyMap("size"), DevGroupbyReduce("size"))
     groupby_mean = GroupByReduce.register(DevGroupbyMap("mean"), DevGroupbyReduce("mean"))
+    groupby_min = GroupByReduce.register(DevGroupbyMap("min"), DevGroupbyReduce("min"))
+    groupby_max = GroupByReduce.register(DevGroupbyMap("max"), DevGroupbyReduce("max"))
 
     # ---- merge (qc.py:657-667 -> MergeImpl.row_axis_merge merge.py:104-252) --------------------------
     def merge(self, right, **kwargs):

@@ -216,6 +216,8 @@ def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) ->
             return g.sum()
         if agg == "count":
             return g.count()
+        if agg in ("min", "max"):
+            return getattr(g, agg)()
         if agg == "size":
             return g.size().to_frame("size")
         if agg == "mean":
@@ -224,6 +226,8 @@ def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) ->
 
     partials = _pmap(lambda b: map_fn(b.copy()), row_blocks, threads)
     stacked = pandas.concat(partials, axis=0)
+    if agg in ("min", "max"):  # impl table storage_formats/pandas/groupby.py:237-248: ("min","min"), ("max","max")
+        return getattr(stacked.groupby(level=0, sort=True), agg)()
     regrouped = stacked.groupby(level=0, sort=True).sum()
     if agg == "mean":
         return regrouped["sum"] / regrouped["count"]

@@ -101,6 +101,12 @@ def hash_aggregate(items, flags, capacity_hint, partial=False, sort=True):
         for v in range(nv):
             x = np.concatenate([_np(it[1][v]) for it in items])
             sums.append(_col(pandas.Series(np.where(np.isnan(x), 0.0, x)).groupby(keys, sort=True).sum().to_numpy()))
+    for flag, fn in ((_lib.GB_MIN, "min"), (_lib.GB_MAX, "max")):
+        if flags & flag:
+            sums = []
+            for v in range(nv):
+                x = np.concatenate([_np(it[1][v]) for it in items])
+                sums.append(_col(getattr(pandas.Series(x).groupby(keys, sort=True), fn)().to_numpy().astype(np.float64)))
     if flags & _lib.GB_COUNT:
         cnts = []
         for v in range(nv):

@@ -181,6 +181,21 @@ def test_against_oracle_various_shapes(n, W, nan):
     assert_exact(df.max().to_numpy(), orc.df_max(pdf, NPART).to_numpy(), "max")
 
 
+def test_groupby_min_max_bit_exact():
+    """storage_formats/pandas/groupby.py:237-248: min -> (min, min), max -> (max, max); no rounding involved."""
+    m = bpd()
+    pdf = synth.host_frame(30011, 3, seed=13, nan_per_64k=20000, key_modulus=977)
+    pdf.loc[pdf["key"] == 5, "c1"] = np.nan  # an all-NaN group -> NaN
+    pdf.loc[3, "c2"] = np.inf
+    pdf.loc[4, "c2"] = -np.inf
+    g = m.DataFrame(pdf).groupby("key")
+    for agg in ("min", "max"):
+        got = getattr(g, agg)()._to_pandas()
+        want = orc.groupby_reduce(pdf, "key", agg, 4)
+        assert_exact(got.index.to_numpy(), want.index.to_numpy(), f"{agg} keys")
+        assert_exact(got.to_numpy(), want.to_numpy(), f"groupby {agg}")
+
+
 def test_prod_tree_reduce():
     m = bpd()
     pdf = synth.host_frame(300, 4, seed=21, nan_per_64k=3000) * 1.7

@@ -69,7 +69,7 @@ def test_groupby_and_merge_through_the_api(cpu_device):
     pdf = synth.host_frame(5003, 3, seed=42, nan_per_64k=2000, key_modulus=41)
     df = bpd.DataFrame(pdf)
     g = df.groupby("key")
-    for agg in ("sum", "count", "mean"):
+    for agg in ("sum", "count", "mean", "min", "max"):
         got = getattr(g, agg)()._to_pandas()
         want = orc.groupby_reduce(pdf, "key", agg, 4)
         assert list(got.index) == list(want.index) and got.index.name == "key"
