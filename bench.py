@@ -315,15 +315,27 @@ def run_b200_arm(args):
             ngroups[0] = len(r)
             del r
 
+        from modin_b200 import config as _cfg
+
         ksteps = max(3, args.steps // 2)
-        total_g, per_g = timed(step_gb, ksteps, 2)
-        ms_g = total_g / ksteps
-        ach = rows_local * (8 + 8 * W) / (statistics.mean(per_g) / 1e3) / 1e9
-        also.append({"metric": "rows/sec groupby('key').sum() 1e9 rows, 1e6 int64 keys, 8 f64 vals",
-                     "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
-                     "roofline": {"bound": "hbm", "kernel": "gb_accumulate_kernel (L2-resident hash aggregate)",
-                                  "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                  "traffic": traffic_for("groupby_sum", rows_local)}})  # fmt: skip
+        # default engine behaviour: one 8 B/row key min/max pre-pass (inside the timed step) picks the dense
+        # (direct-addressed) table because the synthetic keys span [0, G); then the same query with the hash
+        # table forced -- what keys spread over a wide range get
+        for dense_on, label, kern in (
+            (True, "", "key_range_kernel + gb_accumulate_tma_kernel on a dense (direct-addressed) table"),
+            (False, " [hash table forced]", "gb_accumulate_tma_kernel (open-addressed hash aggregate)"),
+        ):
+            _cfg.GroupbyDenseKeys.put(dense_on)
+            total_g, per_g = timed(step_gb, ksteps, 2)
+            ms_g = total_g / ksteps
+            ach = rows_local * (8 + 8 * W) / (statistics.mean(per_g) / 1e3) / 1e9
+            also.append({"metric": f"rows/sec groupby('key').sum() 1e9 rows, 1e6 int64 keys, 8 f64 vals{label}",
+                         "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
+                         "roofline": {"bound": "hbm", "kernel": kern,
+                                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                      "traffic": traffic_for("groupby_sum" if not dense_on else "groupby_sum_dense",
+                                                             rows_local)}})  # fmt: skip
+        _cfg.GroupbyDenseKeys.put(True)
         del g
         torch.cuda.empty_cache()
         # ---- broadcast merge: fact (rows x (key + 8 f64)) LEFT JOIN dim (1e7 x (key + 1 f64)) on int64 key (C5)

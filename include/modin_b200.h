@@ -178,6 +178,27 @@ typedef struct mb200_gb_table mb200_gb_table; /* opaque, device resident */
  * `nvals` float64 accumulator columns.  flags = mb200_gb_flags. */
 int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags,
                     mb200_stream_t stream);
+/* min / max of an int64 key column into minmax_dev[2] (device).  init != 0 resets the pair to
+ * {INT64_MAX, INT64_MIN} first; several row partitions accumulate into one pair with init = 0.
+ * The pre-pass (8 B/row) that lets the caller choose a DENSE table when the key range is narrow. */
+int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* minmax_dev, int init,
+                    mb200_stream_t stream);
+/* Create a DENSE (direct-addressed) table for keys known to lie in [key_min, key_max]
+ * (R = key_max - key_min + 1 <= 2^29): group id = key - key_min, no hashing, no probe; one presence byte
+ * per key.  Same accumulate / merge_partial / ngroups / emit / destroy calls as a hashed table; emit is
+ * always key-ascending and needs no sort.  A key outside the range sets the overflow flag.
+ * acc / cnt / size / present: all NULL = the library allocates; otherwise CALLER-OWNED device arrays
+ * (16-byte aligned; the library initialises them and never frees them) laid out as
+ *   acc[R][vs] float64 (int64 ordered images for MIN / MAX), cnt[R][vs] int64, size[R] int64,
+ *   present[4 * ceil(R / 4)] uint8,      vs = max(4, nvals rounded up to a multiple of 4),
+ * so that the host can run collectives on them (NCCL SUM / MIN / MAX on acc, SUM on cnt and size, MAX on
+ * present merge the tables of several GPUs: the multi-GPU GroupByReduce.reduce for dense keys). */
+int mb200_gb_create_dense(mb200_gb_table** table, int64_t key_min, int64_t key_max, int nvals,
+                          int flags, void* acc, void* cnt, void* size, void* present,
+                          mb200_stream_t stream);
+/* Restrict what mb200_gb_ngroups / mb200_gb_emit report to group ids [gid_lo, gid_hi) (multiples of 4,
+ * or gid_hi = R): after a cross-GPU merge each rank emits its own slice of the key range. */
+int mb200_gb_dense_window(mb200_gb_table* table, int64_t gid_lo, int64_t gid_hi);
 int mb200_gb_destroy(mb200_gb_table* table, mb200_stream_t stream);
 /* Hash-aggregate one block: keys[nrows] int64, vals[nvals][nrows] float64 (device).
  * May be called repeatedly (one call per row partition resident on this GPU);

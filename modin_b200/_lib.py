@@ -63,6 +63,9 @@ _SIGNATURES = {
     "mb200_reduce_scratch_bytes": (C.c_size_t, [C.c_int]),
     "mb200_reduce_columns": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _i64, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "mb200_gb_create": (C.c_int, [_vpp, _i64, C.c_int, C.c_int, _vp]),
+    "mb200_key_range": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp]),
+    "mb200_gb_create_dense": (C.c_int, [_vpp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mb200_gb_dense_window": (C.c_int, [_vp, _i64, _i64]),
     "mb200_gb_destroy": (C.c_int, [_vp, _vp]),
     "mb200_gb_accumulate": (C.c_int, [_vp, _vp, _vpp, _i64, _vp]),
     "mb200_gb_merge_partial": (C.c_int, [_vp, _vp, _vpp, _vpp, _vp, _i64, _vp]),

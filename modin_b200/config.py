@@ -93,3 +93,12 @@ class ReduceVariant(Parameter):
 
     varname = "MB200_REDUCE_VARIANT"
     default = 0
+
+
+class GroupbyDenseKeys(Parameter):
+    """Use a direct-addressed (dense) group table when the key range is narrow (default on);
+    off = always hash.  The decision costs one 8 B/row min/max pre-pass over the key column."""
+
+    varname = "MB200_GB_DENSE"
+    default = True
+    type = bool

@@ -77,6 +77,14 @@ struct mb200_gb_table {
   int vstride;
   int flags;
   mb200::GbMeta* meta;
+  // dense (direct-addressed) tables: gid = key - kbase, no slots; one presence byte per key
+  int dense;
+  long long kbase;
+  unsigned int* present;   // [nwords] words of 4 presence bytes
+  long long nwords;
+  unsigned int* blockoff;  // [nwords / 256 + 1] per-block popcounts -> exclusive offsets (emit)
+  int borrowed;            // acc / cnt / size / present belong to the caller
+  long long win_lo, win_hi;  // gid window that ngroups / emit report (default: the whole range)
 };
 
 namespace mb200 {
@@ -108,6 +116,9 @@ struct GbParams {
   const void* pcnt[MB200_MAX_COLS];   // partial counts (PARTIAL only)
   const long long* psize;             // partial sizes (PARTIAL only)
   long long nrows;
+  int dense;              // direct-addressed table: gid = key - kbase
+  long long kbase;
+  unsigned int* present;  // dense: one byte per key of [kbase, kbase + gcap)
   int policy_mode;  // unused (kept for experiments)
   int prefetch;     // TMA kernel: L2-prefetch the next tile's probe slots (MB200_GB_PREFETCH=0 disables)
 };
@@ -271,6 +282,21 @@ __device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool i
 
 // Dense group id of every lane's key (gcap = table overflowed).  Must be called by all 32 lanes.
 __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t) {
+  if (p.dense) {
+    // direct addressing (kernel-uniform branch): no probe, no slots.  Presence is one BYTE per key (0 / 1)
+    // so that setting it is a plain idempotent store and ranks can merge maps with an NCCL MAX; the
+    // check reads L2 (a stale L1 line would make every later row of that line repeat the store).
+    const unsigned long long d = (unsigned long long)k - (unsigned long long)p.kbase;
+    if (d >= (unsigned long long)p.gcap) {
+      p.meta->overflow = 1;  // key outside the declared range
+      return (int)p.gcap;
+    }
+    unsigned char* w = reinterpret_cast<unsigned char*>(p.present) + d;
+    unsigned int cur;
+    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(cur) : "l"(w) : "memory");
+    if (!cur) asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(w), "r"(1u) : "memory");  // idempotent
+    return (int)d;
+  }
   const int lane = threadIdx.x & 31;
   const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
   const int leader = __ffs(peers) - 1;
@@ -441,6 +467,128 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------- low-cardinality keys: table in shared memory
+// Dense tables small enough for shared memory (R * vs * 8 B per accumulator array; R <= ~2600 at V = 8)
+// are PRIVATISED per CTA: rows are accumulated with shared-memory atomics and each CTA adds its table to
+// the global one once at the end.  With few distinct keys every row of the frame would otherwise hit the
+// same few L2 lines with global atomics (G = 10: ~1e8 serialised RED.ADD.F64 per line per 1e9 rows).
+// Same TMA-staged tile ring as gb_accumulate_tma_kernel; the tail / unaligned cases fall through to
+// gb_accumulate_kernel on the same global arrays.
+struct SmemTableLayout {
+  unsigned int acc_off, cnt_off, size_off, present_off, total;
+};
+
+__global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_smem_kernel(const __grid_constant__ GbParams p,
+                                                                           long long ntiles,
+                                                                           const SmemTableLayout lay) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kGbStages * kStageBytes);
+  uint64_t* empty = full + kGbStages;
+  double* s_acc = reinterpret_cast<double*>(smem_raw + lay.acc_off);
+  long long* s_acc_i = reinterpret_cast<long long*>(s_acc);
+  // per-CTA counts fit 32 bits (a CTA sees < 2^32 rows): native ATOMS.ADD instead of a 64-bit CAS loop
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(smem_raw + lay.cnt_off);
+  unsigned int* s_size = reinterpret_cast<unsigned int*>(smem_raw + lay.size_off);
+  unsigned char* s_present = smem_raw + lay.present_off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = p.nvals, vs = p.vstride;
+  const int R = (int)p.gcap;
+  const bool f_sum = p.flags & MB200_GB_SUM, f_min = p.flags & MB200_GB_MIN, f_max = p.flags & MB200_GB_MAX;
+  const bool f_cnt = p.flags & MB200_GB_COUNT, f_size = p.flags & MB200_GB_SIZE;
+  const bool has_acc = f_sum || f_min || f_max;
+  const long long first = blockIdx.x;
+  const long long nmine = first < ntiles ? (ntiles - first + gridDim.x - 1) / gridDim.x : 0;
+
+  {
+    const long long init = f_min ? 0x7fffffffffffffffLL : (f_max ? (long long)0x8000000000000000ULL : 0LL);
+    for (int i = tid; i < R * vs; i += kGbTmaThreads) {
+      if (has_acc) s_acc_i[i] = init;
+      if (f_cnt) s_cnt[i] = 0u;
+    }
+    for (int i = tid; i < R; i += kGbTmaThreads) {
+      if (f_size) s_size[i] = 0u;
+      s_present[i] = 0;
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kGbStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGbWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kGbWarps) {
+    if (lane == 0) {  // producer: (1 + nv) bulk copies of 2 KiB per tile
+      const uint64_t pol = l2_policy_evict_first();
+      for (long long k = 0; k < nmine; ++k) {
+        const int s = (int)(k % kGbStages);
+        if (k >= kGbStages) mbar_wait(&empty[s], (uint32_t)(((k / kGbStages) - 1) & 1));
+        const long long row0 = (first + k * gridDim.x) * kTileRows;
+        double* stage = reinterpret_cast<double*>(smem_raw + (size_t)s * kStageBytes);
+        mbar_expect_tx(&full[s], (uint32_t)((1 + nv) * kTileRows * 8));
+        tma_bulk_g2s(stage, p.keys + row0, kTileRows * 8, &full[s], pol);
+        for (int c = 0; c < nv; ++c)
+          tma_bulk_g2s(stage + (size_t)(1 + c) * kTileColStride, static_cast<const double*>(p.vals[c]) + row0,
+                       kTileRows * 8, &full[s], pol);
+      }
+    }
+  } else {
+    const int c = lane & 7;
+    for (long long k = 0; k < nmine; ++k) {
+      const int s = (int)(k % kGbStages);
+      mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
+      const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
+      const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
+      const unsigned long long d = (unsigned long long)key - (unsigned long long)p.kbase;
+      const bool inr = d < (unsigned long long)R;
+      const int gid = inr ? (int)d : R;
+      if (inr) {
+        s_present[gid] = 1;
+        if (f_size) atomicAdd(&s_size[gid], 1u);
+      } else {
+        p.meta->overflow = 1;  // key outside the declared range
+      }
+      const double* vt = stage + kTileColStride + warp * 32;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int r = 4 * kk + (lane >> 3);
+        const int g = __shfl_sync(0xffffffffu, gid, r);
+        if (c < nv && g < R) {
+          const double xv = vt[c * kTileColStride + r];
+          if (xv == xv) {
+            const int o = g * vs + c;
+            if (f_sum) atomicAdd(&s_acc[o], xv);
+            else if (f_min) atomicMin(&s_acc_i[o], f64_to_ordered(xv));
+            else if (f_max) atomicMax(&s_acc_i[o], f64_to_ordered(xv));
+            if (f_cnt) atomicAdd(&s_cnt[o], 1u);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+  __syncthreads();
+  // ---- add this CTA's table to the global one (coalesced over the [gid][column] arrays)
+  for (int i = tid; i < R * vs; i += kGbTmaThreads) {
+    const int g = i / vs, cc = i - g * vs;
+    if (cc >= nv || !s_present[g]) continue;
+    if (f_sum) red_add_f64(p.acc + i, s_acc[i], 0);
+    else if (f_min && s_acc_i[i] != 0x7fffffffffffffffLL) red_min_s64(reinterpret_cast<long long*>(p.acc) + i, s_acc_i[i]);
+    else if (f_max && s_acc_i[i] != (long long)0x8000000000000000ULL)
+      red_max_s64(reinterpret_cast<long long*>(p.acc) + i, s_acc_i[i]);
+    if (f_cnt && s_cnt[i]) red_add_u64(p.cnt + i, (long long)s_cnt[i], 0);
+  }
+  for (int g = tid; g < R; g += kGbTmaThreads) {
+    if (!s_present[g]) continue;
+    reinterpret_cast<unsigned char*>(p.present)[g] = 1;
+    if (f_size) red_add_u64(p.size + g, (long long)s_size[g], 0);
+  }
+}
+
 __global__ void gb_fill_kernel(long long* p, long long n, long long v) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
@@ -538,6 +686,144 @@ __global__ void gb_emit_kernel(const __grid_constant__ EmitParams p) {
   }
 }
 
+// ---------------------------------------------------------------- dense tables: key range, ordered emit
+// min / max of an int64 key column (the pre-pass that decides between a dense and a hashed table):
+// 4 x 256-bit streaming loads in flight per thread, one atomic pair per block.
+__global__ void __launch_bounds__(256) key_range_kernel(const long long* __restrict__ keys, long long n,
+                                                        long long* minmax) {
+  __shared__ long long s_min[8], s_max[8];
+  long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000ULL;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long head = (((uintptr_t)keys & 31u) == 0) ? (n & ~15LL) : 0;  // 16 keys per thread-iteration
+  for (long long i = tid * 4; i + 3 < head; i += nthreads * 16) {
+    i64x4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long j = i + (long long)u * nthreads * 4;
+      ok[u] = j + 3 < head;
+      if (ok[u]) v[u] = ldg_stream_i64x4(keys + j);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const long long a = v[u].x < v[u].y ? v[u].x : v[u].y, b = v[u].z < v[u].w ? v[u].z : v[u].w;
+      const long long c = v[u].x > v[u].y ? v[u].x : v[u].y, d = v[u].z > v[u].w ? v[u].z : v[u].w;
+      const long long mn = a < b ? a : b, mx = c > d ? c : d;
+      lo = mn < lo ? mn : lo;
+      hi = mx > hi ? mx : hi;
+    }
+  }
+  for (long long i = head + tid; i < n; i += nthreads) {
+    const long long k = keys[i];
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, lo, m), b = __shfl_xor_sync(0xffffffffu, hi, m);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_min[warp] = lo;
+    s_max[warp] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      lo = s_min[w] < lo ? s_min[w] : lo;
+      hi = s_max[w] > hi ? s_max[w] : hi;
+    }
+    if (lo <= hi) {
+      atomicMin(&minmax[0], lo);
+      atomicMax(&minmax[1], hi);
+    }
+  }
+}
+
+__global__ void key_range_init_kernel(long long* minmax) {
+  minmax[0] = 0x7fffffffffffffffLL;
+  minmax[1] = (long long)0x8000000000000000ULL;
+}
+
+// block b counts the set bits of presence words [256 b, 256 b + 256)
+__global__ void __launch_bounds__(256) dense_count_kernel(const unsigned int* __restrict__ present, long long nwords,
+                                                          unsigned int* __restrict__ blockoff) {
+  __shared__ unsigned int s[8];
+  const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
+  unsigned int c = w < nwords ? __popc(present[w]) : 0u;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = 0;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    blockoff[blockIdx.x] = t;
+  }
+}
+
+// single block: exclusive scan of blockoff[0..nblocks) in place; total -> meta->ngroups
+__global__ void __launch_bounds__(1024) dense_scan_kernel(unsigned int* blockoff, long long nblocks, GbMeta* meta) {
+  __shared__ unsigned int s_part[1024];
+  const int t = threadIdx.x;
+  const long long per = (nblocks + 1023) / 1024;
+  const long long lo = (long long)t * per, hi = (lo + per < nblocks) ? lo + per : nblocks;
+  unsigned int sum = 0;
+  for (long long i = lo; i < hi; ++i) sum += blockoff[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+    const unsigned int v = (t >= off) ? s_part[t - off] : 0u;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  unsigned int run = s_part[t] - sum;
+  for (long long i = lo; i < hi; ++i) {
+    const unsigned int c = blockoff[i];
+    blockoff[i] = run;
+    run += c;
+  }
+  if (t == 1023) meta->ngroups = (int)s_part[1023];
+}
+
+// block b writes the keys / gids of its set bits at blockoff[b] + rank, in ascending key order
+__global__ void __launch_bounds__(256) dense_fill_kernel(const unsigned int* __restrict__ present, long long nwords,
+                                                         const unsigned int* __restrict__ blockoff, long long kbase,
+                                                         long long gid0, long long* __restrict__ keys_out,
+                                                         long long* __restrict__ perm_out, long long nout) {
+  __shared__ unsigned int s[8];
+  const long long w = (long long)blockIdx.x * 256 + threadIdx.x;
+  unsigned int bits = w < nwords ? present[w] : 0u;
+  const unsigned int c = __popc(bits);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int incl = c;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, m);
+    if (lane >= m) incl += v;
+  }
+  if (lane == 31) s[warp] = incl;
+  __syncthreads();
+  unsigned int base = blockoff[blockIdx.x];
+  for (int i = 0; i < warp; ++i) base += s[i];
+  long long o = (long long)base + incl - c;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const long long g = gid0 + w * 4 + (b >> 3);  // presence bytes are 0 / 1: bit 8 j of a word = key 4 w + j
+    if (o < nout) {
+      keys_out[o] = kbase + g;
+      perm_out[o] = g;
+    }
+    ++o;
+  }
+}
+
 static long long next_pow2(long long v) {
   long long p = 1;
   while (p < v) p <<= 1;
@@ -590,6 +876,9 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   p.vstride = t->vstride;
   p.flags = t->flags;
   p.meta = t->meta;
+  p.dense = t->dense;
+  p.kbase = t->kbase;
+  p.present = t->present;
   p.keys = keys;
   bool aligned = aligned16(keys);
   for (int c = 0; c < t->nvals; ++c) {
@@ -659,7 +948,42 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
     }
   }
 
-  if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
+  // low-cardinality dense tables: privatise the table in shared memory (MB200_GB_SMEM=0 disables)
+  bool smem_done = false;
+  if (t->dense && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
+    const char* e = getenv("MB200_GB_SMEM");
+    const size_t arr = (size_t)t->gcap * t->vstride * 8;
+    SmemTableLayout lay;
+    size_t off = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
+    off = (off + 15) & ~(size_t)15;
+    lay.acc_off = (unsigned)off;
+    if (t->flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX)) off += arr;
+    lay.cnt_off = (unsigned)off;
+    if (t->flags & MB200_GB_COUNT) off += arr / 2;  // 32-bit per-CTA counters
+    lay.size_off = (unsigned)off;
+    if (t->flags & MB200_GB_SIZE) off += (((size_t)t->gcap * 4) + 15) & ~(size_t)15;
+    lay.present_off = (unsigned)off;
+    off += ((size_t)t->gcap + 15) & ~(size_t)15;
+    lay.total = (unsigned)off;
+    if (!(e && e[0] == '0') && off <= dp.smem_optin) {
+      const long long ntiles = nrows / kTileRows;
+      MB_CUDA(cudaFuncSetAttribute(gb_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+      int occ = 0;
+      MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_smem_kernel, kGbTmaThreads, off));
+      long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
+      if (grid > ntiles) grid = ntiles;
+      gb_accumulate_smem_kernel<<<(unsigned)grid, kGbTmaThreads, off, st>>>(p, ntiles, lay);
+      MB_LAUNCH_CHECK("gb_accumulate_smem_kernel");
+      const long long done = ntiles * kTileRows;
+      if (done == nrows) return 0;
+      p.keys = keys + done;
+      for (int c = 0; c < t->nvals; ++c)
+        if (p.vals[c]) p.vals[c] = static_cast<const double*>(p.vals[c]) + done;
+      p.nrows = nrows - done;
+      smem_done = true;
+    }
+  }
+  if (!smem_done && variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
     const size_t smem = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
     MB_CUDA(cudaFuncSetAttribute(gb_accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -689,8 +1013,72 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
 
 using namespace mb200;
 
+struct DenseArrays {  // caller-owned arrays of a dense table (all NULL: the library allocates)
+  void* acc;
+  void* cnt;
+  void* size;
+  void* present;
+};
+
+static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags, bool dense,
+                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream);
+
 extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags,
                                mb200_stream_t stream) {
+  return gb_create_impl(table, group_capacity, nvals, flags, false, 0, DenseArrays{}, stream);
+}
+
+extern "C" int mb200_gb_create_dense(mb200_gb_table** table, int64_t key_min, int64_t key_max, int nvals, int flags,
+                                     void* acc, void* cnt, void* size, void* present, mb200_stream_t stream) {
+  if (key_max < key_min) return fail("mb200_gb_create_dense", "empty key range");
+  const unsigned long long range = (unsigned long long)key_max - (unsigned long long)key_min + 1ULL;
+  if (range == 0 || range > (1ULL << 29)) return fail("mb200_gb_create_dense", "key range above 2^29");
+  DenseArrays ext{acc, cnt, size, present};
+  if (present) {
+    const bool need_acc = flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX);
+    if ((need_acc && !acc) || ((flags & MB200_GB_COUNT) && !cnt) || ((flags & MB200_GB_SIZE) && !size))
+      return fail("mb200_gb_create_dense", "caller-owned arrays: every array the flags need must be given");
+    if (!aligned16(acc) || !aligned16(cnt) || !aligned16(size) || !aligned16(present))
+      return fail("mb200_gb_create_dense", "caller-owned arrays must be 16-byte aligned");
+  } else if (acc || cnt || size) {
+    return fail("mb200_gb_create_dense", "caller-owned arrays need the presence array too");
+  }
+  return gb_create_impl(table, (int64_t)range, nvals, flags, true, key_min, ext, stream);
+}
+
+extern "C" int mb200_gb_dense_window(mb200_gb_table* t, int64_t gid_lo, int64_t gid_hi) {
+  if (!t || !t->dense) return fail("mb200_gb_dense_window", "not a dense table");
+  if (gid_lo < 0 || gid_hi < gid_lo || gid_hi > t->gcap || (gid_lo & 3) || ((gid_hi & 3) && gid_hi != t->gcap))
+    return fail("mb200_gb_dense_window", "window must be [lo, hi) within the range, lo and hi multiples of 4");
+  t->win_lo = gid_lo;
+  t->win_hi = gid_hi;
+  return 0;
+}
+
+extern "C" int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* minmax_dev, int init,
+                               mb200_stream_t stream) {
+  if (!minmax_dev) return fail("mb200_key_range", "null output");
+  if (nrows < 0) return fail("mb200_key_range", "negative nrows");
+  if (nrows > 0 && !keys) return fail("mb200_key_range", "null keys");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (init) {
+    key_range_init_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(minmax_dev));
+    MB_LAUNCH_CHECK("key_range_init_kernel");
+  }
+  if (nrows == 0) return 0;
+  long long grid = (long long)dp.sm_count * 8;
+  const long long need = (nrows + 256 * 16 - 1) / (256 * 16);
+  if (grid > need) grid = need;
+  key_range_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const long long*>(keys), nrows,
+                                                  reinterpret_cast<long long*>(minmax_dev));
+  MB_LAUNCH_CHECK("key_range_kernel");
+  return 0;
+}
+
+static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags, bool dense,
+                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream) {
   if (!table) return fail("mb200_gb_create", "null out pointer");
   if (nvals < 0 || nvals > MB200_MAX_COLS) return fail("mb200_gb_create", "nvals out of range (0..32)");
   if (group_capacity < 1) group_capacity = 1;
@@ -701,7 +1089,13 @@ extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, i
   mb200_gb_table* t = new mb200_gb_table();
   memset(t, 0, sizeof(*t));
   t->gcap = group_capacity;
-  t->cap = next_pow2(2 * group_capacity < 1024 ? 1024 : 2 * group_capacity);
+  t->cap = dense ? 0 : next_pow2(2 * group_capacity < 1024 ? 1024 : 2 * group_capacity);
+  t->dense = dense ? 1 : 0;
+  t->kbase = kbase;
+  t->win_lo = 0;
+  t->win_hi = group_capacity;
+  t->borrowed = (dense && ext.present) ? 1 : 0;
+  t->nwords = dense ? (group_capacity + 3) / 4 : 0;  // one presence byte per key, scanned as 32-bit words
   t->nvals = nvals;
   t->vstride = (nvals + 3) & ~3;  // 32-byte sector aligned rows
   if (t->vstride == 0) t->vstride = 4;
@@ -713,13 +1107,25 @@ extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, i
     e = (call);                     \
     if (e != cudaSuccess) goto bad; \
   } while (0)
-  MB_TRY(cudaMallocAsync((void**)&t->slots, (size_t)t->cap * sizeof(Slot), st));
+  if (t->borrowed) {  // arrays live in the caller's allocator (so that it can run collectives on them)
+    t->present = static_cast<unsigned int*>(ext.present);
+    t->acc = static_cast<double*>(ext.acc);
+    t->cnt = static_cast<long long*>(ext.cnt);
+    t->size = static_cast<long long*>(ext.size);
+  }
+  if (dense) {
+    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->present, (size_t)t->nwords * 4, st));
+    MB_TRY(cudaMemsetAsync(t->present, 0, (size_t)t->nwords * 4, st));
+    MB_TRY(cudaMallocAsync((void**)&t->blockoff, (size_t)((t->nwords + 255) / 256 + 1) * 4, st));
+  } else {
+    MB_TRY(cudaMallocAsync((void**)&t->slots, (size_t)t->cap * sizeof(Slot), st));
+  }
   MB_TRY(cudaMallocAsync((void**)&t->meta, sizeof(GbMeta), st));
   if (flags & MB200_GB_SUM) {
-    MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
+    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     MB_TRY(cudaMemsetAsync(t->acc, 0, accb, st));
   } else if (flags & (MB200_GB_MIN | MB200_GB_MAX)) {
-    MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
+    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     // "no value yet": INT64_MAX = bytes ff..ff 7f for min is not a byte pattern; use the fill kernel
     gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
                                                              (long long)(accb / 8),
@@ -729,15 +1135,15 @@ extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, i
     g_launches.fetch_add(1);
   }
   if (flags & MB200_GB_COUNT) {
-    MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
+    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
     MB_TRY(cudaMemsetAsync(t->cnt, 0, accb, st));
   }
   if (flags & MB200_GB_SIZE) {
-    MB_TRY(cudaMallocAsync((void**)&t->size, (size_t)t->gcap * 8, st));
+    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->size, (size_t)t->gcap * 8, st));
     MB_TRY(cudaMemsetAsync(t->size, 0, (size_t)t->gcap * 8, st));
   }
 #undef MB_TRY
-  gb_init_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->meta);
+  gb_init_kernel<<<(unsigned)(dense ? 1 : (t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->meta);
   e = cudaGetLastError();
   if (e != cudaSuccess) goto bad;
   g_launches.fetch_add(1);
@@ -753,9 +1159,13 @@ extern "C" int mb200_gb_destroy(mb200_gb_table* t, mb200_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (t->slots) cudaFreeAsync(t->slots, st);
   if (t->meta) cudaFreeAsync(t->meta, st);
-  if (t->acc) cudaFreeAsync(t->acc, st);
-  if (t->cnt) cudaFreeAsync(t->cnt, st);
-  if (t->size) cudaFreeAsync(t->size, st);
+  if (!t->borrowed) {
+    if (t->acc) cudaFreeAsync(t->acc, st);
+    if (t->cnt) cudaFreeAsync(t->cnt, st);
+    if (t->size) cudaFreeAsync(t->size, st);
+    if (t->present) cudaFreeAsync(t->present, st);
+  }
+  if (t->blockoff) cudaFreeAsync(t->blockoff, st);
   delete t;
   return 0;
 }
@@ -790,6 +1200,14 @@ extern "C" int mb200_gb_merge_partial(mb200_gb_table* t, const int64_t* keys, co
 
 extern "C" int mb200_gb_ngroups(mb200_gb_table* t, int64_t* ngroups, int* overflow, mb200_stream_t stream) {
   if (!t) return fail("mb200_gb_ngroups", "null table");
+  if (t->dense) {  // count the presence bytes of the window
+    const long long w0 = t->win_lo / 4, nw = (t->win_hi - t->win_lo + 3) / 4;
+    const long long nblocks = nw > 0 ? (nw + 255) / 256 : 1;
+    dense_count_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(t->present + w0, nw, t->blockoff);
+    MB_LAUNCH_CHECK("dense_count_kernel");
+    dense_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(t->blockoff, nblocks, t->meta);
+    MB_LAUNCH_CHECK("dense_scan_kernel");
+  }
   GbMeta m;
   MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   MB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -819,13 +1237,29 @@ extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64
   long long* perm = reinterpret_cast<long long*>(s + (size_t)ngroups * 8);
   size_t off = ((size_t)ngroups * 16 + 255) & ~(size_t)255;
   char* sort_s = s + off;
-  gb_collect_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->gcap, keys_by_gid, perm,
-                                                                      t->meta);
-  MB_LAUNCH_CHECK("gb_collect_kernel");
   GbMeta m;
-  MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, st));
-  MB_CUDA(cudaStreamSynchronize(st));
-  if (m.overflow) return fail("mb200_gb_emit", "table overflowed: recreate with a larger group capacity");
+  memset(&m, 0, sizeof(m));
+  if (t->dense) {
+    // presence bits -> (key, gid) lists, already in ascending key order: no collect, no sort, and no host
+    // round trip (mb200_gb_ngroups reported the overflow flag when the caller sized the outputs)
+    const long long w0 = t->win_lo / 4, nw = (t->win_hi - t->win_lo + 3) / 4;
+    const long long nblocks = nw > 0 ? (nw + 255) / 256 : 1;
+    dense_count_kernel<<<(unsigned)nblocks, 256, 0, st>>>(t->present + w0, nw, t->blockoff);
+    MB_LAUNCH_CHECK("dense_count_kernel");
+    dense_scan_kernel<<<1, 1024, 0, st>>>(t->blockoff, nblocks, t->meta);
+    MB_LAUNCH_CHECK("dense_scan_kernel");
+    dense_fill_kernel<<<(unsigned)nblocks, 256, 0, st>>>(t->present + w0, nw, t->blockoff, t->kbase, t->win_lo,
+                                                        keys_by_gid, perm, ngroups);
+    MB_LAUNCH_CHECK("dense_fill_kernel");
+    sort = 0;
+  } else {
+    gb_collect_kernel<<<(unsigned)((t->cap + 255) / 256), 256, 0, st>>>(t->slots, t->cap, t->gcap, keys_by_gid, perm,
+                                                                        t->meta);
+    MB_LAUNCH_CHECK("gb_collect_kernel");
+    MB_CUDA(cudaMemcpyAsync(&m, t->meta, sizeof(m), cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (m.overflow) return fail("mb200_gb_emit", "table overflowed: recreate with a larger group capacity");
+  }
   if (sort) {
     long long* tk = reinterpret_cast<long long*>(sort_s);
     long long* tp = reinterpret_cast<long long*>(sort_s + (size_t)ngroups * 8);

@@ -91,6 +91,27 @@ def shard_bounds(nrows: int, r: int | None = None, ws: int | None = None):
 _REDUCE_OPS = {"sum": "SUM", "min": "MIN", "max": "MAX"}
 
 
+def all_reduce_inplace(tensor, op: str) -> None:
+    """Element-wise all_reduce of one (large) device array in place -- the cross-GPU merge of dense
+    group tables: NVSwitch carries 2 (W-1)/W x the table once, no keys move."""
+    if is_distributed() and tensor.numel():
+        d = _dist()
+        d.all_reduce(tensor, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
+
+
+def dense_split(nkeys: int, r: int | None = None, ws: int | None = None):
+    """Slice [lo, hi) of a dense key range [0, nkeys) that rank r emits: equal chunks rounded up to a
+    multiple of 4 (the presence map is scanned in 4-byte words); trailing ranks may get (0, 0)."""
+    ws = world_size() if ws is None else ws
+    r = rank() if r is None else r
+    chunk = -(-int(nkeys) // ws)
+    chunk = (chunk + 3) & ~3
+    lo = r * chunk
+    if lo >= nkeys:
+        return 0, 0
+    return lo, min(lo + chunk, int(nkeys))
+
+
 def all_reduce_values(tensors: Sequence, ops: Sequence[str]) -> None:
     """In-place all_reduce of many 1-element tensors: one collective per (dtype, op) bucket.
 

@@ -558,6 +558,69 @@ class DevGroupbyReduce(DevFn):
         return self._finalize(k2, cols2, block.columns, key_label)
 
 
+def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", blocks, by_blocks):
+    """GroupByReduce with map and reduce fused for keys in a narrow range: ONE direct-addressed table per
+    GPU absorbs every row partition resident on it (no per-partition emit, no regroup), the tables of
+    all GPUs are merged in place by element-wise collectives (NCCL SUM / MIN / MAX over NVLink; no
+    key exchange at all), and each rank emits its slice of the key range, ascending.
+
+    Returns the finished result block, or None when the keys are not dense-able (the caller then runs
+    the general map -> exchange -> reduce path).  Every rank takes the same decision: it is made on the
+    all-reduced key range and row count."""
+    from . import dist
+    from .config import GroupbyDenseKeys
+
+    if not GroupbyDenseKeys.get() or map_fn.agg != reduce_fn.agg or not blocks or len(blocks) != len(by_blocks):
+        return None
+    agg = map_fn.agg
+    flags = _GB_FLAGS[agg]
+    items, labels, key_label = [], None, None
+    for block, by_block in zip(blocks, by_blocks):
+        _check_block(block, map_fn.op)
+        key, key_label, vals, labels = _split_key_values(block, by_block)
+        if agg == "size":
+            vals, labels = [], labels[:0]
+        else:
+            vals = ops.cast_columns_f64(vals) if agg in ("count", "mean") else vals
+            if any(v.dtype != np.float64 for v in vals):
+                raise NotImplementedError("device groupby.sum aggregates float64 value columns only")
+        items.append((key, vals))
+    if len(labels) > _lib_max_cols():
+        return None
+    t = ops.torch_mod()
+    mm = ops.key_range_device([k for k, _ in items])
+    rows = t.tensor([sum(len(k) for k, _ in items)], dtype=t.int64, device=mm.device)
+    if dist.is_distributed():
+        dist.all_reduce_values([mm[0:1], mm[1:2], rows], ["min", "max", "sum"])
+    lo, hi = (int(v) for v in mm.tolist())
+    total_rows = int(rows.item())
+    if lo > hi:
+        return None  # no rows anywhere
+    cap = max(1024, min(map_fn.capacity_hint, total_rows))
+    if not ops.dense_range_ok(lo, hi, cap, total_rows, len(labels), flags):
+        return None
+    table = ops.GroupTable.dense(lo, hi, len(labels), flags)
+    try:
+        for key, vals in items:
+            table.accumulate(key, vals)
+        if dist.is_distributed():
+            for arr, op in table.collective_arrays():
+                dist.all_reduce_inplace(arr, op)
+            table.window(*dist.dense_split(hi - lo + 1))
+        ng, overflow = table.ngroups()
+        if overflow:
+            raise _lib.B200Error("dense group table saw a key outside its measured range")
+        keys, sums, cnts, sizes = table.emit(ng, sort=False)
+    finally:
+        table.close()
+    part = _partial_block(agg, keys, key_label, sums, cnts, sizes, labels)
+    return reduce_fn._finalize(part.index_cols[0], list(part.cols), part.columns, key_label)
+
+
+def _lib_max_cols() -> int:
+    return 32  # MB200_MAX_COLS
+
+
 # ------------------------------------------------------------------ broadcast merge functor
 class DevMerge(DevFn):
     """Per-row-partition ``pandas.merge(left_block, right, how, on, sort=False)`` of

@@ -153,6 +153,39 @@ class GroupTable:
         _lib.check(self.lib.mb200_gb_create(C.byref(self.handle), self.capacity, self.nvals, self.flags,
                                             current_stream()))  # fmt: skip
 
+    @classmethod
+    def dense(cls, key_min: int, key_max: int, nvals: int, flags: int):
+        """Direct-addressed table for keys in [key_min, key_max] (mb200_gb_create_dense)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self.capacity = R = int(key_max) - int(key_min) + 1
+        self.nvals, self.flags = int(nvals), int(flags)
+        # the arrays live in torch's allocator (layout: include/modin_b200.h) so that the multi-GPU
+        # reduce can run NCCL collectives on them in place
+        t = torch_mod()
+        dev = current_device()
+        vs = max(4, (self.nvals + 3) & ~3)
+        has_acc = self.flags & (_lib.GB_SUM | _lib.GB_MIN | _lib.GB_MAX)
+        self.acc = t.empty(R * vs, dtype=t.float64 if self.flags & _lib.GB_SUM else t.int64, device=dev) if has_acc else None
+        self.cnt = t.empty(R * vs, dtype=t.int64, device=dev) if self.flags & _lib.GB_COUNT else None
+        self.size = t.empty(R, dtype=t.int64, device=dev) if self.flags & _lib.GB_SIZE else None
+        self.present = t.empty(4 * ((R + 3) // 4), dtype=t.uint8, device=dev)
+        ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
+        _lib.check(self.lib.mb200_gb_create_dense(C.byref(self.handle), int(key_min), int(key_max), self.nvals,
+                                                  self.flags, ptr(self.acc), ptr(self.cnt), ptr(self.size),
+                                                  ptr(self.present), current_stream()))  # fmt: skip
+        return self
+
+    def collective_arrays(self):
+        """(tensor, reduce-op) pairs whose element-wise reduction over ranks merges dense tables."""
+        acc_op = "sum" if self.flags & _lib.GB_SUM else ("min" if self.flags & _lib.GB_MIN else "max")
+        out = [(self.acc, acc_op), (self.cnt, "sum"), (self.size, "sum"), (self.present, "max")]
+        return [(x, op) for x, op in out if x is not None]
+
+    def window(self, gid_lo: int, gid_hi: int):
+        _lib.check(self.lib.mb200_gb_dense_window(self.handle, int(gid_lo), int(gid_hi)))
+
     def accumulate(self, keys: DeviceColumn, vals: Sequence[DeviceColumn]):
         if keys.dtype != np.int64:
             raise TypeError("device groupby needs an int64 key column")
@@ -205,11 +238,66 @@ class GroupTable:
             pass
 
 
+DENSE_TABLE_MAX_BYTES = 8 << 30
+
+
+def key_range_device(key_cols: Sequence[DeviceColumn]):
+    """Device tensor [min, max] over int64 key columns ({INT64_MAX, INT64_MIN} when there are no rows)."""
+    lib = _lib.load()
+    t = torch_mod()
+    mm = t.empty(2, dtype=t.int64, device=current_device())
+    if not key_cols:
+        _lib.check(lib.mb200_key_range(None, 0, mm.data_ptr(), 1, current_stream()))
+    for i, k in enumerate(key_cols):
+        if k.dtype != np.int64:
+            raise TypeError("device groupby needs an int64 key column")
+        _lib.check(lib.mb200_key_range(k.ptr, len(k), mm.data_ptr(), 1 if i == 0 else 0, current_stream()))
+    return mm
+
+
+def key_range(key_cols: Sequence[DeviceColumn]):
+    """(min, max) over int64 key columns -- one streaming pass, one 16-byte D2H.  None when empty."""
+    lo, hi = (int(v) for v in key_range_device(key_cols).tolist())
+    return None if lo > hi else (lo, hi)
+
+
+def dense_range_ok(lo: int, hi: int, cap: int, total_rows: int, nvals: int, flags: int) -> bool:
+    """Dense tables pay range-proportional zero-fill and emit scan; their random footprint is only the
+    touched groups.  Take them when the range is within 4x the expected group count (or half the
+    rows) and the arrays stay under DENSE_TABLE_MAX_BYTES."""
+    rng = hi - lo + 1
+    if rng > (1 << 29) or rng > max(4 * cap, total_rows // 2, 1 << 16):
+        return False
+    vstride = max(4, (nvals + 3) & ~3)
+    arrays = (1 if flags & (_lib.GB_SUM | _lib.GB_MIN | _lib.GB_MAX) else 0) + (1 if flags & _lib.GB_COUNT else 0)
+    return rng * (vstride * 8 * arrays + 9) <= DENSE_TABLE_MAX_BYTES
+
+
 def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool = False, sort: bool = True):
-    """Run the hash aggregation over a list of (keys, vals[, cnts, sizes]) inputs, growing the
-    table when it overflows.  Returns (keys, sums, cnts, sizes) device columns."""
+    """Aggregate a list of (keys, vals[, cnts, sizes]) inputs into one table and emit it: a dense
+    (direct-addressed) table when the key range allows, else the hash table, grown when it
+    overflows.  Returns (keys, sums, cnts, sizes) device columns."""
+    from .config import GroupbyDenseKeys
+
     cap = max(int(capacity_hint), 1024)
     nvals = len(key_cols_vals[0][1]) if key_cols_vals[0][1] else 0
+    total_rows = sum(len(item[0]) for item in key_cols_vals)
+    if GroupbyDenseKeys.get() and total_rows > 0:
+        kr = key_range([item[0] for item in key_cols_vals])
+        if kr is not None and dense_range_ok(kr[0], kr[1], cap, total_rows, nvals, flags):
+            table = GroupTable.dense(kr[0], kr[1], nvals, flags)
+            try:
+                for item in key_cols_vals:
+                    if partial:
+                        table.merge_partial(*item)
+                    else:
+                        table.accumulate(item[0], item[1])
+                ng, overflow = table.ngroups()
+                if overflow:
+                    raise _lib.B200Error("dense group table saw a key outside its measured range")
+                return table.emit(ng, sort=False)
+            finally:
+                table.close()
     while True:
         table = GroupTable(cap, nvals, flags)
         try:

@@ -26,7 +26,7 @@ import pandas
 from . import dist
 from .block import DeviceBlock, concat_cols, concat_rows, torch_mod
 from .config import BenchmarkMode, MinColumnPartitionSize, MinRowPartitionSize, NPartitions
-from .functors import DevAffine, DevBinary, DevFma3, DevFn
+from .functors import DevAffine, DevBinary, DevFma3, DevFn, DevGroupbyMap, DevGroupbyReduce, fused_dense_groupby
 
 
 # ------------------------------------------------------------------ small utilities (sfutils.py)
@@ -586,6 +586,14 @@ class B200PartitionManager:
             if partitions.shape[1] > 1:
                 partitions = np.array([[cls._partition_class(concat_cols([p.get() for p in row]))]
                                        for row in partitions])  # fmt: skip
+            # keys in a narrow range: map + reduce fused into one direct-addressed table per GPU, merged
+            # across GPUs by element-wise collectives (functors.fused_dense_groupby); else the general path
+            fn_map, fn_red = unwrap(cls.preprocess_func(map_func))[0], unwrap(cls.preprocess_func(reduce_func))[0]
+            if axis == 0 and isinstance(fn_map, DevGroupbyMap) and isinstance(fn_red, DevGroupbyReduce) and by.shape[1] == 1:
+                fused = fused_dense_groupby(fn_map, fn_red, [row[0].get() for row in partitions],
+                                            [row[0].get() for row in by])  # fmt: skip
+                if fused is not None:
+                    return np.array([[cls._partition_class(fused)]])
             mapped_partitions = cls.broadcast_apply(axis, map_func, left=partitions, right=by)
         else:
             mapped_partitions = cls.map_partitions(partitions, map_func)

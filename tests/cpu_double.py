@@ -122,6 +122,99 @@ def hash_aggregate(items, flags, capacity_hint, partial=False, sort=True):
     return _col(uniq.astype(np.int64)), sums, cnts, sizes
 
 
+def key_range_device(key_cols):
+    ks = [_np(k) for k in key_cols if len(k)]
+    if not ks:
+        return torch.tensor([np.iinfo(np.int64).max, np.iinfo(np.int64).min], dtype=torch.int64)
+    return torch.tensor([min(int(k.min()) for k in ks), max(int(k.max()) for k in ks)], dtype=torch.int64)
+
+
+class GroupTable:
+    """numpy stand-in for the DENSE device table (same array layout as include/modin_b200.h), so that the
+    fused map+reduce path and its cross-rank merge by collectives run under gloo."""
+
+    @classmethod
+    def dense(cls, key_min, key_max, nvals, flags):
+        self = cls()
+        self.kbase, self.R, self.nvals, self.flags = int(key_min), int(key_max) - int(key_min) + 1, nvals, flags
+        self.vs = max(4, (nvals + 3) & ~3)
+        R, vs = self.R, self.vs
+        self.acc = self.cnt = self.size = None
+        if flags & _lib.GB_SUM:
+            self.acc = torch.zeros(R * vs, dtype=torch.float64)
+        elif flags & _lib.GB_MIN:
+            self.acc = torch.full((R * vs,), np.iinfo(np.int64).max, dtype=torch.int64)
+        elif flags & _lib.GB_MAX:
+            self.acc = torch.full((R * vs,), np.iinfo(np.int64).min, dtype=torch.int64)
+        if flags & _lib.GB_COUNT:
+            self.cnt = torch.zeros(R * vs, dtype=torch.int64)
+        if flags & _lib.GB_SIZE:
+            self.size = torch.zeros(R, dtype=torch.int64)
+        self.present = torch.zeros(4 * ((R + 3) // 4), dtype=torch.uint8)
+        self.win = (0, R)
+        return self
+
+    @staticmethod
+    def _ordered(x):  # order-preserving int64 image of float64 (csrc/groupby.cu f64_to_ordered)
+        b = x.view(np.int64)
+        return b ^ ((b >> 63) & np.int64(0x7FFFFFFFFFFFFFFF))
+
+    def accumulate(self, keys, vals):
+        g = _np(keys) - self.kbase
+        assert len(g) == 0 or (g.min() >= 0 and g.max() < self.R)
+        self.present.numpy()[g] = 1
+        if self.size is not None:
+            np.add.at(self.size.numpy(), g, 1)
+        for v, col in enumerate(vals):
+            x = _np(col)
+            ok = ~np.isnan(x)
+            o = g[ok] * self.vs + v
+            if self.flags & _lib.GB_SUM:
+                np.add.at(self.acc.numpy(), o, x[ok])
+            elif self.flags & _lib.GB_MIN:
+                np.minimum.at(self.acc.numpy(), o, self._ordered(x[ok]))
+            elif self.flags & _lib.GB_MAX:
+                np.maximum.at(self.acc.numpy(), o, self._ordered(x[ok]))
+            if self.cnt is not None:
+                np.add.at(self.cnt.numpy(), o, 1)
+
+    def collective_arrays(self):
+        acc_op = "sum" if self.flags & _lib.GB_SUM else ("min" if self.flags & _lib.GB_MIN else "max")
+        out = [(self.acc, acc_op), (self.cnt, "sum"), (self.size, "sum"), (self.present, "max")]
+        return [(x, op) for x, op in out if x is not None]
+
+    def window(self, lo, hi):
+        assert lo % 4 == 0 and (hi % 4 == 0 or hi == self.R) and 0 <= lo <= hi <= self.R
+        self.win = (int(lo), int(hi))
+
+    def _gids(self):
+        lo, hi = self.win
+        return lo + np.nonzero(self.present.numpy()[lo:hi])[0]
+
+    def ngroups(self):
+        return len(self._gids()), False
+
+    def emit(self, ngroups, sort=True):
+        g = self._gids()
+        assert len(g) == ngroups
+        sums = cnts = sizes = None
+        if self.acc is not None:
+            a = self.acc.numpy().reshape(self.R, self.vs)[g]
+            if not self.flags & _lib.GB_SUM:
+                empty = a == (np.iinfo(np.int64).max if self.flags & _lib.GB_MIN else np.iinfo(np.int64).min)
+                a = np.where(empty, np.nan, (a ^ ((a >> 63) & np.int64(0x7FFFFFFFFFFFFFFF))).view(np.float64))
+            sums = [_col(np.ascontiguousarray(a[:, v])) for v in range(self.nvals)]
+        if self.cnt is not None:
+            c = self.cnt.numpy().reshape(self.R, self.vs)[g]
+            cnts = [_col(np.ascontiguousarray(c[:, v])) for v in range(self.nvals)]
+        if self.size is not None:
+            sizes = _col(self.size.numpy()[g])
+        return _col((g + self.kbase).astype(np.int64)), sums, cnts, sizes
+
+    def close(self):
+        pass
+
+
 class JoinTable:
     def __init__(self, dim_keys):
         self.keys = _np(dim_keys)
@@ -177,8 +270,10 @@ def installed():
     saved = {
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
-                                        "compact_hits", "cast_columns_f64", "gen_f64", "gen_i64")},
+                                        "compact_hits", "cast_columns_f64", "gen_f64", "gen_i64", "GroupTable",
+                                        "key_range_device")},
     }  # fmt: skip
+    ops.GroupTable, ops.key_range_device = GroupTable, key_range_device
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device
     ops.map_columns, ops.reduce_columns, ops.hash_aggregate = map_columns, reduce_columns, hash_aggregate

@@ -135,3 +135,59 @@ def test_exchange_with_an_empty_rank():
     vals = np.concatenate([o[1] for o in out])
     assert np.array_equal(np.sort(keys), np.arange(10))
     assert np.array_equal(vals, keys * 2.0)
+
+
+def test_dense_split_covers_the_range_in_word_aligned_slices():
+    for n in (1, 3, 4, 5, 1000, 1_000_000, (1 << 29)):
+        for ws in (1, 2, 3, 8):
+            sl = [bdist.dense_split(n, r, ws) for r in range(ws)]
+            live = [(lo, hi) for lo, hi in sl if hi > lo]
+            assert live[0][0] == 0 and live[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(live, live[1:]))
+            assert all(lo % 4 == 0 and (hi % 4 == 0 or hi == n) for lo, hi in live)
+            assert all(s == (0, 0) for s in sl[len(live):])
+
+
+def _full_stack_groupby_job(rank, ws):
+    """The whole host stack under gloo with the numpy device double: sharded ingest, GroupByReduce template,
+    fused dense table + cross-rank merge by collectives (dense=True) or map -> range exchange -> reduce."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    out = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(20_011, 3, seed=42, nan_per_64k=3000, key_modulus=1237, key_seed=43)
+        pdf["key"] -= 600  # negative base
+        for dense in (True, False):
+            config.GroupbyDenseKeys.put(dense)
+            g = bpd.DataFrame(pdf).groupby("key")
+            for agg in ("sum", "count", "size", "mean", "min", "max"):
+                r = getattr(g, agg)()._query_compiler._modin_frame
+                blks = [p.get() for p in r._partitions[:, 0]]  # this rank's row partitions, in order
+                out[(dense, agg)] = (
+                    np.concatenate([b.index_cols[0].data.numpy() for b in blks]),
+                    np.concatenate([np.stack([c.data.numpy().astype(np.float64) for c in b.cols], axis=1) for b in blks]),
+                )
+    return out
+
+
+def test_full_stack_groupby_dense_and_exchange_paths_agree_with_the_oracle():
+    from oracle import reference_path as orc
+
+    out = _run(_full_stack_groupby_job)
+    pdf = synth.host_frame(20_011, 3, seed=42, nan_per_64k=3000, key_modulus=1237, key_seed=43)
+    pdf["key"] -= 600
+    for dense in (True, False):
+        for agg in ("sum", "count", "size", "mean", "min", "max"):
+            want = orc.groupby_reduce(pdf, "key", agg, 4)
+            keys = np.concatenate([o[(dense, agg)][0] for o in out])
+            vals = np.concatenate([o[(dense, agg)][1] for o in out])
+            assert np.array_equal(keys, want.index.to_numpy()), (dense, agg)  # rank order == key order
+            w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
+            assert np.allclose(vals, w, rtol=0, atol=1e-9, equal_nan=True), (dense, agg)
+            assert all(len(o[(dense, agg)][0]) > 0 for o in out)

@@ -41,6 +41,21 @@ def _four_partitions():
     config.NPartitions.put(old)
 
 
+@pytest.fixture(params=["dense", "dense_global_atomics", "hash"])
+def gb_table_kind(request):
+    """Run a groupby test with the direct-addressed table (narrow key range; small ranges are privatised in
+    shared memory), with the same table but global atomics only, and with the hash table."""
+    from modin_b200 import config
+
+    old = config.GroupbyDenseKeys.get()
+    config.GroupbyDenseKeys.put(request.param != "hash")
+    if request.param == "dense_global_atomics":
+        os.environ["MB200_GB_SMEM"] = "0"
+    yield request.param
+    os.environ.pop("MB200_GB_SMEM", None)
+    config.GroupbyDenseKeys.put(old)
+
+
 def _load(golden_dir, pattern):
     files = sorted(glob.glob(os.path.join(golden_dir, pattern)))
     assert files
@@ -131,7 +146,7 @@ def test_tree_reduce_vs_reference_golden(golden_dir):
         assert df.count().dtype == np.int64
 
 
-def test_groupby_vs_reference_golden(golden_dir):
+def test_groupby_vs_reference_golden(golden_dir, gb_table_kind):
     m = bpd()
     for name, z in _load(golden_dir, "groupby_*.npz"):
         n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
@@ -181,7 +196,7 @@ def test_against_oracle_various_shapes(n, W, nan):
     assert_exact(df.max().to_numpy(), orc.df_max(pdf, NPART).to_numpy(), "max")
 
 
-def test_groupby_min_max_bit_exact():
+def test_groupby_min_max_bit_exact(gb_table_kind):
     """storage_formats/pandas/groupby.py:237-248: min -> (min, min), max -> (max, max); no rounding involved."""
     m = bpd()
     pdf = synth.host_frame(30011, 3, seed=13, nan_per_64k=20000, key_modulus=977)
@@ -267,7 +282,7 @@ def test_edge_cases_and_errors():
         df.merge(df, how="outer", on="a")
 
 
-def test_groupby_with_empty_and_skewed_partitions():
+def test_groupby_with_empty_and_skewed_partitions(gb_table_kind):
     """cf. test_groupby_with_empty_partition (modin/tests/core/storage_formats/pandas/test_internals.py:863)."""
     m = bpd()
     n = 9001
@@ -280,7 +295,37 @@ def test_groupby_with_empty_and_skewed_partitions():
     assert_sum_close(got.to_numpy(), want.to_numpy(), pdf["v"].abs().groupby(pdf["key"]).sum().to_numpy()[:, None], n, "sum")
 
 
-def test_large_scale_invariants():
+def test_dense_and_hash_tables_agree_and_wide_keys_fall_back():
+    """The dense table is chosen from the measured key range; keys spread over a wide range must take the
+    hash table and give the same groups.  Counts / sizes / keys / min / max are bit-identical either way."""
+    from modin_b200 import config, ops
+
+    m = bpd()
+    n = 50021
+    base = synth.host_frame(n, 3, seed=21, nan_per_64k=9000, key_modulus=613)
+    wide = base.copy()
+    wide["key"] = (base["key"] - 300) * 1_000_003_019  # same grouping, range ~6e11: not dense-able
+    assert ops.dense_range_ok(0, 612, 1024, n, 3, 1) and not ops.dense_range_ok(int(wide["key"].min()), int(wide["key"].max()), 1 << 20, n, 3, 1)
+    res = {}
+    for kind, pdf in (("dense", base), ("hash", wide)):
+        g = m.DataFrame(pdf).groupby("key")
+        res[kind] = {a: getattr(g, a)()._to_pandas() for a in ("sum", "count", "size", "min", "max", "mean")}
+    want_keys = np.sort(base["key"].unique())
+    assert_exact(res["dense"]["sum"].index.to_numpy(), want_keys, "dense keys")
+    assert_exact(res["hash"]["sum"].index.to_numpy(), (want_keys - 300) * 1_000_003_019, "wide keys")
+    for a in ("count", "size", "min", "max"):
+        assert_exact(res["dense"][a].to_numpy(), res["hash"][a].to_numpy(), f"dense vs hash {a}")
+    abs_by_group = base.drop(columns="key").abs().groupby(base["key"]).sum().to_numpy()
+    assert_sum_close(res["dense"]["sum"].to_numpy(), res["hash"]["sum"].to_numpy(), abs_by_group, n, "dense vs hash sum")
+    # ops level: key range kernel, negative base, ragged lengths
+    for nn in (1, 15, 16, 17, 4099, 100000):
+        kk = synth.gen_i64(nn, 7, 0, 1000) - 500
+        from modin_b200.block import DeviceColumn
+        assert ops.key_range([DeviceColumn.from_numpy(kk)]) == (int(kk.min()), int(kk.max()))
+    assert config.GroupbyDenseKeys.get()
+
+
+def test_large_scale_invariants(gb_table_kind):
     """Properties that do not need a CPU pass over the data (SURVEY.md §8d "parity at scale")."""
     m = bpd()
     from modin_b200 import config

@@ -63,9 +63,18 @@ def test_frame_frame_ops_and_fusion(cpu_device):
         (A + short)._to_pandas()
 
 
-def test_groupby_and_merge_through_the_api(cpu_device):
+@pytest.mark.parametrize("dense", [True, False])
+def test_groupby_and_merge_through_the_api(cpu_device, dense):
     import modin_b200.pandas as bpd
 
+    config.GroupbyDenseKeys.put(dense)  # fused dense table vs map -> regroup; restored below
+    try:
+        _groupby_and_merge_checks(bpd)
+    finally:
+        config.GroupbyDenseKeys.put(True)
+
+
+def _groupby_and_merge_checks(bpd):
     pdf = synth.host_frame(5003, 3, seed=42, nan_per_64k=2000, key_modulus=41)
     df = bpd.DataFrame(pdf)
     g = df.groupby("key")

@@ -68,19 +68,27 @@ def main():
     cnt = np.maximum(orc.df_count(vals, NP).to_numpy(), 1)
     check("tree_reduce mean", close(dv.mean().to_numpy(), orc.df_mean(vals, NP).to_numpy(), abs_sum / cnt, n))
 
-    g = df.groupby("key")
-    want = orc.groupby_reduce(pdf, "key", "sum", NP)
-    got_local = g.sum()
-    check("groupby: every rank owns a non-empty key range", len(got_local) > 0)
-    got = got_local._to_pandas()  # gathers the per-rank key ranges in rank order
-    gabs = vals.abs().groupby(pdf["key"]).sum().to_numpy()
-    check("groupby keys globally sorted & complete", np.array_equal(got.index.to_numpy(), want.index.to_numpy()))
-    check("groupby sum", close(got.to_numpy(), want.to_numpy(), gabs, n))
-    check("groupby count", exact(g.count()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "count", NP).to_numpy()))
-    check("groupby size", exact(g.size()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "size", NP).to_numpy()))
-    gc = np.maximum(orc.groupby_reduce(pdf, "key", "count", NP).to_numpy(), 1)
-    check("groupby mean", close(g.mean()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "mean", NP).to_numpy(),
-                                gabs / gc, n))
+    from modin_b200 import config as _cfg
+
+    for dense, tag in ((True, "dense table + collectives"), (False, "hash tables + range exchange")):
+        _cfg.GroupbyDenseKeys.put(dense)
+        g = df.groupby("key")
+        want = orc.groupby_reduce(pdf, "key", "sum", NP)
+        got_local = g.sum()
+        check(f"[{tag}] groupby: every rank owns a non-empty key range", len(got_local) > 0)
+        got = got_local._to_pandas()  # gathers the per-rank key ranges in rank order
+        gabs = vals.abs().groupby(pdf["key"]).sum().to_numpy()
+        check(f"[{tag}] groupby keys globally sorted & complete", np.array_equal(got.index.to_numpy(), want.index.to_numpy()))
+        check(f"[{tag}] groupby sum", close(got.to_numpy(), want.to_numpy(), gabs, n))
+        check(f"[{tag}] groupby count", exact(g.count()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "count", NP).to_numpy()))
+        check(f"[{tag}] groupby size", exact(g.size()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "size", NP).to_numpy()))
+        gc = np.maximum(orc.groupby_reduce(pdf, "key", "count", NP).to_numpy(), 1)
+        check(f"[{tag}] groupby mean", close(g.mean()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "mean", NP).to_numpy(),
+                                    gabs / gc, n))
+        for agg in ("min", "max"):
+            check(f"[{tag}] groupby {agg}", exact(getattr(g, agg)()._to_pandas().to_numpy(),
+                                                 orc.groupby_reduce(pdf, "key", agg, NP).to_numpy()))
+    _cfg.GroupbyDenseKeys.put(True)
 
     rng = np.random.RandomState(5)
     dim_keys = rng.permutation(G).astype(np.int64)[: int(G * 0.9)]
