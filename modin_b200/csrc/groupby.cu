@@ -284,8 +284,9 @@ __device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool i
 __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t) {
   if (p.dense) {
     // direct addressing (kernel-uniform branch): no probe, no slots.  Presence is one BYTE per key (0 / 1)
-    // so that setting it is a plain idempotent store and ranks can merge maps with an NCCL MAX; the
-    // check reads L2 (a stale L1 line would make every later row of that line repeat the store).
+    // so that setting it is a plain idempotent store and ranks can merge maps with an NCCL MAX.  The
+    // check goes through L1: reading L2 instead made the few sectors of a small map a hot spot (G = 2500:
+    // 5.7 ms vs 3.4 ms per 2^27 rows); a stale 0 in L1 only repeats the store, which refreshes the line.
     const unsigned long long d = (unsigned long long)k - (unsigned long long)p.kbase;
     if (d >= (unsigned long long)p.gcap) {
       p.meta->overflow = 1;  // key outside the declared range
@@ -293,7 +294,7 @@ __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint6
     }
     unsigned char* w = reinterpret_cast<unsigned char*>(p.present) + d;
     unsigned int cur;
-    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(cur) : "l"(w) : "memory");
+    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(cur) : "l"(w) : "memory");
     if (!cur) asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(w), "r"(1u) : "memory");  // idempotent
     return (int)d;
   }
@@ -468,124 +469,122 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
 }
 
 // ---------------------------------------------------------------- low-cardinality keys: table in shared memory
-// Dense tables small enough for shared memory (R * vs * 8 B per accumulator array; R <= ~2600 at V = 8)
-// are PRIVATISED per CTA: rows are accumulated with shared-memory atomics and each CTA adds its table to
-// the global one once at the end.  With few distinct keys every row of the frame would otherwise hit the
-// same few L2 lines with global atomics (G = 10: ~1e8 serialised RED.ADD.F64 per line per 1e9 rows).
-// Same TMA-staged tile ring as gb_accumulate_tma_kernel; the tail / unaligned cases fall through to
-// gb_accumulate_kernel on the same global arrays.
+// Dense tables small enough for shared memory (R <= ~3100 at V = 8) are PRIVATISED per CTA: rows are
+// accumulated with shared-memory atomics and each CTA adds its table to the global one once at the end.
+// With few distinct keys every row of the frame would otherwise hit the same few L2 lines with global
+// atomics (measured, 2^27 rows, V = 8, G = 16: 68.9 ms with global REDs = 1.9 G rows/s).
+// One 1024-thread CTA per SM, the whole dynamic shared memory is the table; rows are loaded straight from
+// global memory (lane == row, every load a coalesced 256-byte warp access; 32 warps x 9 loads in flight
+// cover the HBM latency) and lane == row also for the atomics: table rows are padded to vs + 1 doubles so
+// that 32 different groups spread over the banks.  64-bit shared atomics are CAS loops on sm_100
+// (ATOMS.CAST.SPIN.64); per-CTA counts fit 32 bits and use the native ATOMS.ADD.
+constexpr int kSmemThreads = 1024;
+
 struct SmemTableLayout {
   unsigned int acc_off, cnt_off, size_off, present_off, total;
+  int svs;      // padded row stride of the shared-memory arrays (doubles)
+  int nrep;     // table replicas (power of two <= 32): lane l of every warp works on replica l & (nrep - 1)
+  int rstride;  // replica stride of acc / cnt in elements, = 1 (mod 16) so replicas sit in different banks
+  int zstride;  // replica stride of the size array (odd)
 };
 
-__global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_smem_kernel(const __grid_constant__ GbParams p,
-                                                                           long long ntiles,
-                                                                           const SmemTableLayout lay) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kGbStages * kStageBytes);
-  uint64_t* empty = full + kGbStages;
+__global__ void __launch_bounds__(kSmemThreads, 1) gb_accumulate_smem_kernel(const __grid_constant__ GbParams p,
+                                                                             const SmemTableLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_acc = reinterpret_cast<double*>(smem_raw + lay.acc_off);
   long long* s_acc_i = reinterpret_cast<long long*>(s_acc);
-  // per-CTA counts fit 32 bits (a CTA sees < 2^32 rows): native ATOMS.ADD instead of a 64-bit CAS loop
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(smem_raw + lay.cnt_off);
   unsigned int* s_size = reinterpret_cast<unsigned int*>(smem_raw + lay.size_off);
   unsigned char* s_present = smem_raw + lay.present_off;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nv = p.nvals, vs = p.vstride;
+  const int tid = threadIdx.x;
+  const int nv = p.nvals, vs = p.vstride, svs = lay.svs;
   const int R = (int)p.gcap;
+  const int nrep = lay.nrep, rstride = lay.rstride, zstride = lay.zstride;
   const bool f_sum = p.flags & MB200_GB_SUM, f_min = p.flags & MB200_GB_MIN, f_max = p.flags & MB200_GB_MAX;
   const bool f_cnt = p.flags & MB200_GB_COUNT, f_size = p.flags & MB200_GB_SIZE;
   const bool has_acc = f_sum || f_min || f_max;
-  const long long first = blockIdx.x;
-  const long long nmine = first < ntiles ? (ntiles - first + gridDim.x - 1) / gridDim.x : 0;
-
-  {
-    const long long init = f_min ? 0x7fffffffffffffffLL : (f_max ? (long long)0x8000000000000000ULL : 0LL);
-    for (int i = tid; i < R * vs; i += kGbTmaThreads) {
-      if (has_acc) s_acc_i[i] = init;
-      if (f_cnt) s_cnt[i] = 0u;
-    }
-    for (int i = tid; i < R; i += kGbTmaThreads) {
-      if (f_size) s_size[i] = 0u;
-      s_present[i] = 0;
-    }
+  const long long init = f_min ? 0x7fffffffffffffffLL : (f_max ? (long long)0x8000000000000000ULL : 0LL);
+  for (int i = tid; i < nrep * rstride; i += kSmemThreads) {
+    if (has_acc) s_acc_i[i] = init;
+    if (f_cnt) s_cnt[i] = 0u;
   }
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kGbStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kGbWarps);
-    }
-    mbar_fence_init();
-  }
+  if (f_size)
+    for (int i = tid; i < nrep * zstride; i += kSmemThreads) s_size[i] = 0u;
+  for (int i = tid; i < R; i += kSmemThreads) s_present[i] = 0;
   __syncthreads();
-
-  if (warp == kGbWarps) {
-    if (lane == 0) {  // producer: (1 + nv) bulk copies of 2 KiB per tile
-      const uint64_t pol = l2_policy_evict_first();
-      for (long long k = 0; k < nmine; ++k) {
-        const int s = (int)(k % kGbStages);
-        if (k >= kGbStages) mbar_wait(&empty[s], (uint32_t)(((k / kGbStages) - 1) & 1));
-        const long long row0 = (first + k * gridDim.x) * kTileRows;
-        double* stage = reinterpret_cast<double*>(smem_raw + (size_t)s * kStageBytes);
-        mbar_expect_tx(&full[s], (uint32_t)((1 + nv) * kTileRows * 8));
-        tma_bulk_g2s(stage, p.keys + row0, kTileRows * 8, &full[s], pol);
-        for (int c = 0; c < nv; ++c)
-          tma_bulk_g2s(stage + (size_t)(1 + c) * kTileColStride, static_cast<const double*>(p.vals[c]) + row0,
-                       kTileRows * 8, &full[s], pol);
-      }
-    }
-  } else {
-    const int c = lane & 7;
-    for (long long k = 0; k < nmine; ++k) {
-      const int s = (int)(k % kGbStages);
-      mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
-      const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
-      const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
-      const unsigned long long d = (unsigned long long)key - (unsigned long long)p.kbase;
-      const bool inr = d < (unsigned long long)R;
-      const int gid = inr ? (int)d : R;
-      if (inr) {
-        s_present[gid] = 1;
-        if (f_size) atomicAdd(&s_size[gid], 1u);
-      } else {
-        p.meta->overflow = 1;  // key outside the declared range
-      }
-      const double* vt = stage + kTileColStride + warp * 32;
+  const uint64_t pol = l2_policy_evict_first();
+  const int rep = tid & (nrep - 1);
+  const int rbase = rep * rstride;
+  const long long stride = (long long)gridDim.x * kSmemThreads;
+  for (long long row = (long long)blockIdx.x * kSmemThreads + tid; row < p.nrows; row += stride) {
+    const long long key = ldg_stream_i64(p.keys + row, pol);
+    double x[8];
+    {
+      const int nc = nv < 8 ? nv : 8;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const int r = 4 * kk + (lane >> 3);
-        const int g = __shfl_sync(0xffffffffu, gid, r);
-        if (c < nv && g < R) {
-          const double xv = vt[c * kTileColStride + r];
-          if (xv == xv) {
-            const int o = g * vs + c;
-            if (f_sum) atomicAdd(&s_acc[o], xv);
-            else if (f_min) atomicMin(&s_acc_i[o], f64_to_ordered(xv));
-            else if (f_max) atomicMax(&s_acc_i[o], f64_to_ordered(xv));
-            if (f_cnt) atomicAdd(&s_cnt[o], 1u);
-          }
+      for (int c = 0; c < 8; ++c)
+        x[c] = (c < nc) ? ldg_stream_f64(static_cast<const double*>(p.vals[c]) + row, pol) : 0.0;
+    }
+    const unsigned long long d = (unsigned long long)key - (unsigned long long)p.kbase;
+    if (d >= (unsigned long long)R) {
+      p.meta->overflow = 1;  // key outside the declared range
+      continue;
+    }
+    const int gid = (int)d;
+    if (!s_present[gid]) s_present[gid] = 1;
+    if (f_size) atomicAdd(&s_size[rep * zstride + gid], 1u);
+    for (int c0 = 0; c0 < nv; c0 += 8) {
+      const int nc = (nv - c0) < 8 ? (nv - c0) : 8;
+      if (c0 > 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          x[c] = (c < nc) ? ldg_stream_f64(static_cast<const double*>(p.vals[c0 + c]) + row, pol) : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < nc && x[c] == x[c]) {
+          const int o = rbase + gid * svs + c0 + c;
+          if (f_sum) atomicAdd(&s_acc[o], x[c]);
+          else if (f_min) atomicMin(&s_acc_i[o], f64_to_ordered(x[c]));
+          else if (f_max) atomicMax(&s_acc_i[o], f64_to_ordered(x[c]));
+          if (f_cnt) atomicAdd(&s_cnt[o], 1u);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
     }
   }
   __syncthreads();
-  // ---- add this CTA's table to the global one (coalesced over the [gid][column] arrays)
-  for (int i = tid; i < R * vs; i += kGbTmaThreads) {
+  // ---- fold the replicas and add this CTA's table to the global one (coalesced over the global [gid][vs] arrays)
+  for (int i = tid; i < R * vs; i += kSmemThreads) {
     const int g = i / vs, cc = i - g * vs;
     if (cc >= nv || !s_present[g]) continue;
-    if (f_sum) red_add_f64(p.acc + i, s_acc[i], 0);
-    else if (f_min && s_acc_i[i] != 0x7fffffffffffffffLL) red_min_s64(reinterpret_cast<long long*>(p.acc) + i, s_acc_i[i]);
-    else if (f_max && s_acc_i[i] != (long long)0x8000000000000000ULL)
-      red_max_s64(reinterpret_cast<long long*>(p.acc) + i, s_acc_i[i]);
-    if (f_cnt && s_cnt[i]) red_add_u64(p.cnt + i, (long long)s_cnt[i], 0);
+    const int o = g * svs + cc;
+    if (f_sum) {
+      double a = s_acc[o];
+      for (int r = 1; r < nrep; ++r) a += s_acc[r * rstride + o];
+      red_add_f64(p.acc + i, a, 0);
+    } else if (f_min || f_max) {
+      long long a = s_acc_i[o];
+      for (int r = 1; r < nrep; ++r) {
+        const long long b = s_acc_i[r * rstride + o];
+        a = f_min ? (b < a ? b : a) : (b > a ? b : a);
+      }
+      if (f_min && a != 0x7fffffffffffffffLL) red_min_s64(reinterpret_cast<long long*>(p.acc) + i, a);
+      if (f_max && a != (long long)0x8000000000000000ULL) red_max_s64(reinterpret_cast<long long*>(p.acc) + i, a);
+    }
+    if (f_cnt) {
+      long long n = 0;
+      for (int r = 0; r < nrep; ++r) n += s_cnt[r * rstride + o];
+      if (n) red_add_u64(p.cnt + i, n, 0);
+    }
   }
-  for (int g = tid; g < R; g += kGbTmaThreads) {
+  for (int g = tid; g < R; g += kSmemThreads) {
     if (!s_present[g]) continue;
     reinterpret_cast<unsigned char*>(p.present)[g] = 1;
-    if (f_size) red_add_u64(p.size + g, (long long)s_size[g], 0);
+    if (f_size) {
+      long long n = 0;
+      for (int r = 0; r < nrep; ++r) n += s_size[r * zstride + g];
+      red_add_u64(p.size + g, n, 0);
+    }
   }
 }
 
@@ -949,41 +948,41 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   }
 
   // low-cardinality dense tables: privatise the table in shared memory (MB200_GB_SMEM=0 disables)
-  bool smem_done = false;
-  if (t->dense && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
+  if (t->dense && !partial) {
     const char* e = getenv("MB200_GB_SMEM");
-    const size_t arr = (size_t)t->gcap * t->vstride * 8;
     SmemTableLayout lay;
-    size_t off = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
-    off = (off + 15) & ~(size_t)15;
-    lay.acc_off = (unsigned)off;
-    if (t->flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX)) off += arr;
-    lay.cnt_off = (unsigned)off;
-    if (t->flags & MB200_GB_COUNT) off += arr / 2;  // 32-bit per-CTA counters
-    lay.size_off = (unsigned)off;
-    if (t->flags & MB200_GB_SIZE) off += (((size_t)t->gcap * 4) + 15) & ~(size_t)15;
-    lay.present_off = (unsigned)off;
-    off += ((size_t)t->gcap + 15) & ~(size_t)15;
-    lay.total = (unsigned)off;
+    lay.svs = t->vstride + 1;
+    lay.rstride = (int)((((size_t)t->gcap * lay.svs + 15) & ~(size_t)15) + 1);
+    lay.zstride = (int)(t->gcap | 1);
+    size_t off = 0;
+    // as many replicas as fit (conflicting lanes of a warp then work on different copies: G = 16 runs
+    // 2.6x faster with 32 replicas than with one)
+    for (int nrep = 32; nrep >= 1; nrep >>= 1) {
+      const size_t elems = (size_t)nrep * lay.rstride;
+      off = 0;
+      lay.nrep = nrep;
+      lay.acc_off = (unsigned)off;
+      if (t->flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX)) off += elems * 8;
+      lay.cnt_off = (unsigned)off;
+      if (t->flags & MB200_GB_COUNT) off += (elems * 4 + 15) & ~(size_t)15;
+      lay.size_off = (unsigned)off;
+      if (t->flags & MB200_GB_SIZE) off += (((size_t)nrep * lay.zstride * 4) + 15) & ~(size_t)15;
+      lay.present_off = (unsigned)off;
+      off += ((size_t)t->gcap + 15) & ~(size_t)15;
+      lay.total = (unsigned)off;
+      if (off <= dp.smem_optin) break;
+    }
     if (!(e && e[0] == '0') && off <= dp.smem_optin) {
-      const long long ntiles = nrows / kTileRows;
       MB_CUDA(cudaFuncSetAttribute(gb_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
-      int occ = 0;
-      MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_smem_kernel, kGbTmaThreads, off));
-      long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
-      if (grid > ntiles) grid = ntiles;
-      gb_accumulate_smem_kernel<<<(unsigned)grid, kGbTmaThreads, off, st>>>(p, ntiles, lay);
+      long long grid = dp.sm_count;
+      const long long need = (nrows + kSmemThreads - 1) / kSmemThreads;
+      if (grid > need) grid = need;
+      gb_accumulate_smem_kernel<<<(unsigned)grid, kSmemThreads, off, st>>>(p, lay);
       MB_LAUNCH_CHECK("gb_accumulate_smem_kernel");
-      const long long done = ntiles * kTileRows;
-      if (done == nrows) return 0;
-      p.keys = keys + done;
-      for (int c = 0; c < t->nvals; ++c)
-        if (p.vals[c]) p.vals[c] = static_cast<const double*>(p.vals[c]) + done;
-      p.nrows = nrows - done;
-      smem_done = true;
+      return 0;
     }
   }
-  if (!smem_done && variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
+  if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
     const size_t smem = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
     MB_CUDA(cudaFuncSetAttribute(gb_accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

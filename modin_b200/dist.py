@@ -99,6 +99,19 @@ def all_reduce_inplace(tensor, op: str) -> None:
         d.all_reduce(tensor, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
 
 
+def all_gather_small(values, extra: int | None = None):
+    """all_gather of a short int64 device vector (+ one host integer appended) -> list of per-rank
+    Python int lists.  One collective and one D2H for the handful of scalars a decision needs."""
+    t = _torch()
+    d = _dist()
+    v = values.reshape(-1)
+    if extra is not None:
+        v = t.cat([v, t.tensor([int(extra)], dtype=v.dtype, device=v.device)])
+    out = t.empty(world_size() * v.numel(), dtype=v.dtype, device=v.device)
+    d.all_gather_into_tensor(out, v.contiguous())
+    return out.reshape(world_size(), v.numel()).tolist()
+
+
 def dense_split(nkeys: int, r: int | None = None, ws: int | None = None):
     """Slice [lo, hi) of a dense key range [0, nkeys) that rank r emits: equal chunks rounded up to a
     multiple of 4 (the presence map is scanned in 4-byte words); trailing ranks may get (0, 0)."""

@@ -587,13 +587,14 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
         items.append((key, vals))
     if len(labels) > _lib_max_cols():
         return None
-    t = ops.torch_mod()
     mm = ops.key_range_device([k for k, _ in items])
-    rows = t.tensor([sum(len(k) for k, _ in items)], dtype=t.int64, device=mm.device)
+    total_rows = sum(len(k) for k, _ in items)
     if dist.is_distributed():
-        dist.all_reduce_values([mm[0:1], mm[1:2], rows], ["min", "max", "sum"])
-    lo, hi = (int(v) for v in mm.tolist())
-    total_rows = int(rows.item())
+        # one small all_gather ([min, max, rows] per rank) + one D2H instead of three all_reduces
+        trip = dist.all_gather_small(mm, extra=total_rows)
+        lo, hi, total_rows = min(r[0] for r in trip), max(r[1] for r in trip), sum(r[2] for r in trip)
+    else:
+        lo, hi = (int(v) for v in mm.tolist())
     if lo > hi:
         return None  # no rows anywhere
     cap = max(1024, min(map_fn.capacity_hint, total_rows))
