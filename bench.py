@@ -302,9 +302,31 @@ def run_b200_arm(args):
                      "roofline": {"bound": "hbm", "kernel": "reduce_tma_kernel<SUM,f64>", "achieved": ach,
                                   "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                   "traffic": traffic_for("reduce_sum", rows_local)}})  # fmt: skip
-        # ---- GroupByReduce: groupby('key').sum(), G = 1e6 int64 keys, 8 float64 values (C4)
+        # ---- Binary template on three frames: a*b+c with b, c frames (C2 secondary form; 256 B/row fused).
+        # Four n x 8 frames are resident, so n = rows/4 (2.5e8 per 1e9: 64 GB on one GPU)
         del a
         torch.cuda.empty_cache()
+        rows3 = max(rows // 4, 1024)
+        fa, fb, fc = (synth.device_frame(rows3, W, seed=s, npartitions=1) for s in (42, 44, 45))
+        for f in (fa, fb, fc):
+            f.execute()
+
+        def step_fma3():
+            out = fa * fb + fc  # two n_ary_op calls -> call queue -> one FMA3 sweep (two roundings)
+            out.execute()
+            del out
+
+        fsteps = max(3, args.steps // 2)
+        total_f, per_f = timed(step_fma3, fsteps, 2)
+        ms_f = total_f / fsteps
+        ach = (rows3 // ws) * W * 32 / (statistics.mean(per_f) / 1e3) / 1e9
+        also.append({"metric": f"rows/sec a*b+c on three frames ({rows3}x8 f64 each), Binary template x2 fused",
+                     "value": rows3 / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f,
+                     "roofline": {"bound": "hbm", "kernel": "map_kernel<FMA3,f64>", "achieved": ach, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None}})  # fmt: skip
+        del fa, fb, fc
+        torch.cuda.empty_cache()
+        # ---- GroupByReduce: groupby('key').sum(), G = 1e6 int64 keys, 8 float64 values (C4)
         g = synth.device_frame(rows, W, seed=42, key_modulus=args.groups, npartitions=1)
         g.execute()
         ngroups = [0]

@@ -126,8 +126,11 @@ struct GbParams {
 // ---- table accesses: relaxed GPU-scope.  L2 eviction-priority hints on these (evict_last / evict_normal
 // via createpolicy + .L2::cache_hint) were measured to make no difference at any table size
 // (gpurun_out/gb_probe.log), so the plain forms are used; `pol` is kept in the signatures for experiments.
-__device__ __forceinline__ void red_add_f64(double* p, double v, uint64_t) {
-  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+__device__ __forceinline__ void red_add_f64(double* p, double v, uint64_t pol) {
+  if (pol)  // experiment (MB200_GB_POLICY): explicit L2 eviction priority on the accumulator updates
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+  else
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_u64(long long* p, long long v, uint64_t) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -143,7 +146,13 @@ __device__ __forceinline__ void st_slot(Slot* s, long long key, int gid, uint64_
   asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(s), "l"((unsigned long long)key), "l"(b)
                : "memory");
 }
-__device__ __forceinline__ uint64_t table_policy(int) { return 0; }
+__device__ __forceinline__ uint64_t table_policy(int mode) {
+  uint64_t pol = 0;
+  if (mode == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if (mode == 2) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  if (mode == 3) asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 
 // min / max accumulators share the `acc` array: doubles are stored through an order-preserving map to
 // int64 (flip the magnitude bits of negatives) so that RED.MIN.S64 / RED.MAX.S64 order them like
@@ -167,6 +176,17 @@ __device__ __forceinline__ void acc_update(const GbParams& p, size_t o, double x
   if (p.flags & MB200_GB_SUM) red_add_f64(p.acc + o, xv, keep);
   else if (p.flags & MB200_GB_MIN) red_min_s64(reinterpret_cast<long long*>(p.acc) + o, f64_to_ordered(xv));
   else if (p.flags & MB200_GB_MAX) red_max_s64(reinterpret_cast<long long*>(p.acc) + o, f64_to_ordered(xv));
+}
+
+// does adding / min-ing / max-ing / counting `xv` leave a trace in a DENSE table's accumulators?
+__device__ __forceinline__ bool dense_visible(const GbParams& p, double xv) {
+  if (xv != xv) return false;                                                   // NaNs are skipped everywhere
+  if (p.flags & (MB200_GB_COUNT | MB200_GB_MIN | MB200_GB_MAX)) return true;  // cnt > 0 / acc != sentinel
+  return __double_as_longlong(xv) != (long long)0x8000000000000000ULL;          // -0.0 + -0.0 stays -0.0
+}
+__device__ __forceinline__ void dense_mark(const GbParams& p, int g) {
+  asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(reinterpret_cast<unsigned char*>(p.present) + g), "r"(1u)
+               : "memory");
 }
 
 // Probing works on BUCKETS of two slots = one 32-byte sector, fetched with one 256-bit load: a probe
@@ -283,19 +303,16 @@ __device__ __noinline__ int insert_rounds(const GbParams& p, long long k, bool i
 // Dense group id of every lane's key (gcap = table overflowed).  Must be called by all 32 lanes.
 __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint64_t) {
   if (p.dense) {
-    // direct addressing (kernel-uniform branch): no probe, no slots.  Presence is one BYTE per key (0 / 1)
-    // so that setting it is a plain idempotent store and ranks can merge maps with an NCCL MAX.  The
-    // check goes through L1: reading L2 instead made the few sectors of a small map a hot spot (G = 2500:
-    // 5.7 ms vs 3.4 ms per 2^27 rows); a stale 0 in L1 only repeats the store, which refreshes the line.
+    // direct addressing (kernel-uniform branch): no probe, no slots, and normally no presence access either:
+    // dense accumulators start from a value no update can leave behind (-0.0 for sums, the "no value yet"
+    // sentinels for min / max, 0 for counts / sizes), so a key is present iff its row changed -- only a row
+    // that changes nothing (all values NaN or -0.0, no size) marks the presence byte (mark_if_invisible).
+    // A per-row presence check cost as many L1 tag lookups as all the REDs of the row together.
     const unsigned long long d = (unsigned long long)k - (unsigned long long)p.kbase;
     if (d >= (unsigned long long)p.gcap) {
       p.meta->overflow = 1;  // key outside the declared range
       return (int)p.gcap;
     }
-    unsigned char* w = reinterpret_cast<unsigned char*>(p.present) + d;
-    unsigned int cur;
-    asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(cur) : "l"(w) : "memory");
-    if (!cur) asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(w), "r"(1u) : "memory");  // idempotent
     return (int)d;
   }
   const int lane = threadIdx.x & 31;
@@ -341,6 +358,7 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
     const bool live = valid && gid < gcap;
 
     if ((p.flags & MB200_GB_SIZE) && live) red_add_u64(p.size + gid, PARTIAL ? p.psize[row] : 1LL, keep);
+    if (p.dense && p.nvals == 0 && !(p.flags & MB200_GB_SIZE) && live) dense_mark(p, gid);  // keys only
     // ---- accumulate, 8 value columns at a time
     for (int c0 = 0; c0 < p.nvals; c0 += 8) {
       const int nc = (p.nvals - c0) < 8 ? (p.nvals - c0) : 8;
@@ -350,10 +368,12 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
           x[c] = (c < nc && valid) ? ldg_stream_f64(static_cast<const double*>(p.vals[c0 + c]) + row, pol) : 0.0;
       }
       if (VARIANT == 1) {  // lane == row (kept for measurement)
+        bool rowvis = false;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           if (c < nc && live) {
             const size_t o = (size_t)gid * p.vstride + c0 + c;
+            rowvis = rowvis || (!PARTIAL && dense_visible(p, x[c]));
             if (x[c] == x[c]) acc_update(p, o, x[c], keep);
             if (p.flags & MB200_GB_COUNT) {
               if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[row], keep);
@@ -361,25 +381,42 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
             }
           }
         }
+        if (p.dense && !(p.flags & MB200_GB_SIZE) && live && !rowvis) dense_mark(p, gid);
       } else {
         double* tile = s_tile[warp];
 #pragma unroll
         for (int c = 0; c < 8; ++c) tile[c * kColStride + lane] = x[c];
         __syncwarp();
         const int c = lane & 7;
+        unsigned int seen = 0, rowok = 0;
+        int gs[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const int r = 4 * kk + (lane >> 3);
           const int g = __shfl_sync(0xffffffffu, gid, r);
           const double xv = tile[c * kColStride + r];
           const bool ok = (base + r < p.nrows) && (c < nc) && (g < gcap);
+          gs[kk] = g;
+          if ((base + r < p.nrows) && g < gcap) rowok |= 1u << kk;
           if (ok) {
             const size_t o = (size_t)g * p.vstride + c0 + c;
+            if (!PARTIAL && dense_visible(p, xv)) seen |= 1u << kk;
             if (xv == xv) acc_update(p, o, xv, keep);
             if (p.flags & MB200_GB_COUNT) {
               if (PARTIAL) red_add_u64(p.cnt + o, static_cast<const long long*>(p.pcnt[c0 + c])[base + r], keep);
               else if (xv == xv) red_add_u64(p.cnt + o, 1LL, keep);
             }
+          }
+        }
+        if (p.dense && !(p.flags & MB200_GB_SIZE)) {  // rows that left no trace mark their presence byte
+          seen |= __shfl_xor_sync(0xffffffffu, seen, 1);
+          seen |= __shfl_xor_sync(0xffffffffu, seen, 2);
+          seen |= __shfl_xor_sync(0xffffffffu, seen, 4);
+          const unsigned int unseen = ~seen & rowok;
+          if (c == 0 && unseen) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              if ((unseen >> kk) & 1u) dense_mark(p, gs[kk]);
           }
         }
         __syncwarp();
@@ -450,17 +487,34 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     const int gid = resolve_gid(p, key, keep);
     if ((p.flags & MB200_GB_SIZE) && gid < gcap) red_add_u64(p.size + gid, 1LL, keep);
     const double* vt = stage + kTileColStride + warp * 32;  // value column 0, this warp's rows
+    unsigned int seen = 0;  // bit kk: this lane's (row 4 kk + lane / 8, column c) update leaves a trace
+    int gs[8];
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int r = 4 * kk + (lane >> 3);
       const int g = __shfl_sync(0xffffffffu, gid, r);
+      gs[kk] = g;
       if (c < nv && g < gcap) {
         const double xv = vt[c * kTileColStride + r];
         const size_t o = (size_t)g * p.vstride + c;
+        if (dense_visible(p, xv)) seen |= 1u << kk;
         if (xv == xv) {
           acc_update(p, o, xv, keep);
           if (p.flags & MB200_GB_COUNT) red_add_u64(p.cnt + o, 1LL, keep);
         }
+      }
+    }
+    if (p.dense && !(p.flags & MB200_GB_SIZE)) {
+      // rows none of whose 8 columns left a trace mark their presence byte (rare).  OR over the 8 lanes of a
+      // row with three shuffles AFTER the REDs: a vote per row inside the loop serialised the tile reads.
+      seen |= __shfl_xor_sync(0xffffffffu, seen, 1);
+      seen |= __shfl_xor_sync(0xffffffffu, seen, 2);
+      seen |= __shfl_xor_sync(0xffffffffu, seen, 4);
+      unsigned int unseen = ~seen & 0xffu;
+      if (c == 0 && unseen) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (((unseen >> kk) & 1u) && gs[kk] < gcap) dense_mark(p, gs[kk]);
       }
     }
     __syncwarp();
@@ -678,6 +732,8 @@ __global__ void gb_emit_kernel(const __grid_constant__ EmitParams p) {
         const long long o = __double_as_longlong(val);
         const bool empty = (p.flags & MB200_GB_MIN) ? (o == 0x7fffffffffffffffLL) : (o == (long long)0x8000000000000000ULL);
         val = empty ? __longlong_as_double(0x7ff8000000000000LL) : ordered_to_f64(o);
+      } else {
+        val = val + 0.0;  // dense sums start from -0.0 (the "untouched" mark): an empty sum is +0.0 as in pandas
       }
       static_cast<double*>(p.out_sums[v])[i] = val;
     }
@@ -746,6 +802,23 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
 __global__ void key_range_init_kernel(long long* minmax) {
   minmax[0] = 0x7fffffffffffffffLL;
   minmax[1] = (long long)0x8000000000000000ULL;
+}
+
+// presence of a dense key = its byte was marked (rows that changed nothing) OR its accumulators moved
+// away from their initial values.  Run before counting; idempotent.
+__global__ void __launch_bounds__(256) dense_presence_kernel(unsigned char* __restrict__ present,
+                                                             const long long* __restrict__ acc,
+                                                             const long long* __restrict__ cnt,
+                                                             const long long* __restrict__ size, long long g0,
+                                                             long long g1, int nvals, int vstride, long long acc_init) {
+  const long long g = g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= g1 || present[g]) return;
+  bool seen = size && size[g] != 0;
+  for (int v = 0; v < nvals && !seen; ++v) {
+    if (acc && acc[g * vstride + v] != acc_init) seen = true;
+    if (cnt && cnt[g * vstride + v] != 0) seen = true;
+  }
+  if (seen) present[g] = 1;
 }
 
 // block b counts the set bits of presence words [256 b, 256 b + 256)
@@ -893,7 +966,7 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   p.nrows = nrows;
   {
     const char* e = getenv("MB200_GB_POLICY");  // none | last | normal
-    p.policy_mode = (e && e[0] == 'l') ? 1 : ((e && e[0] == 'n' && e[1] == 'o' && e[2] == 'r') ? 2 : 0);
+    p.policy_mode = (e && e[0] == 'l') ? 1 : ((e && e[0] == 'n' && e[1] == 'o' && e[2] == 'r') ? 2 : ((e && e[0] == 'u') ? 3 : 0));
     const char* pf = getenv("MB200_GB_PREFETCH");
     p.prefetch = (pf && pf[0] == '1') ? 1 : 0;  // measured: no gain (the limiter is random-sector DRAM traffic)
   }
@@ -920,8 +993,8 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   } guard{st};
   {
     const char* e = getenv("MB200_GB_PERSIST");
-    const bool want = (e && e[0] == '1');
-    if (want && t->acc && table_bytes * 2 > dp.l2_bytes) {
+    const bool want = (e && (e[0] == '1' || e[0] == '2'));
+    if (want && t->acc && (table_bytes * 2 > dp.l2_bytes || e[0] == '2')) {
       int dev = 0, max_persist = 0, max_window = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
@@ -1122,7 +1195,14 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
   MB_TRY(cudaMallocAsync((void**)&t->meta, sizeof(GbMeta), st));
   if (flags & MB200_GB_SUM) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
-    MB_TRY(cudaMemsetAsync(t->acc, 0, accb, st));
+    if (dense) {  // -0.0: the one value no sum can end on (x + -0.0 = x, and sums start from +0.0 in the emit)
+      gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
+                                                               (long long)(accb / 8), (long long)0x8000000000000000ULL);
+      MB_TRY(cudaGetLastError());
+      g_launches.fetch_add(1);
+    } else {
+      MB_TRY(cudaMemsetAsync(t->acc, 0, accb, st));
+    }
   } else if (flags & (MB200_GB_MIN | MB200_GB_MAX)) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     // "no value yet": INT64_MAX = bytes ff..ff 7f for min is not a byte pattern; use the fill kernel
@@ -1197,9 +1277,23 @@ extern "C" int mb200_gb_merge_partial(mb200_gb_table* t, const int64_t* keys, co
                    npartial, true, (cudaStream_t)stream);
 }
 
+static int dense_finalize_presence(mb200_gb_table* t, cudaStream_t st) {
+  const long long n = t->win_hi - t->win_lo;
+  if (n <= 0) return 0;
+  const long long init = (t->flags & MB200_GB_SUM)   ? (long long)0x8000000000000000ULL
+                         : (t->flags & MB200_GB_MIN) ? 0x7fffffffffffffffLL
+                                                     : (long long)0x8000000000000000ULL;
+  dense_presence_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<unsigned char*>(t->present), reinterpret_cast<const long long*>(t->acc), t->cnt, t->size,
+      t->win_lo, t->win_hi, t->nvals, t->vstride, init);
+  MB_LAUNCH_CHECK("dense_presence_kernel");
+  return 0;
+}
+
 extern "C" int mb200_gb_ngroups(mb200_gb_table* t, int64_t* ngroups, int* overflow, mb200_stream_t stream) {
   if (!t) return fail("mb200_gb_ngroups", "null table");
   if (t->dense) {  // count the presence bytes of the window
+    if (int rc = dense_finalize_presence(t, (cudaStream_t)stream)) return rc;
     const long long w0 = t->win_lo / 4, nw = (t->win_hi - t->win_lo + 3) / 4;
     const long long nblocks = nw > 0 ? (nw + 255) / 256 : 1;
     dense_count_kernel<<<(unsigned)nblocks, 256, 0, (cudaStream_t)stream>>>(t->present + w0, nw, t->blockoff);
@@ -1241,6 +1335,7 @@ extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64
   if (t->dense) {
     // presence bits -> (key, gid) lists, already in ascending key order: no collect, no sort, and no host
     // round trip (mb200_gb_ngroups reported the overflow flag when the caller sized the outputs)
+    if (int rc = dense_finalize_presence(t, st)) return rc;
     const long long w0 = t->win_lo / 4, nw = (t->win_hi - t->win_lo + 3) / 4;
     const long long nblocks = nw > 0 ? (nw + 255) / 256 : 1;
     dense_count_kernel<<<(unsigned)nblocks, 256, 0, st>>>(t->present + w0, nw, t->blockoff);

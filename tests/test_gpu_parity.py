@@ -295,6 +295,31 @@ def test_groupby_with_empty_and_skewed_partitions(gb_table_kind):
     assert_sum_close(got.to_numpy(), want.to_numpy(), pdf["v"].abs().groupby(pdf["key"]).sum().to_numpy()[:, None], n, "sum")
 
 
+def test_groups_whose_rows_leave_no_trace_are_still_groups(gb_table_kind):
+    """Dense tables infer presence from the accumulators; rows that change nothing (all values NaN or -0.0)
+    must still create their group: sum 0.0 / count 0 / min, max NaN (or -0.0) exactly as pandas."""
+    m = bpd()
+    n = 4096 + 37
+    pdf = synth.host_frame(n, 3, seed=17, nan_per_64k=3000, key_modulus=10)
+    pdf.loc[pdf["key"] == 3, ["c0", "c1", "c2"]] = np.nan
+    pdf.loc[pdf["key"] == 5, ["c0", "c1", "c2"]] = -0.0
+    pdf.loc[pdf["key"] == 7, ["c0", "c2"]] = np.nan
+    pdf.loc[pdf["key"] == 7, "c1"] = -0.0
+    pdf["key"] = pdf["key"] * 3 - 9  # gaps in the range: absent keys must stay absent
+    g = m.DataFrame(pdf).groupby("key")
+    for agg in ("sum", "count", "size", "min", "max", "mean"):
+        got = getattr(g, agg)()._to_pandas()
+        want = orc.groupby_reduce(pdf, "key", agg, 4)
+        assert_exact(got.index.to_numpy(), want.index.to_numpy(), f"{agg} keys")
+        w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
+        gt = got.to_numpy(dtype=np.float64).reshape(len(got), -1)
+        if agg in ("sum", "mean"):
+            assert np.allclose(gt, w, rtol=0, atol=1e-9, equal_nan=True), agg
+            assert not np.signbit(gt[np.isin(want.index.to_numpy(), [0, 6, 12])]).any() or agg == "mean"
+        else:
+            assert_exact(gt, w, f"groupby {agg}")
+
+
 def test_dense_and_hash_tables_agree_and_wide_keys_fall_back():
     """The dense table is chosen from the measured key range; keys spread over a wide range must take the
     hash table and give the same groups.  Counts / sizes / keys / min / max are bit-identical either way."""

@@ -41,7 +41,9 @@ def main():
     cp = _lib.ptr_array([c.data_ptr() for c in cols])
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     mm = torch.empty(2, dtype=torch.int64, device=dev)
-    for G in (16, 256, 1024, 3000, 4000, 16384, 65_536):
+    Gs = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (16, 256, 1024, 3000, 4000, 16384, 65_536, 1_000_000)
+    kinds = sys.argv[3].split(',') if len(sys.argv) > 3 else ("hash", "dense", "dense_nosmem")
+    for G in Gs:
         _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, G, st))
 
         def krange():
@@ -52,7 +54,7 @@ def main():
         assert (lo, hi) == (0, G - 1), (lo, hi)
         for variant in ("0",):
             os.environ["MB200_GB_VARIANT"] = variant
-            for kind in ("hash", "dense", "dense_nosmem"):
+            for kind in kinds:
                 os.environ["MB200_GB_SMEM"] = "0" if kind == "dense_nosmem" else "1"
 
                 def cold():
