@@ -381,18 +381,28 @@ def run_b200_arm(args):
             del r
 
         msteps = max(3, args.steps // 2)
-        total_m, per_m = timed(step_merge, msteps, 2)
-        ms_m = total_m / msteps
         moved = rows_local * 16  # 8 B key read + 8 B payload written per fact row; fact columns are shared, not copied
-        ach = moved / (statistics.mean(per_m) / 1e3) / 1e9
-        also.append({"metric": f"rows/sec fact.merge(dim, on='key', how='left'), {rows} fact rows x {ndim} dim rows",
-                     "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "rows_out_local": nout[0],
-                     "roofline": {"bound": "hbm", "kernel": "join_build + join_probe_gather (fused probe + payload gather)",
-                                  "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                  "traffic": None,
-                                  "note": "algorithmic bytes here = 16 B/row (key read + payload written); the "
-                                          "reference materialises the whole 152 B/row output, this backend shares "
-                                          "the fact columns by reference"}})  # fmt: skip
+        # default: the dim keys span [0, ndim) so the build picks the direct-addressed table; then the hash table forced
+        for dense_on, label, kern in (
+            (True, "", "join_dense_build + join_dense_probe (direct-addressed dim table, fused payload gather)"),
+            (False, " [hash table forced]", "join_build + join_probe_gather (open-addressed hash table)"),
+        ):
+            if dense_on:
+                os.environ.pop("MB200_JOIN_DENSE", None)
+            else:
+                os.environ["MB200_JOIN_DENSE"] = "0"
+            total_m, per_m = timed(step_merge, msteps, 2)
+            ms_m = total_m / msteps
+            ach = moved / (statistics.mean(per_m) / 1e3) / 1e9
+            also.append({"metric": f"rows/sec fact.merge(dim, on='key', how='left'), {rows} fact rows x {ndim} dim rows{label}",
+                         "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "rows_out_local": nout[0],
+                         "roofline": {"bound": "hbm", "kernel": kern,
+                                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                      "traffic": None,
+                                      "note": "algorithmic bytes here = 16 B/row (key read + payload written); the "
+                                              "reference materialises the whole 152 B/row output, this backend shares "
+                                              "the fact columns by reference"}})  # fmt: skip
+        os.environ.pop("MB200_JOIN_DENSE", None)
         del fact, dim
         torch.cuda.empty_cache()
     else:

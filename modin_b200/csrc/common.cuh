@@ -42,6 +42,10 @@ struct DevProps {
 };
 // cached per-device properties; returns non-zero (error set) if no usable sm_100 device.
 int dev_props(DevProps* out);
+// Reference-counted persisting-L2 carve-out (runtime.cu): acquire returns the carve-out size in bytes (0 =
+// unsupported) and the largest access-policy window; the last release hands the whole L2 back.
+size_t l2_carveout_acquire(size_t* max_window_bytes);
+void l2_carveout_release();
 
 // ---------------------------------------------------------------- streaming loads/stores
 // 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a).  Streaming data is read

@@ -84,6 +84,8 @@ struct mb200_gb_table {
   long long nwords;
   unsigned int* blockoff;  // [nwords / 256 + 1] per-block popcounts -> exclusive offsets (emit)
   int borrowed;            // acc / cnt / size / present belong to the caller
+  int persisted;           // holds a reference on the persisting L2 carve-out (accumulators pinned)
+  size_t carve_bytes, window_bytes;
   long long win_lo, win_hi;  // gid window that ngroups / emit report (default: the whole range)
 };
 
@@ -975,11 +977,15 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
                                                                    ((t->flags & MB200_GB_COUNT) ? 1 : 0));
   const int variant = gb_variant_from_env(table_bytes, dp.l2_bytes);
 
-  // Tables that do not fit the normally-managed L2 next to the stream: pin the accumulator rows (the
-  // 2-sector RED target of every row) in the persisting L2 carve-out for the kernels launched below.
-  // Opt-in (MB200_GB_PERSIST=1): measured on B200 (82.9 MB max carve-out) it changes nothing at G = 1e6
-  // (4.30 ms with and without per 2^27 rows), gains ~12 % at G = 2e6, and the process-wide carve-out
-  // slows every other kernel that wants the whole L2 -- so it is off by default.
+  // Pin the accumulator rows (the 2-sector RED target of every row) in the persisting L2 carve-out for the
+  // kernels launched below (B200: 82.9 MB max carve-out).
+  //  * DENSE tables (default on for acc >= 8 MiB, MB200_GB_PERSIST=0 disables): the accumulators ARE the whole
+  //    table, and ncu shows what the window buys at G = 1e6 (64 MB of sums, 2^27 rows): DRAM traffic
+  //    10.37 GB read + 1.82 GB written -> 9.73 GB + 5.5 MB, 2.69 -> 2.26 ms -- the same speed as a 4 MB
+  //    table.  (An evict_last hint on the REDs alone: 2.46 ms.)  The carve-out is released when the table
+  //    is destroyed (l2_carveout_release) so later kernels get the whole L2 back.
+  //  * HASH tables (opt-in, MB200_GB_PERSIST=1): the probe slots (32 MB at G = 1e6) do not fit next to the
+  //    sums, and pinning the sums alone changed nothing (4.30 ms with and without); ~12 % at G = 2e6.
   struct WindowGuard {
     cudaStream_t st;
     bool on = false;
@@ -993,24 +999,26 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   } guard{st};
   {
     const char* e = getenv("MB200_GB_PERSIST");
-    const bool want = (e && (e[0] == '1' || e[0] == '2'));
-    if (want && t->acc && (table_bytes * 2 > dp.l2_bytes || e[0] == '2')) {
-      int dev = 0, max_persist = 0, max_window = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-      const size_t accb = (size_t)t->gcap * t->vstride * 8;
-      if (max_persist > 0 && max_window > 0) {
-        static size_t configured = 0;
-        if (configured != (size_t)max_persist) {
-          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-          configured = (size_t)max_persist;
+    const size_t acc_bytes = (size_t)t->gcap * t->vstride * 8;
+    const bool forced = e && e[0] == '2';
+    const bool want = t->dense ? (!(e && e[0] == '0') && (acc_bytes >= ((size_t)8 << 20) || forced))
+                               : ((e && e[0] == '1' && table_bytes * 2 > dp.l2_bytes) || forced);
+    if (want && t->acc) {
+      if (!t->persisted) {  // one carve-out reference per table, dropped in mb200_gb_destroy
+        size_t mw = 0;
+        const size_t mp = l2_carveout_acquire(&mw);
+        if (mp) {
+          t->persisted = 1;
+          t->carve_bytes = mp;
+          t->window_bytes = mw;
         }
+      }
+      if (t->persisted) {
         cudaStreamAttrValue v;
         memset(&v, 0, sizeof(v));
         v.accessPolicyWindow.base_ptr = t->acc;
-        v.accessPolicyWindow.num_bytes = accb < (size_t)max_window ? accb : (size_t)max_window;
-        const double fit = (double)max_persist / (double)v.accessPolicyWindow.num_bytes;
+        v.accessPolicyWindow.num_bytes = acc_bytes < t->window_bytes ? acc_bytes : t->window_bytes;
+        const double fit = (double)t->carve_bytes / (double)v.accessPolicyWindow.num_bytes;
         v.accessPolicyWindow.hitRatio = fit >= 1.0 ? 1.0f : (float)fit;
         v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
@@ -1245,6 +1253,7 @@ extern "C" int mb200_gb_destroy(mb200_gb_table* t, mb200_stream_t stream) {
     if (t->present) cudaFreeAsync(t->present, st);
   }
   if (t->blockoff) cudaFreeAsync(t->blockoff, st);
+  if (t->persisted) l2_carveout_release();  // the last table hands the carve-out back to normally managed L2
   delete t;
   return 0;
 }

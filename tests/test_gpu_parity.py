@@ -164,7 +164,16 @@ def test_groupby_vs_reference_golden(golden_dir, gb_table_kind):
         assert_sum_close(g.mean()._to_pandas().to_numpy(), z["mean"], abs_by_group / cnt, n, f"{name}:mean")
 
 
-def test_merge_vs_reference_golden(golden_dir):
+@pytest.fixture(params=["dense", "hash"])
+def join_table_kind(request):
+    """Dim keys in a narrow range get a direct-addressed table; MB200_JOIN_DENSE=0 forces the hash table."""
+    if request.param == "hash":
+        os.environ["MB200_JOIN_DENSE"] = "0"
+    yield request.param
+    os.environ.pop("MB200_JOIN_DENSE", None)
+
+
+def test_merge_vs_reference_golden(golden_dir, join_table_kind):
     m = bpd()
     for name, z in _load(golden_dir, "merge_*.npz"):
         n, nd, hit = (int(x) for x in z["meta"])
@@ -318,6 +327,24 @@ def test_groups_whose_rows_leave_no_trace_are_still_groups(gb_table_kind):
             assert not np.signbit(gt[np.isin(want.index.to_numpy(), [0, 6, 12])]).any() or agg == "mean"
         else:
             assert_exact(gt, w, f"groupby {agg}")
+
+
+def test_merge_with_wide_and_negative_dim_keys():
+    """Dim keys spread over a wide range fall back to the hash table; a narrow range with a negative base and
+    fact keys outside it exercise the dense table's bounds check.  Both against the oracle, bit for bit."""
+    m = bpd()
+    n, nd = 20011, 500
+    rng = np.random.RandomState(3)
+    for scale, shift in ((1, -250), (1_000_003_019, -250)):
+        fact = synth.host_frame(n, 2, seed=42, key_modulus=nd + 80, key_seed=43)  # keys >= nd miss the dim
+        fact["key"] = (fact["key"] + shift) * scale
+        dk = ((rng.permutation(nd)[: nd - 37]).astype(np.int64) + shift) * scale
+        dim = pandas.DataFrame({"key": dk, "d0": synth.gen_f64(len(dk), 11, 0), "d1": np.arange(len(dk), dtype=np.int64)})
+        for how in ("left", "inner"):
+            got = m.DataFrame(fact).merge(m.DataFrame(dim), on="key", how=how)._to_pandas()
+            want = orc.broadcast_merge(fact, dim, "key", how, 4)
+            assert list(got.columns) == list(want.columns)
+            assert_exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), f"merge {how} scale={scale}")
 
 
 def test_dense_and_hash_tables_agree_and_wide_keys_fall_back():
