@@ -360,6 +360,20 @@ def run_b200_arm(args):
         _cfg.GroupbyDenseKeys.put(True)
         del g
         torch.cuda.empty_cache()
+        # ---- the same query on SKEWED keys (Zipf-like, SURVEY 8d: key 0 takes ~11 % of the rows): the pre-pass flags
+        # the skew and the accumulate kernel keeps a per-CTA cache of hot groups in shared memory
+        g = synth.device_frame(rows, W, seed=42, key_modulus=args.groups, npartitions=1, key_skew=True)
+        g.execute()
+        total_g, per_g = timed(step_gb, ksteps, 2)
+        ms_g = total_g / ksteps
+        ach = rows_local * (8 + 8 * W) / (statistics.mean(per_g) / 1e3) / 1e9
+        also.append({"metric": "rows/sec groupby('key').sum() 1e9 rows, 1e6 int64 keys SKEWED (Zipf-like), 8 f64 vals",
+                     "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
+                     "roofline": {"bound": "hbm", "kernel": "key_range_kernel + gb_accumulate_tma_kernel<HOT> (dense table, "
+                                  "per-CTA hot-group cache)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": ach / hbm_peak, "traffic": None}})  # fmt: skip
+        del g
+        torch.cuda.empty_cache()
         # ---- broadcast merge: fact (rows x (key + 8 f64)) LEFT JOIN dim (1e7 x (key + 1 f64)) on int64 key (C5)
         import numpy as np
         import pandas

@@ -178,11 +178,18 @@ typedef struct mb200_gb_table mb200_gb_table; /* opaque, device resident */
  * `nvals` float64 accumulator columns.  flags = mb200_gb_flags. */
 int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags,
                     mb200_stream_t stream);
-/* min / max of an int64 key column into minmax_dev[2] (device).  init != 0 resets the pair to
- * {INT64_MAX, INT64_MIN} first; several row partitions accumulate into one pair with init = 0.
- * The pre-pass (8 B/row) that lets the caller choose a DENSE table when the key range is narrow. */
-int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* minmax_dev, int init,
+/* Key statistics of an int64 key column into stats_dev[4] (device): {min, max, sampled, duplicated}.
+ * init != 0 resets them to {INT64_MAX, INT64_MIN, 0, 0} first; several row partitions accumulate into one
+ * quadruple with init = 0.  `duplicated` of the `sampled` keys shared their value with another of the 32
+ * keys sampled with them: ~496/G of them for uniform keys over G values, most of them under a heavy hitter.
+ * The pre-pass (8 B/row) that lets the caller choose a DENSE table when the key range is narrow and the
+ * hot-key cache (mb200_gb_hint_skew) when the keys are skewed. */
+int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* stats_dev, int init,
                     mb200_stream_t stream);
+/* Tell the table that its keys are skewed (a few keys take a large share of the rows): accumulate calls
+ * then keep a small per-CTA cache of hot groups in shared memory and add it to the table once per CTA,
+ * instead of serialising every row of a hot key on one L2 line.  Supported for SUM / COUNT tables. */
+int mb200_gb_hint_skew(mb200_gb_table* table, int skewed);
 /* Create a DENSE (direct-addressed) table for keys known to lie in [key_min, key_max]
  * (R = key_max - key_min + 1 <= 2^29): group id = key - key_min, no hashing, no probe; one presence byte
  * per key.  Same accumulate / merge_partial / ngroups / emit / destroy calls as a hashed table; emit is
@@ -256,6 +263,10 @@ int mb200_gen_f64(double* out, int64_t nrows, uint64_t seed, uint64_t col, int64
                   int nan_per_64k, mb200_stream_t stream);
 int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
                   uint64_t modulus, mb200_stream_t stream);
+/* Skewed keys in [0, modulus) (the Zipf-like variant of the groupby workload): mass per octave of the key
+ * space grows towards small keys like k^-1.1 -- for modulus = 1e6 key 0 takes ~11 % of the rows. */
+int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                       uint64_t modulus, mb200_stream_t stream);
 
 /* ======================= utilities ========================================= */
 /* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.

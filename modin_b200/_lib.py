@@ -66,6 +66,7 @@ _SIGNATURES = {
     "mb200_key_range": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp]),
     "mb200_gb_create_dense": (C.c_int, [_vpp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "mb200_gb_dense_window": (C.c_int, [_vp, _i64, _i64]),
+    "mb200_gb_hint_skew": (C.c_int, [_vp, C.c_int]),
     "mb200_gb_destroy": (C.c_int, [_vp, _vp]),
     "mb200_gb_accumulate": (C.c_int, [_vp, _vp, _vpp, _i64, _vp]),
     "mb200_gb_merge_partial": (C.c_int, [_vp, _vp, _vpp, _vpp, _vp, _i64, _vp]),
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "mb200_compact_hits": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp]),
+    "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_sort_pairs_i64": (C.c_int, [_vp, _vp, _i64, _vp, C.c_size_t, _vp]),
     "mb200_l2_persist_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -84,6 +84,7 @@ struct mb200_gb_table {
   long long nwords;
   unsigned int* blockoff;  // [nwords / 256 + 1] per-block popcounts -> exclusive offsets (emit)
   int borrowed;            // acc / cnt / size / present belong to the caller
+  int skewed;              // mb200_gb_hint_skew: use the per-CTA hot-group cache
   int persisted;           // holds a reference on the persisting L2 carve-out (accumulators pinned)
   size_t carve_bytes, window_bytes;
   long long win_lo, win_hi;  // gid window that ngroups / emit report (default: the whole range)
@@ -429,17 +430,41 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
 
 // ---------------------------------------------------------------- default: TMA-staged tiles
 // Handles the first ntiles * 256 rows (full tiles only); nvals <= 8; raw rows (not partial tables).
+//
+// HOT = true (skewed keys, mb200_gb_hint_skew): each CTA keeps a direct-mapped cache of kHotSlots groups in
+// shared memory (slot = gid mod kHotSlots, claimed by the first group that arrives and kept to the end: a
+// group with a large share of the rows arrives within the first few rows).  Rows of a cached group are
+// accumulated with shared-memory atomics and the cache is added to the table once per CTA; all other rows
+// take the global REDs.  Without it every row of a hot key serialises on one 64-byte L2 line (~8 ns per row:
+// a key with 10 % of 1e9 rows costs ~0.8 s).  SUM / COUNT tables only.
+constexpr int kHotSlots = 256;
+constexpr int kHotStride = 9;  // doubles per cached group (8 sums + 1 pad against bank conflicts)
+constexpr int kHotOffset = ((kGbStages * kStageBytes + 2 * kGbStages * 8 + 63) / 64) * 64;
+constexpr int kHotBytes = kHotSlots * 4 + kHotSlots * kHotStride * 8 + kHotSlots * kHotStride * 4;
+constexpr int kHotBit = 1 << 30;  // group ids are < 2^29
+
+template <bool HOT>
 __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const __grid_constant__ GbParams p,
                                                                           long long ntiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kGbStages * kStageBytes);
   uint64_t* empty = full + kGbStages;
+  int* s_tag = reinterpret_cast<int*>(smem_raw + kHotOffset);
+  double* s_hot = reinterpret_cast<double*>(smem_raw + kHotOffset + kHotSlots * 4);
+  unsigned int* s_hcnt = reinterpret_cast<unsigned int*>(smem_raw + kHotOffset + kHotSlots * 4 + kHotSlots * kHotStride * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nv = p.nvals;
   const int gcap = (int)p.gcap;
   const long long first = blockIdx.x;
   const long long nmine = first < ntiles ? (ntiles - first + gridDim.x - 1) / gridDim.x : 0;
 
+  if (HOT) {
+    for (int i = tid; i < kHotSlots; i += kGbTmaThreads) s_tag[i] = -1;
+    for (int i = tid; i < kHotSlots * kHotStride; i += kGbTmaThreads) {
+      s_hot[i] = 0.0;
+      s_hcnt[i] = 0u;
+    }
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kGbStages; ++s) {
@@ -486,23 +511,39 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
       const Slot* ns = &p.slots[hash_key(nk) & p.mask];
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ns));
     }
-    const int gid = resolve_gid(p, key, keep);
+    int gid = resolve_gid(p, key, keep);
     if ((p.flags & MB200_GB_SIZE) && gid < gcap) red_add_u64(p.size + gid, 1LL, keep);
+    if (HOT && gid < gcap) {  // is this row's group in the CTA's hot cache (or can it claim its slot)?
+      const int slot = gid & (kHotSlots - 1);
+      int tag = *reinterpret_cast<volatile int*>(&s_tag[slot]);
+      if (tag == -1) {
+        const int old = atomicCAS(&s_tag[slot], -1, gid);
+        tag = old == -1 ? gid : old;
+      }
+      if (tag == gid) gid |= kHotBit;
+    }
     const double* vt = stage + kTileColStride + warp * 32;  // value column 0, this warp's rows
     unsigned int seen = 0;  // bit kk: this lane's (row 4 kk + lane / 8, column c) update leaves a trace
     int gs[8];
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int r = 4 * kk + (lane >> 3);
-      const int g = __shfl_sync(0xffffffffu, gid, r);
+      const int pg = __shfl_sync(0xffffffffu, gid, r);
+      const int g = HOT ? (pg & ~kHotBit) : pg;
       gs[kk] = g;
       if (c < nv && g < gcap) {
         const double xv = vt[c * kTileColStride + r];
-        const size_t o = (size_t)g * p.vstride + c;
         if (dense_visible(p, xv)) seen |= 1u << kk;
         if (xv == xv) {
-          acc_update(p, o, xv, keep);
-          if (p.flags & MB200_GB_COUNT) red_add_u64(p.cnt + o, 1LL, keep);
+          if (HOT && (pg & kHotBit)) {
+            const int o = (g & (kHotSlots - 1)) * kHotStride + c;
+            if (p.flags & MB200_GB_SUM) atomicAdd(&s_hot[o], xv);
+            if (p.flags & MB200_GB_COUNT) atomicAdd(&s_hcnt[o], 1u);
+          } else {
+            const size_t o = (size_t)g * p.vstride + c;
+            acc_update(p, o, xv, keep);
+            if (p.flags & MB200_GB_COUNT) red_add_u64(p.cnt + o, 1LL, keep);
+          }
         }
       }
     }
@@ -521,6 +562,19 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (HOT) {
+    // the 8 consumer warps fold the cache into the table (the producer warp has returned: named barrier)
+    asm volatile("bar.sync 1, %0;" ::"n"(kGbThreads) : "memory");
+    for (int i = tid; i < kHotSlots * 8; i += kGbThreads) {
+      const int slot = i >> 3, cc = i & 7;
+      const int tag = s_tag[slot];
+      if (tag < 0 || cc >= nv) continue;
+      const size_t o = (size_t)tag * p.vstride + cc;
+      if (p.flags & MB200_GB_SUM) red_add_f64(p.acc + o, s_hot[slot * kHotStride + cc], 0);
+      if ((p.flags & MB200_GB_COUNT) && s_hcnt[slot * kHotStride + cc])
+        red_add_u64(p.cnt + o, (long long)s_hcnt[slot * kHotStride + cc], 0);
+    }
   }
 }
 
@@ -753,7 +807,8 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long head = (((uintptr_t)keys & 31u) == 0) ? (n & ~15LL) : 0;  // 16 keys per thread-iteration
-  for (long long i = tid * 4; i + 3 < head; i += nthreads * 16) {
+  unsigned int sampled = 0, dups = 0, iter = 0;
+  for (long long i = tid * 4; i + 3 < head; i += nthreads * 16, ++iter) {
     i64x4 v[4];
     bool ok[4];
 #pragma unroll
@@ -761,6 +816,13 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
       const long long j = i + (long long)u * nthreads * 4;
       ok[u] = j + 3 < head;
       if (ok[u]) v[u] = ldg_stream_i64x4(keys + j);
+    }
+    // skew statistic (every 4th iteration, whole warps only): how many of 32 sampled keys share their value
+    // with another lane's.  Uniform keys over G values: ~ 496 / G of them; a heavy hitter at 10 %: > 80 %.
+    if ((iter & 3u) == 0 && __activemask() == 0xffffffffu) {
+      const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)v[0].x);
+      dups += __popc(__ballot_sync(0xffffffffu, __popc(peers) > 1));
+      sampled += 32;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -787,6 +849,10 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
   if (lane == 0) {
     s_min[warp] = lo;
     s_max[warp] = hi;
+    if (sampled) {  // every lane of a warp holds the same two counters
+      atomicAdd(reinterpret_cast<unsigned long long*>(&minmax[2]), (unsigned long long)sampled);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&minmax[3]), (unsigned long long)dups);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -804,6 +870,8 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
 __global__ void key_range_init_kernel(long long* minmax) {
   minmax[0] = 0x7fffffffffffffffLL;
   minmax[1] = (long long)0x8000000000000000ULL;
+  minmax[2] = 0;  // keys sampled for the skew statistic
+  minmax[3] = 0;  // ... of which shared their value with another of the 32 keys sampled with them
 }
 
 // presence of a dense key = its byte was marked (rows that changed nothing) OR its accumulators moved
@@ -1065,13 +1133,16 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   }
   if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
-    const size_t smem = (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
-    MB_CUDA(cudaFuncSetAttribute(gb_accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool hot = t->skewed && !(t->flags & (MB200_GB_MIN | MB200_GB_MAX | MB200_GB_SIZE));
+    const size_t smem = hot ? (size_t)kHotOffset + kHotBytes
+                            : (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
+    auto kern = hot ? gb_accumulate_tma_kernel<true> : gb_accumulate_tma_kernel<false>;
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gb_accumulate_tma_kernel, kGbTmaThreads, smem));
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGbTmaThreads, smem));
     long long grid = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
     if (grid > ntiles) grid = ntiles;
-    gb_accumulate_tma_kernel<<<(unsigned)grid, kGbTmaThreads, smem, st>>>(p, ntiles);
+    kern<<<(unsigned)grid, kGbTmaThreads, smem, st>>>(p, ntiles);
     MB_LAUNCH_CHECK("gb_accumulate_tma_kernel");
     const long long done = ntiles * kTileRows;
     if (done == nrows) return 0;
@@ -1124,6 +1195,12 @@ extern "C" int mb200_gb_create_dense(mb200_gb_table** table, int64_t key_min, in
     return fail("mb200_gb_create_dense", "caller-owned arrays need the presence array too");
   }
   return gb_create_impl(table, (int64_t)range, nvals, flags, true, key_min, ext, stream);
+}
+
+extern "C" int mb200_gb_hint_skew(mb200_gb_table* t, int skewed) {
+  if (!t) return fail("mb200_gb_hint_skew", "null table");
+  t->skewed = skewed ? 1 : 0;
+  return 0;
 }
 
 extern "C" int mb200_gb_dense_window(mb200_gb_table* t, int64_t gid_lo, int64_t gid_hi) {

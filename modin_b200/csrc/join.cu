@@ -380,7 +380,7 @@ extern "C" int mb200_join_build(mb200_join_table** table, const int64_t* dim_key
     const char* env = getenv("MB200_JOIN_DENSE");
     if (ndim > 0 && !(env && env[0] == '0')) {
       long long* mmbuf = nullptr;
-      e = cudaMallocAsync((void**)&mmbuf, 16, st);
+      e = cudaMallocAsync((void**)&mmbuf, 32, st);  // {min, max, sampled, duplicates}
       if (e != cudaSuccess) {
         mb200_join_destroy(t, stream);
         return cuda_fail("mb200_join_build", e);

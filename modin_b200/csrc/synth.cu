@@ -47,6 +47,33 @@ __global__ void gen_i64_kernel(long long* __restrict__ out, long long n, unsigne
   }
 }
 
+// Skewed keys (the Zipf-like variant of SURVEY 8d): level t in [0, T] is drawn with weight w_t, w_0 = 2^20,
+// w_{t+1} = w_t + (w_t >> 4) + (w_t >> 7) (x 1.0703 per level -- integer recurrence, so numpy reproduces it
+// exactly), T = floor(log2(modulus)); the key is uniform in [0, modulus >> t).  Mass per octave grows towards
+// small keys like k^-1.1: for modulus = 1e6 key 0 takes ~11 % of the rows, the top 256 keys ~60 %.
+struct SkewLevels {
+  unsigned long long cum[66];  // cum[t] = w_0 + ... + w_{t-1};  cum[T + 1] = total
+  int nlevels;                 // T + 1
+};
+
+__global__ void gen_i64_skew_kernel(long long* __restrict__ out, long long n, unsigned long long seed,
+                                    unsigned long long col, long long row_offset, unsigned long long modulus,
+                                    const __grid_constant__ SkewLevels lv) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned long long total = lv.cum[lv.nlevels];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long z1 = mix64(seed * K1 + col * K2 + (unsigned long long)(row_offset + i) + 1ULL);
+    const unsigned long long z2 = mix64(z1 + K3);
+    // pick in [0, total): total < 2^31, so (32-bit piece * total) >> 32 is exact in 64 bits
+    const unsigned long long pick = ((z2 >> 32) * total) >> 32;
+    int t = 0;
+    while (t + 1 < lv.nlevels && lv.cum[t + 1] <= pick) ++t;
+    unsigned long long range = modulus >> t;
+    if (range == 0) range = 1;
+    out[i] = (long long)(((z1 >> 32) * range) >> 32);
+  }
+}
+
 __global__ void flush_kernel(unsigned long long* __restrict__ buf, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (unsigned long long)i;
@@ -83,6 +110,34 @@ extern "C" int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_
   gen_i64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, seed, col,
                                                                    row_offset, modulus);
   MB_LAUNCH_CHECK("gen_i64_kernel");
+  return 0;
+}
+
+extern "C" int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
+                                  uint64_t modulus, mb200_stream_t stream) {
+  if (nrows < 0) return fail("mb200_gen_i64_skew", "negative nrows");
+  if (modulus == 0 || modulus > 0xffffffffULL) return fail("mb200_gen_i64_skew", "modulus must be in [1, 2^32)");
+  if (nrows == 0) return 0;
+  if (!out) return fail("mb200_gen_i64_skew", "null output");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  SkewLevels lv;
+  memset(&lv, 0, sizeof(lv));
+  int T = 0;
+  while ((modulus >> (T + 1)) != 0) ++T;
+  unsigned long long w = 1ULL << 20, acc = 0;
+  for (int t = 0; t <= T; ++t) {
+    lv.cum[t] = acc;
+    acc += w;
+    w = w + (w >> 4) + (w >> 7);
+  }
+  lv.cum[T + 1] = acc;
+  lv.nlevels = T + 1;
+  long long grid = (nrows + 255) / 256;
+  if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
+  gen_i64_skew_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, seed,
+                                                                        col, row_offset, modulus, lv);
+  MB_LAUNCH_CHECK("gen_i64_skew_kernel");
   return 0;
 }
 

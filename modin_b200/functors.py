@@ -590,17 +590,19 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
     mm = ops.key_range_device([k for k, _ in items])
     total_rows = sum(len(k) for k, _ in items)
     if dist.is_distributed():
-        # one small all_gather ([min, max, rows] per rank) + one D2H instead of three all_reduces
+        # one small all_gather ([min, max, sampled, duplicated, rows] per rank) + one D2H
         trip = dist.all_gather_small(mm, extra=total_rows)
-        lo, hi, total_rows = min(r[0] for r in trip), max(r[1] for r in trip), sum(r[2] for r in trip)
+        lo, hi, total_rows = min(r[0] for r in trip), max(r[1] for r in trip), sum(r[4] for r in trip)
+        sampled, dup = trip[dist.rank()][2:4]  # the hot-group cache is a local choice
     else:
-        lo, hi = (int(v) for v in mm.tolist())
+        lo, hi, sampled, dup = (int(v) for v in mm.tolist())
     if lo > hi:
         return None  # no rows anywhere
     cap = max(1024, min(map_fn.capacity_hint, total_rows))
     if not ops.dense_range_ok(lo, hi, cap, total_rows, len(labels), flags):
         return None
     table = ops.GroupTable.dense(lo, hi, len(labels), flags)
+    table.hint_skew(ops.keys_are_skewed(sampled, dup))
     try:
         for key, vals in items:
             table.accumulate(key, vals)

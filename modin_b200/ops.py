@@ -186,6 +186,10 @@ class GroupTable:
     def window(self, gid_lo: int, gid_hi: int):
         _lib.check(self.lib.mb200_gb_dense_window(self.handle, int(gid_lo), int(gid_hi)))
 
+    def hint_skew(self, skewed: bool):
+        """Skewed keys: accumulate with the per-CTA hot-group cache (mb200_gb_hint_skew)."""
+        _lib.check(self.lib.mb200_gb_hint_skew(self.handle, 1 if skewed else 0))
+
     def accumulate(self, keys: DeviceColumn, vals: Sequence[DeviceColumn]):
         if keys.dtype != np.int64:
             raise TypeError("device groupby needs an int64 key column")
@@ -241,11 +245,21 @@ class GroupTable:
 DENSE_TABLE_MAX_BYTES = 8 << 30
 
 
+SKEW_THRESHOLD = 0.05  # share of sampled keys that met their own value among 32 keys (uniform over G keys: ~31/G)
+
+
+def keys_are_skewed(sampled: int, duplicated: int) -> bool:
+    """A heavy hitter (a key with >= ~5 % of the rows) shows up as most sampled keys being duplicates; uniform
+    keys over G values give ~496/G (the shared-memory table takes the small-G cases before this matters)."""
+    return sampled >= 1024 and duplicated > SKEW_THRESHOLD * sampled
+
+
 def key_range_device(key_cols: Sequence[DeviceColumn]):
-    """Device tensor [min, max] over int64 key columns ({INT64_MAX, INT64_MIN} when there are no rows)."""
+    """Device tensor [min, max, sampled, duplicated] over int64 key columns (mb200_key_range;
+    {INT64_MAX, INT64_MIN, 0, 0} when there are no rows)."""
     lib = _lib.load()
     t = torch_mod()
-    mm = t.empty(2, dtype=t.int64, device=current_device())
+    mm = t.empty(4, dtype=t.int64, device=current_device())
     if not key_cols:
         _lib.check(lib.mb200_key_range(None, 0, mm.data_ptr(), 1, current_stream()))
     for i, k in enumerate(key_cols):
@@ -257,7 +271,7 @@ def key_range_device(key_cols: Sequence[DeviceColumn]):
 
 def key_range(key_cols: Sequence[DeviceColumn]):
     """(min, max) over int64 key columns -- one streaming pass, one 16-byte D2H.  None when empty."""
-    lo, hi = (int(v) for v in key_range_device(key_cols).tolist())
+    lo, hi = (int(v) for v in key_range_device(key_cols).tolist()[:2])
     return None if lo > hi else (lo, hi)
 
 
@@ -282,10 +296,14 @@ def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool 
     cap = max(int(capacity_hint), 1024)
     nvals = len(key_cols_vals[0][1]) if key_cols_vals[0][1] else 0
     total_rows = sum(len(item[0]) for item in key_cols_vals)
+    skewed = False
     if GroupbyDenseKeys.get() and total_rows > 0:
-        kr = key_range([item[0] for item in key_cols_vals])
+        lo, hi, sampled, dup = (int(v) for v in key_range_device([item[0] for item in key_cols_vals]).tolist())
+        kr = None if lo > hi else (lo, hi)
+        skewed = not partial and keys_are_skewed(sampled, dup)
         if kr is not None and dense_range_ok(kr[0], kr[1], cap, total_rows, nvals, flags):
             table = GroupTable.dense(kr[0], kr[1], nvals, flags)
+            table.hint_skew(skewed)
             try:
                 for item in key_cols_vals:
                     if partial:
@@ -300,6 +318,7 @@ def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool 
                 table.close()
     while True:
         table = GroupTable(cap, nvals, flags)
+        table.hint_skew(skewed)
         try:
             for item in key_cols_vals:
                 if partial:
@@ -418,10 +437,11 @@ def gen_f64(nrows: int, seed: int, col: int, row_offset: int = 0, nan_per_64k: i
     return c
 
 
-def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0) -> DeviceColumn:
+def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0, skew: bool = False) -> DeviceColumn:
     lib = _lib.load()
     c = DeviceColumn.empty(nrows, np.int64)
-    _lib.check(lib.mb200_gen_i64(c.ptr, nrows, seed, col, row_offset, modulus, current_stream()))
+    fn = lib.mb200_gen_i64_skew if skew else lib.mb200_gen_i64
+    _lib.check(fn(c.ptr, nrows, seed, col, row_offset, modulus, current_stream()))
     return c
 
 

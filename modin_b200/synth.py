@@ -64,19 +64,46 @@ def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0) 
         return (((z1 >> np.uint64(32)) * np.uint64(modulus)) >> np.uint64(32)).astype(np.int64)
 
 
+def skew_levels(modulus: int):
+    """Cumulative level weights of the skewed key generator (same integer recurrence as csrc/synth.cu)."""
+    T = int(modulus).bit_length() - 1
+    w, acc, cum = 1 << 20, 0, []
+    for _ in range(T + 1):
+        cum.append(acc)
+        acc += w
+        w = w + (w >> 4) + (w >> 7)
+    cum.append(acc)
+    return np.array(cum, dtype=np.uint64)
+
+
+def gen_i64_skew(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0) -> np.ndarray:
+    """numpy twin of mb200_gen_i64_skew (Zipf-like keys in [0, modulus): key 0 takes ~11 % at modulus 1e6)."""
+    rows = np.arange(row_offset, row_offset + nrows, dtype=np.int64)
+    cum = skew_levels(modulus)
+    with np.errstate(over="ignore"):
+        z1 = _z1(seed, col, rows)
+        z2 = _mix64(z1 + K3)
+        pick = ((z2 >> np.uint64(32)) * cum[-1]) >> np.uint64(32)
+        t = np.searchsorted(cum[1:-1], pick, side="right").astype(np.uint64)  # largest t with cum[t] <= pick
+        rng = np.maximum(np.uint64(modulus) >> t, np.uint64(1))
+        return (((z1 >> np.uint64(32)) * rng) >> np.uint64(32)).astype(np.int64)
+
+
 def host_frame(nrows: int, ncols: int, seed: int = 42, row_offset: int = 0, nan_per_64k: int = 0,
-               key_modulus: Optional[int] = None, key_seed: int = 43, prefix: str = "c") -> pandas.DataFrame:  # fmt: skip
+               key_modulus: Optional[int] = None, key_seed: int = 43, prefix: str = "c",
+               key_skew: bool = False) -> pandas.DataFrame:  # fmt: skip
     """Host (pandas) synthetic frame: float64 columns c0..c{W-1} and optionally an int64 ``key``."""
     data = {}
     if key_modulus:
-        data["key"] = gen_i64(nrows, key_seed, 0, key_modulus, row_offset)
+        gen = gen_i64_skew if key_skew else gen_i64
+        data["key"] = gen(nrows, key_seed, 0, key_modulus, row_offset)
     for j in range(ncols):
         data[f"{prefix}{j}"] = gen_f64(nrows, seed, j, row_offset, nan_per_64k)
     return pandas.DataFrame(data, index=pandas.RangeIndex(row_offset, row_offset + nrows))
 
 
 def device_blocks(nrows: int, ncols: int, seed: int = 42, nan_per_64k: int = 0, key_modulus: Optional[int] = None,
-                  key_seed: int = 43, npartitions: int = 1, prefix: str = "c") -> List:  # fmt: skip
+                  key_seed: int = 43, npartitions: int = 1, prefix: str = "c", key_skew: bool = False) -> List:  # fmt: skip
     """This rank's shard of the synthetic frame as ``npartitions`` device blocks, generated in HBM."""
     from . import dist, ops
     from .block import DeviceBlock
@@ -92,7 +119,7 @@ def device_blocks(nrows: int, ncols: int, seed: int = 42, nan_per_64k: int = 0, 
             break
         cols, labels = [], []
         if key_modulus:
-            cols.append(ops.gen_i64(n, key_seed, 0, key_modulus, pos))
+            cols.append(ops.gen_i64(n, key_seed, 0, key_modulus, pos, skew=key_skew))
             labels.append("key")
         for j in range(ncols):
             cols.append(ops.gen_f64(n, seed, j, pos, nan_per_64k))

@@ -125,8 +125,8 @@ def hash_aggregate(items, flags, capacity_hint, partial=False, sort=True):
 def key_range_device(key_cols):
     ks = [_np(k) for k in key_cols if len(k)]
     if not ks:
-        return torch.tensor([np.iinfo(np.int64).max, np.iinfo(np.int64).min], dtype=torch.int64)
-    return torch.tensor([min(int(k.min()) for k in ks), max(int(k.max()) for k in ks)], dtype=torch.int64)
+        return torch.tensor([np.iinfo(np.int64).max, np.iinfo(np.int64).min, 0, 0], dtype=torch.int64)
+    return torch.tensor([min(int(k.min()) for k in ks), max(int(k.max()) for k in ks), 0, 0], dtype=torch.int64)
 
 
 class GroupTable:
@@ -182,6 +182,9 @@ class GroupTable:
         acc_op = "sum" if self.flags & _lib.GB_SUM else ("min" if self.flags & _lib.GB_MIN else "max")
         out = [(self.acc, acc_op), (self.cnt, "sum"), (self.size, "sum"), (self.present, "max")]
         return [(x, op) for x, op in out if x is not None]
+
+    def hint_skew(self, skewed):
+        pass
 
     def window(self, lo, hi):
         assert lo % 4 == 0 and (hi % 4 == 0 or hi == self.R) and 0 <= lo <= hi <= self.R

@@ -347,6 +347,39 @@ def test_merge_with_wide_and_negative_dim_keys():
             assert_exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), f"merge {how} scale={scale}")
 
 
+def test_skewed_keys_take_the_hot_group_cache_and_match_the_oracle(gb_table_kind):
+    """Zipf-like keys (SURVEY 8d skew variant): the key pre-pass must flag them, the accumulate kernel then
+    caches hot groups per CTA in shared memory -- same results as the oracle either way."""
+    from modin_b200 import ops
+    from modin_b200.block import DeviceColumn
+
+    m = bpd()
+    n, G = 200_003, 50_000
+    for nn, off in ((1000, 0), (4097, 12345)):
+        assert np.array_equal(ops.gen_i64(nn, 43, 0, G, off, skew=True).to_numpy(), synth.gen_i64_skew(nn, 43, 0, G, off))
+    pdf = synth.host_frame(n, 3, seed=23, nan_per_64k=700, key_modulus=G, key_skew=True)
+    assert (pdf["key"] == 0).mean() > 0.08  # a heavy hitter
+    lo, hi, sampled, dup = (int(v) for v in ops.key_range_device([DeviceColumn.from_numpy(pdf["key"].to_numpy())]).tolist())
+    assert (lo, hi) == (int(pdf["key"].min()), int(pdf["key"].max())) and ops.keys_are_skewed(sampled, dup)
+    uni = synth.gen_i64(n, 43, 0, G)
+    assert not ops.keys_are_skewed(*(int(v) for v in ops.key_range_device([DeviceColumn.from_numpy(uni)]).tolist()[2:]))
+    g = m.DataFrame(pdf).groupby("key")
+    abs_by_group = pdf.drop(columns="key").abs().groupby(pdf["key"]).sum().to_numpy()
+    for agg in ("sum", "count", "mean", "size", "max"):
+        got = getattr(g, agg)()._to_pandas()
+        want = orc.groupby_reduce(pdf, "key", agg, 4)
+        assert_exact(got.index.to_numpy(), want.index.to_numpy(), f"{agg} keys")
+        w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
+        gt = got.to_numpy(dtype=np.float64).reshape(len(got), -1)
+        if agg == "sum":
+            assert_sum_close(gt, w, abs_by_group, n, "skewed sum")
+        elif agg == "mean":
+            cnt = np.maximum(orc.groupby_reduce(pdf, "key", "count", 4).to_numpy(), 1)
+            assert_sum_close(gt, w, abs_by_group / cnt, n, "skewed mean")
+        else:
+            assert_exact(gt, w, f"skewed {agg}")
+
+
 def test_dense_and_hash_tables_agree_and_wide_keys_fall_back():
     """The dense table is chosen from the measured key range; keys spread over a wide range must take the
     hash table and give the same groups.  Counts / sizes / keys / min / max are bit-identical either way."""

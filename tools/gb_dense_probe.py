@@ -40,18 +40,19 @@ def main():
         _lib.check(lib.mb200_gen_f64(c.data_ptr(), n, 42, i, 0, 0, st))
     cp = _lib.ptr_array([c.data_ptr() for c in cols])
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    mm = torch.empty(2, dtype=torch.int64, device=dev)
+    mm = torch.empty(4, dtype=torch.int64, device=dev)
     Gs = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (16, 256, 1024, 3000, 4000, 16384, 65_536, 1_000_000)
     kinds = sys.argv[3].split(',') if len(sys.argv) > 3 else ("hash", "dense", "dense_nosmem")
+    skew = len(sys.argv) > 4 and sys.argv[4] == "skew"
     for G in Gs:
-        _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, G, st))
+        _lib.check((lib.mb200_gen_i64_skew if skew else lib.mb200_gen_i64)(keys.data_ptr(), n, 43, 0, 0, G, st))
 
         def krange():
             _lib.check(lib.mb200_key_range(keys.data_ptr(), n, mm.data_ptr(), 1, st))
 
         tk = timeit(krange)
-        lo, hi = mm.tolist()
-        assert (lo, hi) == (0, G - 1), (lo, hi)
+        lo, hi, sampled, dup = lo_hi_stats = mm.tolist()
+        print(json.dumps({"G": G, "skew": skew, "key_stats": lo_hi_stats, "dup_share": round(dup / max(sampled, 1), 4)}), flush=True)
         for variant in ("0",):
             os.environ["MB200_GB_VARIANT"] = variant
             for kind in kinds:
@@ -63,6 +64,8 @@ def main():
                         _lib.check(lib.mb200_gb_create_dense(C.byref(t2), 0, G - 1, W, _lib.GB_SUM, None, None, None, None, st))
                     else:
                         _lib.check(lib.mb200_gb_create(C.byref(t2), G + 16, W, _lib.GB_SUM, st))
+                    if kind == "dense_hot":
+                        _lib.check(lib.mb200_gb_hint_skew(t2, 1))
                     _lib.check(lib.mb200_gb_accumulate(t2, keys.data_ptr(), cp, n, st))
                     _lib.check(lib.mb200_gb_destroy(t2, st))
 
