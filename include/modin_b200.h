@@ -80,8 +80,9 @@ enum mb200_map_op {
   MB200_OP_LE_S = 15,
   MB200_OP_GT_S = 16,
   MB200_OP_GE_S = 17,
-  MB200_OP_CLIP_S = 18, /* min(max(x, s0), s1), NaN preserved */
+  MB200_OP_CLIP_S = 18, /* x < s0 ? s0 : (x > s1 ? s1 : x); NaN preserved; absent bounds = -inf / +inf (pandas clip) */
   MB200_OP_COPY = 19,
+  MB200_OP_ROUND_S = 20, /* numpy.round(x, d): s0 = 10^|d|, s1 = sign of d; rint(x * s0) / s0 (DataFrame.round) */
   /* two-frame ops (in0 OP in1) */
   MB200_OP_ADD = 32,
   MB200_OP_SUB = 33,
@@ -107,7 +108,10 @@ enum mb200_reduce_op {
   MB200_RED_MIN = 1,  /* out_val = min over non-NaN, out_cnt = #non-NaN             */
   MB200_RED_MAX = 2,
   MB200_RED_COUNT = 3, /* out_cnt only */
-  MB200_RED_PROD = 4   /* out_val = product (NaN skipped iff skipna), out_cnt = #non-NaN */
+  MB200_RED_PROD = 4,  /* out_val = product (NaN skipped iff skipna), out_cnt = #non-NaN */
+  MB200_RED_SSD = 5    /* out_val = sum of (centre - x)^2 (NaN skipped iff skipna), out_cnt = #non-NaN:
+                          the second pass of pandas' two-pass var / std (nanops.nanvar), float64 only,
+                          through mb200_reduce_columns_centered */
 };
 
 /* ---- groupby aggregate selection (bit flags) ------------------------------ */
@@ -170,6 +174,13 @@ size_t mb200_reduce_scratch_bytes(int ncols);
 int mb200_reduce_columns(int op, int dtype, int ncols, const void* const* in, int64_t nrows,
                          int skipna, void* out_val, int64_t* out_cnt, void* scratch,
                          int variant, mb200_stream_t stream);
+/* MB200_RED_SSD: out_val[c] = sum over rows of (centers_dev[c] - x)^2, centers_dev[ncols] a DEVICE array
+ * (the column means from a previous sum / count pass, so no host round trip sits between the passes).
+ * Replaces the per-column work of Reduce.register(pandas.DataFrame.var / std) qc.py:1152-1153. */
+int mb200_reduce_columns_centered(int op, int dtype, int ncols, const void* const* in, int64_t nrows,
+                                  int skipna, const double* centers_dev, void* out_val,
+                                  int64_t* out_cnt, void* scratch, int variant,
+                                  mb200_stream_t stream);
 
 /* ======================= GroupByReduce ===================================== */
 typedef struct mb200_gb_table mb200_gb_table; /* opaque, device resident */

@@ -27,13 +27,13 @@ OP = {
     "abs": 0, "neg": 1, "isna": 2, "notna": 3, "fillna_s": 4, "affine": 5,
     "add_s": 6, "sub_s": 7, "rsub_s": 8, "mul_s": 9, "div_s": 10, "rdiv_s": 11,
     "eq_s": 12, "ne_s": 13, "lt_s": 14, "le_s": 15, "gt_s": 16, "ge_s": 17,
-    "clip_s": 18, "copy": 19,
+    "clip_s": 18, "copy": 19, "round_s": 20,
     "add": 32, "sub": 33, "mul": 34, "div": 35, "eq": 36, "ne": 37, "lt": 38, "le": 39,
     "gt": 40, "ge": 41, "fillna": 42,
     "fma3": 64,
 }  # fmt: skip
 PREDICATES = {"isna", "notna", "eq_s", "ne_s", "lt_s", "le_s", "gt_s", "ge_s", "eq", "ne", "lt", "le", "gt", "ge"}
-RED = {"sum": 0, "min": 1, "max": 2, "count": 3, "prod": 4}
+RED = {"sum": 0, "min": 1, "max": 2, "count": 3, "prod": 4, "ssd": 5}
 GB_SUM, GB_COUNT, GB_SIZE, GB_MIN, GB_MAX = 1, 2, 4, 8, 16
 
 _vp = C.c_void_p
@@ -62,6 +62,8 @@ _SIGNATURES = {
     "mb200_map_host": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _vpp, _vpp, _vpp, _i64, _u64p, _u64p, _i64]),
     "mb200_reduce_scratch_bytes": (C.c_size_t, [C.c_int]),
     "mb200_reduce_columns": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _i64, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
+    "mb200_reduce_columns_centered": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _i64, C.c_int, _vp, _vp, _vp, _vp,
+                                                C.c_int, _vp]),
     "mb200_gb_create": (C.c_int, [_vpp, _i64, C.c_int, C.c_int, _vp]),
     "mb200_key_range": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp]),
     "mb200_gb_create_dense": (C.c_int, [_vpp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),

@@ -106,8 +106,19 @@ __device__ __forceinline__ TO apply(TI a, TI b, TI c, TI s0, TI s1) {
   } else if constexpr (OP == MB200_OP_GE_S || OP == MB200_OP_GE) {
     return (TO)(a >= ((OP == MB200_OP_GE) ? b : s0));
   } else if constexpr (OP == MB200_OP_CLIP_S) {
-    if constexpr (F) return (TO)((a != a) ? a : fmin(fmax(a, s0), s1));
-    else return (TO)(a < s0 ? s0 : (a > s1 ? s1 : a));
+    // pandas clip = where(x >= lower, lower) / where(x <= upper, upper) with NaN kept: comparisons, not
+    // fmin / fmax (which would turn a -0.0 at lower = 0.0 into +0.0); absent bounds are passed as -inf / +inf
+    return (TO)(a < s0 ? s0 : (a > s1 ? s1 : a));
+  } else if constexpr (OP == MB200_OP_ROUND_S) {
+    // numpy.round(x, d) (pandas DataFrame.round): d >= 0: rint(x * 10^d) / 10^d, d < 0: rint(x / 10^-d) * 10^-d;
+    // s0 = 10^|d| (exact in float64 for |d| <= 22), s1 = sign of d.  rint = round-half-to-even.  Like numpy,
+    // no guard against the scaled value overflowing (round(1e308, 2) = inf).
+    if constexpr (F) {
+      if (s1 >= (TI)0) return (TO)__ddiv_rn(rint(__dmul_rn(a, s0)), s0);
+      return (TO)__dmul_rn(rint(__ddiv_rn(a, s0)), s0);
+    } else {
+      return (TO)a;  // integers: decimals >= 0 is the identity (negative decimals are not on this path)
+    }
   } else if constexpr (OP == MB200_OP_COPY) {
     return (TO)a;
   } else if constexpr (OP == MB200_OP_FILLNA) {
@@ -301,6 +312,7 @@ extern "C" int mb200_map(int op, int dtype, int ncols, const void* const* in0, c
       MB_CASE(MB200_OP_GE_S, double, uint8_t)
       MB_CASE(MB200_OP_CLIP_S, double, double)
       MB_CASE(MB200_OP_COPY, double, double)
+      MB_CASE(MB200_OP_ROUND_S, double, double)
       MB_CASE(MB200_OP_ADD, double, double)
       MB_CASE(MB200_OP_SUB, double, double)
       MB_CASE(MB200_OP_MUL, double, double)
@@ -335,6 +347,7 @@ extern "C" int mb200_map(int op, int dtype, int ncols, const void* const* in0, c
       MB_CASE(MB200_OP_GE_S, long long, uint8_t)
       MB_CASE(MB200_OP_CLIP_S, long long, long long)
       MB_CASE(MB200_OP_COPY, long long, long long)
+      MB_CASE(MB200_OP_ROUND_S, long long, long long)
       MB_CASE(MB200_OP_ADD, long long, long long)
       MB_CASE(MB200_OP_SUB, long long, long long)
       MB_CASE(MB200_OP_MUL, long long, long long)

@@ -39,6 +39,7 @@ struct RedParams {
   int skipna;
   void* part_val;       // [ncols][gridDim.x]
   long long* part_cnt;  // [ncols][gridDim.x]
+  const double* centers;  // SSD only: per-column centre (device array [ncols])
 };
 
 // ---------------------------------------------------------------- accumulators
@@ -73,6 +74,17 @@ struct Acc<MB200_RED_SUM, double> {
   }
   __device__ __forceinline__ double value() const { return s - c; }
   static __device__ __forceinline__ double combine(double a, double b) { return a + b; }
+};
+// Sum of squared deviations from a per-column centre: the second pass of pandas' two-pass variance
+// (nanops.nanvar: avg = sum / count; sqr = (avg - values) ** 2; NaNs dropped; result = sqr.sum() / (count - ddof)).
+// One rounding for the difference, one for the square, compensated summation like SUM.
+template <>
+struct Acc<MB200_RED_SSD, double> : Acc<MB200_RED_SUM, double> {
+  double center = 0.0;
+  __device__ __forceinline__ void add(double x, int skipna) {
+    const double d = __dsub_rn(center, x);
+    Acc<MB200_RED_SUM, double>::add(__dmul_rn(d, d), skipna);
+  }
 };
 template <>
 struct Acc<MB200_RED_SUM, long long> {
@@ -256,6 +268,11 @@ __global__ void __launch_bounds__(kRThreads) reduce_ldg_kernel(const __grid_cons
   const long long ntiles = (n + kLdgTile - 1) / kLdgTile;
   const int tid = threadIdx.x;
   Acc<OP, T> acc[4];
+  if constexpr (OP == MB200_RED_SSD) {
+    const double c = p.centers[blockIdx.y];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i].center = c;
+  }
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const long long base = t * kLdgTile;
     if (VEC && base + kLdgTile <= n) {
@@ -336,6 +353,11 @@ __global__ void __launch_bounds__(kTmaThreads) reduce_tma_kernel(const __grid_co
   };
 
   Acc<OP, T> acc[4];
+  if constexpr (OP == MB200_RED_SSD) {
+    const double c = p.centers[blockIdx.y];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i].center = c;
+  }
   if (warp == kConsumerWarps) {
     // ---------------- producer warp
     if (lane == 0) {
@@ -404,7 +426,7 @@ __global__ void reduce_finalize_kernel(const void* part_val, const long long* pa
   Acc<OP, T> ident;
   T v = ident.value();
   long long n = 0;
-  if constexpr (OP == MB200_RED_SUM && std::is_same<T, double>::value) {
+  if constexpr ((OP == MB200_RED_SUM || OP == MB200_RED_SSD) && std::is_same<T, double>::value) {
     // compensated combine of the CTA partials
     Acc<MB200_RED_SUM, double> a;
     for (int i = lane; i < nparts; i += 32) {
@@ -493,9 +515,30 @@ extern "C" size_t mb200_reduce_scratch_bytes(int ncols) {
   return (size_t)MB200_MAX_COLS * kMaxCtasPerCol * 16;
 }
 
+static int reduce_columns_impl(int op, int dtype, int ncols, const void* const* in, int64_t nrows, int skipna,
+                               const double* centers_dev, void* out_val, int64_t* out_cnt, void* scratch, int variant,
+                               mb200_stream_t stream);
+
 extern "C" int mb200_reduce_columns(int op, int dtype, int ncols, const void* const* in, int64_t nrows,
                                     int skipna, void* out_val, int64_t* out_cnt, void* scratch, int variant,
                                     mb200_stream_t stream) {
+  if (op == MB200_RED_SSD) return fail("mb200_reduce_columns", "MB200_RED_SSD needs mb200_reduce_columns_centered");
+  return reduce_columns_impl(op, dtype, ncols, in, nrows, skipna, nullptr, out_val, out_cnt, scratch, variant, stream);
+}
+
+extern "C" int mb200_reduce_columns_centered(int op, int dtype, int ncols, const void* const* in, int64_t nrows,
+                                             int skipna, const double* centers_dev, void* out_val, int64_t* out_cnt,
+                                             void* scratch, int variant, mb200_stream_t stream) {
+  if (op != MB200_RED_SSD || dtype != MB200_F64)
+    return fail("mb200_reduce_columns_centered", "only MB200_RED_SSD over float64 columns takes centres");
+  if (!centers_dev && ncols > 0) return fail("mb200_reduce_columns_centered", "null centres");
+  return reduce_columns_impl(op, dtype, ncols, in, nrows, skipna, centers_dev, out_val, out_cnt, scratch, variant,
+                             stream);
+}
+
+static int reduce_columns_impl(int op, int dtype, int ncols, const void* const* in, int64_t nrows, int skipna,
+                               const double* centers_dev, void* out_val, int64_t* out_cnt, void* scratch, int variant,
+                               mb200_stream_t stream) {
   if (ncols < 0 || ncols > MB200_MAX_COLS) return fail("mb200_reduce_columns", "ncols out of range (0..32)");
   if (nrows < 0) return fail("mb200_reduce_columns", "negative nrows");
   if (ncols == 0) return 0;
@@ -509,6 +552,7 @@ extern "C" int mb200_reduce_columns(int op, int dtype, int ncols, const void* co
   p.ncols = ncols;
   p.nrows = nrows;
   p.skipna = skipna ? 1 : 0;
+  p.centers = centers_dev;
   cudaStream_t st = (cudaStream_t)stream;
   long long* oc = reinterpret_cast<long long*>(out_cnt);
 #define MB_RED(OPC, T) return run_reduce<OPC, T>(p, variant, out_val, oc, scratch, st);
@@ -519,6 +563,7 @@ extern "C" int mb200_reduce_columns(int op, int dtype, int ncols, const void* co
       case MB200_RED_MAX: MB_RED(MB200_RED_MAX, double)
       case MB200_RED_COUNT: MB_RED(MB200_RED_COUNT, double)
       case MB200_RED_PROD: MB_RED(MB200_RED_PROD, double)
+      case MB200_RED_SSD: MB_RED(MB200_RED_SSD, double)
     }
   } else if (dtype == MB200_I64) {
     switch (op) {

@@ -86,6 +86,72 @@ class DevMap(DevFn):
         return block
 
 
+class DevRound(DevFn):
+    """``df.round(decimals)`` -- ``Map.register(pandas.DataFrame.round)`` qc.py:2438; numpy.round semantics
+    (``rint(x * 10**d) / 10**d``, half to even), integer columns unchanged for d >= 0."""
+
+    op = "round"
+
+    def __call__(self, block, *args, decimals=0, **kwargs):
+        _check_block(block, "DevRound")
+        if args:
+            decimals = args[0]
+        if not isinstance(decimals, numbers.Integral) or abs(int(decimals)) > 22:
+            raise NotImplementedError("device round takes one integer `decimals` in [-22, 22]")
+        d = int(decimals)
+        if not block.cols or block.nrows == 0:
+            return block
+        out = list(block.cols)
+        fidx = [j for j, c in enumerate(block.cols) if c.dtype == np.float64]
+        if any(c.dtype == np.int64 for c in block.cols) and d < 0:
+            raise NotImplementedError("round(decimals < 0) on int64 columns is not on the B200 path")
+        if any(c.dtype == np.bool_ for c in block.cols):
+            raise NotImplementedError("round on bool columns is not on the B200 path")
+        if fidx:
+            res = ops.map_columns("round_s", [block.cols[j] for j in fidx], s0=[10.0 ** abs(d)] * len(fidx),
+                                  s1=[1.0 if d >= 0 else -1.0] * len(fidx))  # fmt: skip
+            for j, r in zip(fidx, res):
+                out[j] = r
+        return block.with_cols(out)
+
+
+class DevClip(DevFn):
+    """``df.clip(lower, upper)`` with scalar bounds -- ``Map.register(pandas.DataFrame.clip)`` (qc.py clip);
+    NaNs stay NaN, a missing bound is -inf / +inf."""
+
+    op = "clip"
+
+    def __call__(self, block, *args, lower=None, upper=None, axis=None, inplace=False, **kwargs):
+        _check_block(block, "DevClip")
+        if args:
+            lower = args[0]
+            upper = args[1] if len(args) > 1 else upper
+        for b in (lower, upper):
+            if b is not None and not isinstance(b, numbers.Real):
+                raise NotImplementedError("device clip takes scalar bounds")
+        if lower is not None and upper is not None and lower > upper:
+            lower, upper = upper, lower  # pandas swaps crossed scalar bounds
+        if not block.cols or block.nrows == 0 or (lower is None and upper is None):
+            return block
+        out = list(block.cols)
+        for code, lo_def, hi_def in ((np.float64, -np.inf, np.inf), (np.int64, np.iinfo(np.int64).min, np.iinfo(np.int64).max)):
+            idx = [j for j, c in enumerate(block.cols) if c.dtype == code]
+            if not idx:
+                continue
+            lo = lo_def if lower is None or (code == np.float64 and lower != lower) else lower
+            hi = hi_def if upper is None or (code == np.float64 and upper != upper) else upper
+            if code == np.int64 and (float(lo) != int(lo) or float(hi) != int(hi)):
+                raise NotImplementedError("clip of int64 columns with fractional bounds upcasts to float64 in pandas; "
+                                          "not on the B200 path")  # fmt: skip
+            conv = float if code == np.float64 else int
+            res = ops.map_columns("clip_s", [block.cols[j] for j in idx], s0=[conv(lo)] * len(idx), s1=[conv(hi)] * len(idx))
+            for j, r in zip(idx, res):
+                out[j] = r
+        if any(c.dtype == np.bool_ for c in block.cols):
+            raise NotImplementedError("clip on bool columns is not on the B200 path")
+        return block.with_cols(out)
+
+
 class DevFillna(DevFn):
     """``df.fillna(value=scalar|dict)`` -- the Map branch of qc.fillna (qc.py:2710-2813)."""
 
@@ -412,6 +478,35 @@ class DevMeanReduce(DevFn):
         res = self._divide(sums, cnts, labels)
         res.replicated = True
         return res
+
+
+class DevSsdMap(DevFn):
+    """Second pass of var / std: per-column sum of squared deviations from the column means of the WHOLE frame
+    plus non-NaN counts, as a 1 x 2W partial (W float64 sums, W int64 counts) that
+    ``DevReduce("sum", "reduce")`` adds up across partitions and GPUs.
+
+    The reference registers var / std as full-axis ``Reduce`` of ``pandas.DataFrame.var`` (qc.py:1152-1153), i.e.
+    pandas' two-pass nanops.nanvar on a whole column; the two passes here are ``mean()`` and this functor, so the
+    result does not depend on the partitioning either."""
+
+    op = "ssd_map"
+
+    def __init__(self, centers):
+        self.centers = [float(c) for c in centers]
+
+    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, **kwargs):
+        _check_block(block, "DevSsdMap")
+        if axis not in (0, "index", None):
+            raise NotImplementedError("row-wise var / std is not on the B200 path")
+        if len(self.centers) != len(block.cols):
+            raise ValueError("var / std: one centre per column expected")
+        cols = ops.cast_columns_f64(block.cols)
+        t = ops.torch_mod()
+        centers = t.tensor(self.centers, dtype=t.float64).to(cols[0].data.device) if cols else None
+        vals, cnts = ops.reduce_columns("ssd", cols, skipna=bool(skipna), variant=ReduceVariant.get(), centers=centers)
+        out = [DeviceColumn(v, np.float64) for v in vals] + [DeviceColumn(c, np.int64) for c in cnts]
+        labels = pandas.MultiIndex.from_tuples([("ssd", c) for c in block.columns] + [("count", c) for c in block.columns])
+        return _reduced_block(out, labels)
 
 
 # ------------------------------------------------------------------ GroupByReduce functors

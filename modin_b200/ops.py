@@ -103,8 +103,11 @@ def cast_columns_f64(cols: Sequence[DeviceColumn]) -> List[DeviceColumn]:
 
 
 # ------------------------------------------------------------------ TreeReduce
-def reduce_columns(op: str, cols: Sequence[DeviceColumn], skipna: bool = True, variant: int = 0):
+def reduce_columns(op: str, cols: Sequence[DeviceColumn], skipna: bool = True, variant: int = 0, centers=None):
     """Column-wise reduction.  Returns (values DeviceColumn-per-dtype-group arrays, counts).
+
+    ``op="ssd"`` (sum of squared deviations, float64 only) takes ``centers``: a float64 device tensor with one
+    centre per column.
 
     Output: list of (value_tensor_1elem_view, count_tensor_1elem_view) is avoided; instead two
     device tensors of length W are returned per dtype group, mapped back to column order:
@@ -128,12 +131,23 @@ def reduce_columns(op: str, cols: Sequence[DeviceColumn], skipna: bool = True, v
             ocnt = t.empty(len(sel), dtype=t.int64, device=current_device())
             scratch = _scratch(lib.mb200_reduce_scratch_bytes(len(sel)), "reduce")
             ptrs = _lib.ptr_array([cols[j].ptr for j in sel])
-            _lib.check(
-                lib.mb200_reduce_columns(
-                    _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, oval.data_ptr(), ocnt.data_ptr(),
-                    scratch.data_ptr(), variant, current_stream(),
-                )
-            )  # fmt: skip
+            if op == "ssd":
+                if code != _lib.F64 or centers is None:
+                    raise TypeError("ssd reduces float64 columns around given centres")
+                cen = centers[t.tensor(sel, device=centers.device)].contiguous() if len(sel) != len(cols) else centers
+                _lib.check(
+                    lib.mb200_reduce_columns_centered(
+                        _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, cen.data_ptr(), oval.data_ptr(),
+                        ocnt.data_ptr(), scratch.data_ptr(), variant, current_stream(),
+                    )
+                )  # fmt: skip
+            else:
+                _lib.check(
+                    lib.mb200_reduce_columns(
+                        _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, oval.data_ptr(), ocnt.data_ptr(),
+                        scratch.data_ptr(), variant, current_stream(),
+                    )
+                )  # fmt: skip
             for pos, j in enumerate(sel):
                 vals[j] = oval[pos : pos + 1]
                 cnts[j] = ocnt[pos : pos + 1]

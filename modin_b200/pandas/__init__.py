@@ -72,6 +72,14 @@ class BasePandasDataset:
     def __neg__(self):
         return self._create_or_update_from_compiler(self._query_compiler.negative())
 
+    def round(self, decimals=0, *args, **kwargs):
+        return self._create_or_update_from_compiler(self._query_compiler.round(decimals=decimals))
+
+    def clip(self, lower=None, upper=None, *, axis=None, inplace=False, **kwargs):
+        if inplace:
+            raise NotImplementedError("clip(inplace=True) is not on the B200 path")
+        return self._create_or_update_from_compiler(self._query_compiler.clip(lower=lower, upper=upper))
+
     def isna(self):
         return self._create_or_update_from_compiler(self._query_compiler.isna())
 
@@ -177,6 +185,21 @@ class BasePandasDataset:
 
     def mean(self, axis=0, skipna=True, numeric_only=False, **kwargs):
         return self._stat("mean", axis, skipna, numeric_only)
+
+    def var(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+        """modin/pandas/base.py ``var`` -> ``_stat_operation``; two device passes (mean, squared deviations)."""
+        if axis not in (0, "index", None):
+            raise NotImplementedError("var(axis=1) is not on the B200 path")
+        return self._finish_host_stat(self._query_compiler.var(axis=0, skipna=skipna, ddof=ddof, numeric_only=numeric_only))
+
+    def std(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+        if axis not in (0, "index", None):
+            raise NotImplementedError("std(axis=1) is not on the B200 path")
+        return self._finish_host_stat(self._query_compiler.std(axis=0, skipna=skipna, ddof=ddof, numeric_only=numeric_only))
+
+    def _finish_host_stat(self, ser):
+        ser.name = None
+        return ser
 
     def min(self, axis=0, skipna=True, numeric_only=False, **kwargs):
         return self._stat("min", axis, skipna, numeric_only)
@@ -310,6 +333,9 @@ class Series(BasePandasDataset):
     def _reduce_dimension(self, query_compiler):
         res = super()._reduce_dimension(query_compiler)
         return res.iloc[0]
+
+    def _finish_host_stat(self, ser):
+        return ser.iloc[0]
 
 
 class DataFrameGroupBy:

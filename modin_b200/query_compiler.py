@@ -21,6 +21,7 @@ from .algebra import Binary, GroupByReduce, Map, TreeReduce
 from .dataframe import B200Dataframe
 from .functors import (
     DevBinary,
+    DevClip,
     DevFillna,
     DevGroupbyMap,
     DevGroupbyReduce,
@@ -29,6 +30,8 @@ from .functors import (
     DevMeanReduce,
     DevMerge,
     DevReduce,
+    DevRound,
+    DevSsdMap,
 )
 from .partitioning import Bound
 
@@ -112,6 +115,8 @@ class B200QueryCompiler:
     negative = Map.register(DevMap("neg"), dtypes="copy")
     isna = Map.register(DevMap("isna"), dtypes=np.bool_)
     notna = Map.register(DevMap("notna"), dtypes=np.bool_)
+    round = Map.register(DevRound(), dtypes="copy")  # qc.py:2438
+    clip = Map.register(DevClip(), dtypes="copy")  # qc.py `clip = Map.register(pandas.DataFrame.clip)`
     copy_data = Map.register(DevMap("copy"), dtypes="copy")
 
     def fillna(self, **kwargs):
@@ -148,6 +153,33 @@ class B200QueryCompiler:
     max = TreeReduce.register(DevReduce("max"), DevReduce("max", phase="reduce"))
     min = TreeReduce.register(DevReduce("min"), DevReduce("min", phase="reduce"))
     mean = TreeReduce.register(DevMeanMap(), DevMeanReduce(), compute_dtypes=lambda *a, **k: np.dtype("float64"))
+
+    # ---- var / std (qc.py:1152-1153: Reduce.register(pandas.DataFrame.var / std), pandas' two-pass nanvar) ----
+    def _var(self, axis=0, skipna=True, ddof=1, numeric_only=False, sqrt=False, **kwargs):
+        """1 x W frame of variances (standard deviations when ``sqrt``): pass 1 = ``mean`` (sum, count), pass 2 =
+        sum of squared deviations from those means (``DevSsdMap``), both TreeReduce-shaped and all-reduced across
+        GPUs; the final ``ssd / (count - ddof)`` on W numbers is host arithmetic on the reduced frame."""
+        if axis not in (0, "index", None):
+            raise NotImplementedError("row-wise var / std is not on the B200 path")
+        mean = self.mean(axis=0, skipna=skipna, numeric_only=numeric_only).to_pandas()
+        W = mean.shape[1]
+        parts_qc = TreeReduce.register(DevSsdMap(mean.iloc[0].to_numpy(dtype=np.float64)), DevReduce("sum", phase="reduce"))(
+            self, axis=0, skipna=skipna, numeric_only=numeric_only
+        )  # fmt: skip
+        parts = parts_qc.to_pandas().iloc[0].to_numpy(dtype=np.float64)
+        ssd, cnt = parts[:W], parts[W:]
+        with np.errstate(all="ignore"):
+            out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
+            if sqrt:
+                out = np.sqrt(out)
+        return pandas.Series(out, index=mean.columns, dtype="float64")
+
+    def var(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+        """Reduced result as a host ``pandas.Series`` (W numbers; identical on every rank)."""
+        return self._var(axis, skipna, ddof, numeric_only, sqrt=False)
+
+    def std(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+        return self._var(axis, skipna, ddof, numeric_only, sqrt=True)
 
     # ---- GroupByReduce (qc.py:3741-3748; impl table storage_formats/pandas/groupby.py:237-248) ------
     groupby_sum = GroupByReduce.register(DevGroupbyMap("sum"), DevGroupbyReduce("sum"))

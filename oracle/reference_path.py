@@ -253,3 +253,32 @@ def broadcast_merge(left, right, on: str, how: str, npartitions: int, threads: i
 
 def cpu_threads() -> int:
     return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------ more Map / Reduce registrations
+def df_round(df, decimals, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """qc.round = Map.register(pandas.DataFrame.round) (query_compiler.py:2438)."""
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), lambda b: b.round(decimals), threads))
+
+
+def df_clip(df, lower, upper, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+    """qc.clip = Map.register(pandas.DataFrame.clip) with scalar bounds."""
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), lambda b: b.clip(lower, upper), threads))
+
+
+def reduce_full_axis(df, func: Callable, npartitions: int):
+    """Reduce.register(func) (alg/reduce.py; query_compiler.py:1152-1153 for var / std): the function runs on
+    whole COLUMN partitions (every row block of a column partition concatenated), so the result does not depend
+    on the row partitioning -- only the column grid is restated here."""
+    grid = split_into_partitions(df, npartitions)
+    ncol_parts = len(grid[0]) if grid else 0
+    outs = [func(pandas.concat([row[j] for row in grid], axis=0)) for j in range(ncol_parts)]
+    return pandas.concat(outs) if outs else pandas.Series(dtype="float64")
+
+
+def df_var(df, npartitions: int, ddof: int = 1, skipna: bool = True):
+    return reduce_full_axis(df, lambda x: x.var(axis=0, ddof=ddof, skipna=skipna), npartitions)
+
+
+def df_std(df, npartitions: int, ddof: int = 1, skipna: bool = True):
+    return reduce_full_axis(df, lambda x: x.std(axis=0, ddof=ddof, skipna=skipna), npartitions)

@@ -49,6 +49,8 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
                 "div_s": lambda: x / np.float64(p), "rdiv_s": lambda: np.float64(p) / x,
                 "eq_s": lambda: x == p, "ne_s": lambda: x != p, "lt_s": lambda: x < p, "le_s": lambda: x <= p,
                 "gt_s": lambda: x > p, "ge_s": lambda: x >= p, "copy": lambda: x.copy(),
+                "clip_s": lambda: np.where(x < p, p, np.where(x > q, q, x)).astype(x.dtype),
+                "round_s": lambda: (np.rint(x * p) / p if q >= 0 else np.rint(x / p) * p) if x.dtype == np.float64 else x,
                 "add": lambda: x + y, "sub": lambda: x - y, "mul": lambda: x * y, "div": lambda: x / y,
                 "eq": lambda: x == y, "ne": lambda: x != y, "lt": lambda: x < y, "le": lambda: x <= y,
                 "gt": lambda: x > y, "ge": lambda: x >= y, "fillna": lambda: np.where(np.isnan(x), y, x),
@@ -60,10 +62,17 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
     return out
 
 
-def reduce_columns(op, cols, skipna=True, variant=0):
+def reduce_columns(op, cols, skipna=True, variant=0, centers=None):
     vals, cnts = [], []
-    for c in cols:
+    for j, c in enumerate(cols):
         x = _np(c)
+        if op == "ssd":
+            ok = ~np.isnan(x)
+            with np.errstate(all="ignore"):
+                d = float(centers[j]) - (x[ok] if skipna else x)
+                vals.append(torch.tensor([np.sum(d * d)], dtype=torch.float64))
+            cnts.append(torch.tensor([int(ok.sum())], dtype=torch.int64))
+            continue
         if c.dtype == np.int64:
             n = len(x)
             v = {"sum": x.sum() if n else 0, "min": x.min() if n else np.iinfo(np.int64).max,

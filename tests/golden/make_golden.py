@@ -102,6 +102,32 @@ def main():
         save(tag + "_fma3", meta=np.array([n, W, 42, nan, 7, 9]), out=P(mdf * mb + mc).to_numpy(),
              sub=P(mdf - mb).to_numpy(), div=P(mdf / mb).to_numpy(), ge=P(mdf >= mb).to_numpy())
 
+    # ---- more registrations: prod, var / std, round, clip; groupby min / max
+    for n, W, nan in ((3001, 4, 1500),):
+        pdf = synth.host_frame(n, W, seed=77, nan_per_64k=nan)
+        mdf = mpd.DataFrame(pdf)
+        small = mpd.DataFrame(pdf.iloc[:60] * 1.25)
+        save(
+            f"ext_n{n}_w{W}_nan{nan}",
+            meta=np.array([n, W, 77, nan]),
+            prod60=P(small.prod()).to_numpy(),
+            var=P(mdf.var()).to_numpy(),
+            var_ddof0=P(mdf.var(ddof=0)).to_numpy(),
+            std=P(mdf.std()).to_numpy(),
+            var_noskip=P(mdf.var(skipna=False)).to_numpy(),
+            round2=P(mdf.round(2)).to_numpy(),
+            round0=P(mdf.round(0)).to_numpy(),
+            round_m1=P((mdf * 100.0).round(-1)).to_numpy(),
+            clip=P(mdf.clip(-0.5, 0.75)).to_numpy(),
+            clip_lower=P(mdf.clip(lower=0.0)).to_numpy(),
+        )
+    for n, G, V, nan in ((7001, 97, 3, 4000),):
+        pdf = synth.host_frame(n, V, seed=42, nan_per_64k=nan, key_modulus=G, key_seed=43)
+        g = mpd.DataFrame(pdf).groupby("key")
+        mn, mx = P(g.min()), P(g.max())
+        save(f"ext_groupby_n{n}_g{G}_v{V}_nan{nan}", meta=np.array([n, G, V, nan, 42, 43]), keys=mn.index.to_numpy(),
+             min=mn.to_numpy(), max=mx.to_numpy())
+
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):
         pdf = synth.host_frame(n, V, seed=42, nan_per_64k=nan, key_modulus=G, key_seed=43)

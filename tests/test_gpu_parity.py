@@ -435,3 +435,39 @@ def test_large_scale_invariants(gb_table_kind):
         assert_exact(out.iloc[rows, j].to_numpy(), ref, f"sampled affine col {j}")
     mean = vals.mean().to_numpy()
     assert np.all(np.abs(mean - col_sum / n) <= 1e-15 + 4 * EPS * col_abs / n)
+
+
+def test_more_registrations_vs_reference_golden(golden_dir):
+    """round / clip (bit-exact), var / std (two device passes; relative 1e-12 against the reference's
+    two-pass nanvar), prod, groupby min / max (bit-exact) -- golden vectors from the unmodified reference."""
+    m = bpd()
+    for name, z in _load(golden_dir, "ext_n*.npz"):
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        df = m.DataFrame(pdf)
+        assert_exact(df.round(2)._to_pandas().to_numpy(), z["round2"], f"{name}:round(2)")
+        assert_exact(df.round(0)._to_pandas().to_numpy(), z["round0"], f"{name}:round(0)")
+        assert_exact((df * 100.0).round(-1)._to_pandas().to_numpy(), z["round_m1"], f"{name}:round(-1)")
+        assert_exact(df.clip(-0.5, 0.75)._to_pandas().to_numpy(), z["clip"], f"{name}:clip")
+        assert_exact(df.clip(lower=0.0)._to_pandas().to_numpy(), z["clip_lower"], f"{name}:clip lower")
+        for got, key in ((df.var(), "var"), (df.var(ddof=0), "var_ddof0"), (df.std(), "std")):
+            assert isinstance(got, pandas.Series) and list(got.index) == list(pdf.columns)
+            assert np.allclose(got.to_numpy(), z[key], rtol=1e-12, atol=0), f"{name}:{key}"
+        assert np.isnan(df.var(skipna=False).to_numpy()).all() and np.isnan(z["var_noskip"]).all()
+        small = m.DataFrame(pdf.iloc[:60] * 1.25)
+        assert np.allclose(small.prod().to_numpy(), z["prod60"], rtol=1e-12, atol=0), f"{name}:prod"
+    for name, z in _load(golden_dir, "ext_groupby_*.npz"):
+        n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, V, seed=seed, nan_per_64k=nan, key_modulus=G, key_seed=kseed)
+        g = m.DataFrame(pdf).groupby("key")
+        for agg in ("min", "max"):
+            got = getattr(g, agg)()._to_pandas()
+            assert_exact(got.index.to_numpy(), z["keys"], f"{name}:{agg} keys")
+            assert_exact(got.to_numpy(), z[agg], f"{name}:{agg}")
+    # int64 columns: round(d >= 0) is the identity, clip stays int64, var promotes to float64
+    ipdf = pandas.DataFrame({"a": np.arange(-50, 50, dtype=np.int64), "b": (np.arange(100, dtype=np.int64) * 7) % 13})
+    idf = m.DataFrame(ipdf)
+    assert_exact(idf.round(1)._to_pandas().to_numpy(), ipdf.round(1).to_numpy(), "int round")
+    assert_exact(idf.clip(-3, 9)._to_pandas().to_numpy(), ipdf.clip(-3, 9).to_numpy(), "int clip")
+    assert np.allclose(idf.var().to_numpy(), ipdf.var().to_numpy(), rtol=1e-12)
+    assert np.allclose(idf.std(ddof=0).to_numpy(), ipdf.std(ddof=0).to_numpy(), rtol=1e-12)

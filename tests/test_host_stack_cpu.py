@@ -151,3 +151,27 @@ def test_series_operands_both_axes(cpu_device):
     rowvec = pandas.Series([1.0, -2.0, 0.5], index=pdf.columns)
     assert _same((df + bpd.Series(rowvec))._to_pandas().to_numpy(), (pdf + rowvec).to_numpy())
     assert np.isclose(ser.sum(), col.sum()) and ser.count() == 900
+
+
+def test_round_clip_var_std_through_the_api(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(2003, 4, seed=8, nan_per_64k=3000)
+    df = bpd.DataFrame(pdf)
+    assert _same(df.round(2)._to_pandas().to_numpy(), orc.df_round(pdf, 2, 4).to_numpy())
+    assert _same((df * 100.0).round(-1)._to_pandas().to_numpy(), orc.df_round(pdf * 100.0, -1, 4).to_numpy())
+    assert _same(df.clip(-0.5, 0.75)._to_pandas().to_numpy(), orc.df_clip(pdf, -0.5, 0.75, 4).to_numpy())
+    assert _same(df.clip(upper=0.1)._to_pandas().to_numpy(), orc.df_clip(pdf, None, 0.1, 4).to_numpy())
+    for ddof in (0, 1):
+        assert np.allclose(df.var(ddof=ddof).to_numpy(), orc.df_var(pdf, 4, ddof=ddof).to_numpy(), rtol=1e-12, atol=0)
+        assert np.allclose(df.std(ddof=ddof).to_numpy(), orc.df_std(pdf, 4, ddof=ddof).to_numpy(), rtol=1e-12, atol=0)
+    assert np.isnan(df.var(skipna=False).to_numpy()).all()
+    v = df.var()
+    assert isinstance(v, pandas.Series) and list(v.index) == list(pdf.columns) and v.name is None
+    assert np.isclose(df["c1"].std(), pdf["c1"].std(), rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        df.round(1.5)
+    with pytest.raises(NotImplementedError):
+        df.clip(lower=[1, 2, 3, 4])
+    with pytest.raises(NotImplementedError):
+        df.var(axis=1)

@@ -133,3 +133,27 @@ def test_partition_grid_matches_reference_rule():
     assert orc.compute_chunksize(100, 8, 32) == 32
     grid = orc.split_into_partitions(synth.host_frame(1000, 4), 4)
     assert [len(r[0]) for r in grid] == [250, 250, 250, 250] and all(len(r) == 1 for r in grid)
+
+
+def test_more_registrations_against_reference(golden_dir):
+    """prod, var / std (full-axis Reduce), round, clip, groupby min / max -- pinned to the reference bit for bit."""
+    for name, z in _load(golden_dir, "ext_n*.npz"):
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        assert_bit_equal(orc.df_prod(df.iloc[:60] * 1.25, NP).to_numpy(), z["prod60"], f"{name}:prod")
+        assert_bit_equal(orc.df_var(df, NP).to_numpy(), z["var"], f"{name}:var")
+        assert_bit_equal(orc.df_var(df, NP, ddof=0).to_numpy(), z["var_ddof0"], f"{name}:var ddof=0")
+        assert_bit_equal(orc.df_std(df, NP).to_numpy(), z["std"], f"{name}:std")
+        assert_bit_equal(orc.df_var(df, NP, skipna=False).to_numpy(), z["var_noskip"], f"{name}:var skipna=False")
+        assert_bit_equal(orc.df_round(df, 2, NP).to_numpy(), z["round2"], f"{name}:round(2)")
+        assert_bit_equal(orc.df_round(df, 0, NP).to_numpy(), z["round0"], f"{name}:round(0)")
+        assert_bit_equal(orc.df_round(df * 100.0, -1, NP).to_numpy(), z["round_m1"], f"{name}:round(-1)")
+        assert_bit_equal(orc.df_clip(df, -0.5, 0.75, NP).to_numpy(), z["clip"], f"{name}:clip")
+        assert_bit_equal(orc.df_clip(df, 0.0, None, NP).to_numpy(), z["clip_lower"], f"{name}:clip lower")
+    for name, z in _load(golden_dir, "ext_groupby_*.npz"):
+        n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, V, seed=seed, nan_per_64k=nan, key_modulus=G, key_seed=kseed)
+        for agg in ("min", "max"):
+            got = orc.groupby_reduce(df, "key", agg, NP)
+            assert_bit_equal(got.index.to_numpy(), z["keys"], f"{name}:{agg} keys")
+            assert_bit_equal(got.to_numpy(), z[agg], f"{name}:{agg}")
