@@ -170,6 +170,8 @@ def register(shims: bool | None = None):
         negative = Map.register(fx.DevMap("neg"), dtypes="copy")
         isna = Map.register(fx.DevMap("isna"), dtypes=np.bool_)
         notna = Map.register(fx.DevMap("notna"), dtypes=np.bool_)
+        round = Map.register(fx.DevRound(), dtypes="copy")  # qc.py:2438
+        clip = Map.register(fx.DevClip(), dtypes="copy")
         # Binary (qc.py:535-624)
         add = Binary.register(fx.DevBinary("add"), infer_dtypes="common_cast")
         radd = Binary.register(fx.DevBinary("radd"), infer_dtypes="common_cast")
@@ -192,6 +194,7 @@ def register(shims: bool | None = None):
         max = TreeReduce.register(fx.DevReduce("max"), fx.DevReduce("max", phase="reduce"))
         min = TreeReduce.register(fx.DevReduce("min"), fx.DevReduce("min", phase="reduce"))
         mean = TreeReduce.register(fx.DevMeanMap(), fx.DevMeanReduce(), compute_dtypes=_f64)
+        prod = TreeReduce.register(fx.DevReduce("prod"), fx.DevReduce("prod", phase="reduce"), compute_dtypes=_dtypes_sum)
         # GroupByReduce (qc.py:3741-3748)
         groupby_sum = B200GroupByReduce.register_agg("sum")
         groupby_count = B200GroupByReduce.register_agg("count")

@@ -383,7 +383,53 @@ class DataFrameGroupBy:
     def agg(self, func, *args, **kwargs):
         if isinstance(func, str) and func in ("sum", "count", "mean", "size", "min", "max"):
             return getattr(self, func)()
+        if isinstance(func, dict):
+            return self._dict_agg(func)
         raise NotImplementedError(f"groupby.agg({func!r}) is not on the B200 path")
+
+    def _dict_agg(self, spec):
+        """``groupby(key).agg({column: function})`` -- qc._groupby_dict_reduce (qc.py:3876-3970) splits a dictionary
+        aggregation into per-function map / reduce tables.  Here: one device aggregation per distinct function over
+        the columns that ask for it; every result has the same ascending keys, so the result blocks are zipped
+        column-wise on the device (buffers shared, nothing copied) in the dictionary's order."""
+        from ..block import DeviceBlock
+        from ..dataframe import B200Dataframe
+
+        if not self._drop:
+            raise NotImplementedError("dictionary aggregation needs the key column inside the frame")
+        key = self._by.columns[0]
+        by_func = {}
+        for col, fn in spec.items():
+            if not isinstance(fn, str) or fn not in ("sum", "count", "mean", "min", "max"):
+                raise NotImplementedError(f"groupby.agg({{{col!r}: {fn!r}}}) is not on the B200 path")
+            if col not in self._df.columns or col == key:
+                raise KeyError(col)
+            by_func.setdefault(fn, []).append(col)
+        where = {}
+        frames = []
+        for fn, cols in by_func.items():
+            res = getattr(self._df[[key] + cols].groupby(key, **{k: v for k, v in self._kwargs.items() if k != "level"}), fn)()
+            frame = res._query_compiler._modin_frame
+            if frame._partitions.shape[1] != 1:
+                raise NotImplementedError("dictionary aggregation over more than 32 columns per function")
+            for j, c in enumerate(cols):
+                where[c] = (len(frames), j)
+            frames.append(frame)
+        nparts = {f._partitions.shape[0] for f in frames}
+        if len(nparts) != 1:
+            raise NotImplementedError("per-function results are partitioned differently")
+        blocks = []
+        for i in range(nparts.pop()):
+            blks = [f._partitions[i, 0].get() for f in frames]
+            if len({b.nrows for b in blks}) != 1:
+                raise NotImplementedError("per-function results are partitioned differently")
+            cols = [blks[where[c][0]].cols[where[c][1]] for c in spec]
+            nb = DeviceBlock(cols, pandas.Index(list(spec)), nrows=blks[0].nrows, index_cols=blks[0].index_cols,
+                             index_names=blks[0].index_names)  # fmt: skip
+            nb.keys_sorted_unique = True
+            blocks.append(nb)
+        qc = type(self._query_compiler)(B200Dataframe.from_blocks(blocks))
+        return DataFrame(query_compiler=qc)
 
     aggregate = agg
 

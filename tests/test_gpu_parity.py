@@ -471,3 +471,18 @@ def test_more_registrations_vs_reference_golden(golden_dir):
     assert_exact(idf.clip(-3, 9)._to_pandas().to_numpy(), ipdf.clip(-3, 9).to_numpy(), "int clip")
     assert np.allclose(idf.var().to_numpy(), ipdf.var().to_numpy(), rtol=1e-12)
     assert np.allclose(idf.std(ddof=0).to_numpy(), ipdf.std(ddof=0).to_numpy(), rtol=1e-12)
+
+
+def test_groupby_dictionary_aggregation(gb_table_kind):
+    """qc._groupby_dict_reduce (qc.py:3876-3970): per-column functions; results zipped on the device."""
+    m = bpd()
+    pdf = synth.host_frame(30_011, 4, seed=5, nan_per_64k=2500, key_modulus=4099)
+    spec = {"c2": "max", "c0": "sum", "c3": "count", "c1": "min"}
+    got = m.DataFrame(pdf).groupby("key").agg(spec)._to_pandas()
+    want = pdf.groupby("key").agg(spec)
+    assert list(got.columns) == list(want.columns)
+    assert_exact(got.index.to_numpy(), want.index.to_numpy(), "keys")
+    for c in ("c2", "c3", "c1"):
+        assert_exact(got[c].to_numpy(dtype=np.float64), want[c].to_numpy(dtype=np.float64), f"dict agg {c}")
+    abs0 = pdf["c0"].abs().groupby(pdf["key"]).sum().to_numpy()
+    assert_sum_close(got["c0"].to_numpy(), want["c0"].to_numpy(), abs0, len(pdf), "dict agg sum")

@@ -175,3 +175,23 @@ def test_round_clip_var_std_through_the_api(cpu_device):
         df.clip(lower=[1, 2, 3, 4])
     with pytest.raises(NotImplementedError):
         df.var(axis=1)
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_groupby_dictionary_aggregation(cpu_device, dense):
+    import modin_b200.pandas as bpd
+
+    config.GroupbyDenseKeys.put(dense)
+    try:
+        pdf = synth.host_frame(4001, 4, seed=5, nan_per_64k=2500, key_modulus=53)
+        spec = {"c2": "max", "c0": "sum", "c3": "count", "c1": "sum"}
+        got = bpd.DataFrame(pdf).groupby("key").agg(spec)._to_pandas()
+        want = pdf.groupby("key").agg(spec)
+        assert list(got.columns) == list(want.columns) and list(got.index) == list(want.index) and got.index.name == "key"
+        assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True)
+        with pytest.raises(NotImplementedError):
+            bpd.DataFrame(pdf).groupby("key").agg({"c0": "median"})
+        with pytest.raises(KeyError):
+            bpd.DataFrame(pdf).groupby("key").agg({"nope": "sum"})
+    finally:
+        config.GroupbyDenseKeys.put(True)

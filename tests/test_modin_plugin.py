@@ -72,6 +72,9 @@ def _scenarios(mpd, ns):
     assert _same(P(-mdf).to_numpy(), (-vals).to_numpy())
     assert _same(P(mdf.isna()).to_numpy().astype(float), vals.isna().to_numpy().astype(float))
     assert _same(P(mdf.fillna(2.0)).to_numpy(), orc.df_fillna(vals, 2.0, 4).to_numpy())
+    assert _same(P(mdf.round(2)).to_numpy(), orc.df_round(vals, 2, 4).to_numpy())
+    assert _same(P(mdf.clip(-0.5, 0.75)).to_numpy(), orc.df_clip(vals, -0.5, 0.75, 4).to_numpy())
+    assert np.allclose(P(mdf.prod()).to_numpy(), orc.df_prod(vals, 4).to_numpy(), rtol=1e-9, atol=0, equal_nan=True)
     other = synth.host_frame(2003, 4, seed=12)
     mo = mpd.DataFrame(other)
     assert _same(P(mdf * mo + mo).to_numpy(), orc.a_mul_b_add_c(vals, other, other, 4).to_numpy())
