@@ -5,6 +5,7 @@
 // mb200_map, and copied back D2H, with the three stages overlapped on three streams over a
 // ring of device staging buffers.  PCIe-bound by construction (8 B in + 8 B out per element);
 // pinned host buffers (mb200_alloc_host) make the copies truly asynchronous.
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -52,32 +53,55 @@ extern "C" int mb200_map_host(int op, int dtype, int ncols, const void* const* i
 
   DevProps dp;
   if (int rc = dev_props(&dp)) return rc;
-  Pipe pp;
-  MB_CUDA(cudaStreamCreateWithFlags(&pp.s_in, cudaStreamNonBlocking));
-  MB_CUDA(cudaStreamCreateWithFlags(&pp.s_k, cudaStreamNonBlocking));
-  MB_CUDA(cudaStreamCreateWithFlags(&pp.s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < kRing; ++i) {
-    MB_CUDA(cudaEventCreateWithFlags(&pp.ev_in[i], cudaEventDisableTiming));
-    MB_CUDA(cudaEventCreateWithFlags(&pp.ev_k[i], cudaEventDisableTiming));
-    MB_CUDA(cudaEventCreateWithFlags(&pp.ev_out[i], cudaEventDisableTiming));
-  }
-  // staging: ring x (nin inputs + 1 output) x ncols columns
-  void* d_in[kRing][3][MB200_MAX_COLS];
-  void* d_out[kRing][MB200_MAX_COLS];
-  for (int r = 0; r < kRing; ++r) {
-    for (int c = 0; c < ncols; ++c) {
-      for (int k = 0; k < nin; ++k) {
-        void* p = nullptr;
-        MB_CUDA(cudaMalloc(&p, (size_t)chunk_rows * in_es));
-        pp.dev.push_back(p);
-        d_in[r][k][c] = p;
-      }
-      void* p = nullptr;
-      MB_CUDA(cudaMalloc(&p, (size_t)chunk_rows * out_es));
-      pp.dev.push_back(p);
-      d_out[r][c] = p;
+  // The pipe (3 streams, 9 events, ring x (nin + 1) x ncols staging buffers -- 1.5 GB at the default chunk size
+  // and 8 columns) is kept between calls with the same shape: allocating and freeing it costs more than a chunk.
+  struct Cached {
+    std::unique_ptr<Pipe> pipe;
+    int dev = -1, ncols = 0, nin = 0;
+    long long chunk_rows = 0;
+    size_t out_es = 0;
+    void* d_in[kRing][3][MB200_MAX_COLS];
+    void* d_out[kRing][MB200_MAX_COLS];
+  };
+  static thread_local Cached cache;
+  int dev = 0;
+  MB_CUDA(cudaGetDevice(&dev));
+  if (!cache.pipe || cache.dev != dev || cache.ncols != ncols || cache.nin != nin || cache.chunk_rows != chunk_rows ||
+      cache.out_es != out_es) {
+    cache.pipe.reset();  // frees the previous staging buffers first
+    std::unique_ptr<Pipe> np(new Pipe());
+    MB_CUDA(cudaStreamCreateWithFlags(&np->s_in, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&np->s_k, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&np->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kRing; ++i) {
+      MB_CUDA(cudaEventCreateWithFlags(&np->ev_in[i], cudaEventDisableTiming));
+      MB_CUDA(cudaEventCreateWithFlags(&np->ev_k[i], cudaEventDisableTiming));
+      MB_CUDA(cudaEventCreateWithFlags(&np->ev_out[i], cudaEventDisableTiming));
     }
+    for (int r = 0; r < kRing; ++r) {
+      for (int c = 0; c < ncols; ++c) {
+        for (int k = 0; k < nin; ++k) {
+          void* p = nullptr;
+          MB_CUDA(cudaMalloc(&p, (size_t)chunk_rows * in_es));
+          np->dev.push_back(p);
+          cache.d_in[r][k][c] = p;
+        }
+        void* p = nullptr;
+        MB_CUDA(cudaMalloc(&p, (size_t)chunk_rows * out_es));
+        np->dev.push_back(p);
+        cache.d_out[r][c] = p;
+      }
+    }
+    cache.pipe = std::move(np);
+    cache.dev = dev;
+    cache.ncols = ncols;
+    cache.nin = nin;
+    cache.chunk_rows = chunk_rows;
+    cache.out_es = out_es;
   }
+  Pipe& pp = *cache.pipe;
+  auto& d_in = cache.d_in;
+  auto& d_out = cache.d_out;
   const void* const* hin[3] = {in0_host, in1_host, in2_host};
   const long long nchunks = (nrows + chunk_rows - 1) / chunk_rows;
   for (long long j = 0; j < nchunks; ++j) {
