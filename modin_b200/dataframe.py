@@ -195,6 +195,34 @@ class B200Dataframe:
         return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
 
     # ---- Binary -----------------------------------------------------------------------------------
+    def _repartition_rows(self, lengths: List[int]) -> "B200Dataframe":
+        """Same rows, cut at ``lengths`` instead of ``self.row_lengths`` (the row half of ``_copartition``,
+        df.py:3799-3840, without a reindex): target partitions inside one source partition are views of its
+        buffers; a target partition that spans several sources is a device-to-device concatenation."""
+        from .block import concat_rows
+
+        src_bounds = np.cumsum([0] + list(self.row_lengths))
+        ncolparts = self._partitions.shape[1] if self._partitions.size else 0
+        pc = self._partition_mgr_cls._partition_class
+        new_rows, pos = [], 0
+        for L in lengths:
+            lo, hi = pos, pos + int(L)
+            row = []
+            for j in range(ncolparts):
+                pieces = []
+                for i in range(len(self.row_lengths)):
+                    a, b = max(lo, int(src_bounds[i])), min(hi, int(src_bounds[i + 1]))
+                    if b > a:
+                        pieces.append(self._partitions[i, j].get().slice_rows(a - int(src_bounds[i]), b - int(src_bounds[i])))
+                if not pieces:  # empty target partition
+                    pieces = [self._partitions[0, j].get().slice_rows(0, 0)]
+                row.append(pc(concat_rows(pieces) if len(pieces) > 1 else pieces[0]))
+            new_rows.append(row)
+            pos = hi
+        parts = np.array(new_rows, dtype=object).reshape(len(lengths), ncolparts)
+        return self.__constructor__(parts, self._index_cache, self._columns_cache, list(lengths), self._column_widths_cache,
+                                    self._dtypes)  # fmt: skip
+
     def _check_if_axes_identical(self, other: "B200Dataframe", axis: int = 0) -> bool:
         """df.py:3678-3707."""
         if axis == 0:
@@ -206,14 +234,22 @@ class B200Dataframe:
         """df.py:3851-3950, fast path only: operands must already be co-partitioned (identical labels
         and partition lengths, df.py:3750-3758 -- no data movement).  The general ``_copartition``
         reindex (df.py:3799-3840) is a "next" row."""
+        aligned = []
         for other in right_frames:
             if not (self._check_if_axes_identical(other, 0) and self._check_if_axes_identical(other, 1)):
-                raise NotImplementedError(
-                    "binary op between differently partitioned / labelled frames needs _copartition, "
-                    "which is not on the B200 path yet"
-                )
+                # the part of _copartition (df.py:3709-3848) that needs no reindex: same labels, same column
+                # grid, only the row partition lengths differ -> re-cut the right operand along the left's cuts
+                if (self.columns.equals(other.columns) and self.column_widths == other.column_widths
+                        and sum(self.row_lengths) == sum(other.row_lengths) and self.index.equals(other.index)):  # fmt: skip
+                    other = other._repartition_rows(self.row_lengths)
+                else:
+                    raise NotImplementedError(
+                        "binary op between differently labelled frames needs the reindexing half of _copartition, "
+                        "which is not on the B200 path"
+                    )
+            aligned.append(other)
         new_frame = self._partition_mgr_cls.n_ary_operation(
-            self._partitions, op, [other._partitions for other in right_frames]
+            self._partitions, op, [other._partitions for other in aligned]
         )
         return self.__constructor__(new_frame, self._index_cache, self._columns_cache, self._row_lengths_cache,
                                     self._column_widths_cache, dtypes)  # fmt: skip

@@ -486,3 +486,19 @@ def test_groupby_dictionary_aggregation(gb_table_kind):
         assert_exact(got[c].to_numpy(dtype=np.float64), want[c].to_numpy(dtype=np.float64), f"dict agg {c}")
     abs0 = pdf["c0"].abs().groupby(pdf["key"]).sum().to_numpy()
     assert_sum_close(got["c0"].to_numpy(), want["c0"].to_numpy(), abs0, len(pdf), "dict agg sum")
+
+
+def test_binary_ops_between_differently_partitioned_frames():
+    """Row half of _copartition: the right operand is re-cut along the left's partition lengths; the re-cut
+    blocks are unaligned views (odd row offsets), which exercises the kernels' scalar-load fallback."""
+    from modin_b200 import config
+
+    m = bpd()
+    a, b = synth.host_frame(100_003, 3, seed=1), synth.host_frame(100_003, 3, seed=2, nan_per_64k=5000)
+    A = m.DataFrame(a)
+    config.NPartitions.put(3)
+    B = m.DataFrame(b)
+    config.NPartitions.put(4)
+    assert_exact((A * B + B)._to_pandas().to_numpy(), (a * b + b).to_numpy(), "a*b+b re-cut")
+    assert_exact((B - A)._to_pandas().to_numpy(), (b - a).to_numpy(), "b-a re-cut")
+    assert_exact((A >= B)._to_pandas().to_numpy(), (a >= b).to_numpy(), "a>=b re-cut")

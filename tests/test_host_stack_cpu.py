@@ -195,3 +195,26 @@ def test_groupby_dictionary_aggregation(cpu_device, dense):
             bpd.DataFrame(pdf).groupby("key").agg({"nope": "sum"})
     finally:
         config.GroupbyDenseKeys.put(True)
+
+
+def test_binary_ops_between_differently_partitioned_frames(cpu_device):
+    """The row half of _copartition (df.py:3709-3848): same labels, different row cuts -> the right operand is
+    re-cut along the left's partition lengths (views, or a D2D concat where a target spans several sources)."""
+    import modin_b200.pandas as bpd
+
+    a, b = synth.host_frame(1001, 3, seed=1), synth.host_frame(1001, 3, seed=2, nan_per_64k=5000)
+    A = bpd.DataFrame(a)  # 4 row partitions
+    config.NPartitions.put(3)
+    B = bpd.DataFrame(b)  # 3 row partitions
+    config.NPartitions.put(4)
+    fa, fb = A._query_compiler._modin_frame, B._query_compiler._modin_frame
+    assert fa.row_lengths != fb.row_lengths and sum(fa.row_lengths) == sum(fb.row_lengths)
+    out = A * B + B
+    assert out._query_compiler._modin_frame.row_lengths == fa.row_lengths
+    assert _same(out._to_pandas().to_numpy(), (a * b + b).to_numpy())
+    assert _same((B - A)._to_pandas().to_numpy(), (b - a).to_numpy())  # and the other way round (3 cuts)
+    assert _same((A >= B)._to_pandas().to_numpy(), (a >= b).to_numpy())
+    re = fb._repartition_rows([0, 1001])  # empty partitions are filtered by the frame constructor, as in Modin
+    assert sum(re.row_lengths) == 1001 and _same(re.to_pandas().to_numpy(), b.to_numpy())
+    re = fb._repartition_rows([1, 500, 500])
+    assert re.row_lengths == [1, 500, 500] and _same(re.to_pandas().to_numpy(), b.to_numpy())
