@@ -436,3 +436,53 @@ class DataFrameGroupBy:
 
 def concat(*args, **kwargs):  # pragma: no cover - signature placeholder
     raise NotImplementedError("concat is not on the B200 path")
+
+
+# ---- zero-copy interchange with other GPU libraries (DLPack; the reference's wire format for
+# this is the dataframe interchange protocol, df.py:4803-4867, whose buffers also export __dlpack__) -------------
+def from_dlpack(columns: dict, range_start: int = 0) -> DataFrame:
+    """Frame over device buffers owned by another library: ``{label: object with __dlpack__ (or a torch tensor)}``,
+    1-D contiguous float64 / int64 / bool of equal length on this process's GPU.  Nothing is copied; the frame is
+    ONE row partition (this rank's shard under torchrun)."""
+    import torch
+
+    from ..block import DeviceBlock, DeviceColumn, current_device
+    from ..dataframe import B200Dataframe
+
+    dev = current_device()
+    cols, labels, n = [], [], None
+    for label, obj in columns.items():
+        ten = obj if isinstance(obj, torch.Tensor) else torch.from_dlpack(obj)
+        if ten.dim() != 1 or not ten.is_contiguous():
+            raise ValueError(f"column {label!r}: need a 1-D contiguous buffer")
+        if ten.device != dev:
+            raise ValueError(f"column {label!r} lives on {ten.device}, this process computes on {dev}")
+        np_dtype = {torch.float64: np.float64, torch.int64: np.int64, torch.bool: np.bool_, torch.uint8: np.bool_}.get(ten.dtype)
+        if np_dtype is None:
+            raise TypeError(f"column {label!r}: dtype {ten.dtype} is not on the B200 path (float64 / int64 / bool)")
+        if ten.dtype == torch.bool:
+            ten = ten.view(torch.uint8)
+        if n is None:
+            n = ten.shape[0]
+        elif ten.shape[0] != n:
+            raise ValueError("columns of different lengths")
+        cols.append(DeviceColumn(ten, np.dtype(np_dtype)))
+        labels.append(label)
+    block = DeviceBlock(cols, pandas.Index(labels), nrows=n or 0, range_start=range_start)
+    return DataFrame(query_compiler=B200QueryCompiler(B200Dataframe.from_blocks([block])))
+
+
+def to_dlpack(df: DataFrame) -> dict:
+    """``{label: torch tensor}`` views of the frame's device buffers (each exports ``__dlpack__``).  Zero-copy
+    for a frame with one row partition; several row partitions are concatenated on the device first."""
+    from ..block import concat_cols, concat_rows
+
+    frame = df._query_compiler._modin_frame
+    rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in frame._partitions]
+    block = concat_rows(rows) if len(rows) > 1 else rows[0]
+    import torch
+
+    out = {}
+    for label, c in zip(block.columns, block.cols):
+        out[label] = c.data.view(torch.bool) if c.dtype == np.bool_ else c.data
+    return out

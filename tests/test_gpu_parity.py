@@ -502,3 +502,20 @@ def test_binary_ops_between_differently_partitioned_frames():
     assert_exact((A * B + B)._to_pandas().to_numpy(), (a * b + b).to_numpy(), "a*b+b re-cut")
     assert_exact((B - A)._to_pandas().to_numpy(), (b - a).to_numpy(), "b-a re-cut")
     assert_exact((A >= B)._to_pandas().to_numpy(), (a >= b).to_numpy(), "a>=b re-cut")
+
+
+def test_dlpack_interchange_is_zero_copy_on_device():
+    import torch
+
+    m = bpd()
+    x = torch.randn(100_000, dtype=torch.float64, device="cuda")
+    k = (torch.arange(100_000, device="cuda") % 7).to(torch.int64)
+    df = m.from_dlpack({"x": x, "key": k})
+    v = m.to_dlpack(df)
+    assert v["x"].data_ptr() == x.data_ptr() and v["key"].data_ptr() == k.data_ptr()
+    got = df.groupby("key").sum()._to_pandas()
+    want = pandas.DataFrame({"x": x.cpu().numpy(), "key": k.cpu().numpy()}).groupby("key").sum()
+    assert_exact(got.index.to_numpy(), want.index.to_numpy(), "keys")
+    assert np.allclose(got.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9)
+    y = torch.from_dlpack(m.to_dlpack(df[["x"]] * 2.0)["x"])  # a consumer on the same device, no host round trip
+    assert torch.equal(y, x * 2.0)

@@ -218,3 +218,25 @@ def test_binary_ops_between_differently_partitioned_frames(cpu_device):
     assert sum(re.row_lengths) == 1001 and _same(re.to_pandas().to_numpy(), b.to_numpy())
     re = fb._repartition_rows([1, 500, 500])
     assert re.row_lengths == [1, 500, 500] and _same(re.to_pandas().to_numpy(), b.to_numpy())
+
+
+def test_dlpack_interchange_is_zero_copy(cpu_device):
+    import torch
+
+    import modin_b200.pandas as bpd
+
+    a = torch.arange(10, dtype=torch.float64)
+    k = torch.arange(10, dtype=torch.int64) % 3
+    df = bpd.from_dlpack({"x": a, "key": k})
+    assert list(df.columns) == ["x", "key"] and len(df) == 10
+    views = bpd.to_dlpack(df)
+    assert views["x"].data_ptr() == a.data_ptr() and views["key"].data_ptr() == k.data_ptr()  # no copy either way
+    assert _same((df[["x"]] * 2.0)._to_pandas().to_numpy().ravel(), (a * 2).numpy())
+    got = df.groupby("key").sum()._to_pandas()
+    assert list(got.index) == [0, 1, 2] and _same(got["x"].to_numpy(), [18.0, 12.0, 15.0])
+    out = bpd.to_dlpack(bpd.DataFrame(synth.host_frame(100, 2)))  # 4 row partitions -> one device concatenation
+    assert out["c0"].shape == (100,) and torch.from_dlpack(out["c1"]).shape == (100,)
+    with pytest.raises(TypeError):
+        bpd.from_dlpack({"x": torch.zeros(3, dtype=torch.float32)})
+    with pytest.raises(ValueError):
+        bpd.from_dlpack({"x": a, "y": torch.zeros(3, dtype=torch.float64)})
