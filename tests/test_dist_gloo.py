@@ -191,3 +191,39 @@ def test_full_stack_groupby_dense_and_exchange_paths_agree_with_the_oracle():
             w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
             assert np.allclose(vals, w, rtol=0, atol=1e-9, equal_nan=True), (dense, agg)
             assert all(len(o[(dense, agg)][0]) > 0 for o in out)
+
+
+def _full_stack_var_job(rank, ws):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(9_001, 3, seed=4, nan_per_64k=3000, key_modulus=31)
+        df = bpd.DataFrame(pdf)  # sharded by rank
+        vals = df[["c0", "c1", "c2"]]
+        spec = {"c1": "max", "c0": "sum", "c2": "count"}
+        agg = df.groupby("key").agg(spec)._query_compiler._modin_frame
+        blks = [p.get() for p in agg._partitions[:, 0]]
+        return (vals.var().to_numpy(), vals.std(ddof=0).to_numpy(), vals.mean().to_numpy(),
+                np.concatenate([b.index_cols[0].data.numpy() for b in blks]),
+                np.concatenate([np.stack([c.data.numpy().astype(np.float64) for c in b.cols], axis=1) for b in blks]))
+
+
+def test_full_stack_var_std_and_dict_agg_across_ranks():
+    out = _run(_full_stack_var_job)
+    pdf = synth.host_frame(9_001, 3, seed=4, nan_per_64k=3000, key_modulus=31)
+    vals = pdf[["c0", "c1", "c2"]]
+    for var, std0, mean, _, _ in out:  # replicated on every rank, equal to the whole-frame statistics
+        assert np.allclose(var, vals.var().to_numpy(), rtol=1e-12, atol=0)
+        assert np.allclose(std0, vals.std(ddof=0).to_numpy(), rtol=1e-12, atol=0)
+        assert np.allclose(mean, vals.mean().to_numpy(), rtol=1e-12, atol=0)
+    want = pdf.groupby("key").agg({"c1": "max", "c0": "sum", "c2": "count"})
+    keys = np.concatenate([o[3] for o in out])
+    got = np.concatenate([o[4] for o in out])
+    assert np.array_equal(keys, want.index.to_numpy())
+    assert np.allclose(got, want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9)
