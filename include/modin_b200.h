@@ -83,6 +83,8 @@ enum mb200_map_op {
   MB200_OP_CLIP_S = 18, /* x < s0 ? s0 : (x > s1 ? s1 : x); NaN preserved; absent bounds = -inf / +inf (pandas clip) */
   MB200_OP_COPY = 19,
   MB200_OP_ROUND_S = 20, /* numpy.round(x, d): s0 = 10^|d|, s1 = sign of d; rint(x * s0) / s0 (DataFrame.round) */
+  MB200_OP_ORDERED_S = 21, /* sort key: int64 image whose signed order = sort_values order (float64 or int64 in,
+                              int64 out; NaN last; s0 != 0 = descending).  Feeds mb200_sort_pairs_i64. */
   /* two-frame ops (in0 OP in1) */
   MB200_OP_ADD = 32,
   MB200_OP_SUB = 33,

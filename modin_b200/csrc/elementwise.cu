@@ -119,6 +119,19 @@ __device__ __forceinline__ TO apply(TI a, TI b, TI c, TI s0, TI s1) {
     } else {
       return (TO)a;  // integers: decimals >= 0 is the identity (negative decimals are not on this path)
     }
+  } else if constexpr (OP == MB200_OP_ORDERED_S) {
+    // sort key: an int64 whose signed order is the order sort_values wants.  float64: flip the magnitude bits
+    // of negatives (total order of IEEE doubles), NaN -> INT64_MAX (na_position="last" in either direction);
+    // s0 != 0 = descending: bitwise NOT reverses the order without overflow and keeps ties stable.
+    long long o;
+    if constexpr (F) {
+      if (a != a) return (TO)0x7fffffffffffffffLL;
+      const long long b = __double_as_longlong(a);
+      o = b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+    } else {
+      o = (long long)a;
+    }
+    return (TO)(s0 != (TI)0 ? ~o : o);
   } else if constexpr (OP == MB200_OP_COPY) {
     return (TO)a;
   } else if constexpr (OP == MB200_OP_FILLNA) {
@@ -313,6 +326,7 @@ extern "C" int mb200_map(int op, int dtype, int ncols, const void* const* in0, c
       MB_CASE(MB200_OP_CLIP_S, double, double)
       MB_CASE(MB200_OP_COPY, double, double)
       MB_CASE(MB200_OP_ROUND_S, double, double)
+      MB_CASE(MB200_OP_ORDERED_S, double, long long)
       MB_CASE(MB200_OP_ADD, double, double)
       MB_CASE(MB200_OP_SUB, double, double)
       MB_CASE(MB200_OP_MUL, double, double)
@@ -348,6 +362,7 @@ extern "C" int mb200_map(int op, int dtype, int ncols, const void* const* in0, c
       MB_CASE(MB200_OP_CLIP_S, long long, long long)
       MB_CASE(MB200_OP_COPY, long long, long long)
       MB_CASE(MB200_OP_ROUND_S, long long, long long)
+      MB_CASE(MB200_OP_ORDERED_S, long long, long long)
       MB_CASE(MB200_OP_ADD, long long, long long)
       MB_CASE(MB200_OP_SUB, long long, long long)
       MB_CASE(MB200_OP_MUL, long long, long long)

@@ -22,7 +22,7 @@ import numpy as np
 import pandas
 
 from . import dist
-from .block import DeviceBlock
+from .block import DeviceBlock, torch_mod
 from .functors import MODIN_UNNAMED_SERIES_LABEL
 from .partitioning import B200PartitionManager
 
@@ -195,6 +195,67 @@ class B200Dataframe:
         return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
 
     # ---- Binary -----------------------------------------------------------------------------------
+    def sort_by(self, col_position: int, ascending: bool = True, ignore_index: bool = False) -> "B200Dataframe":
+        """Stable sort of the rows by one float64 / int64 column (NaN last) -- the device form of
+        ``PandasDataframe.sort_by`` (df.py:2741-2791), which range-partitions the rows by sampled pivots
+        (``_apply_func_to_range_partitioning`` df.py:2565-2739) and sorts every range with pandas.
+
+        Here: per GPU, key -> order-preserving int64 image (MB200_OP_ORDERED_S), stable LSD radix sort of
+        (image, row id), one gather of every column by the permutation.  Across GPUs the locally sorted rows are
+        range-partitioned by sampled pivots and exchanged with ONE all_to_all (``dist.exchange_by_key_range``,
+        the raw-row shuffle of SURVEY 8f-2), then the received runs are merged by the same stable sort; rank r ends
+        up with the r-th key range, ties in original row order.  Row labels travel as a device index column."""
+        from . import ops
+        from .block import DeviceBlock, DeviceColumn, concat_cols, concat_rows
+
+        t = torch_mod()
+        rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
+        block = concat_rows(rows) if len(rows) > 1 else rows[0]
+        key = block.cols[col_position]
+        if key.dtype not in (np.float64, np.int64):
+            raise NotImplementedError("device sort_values needs a float64 or int64 key column")
+        if block.index_host is not None and not ignore_index:
+            raise NotImplementedError("sort_values keeps host-resident (non-numeric) row labels only with ignore_index=True")
+        n = block.nrows
+        cols = list(block.cols)
+        if dist.is_distributed() and any(c.dtype == np.bool_ for c in cols):
+            raise NotImplementedError("multi-GPU sort_values moves 8-byte columns only (bool columns are not packed)")
+        if not ignore_index:  # row labels ride along as one more int64 / float64 column
+            if block.index_cols:
+                if len(block.index_cols) != 1:
+                    raise NotImplementedError("sort_values with a MultiIndex is not on the B200 path")
+                cols.append(block.index_cols[0])
+            else:
+                cols.append(DeviceColumn(t.arange(block.range_start, block.range_start + n, dtype=t.int64,
+                                                  device=key.data.device), np.int64))  # fmt: skip
+
+        def sort_local(key_image, columns):
+            perm = DeviceColumn(t.arange(len(key_image), dtype=t.int64, device=key_image.data.device), np.int64)
+            ops.sort_pairs(key_image, perm)  # in place, stable
+            return key_image, ops.take_columns(columns, perm)
+
+        if n:
+            image = ops.map_columns("ordered_s", [key], s0=[(1.0 if key.dtype == np.float64 else 1) if not ascending else 0])[0]
+            image, cols = sort_local(image, cols)
+        else:
+            image = DeviceColumn.empty(0, np.int64)
+        if dist.is_distributed():
+            rk, rcols = dist.exchange_by_key_range(image.data, [c.data for c in cols])
+            image = DeviceColumn(rk, np.int64)
+            cols = [DeviceColumn(x, c.dtype) for x, c in zip(rcols, cols)]
+            if len(image):
+                image, cols = sort_local(image, cols)  # merge of the W sorted runs that arrived (rank order = tie order)
+            n = len(image)
+        if ignore_index:
+            lo = dist.exclusive_row_offset(n) if dist.is_distributed() else 0
+            out = DeviceBlock(cols, block.columns, nrows=n, range_start=lo)
+        else:
+            names = block.index_names if block.index_cols else [None]
+            out = DeviceBlock(cols[:-1], block.columns, nrows=n, index_cols=[cols[-1]], index_names=names)
+        pc = self._partition_mgr_cls._partition_class
+        return self.__constructor__(np.array([[pc(out)]], dtype=object), None, self._columns_cache, [n],
+                                    [len(out.cols)], self._dtypes)  # fmt: skip
+
     def _repartition_rows(self, lengths: List[int]) -> "B200Dataframe":
         """Same rows, cut at ``lengths`` instead of ``self.row_lengths`` (the row half of ``_copartition``,
         df.py:3799-3840, without a reindex): target partitions inside one source partition are views of its

@@ -112,6 +112,16 @@ def all_gather_small(values, extra: int | None = None):
     return out.reshape(world_size(), v.numel()).tolist()
 
 
+def exclusive_row_offset(nrows_local: int) -> int:
+    """Global position of this rank's first row when every rank holds ``nrows_local`` rows in rank order."""
+    if not is_distributed():
+        return 0
+    t = _torch()
+    dev = "cuda" if _dist().get_backend() == "nccl" else "cpu"
+    counts = all_gather_small(t.tensor([int(nrows_local)], dtype=t.int64, device=dev))
+    return int(sum(c[0] for c in counts[: rank()]))
+
+
 def dense_split(nkeys: int, r: int | None = None, ws: int | None = None):
     """Slice [lo, hi) of a dense key range [0, nkeys) that rank r emits: equal chunks rounded up to a
     multiple of 4 (the presence map is scanned in 4-byte words); trailing ranks may get (0, 0)."""

@@ -68,6 +68,8 @@ def map_columns(
             odt = np.dtype("bool")
         elif op in ("div", "div_s", "rdiv_s"):
             odt = np.dtype("float64")
+        elif op == "ordered_s":
+            odt = np.dtype("int64")
         else:
             odt = in0[idxs[0]].dtype
         for k in range(0, len(idxs), 32):

@@ -285,6 +285,17 @@ class DataFrame(BasePandasDataset):
                                 groupby_kwargs=dict(as_index=as_index, sort=sort, group_keys=group_keys,
                                                     observed=observed, dropna=dropna, level=level))  # fmt: skip
 
+    def sort_values(self, by, *, axis=0, ascending=True, inplace=False, kind="quicksort", na_position="last",
+                    ignore_index=False, key=None):  # fmt: skip
+        """modin/pandas/base.py ``sort_values`` -> ``qc.sort_rows_by_column_values``."""
+        if axis not in (0, "index"):
+            raise NotImplementedError("sort_values(axis=1) is not on the B200 path")
+        if inplace:
+            raise NotImplementedError("sort_values(inplace=True) is not on the B200 path")
+        qc = self._query_compiler.sort_rows_by_column_values(by, ascending=ascending, kind=kind, na_position=na_position,
+                                                             ignore_index=ignore_index, key=key)  # fmt: skip
+        return DataFrame(query_compiler=qc)
+
     def merge(self, right, how="inner", on=None, left_on=None, right_on=None, left_index=False, right_index=False,
               sort=False, suffixes=("_x", "_y"), copy=None, indicator=False, validate=None):  # fmt: skip
         """modin/pandas/dataframe.py:1365-1403."""

@@ -282,3 +282,37 @@ def df_var(df, npartitions: int, ddof: int = 1, skipna: bool = True):
 
 def df_std(df, npartitions: int, ddof: int = 1, skipna: bool = True):
     return reduce_full_axis(df, lambda x: x.std(axis=0, ddof=ddof, skipna=skipna), npartitions)
+
+
+# ------------------------------------------------------------------ sort_values (range-partition shuffle)
+def sort_values(df, by: str, ascending: bool, npartitions: int, kind: str = "stable") -> pandas.DataFrame:
+    """qc.sort_rows_by_column_values -> PandasDataframe.sort_by (dataframe.py:2741-2791) ->
+    _apply_func_to_range_partitioning (dataframe.py:2565-2739): pick npartitions-1 pivots from the key column
+    (ShuffleSortFunctions.pick_pivots_from_samples_for_sort, dataframe/utils.py:288-332), route every row of every
+    row partition to the range its key falls in (split_partitions_using_pivots_for_sort, utils.py:334-475; NaN keys go
+    to the last range), concatenate what arrives in partition order and sort each range with
+    ``pandas.DataFrame.sort_values``.  With a stable ``kind`` the concatenation over ranges equals the stable
+    sort of the whole frame, whatever the pivots -- which is what makes the result partition-independent."""
+    grid = split_into_partitions(df, npartitions)
+    row_parts = [pandas.concat(row, axis=1) for row in grid]
+    keys = df[by].dropna().to_numpy()
+    if len(keys) == 0 or npartitions < 2:
+        return df.sort_values(by, ascending=ascending, kind=kind)
+    qs = np.linspace(0, 1, npartitions + 1)[1:-1]
+    pivots = np.quantile(keys, qs, method="inverted_cdf")
+    if not ascending:
+        pivots = pivots[::-1]
+    ranges = [[] for _ in range(npartitions)]
+    for part in row_parts:
+        k = part[by].to_numpy()
+        if ascending:
+            dest = np.searchsorted(pivots, k, side="right")
+        else:
+            dest = np.searchsorted(-pivots, -k, side="right")
+        dest = np.where(np.isnan(k.astype(np.float64)), npartitions - 1, dest)
+        for r in range(npartitions):
+            sel = part[dest == r]
+            if len(sel):
+                ranges[r].append(sel)
+    out = [pandas.concat(parts).sort_values(by, ascending=ascending, kind=kind) for parts in ranges if parts]
+    return pandas.concat(out)

@@ -50,6 +50,7 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
                 "eq_s": lambda: x == p, "ne_s": lambda: x != p, "lt_s": lambda: x < p, "le_s": lambda: x <= p,
                 "gt_s": lambda: x > p, "ge_s": lambda: x >= p, "copy": lambda: x.copy(),
                 "clip_s": lambda: np.where(x < p, p, np.where(x > q, q, x)).astype(x.dtype),
+                "ordered_s": lambda: _ordered_image(x, p),
                 "round_s": lambda: (np.rint(x * p) / p if q >= 0 else np.rint(x / p) * p) if x.dtype == np.float64 else x,
                 "add": lambda: x + y, "sub": lambda: x - y, "mul": lambda: x * y, "div": lambda: x / y,
                 "eq": lambda: x == y, "ne": lambda: x != y, "lt": lambda: x < y, "le": lambda: x <= y,
@@ -60,6 +61,24 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
             r = r.astype(np.float64)
         out.append(_col(np.asarray(r)))
     return out
+
+
+def _ordered_image(x, desc):
+    """numpy restatement of MB200_OP_ORDERED_S (csrc/elementwise.cu)."""
+    if x.dtype == np.float64:
+        b = x.view(np.int64)
+        o = b ^ ((b >> 63) & np.int64(0x7FFFFFFFFFFFFFFF))
+        o = np.where(desc, ~o, o)
+        return np.where(np.isnan(x), np.iinfo(np.int64).max, o).astype(np.int64)
+    o = x.astype(np.int64)
+    return (~o if desc else o).astype(np.int64)
+
+
+def sort_pairs(keys, payload):
+    """In-place stable sort of (keys, payload) by key."""
+    k, p = _np(keys), _np(payload)
+    order = np.argsort(k, kind="stable")
+    k[:], p[:] = k[order], p[order]
 
 
 def reduce_columns(op, cols, skipna=True, variant=0, centers=None):
@@ -283,9 +302,9 @@ def installed():
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
                                         "compact_hits", "cast_columns_f64", "gen_f64", "gen_i64", "GroupTable",
-                                        "key_range_device")},
+                                        "key_range_device", "sort_pairs")},
     }  # fmt: skip
-    ops.GroupTable, ops.key_range_device = GroupTable, key_range_device
+    ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device
     ops.map_columns, ops.reduce_columns, ops.hash_aggregate = map_columns, reduce_columns, hash_aggregate

@@ -227,3 +227,42 @@ def test_full_stack_var_std_and_dict_agg_across_ranks():
     got = np.concatenate([o[4] for o in out])
     assert np.array_equal(keys, want.index.to_numpy())
     assert np.allclose(got, want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9)
+
+
+def _full_stack_sort_job(rank, ws):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    out = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(5_003, 2, seed=6, nan_per_64k=5000, key_modulus=13)
+        df = bpd.DataFrame(pdf)  # sharded by rank
+        for by, asc in (("key", True), ("c0", False)):
+            blk = df.sort_values(by, ascending=asc)._query_compiler._modin_frame._partitions[0, 0].get()
+            out[(by, asc)] = (blk.index_cols[0].data.numpy().copy(),
+                              np.stack([c.data.numpy().astype(np.float64) for c in blk.cols], axis=1))
+        blk = df.sort_values("c1", ignore_index=True)._query_compiler._modin_frame._partitions[0, 0].get()
+        out["ignore"] = (np.arange(blk.range_start, blk.range_start + blk.nrows),
+                         np.stack([c.data.numpy().astype(np.float64) for c in blk.cols], axis=1))
+    return out
+
+
+def test_full_stack_sort_values_across_ranks():
+    """The raw-row range shuffle: rank r ends up with the r-th key range, ties in original order."""
+    out = _run(_full_stack_sort_job)
+    pdf = synth.host_frame(5_003, 2, seed=6, nan_per_64k=5000, key_modulus=13)
+    for by, asc in (("key", True), ("c0", False)):
+        want = pdf.sort_values(by, ascending=asc, kind="stable")
+        idx = np.concatenate([o[(by, asc)][0] for o in out])
+        vals = np.concatenate([o[(by, asc)][1] for o in out])
+        assert np.array_equal(idx, want.index.to_numpy()), (by, asc)
+        assert np.array_equal(vals, want.to_numpy(dtype=np.float64), equal_nan=True), (by, asc)
+        assert all(len(o[(by, asc)][0]) > 0 for o in out)
+    want = pdf.sort_values("c1", kind="stable", ignore_index=True)
+    assert np.array_equal(np.concatenate([o["ignore"][0] for o in out]), want.index.to_numpy())
+    assert np.array_equal(np.concatenate([o["ignore"][1] for o in out]), want.to_numpy(dtype=np.float64), equal_nan=True)

@@ -519,3 +519,20 @@ def test_dlpack_interchange_is_zero_copy_on_device():
     assert np.allclose(got.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9)
     y = torch.from_dlpack(m.to_dlpack(df[["x"]] * 2.0)["x"])  # a consumer on the same device, no host round trip
     assert torch.equal(y, x * 2.0)
+
+
+def test_sort_values_stable_nan_last():
+    """SURVEY 8f-2 on one GPU: order-preserving key image + stable radix sort + one gather per column; equals
+    pandas' stable sort bit for bit, row labels included."""
+    m = bpd()
+    pdf = synth.host_frame(100_003, 3, seed=2, nan_per_64k=4000, key_modulus=1009)
+    pdf.loc[5, "c1"], pdf.loc[6, "c1"], pdf.loc[7, "c1"] = np.inf, -np.inf, -0.0
+    df = m.DataFrame(pdf)
+    for by, asc in (("key", True), ("key", False), ("c1", True), ("c1", False)):
+        got = df.sort_values(by, ascending=asc)._to_pandas()
+        want = pdf.sort_values(by, ascending=asc, kind="stable")
+        assert_exact(got.index.to_numpy(), want.index.to_numpy(), f"sort {by} asc={asc}: row labels")
+        assert_exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), f"sort {by} asc={asc}")
+    got = df.sort_values("c0", ignore_index=True)._to_pandas()
+    want = pdf.sort_values("c0", kind="stable", ignore_index=True)
+    assert isinstance(got.index, pandas.RangeIndex) and assert_exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), "ignore_index") is None

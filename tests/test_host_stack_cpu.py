@@ -240,3 +240,22 @@ def test_dlpack_interchange_is_zero_copy(cpu_device):
         bpd.from_dlpack({"x": torch.zeros(3, dtype=torch.float32)})
     with pytest.raises(ValueError):
         bpd.from_dlpack({"x": a, "y": torch.zeros(3, dtype=torch.float64)})
+
+
+def test_sort_values_is_a_stable_sort_with_nan_last(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(3001, 3, seed=2, nan_per_64k=4000, key_modulus=17)
+    df = bpd.DataFrame(pdf)
+    for by, asc in (("key", True), ("key", False), ("c1", True), ("c1", False)):
+        got = df.sort_values(by, ascending=asc)._to_pandas()
+        want = pdf.sort_values(by, ascending=asc, kind="stable")
+        assert list(got.index) == list(want.index), (by, asc)  # permuted row labels travel with the rows
+        assert _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64)), (by, asc)
+    got = df.sort_values("c0", ignore_index=True)._to_pandas()
+    want = pdf.sort_values("c0", kind="stable", ignore_index=True)
+    assert list(got.index) == list(want.index) and _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    with pytest.raises(NotImplementedError):
+        df.sort_values(["key", "c0"])
+    with pytest.raises(KeyError):
+        df.sort_values("nope")
