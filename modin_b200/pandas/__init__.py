@@ -348,6 +348,31 @@ class Series(BasePandasDataset):
     def _finish_host_stat(self, ser):
         return ser.iloc[0]
 
+    # ---- distinct values of an int64 Series, through the group tables (qc.py:1109-1142 nunique / unique; the
+    # reference's range-partitioning variants are built on the same shuffle as sort_values) ----------------------
+    def _as_key_frame(self):
+        label = self._query_compiler.columns[0]
+        return DataFrame(query_compiler=self._query_compiler), label
+
+    def nunique(self, dropna=True):
+        """Number of distinct values = number of groups (int64 values only; int64 holds no NaN)."""
+        df, label = self._as_key_frame()
+        frame = df.groupby(label).size()._query_compiler._modin_frame
+        return int(frame.global_nrows)
+
+    def value_counts(self, normalize=False, sort=True, ascending=False, bins=None, dropna=True):
+        """``Series.value_counts`` (modin/pandas/base.py -> qc.value_counts): group sizes keyed by value, most
+        frequent first.  Ties come out in ascending value order (pandas leaves tie order unspecified)."""
+        if normalize or bins is not None:
+            raise NotImplementedError("value_counts(normalize= / bins=) is not on the B200 path")
+        df, label = self._as_key_frame()
+        sizes = df.groupby(label).size()  # Series over the group keys
+        if not sort:
+            return sizes
+        frame = DataFrame(query_compiler=sizes._query_compiler).sort_values(sizes._query_compiler.columns[0],
+                                                                            ascending=ascending)  # fmt: skip
+        return Series(query_compiler=frame._query_compiler)
+
 
 class DataFrameGroupBy:
     """modin/pandas/groupby.py (``_wrap_aggregation`` :1829-1886)."""

@@ -536,3 +536,14 @@ def test_sort_values_stable_nan_last():
     got = df.sort_values("c0", ignore_index=True)._to_pandas()
     want = pdf.sort_values("c0", kind="stable", ignore_index=True)
     assert isinstance(got.index, pandas.RangeIndex) and assert_exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), "ignore_index") is None
+
+
+def test_series_nunique_and_value_counts():
+    m = bpd()
+    pdf = synth.host_frame(60_001, 1, seed=3, key_modulus=5003, key_skew=True)
+    s = m.DataFrame(pdf)["key"]
+    assert s.nunique() == pdf["key"].nunique()
+    got = s.value_counts()._to_pandas()
+    want = pdf["key"].value_counts()
+    assert_exact(got.to_numpy(), want.to_numpy(), "value counts, most frequent first")
+    assert dict(zip(got.index, got.to_numpy())) == dict(zip(want.index, want.to_numpy()))

@@ -259,3 +259,18 @@ def test_sort_values_is_a_stable_sort_with_nan_last(cpu_device):
         df.sort_values(["key", "c0"])
     with pytest.raises(KeyError):
         df.sort_values("nope")
+
+
+def test_series_nunique_and_value_counts(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(4001, 1, seed=3, key_modulus=29, key_skew=True)
+    s = bpd.DataFrame(pdf)["key"]
+    assert s.nunique() == pdf["key"].nunique()
+    got = s.value_counts()._to_pandas()
+    want = pdf["key"].value_counts()
+    assert list(got.to_numpy()) == list(want.to_numpy())  # counts, most frequent first
+    assert dict(zip(got.index, got.to_numpy())) == dict(zip(want.index, want.to_numpy()))
+    asc = s.value_counts(ascending=True)._to_pandas()
+    assert list(asc.to_numpy()) == sorted(want.to_numpy())
+    assert len(s.value_counts(sort=False)) == pdf["key"].nunique()
