@@ -85,6 +85,7 @@ enum mb200_map_op {
   MB200_OP_ROUND_S = 20, /* numpy.round(x, d): s0 = 10^|d|, s1 = sign of d; rint(x * s0) / s0 (DataFrame.round) */
   MB200_OP_ORDERED_S = 21, /* sort key: int64 image whose signed order = sort_values order (float64 or int64 in,
                               int64 out; NaN last; s0 != 0 = descending).  Feeds mb200_sort_pairs_i64. */
+  MB200_OP_NOT = 22, /* bool (uint8) in, bool out: ~x (qc.py:541-571 logical ops; DataFrame.__invert__) */
   /* two-frame ops (in0 OP in1) */
   MB200_OP_ADD = 32,
   MB200_OP_SUB = 33,
@@ -97,6 +98,9 @@ enum mb200_map_op {
   MB200_OP_GT = 40,
   MB200_OP_GE = 41,
   MB200_OP_FILLNA = 42, /* isnan(in0) ? in1 : in0 */
+  MB200_OP_AND = 43, /* bool columns: in0 & in1, | and ^ (Binary.register(pandas.DataFrame.__and__ ...) qc.py:541-571) */
+  MB200_OP_OR = 44,
+  MB200_OP_XOR = 45,
   /* three-frame op */
   MB200_OP_FMA3 = 64
 };

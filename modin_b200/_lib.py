@@ -27,7 +27,8 @@ OP = {
     "abs": 0, "neg": 1, "isna": 2, "notna": 3, "fillna_s": 4, "affine": 5,
     "add_s": 6, "sub_s": 7, "rsub_s": 8, "mul_s": 9, "div_s": 10, "rdiv_s": 11,
     "eq_s": 12, "ne_s": 13, "lt_s": 14, "le_s": 15, "gt_s": 16, "ge_s": 17,
-    "clip_s": 18, "copy": 19, "round_s": 20, "ordered_s": 21,
+    "clip_s": 18, "copy": 19, "round_s": 20, "ordered_s": 21, "not": 22,
+    "and": 43, "or": 44, "xor": 45,
     "add": 32, "sub": 33, "mul": 34, "div": 35, "eq": 36, "ne": 37, "lt": 38, "le": 39,
     "gt": 40, "ge": 41, "fillna": 42,
     "fma3": 64,

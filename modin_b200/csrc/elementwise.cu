@@ -46,6 +46,10 @@ template <>
 __device__ __forceinline__ long long from_bits<long long>(uint64_t b) {
   return (long long)b;
 }
+template <>
+__device__ __forceinline__ uint8_t from_bits<uint8_t>(uint64_t b) {
+  return (uint8_t)(b != 0);
+}
 
 constexpr __host__ __device__ int op_nin(int op) { return op >= 64 ? 3 : (op >= 32 ? 2 : 1); }
 constexpr __host__ __device__ bool op_is_pred(int op) {
@@ -119,6 +123,14 @@ __device__ __forceinline__ TO apply(TI a, TI b, TI c, TI s0, TI s1) {
     } else {
       return (TO)a;  // integers: decimals >= 0 is the identity (negative decimals are not on this path)
     }
+  } else if constexpr (OP == MB200_OP_NOT) {
+    return (TO)(a == (TI)0);
+  } else if constexpr (OP == MB200_OP_AND) {
+    return (TO)((a != (TI)0) && (b != (TI)0));
+  } else if constexpr (OP == MB200_OP_OR) {
+    return (TO)((a != (TI)0) || (b != (TI)0));
+  } else if constexpr (OP == MB200_OP_XOR) {
+    return (TO)((a != (TI)0) != (b != (TI)0));
   } else if constexpr (OP == MB200_OP_ORDERED_S) {
     // sort key: an int64 whose signed order is the order sort_values wants.  float64: flip the magnitude bits
     // of negatives (total order of IEEE doubles), NaN -> INT64_MAX (na_position="last" in either direction);
@@ -157,6 +169,24 @@ struct Vec4<long long> {
   using type = i64x4;
   static __device__ __forceinline__ i64x4 load(const long long* p) { return ldg_stream_i64x4(p); }
   static __device__ __forceinline__ void store(long long* p, const i64x4& v) { stg_stream_i64x4(p, v); }
+};
+
+// bool columns (uint8 0 / 1): four elements = one 32-bit word
+struct u8x4 {
+  uint8_t x, y, z, w;
+};
+template <>
+struct Vec4<uint8_t> {
+  using type = u8x4;
+  static __device__ __forceinline__ u8x4 load(const uint8_t* p) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+    u8x4 r;
+    r.x = (uint8_t)(v & 0xffu);
+    r.y = (uint8_t)((v >> 8) & 0xffu);
+    r.z = (uint8_t)((v >> 16) & 0xffu);
+    r.w = (uint8_t)(v >> 24);
+    return r;
+  }
 };
 
 template <typename TO, typename VO>
@@ -376,6 +406,17 @@ extern "C" int mb200_map(int op, int dtype, int ncols, const void* const* in0, c
       MB_CASE(MB200_OP_FMA3, long long, long long)
       default:
         return fail("mb200_map", "unsupported op for int64");
+    }
+  } else if (dtype == MB200_U8) {
+    // bool columns: logical ops stay bool; COPY widens to int64 (what a reduction over booleans consumes)
+    switch (op) {
+      MB_CASE(MB200_OP_COPY, uint8_t, long long)
+      MB_CASE(MB200_OP_NOT, uint8_t, uint8_t)
+      MB_CASE(MB200_OP_AND, uint8_t, uint8_t)
+      MB_CASE(MB200_OP_OR, uint8_t, uint8_t)
+      MB_CASE(MB200_OP_XOR, uint8_t, uint8_t)
+      default:
+        return fail("mb200_map", "unsupported op for bool");
     }
   }
   return fail("mb200_map", "unsupported dtype");

@@ -61,12 +61,14 @@ class DevMap(DevFn):
     """Unary elementwise map: abs / neg / isna / notna (qc.py:2036, 2063-2106)."""
 
     def __init__(self, op: str):
-        if op not in ("abs", "neg", "isna", "notna", "copy"):
+        if op not in ("abs", "neg", "isna", "notna", "copy", "not"):
             raise ValueError(op)
         self.op = op
 
     def __call__(self, block, *args, **kwargs):
         _check_block(block, f"DevMap({self.op})")
+        if self.op == "not" and any(c.dtype != np.bool_ for c in block.cols):
+            raise NotImplementedError("~frame on the B200 path needs bool columns (bitwise integer NOT is not on it)")
         if not block.cols or block.nrows == 0:
             return self._empty(block)
         if self.op in ("isna", "notna"):
@@ -268,6 +270,75 @@ class DevBinary(DevFn):
         raise NotImplementedError(f"binary op with {type(other).__name__} operand is not on the B200 path")
 
 
+class DevLogical(DevFn):
+    """``a & b``, ``a | b``, ``a ^ b`` between co-partitioned BOOL frames -- ``Binary.register(pandas.DataFrame.__and__
+    / __or__ / __xor__)`` (qc.py:541-571).  Bool columns are uint8 0 / 1 buffers; the result stays bool."""
+
+    def __init__(self, op: str):
+        if op not in ("and", "or", "xor"):
+            raise ValueError(op)
+        self.op = op
+
+    def __call__(self, block, other, *args, axis=None, level=None, fill_value=None, **kwargs):
+        _check_block(block, f"DevLogical({self.op})")
+        if not isinstance(other, DeviceBlock):
+            raise NotImplementedError("logical ops on the B200 path take another bool frame")
+        if block.nrows != other.nrows or len(block.cols) != len(other.cols) or not block.columns.equals(other.columns):
+            raise NotImplementedError("logical op between differently shaped / labelled blocks")
+        if any(c.dtype != np.bool_ for c in list(block.cols) + list(other.cols)):
+            raise NotImplementedError("logical ops on the B200 path need bool columns (bitwise integer ops are not on it)")
+        if block.nrows == 0 or not block.cols:
+            return block
+        return block.with_cols(ops.map_columns(self.op, block.cols, other.cols))
+
+
+class DevBoolReduce(DevFn):
+    """``df.any()`` / ``df.all()`` over BOOL columns -- ``TreeReduce.register(pandas.DataFrame.any / all)``
+    (qc.py:986-987): any = max, all = min of the 0 / 1 values, per partition and again over the partials
+    (and over the GPUs with one packed all_reduce).  An empty column gives any = False, all = True like pandas."""
+
+    def __init__(self, op: str, phase: str = "map"):
+        if op not in ("any", "all"):
+            raise ValueError(op)
+        self.op, self.phase = op, phase
+        self.kop = "max" if op == "any" else "min"
+
+    def _ints(self, block):
+        if self.phase == "map":
+            if any(c.dtype != np.bool_ for c in block.cols):
+                raise NotImplementedError("any / all on the B200 path reduce bool columns (compare first)")
+            return ops.cast_columns_i64(block.cols)
+        return list(block.cols)  # partials are int64 0 / 1 (or the +-max identities of empty partitions)
+
+    def _finish(self, vals, block):
+        ints = [DeviceColumn(v, np.int64) for v in vals]
+        if self.phase == "map":
+            return _reduced_block(ints, block.columns)
+        # reduce phase: int64 -> bool.  An all-empty frame leaves the identity: INT64_MIN for max (any -> False),
+        # INT64_MAX for min (all -> True); both fall out of "> 0".
+        return _reduced_block(ops.map_columns("gt_s", ints, s0=[0] * len(ints)), block.columns)
+
+    def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
+        _check_block(block, f"DevBoolReduce({self.op})")
+        if axis not in (0, "index", None):
+            raise NotImplementedError("row-wise any / all is not on the B200 path")
+        if not block.cols:
+            return _reduced_block([], block.columns)
+        vals, _ = ops.reduce_columns(self.kop, self._ints(block), skipna=True, variant=1)
+        return self._finish(vals, block)
+
+    def run_distributed(self, block, *args, axis=0, skipna=True, **kwargs):
+        from . import dist
+
+        if not block.cols:
+            return _reduced_block([], block.columns)
+        vals, _ = ops.reduce_columns(self.kop, self._ints(block), skipna=True, variant=1)
+        dist.all_reduce_values(vals, [self.kop] * len(vals))
+        res = self._finish(vals, block)
+        res.replicated = True
+        return res
+
+
 class DevAffine(DevFn):
     """Fused ``x * s + t`` (two roundings) produced by the call-queue fusion pass."""
 
@@ -335,6 +406,16 @@ class DevReduce(DevFn):
             return "sum"  # counts add up (qc.py:976: TreeReduce.register(count, sum))
         return self.op
 
+    @staticmethod
+    def _widen_bools(block, kop):
+        """sum / count of bool columns: pandas sums booleans as int64 (``(df > 0).sum()``); min / max / prod of
+        booleans would have to return bool and are left out."""
+        if not any(c.dtype == np.bool_ for c in block.cols):
+            return block
+        if kop not in ("sum", "count"):
+            raise NotImplementedError(f"{kop} over bool columns is not on the B200 path (use any / all / sum)")
+        return block.with_cols(ops.cast_columns_i64(block.cols))
+
     def _check(self, block, axis, min_count):
         _check_block(block, f"DevReduce({self.op})")
         if axis not in (0, "index", None):
@@ -347,6 +428,7 @@ class DevReduce(DevFn):
         if not block.cols:
             return _reduced_block([], block.columns)
         kop = self._kernel_op()
+        block = self._widen_bools(block, kop)
         vals, cnts = ops.reduce_columns(kop, block.cols, skipna=bool(skipna), variant=ReduceVariant.get())
         out = []
         for j, c in enumerate(block.cols):
@@ -371,6 +453,7 @@ class DevReduce(DevFn):
             return _reduced_block([], block.columns)
         t = ops.torch_mod()
         kop = self._kernel_op()
+        block = self._widen_bools(block, kop)
         vals, cnts = ops.reduce_columns(kop, block.cols, skipna=bool(skipna), variant=ReduceVariant.get())
         W = len(block.cols)
         if kop == "count":

@@ -63,8 +63,10 @@ def map_columns(
         groups.setdefault(c.code, []).append(j)
     for code, idxs in groups.items():
         if code == _lib.U8:
-            raise TypeError(f"elementwise {op!r} on bool columns is not on the B200 path")
-        if op in _lib.PREDICATES:
+            if op not in ("copy", "not", "and", "or", "xor"):
+                raise TypeError(f"elementwise {op!r} on bool columns is not on the B200 path")
+            odt = np.dtype("int64") if op == "copy" else np.dtype("bool")  # copy widens bool -> int64
+        elif op in _lib.PREDICATES:
             odt = np.dtype("bool")
         elif op in ("div", "div_s", "rdiv_s"):
             odt = np.dtype("float64")
@@ -91,12 +93,19 @@ def map_columns(
     return out  # type: ignore[return-value]
 
 
+def cast_columns_i64(cols: Sequence[DeviceColumn]) -> List[DeviceColumn]:
+    """bool -> int64 widening (what pandas does before it sums / averages booleans); others unchanged."""
+    return [map_columns("copy", [c])[0] if c.dtype == np.bool_ else c for c in cols]
+
+
 def cast_columns_f64(cols: Sequence[DeviceColumn]) -> List[DeviceColumn]:
-    """int64 -> float64 promotion (x / 1.0 through the division kernel)."""
+    """int64 -> float64 promotion (x / 1.0 through the division kernel); bool goes through int64."""
     res = []
     for c in cols:
         if c.dtype == np.float64:
             res.append(c)
+        elif c.dtype == np.bool_:
+            res.extend(map_columns("div_s", cast_columns_i64([c]), s0=[1]))
         elif c.dtype == np.int64:
             res.extend(map_columns("div_s", [c], s0=[1]))
         else:

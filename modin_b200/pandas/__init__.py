@@ -166,6 +166,20 @@ class BasePandasDataset:
     __ge__ = lambda self, o: self.ge(o)  # noqa: E731
     __hash__ = None
 
+    # ---- logical ops on bool frames (what comparisons produce) --------------------------------------
+    __and__ = lambda self, o: self._binary_op("__and__", o)  # noqa: E731
+    __or__ = lambda self, o: self._binary_op("__or__", o)  # noqa: E731
+    __xor__ = lambda self, o: self._binary_op("__xor__", o)  # noqa: E731
+
+    def __invert__(self):
+        return self._create_or_update_from_compiler(self._query_compiler.invert())
+
+    def any(self, axis=0, bool_only=False, skipna=True, **kwargs):
+        return self._stat("any", axis, skipna, False)
+
+    def all(self, axis=0, bool_only=False, skipna=True, **kwargs):
+        return self._stat("all", axis, skipna, False)
+
     # ---- TreeReduce --------------------------------------------------------------------------------
     def _stat(self, name, axis=0, skipna=True, numeric_only=False, **kwargs):
         if axis not in (0, "index", None):

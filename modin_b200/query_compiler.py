@@ -21,10 +21,12 @@ from .algebra import Binary, GroupByReduce, Map, TreeReduce
 from .dataframe import B200Dataframe
 from .functors import (
     DevBinary,
+    DevBoolReduce,
     DevClip,
     DevFillna,
     DevGroupbyMap,
     DevGroupbyReduce,
+    DevLogical,
     DevMap,
     DevMeanMap,
     DevMeanReduce,
@@ -162,6 +164,11 @@ class B200QueryCompiler:
     le = Binary.register(DevBinary("le"), infer_dtypes="bool")
     gt = Binary.register(DevBinary("gt"), infer_dtypes="bool")
     ge = Binary.register(DevBinary("ge"), infer_dtypes="bool")
+    # logical ops between bool frames (qc.py:541-571) and ~frame (qc.py `invert`)
+    __and__ = Binary.register(DevLogical("and"), infer_dtypes="bool")
+    __or__ = Binary.register(DevLogical("or"), infer_dtypes="bool")
+    __xor__ = Binary.register(DevLogical("xor"), infer_dtypes="bool")
+    invert = Map.register(DevMap("not"), dtypes=np.bool_)
 
     # ---- TreeReduce (qc.py:976-1096) ----------------------------------------------------------------
     count = TreeReduce.register(DevReduce("count"), DevReduce("count", phase="reduce"))
@@ -170,6 +177,10 @@ class B200QueryCompiler:
     max = TreeReduce.register(DevReduce("max"), DevReduce("max", phase="reduce"))
     min = TreeReduce.register(DevReduce("min"), DevReduce("min", phase="reduce"))
     mean = TreeReduce.register(DevMeanMap(), DevMeanReduce(), compute_dtypes=lambda *a, **k: np.dtype("float64"))
+    any = TreeReduce.register(DevBoolReduce("any"), DevBoolReduce("any", phase="reduce"),
+                              compute_dtypes=lambda *a, **k: np.dtype("bool"))  # qc.py:986
+    all = TreeReduce.register(DevBoolReduce("all"), DevBoolReduce("all", phase="reduce"),
+                              compute_dtypes=lambda *a, **k: np.dtype("bool"))  # qc.py:987
 
     # ---- var / std (qc.py:1152-1153: Reduce.register(pandas.DataFrame.var / std), pandas' two-pass nanvar) ----
     def _var(self, axis=0, skipna=True, ddof=1, numeric_only=False, sqrt=False, **kwargs):

@@ -39,7 +39,7 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
         z = _np(in2[j]) if in2 is not None else None
         p = s0[j] if s0 is not None else None
         q = s1[j] if s1 is not None else None
-        if a.dtype == np.bool_:
+        if a.dtype == np.bool_ and op not in ("copy", "not", "and", "or", "xor"):
             raise TypeError("bool columns")
         with np.errstate(all="ignore"):
             r = {
@@ -48,9 +48,11 @@ def map_columns(op, in0, in1=None, in2=None, s0=None, s1=None):
                 "add_s": lambda: x + p, "sub_s": lambda: x - p, "rsub_s": lambda: p - x, "mul_s": lambda: x * p,
                 "div_s": lambda: x / np.float64(p), "rdiv_s": lambda: np.float64(p) / x,
                 "eq_s": lambda: x == p, "ne_s": lambda: x != p, "lt_s": lambda: x < p, "le_s": lambda: x <= p,
-                "gt_s": lambda: x > p, "ge_s": lambda: x >= p, "copy": lambda: x.copy(),
+                "gt_s": lambda: x > p, "ge_s": lambda: x >= p,
+                "copy": lambda: x.astype(np.int64) if x.dtype == np.bool_ else x.copy(),
                 "clip_s": lambda: np.where(x < p, p, np.where(x > q, q, x)).astype(x.dtype),
                 "ordered_s": lambda: _ordered_image(x, p),
+                "not": lambda: ~x, "and": lambda: x & y, "or": lambda: x | y, "xor": lambda: x ^ y,
                 "round_s": lambda: (np.rint(x * p) / p if q >= 0 else np.rint(x / p) * p) if x.dtype == np.float64 else x,
                 "add": lambda: x + y, "sub": lambda: x - y, "mul": lambda: x * y, "div": lambda: x / y,
                 "eq": lambda: x == y, "ne": lambda: x != y, "lt": lambda: x < y, "le": lambda: x <= y,
@@ -293,6 +295,10 @@ def cast_columns_f64(cols):
     return [c if c.dtype == np.float64 else _col(_np(c).astype(np.float64)) for c in cols]
 
 
+def cast_columns_i64(cols):
+    return [_col(_np(c).astype(np.int64)) if c.dtype == np.bool_ else c for c in cols]
+
+
 @contextlib.contextmanager
 def installed():
     """Swap the device for the double (context manager used by the ``cpu_device`` fixture)."""
@@ -301,10 +307,11 @@ def installed():
     saved = {
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
-                                        "compact_hits", "cast_columns_f64", "gen_f64", "gen_i64", "GroupTable",
+                                        "compact_hits", "cast_columns_f64", "cast_columns_i64", "gen_f64", "gen_i64", "GroupTable",
                                         "key_range_device", "sort_pairs")},
     }  # fmt: skip
     ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
+    ops.cast_columns_i64 = cast_columns_i64
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device
     ops.map_columns, ops.reduce_columns, ops.hash_aggregate = map_columns, reduce_columns, hash_aggregate

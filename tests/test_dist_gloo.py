@@ -209,6 +209,9 @@ def _full_stack_var_job(rank, ws):
         spec = {"c1": "max", "c0": "sum", "c2": "count"}
         agg = df.groupby("key").agg(spec)._query_compiler._modin_frame
         blks = [p.get() for p in agg._partitions[:, 0]]
+        mask = (vals > 0.0) & (vals < 2.5)
+        assert list(mask.any().to_numpy()) == [True, True, True] and list((vals > 2.5).all().to_numpy()) == [False] * 3
+        assert list(mask.sum().to_numpy()) == list(((pdf[["c0", "c1", "c2"]] > 0.0) & (pdf[["c0", "c1", "c2"]] < 2.5)).sum().to_numpy())
         return (vals.var().to_numpy(), vals.std(ddof=0).to_numpy(), vals.mean().to_numpy(),
                 np.concatenate([b.index_cols[0].data.numpy() for b in blks]),
                 np.concatenate([np.stack([c.data.numpy().astype(np.float64) for c in b.cols], axis=1) for b in blks]))

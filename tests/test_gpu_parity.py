@@ -547,3 +547,23 @@ def test_series_nunique_and_value_counts():
     want = pdf["key"].value_counts()
     assert_exact(got.to_numpy(), want.to_numpy(), "value counts, most frequent first")
     assert dict(zip(got.index, got.to_numpy())) == dict(zip(want.index, want.to_numpy()))
+
+
+def test_boolean_pipelines_on_device():
+    """bool (uint8) columns through the map kernel: & | ^ ~ (32-bit packed loads), widening copy for sum / mean,
+    any / all as max / min -- bit-exact against pandas, odd lengths and unaligned views included."""
+    m = bpd()
+    for n in (5, 4099, 100_003):
+        pdf = synth.host_frame(n, 3, seed=4, nan_per_64k=2000)
+        df = m.DataFrame(pdf)
+        mk, pm = (df > 0.0) & (df < 1.0), (pdf > 0.0) & (pdf < 1.0)
+        assert_exact(mk._to_pandas().to_numpy(), pm.to_numpy(), f"and n={n}")
+        assert_exact(((df > 0.5) | (df < -0.5))._to_pandas().to_numpy(), ((pdf > 0.5) | (pdf < -0.5)).to_numpy(), "or")
+        assert_exact(((df > 0.0) ^ (df > 1.0))._to_pandas().to_numpy(), ((pdf > 0.0) ^ (pdf > 1.0)).to_numpy(), "xor")
+        assert_exact((~mk)._to_pandas().to_numpy(), (~pm).to_numpy(), "not")
+        assert_exact(mk.sum().to_numpy(), pm.sum().to_numpy(), "sum of bools")
+        assert mk.sum().dtype == np.int64
+        assert np.allclose(mk.mean().to_numpy(), pm.mean().to_numpy(), rtol=1e-12)
+        assert_exact(mk.any().to_numpy(), pm.any().to_numpy(), "any")
+        assert_exact(mk.all().to_numpy(), pm.all().to_numpy(), "all")
+        assert_exact((df > -100.0).all().to_numpy(), (pdf > -100.0).all().to_numpy(), "all with NaN")

@@ -274,3 +274,29 @@ def test_series_nunique_and_value_counts(cpu_device):
     asc = s.value_counts(ascending=True)._to_pandas()
     assert list(asc.to_numpy()) == sorted(want.to_numpy())
     assert len(s.value_counts(sort=False)) == pdf["key"].nunique()
+
+
+def test_boolean_pipelines(cpu_device):
+    """Comparisons produce bool frames; & | ^ ~, any / all, and sum / mean / count over them stay on the device."""
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(2003, 3, seed=4, nan_per_64k=2000)
+    df = bpd.DataFrame(pdf)
+    m, pm = (df > 0.0) & (df < 1.0), (pdf > 0.0) & (pdf < 1.0)
+    assert _same(m._to_pandas().to_numpy().astype(float), pm.to_numpy().astype(float))
+    assert _same(((df > 0.5) | (df < -0.5))._to_pandas().to_numpy().astype(float), ((pdf > 0.5) | (pdf < -0.5)).to_numpy().astype(float))
+    assert _same(((df > 0.0) ^ (df > 1.0))._to_pandas().to_numpy().astype(float), ((pdf > 0.0) ^ (pdf > 1.0)).to_numpy().astype(float))
+    assert _same((~m)._to_pandas().to_numpy().astype(float), (~pm).to_numpy().astype(float))
+    assert list(m.sum().to_numpy()) == list(pm.sum().to_numpy()) and m.sum().dtype == np.int64
+    assert list(m.count().to_numpy()) == list(pm.count().to_numpy())
+    assert np.allclose(m.mean().to_numpy(), pm.mean().to_numpy(), rtol=1e-12)
+    assert list(m.any().to_numpy()) == list(pm.any().to_numpy()) and m.any().dtype == np.bool_
+    assert list(m.all().to_numpy()) == list(pm.all().to_numpy())
+    assert list((df > -100.0).all().to_numpy()) == list((pdf > -100.0).all().to_numpy())  # NaN > x is False
+    assert list((df > 100.0).any().to_numpy()) == [False, False, False]
+    with pytest.raises(NotImplementedError):
+        df.any()  # numeric frames: compare first
+    with pytest.raises(NotImplementedError):
+        m & df
+    with pytest.raises(NotImplementedError):
+        m.max()
