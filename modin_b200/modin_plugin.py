@@ -187,6 +187,10 @@ def register(shims: bool | None = None):
         le = Binary.register(fx.DevBinary("le"), infer_dtypes="bool")
         gt = Binary.register(fx.DevBinary("gt"), infer_dtypes="bool")
         ge = Binary.register(fx.DevBinary("ge"), infer_dtypes="bool")
+        __and__ = Binary.register(fx.DevLogical("and"), infer_dtypes="bool")  # qc.py:541-571
+        __or__ = Binary.register(fx.DevLogical("or"), infer_dtypes="bool")
+        __xor__ = Binary.register(fx.DevLogical("xor"), infer_dtypes="bool")
+        invert = Map.register(fx.DevMap("not"), dtypes=np.bool_)
         # TreeReduce (qc.py:976-1096)
         count = TreeReduce.register(fx.DevReduce("count"), fx.DevReduce("count", phase="reduce"),
                                     compute_dtypes=lambda *a, **k: np.dtype("int64"))  # fmt: skip
@@ -195,6 +199,10 @@ def register(shims: bool | None = None):
         min = TreeReduce.register(fx.DevReduce("min"), fx.DevReduce("min", phase="reduce"))
         mean = TreeReduce.register(fx.DevMeanMap(), fx.DevMeanReduce(), compute_dtypes=_f64)
         prod = TreeReduce.register(fx.DevReduce("prod"), fx.DevReduce("prod", phase="reduce"), compute_dtypes=_dtypes_sum)
+        any = TreeReduce.register(fx.DevBoolReduce("any"), fx.DevBoolReduce("any", phase="reduce"),
+                                  compute_dtypes=lambda *a, **k: np.dtype("bool"))  # qc.py:986
+        all = TreeReduce.register(fx.DevBoolReduce("all"), fx.DevBoolReduce("all", phase="reduce"),
+                                  compute_dtypes=lambda *a, **k: np.dtype("bool"))  # qc.py:987
         # GroupByReduce (qc.py:3741-3748)
         groupby_sum = B200GroupByReduce.register_agg("sum")
         groupby_count = B200GroupByReduce.register_agg("count")

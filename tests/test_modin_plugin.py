@@ -75,6 +75,12 @@ def _scenarios(mpd, ns):
     assert _same(P(mdf.round(2)).to_numpy(), orc.df_round(vals, 2, 4).to_numpy())
     assert _same(P(mdf.clip(-0.5, 0.75)).to_numpy(), orc.df_clip(vals, -0.5, 0.75, 4).to_numpy())
     assert np.allclose(P(mdf.prod()).to_numpy(), orc.df_prod(vals, 4).to_numpy(), rtol=1e-9, atol=0, equal_nan=True)
+    mask, pmask = (mdf > 0.0) & (mdf < 1.0), (vals > 0.0) & (vals < 1.0)
+    assert _same(P(mask).to_numpy().astype(float), pmask.to_numpy().astype(float))
+    assert _same(P(~mask | (mdf > 2.0)).to_numpy().astype(float), (~pmask | (vals > 2.0)).to_numpy().astype(float))
+    assert list(P(mask.sum()).to_numpy()) == list(pmask.sum().to_numpy())
+    assert list(P(mask.any()).to_numpy()) == list(pmask.any().to_numpy())
+    assert list(P((mdf > -100.0).all()).to_numpy()) == list((vals > -100.0).all().to_numpy())
     other = synth.host_frame(2003, 4, seed=12)
     mo = mpd.DataFrame(other)
     assert _same(P(mdf * mo + mo).to_numpy(), orc.a_mul_b_add_c(vals, other, other, 4).to_numpy())
