@@ -288,7 +288,9 @@ def run_b200_arm(args):
                 "algorithmic_bytes_per_launch": alg_bytes_local, "launch_ms": kernel_ms}  # fmt: skip
 
     also = []
-    if not args.skip_also:
+
+    def _secondary_legs():
+        nonlocal a
         # ---- TreeReduce: df.sum() over this frame (C3 uses 16 columns: two sweeps of 8 are one launch each)
         def step_sum():
             s = a.sum()
@@ -419,9 +421,15 @@ def run_b200_arm(args):
         os.environ.pop("MB200_JOIN_DENSE", None)
         del fact, dim
         torch.cuda.empty_cache()
-    else:
-        del a
-        torch.cuda.empty_cache()
+
+    if not args.skip_also:
+        try:
+            _secondary_legs()
+        except Exception as exc:  # a secondary leg must never cost the headline line
+            also.append({"metric": "secondary legs aborted", "error": f"{type(exc).__name__}: {exc}"[:400]})
+            os.environ.pop("MB200_JOIN_DENSE", None)
+    a = None
+    torch.cuda.empty_cache()
 
     # ---- e2e: host buffers in, host buffers out (rank-local sample) ---------------------------
     e2e = None
