@@ -300,3 +300,21 @@ def test_boolean_pipelines(cpu_device):
         m & df
     with pytest.raises(NotImplementedError):
         m.max()
+
+
+def test_repartition_rows_random_cuts(cpu_device):
+    """Property: re-cutting never changes the rows, whatever the source and target cuts."""
+    import modin_b200.pandas as bpd
+
+    rng = np.random.RandomState(7)
+    pdf = synth.host_frame(257, 2, seed=9, nan_per_64k=9000)
+    for trial in range(25):
+        config.NPartitions.put(int(rng.randint(1, 7)))
+        frame = bpd.DataFrame(pdf)._query_compiler._modin_frame
+        k = int(rng.randint(1, 6))
+        cuts = np.sort(rng.randint(0, 258, size=k - 1)) if k > 1 else np.array([], dtype=int)
+        lengths = np.diff(np.concatenate([[0], cuts, [257]])).tolist()
+        re = frame._repartition_rows(lengths)
+        assert sum(re.row_lengths) == 257 and [n for n in lengths if n] == re.row_lengths, (trial, lengths)
+        assert _same(re.to_pandas().to_numpy(), pdf.to_numpy())
+    config.NPartitions.put(4)
