@@ -259,7 +259,10 @@ int mb200_join_is_unique(mb200_join_table* table, int* unique, mb200_stream_t st
 int mb200_join_probe(mb200_join_table* table, const int64_t* fact_keys, int64_t nfact,
                      int64_t* out_idx, int64_t* out_nmatch_dev, mb200_stream_t stream);
 /* fused left-join payload gather for unique dim keys:
- * out[c][i] = hit ? dim_cols[c][idx] : NaN  (float64 payload; int64 payload promoted by caller) */
+ * out[c][i] = hit ? dim_cols[c][idx] : NaN  (float64 payload; int64 payload promoted by caller).
+ * out_nmatch_dev may be NULL.  A dense table probed with float64 payload and no match count keeps key-ordered
+ * copies of the payload columns (range x 8 B each, cached by source pointer until the table is destroyed or other
+ * columns are passed: the caller must keep the payload buffers alive that long) and reads one value per row. */
 int mb200_join_probe_gather(mb200_join_table* table, const int64_t* fact_keys, int64_t nfact,
                             int ncols, const void* const* dim_cols, int dim_dtype,
                             void* const* out_cols, int64_t* out_nmatch_dev,

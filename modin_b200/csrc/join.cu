@@ -48,6 +48,10 @@ struct mb200_join_table {
   int* rows;
   int persisted;  // holds a reference on the persisting L2 carve-out
   size_t carve_bytes, window_bytes;
+  // key-ordered copies of float64 payload columns (dense tables; see join_order_payload_kernel)
+  int nordered;
+  const void* ordered_src[MB200_MAX_COLS];
+  double* ordered[MB200_MAX_COLS];
 };
 
 namespace mb200 {
@@ -256,6 +260,53 @@ __global__ void __launch_bounds__(256) join_dense_probe_kernel(const int* __rest
   if (lane == 0 && hits && nmatch) atomicAdd(nmatch, hits);
 }
 
+// Key-ordered payload of a dense table: ord[g] = rows[g] >= 0 ? col[rows[g]] : NaN.  Built once per (table, payload
+// column) on the first left-join probe that does not need the match count; the probe then makes ONE random
+// read per fact row and payload column (ord[key - kmin]) instead of two (rows[], then col[row]).
+__global__ void join_order_payload_kernel(const int* __restrict__ rows, unsigned long long range,
+                                          const double* __restrict__ col, double* __restrict__ ord) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < (long long)range; g += stride) {
+    const int r = rows[g];
+    ord[g] = r >= 0 ? col[r] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
+struct OrderedParams {
+  const double* ord[MB200_MAX_COLS];
+  double* out[MB200_MAX_COLS];
+  int ncols;
+};
+
+__global__ void __launch_bounds__(256) join_dense_ordered_probe_kernel(long long kmin, unsigned long long range,
+                                                                       const long long* __restrict__ fact_keys,
+                                                                       long long n,
+                                                                       const __grid_constant__ OrderedParams g) {
+  constexpr int U = 4;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const uint64_t pol = l2_policy_evict_first();
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += nthreads * U) {
+    unsigned long long d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nthreads;
+      const long long k = i < n ? ldg_stream_i64(fact_keys + i, pol) : kmin - 1;
+      d[u] = (unsigned long long)k - (unsigned long long)kmin;
+    }
+    for (int c = 0; c < g.ncols; ++c) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (i0 + u * nthreads < n && d[u] < range) ? __ldg(g.ord[c] + d[u]) : nan;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * nthreads;
+        if (i < n) __stcs(g.out[c] + i, v[u]);
+      }
+    }
+  }
+}
+
 // ---- compaction of hit positions: block counts -> scan -> ranked scatter
 constexpr int kCompBlock = 256;
 constexpr int kCompItems = 2048;  // per block
@@ -444,6 +495,8 @@ extern "C" int mb200_join_destroy(mb200_join_table* t, mb200_stream_t stream) {
   if (!t) return 0;
   if (t->slots) cudaFreeAsync(t->slots, (cudaStream_t)stream);
   if (t->rows) cudaFreeAsync(t->rows, (cudaStream_t)stream);
+  for (int c = 0; c < t->nordered; ++c)
+    if (t->ordered[c]) cudaFreeAsync(t->ordered[c], (cudaStream_t)stream);
   if (t->meta) cudaFreeAsync(t->meta, (cudaStream_t)stream);
   if (t->persisted) l2_carveout_release();
   delete t;
@@ -544,6 +597,41 @@ extern "C" int mb200_join_probe_gather(mb200_join_table* t, const int64_t* fact_
   const unsigned int mask = (unsigned int)(t->cap - 1);
   unsigned long long* nm = reinterpret_cast<unsigned long long*>(out_nmatch_dev);
   const long long* fk = reinterpret_cast<const long long*>(fact_keys);
+  if (t->dense && dim_dtype == MB200_F64 && !out_nmatch_dev && ncols > 0) {
+    // left join, float64 payload, nobody asks for the match count: probe the key-ordered payload copies
+    // (MB200_JOIN_ORDERED=0 keeps the two-read probe)
+    const char* oe = getenv("MB200_JOIN_ORDERED");
+    if (!(oe && oe[0] == '0')) {
+      bool same = t->nordered == ncols;
+      for (int c = 0; same && c < ncols; ++c) same = t->ordered_src[c] == dim_cols[c];
+      if (!same) {
+        for (int c = 0; c < t->nordered; ++c)
+          if (t->ordered[c]) cudaFreeAsync(t->ordered[c], st);
+        t->nordered = 0;
+        int ogrid;
+        if (int rc = launch_grid((long long)t->range, 256, 8, &ogrid)) return rc;
+        for (int c = 0; c < ncols; ++c) {
+          t->ordered[c] = nullptr;
+          MB_CUDA(cudaMallocAsync((void**)&t->ordered[c], (size_t)t->range * 8, st));
+          t->ordered_src[c] = dim_cols[c];
+          t->nordered = c + 1;
+          join_order_payload_kernel<<<ogrid, 256, 0, st>>>(t->rows, t->range, static_cast<const double*>(dim_cols[c]),
+                                                          t->ordered[c]);
+          MB_LAUNCH_CHECK("join_order_payload_kernel");
+        }
+      }
+      OrderedParams op;
+      memset(&op, 0, sizeof(op));
+      op.ncols = ncols;
+      for (int c = 0; c < ncols; ++c) {
+        op.ord[c] = t->ordered[c];
+        op.out[c] = static_cast<double*>(out_cols[c]);
+      }
+      join_dense_ordered_probe_kernel<<<grid, 256, 0, st>>>(t->kmin, t->range, fk, nfact, op);
+      MB_LAUNCH_CHECK("join_dense_ordered_probe_kernel");
+      return 0;
+    }
+  }
   if (t->dense) {
     const char* pe = getenv("MB200_JOIN_PERSIST");
     const bool pin_payload = pe && pe[0] == 'p' && ncols > 0;

@@ -394,6 +394,12 @@ class JoinTable:
         groups = {}
         for j, c in enumerate(dim_cols):
             groups.setdefault(c.code, []).append(j)
+        # the match count is only needed to decide whether int64 payload has to be promoted (misses -> NaN), so
+        # only the int64 launch counts; float64-only payload lets the library probe its key-ordered payload
+        # copies (one random read per row).  The table caches those copies by source pointer: keep the
+        # source columns alive as long as the table is.
+        count_code = _lib.I64 if _lib.I64 in groups else None
+        self._payload_refs = list(dim_cols)
         for code, idxs in groups.items():
             if code == _lib.U8:
                 raise TypeError("bool payload columns are not on the device merge path")
@@ -401,7 +407,7 @@ class JoinTable:
             _lib.check(
                 self.lib.mb200_join_probe_gather(
                     self.handle, fact_keys.ptr, n, len(idxs), _lib.ptr_array([dim_cols[j].ptr for j in idxs]), code,
-                    _lib.ptr_array([c.ptr for c in sel_out]), nm.data_ptr() if code == list(groups)[0] else None,
+                    _lib.ptr_array([c.ptr for c in sel_out]), nm.data_ptr() if code == count_code else None,
                     current_stream(),
                 )
             )  # fmt: skip

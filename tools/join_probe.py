@@ -43,19 +43,20 @@ def main():
     pay = torch.randn(nd, dtype=torch.float64, device=dev)
     out = torch.empty(n, dtype=torch.float64, device=dev)
     nm = torch.zeros(1, dtype=torch.int64, device=dev)
-    for dense, persist in (("1", "0"), ("1", "rows"), ("1", "payload"), ("0", "0")):
+    for dense, persist, ordered in (("1", "0", "1"), ("1", "0", "0"), ("0", "0", "0")):
         os.environ["MB200_JOIN_DENSE"] = dense
         os.environ["MB200_JOIN_PERSIST"] = persist
+        os.environ["MB200_JOIN_ORDERED"] = ordered
         tab = C.c_void_p()
         _lib.check(lib.mb200_join_build(C.byref(tab), dk.data_ptr(), nd, st))
 
         def probe():
             _lib.check(lib.mb200_join_probe_gather(tab, keys.data_ptr(), n, 1, _lib.ptr_array([pay.data_ptr()]), _lib.F64,
-                                                   _lib.ptr_array([out.data_ptr()]), nm.data_ptr(), st))
+                                                   _lib.ptr_array([out.data_ptr()]), None if ordered == "1" else nm.data_ptr(), st))
 
         t = timeit(probe)
         _lib.check(lib.mb200_join_destroy(tab, st))
-        print(json.dumps({"dense": dense, "persist": persist, "probe_ms": round(t, 3), "Grows": round(n / t / 1e6, 2)}),
+        print(json.dumps({"dense": dense, "persist": persist, "ordered_payload": ordered, "probe_ms": round(t, 3), "Grows": round(n / t / 1e6, 2)}),
               flush=True)
 
 
