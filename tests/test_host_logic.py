@@ -159,3 +159,52 @@ def test_config_parameters():
         config.NPartitions.put(0)
     config.NPartitions.put(old)
     assert config.MinRowPartitionSize.get() == 32
+
+
+def test_dense_table_and_skew_decisions():
+    """Host-side rules that pick the table form (ops.dense_range_ok) and the hot-group cache (ops.keys_are_skewed)."""
+    from modin_b200 import _lib, ops
+
+    S = _lib.GB_SUM
+    assert ops.dense_range_ok(0, 999_999, 1 << 20, 10**9, 8, S)  # the benchmark: keys in [0, 1e6)
+    assert ops.dense_range_ok(-5, 5, 1024, 11, 3, S)  # tiny frames: range <= 65536 is always fine
+    assert not ops.dense_range_ok(0, 10**12, 1 << 20, 10**9, 8, S)  # ids spread over a huge range -> hash table
+    assert not ops.dense_range_ok(0, (1 << 29) + 1, 1 << 30, 10**10, 1, S)  # above the 2^29 group-id space
+    assert ops.dense_range_ok(0, 10**8, 1 << 20, 10**9, 1, S)  # range <= rows / 2 ...
+    assert not ops.dense_range_ok(0, 10**8, 1 << 20, 10**9, 32, S | _lib.GB_COUNT)  # ... unless the arrays pass 8 GiB
+    # skew: share of sampled keys that met their own value among 32 keys; uniform over G keys ~ 31 / G
+    assert not ops.keys_are_skewed(10**6, 31 * 10**6 // 4000)  # uniform, G = 4000 (below the shared-memory limit anyway)
+    assert ops.keys_are_skewed(10**6, 276_000)  # the Zipf-like generator: 27.6 %
+    assert not ops.keys_are_skewed(512, 500)  # too few samples to say anything
+
+
+def test_skewed_generator_is_heavy_headed_and_reproducible():
+    from modin_b200 import synth
+
+    a = synth.gen_i64_skew(200_000, 43, 0, 1_000_000)
+    assert np.array_equal(a[1000:2000], synth.gen_i64_skew(1000, 43, 0, 1_000_000, row_offset=1000))
+    assert a.min() == 0 and a.max() < 1_000_000
+    share0 = (a == 0).mean()
+    assert 0.08 < share0 < 0.2
+    top = np.sort(np.bincount(a[a < 4096], minlength=4096))[::-1]
+    assert top[:256].sum() / len(a) > 0.5  # the 256 hottest keys carry more than half of the rows
+    lv = synth.skew_levels(1_000_000)
+    assert len(lv) == 21 and int(lv[-1]) < 2**31 and np.all(np.diff(lv.astype(np.int64)) > 0)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) on a tiny sample."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-rows", "200000"], capture_output=True, text=True, timeout=300, cwd=ROOT)  # fmt: skip
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    j = json.loads(line)
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):  # fmt: skip
+        assert key in j, key
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
