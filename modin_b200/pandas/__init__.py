@@ -281,9 +281,10 @@ class DataFrame(BasePandasDataset):
             raise NotImplementedError("groupby(axis=1) is not on the B200 path")
         if level is not None:
             raise NotImplementedError("groupby(level=) is not on the B200 path")
+        kwargs = dict(as_index=as_index, sort=sort, group_keys=group_keys, observed=observed, dropna=dropna, level=level)
         if isinstance(by, (list, tuple)):
             if len(by) != 1:
-                raise NotImplementedError("multi-column groupby is not on the B200 path yet")
+                return _multi_key_groupby(self, list(by), kwargs)
             by = by[0]
         drop = False
         if isinstance(by, Series):
@@ -388,8 +389,93 @@ class Series(BasePandasDataset):
         return Series(query_compiler=frame._query_compiler)
 
 
+_PACKED_KEY = "__packed_key__"
+
+
+def _multi_key_groupby(df: "DataFrame", by: list, groupby_kwargs: dict) -> "DataFrameGroupBy":
+    """``df.groupby([k1, k2, ...])`` over int64 key columns: the keys are PACKED into one int64,
+    ``sum_i (k_i - min_i) * stride_i`` with ``stride_i = prod_{j>i} (max_j - min_j + 1)`` -- an order-preserving image of
+    the key tuples -- and the single-key device groupby (dense or hashed table) runs on it; the G result keys are
+    unpacked into a MultiIndex afterwards.  The reference gets the same result from pandas' own
+    ``get_group_index`` inside ``df.groupby([...])`` per block (alg/groupby.py:124-208).
+
+    Per row: one int64 AFFINE sweep per key column and k - 1 adds (device); per GROUP: one divmod on the host
+    (result-sized, not row-sized)."""
+    from .. import dist, ops
+    from ..block import DeviceBlock, concat_cols
+    from ..dataframe import B200Dataframe
+
+    for k in by:
+        if k not in df.columns:
+            raise KeyError(k)
+    if len(set(by)) != len(by):
+        raise ValueError("duplicate key columns")
+    frame = df._query_compiler._modin_frame
+    rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in frame._partitions]
+    pos = [int(df.columns.get_loc(k)) for k in by]
+    for b in rows:
+        for p in pos:
+            if b.cols[p].dtype != np.int64:
+                raise NotImplementedError("multi-column groupby on the B200 path needs int64 key columns")
+    # global [min, max] of every key column (one all_gather across ranks so that every rank packs alike)
+    mins, maxs = [], []
+    for p in pos:
+        st = ops.key_range_device([b.cols[p] for b in rows])
+        if dist.is_distributed():
+            per_rank = dist.all_gather_small(st[:2])
+            lo, hi = min(r[0] for r in per_rank), max(r[1] for r in per_rank)
+        else:
+            lo, hi = (int(v) for v in st[:2].tolist())
+        if lo > hi:
+            lo = hi = 0  # no rows anywhere
+        mins.append(lo)
+        maxs.append(hi)
+    ranges = [hi - lo + 1 for lo, hi in zip(mins, maxs)]
+    strides = [1] * len(by)
+    for i in range(len(by) - 2, -1, -1):
+        strides[i] = strides[i + 1] * ranges[i + 1]
+    if strides[0] * ranges[0] >= 1 << 62:
+        raise NotImplementedError("the key ranges of this multi-column groupby do not pack into 62 bits")
+    keep = [j for j in range(len(df.columns)) if j not in pos]
+    blocks = []
+    for b in rows:
+        packed = None
+        for p, lo, s in zip(pos, mins, strides):
+            term = ops.map_columns("affine", [b.cols[p]], s0=[s], s1=[-lo * s])[0] if b.nrows else b.cols[p]
+            packed = term if packed is None else ops.map_columns("add", [packed], [term])[0]
+        cols = [b.cols[j] for j in keep] + [packed]
+        labels = pandas.Index([df.columns[j] for j in keep] + [_PACKED_KEY])
+        blocks.append(DeviceBlock(cols, labels, nrows=b.nrows, range_start=b.range_start))
+    tmp = DataFrame(query_compiler=type(df._query_compiler)(B200Dataframe.from_blocks(blocks)))
+    g = DataFrameGroupBy(tmp, tmp[_PACKED_KEY]._query_compiler, drop=True, groupby_kwargs=groupby_kwargs)
+    g._unpack = (list(by), mins, ranges, strides)
+    return g
+
+
+def _unpack_group_keys(result_qc, unpack):
+    """Packed int64 group keys -> one device index column per original key (G values: host divmod)."""
+    from ..block import DeviceBlock, DeviceColumn
+    from ..dataframe import B200Dataframe
+
+    names, mins, ranges, strides = unpack
+    frame = result_qc._modin_frame
+    blocks = []
+    for row in frame._partitions:
+        if len(row) != 1:
+            raise NotImplementedError("multi-column groupby results wider than one column partition")
+        b = row[0].get()
+        packed = b.index_cols[0].to_numpy().astype(np.int64)
+        icols = [DeviceColumn.from_numpy(((packed // s) % r + lo).astype(np.int64)) for lo, r, s in zip(mins, ranges, strides)]
+        nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=icols, index_names=list(names))
+        nb.keys_sorted_unique = True
+        blocks.append(nb)
+    return type(result_qc)(B200Dataframe.from_blocks(blocks))
+
+
 class DataFrameGroupBy:
     """modin/pandas/groupby.py (``_wrap_aggregation`` :1829-1886)."""
+
+    _unpack = None  # set by _multi_key_groupby: (key labels, mins, ranges, strides)
 
     def __init__(self, df: DataFrame, by_qc, drop, groupby_kwargs):
         self._df = df
@@ -407,6 +493,8 @@ class DataFrameGroupBy:
             pass
         result_qc = qc_method(qc, by=self._by, axis=0, groupby_kwargs=self._kwargs, agg_args=agg_args or [],
                               agg_kwargs=agg_kwargs or {}, drop=self._drop)  # fmt: skip
+        if self._unpack is not None:
+            result_qc = _unpack_group_keys(result_qc, self._unpack)
         return DataFrame(query_compiler=result_qc)
 
     def sum(self, numeric_only=False, min_count=0):
@@ -479,6 +567,8 @@ class DataFrameGroupBy:
             nb.keys_sorted_unique = True
             blocks.append(nb)
         qc = type(self._query_compiler)(B200Dataframe.from_blocks(blocks))
+        if self._unpack is not None:
+            qc = _unpack_group_keys(qc, self._unpack)
         return DataFrame(query_compiler=qc)
 
     aggregate = agg

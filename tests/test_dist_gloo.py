@@ -209,6 +209,11 @@ def _full_stack_var_job(rank, ws):
         spec = {"c1": "max", "c0": "sum", "c2": "count"}
         agg = df.groupby("key").agg(spec)._query_compiler._modin_frame
         blks = [p.get() for p in agg._partitions[:, 0]]
+        pdf2 = pdf.copy()
+        pdf2["k2"] = synth.gen_i64(len(pdf2), 77, 1, 4) - 2
+        mk = bpd.DataFrame(pdf2).groupby(["key", "k2"]).sum()._to_pandas()  # gathers the per-rank key ranges in order
+        want2 = pdf2.groupby(["key", "k2"]).sum()
+        assert mk.index.equals(want2.index) and np.allclose(mk.to_numpy(), want2.to_numpy(), rtol=0, atol=1e-9)
         mask = (vals > 0.0) & (vals < 2.5)
         assert list(mask.any().to_numpy()) == [True, True, True] and list((vals > 2.5).all().to_numpy()) == [False] * 3
         assert list(mask.sum().to_numpy()) == list(((pdf[["c0", "c1", "c2"]] > 0.0) & (pdf[["c0", "c1", "c2"]] < 2.5)).sum().to_numpy())

@@ -567,3 +567,21 @@ def test_boolean_pipelines_on_device():
         assert_exact(mk.any().to_numpy(), pm.any().to_numpy(), "any")
         assert_exact(mk.all().to_numpy(), pm.all().to_numpy(), "all")
         assert_exact((df > -100.0).all().to_numpy(), (pdf > -100.0).all().to_numpy(), "all with NaN")
+
+
+def test_multi_key_groupby_packs_the_keys(gb_table_kind):
+    """groupby([k1, k2, ...]) on int64 keys: packed into one order-preserving int64 on the device, single-key
+    group table, MultiIndex unpacked from the G result keys."""
+    m = bpd()
+    n = 40_009
+    pdf = synth.host_frame(n, 3, seed=12, nan_per_64k=2000, key_modulus=97)
+    pdf["k2"] = synth.gen_i64(n, 99, 1, 11) * 10 - 20
+    df = m.DataFrame(pdf)
+    g, pg = df.groupby(["key", "k2"]), pdf.groupby(["key", "k2"])
+    abs_by_group = pdf[["c0", "c1", "c2"]].abs().groupby([pdf["key"], pdf["k2"]]).sum().to_numpy()
+    got, want = g.sum()._to_pandas(), pg.sum()
+    assert got.index.equals(want.index) and list(got.index.names) == ["key", "k2"]
+    assert_sum_close(got.to_numpy(), want.to_numpy(), abs_by_group, n, "multi-key sum")
+    for agg in ("count", "min", "max"):
+        assert_exact(getattr(g, agg)()._to_pandas().to_numpy(dtype=np.float64), getattr(pg, agg)().to_numpy(dtype=np.float64), agg)
+    assert_exact(g.size()._to_pandas().to_numpy(), pg.size().to_numpy(), "size")

@@ -318,3 +318,35 @@ def test_repartition_rows_random_cuts(cpu_device):
         assert sum(re.row_lengths) == 257 and [n for n in lengths if n] == re.row_lengths, (trial, lengths)
         assert _same(re.to_pandas().to_numpy(), pdf.to_numpy())
     config.NPartitions.put(4)
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_multi_key_groupby_packs_the_keys(cpu_device, dense):
+    import modin_b200.pandas as bpd
+
+    config.GroupbyDenseKeys.put(dense)
+    try:
+        pdf = synth.host_frame(6007, 3, seed=12, nan_per_64k=2000, key_modulus=7)
+        pdf["k2"] = synth.gen_i64(6007, 99, 1, 5) * 10 - 20  # negative base, gaps
+        pdf["k3"] = synth.gen_i64(6007, 98, 2, 3)
+        for keys in (["key", "k2"], ["k2", "key", "k3"]):
+            src = pdf if "k3" in keys else pdf.drop(columns="k3")  # value columns must be float64 on this path
+            g, pg = bpd.DataFrame(src).groupby(keys), src.groupby(keys)
+            for agg in ("sum", "count", "mean", "min", "max"):
+                got, want = getattr(g, agg)()._to_pandas(), getattr(pg, agg)()
+                assert list(got.index.names) == keys and list(got.columns) == list(want.columns)
+                assert got.index.equals(want.index), (keys, agg)
+                assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9,
+                                   equal_nan=True), (keys, agg)  # fmt: skip
+            sz = g.size()._to_pandas()
+            assert sz.index.equals(pg.size().index) and list(sz.to_numpy()) == list(pg.size().to_numpy())
+        df = bpd.DataFrame(pdf.drop(columns="k3"))
+        got = df.groupby(["key", "k2"]).agg({"c1": "max", "c0": "sum"})._to_pandas()
+        want = pdf.groupby(["key", "k2"]).agg({"c1": "max", "c0": "sum"})
+        assert got.index.equals(want.index) and np.allclose(got.to_numpy(), want.to_numpy(), atol=1e-9, equal_nan=True)
+        with pytest.raises(KeyError):
+            df.groupby(["key", "nope"])
+        with pytest.raises(NotImplementedError):
+            df.groupby(["key", "c0"])  # float key
+    finally:
+        config.GroupbyDenseKeys.put(True)
