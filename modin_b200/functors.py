@@ -21,7 +21,7 @@ import numpy as np
 import pandas
 
 from . import _lib, ops
-from .block import DeviceBlock, DeviceColumn, concat_rows
+from .block import DeviceBlock, DeviceColumn
 from .config import ReduceVariant
 
 MODIN_UNNAMED_SERIES_LABEL = "__reduced__"  # modin/utils.py:98

@@ -11,10 +11,9 @@ import ctypes as C
 from typing import List, Optional, Sequence
 
 import numpy as np
-import pandas
 
 from . import _lib
-from .block import DeviceBlock, DeviceColumn, current_stream, torch_mod, current_device
+from .block import DeviceColumn, current_device, current_stream, torch_mod
 
 _scratch_cache = {}
 

@@ -17,8 +17,7 @@ when the job spans several GPUs (dist.py).
 
 from __future__ import annotations
 
-import math
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Optional
 
 import numpy as np
 import pandas
