@@ -195,6 +195,60 @@ class B200Dataframe:
         return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
 
     # ---- Binary -----------------------------------------------------------------------------------
+    def relabel_columns(self, new_labels: pandas.Index) -> "B200Dataframe":
+        """New column labels over the same column buffers (no kernel, no copy)."""
+        bounds = np.cumsum([0] + list(self.column_widths))
+        pc = self._partition_mgr_cls._partition_class
+        new_rows = []
+        for row in self._partitions:
+            new_row = []
+            for j, p in enumerate(row):
+                blk = p.get()
+                new_row.append(pc(blk.with_cols(blk.cols, new_labels[bounds[j] : bounds[j + 1]])))
+            new_rows.append(new_row)
+        parts = np.array(new_rows, dtype=object).reshape(self._partitions.shape)
+        dtypes = None
+        if self._dtypes is not None:
+            dtypes = self._dtypes.copy()
+            dtypes.index = new_labels
+        return self.__constructor__(parts, self._index_cache, new_labels, self._row_lengths_cache,
+                                    self._column_widths_cache, dtypes)  # fmt: skip
+
+    def rowwise_to_column(self, func) -> "B200Dataframe":
+        """``func(whole row block) -> one-column block`` per row partition (a row-wise reduction such as
+        ``all(axis=1)``): same row partitioning and row labels, one column partition."""
+        from .block import concat_cols
+
+        pc = self._partition_mgr_cls._partition_class
+        new_rows = []
+        for row in self._partitions:
+            blk = concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get()
+            new_rows.append([pc(func(blk))])
+        parts = np.array(new_rows, dtype=object).reshape(len(new_rows), 1)
+        return self.__constructor__(parts, self._index_cache, None, self._row_lengths_cache, [1], None)
+
+    def filter_rows(self, mask: "B200Dataframe") -> "B200Dataframe":
+        """Rows where the one-column bool frame ``mask`` is True (boolean indexing; no cross-partition movement:
+        every row partition is compacted on its own, so the result keeps the partitioning and the row order)."""
+        from .functors import DevRowFilter
+
+        if len(mask.columns) != 1:
+            raise NotImplementedError("row selection takes a one-column bool mask")
+        if sum(mask.row_lengths) != sum(self.row_lengths):
+            raise ValueError("Item wrong length: the mask has to cover the rows of the frame one to one")
+        if mask.row_lengths != self.row_lengths:
+            mask = mask._repartition_rows(self.row_lengths)
+        from .block import concat_cols
+
+        pc = self._partition_mgr_cls._partition_class
+        fn = DevRowFilter()
+        new_rows = []
+        for row, mrow in zip(self._partitions, mask._partitions):
+            blk = concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get()
+            new_rows.append([pc(fn(blk, mrow[0].get()))])
+        parts = np.array(new_rows, dtype=object).reshape(len(new_rows), 1)
+        return self.__constructor__(parts, None, self._columns_cache, None, None, self._dtypes)
+
     def sort_by(self, col_position: int, ascending: bool = True, ignore_index: bool = False) -> "B200Dataframe":
         """Stable sort of the rows by one float64 / int64 column (NaN last) -- the device form of
         ``PandasDataframe.sort_by`` (df.py:2741-2791), which range-partitions the rows by sampled pivots

@@ -292,6 +292,63 @@ class DevLogical(DevFn):
         return block.with_cols(ops.map_columns(self.op, block.cols, other.cols))
 
 
+class DevRowLogical(DevFn):
+    """Row-wise ``all`` / ``any`` over the BOOL columns of a block -> one bool column (``df.all(axis=1)`` on the
+    result of a predicate; what ``dropna`` needs).  W - 1 logical sweeps."""
+
+    def __init__(self, op: str, label="__reduced__"):
+        if op not in ("all", "any"):
+            raise ValueError(op)
+        self.op, self.label = op, label
+
+    def __call__(self, block, *args, **kwargs):
+        _check_block(block, f"DevRowLogical({self.op})")
+        if not block.cols:
+            raise NotImplementedError("row-wise all / any of a frame without columns")
+        if any(c.dtype != np.bool_ for c in block.cols):
+            raise NotImplementedError("row-wise all / any on the B200 path needs bool columns")
+        acc = block.cols[0]
+        kop = "and" if self.op == "all" else "or"
+        for c in block.cols[1:]:
+            acc = ops.map_columns(kop, [acc], [c])[0] if block.nrows else acc
+        return block.with_cols([acc], pandas.Index([self.label]))
+
+
+class DevRowFilter(DevFn):
+    """``block[mask]`` for a co-partitioned bool column: boolean row selection (``df[bool_series]``,
+    ``df.dropna()``; the reference reaches it through ``getitem_array`` -> ``take_2d_labels_or_positional``,
+    df.py:1188-1389).  mask -> hit positions (ranked compaction) -> one gather per column; the surviving row
+    labels travel as a device index column."""
+
+    op = "row_filter"
+
+    def __call__(self, block, mask_block=None, *args, **kwargs):
+        _check_block(block, "DevRowFilter")
+        if not isinstance(mask_block, DeviceBlock) or len(mask_block.cols) != 1 or mask_block.cols[0].dtype != np.bool_:
+            raise NotImplementedError("row selection on the B200 path takes one co-partitioned bool column")
+        if mask_block.nrows != block.nrows:
+            raise ValueError("Item wrong length: the mask has to cover the rows of the frame one to one")
+        if any(c.dtype == np.bool_ for c in block.cols):
+            raise NotImplementedError("row selection of frames with bool columns is not on the B200 path")
+        if block.index_host is not None:
+            raise NotImplementedError("row selection keeps numeric / range row labels only")
+        if block.index_cols and len(block.index_cols) != 1:
+            raise NotImplementedError("row selection of a frame with a MultiIndex is not on the B200 path")
+        if block.nrows == 0:
+            return block
+        flags = ops.cast_columns_i64([mask_block.cols[0]])
+        idx = ops.map_columns("add_s", flags, s0=[-1])[0]  # 0 -> -1 (drop), 1 -> 0 (keep)
+        pos, k = ops.compact_hits(idx)
+        cols = ops.take_columns(block.cols, pos) if block.cols else []
+        if block.index_cols:
+            labels = ops.take_columns(block.index_cols, pos)[0]
+            names = block.index_names
+        else:
+            labels = ops.map_columns("add_s", [pos], s0=[int(block.range_start)])[0] if k else pos
+            names = [None]
+        return DeviceBlock(cols, block.columns, nrows=k, index_cols=[labels], index_names=names)
+
+
 class DevBoolReduce(DevFn):
     """``df.any()`` / ``df.all()`` over BOOL columns -- ``TreeReduce.register(pandas.DataFrame.any / all)``
     (qc.py:986-987): any = max, all = min of the 0 / 1 values, per partition and again over the partials

@@ -41,6 +41,11 @@ class BasePandasDataset:
     def _binary_op(self, op, other, **kwargs):
         """modin/pandas/base.py:485-542."""
         other_qc = self._validate_other(other)
+        if isinstance(other, Series) and isinstance(self, Series) and self.name != other.name:
+            # Series (op) Series aligns on the row labels, not on the names; pandas drops the name when they differ
+            unnamed = pandas.Index([MODIN_UNNAMED_SERIES_LABEL])
+            new_qc = getattr(self._query_compiler.relabel_columns(unnamed), op)(other_qc.relabel_columns(unnamed), **kwargs)
+            return self._create_or_update_from_compiler(new_qc)
         if isinstance(other, Series) and isinstance(self, DataFrame):
             if kwargs.get("axis") in (0, "index"):
                 # frame (op) Series along the rows: a column vector co-partitioned with the frame -> the
@@ -265,7 +270,25 @@ class DataFrame(BasePandasDataset):
     def __len__(self):
         return self._query_compiler.get_axis_len(0)
 
+    def dropna(self, *, axis=0, how="any", subset=None, inplace=False, ignore_index=False, **kwargs):
+        """Drop rows with missing values: ``notna()`` -> row-wise all / any -> boolean row selection, all on the
+        device (the reference: qc.dropna, a full-axis apply of ``pandas.DataFrame.dropna``)."""
+        if axis not in (0, "index") or inplace or ignore_index or kwargs.get("thresh") is not None:
+            raise NotImplementedError("dropna on the B200 path: rows only, how='any'|'all', optional subset")
+        if how not in ("any", "all"):
+            raise ValueError(f"invalid how option: {how}")
+        cols = list(self.columns) if subset is None else ([subset] if not isinstance(subset, (list, tuple)) else list(subset))
+        probe = self[cols].notna()._query_compiler
+        keep = probe.row_all() if how == "any" else probe.row_any()
+        return DataFrame(query_compiler=self._query_compiler.getitem_row_mask(keep))
+
     def __getitem__(self, key):
+        if isinstance(key, Series) or (isinstance(key, DataFrame) and len(key.columns) == 1 and
+                                       key._query_compiler.dtypes.iloc[0] == np.bool_):  # fmt: skip
+            # boolean row selection: df[df["c0"] > 0]
+            if key._query_compiler.dtypes.iloc[0] != np.bool_:
+                raise NotImplementedError("indexing a frame with a non-bool Series is not on the B200 path")
+            return DataFrame(query_compiler=self._query_compiler.getitem_row_mask(key._query_compiler))
         if isinstance(key, (list, pandas.Index, np.ndarray)):
             return DataFrame(query_compiler=self._query_compiler.getitem_column_array(list(key)))
         if key not in self.columns:

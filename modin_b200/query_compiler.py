@@ -118,6 +118,29 @@ class B200QueryCompiler:
         pos = int(self.columns.get_loc(cols[0]))
         return self.__constructor__(self._modin_frame.sort_by(pos, bool(asc), bool(kwargs.get("ignore_index", False))))
 
+    def relabel_columns(self, new_labels):
+        """Same buffers, new column labels (metadata only; ``qc.columns = ...`` in the reference)."""
+        new_labels = pandas.Index(new_labels)
+        if len(new_labels) != len(self.columns):
+            raise ValueError("Length mismatch: expected axis has %d elements, new values have %d elements"
+                             % (len(self.columns), len(new_labels)))  # fmt: skip
+        return self.__constructor__(self._modin_frame.relabel_columns(new_labels))
+
+    def getitem_row_mask(self, mask_qc):
+        """``df[bool_series]`` (qc.getitem_array with a boolean key, qc.py:2907-2960): rows where the mask holds."""
+        return self.__constructor__(self._modin_frame.filter_rows(mask_qc._modin_frame))
+
+    def row_all(self):
+        """Row-wise AND over bool columns -> one bool column (``(...).all(axis=1)``; used by dropna)."""
+        from .functors import DevRowLogical
+
+        return self.__constructor__(self._modin_frame.rowwise_to_column(DevRowLogical("all")))
+
+    def row_any(self):
+        from .functors import DevRowLogical
+
+        return self.__constructor__(self._modin_frame.rowwise_to_column(DevRowLogical("any")))
+
     def getitem_column_array(self, key, numeric=False, ignore_order=False):
         """qc.py:2885-2905."""
         if numeric:

@@ -350,3 +350,34 @@ def test_multi_key_groupby_packs_the_keys(cpu_device, dense):
             df.groupby(["key", "c0"])  # float key
     finally:
         config.GroupbyDenseKeys.put(True)
+
+
+def test_boolean_row_selection_and_dropna(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(3001, 3, seed=21, nan_per_64k=6000, key_modulus=9)
+    df = bpd.DataFrame(pdf)
+    for got, want in (
+        (df[df["c0"] > 0.5], pdf[pdf["c0"] > 0.5]),
+        (df[(df["c0"] > 0.0) & (df["c1"] < 0.0)], pdf[(pdf["c0"] > 0.0) & (pdf["c1"] < 0.0)]),
+        (df[df["key"] == 3], pdf[pdf["key"] == 3]),
+        (df[df["c2"] > 100.0], pdf[pdf["c2"] > 100.0]),  # nothing survives
+        (df.dropna(), pdf.dropna()),
+        (df.dropna(how="all", subset=["c0", "c1"]), pdf.dropna(how="all", subset=["c0", "c1"])),
+        (df.dropna(subset=["c2"]), pdf.dropna(subset=["c2"])),
+    ):
+        g = got._to_pandas()
+        assert list(g.index) == list(want.index) and list(g.columns) == list(want.columns)
+        assert _same(g.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    # the filtered frame is a normal frame: reduce / group / filter again
+    sel = df[df["c0"] > 0.0]
+    assert np.allclose(sel.sum().to_numpy(), pdf[pdf["c0"] > 0.0].sum().to_numpy(), atol=1e-9)
+    g = sel.groupby("key").count()._to_pandas()
+    assert _same(g.to_numpy(), pdf[pdf["c0"] > 0.0].groupby("key").count().to_numpy())
+    again = sel[sel["c1"] > 0.0]._to_pandas()
+    want = pdf[(pdf["c0"] > 0.0) & (pdf["c1"] > 0.0)]
+    assert list(again.index) == list(want.index) and _same(again.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    with pytest.raises(ValueError):
+        df[bpd.DataFrame(pdf.iloc[:100])["c0"] > 0.0]
+    with pytest.raises(NotImplementedError):
+        df[df["c0"]]
