@@ -195,6 +195,56 @@ class B200Dataframe:
         return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
 
     # ---- Binary -----------------------------------------------------------------------------------
+    def hstack(self, other: "B200Dataframe") -> "B200Dataframe":
+        """Columns of ``self`` followed by the columns of ``other`` (same rows, same row labels): the column half of
+        ``PandasDataframe.concat(axis=1)`` (df.py:3952-4096) for operands that only need their row cuts aligned.
+        Buffers are shared; up to 32 columns stay one column partition."""
+        from .block import concat_cols
+
+        if sum(self.row_lengths) != sum(other.row_lengths):
+            raise ValueError("Length of values does not match length of index")
+        if other.row_lengths != self.row_lengths:
+            other = other._repartition_rows(self.row_lengths)
+        if len(set(self.columns) & set(other.columns)):
+            raise ValueError("hstack needs distinct column labels")
+        pc = self._partition_mgr_cls._partition_class
+        total = len(self.columns) + len(other.columns)
+        new_rows = []
+        for row, orow in zip(self._partitions, other._partitions):
+            if total <= 32:
+                new_rows.append([pc(concat_cols([p.get() for p in row] + [p.get() for p in orow]))])
+            else:
+                new_rows.append(list(row) + list(orow))
+        parts = np.array(new_rows, dtype=object).reshape(len(new_rows), -1)
+        widths = [total] if total <= 32 else list(self.column_widths) + list(other.column_widths)
+        return self.__constructor__(parts, self._index_cache, self.columns.append(other.columns), self._row_lengths_cache,
+                                    widths, None)  # fmt: skip
+
+    def head_rows(self, n: int) -> "B200Dataframe":
+        """First ``n`` rows of the job-wide frame (views of the first partitions' buffers)."""
+        n = max(int(n), 0)
+        lo = dist.exclusive_row_offset(len(self)) if dist.is_distributed() else 0
+        take = max(0, min(len(self), n - lo))
+        return self._slice_local(0, take)
+
+    def tail_rows(self, n: int) -> "B200Dataframe":
+        n = max(int(n), 0)
+        total = self.global_nrows
+        lo = dist.exclusive_row_offset(len(self)) if dist.is_distributed() else 0
+        start = max(0, (total - n) - lo)
+        return self._slice_local(min(start, len(self)), len(self))
+
+    def _slice_local(self, start: int, stop: int) -> "B200Dataframe":
+        cut = self._repartition_rows([start, stop - start, len(self) - stop])
+        bounds = np.cumsum([0] + list(cut.row_lengths))
+        keep = [i for i in range(len(cut.row_lengths)) if bounds[i] >= start and bounds[i + 1] <= stop and cut.row_lengths[i]]
+        if not keep:  # empty selection: a zero-row view of the first partition
+            pc = self._partition_mgr_cls._partition_class
+            parts = np.array([[pc(p.get().slice_rows(0, 0)) for p in self._partitions[0]]], dtype=object)
+            return self.__constructor__(parts, None, self._columns_cache, None, self._column_widths_cache, self._dtypes)
+        return self.__constructor__(cut._partitions[keep, :], None, self._columns_cache, [cut.row_lengths[i] for i in keep],
+                                    self._column_widths_cache, self._dtypes)  # fmt: skip
+
     def relabel_columns(self, new_labels: pandas.Index) -> "B200Dataframe":
         """New column labels over the same column buffers (no kernel, no copy)."""
         bounds = np.cumsum([0] + list(self.column_widths))

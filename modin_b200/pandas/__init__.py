@@ -270,6 +270,51 @@ class DataFrame(BasePandasDataset):
     def __len__(self):
         return self._query_compiler.get_axis_len(0)
 
+    # ---- structure (metadata only: buffers are shared, nothing is copied or launched) --------------------------
+    def copy(self, deep=True):
+        return DataFrame(query_compiler=self._query_compiler)  # blocks are immutable values
+
+    def __setitem__(self, key, value):
+        """``df["d"] = df["a"] * 2`` -- a co-partitioned Series (or one-column frame) becomes / replaces a column."""
+        if isinstance(key, (list, tuple)):
+            raise NotImplementedError("assigning several columns at once is not on the B200 path")
+        if isinstance(value, (Series, DataFrame)):
+            vqc = value._query_compiler
+            if len(vqc.columns) != 1:
+                raise ValueError("Cannot set a DataFrame with multiple columns to the single column " + str(key))
+        else:
+            raise NotImplementedError("column assignment on the B200 path takes a device Series")
+        self._query_compiler = self._query_compiler.set_column(key, vqc)
+
+    def assign(self, **kwargs):
+        out = self.copy()
+        for k, v in kwargs.items():
+            out[k] = v(out) if callable(v) else v
+        return out
+
+    def drop(self, labels=None, *, axis=0, index=None, columns=None, inplace=False, errors="raise", **kwargs):
+        if inplace or index is not None or (labels is not None and axis in (0, "index")):
+            raise NotImplementedError("drop on the B200 path removes columns")
+        cols = columns if columns is not None else labels
+        cols = [cols] if not isinstance(cols, (list, tuple, pandas.Index)) else list(cols)
+        missing = [c for c in cols if c not in self.columns]
+        if missing and errors == "raise":
+            raise KeyError(f"{missing} not found in axis")
+        return self[[c for c in self.columns if c not in cols]]
+
+    def rename(self, mapper=None, *, columns=None, axis=None, inplace=False, **kwargs):
+        if inplace or (mapper is not None and axis not in (1, "columns")) or kwargs.get("index") is not None:
+            raise NotImplementedError("rename on the B200 path renames columns")
+        mapping = columns if columns is not None else mapper
+        new = [mapping(c) if callable(mapping) else mapping.get(c, c) for c in self.columns]
+        return DataFrame(query_compiler=self._query_compiler.relabel_columns(new))
+
+    def head(self, n=5):
+        return DataFrame(query_compiler=self._query_compiler.head(n))
+
+    def tail(self, n=5):
+        return DataFrame(query_compiler=self._query_compiler.tail(n))
+
     def dropna(self, *, axis=0, how="any", subset=None, inplace=False, ignore_index=False, **kwargs):
         """Drop rows with missing values: ``notna()`` -> row-wise all / any -> boolean row selection, all on the
         device (the reference: qc.dropna, a full-axis apply of ``pandas.DataFrame.dropna``)."""

@@ -126,6 +126,25 @@ class B200QueryCompiler:
                              % (len(self.columns), len(new_labels)))  # fmt: skip
         return self.__constructor__(self._modin_frame.relabel_columns(new_labels))
 
+    def set_column(self, label, value_qc):
+        """``df[label] = series``: append (or replace) one column, sharing every buffer (qc.setitem / insert)."""
+        value_qc = value_qc.relabel_columns([label])
+        labels = list(self.columns)
+        if label in labels:
+            pos = labels.index(label)
+            others = [i for i in range(len(labels)) if i != pos]
+            base = self.__constructor__(self._modin_frame.take_2d_labels_or_positional(col_positions=others))
+            stacked = self.__constructor__(base._modin_frame.hstack(value_qc._modin_frame))
+            order = list(range(pos)) + [len(others)] + list(range(pos, len(others)))
+            return self.__constructor__(stacked._modin_frame.take_2d_labels_or_positional(col_positions=order))
+        return self.__constructor__(self._modin_frame.hstack(value_qc._modin_frame))
+
+    def head(self, n):
+        return self.__constructor__(self._modin_frame.head_rows(n))
+
+    def tail(self, n):
+        return self.__constructor__(self._modin_frame.tail_rows(n))
+
     def getitem_row_mask(self, mask_qc):
         """``df[bool_series]`` (qc.getitem_array with a boolean key, qc.py:2907-2960): rows where the mask holds."""
         return self.__constructor__(self._modin_frame.filter_rows(mask_qc._modin_frame))

@@ -381,3 +381,35 @@ def test_boolean_row_selection_and_dropna(cpu_device):
         df[bpd.DataFrame(pdf.iloc[:100])["c0"] > 0.0]
     with pytest.raises(NotImplementedError):
         df[df["c0"]]
+
+
+def test_structural_ops_share_buffers(cpu_device):
+    """setitem / assign / drop / rename / head / tail are metadata: no kernel, no copy."""
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(1003, 3, seed=31, nan_per_64k=1000, key_modulus=5)
+    df = bpd.DataFrame(pdf)
+    df2 = df.copy()
+    df2["d"] = df2["c0"] * 2.0
+    want = pdf.copy()
+    want["d"] = want["c0"] * 2.0
+    assert list(df2.columns) == list(want.columns) and _same(df2._to_pandas().to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    assert list(df.columns) == list(pdf.columns)  # the original is untouched
+    df2["c1"] = df2["c0"] + df2["c2"]  # replace in place, order kept
+    want["c1"] = want["c0"] + want["c2"]
+    assert list(df2.columns) == list(want.columns) and _same(df2._to_pandas().to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    a = df.assign(e=lambda x: x["c0"] - x["c1"], f=df["c2"])
+    wa = pdf.assign(e=lambda x: x["c0"] - x["c1"], f=pdf["c2"])
+    assert list(a.columns) == list(wa.columns) and _same(a._to_pandas().to_numpy(dtype=np.float64), wa.to_numpy(dtype=np.float64))
+    assert list(df.drop(columns=["c1", "key"]).columns) == ["c0", "c2"]
+    assert list(df.rename(columns={"c0": "x"}).columns) == ["key", "x", "c1", "c2"]
+    with pytest.raises(KeyError):
+        df.drop(columns=["nope"])
+    for n in (0, 1, 5, 250, 251, 1003, 5000):
+        assert _same(df.head(n)._to_pandas().to_numpy(dtype=np.float64), pdf.head(n).to_numpy(dtype=np.float64)), n
+        assert _same(df.tail(n)._to_pandas().to_numpy(dtype=np.float64), pdf.tail(n).to_numpy(dtype=np.float64)), n
+    assert list(df.tail(7)._to_pandas().index) == list(pdf.tail(7).index)
+    # a pipeline on top: filter, derive, aggregate
+    out = df[df["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()._to_pandas()
+    w = pdf[pdf["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()
+    assert list(out.columns) == list(w.columns) and np.allclose(out.to_numpy(), w.to_numpy(), atol=1e-9)

@@ -46,3 +46,29 @@ def test_boolean_row_selection_and_dropna_on_device():
         _exact(sel.groupby("key").count()._to_pandas().to_numpy(), want.groupby("key").count().to_numpy(), "count after filter")
     finally:
         config.NPartitions.put(old)
+
+
+def test_pipeline_filter_derive_aggregate_on_device():
+    """setitem / assign / drop / rename / head / tail are metadata over shared buffers; a whole pipeline stays on
+    the device: filter -> derived column -> groupby."""
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        pdf = synth.host_frame(50_003, 3, seed=31, nan_per_64k=1000, key_modulus=5)
+        df = bpd.DataFrame(pdf)
+        out = df[df["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()._to_pandas()
+        w = pdf[pdf["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()
+        assert list(out.columns) == list(w.columns) and np.allclose(out.to_numpy(), w.to_numpy(), rtol=0, atol=1e-8)
+        d2 = df.copy()
+        d2["c1"] = d2["c0"] + d2["c2"]
+        want = pdf.copy()
+        want["c1"] = want["c0"] + want["c2"]
+        _exact(d2._to_pandas().to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), "setitem replace")
+        for n in (0, 7, 12_501, 50_003):
+            _exact(df.head(n)._to_pandas().to_numpy(dtype=np.float64), pdf.head(n).to_numpy(dtype=np.float64), f"head {n}")
+            _exact(df.tail(n)._to_pandas().to_numpy(dtype=np.float64), pdf.tail(n).to_numpy(dtype=np.float64), f"tail {n}")
+    finally:
+        config.NPartitions.put(old)
