@@ -292,6 +292,43 @@ class DevLogical(DevFn):
         return block.with_cols(ops.map_columns(self.op, block.cols, other.cols))
 
 
+class DevIsin(DevFn):
+    """``frame.isin(values)`` for int64 columns and a list of integers -- ``Map.register(pandas.DataFrame.isin)``
+    (qc.py `isin`): a membership test is a join probe without payload: build a (dense or hashed) table over the
+    distinct values once, probe every column, ``index >= 0`` is the answer."""
+
+    op = "isin"
+
+    def __init__(self, values):
+        vals = np.asarray(list(values))
+        if vals.size and vals.dtype.kind not in "iu":
+            raise NotImplementedError("device isin takes integer values")
+        self.values = np.unique(vals.astype(np.int64))
+        self._tables = {}
+
+    def _table(self, device):
+        tab = self._tables.get(device)
+        if tab is None:
+            tab = ops.JoinTable(DeviceColumn.from_numpy(self.values))
+            self._tables[device] = tab
+        return tab
+
+    def __call__(self, block, *args, **kwargs):
+        _check_block(block, "DevIsin")
+        if any(c.dtype != np.int64 for c in block.cols):
+            raise NotImplementedError("device isin tests int64 columns")
+        if not block.cols or block.nrows == 0:
+            return block.with_cols([DeviceColumn.empty(block.nrows, np.bool_) for _ in block.cols])
+        if self.values.size == 0:
+            return block.with_cols(ops.map_columns("ne", list(block.cols), list(block.cols)))  # all False
+        tab = self._table(str(block.cols[0].data.device))
+        out = []
+        for c in block.cols:
+            idx, _ = tab.probe(c)
+            out.extend(ops.map_columns("ge_s", [idx], s0=[0]))
+        return block.with_cols(out)
+
+
 class DevRowLogical(DevFn):
     """Row-wise ``all`` / ``any`` over the BOOL columns of a block -> one bool column (``df.all(axis=1)`` on the
     result of a predicate; what ``dropna`` needs).  W - 1 logical sweeps."""

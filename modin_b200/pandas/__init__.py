@@ -85,6 +85,11 @@ class BasePandasDataset:
             raise NotImplementedError("clip(inplace=True) is not on the B200 path")
         return self._create_or_update_from_compiler(self._query_compiler.clip(lower=lower, upper=upper))
 
+    def isin(self, values):
+        if isinstance(values, (BasePandasDataset, pandas.Series, pandas.DataFrame, dict)):
+            raise NotImplementedError("isin on the B200 path takes a list / array of integers")
+        return self._create_or_update_from_compiler(self._query_compiler.isin(values))
+
     def isna(self):
         return self._create_or_update_from_compiler(self._query_compiler.isna())
 

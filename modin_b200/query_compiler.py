@@ -145,6 +145,12 @@ class B200QueryCompiler:
     def tail(self, n):
         return self.__constructor__(self._modin_frame.tail_rows(n))
 
+    def isin(self, values, **kwargs):
+        """qc.py ``isin = Map.register(pandas.DataFrame.isin, dtypes=np.bool_)``: integer values, int64 columns."""
+        from .functors import DevIsin
+
+        return self.__constructor__(self._modin_frame.map(DevIsin(values), dtypes=np.bool_))
+
     def getitem_row_mask(self, mask_qc):
         """``df[bool_series]`` (qc.getitem_array with a boolean key, qc.py:2907-2960): rows where the mask holds."""
         return self.__constructor__(self._modin_frame.filter_rows(mask_qc._modin_frame))

@@ -413,3 +413,23 @@ def test_structural_ops_share_buffers(cpu_device):
     out = df[df["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()._to_pandas()
     w = pdf[pdf["c0"] > 0.0].assign(g=lambda x: x["c1"] * x["c2"]).groupby("key").sum()
     assert list(out.columns) == list(w.columns) and np.allclose(out.to_numpy(), w.to_numpy(), atol=1e-9)
+
+
+def test_isin_is_a_join_probe(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(2003, 2, seed=5, key_modulus=50)
+    pdf["k2"] = synth.gen_i64(2003, 3, 1, 9) - 4
+    df = bpd.DataFrame(pdf)
+    vals = [3, 7, 7, 41, -2, 1000]
+    got = df[["key", "k2"]].isin(vals)._to_pandas()
+    want = pdf[["key", "k2"]].isin(vals)
+    assert _same(got.to_numpy().astype(float), want.to_numpy().astype(float))
+    sel = df[df["key"].isin([1, 2, 3])]._to_pandas()
+    w = pdf[pdf["key"].isin([1, 2, 3])]
+    assert list(sel.index) == list(w.index) and _same(sel.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64))
+    assert not df["key"].isin([])._to_pandas().any()
+    with pytest.raises(NotImplementedError):
+        df[["c0"]].isin([1])
+    with pytest.raises(NotImplementedError):
+        df["key"].isin([1.5])

@@ -72,3 +72,17 @@ def test_pipeline_filter_derive_aggregate_on_device():
             _exact(df.tail(n)._to_pandas().to_numpy(dtype=np.float64), pdf.tail(n).to_numpy(dtype=np.float64), f"tail {n}")
     finally:
         config.NPartitions.put(old)
+
+
+def test_isin_is_a_join_probe_on_device():
+    import modin_b200.pandas as bpd
+
+    pdf = synth.host_frame(30_011, 2, seed=5, key_modulus=500)
+    df = bpd.DataFrame(pdf)
+    vals = [3, 7, 7, 41, -2, 100_000]
+    got = df[["key"]].isin(vals)._to_pandas()
+    assert np.array_equal(got.to_numpy(), pdf[["key"]].isin(vals).to_numpy())
+    sel = df[df["key"].isin([1, 2, 3])]._to_pandas()
+    w = pdf[pdf["key"].isin([1, 2, 3])]
+    assert np.array_equal(sel.index.to_numpy(), w.index.to_numpy())
+    _exact(sel.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), "filter by isin")
