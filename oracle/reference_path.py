@@ -228,9 +228,10 @@ def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) ->
 
     partials = _pmap(lambda b: map_fn(b.copy()), row_blocks, threads)
     stacked = pandas.concat(partials, axis=0)
+    levels = list(range(len(by))) if isinstance(by, (list, tuple)) else 0  # several key columns -> MultiIndex levels
     if agg in ("min", "max"):  # impl table storage_formats/pandas/groupby.py:237-248: ("min","min"), ("max","max")
-        return getattr(stacked.groupby(level=0, sort=True), agg)()
-    regrouped = stacked.groupby(level=0, sort=True).sum()
+        return getattr(stacked.groupby(level=levels, sort=True), agg)()
+    regrouped = stacked.groupby(level=levels, sort=True).sum()
     if agg == "mean":
         return regrouped["sum"] / regrouped["count"]
     if agg == "size":
@@ -318,3 +319,47 @@ def sort_values(df, by: str, ascending: bool, npartitions: int, kind: str = "sta
                 ranges[r].append(sel)
     out = [pandas.concat(parts).sort_values(by, ascending=ascending, kind=kind) for parts in ranges if parts]
     return pandas.concat(out)
+
+
+# ------------------------------------------------------------------ more registrations, second batch
+_DICT_REDUCE = {"sum": "sum", "count": "sum", "min": "min", "max": "max"}  # storage_formats/pandas/groupby.py:237-248
+
+
+def groupby_dict_reduce(df, by, spec: dict, npartitions: int) -> pandas.DataFrame:
+    """``df.groupby(by).agg({column: function})`` -- qc._groupby_dict_reduce (query_compiler.py:3876-3970): the
+    dictionary is split into a map dictionary (per row block) and a reduce dictionary (sum of sums / counts,
+    min of mins, max of maxes) applied to the concatenated partial tables."""
+    grid = split_into_partitions(df, npartitions)
+    row_blocks = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
+    partials = [b.groupby(by, as_index=True, sort=True, observed=True).agg(spec) for b in row_blocks]
+    stacked = pandas.concat(partials, axis=0)
+    levels = list(range(len(by))) if isinstance(by, (list, tuple)) else 0
+    return stacked.groupby(level=levels, sort=True).agg({c: _DICT_REDUCE[f] for c, f in spec.items()})
+
+
+def df_logical(df_a, df_b, op: str, npartitions: int) -> pandas.DataFrame:
+    """Binary.register(pandas.DataFrame.__and__ / __or__ / __xor__) (query_compiler.py:541-571) on co-partitioned frames."""
+    return to_pandas(n_ary_op([df_a, df_b], lambda a, b: getattr(a, op)(b), npartitions))
+
+
+def df_any_all(df, which: str, npartitions: int):
+    """qc.any / qc.all = TreeReduce.register(pandas.DataFrame.any / all) (query_compiler.py:986-987)."""
+    fn = (lambda x: x.any(axis=0)) if which == "any" else (lambda x: x.all(axis=0))
+    return tree_reduce(df, fn, None, npartitions)
+
+
+def df_isin(df, values, npartitions: int) -> pandas.DataFrame:
+    """qc.isin = Map.register(pandas.DataFrame.isin)."""
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), lambda b: b.isin(values)))
+
+
+def filter_rows(df, mask: pandas.Series, npartitions: int) -> pandas.DataFrame:
+    """``df[bool_series]``: every row partition keeps its rows where the co-partitioned mask holds; partition order
+    and row labels are preserved (the reference goes through getitem_array -> take_2d_labels_or_positional)."""
+    grid = split_into_partitions(df, npartitions)
+    out, pos = [], 0
+    for row in grid:
+        blk = pandas.concat(row, axis=1) if len(row) > 1 else row[0]
+        out.append(blk[mask.iloc[pos : pos + len(blk)].to_numpy()])
+        pos += len(blk)
+    return pandas.concat(out, axis=0)

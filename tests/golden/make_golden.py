@@ -128,6 +128,40 @@ def main():
         save(f"ext_groupby_n{n}_g{G}_v{V}_nan{nan}", meta=np.array([n, G, V, nan, 42, 43]), keys=mn.index.to_numpy(),
              min=mn.to_numpy(), max=mx.to_numpy())
 
+    # ---- second batch: logical ops, any / all, bool sums, isin, boolean row selection, dropna, multi-key groupby,
+    # dictionary aggregation, value_counts, nunique
+    for n, nan in ((3001, 6000),):
+        pdf = synth.host_frame(n, 3, seed=21, nan_per_64k=nan, key_modulus=9)
+        pdf["k2"] = synth.gen_i64(n, 99, 1, 5) * 10 - 20
+        mdf = mpd.DataFrame(pdf)
+        v = ["c0", "c1", "c2"]
+        band = (mdf[v] > 0.0) & (mdf[v] < 1.0)
+        sel = P(mdf[mdf["c0"] > 0.5])
+        dn = P(mdf.dropna())
+        mk = P(mdf.groupby(["key", "k2"]).sum())
+        da = P(mdf.groupby("key").agg({"c1": "max", "c0": "sum", "c2": "count"}))
+        vc = P(mdf["key"].value_counts())
+        save(
+            f"ext2_n{n}_nan{nan}",
+            meta=np.array([n, 21, nan, 9]),
+            band=P(band).to_numpy(),
+            bor=P((mdf[v] > 0.5) | (mdf[v] < -0.5)).to_numpy(),
+            bxor=P((mdf[v] > 0.0) ^ (mdf[v] > 1.0)).to_numpy(),
+            bnot=P(~band).to_numpy(),
+            any=P(band.any()).to_numpy(),
+            all_true=P((mdf[v] > -100.0).all()).to_numpy(),
+            boolsum=P(band.sum()).to_numpy(),
+            boolmean=P(band.mean()).to_numpy(),
+            isin=P(mdf[["key", "k2"]].isin([3, 7, -20, 30])).to_numpy(),
+            sel_index=sel.index.to_numpy(), sel=sel.to_numpy(dtype=np.float64),
+            dropna_index=dn.index.to_numpy(), dropna=dn.to_numpy(dtype=np.float64),
+            mk_k1=mk.index.get_level_values(0).to_numpy(), mk_k2=mk.index.get_level_values(1).to_numpy(),
+            mk_sum=mk.to_numpy(),
+            dict_keys=da.index.to_numpy(), dict_agg=da.to_numpy(dtype=np.float64),
+            vc_counts=vc.to_numpy(), vc_keys=vc.index.to_numpy(),
+            nunique=np.array([mdf["key"].nunique()]),
+        )
+
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):
         pdf = synth.host_frame(n, V, seed=42, nan_per_64k=nan, key_modulus=G, key_seed=43)

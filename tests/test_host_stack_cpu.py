@@ -433,3 +433,15 @@ def test_isin_is_a_join_probe(cpu_device):
         df[["c0"]].isin([1])
     with pytest.raises(NotImplementedError):
         df["key"].isin([1.5])
+
+
+def test_late_gpu_tests_are_sound_on_the_double(cpu_device, golden_dir):
+    """tests/test_zz_gpu_row_selection.py could not be run on a GPU in the round it was written; run its bodies on
+    the device double so that at least the test logic (and the host side it drives) is known to be right."""
+    import importlib
+
+    mod = importlib.import_module("test_zz_gpu_row_selection")
+    mod.test_boolean_row_selection_and_dropna_on_device()
+    mod.test_pipeline_filter_derive_aggregate_on_device()
+    mod.test_isin_is_a_join_probe_on_device()
+    mod.test_second_batch_vs_reference_golden(golden_dir)

@@ -170,3 +170,39 @@ def test_sort_values_restatement_equals_a_stable_pandas_sort():
         want = df.sort_values(by, ascending=asc, kind="stable")
         assert list(got.index) == list(want.index)
         assert_bit_equal(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), f"sort {by} asc={asc}")
+
+
+def test_second_batch_against_reference(golden_dir):
+    """Logical ops, any / all, sums and means of booleans, isin, boolean row selection, dropna, multi-column
+    groupby, dictionary aggregation -- the oracle's restatements pinned to the unmodified reference, bit for bit."""
+    for name, z in _load(golden_dir, "ext2_*.npz"):
+        n, seed, nan, G = (int(x) for x in z["meta"])
+        df = synth.host_frame(n, 3, seed=seed, nan_per_64k=nan, key_modulus=G)
+        df["k2"] = synth.gen_i64(n, 99, 1, 5) * 10 - 20
+        v = df[["c0", "c1", "c2"]]
+        band = orc.df_logical(v > 0.0, v < 1.0, "__and__", NP)
+        assert_bit_equal(band.to_numpy(), z["band"], f"{name}:and")
+        assert_bit_equal(orc.df_logical(v > 0.5, v < -0.5, "__or__", NP).to_numpy(), z["bor"], f"{name}:or")
+        assert_bit_equal(orc.df_logical(v > 0.0, v > 1.0, "__xor__", NP).to_numpy(), z["bxor"], f"{name}:xor")
+        assert_bit_equal((~band).to_numpy(), z["bnot"], f"{name}:not")
+        assert_bit_equal(orc.df_any_all(band, "any", NP).to_numpy(), z["any"], f"{name}:any")
+        assert_bit_equal(orc.df_any_all(v > -100.0, "all", NP).to_numpy(), z["all_true"], f"{name}:all")
+        assert_bit_equal(orc.df_sum(band, NP).to_numpy(), z["boolsum"], f"{name}:sum of bools")
+        assert_bit_equal(orc.df_mean(band, NP).to_numpy(), z["boolmean"], f"{name}:mean of bools")
+        assert_bit_equal(orc.df_isin(df[["key", "k2"]], [3, 7, -20, 30], NP).to_numpy(), z["isin"], f"{name}:isin")
+        sel = orc.filter_rows(df, df["c0"] > 0.5, NP)
+        assert_bit_equal(sel.index.to_numpy(), z["sel_index"], f"{name}:filter labels")
+        assert_bit_equal(sel.to_numpy(dtype=np.float64), z["sel"], f"{name}:filter")
+        dn = orc.filter_rows(df, df.notna().all(axis=1), NP)
+        assert_bit_equal(dn.index.to_numpy(), z["dropna_index"], f"{name}:dropna labels")
+        assert_bit_equal(dn.to_numpy(dtype=np.float64), z["dropna"], f"{name}:dropna")
+        mk = orc.groupby_reduce(df, ["key", "k2"], "sum", NP)
+        assert_bit_equal(mk.index.get_level_values(0).to_numpy(), z["mk_k1"], f"{name}:multi-key level 0")
+        assert_bit_equal(mk.index.get_level_values(1).to_numpy(), z["mk_k2"], f"{name}:multi-key level 1")
+        assert_bit_equal(mk.to_numpy(), z["mk_sum"], f"{name}:multi-key sum")
+        da = orc.groupby_dict_reduce(df, "key", {"c1": "max", "c0": "sum", "c2": "count"}, NP)
+        assert_bit_equal(da.index.to_numpy(), z["dict_keys"], f"{name}:dict agg keys")
+        assert_bit_equal(da.to_numpy(dtype=np.float64), z["dict_agg"], f"{name}:dict agg")
+        vc = df["key"].value_counts()
+        assert sorted(zip(vc.index, vc.to_numpy())) == sorted(zip(z["vc_keys"], z["vc_counts"]))
+        assert list(z["vc_counts"]) == sorted(z["vc_counts"], reverse=True) and int(z["nunique"][0]) == df["key"].nunique()

@@ -86,3 +86,55 @@ def test_isin_is_a_join_probe_on_device():
     w = pdf[pdf["key"].isin([1, 2, 3])]
     assert np.array_equal(sel.index.to_numpy(), w.index.to_numpy())
     _exact(sel.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), "filter by isin")
+
+
+def test_second_batch_vs_reference_golden(golden_dir):
+    """The same operations against golden vectors produced by the UNMODIFIED reference (tests/golden/ext2_*.npz):
+    logical ops, any / all, bool sums, isin, boolean row selection, dropna, multi-column groupby, dict aggregation,
+    value_counts, nunique."""
+    import glob
+    import os
+
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        files = sorted(glob.glob(os.path.join(golden_dir, "ext2_*.npz")))
+        assert files
+        for f in files:
+            z = np.load(f, allow_pickle=False)
+            n, seed, nan, G = (int(x) for x in z["meta"])
+            pdf = synth.host_frame(n, 3, seed=seed, nan_per_64k=nan, key_modulus=G)
+            pdf["k2"] = synth.gen_i64(n, 99, 1, 5) * 10 - 20
+            df = bpd.DataFrame(pdf)
+            v = df[["c0", "c1", "c2"]]
+            band = (v > 0.0) & (v < 1.0)
+            assert np.array_equal(band._to_pandas().to_numpy(), z["band"])
+            assert np.array_equal(((v > 0.5) | (v < -0.5))._to_pandas().to_numpy(), z["bor"])
+            assert np.array_equal(((v > 0.0) ^ (v > 1.0))._to_pandas().to_numpy(), z["bxor"])
+            assert np.array_equal((~band)._to_pandas().to_numpy(), z["bnot"])
+            assert np.array_equal(band.any().to_numpy(), z["any"]) and np.array_equal((v > -100.0).all().to_numpy(), z["all_true"])
+            assert np.array_equal(band.sum().to_numpy(), z["boolsum"])
+            assert np.allclose(band.mean().to_numpy(), z["boolmean"], rtol=1e-12, atol=0)
+            assert np.array_equal(df[["key", "k2"]].isin([3, 7, -20, 30])._to_pandas().to_numpy(), z["isin"])
+            sel = df[df["c0"] > 0.5]._to_pandas()
+            assert np.array_equal(sel.index.to_numpy(), z["sel_index"])
+            _exact(sel.to_numpy(dtype=np.float64), z["sel"], "filter")
+            dn = df.dropna()._to_pandas()
+            assert np.array_equal(dn.index.to_numpy(), z["dropna_index"])
+            _exact(dn.to_numpy(dtype=np.float64), z["dropna"], "dropna")
+            mk = df.groupby(["key", "k2"]).sum()._to_pandas()
+            assert np.array_equal(mk.index.get_level_values(0).to_numpy(), z["mk_k1"])
+            assert np.array_equal(mk.index.get_level_values(1).to_numpy(), z["mk_k2"])
+            assert np.allclose(mk.to_numpy(), z["mk_sum"], rtol=0, atol=1e-9)
+            da = df.groupby("key").agg({"c1": "max", "c0": "sum", "c2": "count"})._to_pandas()
+            assert np.array_equal(da.index.to_numpy(), z["dict_keys"])
+            assert np.allclose(da.to_numpy(dtype=np.float64), z["dict_agg"], rtol=0, atol=1e-9)
+            vc = df["key"].value_counts()._to_pandas()
+            assert np.array_equal(vc.to_numpy(), z["vc_counts"])
+            assert dict(zip(vc.index, vc.to_numpy())) == dict(zip(z["vc_keys"], z["vc_counts"]))
+            assert df["key"].nunique() == int(z["nunique"][0])
+    finally:
+        config.NPartitions.put(old)
