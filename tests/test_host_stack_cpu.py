@@ -438,9 +438,13 @@ def test_isin_is_a_join_probe(cpu_device):
 def test_late_gpu_tests_are_sound_on_the_double(cpu_device, golden_dir):
     """tests/test_zz_gpu_row_selection.py could not be run on a GPU in the round it was written; run its bodies on
     the device double so that at least the test logic (and the host side it drives) is known to be right."""
-    import importlib
+    import importlib.util
+    import os
 
-    mod = importlib.import_module("test_zz_gpu_row_selection")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_zz_gpu_row_selection.py")
+    spec = importlib.util.spec_from_file_location("late_gpu_tests", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
     mod.test_boolean_row_selection_and_dropna_on_device()
     mod.test_pipeline_filter_derive_aggregate_on_device()
     mod.test_isin_is_a_join_probe_on_device()
