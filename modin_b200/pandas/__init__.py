@@ -647,8 +647,55 @@ class DataFrameGroupBy:
     aggregate = agg
 
 
-def concat(*args, **kwargs):  # pragma: no cover - signature placeholder
-    raise NotImplementedError("concat is not on the B200 path")
+def concat(objs, *, axis=0, join="outer", ignore_index=False, **kwargs):
+    """``pandas.concat`` of device frames (modin/pandas/general.py ``concat`` -> qc.concat -> PandasDataframe.concat,
+    df.py:3952-4096) for the two shapes that need no label alignment: rows of frames with identical columns
+    (axis=0: the row partitions are simply lined up, buffers shared) and columns of frames with identical rows and
+    distinct labels (axis=1: ``hstack``)."""
+    from .. import dist
+    from ..dataframe import B200Dataframe
+
+    objs = list(objs)
+    if not objs or not all(isinstance(o, DataFrame) for o in objs):
+        raise NotImplementedError("concat on the B200 path takes a list of device DataFrames")
+    if axis in (1, "columns"):
+        frame = objs[0]._query_compiler._modin_frame
+        for o in objs[1:]:
+            frame = frame.hstack(o._query_compiler._modin_frame)
+        return DataFrame(query_compiler=type(objs[0]._query_compiler)(frame))
+    if axis not in (0, "index"):
+        raise ValueError(f"No axis named {axis}")
+    if dist.is_distributed():
+        raise NotImplementedError("row-wise concat of sharded frames would interleave the shards; not on the B200 path")
+    cols = objs[0].columns
+    for o in objs[1:]:
+        if not o.columns.equals(cols):
+            raise NotImplementedError("row-wise concat on the B200 path needs identical column labels")
+        if list(o.dtypes) != list(objs[0].dtypes):  # pandas would promote; shared buffers cannot
+            raise NotImplementedError("row-wise concat on the B200 path needs identical column dtypes")
+    from ..block import DeviceBlock, concat_cols
+
+    first = objs[0]._query_compiler._modin_frame
+    pc = first._partition_mgr_cls._partition_class
+    blocks, pos = [], 0
+    for o in objs:
+        f = o._query_compiler._modin_frame
+        if len(f) == 0:
+            continue
+        for row in f._partitions:
+            b = concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get()
+            if ignore_index:  # fresh 0..n labels; the column buffers are shared, not copied
+                b = DeviceBlock(b.cols, b.columns, nrows=b.nrows, range_start=pos)
+            blocks.append(b)
+            pos += b.nrows
+    if not blocks:
+        return objs[0].copy()
+    # from_blocks assumes the blocks' range labels run on from each other, which only holds after ignore_index;
+    # otherwise leave the index cache empty so the labels are read from the blocks (each keeps its own)
+    index = pandas.RangeIndex(0, pos) if ignore_index else None
+    parts = np.array([[pc.put(b)] for b in blocks], dtype=object)
+    frame = B200Dataframe(parts, index, cols, [b.nrows for b in blocks], [len(cols)], dtypes=None)
+    return DataFrame(query_compiler=type(objs[0]._query_compiler)(frame))
 
 
 # ---- zero-copy interchange with other GPU libraries (SURVEY 8f-1: DLPack; the reference's wire format for

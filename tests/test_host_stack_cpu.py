@@ -415,6 +415,51 @@ def test_structural_ops_share_buffers(cpu_device):
     assert list(out.columns) == list(w.columns) and np.allclose(out.to_numpy(), w.to_numpy(), atol=1e-9)
 
 
+def test_concat_lines_up_partitions_without_copying(cpu_device):
+    """concat(axis=0) of equal-column frames and concat(axis=1) of equal-row frames: values AND row labels as pandas."""
+    import modin_b200.pandas as bpd
+
+    pa = synth.host_frame(1003, 3, seed=41, nan_per_64k=1000, key_modulus=5)
+    pb = synth.host_frame(517, 3, seed=42, nan_per_64k=1000, key_modulus=5)
+    a, b = bpd.DataFrame(pa), bpd.DataFrame(pb)
+    for ignore in (False, True):
+        got = bpd.concat([a, b, a], ignore_index=ignore)._to_pandas()
+        want = pandas.concat([pa, pb, pa], ignore_index=ignore)
+        assert list(got.columns) == list(want.columns)
+        # labels restart at 0 for every input unless ignore_index: they are NOT one running range
+        assert list(got.index) == list(want.index), ignore
+        assert _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64)), ignore
+    # the result is an ordinary frame: operators run over the lined-up partitions
+    cat = bpd.concat([a, b], ignore_index=True)
+    wcat = pandas.concat([pa, pb], ignore_index=True)
+    assert len(cat) == len(wcat)
+    s, ws = cat[["c0", "c1", "c2"]].sum(), wcat[["c0", "c1", "c2"]].sum()
+    s = s._to_pandas() if hasattr(s, "_to_pandas") else s
+    assert list(s.index) == list(ws.index) and np.allclose(np.asarray(s), ws.to_numpy(), rtol=0, atol=1e-9)
+    g = cat.groupby("key").sum()._to_pandas()
+    wg = wcat.groupby("key").sum()
+    assert list(g.index) == list(wg.index) and np.allclose(g.to_numpy(), wg.to_numpy(), atol=1e-9)
+    assert _same((cat * 2.0)._to_pandas().to_numpy(dtype=np.float64), (wcat * 2.0).to_numpy(dtype=np.float64))
+    # inputs are untouched and a single-frame concat is the frame
+    assert list(a._to_pandas().index) == list(pa.index)
+    assert _same(bpd.concat([b])._to_pandas().to_numpy(dtype=np.float64), pb.to_numpy(dtype=np.float64))
+    # axis=1: distinct labels over the same rows
+    right = a[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})
+    wide = bpd.concat([a, right], axis=1)._to_pandas()
+    wwide = pandas.concat([pa, pa[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})], axis=1)
+    assert list(wide.columns) == list(wwide.columns)
+    assert _same(wide.to_numpy(dtype=np.float64), wwide.to_numpy(dtype=np.float64))
+    # what needs label alignment or dtype promotion is refused, not approximated
+    with pytest.raises(NotImplementedError):
+        bpd.concat([a, a[["c0", "c1"]]])
+    with pytest.raises(NotImplementedError):
+        bpd.concat([a[["c0"]], a[["key"]].rename(columns={"key": "c0"})])
+    with pytest.raises(ValueError):
+        bpd.concat([a, b], axis=1)
+    with pytest.raises(ValueError):
+        bpd.concat([a, b], axis=2)
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 
