@@ -117,6 +117,51 @@ class DevRound(DevFn):
         return block.with_cols(out)
 
 
+class DevAstype(DevFn):
+    """``df.astype(dtype)`` -- qc.py ``astype`` (a Map over ``pandas.DataFrame.astype``) for the widening casts the
+    map kernels already carry: int64 / bool -> float64 (the ``x / 1`` division kernel, round to nearest even above
+    2**53 exactly as numpy) and bool -> int64 (the widening copy).  A column already of the target dtype shares its
+    buffer.  float64 -> int64 (pandas raises on NaN / inf, truncates otherwise) and anything -> bool have no kernel
+    on this path and are refused."""
+
+    op = "astype"
+
+    @staticmethod
+    def target(dtype) -> np.dtype:
+        try:
+            dt = np.dtype(pandas.api.types.pandas_dtype(dtype))
+        except TypeError:
+            raise NotImplementedError(f"astype({dtype!r}) is not on the B200 path") from None
+        if dt not in (np.dtype("float64"), np.dtype("int64"), np.dtype("bool")):
+            raise NotImplementedError(f"astype({dt}) is not on the B200 path (float64 / int64 / bool columns only)")
+        return dt
+
+    def __call__(self, block, *args, col_dtypes=None, **kwargs):
+        _check_block(block, "DevAstype")
+        if args:
+            col_dtypes = args[0]
+        if not isinstance(col_dtypes, dict):
+            raise TypeError("DevAstype takes a {column label: dtype} mapping")
+        out = list(block.cols)
+        for j, label in enumerate(block.columns):
+            if label not in col_dtypes:
+                continue
+            src, dst = block.cols[j].dtype, self.target(col_dtypes[label])
+            if src == dst:
+                continue
+            if not (dst == np.float64 or (dst == np.int64 and src == np.bool_)):
+                raise NotImplementedError(f"astype {src} -> {dst} is not on the B200 path")
+            if block.nrows == 0:  # nothing to launch, but the dtype still changes
+                out[j] = DeviceColumn.empty(0, dst)
+            elif dst == np.float64:
+                out[j] = ops.cast_columns_f64([block.cols[j]])[0]
+            elif dst == np.int64 and src == np.bool_:
+                out[j] = ops.cast_columns_i64([block.cols[j]])[0]
+            else:
+                raise NotImplementedError(f"astype {src} -> {dst} is not on the B200 path")
+        return block.with_cols(out)
+
+
 class DevClip(DevFn):
     """``df.clip(lower, upper)`` with scalar bounds -- ``Map.register(pandas.DataFrame.clip)`` (qc.py clip);
     NaNs stay NaN, a missing bound is -inf / +inf."""

@@ -80,6 +80,14 @@ class BasePandasDataset:
     def round(self, decimals=0, *args, **kwargs):
         return self._create_or_update_from_compiler(self._query_compiler.round(decimals=decimals))
 
+    def astype(self, dtype, copy=None, errors="raise"):
+        """modin/pandas/base.py ``astype`` -> qc.astype: one dtype for all columns, or {label: dtype}."""
+        if isinstance(dtype, (pandas.Series, BasePandasDataset)):
+            raise NotImplementedError("astype on the B200 path takes a dtype or a {column: dtype} dict")
+        if isinstance(self, Series) and isinstance(dtype, dict):
+            raise NotImplementedError("Series.astype on the B200 path takes a single dtype")
+        return self._create_or_update_from_compiler(self._query_compiler.astype(dtype, errors=errors))
+
     def clip(self, lower=None, upper=None, *, axis=None, inplace=False, **kwargs):
         if inplace:
             raise NotImplementedError("clip(inplace=True) is not on the B200 path")
@@ -319,6 +327,18 @@ class DataFrame(BasePandasDataset):
 
     def tail(self, n=5):
         return DataFrame(query_compiler=self._query_compiler.tail(n))
+
+    def nunique(self, axis=0, dropna=True):
+        """Distinct values per column: one device group table per column, the answer is its row count.  int64
+        columns only -- a float column would need pandas' NaN handling (``dropna``), which the group tables do not
+        have.  The W counts come back as a host Series, like the other column reductions."""
+        if axis not in (0, "index"):
+            raise NotImplementedError("nunique(axis=1) is not on the B200 path")
+        bad = [c for c, dt in zip(self.columns, self.dtypes) if np.dtype(dt) != np.int64]
+        if bad:
+            raise NotImplementedError(f"nunique on the B200 path counts int64 columns only (got {bad!r})")
+        counts = [self[c].nunique() for c in self.columns]
+        return pandas.Series(counts, index=self.columns, dtype=np.int64)
 
     def dropna(self, *, axis=0, how="any", subset=None, inplace=False, ignore_index=False, **kwargs):
         """Drop rows with missing values: ``notna()`` -> row-wise all / any -> boolean row selection, all on the

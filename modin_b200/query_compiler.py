@@ -20,6 +20,7 @@ import pandas
 from .algebra import Binary, GroupByReduce, Map, TreeReduce
 from .dataframe import B200Dataframe
 from .functors import (
+    DevAstype,
     DevBinary,
     DevBoolReduce,
     DevClip,
@@ -185,6 +186,25 @@ class B200QueryCompiler:
     round = Map.register(DevRound(), dtypes="copy")  # qc.py:2438
     clip = Map.register(DevClip(), dtypes="copy")  # qc.py `clip = Map.register(pandas.DataFrame.clip)`
     copy_data = Map.register(DevMap("copy"), dtypes="copy")
+    _astype_map = Map.register(DevAstype())  # result dtypes are read back from the blocks
+
+    def astype(self, col_dtypes, errors: str = "raise"):
+        """qc.py ``astype(col_dtypes, errors)``: ``col_dtypes`` is one dtype for every column or a
+        {column label: dtype} mapping.  Only the widening casts of ``DevAstype``; checked here, before any launch,
+        so that a refused cast leaves no half-converted frame."""
+        if errors != "raise":
+            raise NotImplementedError("astype(errors='ignore') is not on the B200 path")
+        if not isinstance(col_dtypes, dict):
+            col_dtypes = {label: col_dtypes for label in self.columns}
+        have = self.dtypes
+        for label, dt in col_dtypes.items():
+            if label not in have.index:
+                raise KeyError("Only a column name can be used for the key in a dtype mappings argument. "
+                               f"'{label}' not found in columns.")  # fmt: skip
+            src, dst = np.dtype(have[label]), DevAstype.target(dt)
+            if src != dst and not (dst == np.float64 or (dst == np.int64 and src == np.bool_)):
+                raise NotImplementedError(f"astype {src} -> {dst} is not on the B200 path")
+        return self._astype_map(col_dtypes)
 
     def fillna(self, **kwargs):
         """qc.py:2710-2813: scalar / dict values are a Map; ``method``/``limit`` would be a Fold."""

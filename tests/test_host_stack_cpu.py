@@ -460,6 +460,57 @@ def test_concat_lines_up_partitions_without_copying(cpu_device):
         bpd.concat([a, b], axis=2)
 
 
+def test_astype_widening_casts_and_frame_nunique(cpu_device):
+    import modin_b200.pandas as bpd
+
+    rng = np.random.default_rng(51)
+    n = 1003
+    pdf = pandas.DataFrame({
+        "k": rng.integers(-7, 7, n),
+        "big": rng.integers(-(2**62), 2**62, n),  # above 2**53: the cast has to round like numpy
+        "x": rng.standard_normal(n),
+        "flag": rng.integers(0, 2, n).astype(bool),
+    })  # fmt: skip
+    pdf.loc[::97, "x"] = np.nan
+    df = bpd.DataFrame(pdf)
+
+    got, want = df.astype("float64"), pdf.astype("float64")
+    assert list(got.dtypes) == list(want.dtypes)
+    assert _same(got._to_pandas().to_numpy(), want.to_numpy())
+    got, want = df.astype({"k": np.float64, "flag": "int64"}), pdf.astype({"k": np.float64, "flag": "int64"})
+    assert list(got.dtypes) == list(want.dtypes)
+    gp = got._to_pandas()
+    for c in want.columns:
+        assert gp[c].dtype == want[c].dtype and _same(gp[c].to_numpy(), want[c].to_numpy()), c
+    assert list(df.dtypes) == list(pdf.dtypes)  # the source frame keeps its dtypes
+    s = df["flag"].astype(float)
+    assert _same(s._to_pandas().to_numpy(), pdf["flag"].astype(float).to_numpy())
+    # a cast that changes nothing is a no-op on the same buffers
+    same = df[["x"]].astype("float64")
+    assert _same(same._to_pandas().to_numpy(), pdf[["x"]].to_numpy())
+    # the result feeds the operators
+    assert np.allclose((df[["k"]].astype("float64") * 0.5)._to_pandas().to_numpy(), (pdf[["k"]].astype("float64") * 0.5).to_numpy())
+    # refused before anything is launched: narrowing / truncating casts, unknown columns, other dtypes
+    with pytest.raises(NotImplementedError):
+        df.astype("int64")  # float64 -> int64 (pandas raises on the NaNs, truncates otherwise)
+    with pytest.raises(NotImplementedError):
+        df[["k"]].astype(bool)
+    with pytest.raises(NotImplementedError):
+        df.astype("float32")
+    with pytest.raises(KeyError):
+        df.astype({"nope": "float64"})
+    with pytest.raises(KeyError):
+        pdf.astype({"nope": "float64"})  # same error type as pandas
+
+    ints = df[["k", "big"]]
+    got, want = ints.nunique(), pdf[["k", "big"]].nunique()
+    assert list(got.index) == list(want.index) and list(got) == list(want) and got.dtype == want.dtype
+    with pytest.raises(NotImplementedError):
+        df.nunique()  # float / bool columns
+    with pytest.raises(NotImplementedError):
+        ints.nunique(axis=1)
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 
@@ -493,4 +544,6 @@ def test_late_gpu_tests_are_sound_on_the_double(cpu_device, golden_dir):
     mod.test_boolean_row_selection_and_dropna_on_device()
     mod.test_pipeline_filter_derive_aggregate_on_device()
     mod.test_isin_is_a_join_probe_on_device()
+    mod.test_concat_on_device()
+    mod.test_astype_and_frame_nunique_on_device()
     mod.test_second_batch_vs_reference_golden(golden_dir)

@@ -4,6 +4,10 @@ Written after this round's GPU budget was spent, so it has only run on the CPU d
 (tests/test_host_stack_cpu.py::test_boolean_row_selection_and_dropna).  Every kernel it reaches is covered by
 other GPU tests (bool widening and logical ops: test_boolean_pipelines_on_device; compaction and gather: the
 inner-merge tests); the file sorts last so that a surprise here cannot hide the rest of the suite behind ``-x``.
+
+The same holds for the later additions in this file (isin, concat, astype / DataFrame.nunique, the ext2 golden
+vectors): NOT yet run on a B200, only on the double.  concat launches nothing itself; astype reuses the
+true-division and widening-copy kernels that the var / std and bool-sum GPU tests already reach.
 """
 
 import numpy as np
@@ -86,6 +90,70 @@ def test_isin_is_a_join_probe_on_device():
     w = pdf[pdf["key"].isin([1, 2, 3])]
     assert np.array_equal(sel.index.to_numpy(), w.index.to_numpy())
     _exact(sel.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), "filter by isin")
+
+
+def test_concat_on_device():
+    """concat(axis=0) lines up row partitions (labels restart per input unless ignore_index); axis=1 is hstack.
+    No kernel of its own: what is checked on the device is that operators run over the lined-up partitions."""
+    import pandas
+
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        pa = synth.host_frame(40_003, 3, seed=41, nan_per_64k=1000, key_modulus=5)
+        pb = synth.host_frame(20_017, 3, seed=42, nan_per_64k=1000, key_modulus=5)
+        a, b = bpd.DataFrame(pa), bpd.DataFrame(pb)
+        for ignore in (False, True):
+            got = bpd.concat([a, b, a], ignore_index=ignore)._to_pandas()
+            want = pandas.concat([pa, pb, pa], ignore_index=ignore)
+            assert np.array_equal(got.index.to_numpy(), want.index.to_numpy()) and list(got.columns) == list(want.columns)
+            _exact(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), "concat rows")
+        cat, wcat = bpd.concat([a, b], ignore_index=True), pandas.concat([pa, pb], ignore_index=True)
+        _exact((cat * 2.0)._to_pandas().to_numpy(dtype=np.float64), (wcat * 2.0).to_numpy(dtype=np.float64), "map over concat")
+        g, wg = cat.groupby("key").sum()._to_pandas(), wcat.groupby("key").sum()
+        assert np.array_equal(g.index.to_numpy(), wg.index.to_numpy()) and np.allclose(g.to_numpy(), wg.to_numpy(), rtol=0, atol=1e-8)
+        right = a[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})
+        wide = bpd.concat([a, right], axis=1)._to_pandas()
+        wwide = pandas.concat([pa, pa[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})], axis=1)
+        assert list(wide.columns) == list(wwide.columns)
+        _exact(wide.to_numpy(dtype=np.float64), wwide.to_numpy(dtype=np.float64), "concat columns")
+    finally:
+        config.NPartitions.put(old)
+
+
+def test_astype_and_frame_nunique_on_device():
+    """int64 / bool -> float64 through the true-division kernel (round to nearest even above 2**53, as numpy),
+    bool -> int64 through the widening copy; DataFrame.nunique = rows of one group table per int64 column."""
+    import pandas
+
+    import modin_b200.pandas as bpd
+
+    rng = np.random.default_rng(51)
+    n = 60_007
+    pdf = pandas.DataFrame({
+        "k": rng.integers(-7, 7, n),
+        "big": rng.integers(-(2**62), 2**62, n),
+        "x": rng.standard_normal(n),
+        "flag": rng.integers(0, 2, n).astype(bool),
+    })  # fmt: skip
+    pdf.loc[::97, "x"] = np.nan
+    df = bpd.DataFrame(pdf)
+    got, want = df.astype("float64"), pdf.astype("float64")
+    assert list(got.dtypes) == list(want.dtypes)
+    _exact(got._to_pandas().to_numpy(), want.to_numpy(), "astype float64")
+    got = df.astype({"k": np.float64, "flag": "int64"})._to_pandas()
+    want = pdf.astype({"k": np.float64, "flag": "int64"})
+    for c in want.columns:
+        assert got[c].dtype == want[c].dtype, c
+        _exact(got[c].to_numpy(dtype=np.float64), want[c].to_numpy(dtype=np.float64), f"astype dict {c}")
+    assert np.array_equal(got["big"].to_numpy(), want["big"].to_numpy())  # untouched int64 column, exact
+    with pytest.raises(NotImplementedError):
+        df.astype("int64")
+    nu, wnu = df[["k", "big"]].nunique(), pdf[["k", "big"]].nunique()
+    assert list(nu.index) == list(wnu.index) and list(nu) == list(wnu)
 
 
 def test_second_batch_vs_reference_golden(golden_dir):
