@@ -360,6 +360,22 @@ class B200Dataframe:
         return self.__constructor__(np.array([[pc(out)]], dtype=object), None, self._columns_cache, [n],
                                     [len(out.cols)], self._dtypes)  # fmt: skip
 
+    def drop_duplicate_rows(self, col_position: int, keep: str = "first", ignore_index: bool = False) -> "B200Dataframe":
+        """Rows holding the first / last occurrence of every value of one int64 column, in row order
+        (``DevDropDuplicates``).  Single process: equal keys on different GPUs would need the key-range exchange
+        of ``sort_by`` first, which is not wired up for this operation."""
+        from .block import concat_cols, concat_rows
+        from .functors import DevDropDuplicates
+
+        if dist.is_distributed():
+            raise NotImplementedError("multi-GPU drop_duplicates is not on the B200 path")
+        rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
+        block = concat_rows(rows) if len(rows) > 1 else rows[0]
+        out = DevDropDuplicates()(block, col_position, keep=keep, ignore_index=ignore_index)
+        pc = self._partition_mgr_cls._partition_class
+        return self.__constructor__(np.array([[pc(out)]], dtype=object), None, self._columns_cache, [out.nrows],
+                                    [len(out.cols)], self._dtypes)  # fmt: skip
+
     def _repartition_rows(self, lengths: List[int]) -> "B200Dataframe":
         """Same rows, cut at ``lengths`` instead of ``self.row_lengths`` (the row half of ``_copartition``,
         df.py:3799-3840, without a reindex): target partitions inside one source partition are views of its

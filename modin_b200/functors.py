@@ -431,6 +431,68 @@ class DevRowFilter(DevFn):
         return DeviceBlock(cols, block.columns, nrows=k, index_cols=[labels], index_names=names)
 
 
+class DevDropDuplicates(DevFn):
+    """``df.drop_duplicates(subset=[one int64 column], keep="first" | "last")`` on one block holding all the rows.
+    The reference (modin/pandas/base.py:1600-1623 -> qc.unique, qc.py:2231-2270 -> BaseQueryCompiler.unique,
+    base/query_compiler.py:2410-2435) computes ``duplicated(keep)`` over the subset, inverts it, selects the rows
+    with that mask and optionally resets the index.  Same result here without materialising the mask in row order
+    (there is no scatter on this path); composed from the sort, compaction and gather kernels, nothing of its own:
+
+    1. stable sort of (key, row id): equal keys become runs, row ids ascending inside a run;
+    2. run edges: ``sorted[i + 1] != sorted[i]`` (one elementwise sweep over two views shifted by a row);
+    3. the row ids at the edges (first or last of every run) by ranked compaction + gather;
+    4. those K row ids sorted back into row order, and one gather per column.
+
+    Original row order and row labels are kept, as in pandas."""
+
+    op = "drop_duplicates"
+
+    def __call__(self, block, key_position=0, keep="first", ignore_index=False, **kwargs):
+        from .block import torch_mod
+
+        _check_block(block, "DevDropDuplicates")
+        if keep not in ("first", "last"):
+            raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
+        key = block.cols[key_position]
+        if key.dtype != np.int64:
+            raise NotImplementedError("device drop_duplicates needs an int64 subset column")
+        if any(c.dtype == np.bool_ for c in block.cols):
+            raise NotImplementedError("drop_duplicates of frames with bool columns is not on the B200 path")
+        if block.index_host is not None and not ignore_index:
+            raise NotImplementedError("drop_duplicates keeps numeric / range row labels only (or ignore_index=True)")
+        if block.index_cols and len(block.index_cols) != 1 and not ignore_index:
+            raise NotImplementedError("drop_duplicates of a frame with a MultiIndex is not on the B200 path")
+        t = torch_mod()
+        n = block.nrows
+        if n <= 1:
+            if ignore_index:
+                return DeviceBlock(block.cols, block.columns, nrows=n, range_start=0)
+            return block
+        image = ops.map_columns("ordered_s", [key], s0=[0])[0]  # fresh buffer: the sort is in place
+        perm = DeviceColumn(t.arange(n, dtype=t.int64, device=key.data.device), np.int64)
+        ops.sort_pairs(image, perm)
+        edge = ops.map_columns("ne", [image.slice(1, n)], [image.slice(0, n - 1)])[0]  # edge[i]: run ends at i
+        idx = ops.map_columns("add_s", ops.cast_columns_i64([edge]), s0=[-1])[0]  # 0 -> -1 (skip), 1 -> 0 (hit)
+        pos, k = ops.compact_hits(idx)
+        if keep == "first":  # sorted row 0 opens the first run; every edge i opens a run at i + 1
+            always = perm.slice(0, 1)
+            if k:
+                pos = ops.map_columns("add_s", [pos], s0=[1])[0]
+        else:  # every edge i closes a run at i; sorted row n - 1 closes the last one
+            always = perm.slice(n - 1, n)
+        picked = [ops.take_columns([perm], pos)[0].data] if k else []
+        rid = DeviceColumn(t.cat([always.data] + picked), np.int64)  # K = k + 1 row ids, in key order
+        ops.sort_pairs(rid, DeviceColumn.empty(k + 1, np.int64))  # back into row order (payload unused)
+        cols = ops.take_columns(block.cols, rid) if block.cols else []
+        if ignore_index:
+            return DeviceBlock(cols, block.columns, nrows=k + 1, range_start=0)
+        if block.index_cols:
+            labels, names = ops.take_columns(block.index_cols, rid)[0], block.index_names
+        else:
+            labels, names = ops.map_columns("add_s", [rid], s0=[int(block.range_start)])[0], [None]
+        return DeviceBlock(cols, block.columns, nrows=k + 1, index_cols=[labels], index_names=names)
+
+
 class DevBoolReduce(DevFn):
     """``df.any()`` / ``df.all()`` over BOOL columns -- ``TreeReduce.register(pandas.DataFrame.any / all)``
     (qc.py:986-987): any = max, all = min of the 0 / 1 values, per partition and again over the partials

@@ -80,6 +80,15 @@ class BasePandasDataset:
     def round(self, decimals=0, *args, **kwargs):
         return self._create_or_update_from_compiler(self._query_compiler.round(decimals=decimals))
 
+    def drop_duplicates(self, subset=None, *, keep="first", inplace=False, ignore_index=False):
+        """modin/pandas/base.py ``drop_duplicates`` -> qc.drop_duplicates; row order and row labels as pandas."""
+        if inplace:
+            raise NotImplementedError("drop_duplicates(inplace=True) is not on the B200 path")
+        if isinstance(self, Series) and subset is not None:
+            raise TypeError("Series.drop_duplicates() got an unexpected keyword argument 'subset'")
+        qc = self._query_compiler.drop_duplicates(subset=subset, keep=keep, ignore_index=ignore_index)
+        return self._create_or_update_from_compiler(qc)
+
     def astype(self, dtype, copy=None, errors="raise"):
         """modin/pandas/base.py ``astype`` -> qc.astype: one dtype for all columns, or {label: dtype}."""
         if isinstance(dtype, (pandas.Series, BasePandasDataset)):

@@ -119,6 +119,23 @@ class B200QueryCompiler:
         pos = int(self.columns.get_loc(cols[0]))
         return self.__constructor__(self._modin_frame.sort_by(pos, bool(asc), bool(kwargs.get("ignore_index", False))))
 
+    def drop_duplicates(self, subset=None, keep="first", ignore_index=False):
+        """What ``BasePandasDataset.drop_duplicates`` (modin/pandas/base.py:1600-1623) asks of the query compiler --
+        ``qc.unique(keep, ignore_index, subset)``, qc.py:2231-2270: rows with the first / last occurrence of every
+        value of ONE int64 subset column (``subset=None`` means all columns, so it is accepted only for a
+        one-column frame)."""
+        cols = list(self.columns) if subset is None else ([subset] if not isinstance(subset, (list, tuple)) else list(subset))
+        if len(cols) != 1:
+            raise NotImplementedError("device drop_duplicates compares one int64 column (pass subset=[column])")
+        if cols[0] not in self.columns:
+            raise KeyError(pandas.Index([cols[0]]))
+        if keep not in ("first", "last"):
+            if keep is False:
+                raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
+            raise ValueError('keep must be either "first", "last" or False')
+        pos = int(self.columns.get_loc(cols[0]))
+        return self.__constructor__(self._modin_frame.drop_duplicate_rows(pos, keep, bool(ignore_index)))
+
     def relabel_columns(self, new_labels):
         """Same buffers, new column labels (metadata only; ``qc.columns = ...`` in the reference)."""
         new_labels = pandas.Index(new_labels)

@@ -363,3 +363,48 @@ def filter_rows(df, mask: pandas.Series, npartitions: int) -> pandas.DataFrame:
         out.append(blk[mask.iloc[pos : pos + len(blk)].to_numpy()])
         pos += len(blk)
     return pandas.concat(out, axis=0)
+
+
+def drop_duplicates(df, subset, keep: str, ignore_index: bool, npartitions: int) -> pandas.DataFrame:
+    """modin/pandas/base.py:1600-1623 -> qc.unique (qc.py:2231-2270; without range partitioning and with a subset it
+    defers to BaseQueryCompiler.unique, base/query_compiler.py:2410-2435): ``duplicated(keep)`` over the subset
+    columns -- a full-axis ``pandas.DataFrame.duplicated`` (qc.py:3346-3387) -- inverted, boolean row selection with
+    that mask, then ``reset_index(drop=True)`` when ``ignore_index``."""
+    subset = [subset] if not isinstance(subset, (list, tuple)) else list(subset)
+    grid = split_into_partitions(df[subset], npartitions)
+    if len(grid[0]) != 1:  # wider subsets are md5-hashed row by row first (qc.py:3369-3376); not restated
+        raise NotImplementedError("duplicated() over more than one column partition is not restated")
+    # apply_full_axis(axis=0): the row blocks of the column partition are concatenated, pandas sees whole columns
+    dup = pandas.concat([row[0] for row in grid], axis=0).duplicated(keep=keep)
+    out = filter_rows(df, ~dup, npartitions)
+    return out.reset_index(drop=True) if ignore_index else out
+
+
+def concat_frames(frames: Sequence[pandas.DataFrame], axis: int, ignore_index: bool, npartitions: int) -> pandas.DataFrame:
+    """modin/pandas/general.py:441 ``concat`` -> qc.concat (qc.py:482-503) -> PandasDataframe.concat (df.py:3953-4096).
+    For frames whose labels along the other axis are equal no reindexing is needed: the partition grids are stacked
+    (``pm.concat``, partition_manager.py:943-986) and the labels along ``axis`` are appended; ``ignore_index`` is a
+    ``reset_index(drop=True)`` (axis 0) afterwards."""
+    grids = [split_into_partitions(f, npartitions) for f in frames]
+    if axis == 0:
+        stacked = [row for g in grids for row in g]
+        out = pandas.concat([pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in stacked], axis=0)
+        return out.reset_index(drop=True) if ignore_index else out
+    return pandas.concat([to_pandas(g) for g in grids], axis=1)
+
+
+def df_astype(df, col_dtypes, npartitions: int) -> pandas.DataFrame:
+    """qc.astype (qc.py:2335-2343) -> PandasDataframe.astype (df.py:1707-1810): ``df.astype(col_dtypes)`` mapped over
+    the block partitions (``lazy_map_partitions``); a mapping is cut down to the labels of each block."""
+    def cast(block):
+        if isinstance(col_dtypes, dict):
+            return block.astype({c: t for c, t in col_dtypes.items() if c in block.columns})
+        return block.astype(col_dtypes)
+
+    return to_pandas(map_partitions(split_into_partitions(df, npartitions), cast))
+
+
+def df_nunique(df, npartitions: int) -> pandas.Series:
+    """qc.nunique (qc.py:1109-1113, range partitioning off): ``Reduce.register(pandas.DataFrame.nunique)`` -- a
+    full-axis reduce, every column partition sees whole columns."""
+    return reduce_full_axis(df, lambda full: full.nunique(), npartitions)

@@ -52,6 +52,20 @@ def apply_pandas3_shims():
         cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: _f(self, *a, **k))
 
 
+def third_batch_frames(synth, n, nb, nan, G):
+    """Inputs of the ``ext3`` cases (also used by the tests, so generator and checkers cannot drift apart): two frames
+    with the same columns -- int64 keys, an int64 column beyond 2**53, float64 values with NaNs, one bool column."""
+    frames = []
+    for rows, seed, kseed in ((n, 33, 98), (nb, 34, 97)):
+        f = synth.host_frame(rows, 3, seed=seed, nan_per_64k=nan, key_modulus=G)
+        f["k2"] = synth.gen_i64(rows, kseed, 1, 7) * 5 - 10
+        # high and low bits both set, so the cast to float64 has to round (not exactly representable)
+        f["big"] = (synth.gen_i64(rows, kseed + 10, 2, 1 << 20) << 42) + synth.gen_i64(rows, kseed + 11, 3, 1 << 20) - (1 << 61)
+        f["flag"] = f["c0"] > 0.0
+        frames.append(f)
+    return frames
+
+
 def main():
     os.environ["MODIN_ENGINE"] = "python"
     apply_pandas3_shims()
@@ -65,7 +79,11 @@ def main():
     cfg.NPartitions.put(4)
     from modin_b200 import synth
 
+    only = os.environ.get("GOLDEN_ONLY")  # e.g. GOLDEN_ONLY=ext3_ : leave the other (already committed) files alone
+
     def save(name, **arrays):
+        if only and not name.startswith(only):
+            return
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
         print("wrote", name, {k: getattr(v, "shape", None) for k, v in arrays.items()})
 
@@ -161,6 +179,36 @@ def main():
             vc_counts=vc.to_numpy(), vc_keys=vc.index.to_numpy(),
             nunique=np.array([mdf["key"].nunique()]),
         )
+
+    # ---- third batch: drop_duplicates, concat, astype, DataFrame.nunique
+    for n, nb, nan, G in ((3001, 1501, 3000, 40),):
+        pdf, pb = third_batch_frames(synth, n, nb, nan, G)
+        mdf, mb = mpd.DataFrame(pdf), mpd.DataFrame(pb)
+        num = ["key", "k2", "c0", "c1", "c2"]  # drop_duplicates on the device path carries no bool columns
+        arrays = {}
+        for keep in ("first", "last"):
+            r = P(mdf[num].drop_duplicates(subset=["key"], keep=keep))
+            arrays[f"dd_{keep}_index"], arrays[f"dd_{keep}"] = r.index.to_numpy(), r.to_numpy(dtype=np.float64)
+        r = P(mdf[num].drop_duplicates(subset=["k2"], keep="last", ignore_index=True))
+        arrays["dd_k2_ignore_index"], arrays["dd_k2_ignore"] = r.index.to_numpy(), r.to_numpy(dtype=np.float64)
+        r = P(mdf["k2"].drop_duplicates())
+        arrays["dd_series_index"], arrays["dd_series"] = r.index.to_numpy(), r.to_numpy()
+        for ig in (False, True):
+            r = P(mpd.concat([mdf[num], mb[num], mdf[num]], ignore_index=ig))
+            arrays[f"cat0_ig{int(ig)}_index"], arrays[f"cat0_ig{int(ig)}"] = r.index.to_numpy(), r.to_numpy(dtype=np.float64)
+        r = P(mpd.concat([mdf[num], mdf[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})], axis=1))
+        arrays["cat1"], arrays["cat1_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
+        r = P(mdf.astype("float64"))
+        assert all(t == np.float64 for t in r.dtypes)
+        arrays["astype_f64"] = r.to_numpy()
+        r = P(mdf.astype({"key": np.float64, "flag": "int64"}))
+        arrays["astype_dict_dtypes"] = np.array([str(t) for t in r.dtypes])
+        arrays["astype_dict"] = r.to_numpy(dtype=np.float64)
+        r = P(mdf[["key", "k2", "big"]].astype("float64"))
+        arrays["astype_big"] = r.to_numpy()
+        r = P(mdf[["key", "k2", "big"]].nunique())
+        arrays["nunique"], arrays["nunique_cols"] = r.to_numpy(), np.array(list(r.index))
+        save(f"ext3_n{n}_nan{nan}", meta=np.array([n, nb, nan, G]), **arrays)
 
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):

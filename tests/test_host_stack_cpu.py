@@ -511,6 +511,60 @@ def test_astype_widening_casts_and_frame_nunique(cpu_device):
         ints.nunique(axis=1)
 
 
+def test_drop_duplicates_keeps_first_or_last_in_row_order(cpu_device):
+    import modin_b200.pandas as bpd
+
+    def check(pdf, **kw):
+        got = bpd.DataFrame(pdf).drop_duplicates(**kw)._to_pandas()
+        want = pdf.drop_duplicates(**kw)
+        assert list(got.columns) == list(want.columns), kw
+        assert list(got.index) == list(want.index), (kw, len(pdf))
+        assert _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64)), (kw, len(pdf))
+
+    rng = np.random.default_rng(61)
+    for n, lo, hi in ((1003, -6, 7), (1003, 0, 10**12), (1003, 5, 6), (2, 0, 2), (2, 3, 4), (1, 0, 3), (700, -(2**62), 2**62)):
+        pdf = pandas.DataFrame({"key": rng.integers(lo, hi, n), "x": rng.standard_normal(n), "y": rng.standard_normal(n)})
+        pdf.loc[::13, "x"] = np.nan
+        for keep in ("first", "last"):
+            for ignore in (False, True):
+                check(pdf, subset=["key"], keep=keep, ignore_index=ignore)
+        check(pdf, subset="key")
+    # sorted and reverse-sorted keys (runs already contiguous), and a shifted range index
+    pdf = pandas.DataFrame({"key": np.repeat(np.arange(50), 7), "x": rng.standard_normal(350)})
+    check(pdf, subset=["key"], keep="last")
+    check(pdf.iloc[::-1].reset_index(drop=True), subset=["key"])
+    shifted = pdf.copy()
+    shifted.index = pandas.RangeIndex(1000, 1350)
+    check(shifted, subset=["key"], keep="last")
+    # labels that are already a device index column: the rows a filter left behind
+    big = pandas.DataFrame({"key": rng.integers(0, 40, 2003), "x": rng.standard_normal(2003)})
+    df = bpd.DataFrame(big)
+    got = df[df["x"] > 0.0].drop_duplicates(subset=["key"])._to_pandas()
+    want = big[big["x"] > 0.0].drop_duplicates(subset=["key"])
+    assert list(got.index) == list(want.index) and _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    # Series form, and a one-column frame with subset=None (= all columns)
+    s, ws = df["key"].drop_duplicates()._to_pandas(), big["key"].drop_duplicates()
+    assert list(s.index) == list(ws.index) and list(np.asarray(s).ravel()) == list(ws)
+    check(big[["key"]])
+    assert len(df.drop_duplicates(subset=["key"])) == big["key"].nunique() == df["key"].nunique()
+    # the source frame is untouched; what is not on the path is refused with pandas' error types where it has one
+    assert len(df) == len(big)
+    with pytest.raises(NotImplementedError):
+        df.drop_duplicates()  # all columns
+    with pytest.raises(NotImplementedError):
+        df.drop_duplicates(subset=["key", "x"])
+    with pytest.raises(NotImplementedError):
+        df.drop_duplicates(subset=["x"])  # float subset: NaN == NaN and -0.0 == 0.0 need their own handling
+    with pytest.raises(NotImplementedError):
+        df.drop_duplicates(subset=["key"], keep=False)
+    with pytest.raises(KeyError):
+        df.drop_duplicates(subset=["nope"])
+    with pytest.raises(KeyError):
+        big.drop_duplicates(subset=["nope"])
+    with pytest.raises(ValueError):
+        df.drop_duplicates(subset=["key"], keep="middle")
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 
@@ -547,3 +601,4 @@ def test_late_gpu_tests_are_sound_on_the_double(cpu_device, golden_dir):
     mod.test_concat_on_device()
     mod.test_astype_and_frame_nunique_on_device()
     mod.test_second_batch_vs_reference_golden(golden_dir)
+    mod.test_third_batch_vs_reference_golden(golden_dir)

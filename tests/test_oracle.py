@@ -206,3 +206,50 @@ def test_second_batch_against_reference(golden_dir):
         vc = df["key"].value_counts()
         assert sorted(zip(vc.index, vc.to_numpy())) == sorted(zip(z["vc_keys"], z["vc_counts"]))
         assert list(z["vc_counts"]) == sorted(z["vc_counts"], reverse=True) and int(z["nunique"][0]) == df["key"].nunique()
+
+
+def third_batch_inputs(golden_dir, z):
+    """The ext3 inputs, built by the generator's own helper so that generator and checkers cannot drift apart."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)  # defines functions only; the reference is imported inside main()
+    n, nb, nan, G = (int(x) for x in z["meta"])
+    return mod.third_batch_frames(synth, n, nb, nan, G)
+
+
+def test_third_batch_against_reference(golden_dir):
+    """drop_duplicates, concat, astype and DataFrame.nunique: the restatements pinned to the unmodified reference."""
+    num = ["key", "k2", "c0", "c1", "c2"]
+    for name, z in _load(golden_dir, "ext3_*.npz"):
+        df, db = third_batch_inputs(golden_dir, z)
+        for keep in ("first", "last"):
+            r = orc.drop_duplicates(df[num], ["key"], keep, False, NP)
+            assert_bit_equal(r.index.to_numpy(), z[f"dd_{keep}_index"], f"{name}:drop_duplicates {keep} labels")
+            assert_bit_equal(r.to_numpy(dtype=np.float64), z[f"dd_{keep}"], f"{name}:drop_duplicates {keep}")
+        r = orc.drop_duplicates(df[num], "k2", "last", True, NP)
+        assert_bit_equal(r.index.to_numpy(), z["dd_k2_ignore_index"], f"{name}:drop_duplicates ignore_index labels")
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z["dd_k2_ignore"], f"{name}:drop_duplicates ignore_index")
+        r = orc.drop_duplicates(df[["k2"]], "k2", "first", False, NP)
+        assert_bit_equal(r.index.to_numpy(), z["dd_series_index"], f"{name}:Series.drop_duplicates labels")
+        assert_bit_equal(r["k2"].to_numpy(), z["dd_series"], f"{name}:Series.drop_duplicates")
+        for ig in (False, True):
+            r = orc.concat_frames([df[num], db[num], df[num]], 0, ig, NP)
+            assert_bit_equal(r.index.to_numpy(), z[f"cat0_ig{int(ig)}_index"], f"{name}:concat rows labels ig={ig}")
+            assert_bit_equal(r.to_numpy(dtype=np.float64), z[f"cat0_ig{int(ig)}"], f"{name}:concat rows ig={ig}")
+        r = orc.concat_frames([df[num], df[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})], 1, False, NP)
+        assert list(r.columns) == list(z["cat1_cols"])
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z["cat1"], f"{name}:concat columns")
+        r = orc.df_astype(df, "float64", NP)
+        assert all(t == np.float64 for t in r.dtypes)
+        assert_bit_equal(r.to_numpy(), z["astype_f64"], f"{name}:astype float64")
+        r = orc.df_astype(df, {"key": np.float64, "flag": "int64"}, NP)
+        assert [str(t) for t in r.dtypes] == list(z["astype_dict_dtypes"])
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z["astype_dict"], f"{name}:astype mapping")
+        assert_bit_equal(orc.df_astype(df[["key", "k2", "big"]], "float64", NP).to_numpy(), z["astype_big"], f"{name}:astype of large ints")
+        # the large ints really are beyond exact float64 range, i.e. the cast rounds
+        assert (df["big"].astype("float64").astype("int64") != df["big"]).any()
+        r = orc.df_nunique(df[["key", "k2", "big"]], NP)
+        assert list(r.index) == list(z["nunique_cols"])
+        assert_bit_equal(r.to_numpy(), z["nunique"], f"{name}:nunique")

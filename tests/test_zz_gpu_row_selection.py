@@ -5,9 +5,12 @@ Written after this round's GPU budget was spent, so it has only run on the CPU d
 other GPU tests (bool widening and logical ops: test_boolean_pipelines_on_device; compaction and gather: the
 inner-merge tests); the file sorts last so that a surprise here cannot hide the rest of the suite behind ``-x``.
 
-The same holds for the later additions in this file (isin, concat, astype / DataFrame.nunique, the ext2 golden
-vectors): NOT yet run on a B200, only on the double.  concat launches nothing itself; astype reuses the
-true-division and widening-copy kernels that the var / std and bool-sum GPU tests already reach.
+The same holds for the later additions in this file (isin, concat, astype / DataFrame.nunique, drop_duplicates, the
+ext2 and ext3 golden vectors): NOT yet run on a B200, only on the double.  concat launches nothing itself; astype
+reuses the true-division and widening-copy kernels that the var / std and bool-sum GPU tests already reach;
+drop_duplicates is sort + elementwise compare + compaction + gather, each reached by sort_values / row selection
+tests -- the one new thing it does to a kernel is hand the elementwise compare two views shifted by one row (8-byte
+aligned, not 32), which elementwise.cu routes to its scalar sweep (``aligned32`` test on every operand).
 """
 
 import numpy as np
@@ -204,5 +207,59 @@ def test_second_batch_vs_reference_golden(golden_dir):
             assert np.array_equal(vc.to_numpy(), z["vc_counts"])
             assert dict(zip(vc.index, vc.to_numpy())) == dict(zip(z["vc_keys"], z["vc_counts"]))
             assert df["key"].nunique() == int(z["nunique"][0])
+    finally:
+        config.NPartitions.put(old)
+
+
+def test_third_batch_vs_reference_golden(golden_dir):
+    """drop_duplicates, concat, astype, DataFrame.nunique against golden vectors produced by the UNMODIFIED reference
+    (tests/golden/ext3_*.npz); inputs come from the generator's own helper (no reference needed to build them)."""
+    import glob
+    import importlib.util
+    import os
+
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        files = sorted(glob.glob(os.path.join(golden_dir, "ext3_*.npz")))
+        assert files
+        num = ["key", "k2", "c0", "c1", "c2"]
+        for f in files:
+            z = np.load(f, allow_pickle=False)
+            n, nb, nan, G = (int(x) for x in z["meta"])
+            pdf, pb = gen.third_batch_frames(synth, n, nb, nan, G)
+            df, db = bpd.DataFrame(pdf), bpd.DataFrame(pb)
+            for keep in ("first", "last"):
+                r = df[num].drop_duplicates(subset=["key"], keep=keep)._to_pandas()
+                assert np.array_equal(r.index.to_numpy(), z[f"dd_{keep}_index"]), keep
+                _exact(r.to_numpy(dtype=np.float64), z[f"dd_{keep}"], f"drop_duplicates {keep}")
+            r = df[num].drop_duplicates(subset=["k2"], keep="last", ignore_index=True)._to_pandas()
+            assert np.array_equal(r.index.to_numpy(), z["dd_k2_ignore_index"])
+            _exact(r.to_numpy(dtype=np.float64), z["dd_k2_ignore"], "drop_duplicates ignore_index")
+            r = df["k2"].drop_duplicates()._to_pandas()
+            assert np.array_equal(r.index.to_numpy(), z["dd_series_index"])
+            assert np.array_equal(np.asarray(r).ravel(), z["dd_series"])
+            for ig in (False, True):
+                r = bpd.concat([df[num], db[num], df[num]], ignore_index=ig)._to_pandas()
+                assert np.array_equal(r.index.to_numpy(), z[f"cat0_ig{int(ig)}_index"]), ig
+                _exact(r.to_numpy(dtype=np.float64), z[f"cat0_ig{int(ig)}"], f"concat rows ig={ig}")
+            r = bpd.concat([df[num], df[["c0", "c1"]].rename(columns={"c0": "x", "c1": "y"})], axis=1)._to_pandas()
+            assert list(r.columns) == list(z["cat1_cols"])
+            _exact(r.to_numpy(dtype=np.float64), z["cat1"], "concat columns")
+            r = df.astype("float64")
+            assert all(t == np.float64 for t in r.dtypes)
+            _exact(r._to_pandas().to_numpy(), z["astype_f64"], "astype float64")
+            r = df.astype({"key": np.float64, "flag": "int64"})
+            assert [str(t) for t in r.dtypes] == list(z["astype_dict_dtypes"])
+            _exact(r._to_pandas().to_numpy(dtype=np.float64), z["astype_dict"], "astype mapping")
+            _exact(df[["key", "k2", "big"]].astype("float64")._to_pandas().to_numpy(), z["astype_big"], "astype of large ints")
+            r = df[["key", "k2", "big"]].nunique()
+            assert list(r.index) == list(z["nunique_cols"]) and np.array_equal(np.asarray(r), z["nunique"])
     finally:
         config.NPartitions.put(old)
