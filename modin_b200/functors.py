@@ -136,6 +136,22 @@ class DevAstype(DevFn):
             raise NotImplementedError(f"astype({dt}) is not on the B200 path (float64 / int64 / bool columns only)")
         return dt
 
+    @classmethod
+    def validate(cls, have: pandas.Series, col_dtypes) -> dict:
+        """{label: dtype} for ``col_dtypes`` (one dtype for every column, or a mapping) after checking every cast
+        against the current dtypes ``have`` -- called by the query compilers BEFORE anything is launched, so a
+        refused cast cannot leave a half-converted frame.  An unknown label raises pandas' KeyError."""
+        if not isinstance(col_dtypes, dict):
+            col_dtypes = {label: col_dtypes for label in have.index}
+        for label, dt in col_dtypes.items():
+            if label not in have.index:
+                raise KeyError("Only a column name can be used for the key in a dtype mappings argument. "
+                               f"'{label}' not found in columns.")  # fmt: skip
+            src, dst = np.dtype(have[label]), cls.target(dt)
+            if src != dst and not (dst == np.float64 or (dst == np.int64 and src == np.bool_)):
+                raise NotImplementedError(f"astype {src} -> {dst} is not on the B200 path")
+        return dict(col_dtypes)
+
     def __call__(self, block, *args, col_dtypes=None, **kwargs):
         _check_block(block, "DevAstype")
         if args:
@@ -446,6 +462,21 @@ class DevDropDuplicates(DevFn):
     Original row order and row labels are kept, as in pandas."""
 
     op = "drop_duplicates"
+
+    @staticmethod
+    def resolve(columns: pandas.Index, subset, keep) -> int:
+        """Position of the ONE subset column, after the argument checks both query compilers share (``subset=None``
+        means all columns, so it is accepted only for a one-column frame).  pandas' error types where it has one."""
+        cols = list(columns) if subset is None else ([subset] if not isinstance(subset, (list, tuple)) else list(subset))
+        if len(cols) != 1:
+            raise NotImplementedError("device drop_duplicates compares one int64 column (pass subset=[column])")
+        if cols[0] not in columns:
+            raise KeyError(pandas.Index([cols[0]]))
+        if keep not in ("first", "last"):
+            if keep is False:
+                raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
+            raise ValueError('keep must be either "first", "last" or False')
+        return int(columns.get_loc(cols[0]))
 
     def __call__(self, block, key_position=0, keep="first", ignore_index=False, **kwargs):
         from .block import torch_mod

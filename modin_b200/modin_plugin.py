@@ -224,6 +224,57 @@ def register(shims: bool | None = None):
             kw = {k: v for k, v in kwargs.items() if k in ("value",)}
             return self.__constructor__(self._modin_frame.map(lambda x: fx.DevFillna()(x, **kw), dtypes="copy"))
 
+        def astype(self, col_dtypes, errors: str = "raise"):
+            """qc.py:2335-2343 -> PandasDataframe.astype (df.py:1707-1810) maps ``df.astype`` over the blocks; here the
+            block function is the device cast (widening casts only, checked before anything is launched)."""
+            if errors != "raise":
+                raise NotImplementedError("astype(errors='ignore') is not on the B200 path")
+            mapping = fx.DevAstype.validate(self.dtypes, col_dtypes)
+            fn = fx.DevAstype()
+            return self.__constructor__(self._modin_frame.map(lambda blk: fn(blk, col_dtypes=mapping)),
+                                        shape_hint=self._shape_hint)  # fmt: skip
+
+        def unique(self, keep="first", ignore_index=True, subset=None):
+            """qc.py:2231-2270 -- what ``drop_duplicates`` (modin/pandas/base.py:1600-1623) and ``Series.unique``
+            ask for.  One full-axis application of the device functor instead of duplicated() + row selection."""
+            pos = fx.DevDropDuplicates.resolve(self.columns, subset, keep)
+            frame = self._modin_frame
+            if frame._partitions.shape[1] != 1:
+                raise NotImplementedError("device drop_duplicates: frames of one column partition (up to 32 columns)")
+            fn = fx.DevDropDuplicates()
+            new_frame = frame.apply_full_axis(
+                0, lambda blk: fn(blk, pos, keep=keep, ignore_index=bool(ignore_index)), new_columns=self.columns,
+                dtypes="copy", keep_partitioning=True, num_splits=1, sync_labels=False,
+            )  # fmt: skip
+            return self.__constructor__(new_frame, shape_hint=self._shape_hint)
+
+        def nunique(self, axis=0, dropna=True):
+            """qc.py:1109-1113 is a full-axis ``pandas.DataFrame.nunique``; here one group table per int64 column,
+            the answer is its number of groups.  The W counts go back as a 1 x W frame like the other reductions."""
+            if axis != 0:
+                raise NotImplementedError("nunique(axis=1) is not on the B200 path")
+            bad = [c for c, dt in zip(self.columns, self.dtypes) if np.dtype(dt) != np.int64]
+            if bad:
+                raise NotImplementedError(f"nunique on the B200 path counts int64 columns only (got {bad!r})")
+            counts = []
+            for label in self.columns:
+                key = self.getitem_column_array([label])
+                sizes = key.groupby_size(by=key, axis=0, groupby_kwargs={}, agg_args=(), agg_kwargs={})
+                counts.append(len(sizes.index))
+            from modin.utils import MODIN_UNNAMED_SERIES_LABEL
+
+            host = pandas.DataFrame([counts], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.int64)
+            return self.from_pandas(host, type(self._modin_frame))
+
+        def reset_index(self, **kwargs):
+            """qc.py ``reset_index``: only ``drop=True`` over all levels -- a renumbering of the blocks' range starts
+            (metadata).  Turning row labels into columns would need the labels on the device first."""
+            if not kwargs.get("drop", False) or kwargs.get("level") is not None:
+                raise NotImplementedError("reset_index on the B200 path: drop=True, no level=")
+            from .query_compiler import _reset_row_index
+
+            return self.__constructor__(_reset_row_index(self._modin_frame))
+
         def merge(self, right, **kwargs):
             """qc.py:657-667 -> MergeImpl.row_axis_merge (merge.py:104-252) with the per-block
             ``pandas.merge`` replaced by the device hash-join functor."""

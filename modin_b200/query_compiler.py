@@ -124,16 +124,9 @@ class B200QueryCompiler:
         ``qc.unique(keep, ignore_index, subset)``, qc.py:2231-2270: rows with the first / last occurrence of every
         value of ONE int64 subset column (``subset=None`` means all columns, so it is accepted only for a
         one-column frame)."""
-        cols = list(self.columns) if subset is None else ([subset] if not isinstance(subset, (list, tuple)) else list(subset))
-        if len(cols) != 1:
-            raise NotImplementedError("device drop_duplicates compares one int64 column (pass subset=[column])")
-        if cols[0] not in self.columns:
-            raise KeyError(pandas.Index([cols[0]]))
-        if keep not in ("first", "last"):
-            if keep is False:
-                raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
-            raise ValueError('keep must be either "first", "last" or False')
-        pos = int(self.columns.get_loc(cols[0]))
+        from .functors import DevDropDuplicates
+
+        pos = DevDropDuplicates.resolve(self.columns, subset, keep)
         return self.__constructor__(self._modin_frame.drop_duplicate_rows(pos, keep, bool(ignore_index)))
 
     def relabel_columns(self, new_labels):
@@ -211,17 +204,7 @@ class B200QueryCompiler:
         so that a refused cast leaves no half-converted frame."""
         if errors != "raise":
             raise NotImplementedError("astype(errors='ignore') is not on the B200 path")
-        if not isinstance(col_dtypes, dict):
-            col_dtypes = {label: col_dtypes for label in self.columns}
-        have = self.dtypes
-        for label, dt in col_dtypes.items():
-            if label not in have.index:
-                raise KeyError("Only a column name can be used for the key in a dtype mappings argument. "
-                               f"'{label}' not found in columns.")  # fmt: skip
-            src, dst = np.dtype(have[label]), DevAstype.target(dt)
-            if src != dst and not (dst == np.float64 or (dst == np.int64 and src == np.bool_)):
-                raise NotImplementedError(f"astype {src} -> {dst} is not on the B200 path")
-        return self._astype_map(col_dtypes)
+        return self._astype_map(DevAstype.validate(self.dtypes, col_dtypes))
 
     def fillna(self, **kwargs):
         """qc.py:2710-2813: scalar / dict values are a Map; ``method``/``limit`` would be a Fold."""

@@ -263,3 +263,42 @@ def test_third_batch_vs_reference_golden(golden_dir):
             assert list(r.index) == list(z["nunique_cols"]) and np.array_equal(np.asarray(r), z["nunique"])
     finally:
         config.NPartitions.put(old)
+
+
+def test_late_additions_under_real_modin_on_b200():
+    """The same astype / drop_duplicates / unique / concat / nunique / reset_index scenarios as
+    tests/test_modin_plugin.py::test_late_additions_under_real_modin_cpu_double, through real ``modin.pandas`` with
+    the B200 execution plugged in.  Needs the reference Modin under baseline/_ref (it travels with the snapshot)."""
+    import importlib.util
+    import os
+    import sys
+    import warnings
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "modin")):
+        pytest.skip("reference Modin not installed under baseline/_ref")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    warnings.filterwarnings("ignore")
+    from modin_b200 import _lib, config, modin_plugin
+
+    ns = modin_plugin.register()
+    import modin
+    import modin.config as cfg
+    import modin.pandas as mpd
+
+    modin.set_execution(engine="B200", storage_format="Arrow")
+    cfg.NPartitions.put(4)
+    spec = importlib.util.spec_from_file_location("plugin_scenarios", os.path.join(root, "tests", "test_modin_plugin.py"))
+    scen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scen)
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        lib = _lib.load()
+        before = lib.mb200_launch_count()
+        scen._late_scenarios(mpd, ns)
+        assert lib.mb200_launch_count() > before
+    finally:
+        config.NPartitions.put(old)
