@@ -262,6 +262,36 @@ class DeviceBlock:
             replicated=self.replicated,
         )
 
+    def set_axis(self, labels, axis=0, **kwargs) -> "DeviceBlock":
+        """New labels over the same column buffers.  Under real Modin this is what ``PandasDataframe``'s deferred label
+        synchronisation applies to every partition (``apply_idx_objs``: ``df.set_axis(idx, axis="index")`` /
+        ``df.set_axis(cols, axis="columns")``, df.py:940-1030), so the block has to answer it like a pandas frame."""
+        if axis in (1, "columns"):
+            labels = labels if isinstance(labels, pandas.Index) else pandas.Index(list(labels))
+            if len(labels) != len(self.cols):
+                raise ValueError(f"Length mismatch: Expected axis has {len(self.cols)} elements, "
+                                 f"new values have {len(labels)} elements")  # fmt: skip
+            return self.with_cols(self.cols, labels)
+        if axis not in (0, "index"):
+            raise ValueError(f"No axis named {axis} for object type DeviceBlock")
+        labels = labels if isinstance(labels, pandas.Index) else pandas.Index(labels)
+        if len(labels) != self.nrows:
+            raise ValueError(f"Length mismatch: Expected axis has {self.nrows} elements, "
+                             f"new values have {len(labels)} elements")  # fmt: skip
+        if isinstance(labels, pandas.RangeIndex) and labels.step == 1 and labels.name is None:
+            if self.has_range_index() and labels.start == self.range_start:
+                return self
+            out = DeviceBlock(self.cols, self.columns, nrows=self.nrows, range_start=labels.start)
+        elif not isinstance(labels, pandas.MultiIndex) and labels.dtype.kind in "if" and len(labels) > 0:
+            arr = labels.to_numpy()
+            arr = arr.astype(np.int64) if arr.dtype.kind == "i" else arr.astype(np.float64)
+            out = DeviceBlock(self.cols, self.columns, nrows=self.nrows, index_cols=[DeviceColumn.from_numpy(arr)],
+                              index_names=[labels.name])  # fmt: skip
+        else:
+            out = DeviceBlock(self.cols, self.columns, nrows=self.nrows, index_host=labels)
+        out.replicated = self.replicated
+        return out
+
     def select_columns(self, positions: Sequence[int]) -> "DeviceBlock":
         """Column subset sharing the buffers (mask along axis 1)."""
         return self.with_cols([self.cols[i] for i in positions], self.columns[list(positions)])

@@ -187,6 +187,14 @@ def register(shims: bool | None = None):
         le = Binary.register(fx.DevBinary("le"), infer_dtypes="bool")
         gt = Binary.register(fx.DevBinary("gt"), infer_dtypes="bool")
         ge = Binary.register(fx.DevBinary("ge"), infer_dtypes="bool")
+        # Series comparisons are separate registrations in the reference (qc.py:586-604, they take fill_value);
+        # on the device a Series is a one-column frame, so the same functors serve
+        series_eq = Binary.register(fx.DevBinary("eq"), infer_dtypes="bool")
+        series_ne = Binary.register(fx.DevBinary("ne"), infer_dtypes="bool")
+        series_lt = Binary.register(fx.DevBinary("lt"), infer_dtypes="bool")
+        series_le = Binary.register(fx.DevBinary("le"), infer_dtypes="bool")
+        series_gt = Binary.register(fx.DevBinary("gt"), infer_dtypes="bool")
+        series_ge = Binary.register(fx.DevBinary("ge"), infer_dtypes="bool")
         __and__ = Binary.register(fx.DevLogical("and"), infer_dtypes="bool")  # qc.py:541-571
         __or__ = Binary.register(fx.DevLogical("or"), infer_dtypes="bool")
         __xor__ = Binary.register(fx.DevLogical("xor"), infer_dtypes="bool")
@@ -265,6 +273,85 @@ def register(shims: bool | None = None):
 
             host = pandas.DataFrame([counts], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.int64)
             return self.from_pandas(host, type(self._modin_frame))
+
+        def getitem_array(self, key):
+            """qc.py:3072-3103.  A one-column bool query compiler is boolean row selection: the reference registers
+            ``lambda df, r: df[r]`` as a Binary template (``__getitem_bool``, qc.py:3021-3025) and calls it with
+            ``broadcast=True`` -- ``broadcast_apply(axis=0, ..., join_type="left", labels="drop")``.  Same call here
+            with the device row filter as the block function (the template itself cannot be reused: its broadcast
+            branch calls ``right.squeeze()`` on the block, binary.py:396-402).  Lists of labels go to Modin's code."""
+            if isinstance(key, type(self)) and len(key.dtypes) == 1 and pandas.api.types.is_bool_dtype(key.dtypes.iloc[0]):
+                if len(key.index) != len(self.index):
+                    raise ValueError(f"Item wrong length {len(key.index)} instead of {len(self.index)}.")
+                fn = fx.DevRowFilter()
+                new_frame = self._modin_frame.broadcast_apply(
+                    0, lambda left, right: fn(left, right), key._modin_frame, join_type="left", labels="drop",
+                    dtypes="copy",
+                )  # fmt: skip
+                return self.__constructor__(new_frame)
+            return super().getitem_array(key)
+
+        def isin(self, values, ignore_indices=False):
+            """qc.py ``isin`` (a Map over ``pandas.DataFrame.isin``): a list of integers against int64 columns."""
+            if isinstance(values, (type(self), dict, pandas.Series, pandas.DataFrame)) or ignore_indices:
+                raise NotImplementedError("isin on the B200 path takes a list / array of integers")
+            fn = fx.DevIsin(values)
+            return self.__constructor__(self._modin_frame.map(lambda blk: fn(blk), dtypes=np.bool_))
+
+        def dropna(self, **kwargs):
+            """qc.py:3249-3333.  Rows only: ``notna`` of the (subset) columns -> row-wise all / any -> the boolean
+            row selection above, all on the device."""
+            from pandas._libs import lib as pandas_lib
+
+            how = kwargs.get("how", "any")
+            how = "any" if how is pandas_lib.no_default or how is None else how
+            if kwargs.get("axis", 0) not in (0, "index") or kwargs.get("thresh", pandas_lib.no_default) not in (pandas_lib.no_default, None):
+                raise NotImplementedError("dropna on the B200 path drops rows, without thresh=")
+            if how not in ("any", "all"):
+                raise ValueError(f"invalid how option: {how}")
+            subset = kwargs.get("subset")
+            src = self if subset is None else self.getitem_column_array(list(subset) if pandas.api.types.is_list_like(subset) else [subset])
+            flags = src.notna()._modin_frame
+            from modin.utils import MODIN_UNNAMED_SERIES_LABEL
+
+            fn = fx.DevRowLogical("all" if how == "any" else "any", label=MODIN_UNNAMED_SERIES_LABEL)
+            mask = flags.apply_full_axis(
+                1, lambda blk: fn(blk), new_index=flags.copy_index_cache(), new_columns=pandas.Index([MODIN_UNNAMED_SERIES_LABEL]),
+                dtypes=np.bool_, keep_partitioning=True, num_splits=1, sync_labels=False,
+            )  # fmt: skip
+            return self.getitem_array(self.__constructor__(mask, shape_hint="column"))
+
+        def _var(self, sqrt, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+            """Two TreeReduce passes like the standalone query compiler: the means, then the sums of squared deviations
+            from them (``DevSsdMap``); ``ssd / (count - ddof)`` on the W reduced numbers is host arithmetic, and the
+            result goes back as the 1 x W frame the API layer expects from a reduction."""
+            if axis not in (0, "index", None):
+                raise NotImplementedError("row-wise var / std is not on the B200 path")
+            from modin.utils import MODIN_UNNAMED_SERIES_LABEL
+
+            if self._modin_frame._partitions.shape[1] != 1:
+                raise NotImplementedError("device var / std: frames of one column partition (up to 32 columns)")
+            mean = self.mean(axis=0, skipna=skipna, numeric_only=numeric_only).to_pandas()
+            centers = np.asarray(mean, dtype=np.float64).ravel()
+            W = len(centers)
+            parts_qc = TreeReduce.register(fx.DevSsdMap(centers), fx.DevReduce("sum", phase="reduce"))(
+                self, axis=0, skipna=skipna, numeric_only=numeric_only
+            )  # fmt: skip
+            # the reduced block is 1 x 2W (sums of squares, then counts) while the template's metadata says W columns,
+            # so it is read from the partition directly instead of through PandasDataframe.to_pandas' shape check
+            parts = np.asarray(parts_qc._modin_frame._partitions[0, 0].get().to_numpy(), dtype=np.float64).ravel()
+            ssd, cnt = parts[:W], parts[W:]
+            with np.errstate(all="ignore"):
+                out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
+                out = np.sqrt(out) if sqrt else out
+            host = pandas.DataFrame([out], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.float64)
+            return self.from_pandas(host, type(self._modin_frame))
+
+        def var(self, axis=0, **kwargs):  # qc.py:1152 (a Reduce over pandas.DataFrame.var in the reference)
+            return self._var(False, axis, **kwargs)
+
+        def std(self, axis=0, **kwargs):  # qc.py:1153
+            return self._var(True, axis, **kwargs)
 
         def reset_index(self, **kwargs):
             """qc.py ``reset_index``: only ``drop=True`` over all levels -- a renumbering of the blocks' range starts

@@ -565,6 +565,32 @@ def test_drop_duplicates_keeps_first_or_last_in_row_order(cpu_device):
         df.drop_duplicates(subset=["key"], keep="middle")
 
 
+def test_block_set_axis_relabels_without_copying(cpu_device):
+    """What real Modin's deferred label synchronisation applies to every partition (df.py:940-1030)."""
+    from modin_b200.block import DeviceBlock
+
+    pdf = pandas.DataFrame({"a": np.arange(5, dtype=np.float64), "b": np.arange(5, dtype=np.int64) * 3})
+    blk = DeviceBlock.from_pandas(pdf)
+    cols = blk.set_axis(pandas.Index(["x", "y"]), axis="columns")
+    assert list(cols.columns) == ["x", "y"] and cols.cols[0] is blk.cols[0] and list(blk.columns) == ["a", "b"]
+    assert blk.set_axis(pandas.RangeIndex(0, 5), axis="index") is blk  # nothing to do
+    shifted = blk.set_axis(pandas.RangeIndex(10, 15), axis="index")
+    assert shifted.has_range_index() and shifted.range_start == 10 and shifted.cols[1] is blk.cols[1]
+    for labels in (pandas.Index([7, 3, 9, 1, 5]), pandas.Index([0.5, 1.5, 2.5, 3.5, 4.5], name="t"),
+                   pandas.Index(list("vwxyz")), pandas.RangeIndex(0, 10, 2)):  # fmt: skip
+        out = blk.set_axis(labels, axis=0)
+        want = pdf.set_axis(labels, axis=0)
+        got = out.to_pandas()
+        assert got.index.equals(want.index) and got.index.name == want.index.name, labels
+        assert _same(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64))
+    with pytest.raises(ValueError):
+        blk.set_axis(pandas.Index(["only"]), axis=1)
+    with pytest.raises(ValueError):
+        blk.set_axis(pandas.RangeIndex(4), axis=0)
+    with pytest.raises(ValueError):
+        blk.set_axis(pandas.RangeIndex(5), axis=2)
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 

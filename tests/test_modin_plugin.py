@@ -157,6 +157,32 @@ def _late_scenarios(mpd, ns):
     dd, wdd = mdf.drop_duplicates(subset=["key"], keep="last"), pdf.drop_duplicates(subset=["key"], keep="last")
     assert P(dd.reset_index(drop=True)).equals(wdd.reset_index(drop=True))  # non-range labels -> 0..K-1
 
+    # Series comparisons (qc.series_gt ...), logical ops between Series, and what hangs off them
+    assert P(mdf["c0"] > 0.0).equals(pdf["c0"] > 0.0) and P(mdf["key"] == 3).equals(pdf["key"] == 3)
+    assert P(mdf["c0"] >= mdf["c1"]).equals(pdf["c0"] >= pdf["c1"])
+    assert P((mdf["c0"] > 0.0) & (mdf["c1"] < 0.0)).equals((pdf["c0"] > 0.0) & (pdf["c1"] < 0.0))
+    assert P(mdf[mdf["c0"] > 0.5]).equals(pdf[pdf["c0"] > 0.5])  # boolean row selection, labels kept
+    assert P(mdf[(mdf["c0"] > 0.0) | (mdf["key"] == 3)]).equals(pdf[(pdf["c0"] > 0.0) | (pdf["key"] == 3)])
+    assert P(mdf[mdf["c0"] > 100.0]).shape == (0, pdf.shape[1])
+    sel, wsel = mdf[mdf["c0"] > 0.0], pdf[pdf["c0"] > 0.0]
+    assert np.allclose(P(sel[["c0", "c1", "c2"]].sum()).to_numpy(), wsel[["c0", "c1", "c2"]].sum().to_numpy(), rtol=0, atol=1e-9)
+    assert P(mdf.dropna()).equals(pdf.dropna())
+    assert P(mdf.dropna(how="all", subset=["c0", "c1"])).equals(pdf.dropna(how="all", subset=["c0", "c1"]))
+    with pytest.raises(NotImplementedError):
+        mdf.dropna(axis=1)
+    assert P(mdf[["key", "k2"]].isin([3, 7, -10, 20])).equals(pdf[["key", "k2"]].isin([3, 7, -10, 20]))
+    assert P(mdf[mdf["key"].isin([1, 2, 3])]).equals(pdf[pdf["key"].isin([1, 2, 3])])
+    assert P(mdf.assign(d=mdf["c0"] * 2.0)).equals(pdf.assign(d=pdf["c0"] * 2.0))
+    assert P(mdf.head(7)).equals(pdf.head(7))
+    # var / std: a different summation order than pandas, so the last bits may differ (rtol, not equals)
+    fcols = ["c0", "c1", "c2"]
+    for ddof in (1, 0):
+        got, want = P(mdf[fcols].var(ddof=ddof)), pdf[fcols].var(ddof=ddof)
+        assert list(got.index) == list(want.index) and np.allclose(got.to_numpy(), want.to_numpy(), rtol=1e-12, atol=0)
+    assert np.allclose(P(mdf[fcols].std()).to_numpy(), pdf[fcols].std().to_numpy(), rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):
+        mdf[fcols].var(axis=1)
+
 
 def test_late_additions_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
     import torch
