@@ -135,6 +135,13 @@ class DeviceColumn:
         return DeviceColumn(self.data[start:stop], self.dtype)
 
 
+class NotOnDevicePath(NotImplementedError, AttributeError):
+    """A pandas method was looked up on a device block.  Under real Modin that means a query-compiler method the
+    plug-in does not override reached a partition with Modin's pandas lambda.  ``NotImplementedError`` because that
+    is this package's contract for anything off the path (no pandas fallback); ``AttributeError`` as well so that
+    ``hasattr`` / ``getattr(x, name, default)`` probes (numpy, torch, copy, pickle) keep working."""
+
+
 class DeviceBlock:
     """Columnar device block = payload of one block partition."""
 
@@ -178,6 +185,15 @@ class DeviceBlock:
         self.index_cols = list(index_cols) if index_cols else None
         self.index_names = list(index_names) if index_names else None
         self.index_host = index_host  # only for small blocks (reduction results etc.)
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails (every slot is set in __init__)
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)  # protocol probes: plain AttributeError, no story to tell
+        raise NotOnDevicePath(
+            f"DeviceBlock has no pandas method {name!r}: the operation that reached this partition has no device "
+            "implementation in modin_b200 (unsupported operations raise instead of falling back to pandas)"
+        )
 
     # ---- pandas-like surface used by the partition layer ---------------------------------
     def __len__(self):

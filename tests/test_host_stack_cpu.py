@@ -591,6 +591,26 @@ def test_block_set_axis_relabels_without_copying(cpu_device):
         blk.set_axis(pandas.RangeIndex(5), axis=2)
 
 
+def test_pandas_method_on_a_block_is_a_clear_refusal(cpu_device):
+    """A pandas lambda reaching a device block (an operation without a device functor) must say so -- and must not
+    disturb attribute probing by numpy / torch / copy."""
+    import copy
+
+    from modin_b200.block import DeviceBlock, NotOnDevicePath
+
+    blk = DeviceBlock.from_pandas(pandas.DataFrame({"a": [1.0, 2.0]}))
+    with pytest.raises(NotImplementedError, match="no device implementation"):
+        blk.squeeze(axis=1)
+    with pytest.raises(AttributeError):
+        blk.cumsum
+    assert issubclass(NotOnDevicePath, NotImplementedError) and issubclass(NotOnDevicePath, AttributeError)
+    assert not hasattr(blk, "squeeze") and getattr(blk, "iloc", None) is None
+    assert not hasattr(blk, "__array__") and not hasattr(blk, "__cuda_array_interface__")
+    dup = copy.copy(blk)
+    assert dup.nrows == 2 and dup.cols[0] is blk.cols[0] and list(dup.columns) == ["a"]
+    assert np.asarray([[blk]], dtype=object).shape == (1, 1)  # still an opaque object to numpy, not a sequence
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 

@@ -182,6 +182,10 @@ def _late_scenarios(mpd, ns):
     assert np.allclose(P(mdf[fcols].std()).to_numpy(), pdf[fcols].std().to_numpy(), rtol=1e-12, atol=0)
     with pytest.raises(NotImplementedError):
         mdf[fcols].var(axis=1)
+    # a query-compiler method the plug-in does not override reaches the blocks with Modin's pandas lambda: refused
+    # with a message that says so (it used to be a bare AttributeError on the block)
+    with pytest.raises(NotImplementedError, match="no device implementation"):
+        P(mdf[fcols].cumsum())
 
 
 def test_late_additions_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
