@@ -644,6 +644,7 @@ def test_late_gpu_tests_are_sound_on_the_double(cpu_device, golden_dir):
     mod.test_boolean_row_selection_and_dropna_on_device()
     mod.test_pipeline_filter_derive_aggregate_on_device()
     mod.test_isin_is_a_join_probe_on_device()
+    mod.test_baseline_config0_abs_and_sum_at_its_own_size()
     mod.test_concat_on_device()
     mod.test_astype_and_frame_nunique_on_device()
     mod.test_second_batch_vs_reference_golden(golden_dir)

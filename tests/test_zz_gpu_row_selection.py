@@ -95,6 +95,33 @@ def test_isin_is_a_join_probe_on_device():
     _exact(sel.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), "filter by isin")
 
 
+def test_baseline_config0_abs_and_sum_at_its_own_size():
+    """BASELINE.json configs[0] -- ``df.abs()`` + ``df.sum()`` on 1e6 x 4 float64, the reference's own CPU-runnable
+    case -- at exactly that size against the oracle (NPartitions=4): abs bit-exact, the sum within the fp64 tolerance
+    the north star states, 4 * log2(n) * 2**-53 * sum|x| (same code path as test_against_oracle_various_shapes, which
+    stops at 262144 rows)."""
+    import math
+
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+    from oracle import reference_path as orc
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        n, W = 1_000_000, 4
+        pdf = synth.host_frame(n, W, seed=5, nan_per_64k=500)
+        df = bpd.DataFrame(pdf)
+        _exact(df.abs()._to_pandas().to_numpy(), orc.df_abs(pdf, 4).to_numpy(), "abs 1e6 x 4")
+        got, want = np.asarray(df.sum(), dtype=np.float64), orc.df_sum(pdf, 4).to_numpy()
+        tol = 4.0 * math.log2(n) * 2.0**-53 * np.nansum(np.abs(pdf.to_numpy()), axis=0)
+        assert got.shape == want.shape == (W,) and (np.abs(got - want) <= tol).all(), (got - want, tol)
+        gabs = np.asarray(df.abs().sum(), dtype=np.float64)  # the config's two operations chained
+        assert (np.abs(gabs - orc.df_sum(orc.df_abs(pdf, 4), 4).to_numpy()) <= tol).all()
+    finally:
+        config.NPartitions.put(old)
+
+
 def test_concat_on_device():
     """concat(axis=0) lines up row partitions (labels restart per input unless ignore_index); axis=1 is hstack.
     No kernel of its own: what is checked on the device is that operators run over the lined-up partitions."""
