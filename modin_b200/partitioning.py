@@ -772,6 +772,18 @@ def gather_block(block: DeviceBlock) -> DeviceBlock:
         ic = [DeviceColumn(g, c.dtype) for g, c in zip(gathered[ncol:], icols)]
         out = DeviceBlock(cols, block.columns, nrows=nrows, index_cols=ic, index_names=block.index_names)
     else:
-        out = DeviceBlock(cols, block.columns, nrows=nrows, range_start=0)
+        if block.index_host is not None:
+            raise NotImplementedError("gathering row shards with host-resident (non-numeric) row labels is not on the B200 path")
+        # every shard is a run of a RangeIndex, but not necessarily of 0..N: tail() / a shifted RangeIndex start
+        # later, and slices taken shard by shard need not run on from each other
+        t = torch_mod()
+        dev = tensors[0].device if tensors else ("cuda" if dist._dist().get_backend() == "nccl" else "cpu")
+        spans = dist.all_gather_small(t.tensor([block.range_start, block.nrows], dtype=t.int64, device=dev))
+        spans = [(int(s), int(n)) for s, n in spans if n > 0]
+        if all(b[0] == a[0] + a[1] for a, b in zip(spans, spans[1:])):  # one job-wide range: labels stay O(1)
+            out = DeviceBlock(cols, block.columns, nrows=nrows, range_start=spans[0][0] if spans else 0)
+        else:
+            labels = t.cat([t.arange(s, s + n, dtype=t.int64, device=dev) for s, n in spans])
+            out = DeviceBlock(cols, block.columns, nrows=nrows, index_cols=[DeviceColumn(labels, np.int64)], index_names=[None])
     out.replicated = True
     return out

@@ -8,6 +8,7 @@ import os
 import socket
 
 import numpy as np
+import pandas
 import pytest
 import torch
 import torch.distributed as dist
@@ -235,6 +236,81 @@ def test_full_stack_var_std_and_dict_agg_across_ranks():
     got = np.concatenate([o[4] for o in out])
     assert np.array_equal(keys, want.index.to_numpy())
     assert np.allclose(got, want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9)
+
+
+def _full_stack_late_ops_job(rank, ws):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    def refused(f):
+        try:
+            f()
+        except NotImplementedError:
+            return True
+        return False
+
+    out = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(7_001, 3, seed=8, nan_per_64k=4000, key_modulus=29)
+        pdf["k2"] = synth.gen_i64(len(pdf), 55, 1, 6) - 3
+        df = bpd.DataFrame(pdf)  # sharded by rank; _to_pandas() gathers the shards in rank order
+        out["astype"] = df.astype({"key": "float64"})._to_pandas()
+        out["filter"] = df[df["c0"] > 0.25]._to_pandas()
+        out["dropna"] = df.dropna()._to_pandas()
+        out["isin"] = df[df["key"].isin([1, 5, 28])]._to_pandas()
+        out["wide"] = bpd.concat([df, df[["c0"]].rename(columns={"c0": "x"})], axis=1)._to_pandas()
+        out["head"], out["tail"] = df.head(4000)._to_pandas(), df.tail(4000)._to_pandas()
+        # row labels of gathered range-indexed shards: a RangeIndex that does not start at 0, and shard-local slices
+        # whose ranges do not run on from each other (explicit labels after the gather)
+        shifted = pdf.copy()
+        shifted.index = pandas.RangeIndex(1000, 1000 + len(pdf))
+        out["shifted"] = bpd.DataFrame(shifted)._to_pandas()
+        frame = df._query_compiler._modin_frame
+        out["sliced"] = type(df._query_compiler)(frame._slice_local(10, 100))._modin_frame.to_pandas()
+        out["nunique"] = df[["key", "k2"]].nunique()  # group tables are merged across the ranks
+        out["series_nunique"] = df["key"].nunique()
+        # a shard-local answer would be wrong for these: refused on every rank
+        out["concat_rows_refused"] = refused(lambda: bpd.concat([df, df]))
+        out["drop_duplicates_refused"] = refused(lambda: df.drop_duplicates(subset=["key"]))
+        out["local_rows"] = len(df._query_compiler._modin_frame)
+    return out
+
+
+def test_full_stack_late_ops_across_ranks():
+    """astype / row selection / dropna / isin / column concat / head / tail work shard by shard and gather to the
+    whole-frame pandas answer; nunique counts groups job-wide; row concat and drop_duplicates refuse under
+    torch.distributed instead of answering per shard."""
+    import pandas
+
+    out = _run(_full_stack_late_ops_job)
+    pdf = synth.host_frame(7_001, 3, seed=8, nan_per_64k=4000, key_modulus=29)
+    pdf["k2"] = synth.gen_i64(len(pdf), 55, 1, 6) - 3
+    assert sum(o["local_rows"] for o in out) == len(pdf) and all(o["local_rows"] > 0 for o in out)
+    want = {
+        "astype": pdf.astype({"key": "float64"}),
+        "filter": pdf[pdf["c0"] > 0.25],
+        "dropna": pdf.dropna(),
+        "isin": pdf[pdf["key"].isin([1, 5, 28])],
+        "wide": pandas.concat([pdf, pdf[["c0"]].rename(columns={"c0": "x"})], axis=1),
+        "head": pdf.head(4000),
+        "tail": pdf.tail(4000),
+        "shifted": pdf.set_axis(pandas.RangeIndex(1000, 1000 + len(pdf)), axis=0),
+        "sliced": pandas.concat([pdf.iloc[lo + 10 : lo + 100] for lo, _ in (bdist.shard_bounds(len(pdf), r, 2) for r in range(2))]),
+    }
+    for o in out:  # the gathered frame is the same on every rank
+        for name, w in want.items():
+            g = o[name]
+            assert list(g.columns) == list(w.columns) and np.array_equal(g.index.to_numpy(), w.index.to_numpy()), name
+            assert [str(t) for t in g.dtypes] == [str(t) for t in w.dtypes], name
+            assert np.array_equal(g.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), equal_nan=True), name
+        assert list(o["nunique"].index) == ["key", "k2"] and list(o["nunique"]) == list(pdf[["key", "k2"]].nunique())
+        assert o["series_nunique"] == pdf["key"].nunique()
+        assert o["concat_rows_refused"] and o["drop_duplicates_refused"]
 
 
 def _full_stack_sort_job(rank, ws):
