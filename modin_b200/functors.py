@@ -482,6 +482,11 @@ class DevDropDuplicates(DevFn):
         from .block import torch_mod
 
         _check_block(block, "DevDropDuplicates")
+        from . import dist
+
+        if dist.is_distributed() and not block.replicated:
+            # equal keys on different GPUs: a shard-local answer would be wrong, and both front doors end up here
+            raise NotImplementedError("multi-GPU drop_duplicates is not on the B200 path")
         if keep not in ("first", "last"):
             raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
         key = block.cols[key_position]

@@ -86,6 +86,7 @@ def register(shims: bool | None = None):
     from modin.core.io.io import BaseIO
     from modin.core.storage_formats.pandas.query_compiler import PandasQueryCompiler
 
+    from . import dist as bdist
     from . import functors as fx
     from . import partitioning as bp
     from .block import DeviceBlock
@@ -261,6 +262,10 @@ def register(shims: bool | None = None):
             the answer is its number of groups.  The W counts go back as a 1 x W frame like the other reductions."""
             if axis != 0:
                 raise NotImplementedError("nunique(axis=1) is not on the B200 path")
+            if bdist.is_distributed():
+                # each rank would count only its own key range of the group table; the multi-GPU path is the
+                # standalone front door (modin_b200.pandas), the plug-in has not been run under torch.distributed
+                raise NotImplementedError("nunique through the Modin plug-in is single-process")
             bad = [c for c, dt in zip(self.columns, self.dtypes) if np.dtype(dt) != np.int64]
             if bad:
                 raise NotImplementedError(f"nunique on the B200 path counts int64 columns only (got {bad!r})")
