@@ -313,6 +313,71 @@ def test_full_stack_late_ops_across_ranks():
         assert o["concat_rows_refused"] and o["drop_duplicates_refused"]
 
 
+def _full_stack_api_sweep_job(rank, ws):
+    """Every case: (device expression on the sharded frame, pandas expression on the whole frame)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    res = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(6_001, 3, seed=9, nan_per_64k=4000, key_modulus=17)
+        other = synth.host_frame(6_001, 3, seed=10, nan_per_64k=0, key_modulus=17)
+        rng = np.random.RandomState(3)
+        dim = pandas.DataFrame({"key": rng.permutation(17)[:14].astype(np.int64), "d0": rng.randn(14)})
+        df, do, dd = bpd.DataFrame(pdf), bpd.DataFrame(other), bpd.DataFrame(dim)
+        f = ["c0", "c1", "c2"]
+        v, pv, vo, pvo = df[f], pdf[f], do[f], other[f]
+        cases = {
+            "round": (lambda: v.round(2), lambda: pv.round(2)),
+            "clip": (lambda: v.clip(-0.5, 0.5), lambda: pv.clip(-0.5, 0.5)),
+            "fillna": (lambda: v.fillna(1.0), lambda: pv.fillna(1.0)),
+            "a*b+c": (lambda: v * vo + vo, lambda: pv * pvo + pvo),
+            "mul by a column": (lambda: v.mul(df["c1"], axis=0), lambda: pv.mul(pdf["c1"], axis=0)),
+            "comparison": (lambda: v < 0.0, lambda: pv < 0.0),
+            "logical": (lambda: (v > 0.0) & (v < 1.0), lambda: (pv > 0.0) & (pv < 1.0)),
+            "assign": (lambda: df.assign(d=df["c0"] * 2.0), lambda: pdf.assign(d=pdf["c0"] * 2.0)),
+            "drop + rename": (lambda: df.drop(columns=["c1"]).rename(columns={"c0": "x"}),
+                              lambda: pdf.drop(columns=["c1"]).rename(columns={"c0": "x"})),
+            "merge left": (lambda: df.merge(dd, on="key", how="left"), lambda: pdf.merge(dim, on="key", how="left")),
+            "merge inner": (lambda: df.merge(dd, on="key", how="inner"), lambda: pdf.merge(dim, on="key", how="inner")),
+            "isin": (lambda: df[["key"]].isin([1, 2, 16]), lambda: pdf[["key"]].isin([1, 2, 16])),
+            "groupby size": (lambda: df.groupby("key").size(), lambda: pdf.groupby("key").size()),
+            "groupby max": (lambda: df.groupby("key").max(), lambda: pdf.groupby("key").max()),
+            "filter -> groupby": (lambda: df[df["c0"] > 0.0].groupby("key").sum(), lambda: pdf[pdf["c0"] > 0.0].groupby("key").sum()),
+            "filter -> tail": (lambda: df[df["c0"] > 0.0].tail(50), lambda: pdf[pdf["c0"] > 0.0].tail(50)),
+            "filter -> head": (lambda: df[df["c0"] > 0.0].head(50), lambda: pdf[pdf["c0"] > 0.0].head(50)),
+            "sort -> head": (lambda: df.sort_values("c0").head(20), lambda: pdf.sort_values("c0", kind="stable").head(20)),
+            "astype -> sum": (lambda: df.astype({"key": "float64"}).sum(), lambda: pdf.astype({"key": "float64"}).sum()),
+            "prod": (lambda: (v.head(40) * 1.1).prod(), lambda: (pv.head(40) * 1.1).prod()),
+        }
+        for red in ("sum", "mean", "min", "max", "count"):
+            cases[red] = ((lambda r=red: getattr(v, r)()), (lambda r=red: getattr(pv, r)()))
+        for name, (dev, host) in cases.items():
+            g, want = dev(), host()
+            g = g._to_pandas() if hasattr(g, "_to_pandas") else g
+            labels_ok = list(g.index) == list(want.index)
+            vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
+                                                            rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
+            res[name] = "ok" if labels_ok and vals_ok else f"values {vals_ok}, labels {labels_ok}, shape {g.shape} vs {want.shape}"
+        vc, wvc = df["key"].value_counts()._to_pandas(), pdf["key"].value_counts()  # tie order is unspecified
+        res["value_counts"] = "ok" if sorted(zip(vc.index, np.asarray(vc).ravel())) == sorted(zip(wvc.index, wvc)) else "pairs differ"
+    return res
+
+
+def test_full_stack_api_sweep_across_ranks():
+    """A regression net for silently wrong multi-GPU answers (the kind the gather's row labels were): compositions
+    of the API on a frame sharded over 2 ranks, gathered, against pandas on the whole frame -- values AND labels."""
+    out = _run(_full_stack_api_sweep_job)
+    for r, res in enumerate(out):
+        bad = {k: s for k, s in res.items() if s != "ok"}
+        assert not bad and len(res) >= 26, (r, bad)
+
+
 def _full_stack_sort_job(rank, ws):
     import sys
 
