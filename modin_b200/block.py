@@ -398,6 +398,12 @@ def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
             pos += b.nrows
     if contiguous:
         return DeviceBlock(cols, first.columns, nrows=nrows, range_start=first.range_start)
+    if all(b.has_range_index() for b in blocks) and cols:
+        # ranges that do not run on from each other (row-wise concat of frames, shard-local slices): still numeric
+        # labels, so they stay on the device as an int64 index column instead of becoming a host index
+        dev = cols[0].data.device
+        labels = t.cat([t.arange(b.range_start, b.range_start + b.nrows, dtype=t.int64, device=dev) for b in blocks])
+        return DeviceBlock(cols, first.columns, nrows=nrows, index_cols=[DeviceColumn(labels, np.int64)], index_names=[None])
     ih = blocks[0].index
     for b in blocks[1:]:
         ih = ih.append(b.index)

@@ -307,12 +307,45 @@ class DevBinary(DevFn):
                 a, b = ops.cast_columns_f64(a), ops.cast_columns_f64(b)
         return left.with_cols(ops.map_columns(kop, a, b))
 
+    def _empty(self, block, other):
+        """Zero rows: nothing to launch, but the result still has the dtypes the rules above give it (a comparison of
+        an empty frame is an empty BOOL frame -- ``df[df.x > 100][df.y > 0]`` and ``(empty > 0).any()`` depend on it)."""
+        f64, i64 = np.dtype("float64"), np.dtype("int64")
+        ldt = [c.dtype for c in block.cols]
+        if isinstance(other, DeviceBlock):
+            kop = "fillna" if self.op == "fillna" else _REFLECTED_FRAME.get(self.op) or _BINARY_TO_FRAME[self.op]
+            rdt = [c.dtype for c in other.cols]
+            rdt = rdt * len(ldt) if len(rdt) == 1 else rdt
+            if kop in _lib.PREDICATES:
+                dts = [np.dtype("bool")] * len(ldt)
+            elif kop == "div":
+                dts = [f64] * len(ldt)
+            elif kop != "fillna" and any(x != y for x, y in zip(ldt, rdt)):
+                dts = [f64] * len(ldt)  # mixed int64 / float64 operands are all promoted
+            else:
+                dts = ldt
+        else:
+            scalars = list(other) if isinstance(other, (list, tuple, np.ndarray, pandas.Series)) else [other]
+            kop = _BINARY_TO_SCALAR.get(self.op)
+            if kop is None:  # frame-only ops ("fillna"): nothing to decide without the frame
+                return block
+            any_float = any(isinstance(s, (float, np.floating)) for s in scalars)
+            if kop in _lib.PREDICATES:
+                dts = [np.dtype("bool")] * len(ldt)
+            elif kop in ("div_s", "rdiv_s"):
+                dts = [f64] * len(ldt)
+            else:
+                dts = [f64 if (any_float and d == i64) else d for d in ldt]
+        return block.with_cols([c if c.dtype == d else DeviceColumn.empty(0, d) for c, d in zip(block.cols, dts)])
+
     def __call__(self, block, other, *args, axis=None, level=None, fill_value=None, **kwargs):
         _check_block(block, f"DevBinary({self.op})")
         if level is not None or fill_value is not None:
             raise NotImplementedError("level= / fill_value= are not implemented on the B200 path")
-        if block.nrows == 0 or not block.cols:
+        if not block.cols:
             return block
+        if block.nrows == 0:
+            return self._empty(block, other)
         if isinstance(other, DeviceBlock):
             return self._frame(block, other)
         if _is_scalar(other):

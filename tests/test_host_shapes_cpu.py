@@ -1,0 +1,118 @@
+"""Odd frame SHAPES through the API on the CPU device double: frames made of several unequal row partitions whose
+range labels restart (what a row-wise concat produces), empty frames (a filter nothing passes) and one-row frames,
+flowing into the other operations.  Values, row labels and column labels against pandas.
+
+Found with this sweep and fixed: comparisons of an EMPTY frame kept the input dtype instead of giving an empty bool
+frame (so ``empty[empty.x > 0]`` and ``(empty > 0).any()`` were refused), and row-wise concatenation demoted restarting
+numeric labels to a host index (so ``sort_values`` of a concatenated frame was refused as "non-numeric labels").
+"""
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import config, synth
+
+
+@pytest.fixture(autouse=True)
+def _np4():
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    yield
+    config.NPartitions.put(old)
+
+
+def _compare(cases):
+    bad = {}
+    for name, (dev, host) in cases.items():
+        want = host()
+        g = dev()
+        g = g._to_pandas() if hasattr(g, "_to_pandas") else g
+        labels_ok = list(g.index) == list(want.index)
+        cols_ok = not hasattr(want, "columns") or list(g.columns) == list(want.columns)
+        vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
+                                                        rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
+        if not (labels_ok and cols_ok and vals_ok):
+            bad[name] = f"values {vals_ok}, labels {labels_ok}, columns {cols_ok}, shape {g.shape} vs {want.shape}"
+    assert not bad, bad
+
+
+@pytest.fixture
+def frames(cpu_device):
+    import modin_b200.pandas as bpd
+
+    pa = synth.host_frame(1003, 3, seed=1, nan_per_64k=3000, key_modulus=11)
+    pb = synth.host_frame(517, 3, seed=2, nan_per_64k=3000, key_modulus=11)
+    rng = np.random.RandomState(3)
+    dim = pandas.DataFrame({"key": rng.permutation(11)[:9].astype(np.int64), "d0": rng.randn(9)})
+    return bpd, pa, pb, dim
+
+
+def test_concatenated_frames_flow_into_the_other_operations(frames):
+    bpd, pa, pb, dim = frames
+    a, b, dd = bpd.DataFrame(pa), bpd.DataFrame(pb), bpd.DataFrame(dim)
+    cat, wcat = bpd.concat([a, b, a]), pandas.concat([pa, pb, pa])  # labels restart: 0..1002, 0..516, 0..1002
+    cati, wcati = bpd.concat([a, b, a], ignore_index=True), pandas.concat([pa, pb, pa], ignore_index=True)
+    f = ["c0", "c1", "c2"]
+    _compare({
+        "filter": (lambda: cat[cat["c0"] > 0.0], lambda: wcat[wcat["c0"] > 0.0]),
+        "dropna": (lambda: cat.dropna(), lambda: wcat.dropna()),
+        "head": (lambda: cat.head(1200), lambda: wcat.head(1200)),
+        "tail": (lambda: cat.tail(1200), lambda: wcat.tail(1200)),
+        "sort": (lambda: cat.sort_values("c0"), lambda: wcat.sort_values("c0", kind="stable")),
+        "sort ignore_index": (lambda: cat.sort_values("c0", ignore_index=True),
+                              lambda: wcat.sort_values("c0", kind="stable", ignore_index=True)),
+        "merge left": (lambda: cat.merge(dd, on="key", how="left"), lambda: wcat.merge(dim, on="key", how="left")),
+        "merge inner": (lambda: cat.merge(dd, on="key", how="inner"), lambda: wcat.merge(dim, on="key", how="inner")),
+        "groupby": (lambda: cat.groupby("key").mean(), lambda: wcat.groupby("key").mean()),
+        "binary with itself": (lambda: cat[f] + cat[f], lambda: wcat[f] + wcat[f]),
+        "a*b+c": (lambda: cati[f] * cati[f] + cati[f], lambda: wcati[f] * wcati[f] + wcati[f]),
+        "assign": (lambda: cat.assign(d=cat["c0"] * 2.0), lambda: wcat.assign(d=wcat["c0"] * 2.0)),
+        "drop_duplicates": (lambda: cat.drop_duplicates(subset=["key"]), lambda: wcat.drop_duplicates(subset=["key"])),
+        "drop_duplicates ignore_index": (lambda: cat.drop_duplicates(subset=["key"], ignore_index=True),
+                                         lambda: wcat.drop_duplicates(subset=["key"], ignore_index=True)),
+        "drop_duplicates last": (lambda: cati.drop_duplicates(subset=["key"], keep="last"),
+                                 lambda: wcati.drop_duplicates(subset=["key"], keep="last")),
+        "astype": (lambda: cat.astype({"key": "float64"}), lambda: wcat.astype({"key": "float64"})),
+        "concat of concats": (lambda: bpd.concat([cat, cati]), lambda: pandas.concat([wcat, wcati])),
+        "var": (lambda: cat[f].var(), lambda: wcat[f].var()),
+        "sum": (lambda: cat[f].sum(), lambda: wcat[f].sum()),
+    })  # fmt: skip
+
+
+def test_empty_and_one_row_frames(frames):
+    bpd, pa, pb, dim = frames
+    a, b, dd = bpd.DataFrame(pa), bpd.DataFrame(pb), bpd.DataFrame(dim)
+    emp, wemp = a[a["c0"] > 100.0], pa[pa["c0"] > 100.0]
+    assert len(emp) == 0
+    f = ["c0", "c1", "c2"]
+    # an empty comparison is an empty BOOL frame, an empty true division is float64, int (op) float promotes
+    assert list((emp[f] > 0.0).dtypes) == [np.dtype("bool")] * 3 and list((emp[f] >= emp[f]).dtypes) == [np.dtype("bool")] * 3
+    assert list((emp[["key"]] / 2).dtypes) == [np.dtype("float64")] and list((emp[["key"]] * 2).dtypes) == [np.dtype("int64")]
+    assert list((emp[["key"]] * 0.5).dtypes) == [np.dtype("float64")] and list((emp[["key"]] == 3).dtypes) == [np.dtype("bool")]
+    _compare({
+        "to_pandas": (lambda: emp, lambda: wemp),
+        "sum": (lambda: emp[f].sum(), lambda: wemp[f].sum()),
+        "mean": (lambda: emp[f].mean(), lambda: wemp[f].mean()),
+        "count": (lambda: emp[f].count(), lambda: wemp[f].count()),
+        "min": (lambda: emp[f].min(), lambda: wemp[f].min()),
+        "var": (lambda: emp[f].var(), lambda: wemp[f].var()),
+        "abs": (lambda: emp[f].abs(), lambda: wemp[f].abs()),
+        "affine": (lambda: emp[f] * 2.0 + 1.0, lambda: wemp[f] * 2.0 + 1.0),
+        "any": (lambda: (emp[f] > 0.0).any(), lambda: (wemp[f] > 0.0).any()),
+        "all": (lambda: (emp[f] > 0.0).all(), lambda: (wemp[f] > 0.0).all()),
+        "filter again": (lambda: emp[emp["c1"] > 0.0], lambda: wemp[wemp["c1"] > 0.0]),
+        "groupby": (lambda: emp.groupby("key").sum(), lambda: wemp.groupby("key").sum()),
+        "merge": (lambda: emp.merge(dd, on="key", how="left"), lambda: wemp.merge(dim, on="key", how="left")),
+        "sort": (lambda: emp.sort_values("c0"), lambda: wemp.sort_values("c0")),
+        "head": (lambda: emp.head(5), lambda: wemp.head(5)),
+        "drop_duplicates": (lambda: emp.drop_duplicates(subset=["key"]), lambda: wemp.drop_duplicates(subset=["key"])),
+        "astype": (lambda: emp.astype({"key": "float64"}), lambda: wemp.astype({"key": "float64"})),
+        "nunique": (lambda: emp[["key"]].nunique(), lambda: wemp[["key"]].nunique()),
+        "concat with an empty frame": (lambda: bpd.concat([a, emp, b]), lambda: pandas.concat([pa, wemp, pb])),
+        "concat of empties": (lambda: bpd.concat([emp, emp]), lambda: pandas.concat([wemp, wemp])),
+        "head(0) sum": (lambda: a.head(0)[f].sum(), lambda: pa.head(0)[f].sum()),
+        "one row drop_duplicates": (lambda: a.head(1).drop_duplicates(subset=["key"]), lambda: pa.head(1).drop_duplicates(subset=["key"])),
+        "one row sort": (lambda: a.head(1).sort_values("c0"), lambda: pa.head(1).sort_values("c0")),
+        "one row groupby": (lambda: a.head(1).groupby("key").sum(), lambda: pa.head(1).groupby("key").sum()),
+    })  # fmt: skip
