@@ -28,7 +28,7 @@ def _compare(cases):
         want = host()
         g = dev()
         g = g._to_pandas() if hasattr(g, "_to_pandas") else g
-        labels_ok = list(g.index) == list(want.index)
+        labels_ok = list(g.index) == list(want.index) and g.index.name == want.index.name
         cols_ok = not hasattr(want, "columns") or list(g.columns) == list(want.columns)
         vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
                                                         rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
@@ -116,3 +116,86 @@ def test_empty_and_one_row_frames(frames):
         "one row sort": (lambda: a.head(1).sort_values("c0"), lambda: pa.head(1).sort_values("c0")),
         "one row groupby": (lambda: a.head(1).groupby("key").sum(), lambda: pa.head(1).groupby("key").sum()),
     })  # fmt: skip
+
+
+def test_wide_frames_use_the_2d_grid_everywhere(frames):
+    """More than 32 columns: several column partitions, so every operation sees a 2-D grid of blocks."""
+    bpd, pa, pb, dim = frames
+    rng = np.random.RandomState(7)
+    W = 40
+    fcols = [f"w{i}" for i in range(W)]
+    wide = pandas.DataFrame(rng.randn(300, W), columns=fcols)
+    wide.iloc[::17, 3] = np.nan
+    wide.iloc[::29, 35] = np.nan
+    wide.insert(0, "key", rng.randint(0, 7, 300).astype(np.int64))
+    dw, dd, a = bpd.DataFrame(wide), bpd.DataFrame(dim), bpd.DataFrame(pa)
+    assert dw._query_compiler._modin_frame._partitions.shape[1] == 2
+    _compare({
+        "to_pandas": (lambda: dw, lambda: wide),
+        "filter": (lambda: dw[dw["w0"] > 0.0], lambda: wide[wide["w0"] > 0.0]),
+        "dropna": (lambda: dw.dropna(), lambda: wide.dropna()),
+        "head": (lambda: dw.head(77), lambda: wide.head(77)),
+        "tail": (lambda: dw.tail(77), lambda: wide.tail(77)),
+        "sum": (lambda: dw[fcols].sum(), lambda: wide[fcols].sum()),
+        "var": (lambda: dw[fcols].var(), lambda: wide[fcols].var()),
+        "a*b+c": (lambda: dw[fcols] * dw[fcols] + dw[fcols], lambda: wide[fcols] * wide[fcols] + wide[fcols]),
+        "comparison": (lambda: dw[fcols] < 0.0, lambda: wide[fcols] < 0.0),
+        "round": (lambda: dw[fcols].round(1), lambda: wide[fcols].round(1)),
+        "sort": (lambda: dw.sort_values("w5"), lambda: wide.sort_values("w5", kind="stable")),
+        "groupby": (lambda: dw.groupby("key").sum(), lambda: wide.groupby("key").sum()),
+        "merge": (lambda: dw.merge(dd, on="key", how="left"), lambda: wide.merge(dim, on="key", how="left")),
+        "drop_duplicates": (lambda: dw.drop_duplicates(subset=["key"]), lambda: wide.drop_duplicates(subset=["key"])),
+        "astype": (lambda: dw.astype({"key": "float64"}), lambda: wide.astype({"key": "float64"})),
+        "concat rows": (lambda: bpd.concat([dw, dw]), lambda: pandas.concat([wide, wide])),
+        "concat columns": (lambda: bpd.concat([dw, a.head(300)[["c0"]]], axis=1),
+                           lambda: pandas.concat([wide, pa.head(300)[["c0"]]], axis=1)),
+        "assign": (lambda: dw.assign(z=dw["w1"] * 2.0), lambda: wide.assign(z=wide["w1"] * 2.0)),
+        "columns from both partitions": (lambda: dw[["w39", "w2"]], lambda: wide[["w39", "w2"]]),
+    })  # fmt: skip
+
+
+def test_frames_whose_labels_are_not_a_plain_range(frames):
+    """Group tables and filtered frames carry their labels as device index columns; inputs may come with a named
+    integer index, a float index or (small frames) a string index."""
+    bpd, pa, pb, dim = frames
+    a, dd = bpd.DataFrame(pa), bpd.DataFrame(dim)
+    g, wg = a.groupby("key").sum(), pa.groupby("key").sum()
+    fl, wfl = a[a["c0"] > 0.0], pa[pa["c0"] > 0.0]
+    named = pa.set_axis(pandas.Index(np.arange(len(pa))[::-1] * 2, name="rid"), axis=0)
+    fidx = pa.set_axis(pandas.Index(np.linspace(0.0, 1.0, len(pa))), axis=0)
+    sidx = pa.head(40).set_axis(pandas.Index([f"r{i}" for i in range(40)]), axis=0)
+    dn, df_, ds = bpd.DataFrame(named), bpd.DataFrame(fidx), bpd.DataFrame(sidx)
+    _compare({
+        "group table * 2": (lambda: g * 2.0, lambda: wg * 2.0),
+        "group table head": (lambda: g.head(3), lambda: wg.head(3)),
+        "group table filter": (lambda: g[g["c0"] > 0.0], lambda: wg[wg["c0"] > 0.0]),
+        "group table sort": (lambda: g.sort_values("c1"), lambda: wg.sort_values("c1", kind="stable")),
+        "group table sum": (lambda: g.sum(), lambda: wg.sum()),
+        "group table + itself": (lambda: g + g, lambda: wg + wg),
+        "group table assign": (lambda: g.assign(z=g["c0"] - g["c1"]), lambda: wg.assign(z=wg["c0"] - wg["c1"])),
+        "filter twice": (lambda: fl[fl["c1"] > 0.0], lambda: wfl[wfl["c1"] > 0.0]),
+        "filter -> sort": (lambda: fl.sort_values("c2"), lambda: wfl.sort_values("c2", kind="stable")),
+        "filter -> merge": (lambda: fl.merge(dd, on="key", how="inner"), lambda: wfl.merge(dim, on="key", how="inner")),
+        "filter -> square": (lambda: fl[["c0"]] * fl[["c0"]], lambda: wfl[["c0"]] * wfl[["c0"]]),
+        "filter -> assign": (lambda: fl.assign(z=fl["c0"] + 1.0), lambda: wfl.assign(z=wfl["c0"] + 1.0)),
+        "filter -> tail": (lambda: fl.tail(13), lambda: wfl.tail(13)),
+        "filter -> drop_duplicates": (lambda: fl.drop_duplicates(subset=["key"], keep="last"),
+                                      lambda: wfl.drop_duplicates(subset=["key"], keep="last")),
+        "concat of filtered": (lambda: bpd.concat([fl, fl]), lambda: pandas.concat([wfl, wfl])),
+        "concat of plain and filtered": (lambda: bpd.concat([a, fl]), lambda: pandas.concat([pa, wfl])),
+        "named int index": (lambda: dn, lambda: named),
+        "named int index filter": (lambda: dn[dn["c0"] > 0.0], lambda: named[named["c0"] > 0.0]),
+        "named int index sort": (lambda: dn.sort_values("c0"), lambda: named.sort_values("c0", kind="stable")),
+        "named int index head": (lambda: dn.head(5), lambda: named.head(5)),
+        "named int index * 2": (lambda: dn * 2, lambda: named * 2),
+        "float index filter": (lambda: df_[df_["c0"] > 0.0], lambda: fidx[fidx["c0"] > 0.0]),
+        "float index tail": (lambda: df_.tail(5), lambda: fidx.tail(5)),
+        "string index": (lambda: ds, lambda: sidx),
+        "string index * 2": (lambda: ds[["c0"]] * 2.0, lambda: sidx[["c0"]] * 2.0),
+        "string index head": (lambda: ds.head(5), lambda: sidx.head(5)),
+        "string index sum": (lambda: ds[["c0", "c1"]].sum(), lambda: sidx[["c0", "c1"]].sum()),
+        "string index sort, ignore_index": (lambda: ds.sort_values("c0", ignore_index=True),
+                                            lambda: sidx.sort_values("c0", kind="stable", ignore_index=True)),
+    })  # fmt: skip
+    with pytest.raises(NotImplementedError, match="numeric / range row labels"):
+        ds[ds["c0"] > 0.0]._to_pandas()  # string labels cannot ride through the device compaction: refused, not dropped
