@@ -910,7 +910,7 @@ class DevGroupbyMap(DevFn):
         else:
             vals = ops.cast_columns_f64(vals) if self.agg in ("count", "mean") else vals
             if any(v.dtype != np.float64 for v in vals):
-                raise NotImplementedError("device groupby.sum aggregates float64 value columns only")
+                raise NotImplementedError(f"device groupby.{self.agg} aggregates float64 value columns only")
         cap = max(1024, min(self.capacity_hint, block.nrows))
         keys, sums, cnts, sizes = ops.hash_aggregate([(key, vals)], flags, cap)
         return _partial_block(self.agg, keys, key_label, sums, cnts, sizes, labels)
@@ -1031,7 +1031,7 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
         else:
             vals = ops.cast_columns_f64(vals) if agg in ("count", "mean") else vals
             if any(v.dtype != np.float64 for v in vals):
-                raise NotImplementedError("device groupby.sum aggregates float64 value columns only")
+                raise NotImplementedError(f"device groupby.{agg} aggregates float64 value columns only")
         items.append((key, vals))
     if len(labels) > _lib_max_cols():
         return None

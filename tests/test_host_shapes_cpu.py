@@ -22,7 +22,7 @@ def _np4():
     config.NPartitions.put(old)
 
 
-def _compare(cases):
+def _compare(cases, check_dtypes=False):
     bad = {}
     for name, (dev, host) in cases.items():
         want = host()
@@ -32,8 +32,12 @@ def _compare(cases):
         cols_ok = not hasattr(want, "columns") or list(g.columns) == list(want.columns)
         vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
                                                         rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
-        if not (labels_ok and cols_ok and vals_ok):
-            bad[name] = f"values {vals_ok}, labels {labels_ok}, columns {cols_ok}, shape {g.shape} vs {want.shape}"
+        gd = [str(t) for t in (g.dtypes if hasattr(g, "columns") else [g.dtype])]
+        wd = [str(t) for t in (want.dtypes if hasattr(want, "columns") else [want.dtype])]
+        dtypes_ok = gd == wd or not check_dtypes
+        if not (labels_ok and cols_ok and vals_ok and dtypes_ok):
+            bad[name] = (f"values {vals_ok}, labels {labels_ok}, columns {cols_ok}, shape {g.shape} vs {want.shape}, "
+                         f"dtypes {gd} vs {wd}")  # fmt: skip
     assert not bad, bad
 
 
@@ -116,6 +120,83 @@ def test_empty_and_one_row_frames(frames):
         "one row sort": (lambda: a.head(1).sort_values("c0"), lambda: pa.head(1).sort_values("c0")),
         "one row groupby": (lambda: a.head(1).groupby("key").sum(), lambda: pa.head(1).groupby("key").sum()),
     })  # fmt: skip
+
+
+def test_int64_bool_and_mixed_value_columns(cpu_device):
+    """The synthetic frames are float64; int64 and bool VALUE columns take the promotion / widening paths.  Values,
+    labels and the result dtypes against pandas; what is not on the path is refused, never approximated."""
+    import modin_b200.pandas as bpd
+
+    rng = np.random.RandomState(11)
+    n = 803
+    pdf = pandas.DataFrame({
+        "key": rng.randint(0, 9, n).astype(np.int64), "i": rng.randint(-1000, 1000, n).astype(np.int64),
+        "j": rng.randint(1, 50, n).astype(np.int64), "x": rng.randn(n), "b": rng.rand(n) > 0.5, "c": rng.rand(n) > 0.2,
+    })  # fmt: skip
+    pdf.loc[::37, "x"] = np.nan
+    df = bpd.DataFrame(pdf)
+    ints, wints = df[["i", "j"]], pdf[["i", "j"]]
+    bools, wbools = df[["b", "c"]], pdf[["b", "c"]]
+    mixed, wmixed = df[["i", "x"]], pdf[["i", "x"]]
+    as_i = {"columns": {"x": "i", "j": "i", "c": "b"}}  # a second operand under the first one's label
+    cases = {
+        "int abs": (lambda: ints.abs(), lambda: wints.abs()),
+        "int neg": (lambda: -ints, lambda: -wints),
+        "int + int scalar": (lambda: ints + 3, lambda: wints + 3),
+        "int * float scalar": (lambda: ints * 2.5, lambda: wints * 2.5),
+        "int / int scalar": (lambda: ints / 4, lambda: wints / 4),
+        "int / int frame": (lambda: ints / ints, lambda: wints / wints),
+        "int * int frame": (lambda: ints * ints, lambda: wints * wints),
+        "int - float frame": (lambda: df[["i"]] - df[["x"]].rename(**as_i), lambda: pdf[["i"]] - pdf[["x"]].rename(**as_i)),
+        "int == int scalar": (lambda: ints == 3, lambda: wints == 3),
+        "int > int frame": (lambda: df[["i"]] > df[["j"]].rename(**as_i), lambda: pdf[["i"]] > pdf[["j"]].rename(**as_i)),
+        "float > int scalar": (lambda: df[["x"]] > 0, lambda: pdf[["x"]] > 0),
+        "int isna": (lambda: ints.isna(), lambda: wints.isna()),
+        "int fillna": (lambda: ints.fillna(0), lambda: wints.fillna(0)),
+        "int round": (lambda: ints.round(1), lambda: wints.round(1)),
+        "int clip": (lambda: ints.clip(-10, 10), lambda: wints.clip(-10, 10)),
+        "int isin": (lambda: ints.isin([1, 2, 3]), lambda: wints.isin([1, 2, 3])),
+        "sort by int": (lambda: df.sort_values("i"), lambda: pdf.sort_values("i", kind="stable")),
+        "sort by int, descending": (lambda: df.sort_values("i", ascending=False),
+                                    lambda: pdf.sort_values("i", ascending=False, kind="stable")),
+        "mixed frame": (lambda: mixed, lambda: wmixed),
+        "mixed * int scalar": (lambda: mixed * 2, lambda: wmixed * 2),
+        "mixed * float scalar": (lambda: mixed * 2.0, lambda: wmixed * 2.0),
+        "mixed round": (lambda: mixed.round(1), lambda: wmixed.round(1)),
+        "mixed abs": (lambda: mixed.abs(), lambda: wmixed.abs()),
+        "mixed dropna": (lambda: mixed.dropna(), lambda: wmixed.dropna()),
+        "mixed fillna": (lambda: mixed.fillna(0.5), lambda: wmixed.fillna(0.5)),
+        "bool frame": (lambda: bools, lambda: wbools),
+        "bool and": (lambda: df[["b"]] & df[["c"]].rename(**as_i), lambda: pdf[["b"]] & pdf[["c"]].rename(**as_i)),
+        "bool not": (lambda: ~bools, lambda: ~wbools),
+        "bool -> int64": (lambda: bools.astype("int64"), lambda: wbools.astype("int64")),
+        "bool -> float64": (lambda: bools.astype("float64"), lambda: wbools.astype("float64")),
+        "rows where a bool column holds": (lambda: df[["key", "i", "x"]][df["b"]], lambda: pdf[["key", "i", "x"]][pdf["b"]]),
+        "rows where a float column is positive": (lambda: df[["key", "i", "j", "x"]][df["x"] > 0],
+                                                  lambda: pdf[["key", "i", "j", "x"]][pdf["x"] > 0]),
+        "groupby count of ints": (lambda: df[["key", "i"]].groupby("key").count(), lambda: pdf[["key", "i"]].groupby("key").count()),
+        "groupby mean of ints": (lambda: df[["key", "i"]].groupby("key").mean(), lambda: pdf[["key", "i"]].groupby("key").mean()),
+        "groupby mean, mixed": (lambda: df[["key", "i", "x"]].groupby("key").mean(), lambda: pdf[["key", "i", "x"]].groupby("key").mean()),
+        "head of all dtypes": (lambda: df.head(9), lambda: pdf.head(9)),
+    }  # fmt: skip
+    for red in ("sum", "mean", "min", "max", "count", "var", "std"):
+        cases[f"int {red}"] = ((lambda r=red: getattr(ints, r)()), (lambda r=red: getattr(wints, r)()))
+    for red in ("sum", "mean", "min", "var"):
+        cases[f"mixed {red}"] = ((lambda r=red: getattr(mixed, r)()), (lambda r=red: getattr(wmixed, r)()))
+    for red in ("sum", "mean", "any", "all", "count", "var"):
+        cases[f"bool {red}"] = ((lambda r=red: getattr(bools, r)()), (lambda r=red: getattr(wbools, r)()))
+    cases["int prod"] = (lambda: ints.head(5).prod(), lambda: wints.head(5).prod())
+    _compare(cases, check_dtypes=True)
+    for refused in (
+        lambda: bools.min(),  # any / all / sum cover bool columns
+        lambda: df[["key", "i"]].groupby("key").sum()._to_pandas(),  # group tables accumulate float64 values
+        lambda: df[["key", "i"]].groupby("key").min()._to_pandas(),
+        lambda: (df[["i"]] > 0.5)._to_pandas(),  # int64 column against a float scalar would need a float compare
+    ):
+        with pytest.raises(NotImplementedError):
+            refused()
+    with pytest.raises(NotImplementedError, match="groupby.min"):
+        df[["key", "i"]].groupby("key").min()._to_pandas()
 
 
 def test_wide_frames_use_the_2d_grid_everywhere(frames):
