@@ -268,15 +268,15 @@ class DevBinary(DevFn):
         kop = _BINARY_TO_SCALAR[self.op]
         is_pred = kop in _lib.PREDICATES
         any_float = any(isinstance(s, (float, np.floating)) for s in scalars)
-        cols = self._promote(block.cols, any_float and not is_pred) if not is_pred else list(block.cols)
-        out = [None] * len(cols)
+        if is_pred:
+            # an int64 column against a FLOAT scalar is compared in float64, as numpy / pandas do (the column is
+            # converted, rounding included above 2**53); int against int stays an exact integer compare
+            cols = [ops.cast_columns_f64([c])[0] if c.dtype == np.int64 and isinstance(s, (float, np.floating)) else c
+                    for c, s in zip(block.cols, scalars)]  # fmt: skip
+        else:
+            cols = self._promote(block.cols, any_float)
         # group by dtype handled inside map_columns; scalars must match the column dtype
-        svals = []
-        for c, s in zip(cols, scalars):
-            if c.dtype == np.int64 and isinstance(s, (float, np.floating)):
-                # predicate of int column vs float scalar: compare in float64
-                raise NotImplementedError("comparison of int64 columns with a float scalar is not on the B200 path")
-            svals.append(float(s) if c.dtype == np.float64 else int(s))
+        svals = [float(s) if c.dtype == np.float64 else int(s) for c, s in zip(cols, scalars)]
         out = ops.map_columns(kop, cols, s0=svals)
         return block.with_cols(out)
 

@@ -186,12 +186,23 @@ def test_int64_bool_and_mixed_value_columns(cpu_device):
     for red in ("sum", "mean", "any", "all", "count", "var"):
         cases[f"bool {red}"] = ((lambda r=red: getattr(bools, r)()), (lambda r=red: getattr(wbools, r)()))
     cases["int prod"] = (lambda: ints.head(5).prod(), lambda: wints.head(5).prod())
+    # an int64 column against a FLOAT scalar is compared in float64 like numpy / pandas do -- including the rounding
+    # of the converted column above 2**53, where exact integer arithmetic would answer differently
+    for opname in ("gt", "ge", "lt", "le", "eq", "ne"):
+        for s in (0.5, -3.0, 7.0, float("nan"), float("inf")):
+            cases[f"int {opname} {s}"] = ((lambda o=opname, v=s: getattr(ints, o)(v)), (lambda o=opname, v=s: getattr(wints, o)(v)))
+    edge = pandas.DataFrame({"e": np.array([2**53 - 1, 2**53, 2**53 + 1, 2**53 + 2, -(2**53) - 1, 0], dtype=np.int64)})
+    dedge = bpd.DataFrame(edge)
+    for opname in ("gt", "ge", "lt", "le", "eq", "ne"):
+        for s in (float(2**53), float(-(2**53)), 9007199254740993.0):
+            cases[f"2**53 edge {opname} {s}"] = ((lambda o=opname, v=s: getattr(dedge, o)(v)), (lambda o=opname, v=s: getattr(edge, o)(v)))
+    assert bool((edge["e"] > float(2**53)).iloc[2]) is False  # pandas: 2**53 + 1 rounds to 2**53; exact math says True
+    cases["filter by int > float"] = (lambda: df[["key", "i"]][df["i"] > 0.5], lambda: pdf[["key", "i"]][pdf["i"] > 0.5])
     _compare(cases, check_dtypes=True)
     for refused in (
         lambda: bools.min(),  # any / all / sum cover bool columns
         lambda: df[["key", "i"]].groupby("key").sum()._to_pandas(),  # group tables accumulate float64 values
         lambda: df[["key", "i"]].groupby("key").min()._to_pandas(),
-        lambda: (df[["i"]] > 0.5)._to_pandas(),  # int64 column against a float scalar would need a float compare
     ):
         with pytest.raises(NotImplementedError):
             refused()
