@@ -188,6 +188,87 @@ def _late_scenarios(mpd, ns):
         P(mdf[fcols].cumsum())
 
 
+def test_odd_shapes_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
+    """Wide frames (two column partitions), empty results, frames whose labels are device index columns (filter /
+    groupby results) through real ``modin.pandas`` with the plug-in: values, row labels, column labels vs pandas."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: host-logic sweep, runs on the double only")
+    ns, mpd = modin_b200_execution
+    rng = np.random.RandomState(7)
+    W = 40
+    fcols = [f"w{i}" for i in range(W)]
+    wide = pandas.DataFrame(rng.randn(300, W), columns=fcols)
+    wide.iloc[::17, 3] = np.nan
+    wide.iloc[::29, 35] = np.nan
+    wide.insert(0, "key", rng.randint(0, 7, 300).astype(np.int64))
+    pa = synth.host_frame(1003, 3, seed=1, nan_per_64k=3000, key_modulus=11)
+    dim = pandas.DataFrame({"key": rng.permutation(11)[:9].astype(np.int64), "d0": rng.randn(9)})
+    dw, a, dd = mpd.DataFrame(wide), mpd.DataFrame(pa), mpd.DataFrame(dim)
+    assert dw._query_compiler._modin_frame._partitions.shape[1] == 2
+    f = ["c0", "c1", "c2"]
+    emp, wemp = a[a["c0"] > 100.0], pa[pa["c0"] > 100.0]
+    fl, wfl = a[a["c0"] > 0.0], pa[pa["c0"] > 0.0]
+    g, wg = a.groupby("key").sum(), pa.groupby("key").sum()
+    cases = {
+        "wide": (lambda: dw, lambda: wide),
+        "wide filter": (lambda: dw[dw["w0"] > 0.0], lambda: wide[wide["w0"] > 0.0]),
+        "wide dropna": (lambda: dw.dropna(), lambda: wide.dropna()),
+        "wide astype": (lambda: dw.astype({"key": "float64"}), lambda: wide.astype({"key": "float64"})),
+        "wide sum": (lambda: dw[fcols].sum(), lambda: wide[fcols].sum()),
+        "wide a*b+c": (lambda: dw[fcols] * dw[fcols] + dw[fcols], lambda: wide[fcols] * wide[fcols] + wide[fcols]),
+        "wide comparison": (lambda: dw[fcols] < 0.0, lambda: wide[fcols] < 0.0),
+        "wide groupby": (lambda: dw.groupby("key").sum(), lambda: wide.groupby("key").sum()),
+        "wide merge": (lambda: dw.merge(dd, on="key", how="left"), lambda: wide.merge(dim, on="key", how="left")),
+        "wide concat": (lambda: mpd.concat([dw, dw]), lambda: pandas.concat([wide, wide])),
+        "wide head": (lambda: dw.head(77), lambda: wide.head(77)),
+        "wide assign": (lambda: dw.assign(z=dw["w1"] * 2.0), lambda: wide.assign(z=wide["w1"] * 2.0)),
+        "wide isin": (lambda: dw[["key"]].isin([1, 2]), lambda: wide[["key"]].isin([1, 2])),
+        "empty": (lambda: emp, lambda: wemp),
+        "empty abs": (lambda: emp[f].abs(), lambda: wemp[f].abs()),
+        "empty drop_duplicates": (lambda: emp.drop_duplicates(subset=["key"]), lambda: wemp.drop_duplicates(subset=["key"])),
+        "empty astype": (lambda: emp.astype({"key": "float64"}), lambda: wemp.astype({"key": "float64"})),
+        "concat with an empty frame": (lambda: mpd.concat([a, emp]), lambda: pandas.concat([pa, wemp])),
+        "filter twice": (lambda: fl[fl["c1"] > 0.0], lambda: wfl[wfl["c1"] > 0.0]),
+        "filter -> sum": (lambda: fl[f].sum(), lambda: wfl[f].sum()),
+        "filter -> groupby": (lambda: fl.groupby("key").mean(), lambda: wfl.groupby("key").mean()),
+        "filter -> merge": (lambda: fl.merge(dd, on="key", how="inner"), lambda: wfl.merge(dim, on="key", how="inner")),
+        "filter -> square": (lambda: fl[["c0"]] * fl[["c0"]], lambda: wfl[["c0"]] * wfl[["c0"]]),
+        "filter -> assign": (lambda: fl.assign(z=fl["c0"] + 1.0), lambda: wfl.assign(z=wfl["c0"] + 1.0)),
+        "filter -> drop_duplicates": (lambda: fl.drop_duplicates(subset=["key"], keep="last"),
+                                      lambda: wfl.drop_duplicates(subset=["key"], keep="last")),
+        "filter -> head": (lambda: fl.head(13), lambda: wfl.head(13)),
+        "filter -> tail": (lambda: fl.tail(13), lambda: wfl.tail(13)),
+        "filter -> dropna": (lambda: fl.dropna(), lambda: wfl.dropna()),
+        "concat of filtered and plain": (lambda: mpd.concat([fl, a]), lambda: pandas.concat([wfl, pa])),
+        "group table * 2": (lambda: g * 2.0, lambda: wg * 2.0),
+        "group table filter": (lambda: g[g["c0"] > 0.0], lambda: wg[wg["c0"] > 0.0]),
+        "group table sum": (lambda: g.sum(), lambda: wg.sum()),
+        "group table + itself": (lambda: g + g, lambda: wg + wg),
+        "group table head": (lambda: g.head(3), lambda: wg.head(3)),
+        "int column > float scalar": (lambda: a[a["key"] > 4.5], lambda: pa[pa["key"] > 4.5]),
+        "tail": (lambda: a.tail(9), lambda: pa.tail(9)),
+    }  # fmt: skip
+    bad = {}
+    for name, (dev, host) in cases.items():
+        got, want = dev()._to_pandas(), host()
+        ok = (list(got.index) == list(want.index) and (not hasattr(want, "columns") or list(got.columns) == list(want.columns))
+              and got.shape == want.shape
+              and np.allclose(np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64), rtol=1e-12, atol=1e-9, equal_nan=True))  # fmt: skip
+        if not ok:
+            bad[name] = (got.shape, want.shape, list(got.index)[:3], list(want.index)[:3])
+    assert not bad, bad
+    for refused in (lambda: dw.drop_duplicates(subset=["key"]), lambda: dw[fcols].var()):  # need one column partition
+        with pytest.raises(NotImplementedError, match="one column partition"):
+            refused()
+    # NOT covered, and not this package's doing: reductions / filters / groupby of an EMPTY frame make Modin's API
+    # layer default to pandas, and that path builds ``pandas.Series(..., fastpath=...)`` (modin/pandas/series.py:166),
+    # a keyword pandas 3 removed (the reference pins pandas < 2.4)
+    with pytest.raises(TypeError, match="fastpath"):
+        emp[f].sum()
+
+
 def test_late_additions_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
     import torch
 
