@@ -480,6 +480,37 @@ class DevRowFilter(DevFn):
         return DeviceBlock(cols, block.columns, nrows=k, index_cols=[labels], index_names=names)
 
 
+class DevSortRows(DevFn):
+    """``df.sort_values(by=one column)`` on one block holding all the rows -- the block-function form of
+    ``B200Dataframe.sort_by`` for callers that apply functions to full-axis partitions (the Modin plug-in's
+    ``qc.sort_rows_by_column_values``).  Nothing is re-implemented: the block is wrapped in a one-partition frame and
+    handed to ``sort_by`` (order-preserving key image, stable LSD radix sort of (image, row id), one gather)."""
+
+    op = "sort_rows"
+
+    @staticmethod
+    def resolve(columns: pandas.Index, by, ascending=True, **kwargs):
+        """(key position, ascending) after the argument checks both query compilers share."""
+        cols = [by] if not isinstance(by, (list, tuple)) else list(by)
+        asc = ascending[0] if isinstance(ascending, (list, tuple)) else ascending
+        if len(cols) != 1:
+            raise NotImplementedError("device sort_values sorts by one column")
+        if kwargs.get("na_position", "last") != "last":
+            raise NotImplementedError("sort_values(na_position='first') is not on the B200 path")
+        if kwargs.get("key") is not None:
+            raise NotImplementedError("sort_values(key=) is not on the B200 path")
+        if cols[0] not in columns:
+            raise KeyError(cols[0])
+        return int(columns.get_loc(cols[0])), bool(asc)
+
+    def __call__(self, block, key_position=0, ascending=True, ignore_index=False, **kwargs):
+        from .dataframe import B200Dataframe
+
+        _check_block(block, "DevSortRows")
+        frame = B200Dataframe.from_blocks([block])
+        return frame.sort_by(int(key_position), bool(ascending), bool(ignore_index))._partitions[0, 0].get()
+
+
 class DevDropDuplicates(DevFn):
     """``df.drop_duplicates(subset=[one int64 column], keep="first" | "last")`` on one block holding all the rows.
     The reference (modin/pandas/base.py:1600-1623 -> qc.unique, qc.py:2231-2270 -> BaseQueryCompiler.unique,

@@ -257,6 +257,23 @@ def register(shims: bool | None = None):
             )  # fmt: skip
             return self.__constructor__(new_frame, shape_hint=self._shape_hint)
 
+        def sort_rows_by_column_values(self, columns, ascending=True, **kwargs):
+            """qc.py ``sort_rows_by_column_values`` -> PandasDataframe.sort_by (df.py:2741-2791), a range-partitioning
+            shuffle that samples the blocks with pandas code.  Here one full-axis application of the device sort
+            (stable, NaN last; one float64 / int64 key column)."""
+            pos, asc = fx.DevSortRows.resolve(self.columns, columns, ascending, **kwargs)
+            frame = self._modin_frame
+            if frame._partitions.shape[1] != 1:
+                raise NotImplementedError("device sort_values: frames of one column partition (up to 32 columns)")
+            if bdist.is_distributed():
+                raise NotImplementedError("sort_values through the Modin plug-in is single-process")
+            fn, ignore = fx.DevSortRows(), bool(kwargs.get("ignore_index", False))
+            new_frame = frame.apply_full_axis(
+                0, lambda blk: fn(blk, pos, asc, ignore), new_columns=self.columns, dtypes="copy",
+                keep_partitioning=True, num_splits=1, sync_labels=False,
+            )  # fmt: skip
+            return self.__constructor__(new_frame)
+
         def nunique(self, axis=0, dropna=True):
             """qc.py:1109-1113 is a full-axis ``pandas.DataFrame.nunique``; here one group table per int64 column,
             the answer is its number of groups.  The W counts go back as a 1 x W frame like the other reductions."""

@@ -106,18 +106,10 @@ class B200QueryCompiler:
         """qc.py ``sort_rows_by_column_values`` -> ``PandasDataframe.sort_by`` (df.py:2741-2791): one float64 / int64
         key column, NaN last, ties in original row order (pandas ``kind="stable"``; the default quicksort leaves
         tie order unspecified, so a stable result is a valid answer for every ``kind``)."""
-        cols = [columns] if not isinstance(columns, (list, tuple)) else list(columns)
-        asc = ascending[0] if isinstance(ascending, (list, tuple)) else ascending
-        if len(cols) != 1:
-            raise NotImplementedError("device sort_values sorts by one column")
-        if kwargs.get("na_position", "last") != "last":
-            raise NotImplementedError("sort_values(na_position='first') is not on the B200 path")
-        if kwargs.get("key") is not None:
-            raise NotImplementedError("sort_values(key=) is not on the B200 path")
-        if cols[0] not in self.columns:
-            raise KeyError(cols[0])
-        pos = int(self.columns.get_loc(cols[0]))
-        return self.__constructor__(self._modin_frame.sort_by(pos, bool(asc), bool(kwargs.get("ignore_index", False))))
+        from .functors import DevSortRows
+
+        pos, asc = DevSortRows.resolve(self.columns, columns, ascending, **kwargs)
+        return self.__constructor__(self._modin_frame.sort_by(pos, asc, bool(kwargs.get("ignore_index", False))))
 
     def drop_duplicates(self, subset=None, keep="first", ignore_index=False):
         """What ``BasePandasDataset.drop_duplicates`` (modin/pandas/base.py:1600-1623) asks of the query compiler --

@@ -182,6 +182,19 @@ def _late_scenarios(mpd, ns):
     assert np.allclose(P(mdf[fcols].std()).to_numpy(), pdf[fcols].std().to_numpy(), rtol=1e-12, atol=0)
     with pytest.raises(NotImplementedError):
         mdf[fcols].var(axis=1)
+    # sort_values: stable, NaN last (the reference's own range-partitioning sort returns an empty frame under pandas 3)
+    for by, asc in (("c0", True), ("c0", False), ("key", True), ("k2", False)):
+        assert P(mdf.sort_values(by, ascending=asc)).equals(pdf.sort_values(by, ascending=asc, kind="stable")), (by, asc)
+    assert P(mdf.sort_values("c1", ignore_index=True)).equals(pdf.sort_values("c1", kind="stable", ignore_index=True))
+    sel, wsel = mdf[mdf["c0"] > 0.0], pdf[pdf["c0"] > 0.0]
+    assert P(sel.sort_values("c2")).equals(wsel.sort_values("c2", kind="stable"))  # labels ride along as a device column
+    assert P(mdf.sort_values("c0").head(10)).equals(pdf.sort_values("c0", kind="stable").head(10))
+    with pytest.raises(NotImplementedError):
+        mdf.sort_values(["c0", "c1"])
+    with pytest.raises(NotImplementedError):
+        mdf.sort_values("c0", na_position="first")
+    with pytest.raises(KeyError):
+        mdf.sort_values("nope")
     # a query-compiler method the plug-in does not override reaches the blocks with Modin's pandas lambda: refused
     # with a message that says so (it used to be a bare AttributeError on the block)
     with pytest.raises(NotImplementedError, match="no device implementation"):
