@@ -761,8 +761,26 @@ def gather_block(block: DeviceBlock) -> DeviceBlock:
     """All-gather the row shards of a block so that every rank holds all rows."""
     from .block import DeviceColumn
 
+    t = torch_mod()
     tensors = [c.data for c in block.cols]
-    icols = block.index_cols or []
+    icols = list(block.index_cols or [])
+    dev = tensors[0].device if tensors else ("cuda" if dist._dist().get_backend() == "nccl" else "cpu")
+    # The ranks first agree on the label layout, in ONE small collective that every rank issues whatever its shard
+    # looks like: the layouts can differ (a row filter gives the ranks that had rows a device label column while a
+    # rank whose shard was already empty keeps its range), and ranks that then gathered different tensor lists -- or
+    # one rank raising while the others wait -- would deadlock.
+    label_is_float = int(bool(icols) and icols[0].dtype == np.float64)
+    meta = dist.all_gather_small(t.tensor([len(icols), int(block.index_host is not None), block.range_start, block.nrows,
+                                           label_is_float], dtype=t.int64, device=dev))  # fmt: skip
+    if any(m[1] for m in meta):  # on every rank, not just the one that holds them
+        raise NotImplementedError("gathering row shards with host-resident (non-numeric) row labels is not on the B200 path")
+    nlabel = max(int(m[0]) for m in meta)
+    if nlabel > 1 and len(icols) != nlabel:
+        raise NotImplementedError("gathering row shards whose label levels differ between ranks is not on the B200 path")
+    if nlabel == 1 and not icols:  # explicit labels elsewhere: this rank's range becomes explicit too, in their dtype
+        as_float = any(m[0] and m[4] for m in meta)
+        ldt, ndt = (t.float64, np.float64) if as_float else (t.int64, np.int64)
+        icols = [DeviceColumn(t.arange(block.range_start, block.range_start + block.nrows, dtype=ldt, device=dev), ndt)]
     tensors += [c.data for c in icols]
     gathered = dist.all_gather_rows(tensors)
     ncol = len(block.cols)
@@ -770,16 +788,11 @@ def gather_block(block: DeviceBlock) -> DeviceBlock:
     nrows = int(gathered[0].shape[0]) if gathered else 0
     if icols:
         ic = [DeviceColumn(g, c.dtype) for g, c in zip(gathered[ncol:], icols)]
-        out = DeviceBlock(cols, block.columns, nrows=nrows, index_cols=ic, index_names=block.index_names)
+        out = DeviceBlock(cols, block.columns, nrows=nrows, index_cols=ic, index_names=block.index_names or [None] * len(ic))
     else:
-        if block.index_host is not None:
-            raise NotImplementedError("gathering row shards with host-resident (non-numeric) row labels is not on the B200 path")
         # every shard is a run of a RangeIndex, but not necessarily of 0..N: tail() / a shifted RangeIndex start
         # later, and slices taken shard by shard need not run on from each other
-        t = torch_mod()
-        dev = tensors[0].device if tensors else ("cuda" if dist._dist().get_backend() == "nccl" else "cpu")
-        spans = dist.all_gather_small(t.tensor([block.range_start, block.nrows], dtype=t.int64, device=dev))
-        spans = [(int(s), int(n)) for s, n in spans if n > 0]
+        spans = [(int(m[2]), int(m[3])) for m in meta if m[3] > 0]
         if all(b[0] == a[0] + a[1] for a, b in zip(spans, spans[1:])):  # one job-wide range: labels stay O(1)
             out = DeviceBlock(cols, block.columns, nrows=nrows, range_start=spans[0][0] if spans else 0)
         else:

@@ -378,6 +378,69 @@ def test_full_stack_api_sweep_across_ranks():
         assert not bad and len(res) >= 26, (r, bad)
 
 
+def _tiny_frames_job(rank, ws):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    res = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        base = synth.host_frame(64, 3, seed=9, nan_per_64k=0, key_modulus=3)
+        dim = pandas.DataFrame({"key": np.array([2, 0, 1], dtype=np.int64), "d0": np.random.RandomState(3).randn(3)})
+        f = ["c0", "c1", "c2"]
+        cases = {
+            "to_pandas": (lambda df: df, lambda p: p),
+            "abs": (lambda df: df[f].abs(), lambda p: p[f].abs()),
+            "affine": (lambda df: df[f] * 2.0 + 1.0, lambda p: p[f] * 2.0 + 1.0),
+            "sum": (lambda df: df[f].sum(), lambda p: p[f].sum()),
+            "mean": (lambda df: df[f].mean(), lambda p: p[f].mean()),
+            "min": (lambda df: df[f].min(), lambda p: p[f].min()),
+            "count": (lambda df: df[f].count(), lambda p: p[f].count()),
+            "var": (lambda df: df[f].var(), lambda p: p[f].var()),
+            "any": (lambda df: (df[f] > 0.0).any(), lambda p: (p[f] > 0.0).any()),
+            "filter": (lambda df: df[df["c0"] > 0.0], lambda p: p[p["c0"] > 0.0]),
+            "filter, nothing passes": (lambda df: df[df["c0"] > 100.0], lambda p: p[p["c0"] > 100.0]),
+            "dropna": (lambda df: df.dropna(), lambda p: p.dropna()),
+            "isin": (lambda df: df[["key"]].isin([1]), lambda p: p[["key"]].isin([1])),
+            "groupby sum": (lambda df: df.groupby("key").sum(), lambda p: p.groupby("key").sum()),
+            "groupby size": (lambda df: df.groupby("key").size(), lambda p: p.groupby("key").size()),
+            "merge left": (lambda df: df.merge(bpd.DataFrame(dim), on="key", how="left"), lambda p: p.merge(dim, on="key", how="left")),
+            "merge inner": (lambda df: df.merge(bpd.DataFrame(dim), on="key", how="inner"), lambda p: p.merge(dim, on="key", how="inner")),
+            "sort": (lambda df: df.sort_values("c0"), lambda p: p.sort_values("c0", kind="stable")),
+            "head": (lambda df: df.head(1), lambda p: p.head(1)),
+            "tail": (lambda df: df.tail(3), lambda p: p.tail(3)),
+            "head -> filter": (lambda df: (lambda h: h[h["c0"] > 0.0])(df.head(2)), lambda p: (lambda h: h[h["c0"] > 0.0])(p.head(2))),
+            "astype": (lambda df: df.astype({"key": "float64"}), lambda p: p.astype({"key": "float64"})),
+            "nunique": (lambda df: df[["key"]].nunique(), lambda p: p[["key"]].nunique()),
+        }  # fmt: skip
+        for n in (0, 1, 2, 5):  # fewer rows than ranks: some shards are empty from the start
+            pdf = base.head(n)
+            for name, (dev, host) in cases.items():
+                want = host(pdf)
+                g = dev(bpd.DataFrame(pdf))
+                g = g._to_pandas() if hasattr(g, "_to_pandas") else g
+                labels_ok = list(g.index) == list(want.index)
+                vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
+                                                                rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
+                res[f"n={n} {name}"] = "ok" if labels_ok and vals_ok else f"values {vals_ok}, labels {labels_ok}, shape {g.shape} vs {want.shape}"
+    return res
+
+
+@pytest.mark.timeout(300)
+def test_tiny_frames_leave_some_ranks_empty():
+    """0 / 1 / 2 / 5 rows over THREE ranks.  A rank whose shard is empty from the start used to keep range labels
+    through a row filter while the ranks with rows got a device label column; the gather then issued different
+    collectives on different ranks and hung.  The ranks now agree on the label layout first (``gather_block``)."""
+    out = _run(_tiny_frames_job, ws=3)
+    for r, res in enumerate(out):
+        bad = {k: s for k, s in res.items() if s != "ok"}
+        assert not bad and len(res) == 4 * 23, (r, bad)
+
+
 def _full_stack_sort_job(rank, ws):
     import sys
 
