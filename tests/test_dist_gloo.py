@@ -441,6 +441,80 @@ def test_tiny_frames_leave_some_ranks_empty():
         assert not bad and len(res) == 4 * 23, (r, bad)
 
 
+def _wide_and_labelled_job(rank, ws):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    res = {}
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        rng = np.random.RandomState(7)
+        fcols = [f"w{i}" for i in range(40)]
+        wide = pandas.DataFrame(rng.randn(301, 40), columns=fcols)  # two column partitions on every rank
+        wide.iloc[::17, 3] = np.nan
+        wide.iloc[::29, 35] = np.nan
+        wide.insert(0, "key", rng.randint(0, 7, 301).astype(np.int64))
+        pa = synth.host_frame(1003, 3, seed=1, nan_per_64k=3000, key_modulus=11)
+        named = pa.set_axis(pandas.Index(np.arange(len(pa))[::-1] * 2, name="rid"), axis=0)
+        fidx = pa.set_axis(pandas.Index(np.linspace(0.0, 1.0, len(pa))), axis=0)
+        dim = pandas.DataFrame({"key": rng.permutation(11)[:9].astype(np.int64), "d0": rng.randn(9)})
+        f = ["c0", "c1", "c2"]
+        mk = bpd.DataFrame
+        cases = {
+            "wide": (lambda: mk(wide), lambda: wide),
+            "wide filter": (lambda: (lambda d: d[d["w0"] > 0.0])(mk(wide)), lambda: wide[wide["w0"] > 0.0]),
+            "wide dropna": (lambda: mk(wide).dropna(), lambda: wide.dropna()),
+            "wide sum": (lambda: mk(wide)[fcols].sum(), lambda: wide[fcols].sum()),
+            "wide var": (lambda: mk(wide)[fcols].var(), lambda: wide[fcols].var()),
+            "wide a*b+c": (lambda: (lambda d: d[fcols] * d[fcols] + d[fcols])(mk(wide)), lambda: wide[fcols] * wide[fcols] + wide[fcols]),
+            "wide groupby": (lambda: mk(wide).groupby("key").sum(), lambda: wide.groupby("key").sum()),
+            "wide merge": (lambda: mk(wide).merge(mk(dim), on="key", how="left"), lambda: wide.merge(dim, on="key", how="left")),
+            "wide sort": (lambda: mk(wide).sort_values("w5"), lambda: wide.sort_values("w5", kind="stable")),
+            "wide head": (lambda: mk(wide).head(200), lambda: wide.head(200)),
+            "wide tail": (lambda: mk(wide).tail(200), lambda: wide.tail(200)),
+            "wide astype": (lambda: mk(wide).astype({"key": "float64"}), lambda: wide.astype({"key": "float64"})),
+            "wide assign": (lambda: (lambda d: d.assign(z=d["w1"] * 2.0))(mk(wide)), lambda: wide.assign(z=wide["w1"] * 2.0)),
+            "wide concat columns": (lambda: (lambda d: bpd.concat([d, d[["w0"]].rename(columns={"w0": "zz"})], axis=1))(mk(wide)),
+                                    lambda: pandas.concat([wide, wide[["w0"]].rename(columns={"w0": "zz"})], axis=1)),
+            "named index": (lambda: mk(named), lambda: named),
+            "named index filter": (lambda: (lambda d: d[d["c0"] > 0.0])(mk(named)), lambda: named[named["c0"] > 0.0]),
+            "named index sort": (lambda: mk(named).sort_values("c0"), lambda: named.sort_values("c0", kind="stable")),
+            "named index head": (lambda: mk(named).head(600), lambda: named.head(600)),
+            "named index tail": (lambda: mk(named).tail(600), lambda: named.tail(600)),
+            "named index groupby": (lambda: mk(named).groupby("key").sum(), lambda: named.groupby("key").sum()),
+            "named index * 2": (lambda: mk(named)[f] * 2.0, lambda: named[f] * 2.0),
+            "named index merge": (lambda: mk(named).merge(mk(dim), on="key", how="left"), lambda: named.merge(dim, on="key", how="left")),
+            "float index": (lambda: mk(fidx), lambda: fidx),
+            "float index filter": (lambda: (lambda d: d[d["c0"] > 0.0])(mk(fidx)), lambda: fidx[fidx["c0"] > 0.0]),
+            "float index tail": (lambda: mk(fidx).tail(600), lambda: fidx.tail(600)),
+            "float index sort": (lambda: mk(fidx).sort_values("c1"), lambda: fidx.sort_values("c1", kind="stable")),
+            "float index head -> filter": (lambda: (lambda h: h[h["c0"] > 0.0])(mk(fidx).head(100)),
+                                           lambda: (lambda h: h[h["c0"] > 0.0])(fidx.head(100))),
+        }  # fmt: skip
+        for name, (dev, host) in cases.items():
+            g, want = dev(), host()
+            g = g._to_pandas() if hasattr(g, "_to_pandas") else g
+            labels_ok = list(g.index) == list(want.index) and g.index.name == want.index.name
+            cols_ok = not hasattr(want, "columns") or list(g.columns) == list(want.columns)
+            vals_ok = g.shape == want.shape and np.allclose(np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64),
+                                                            rtol=1e-12, atol=1e-9, equal_nan=True)  # fmt: skip
+            res[name] = "ok" if labels_ok and cols_ok and vals_ok else f"values {vals_ok}, labels {labels_ok}, columns {cols_ok}"
+    return res
+
+
+@pytest.mark.timeout(300)
+def test_wide_and_labelled_frames_across_ranks():
+    """Two column partitions per rank, and inputs with a named int index / a float index, sharded over 2 ranks."""
+    out = _run(_wide_and_labelled_job)
+    for r, res in enumerate(out):
+        bad = {k: s for k, s in res.items() if s != "ok"}
+        assert not bad and len(res) == 27, (r, bad)
+
+
 def _full_stack_sort_job(rank, ws):
     import sys
 
