@@ -119,6 +119,16 @@ class Binary(Operator):
                 other = pandas.Series(other)
             if len(query_compiler.columns) == 1 and np.isscalar(other):
                 shape_hint = "column"
+            if (isinstance(other, (list, tuple, np.ndarray)) and axis not in (0, "index")
+                    and query_compiler._modin_frame._partitions.shape[1] > 1):  # fmt: skip
+                # a positional row vector over SEVERAL column partitions: the reference applies it full-axis so that
+                # every call sees whole rows (binary.py:431-442, whose TODO proposes chunking `other` instead); here it
+                # is labelled with the frame's columns and each block takes its slice by label, as for a Series.  One
+                # column partition keeps the list (fusable).
+                W = len(query_compiler.columns)
+                if len(other) != W:
+                    raise ValueError(f"Unable to coerce to Series, length must be {W}: given {len(other)}")
+                other = pandas.Series(list(other), index=query_compiler.columns)
             # scalar / list / Series operand: lazy map (binary.py:449-455) -> lands in the call queue
             new_modin_frame = query_compiler._modin_frame.map(
                 func, func_args=(other, *args), func_kwargs=kwargs, dtypes=dtypes, lazy=True

@@ -291,3 +291,85 @@ def test_frames_whose_labels_are_not_a_plain_range(frames):
     })  # fmt: skip
     with pytest.raises(NotImplementedError, match="numeric / range row labels"):
         ds[ds["c0"] > 0.0]._to_pandas()  # string labels cannot ride through the device compaction: refused, not dropped
+
+
+def test_binary_template_operand_shapes_are_bit_exact(cpu_device):
+    """The Binary template's operand shapes -- scalars on either side, positional and labelled row vectors, a column
+    Series along axis 0, co-partitioned frames, fused x*s+t chains -- on plain, wide (two column partitions), filtered
+    and int64 frames: values bit for bit, labels and dtypes as pandas.  Found with this sweep and fixed: a positional
+    row vector (list) on a frame with several column partitions reached every partition whole."""
+    import modin_b200.pandas as bpd
+
+    rng = np.random.RandomState(5)
+    pa = synth.host_frame(1003, 3, seed=1, nan_per_64k=3000, key_modulus=11)
+    f = ["c0", "c1", "c2"]
+    v, dv = pa[f], bpd.DataFrame(pa)[f]
+    other = synth.host_frame(1003, 3, seed=2, nan_per_64k=2000, key_modulus=11)[f]
+    do = bpd.DataFrame(other)
+    W = 40
+    fc = [f"w{i}" for i in range(W)]
+    wide = pandas.DataFrame(rng.randn(200, W), columns=fc); wide.iloc[::13, 33] = np.nan
+    dw = bpd.DataFrame(wide)
+    ints = pandas.DataFrame({"i": rng.randint(-50, 50, 300).astype(np.int64), "j": rng.randint(1, 9, 300).astype(np.int64)})
+    di = bpd.DataFrame(ints)
+    fl, dfl = v[v["c0"] > 0.0], dv[dv["c0"] > 0.0]
+    row3 = [0.5, -1.0, 2.0]; srow = pandas.Series(row3, index=f)
+    roww = list(np.linspace(-1, 1, W)); sroww = pandas.Series(roww, index=fc)
+    cases = {
+        "2 - df": (lambda: 2.0 - dv, lambda: 2.0 - v), "1 / df": (lambda: 1.0 / dv, lambda: 1.0 / v),
+        "2 + df": (lambda: 2.0 + dv, lambda: 2.0 + v), "3 * df": (lambda: 3 * dv, lambda: 3 * v),
+        "df - 2": (lambda: dv - 2, lambda: v - 2), "df / 4": (lambda: dv / 4, lambda: v / 4),
+        "df.rsub(1)": (lambda: dv.rsub(1.0), lambda: v.rsub(1.0)), "df.rtruediv(2)": (lambda: dv.rtruediv(2.0), lambda: v.rtruediv(2.0)),
+        "df + list": (lambda: dv + row3, lambda: v + row3), "df * Series": (lambda: dv * bpd.Series(srow), lambda: v * srow),
+        "df * pandas Series": (lambda: dv * srow, lambda: v * srow),
+        "df - list": (lambda: dv - row3, lambda: v - row3), "df / list": (lambda: dv / row3, lambda: v / row3),
+        "df < list": (lambda: dv < row3, lambda: v < row3),
+        "df.mul(col, 0)": (lambda: dv.mul(dv["c1"], axis=0), lambda: v.mul(v["c1"], axis=0)),
+        "df.sub(col, 0)": (lambda: dv.sub(dv["c1"], axis=0), lambda: v.sub(v["c1"], axis=0)),
+        "df.rsub(col, 0)": (lambda: dv.rsub(dv["c1"], axis=0), lambda: v.rsub(v["c1"], axis=0)),
+        "df.truediv(col, 0)": (lambda: dv.truediv(dv["c1"], axis=0), lambda: v.truediv(v["c1"], axis=0)),
+        "df.add(col, 0)": (lambda: dv.add(dv["c1"], axis=0), lambda: v.add(v["c1"], axis=0)),
+        "df.lt(col, 0)": (lambda: dv.lt(dv["c1"], axis=0), lambda: v.lt(v["c1"], axis=0)),
+        "df - other": (lambda: dv - do, lambda: v - other), "df / other": (lambda: dv / do, lambda: v / other),
+        "other.rsub(df)": (lambda: do.rsub(dv), lambda: other.rsub(v)), "df.rtruediv(other)": (lambda: dv.rtruediv(do), lambda: v.rtruediv(other)),
+        "df >= other": (lambda: dv >= do, lambda: v >= other), "df != other": (lambda: dv != do, lambda: v != other),
+        "a*b+c frames": (lambda: dv * do + do, lambda: v * other + other),
+        "a*s+t": (lambda: dv * 1.5 + 0.25, lambda: v * 1.5 + 0.25), "a*s-t": (lambda: dv * 1.5 - 0.25, lambda: v * 1.5 - 0.25),
+        "(a+s)*t": (lambda: (dv + 1.0) * 2.0, lambda: (v + 1.0) * 2.0), "a*s*t": (lambda: dv * 2.0 * 3.0, lambda: v * 2.0 * 3.0),
+        "a*list+list": (lambda: dv * row3 + row3, lambda: v * row3 + row3),
+        "-(a*2)": (lambda: -(dv * 2.0), lambda: -(v * 2.0)), "abs(a-1)": (lambda: (dv - 1.0).abs(), lambda: (v - 1.0).abs()),
+        "fillna dict": (lambda: dv.fillna({"c0": 1.0, "c2": -1.0}), lambda: v.fillna({"c0": 1.0, "c2": -1.0})),
+        "fillna frame": (lambda: dv.fillna(do), lambda: v.fillna(other)),
+        "fillna then mul": (lambda: dv.fillna(0.0) * 2.0, lambda: v.fillna(0.0) * 2.0),
+        "clip lower": (lambda: dv.clip(lower=0.0), lambda: v.clip(lower=0.0)), "clip upper": (lambda: dv.clip(upper=0.0), lambda: v.clip(upper=0.0)),
+        "round then sum": (lambda: dv.round(1).sum(), lambda: v.round(1).sum()),
+        "wide + list": (lambda: dw + roww, lambda: wide + roww), "wide * Series": (lambda: dw * sroww, lambda: wide * sroww),
+        "wide.mul(col,0)": (lambda: dw.mul(dw["w3"], axis=0), lambda: wide.mul(wide["w3"], axis=0)),
+        "wide a*s+t": (lambda: dw * 1.5 + 0.25, lambda: wide * 1.5 + 0.25), "2 - wide": (lambda: 2.0 - dw, lambda: 2.0 - wide),
+        "wide - wide": (lambda: dw - dw, lambda: wide - wide), "wide fillna": (lambda: dw.fillna(0.5), lambda: wide.fillna(0.5)),
+        "filtered * 2": (lambda: dfl * 2.0, lambda: fl * 2.0), "filtered + list": (lambda: dfl + row3, lambda: fl + row3),
+        "filtered.mul(col,0)": (lambda: dfl.mul(dfl["c1"], axis=0), lambda: fl.mul(fl["c1"], axis=0)),
+        "filtered - filtered": (lambda: dfl - dfl, lambda: fl - fl), "2 - filtered": (lambda: 2.0 - dfl, lambda: 2.0 - fl),
+        "int - 2": (lambda: di - 2, lambda: ints - 2), "2 - int": (lambda: 2 - di, lambda: 2 - ints), "2.5 - int": (lambda: 2.5 - di, lambda: 2.5 - ints),
+        "1 / int": (lambda: 1 / di, lambda: 1 / ints), "int + list": (lambda: di + [1, 2], lambda: ints + [1, 2]),
+        "int * flist": (lambda: di * [0.5, 2.0], lambda: ints * [0.5, 2.0]), "int.mul(col,0)": (lambda: di.mul(di["j"], axis=0), lambda: ints.mul(ints["j"], axis=0)),
+        "int / int col": (lambda: di.truediv(di["j"], axis=0), lambda: ints.truediv(ints["j"], axis=0)),
+        "int*2+1": (lambda: di * 2 + 1, lambda: ints * 2 + 1), "int*2.0+1": (lambda: di * 2.0 + 1, lambda: ints * 2.0 + 1),
+    }
+    bad = {}
+    for name, (dev, host) in cases.items():
+        want = host()
+        g = dev()
+        g = g._to_pandas() if hasattr(g, "_to_pandas") else g
+        gv, wv = np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64)
+        exact = g.shape == want.shape and bool(((gv == wv) | (np.isnan(gv) & np.isnan(wv))).all())
+        if name == "round then sum":  # a reduction: summation order, not bit-exact
+            exact = g.shape == want.shape and np.allclose(gv, wv, rtol=0, atol=1e-9)
+        gd = [str(t) for t in (g.dtypes if hasattr(g, "columns") else [g.dtype])]
+        wd = [str(t) for t in (want.dtypes if hasattr(want, "columns") else [want.dtype])]
+        cols_ok = not hasattr(want, "columns") or list(g.columns) == list(want.columns)
+        if not (exact and list(g.index) == list(want.index) and cols_ok and gd == wd):
+            bad[name] = (exact, gd[:3], wd[:3])
+    assert not bad and len(cases) >= 60, bad
+    with pytest.raises(ValueError, match="length must be 40"):
+        (dw + roww[:-1])._to_pandas()
