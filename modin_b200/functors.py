@@ -876,17 +876,32 @@ class DevSsdMap(DevFn):
     op = "ssd_map"
 
     def __init__(self, centers):
-        self.centers = [float(c) for c in centers]
+        """``centers``: a ``pandas.Series`` of column means indexed by column label (each block picks the centres of
+        ITS columns -- a frame wider than one column partition hands every partition the same functor), or a plain
+        sequence holding one centre per column of the block."""
+        if isinstance(centers, pandas.Series):
+            self.by_label, self.centers = {k: float(v) for k, v in centers.items()}, None
+        else:
+            self.by_label, self.centers = None, [float(c) for c in centers]
+
+    def _centers_for(self, block):
+        if self.by_label is not None:
+            missing = [c for c in block.columns if c not in self.by_label]
+            if missing:
+                raise ValueError(f"var / std: no centre for columns {missing!r}")
+            return [self.by_label[c] for c in block.columns]
+        if len(self.centers) != len(block.cols):
+            raise ValueError("var / std: one centre per column expected")
+        return self.centers
 
     def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, **kwargs):
         _check_block(block, "DevSsdMap")
         if axis not in (0, "index", None):
             raise NotImplementedError("row-wise var / std is not on the B200 path")
-        if len(self.centers) != len(block.cols):
-            raise ValueError("var / std: one centre per column expected")
+        block_centers = self._centers_for(block)
         cols = ops.cast_columns_f64(block.cols)
         t = ops.torch_mod()
-        centers = t.tensor(self.centers, dtype=t.float64).to(cols[0].data.device) if cols else None
+        centers = t.tensor(block_centers, dtype=t.float64).to(cols[0].data.device) if cols else None
         vals, cnts = ops.reduce_columns("ssd", cols, skipna=bool(skipna), variant=ReduceVariant.get(), centers=centers)
         out = [DeviceColumn(v, np.float64) for v in vals] + [DeviceColumn(c, np.int64) for c in cnts]
         labels = pandas.MultiIndex.from_tuples([("ssd", c) for c in block.columns] + [("count", c) for c in block.columns])

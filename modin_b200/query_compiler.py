@@ -250,12 +250,14 @@ class B200QueryCompiler:
         if axis not in (0, "index", None):
             raise NotImplementedError("row-wise var / std is not on the B200 path")
         mean = self.mean(axis=0, skipna=skipna, numeric_only=numeric_only).to_pandas()
-        W = mean.shape[1]
-        parts_qc = TreeReduce.register(DevSsdMap(mean.iloc[0].to_numpy(dtype=np.float64)), DevReduce("sum", phase="reduce"))(
+        # centres by column label: a frame wider than one column partition gives every partition the same functor
+        parts_qc = TreeReduce.register(DevSsdMap(mean.iloc[0].astype(np.float64)), DevReduce("sum", phase="reduce"))(
             self, axis=0, skipna=skipna, numeric_only=numeric_only
         )  # fmt: skip
-        parts = parts_qc.to_pandas().iloc[0].to_numpy(dtype=np.float64)
-        ssd, cnt = parts[:W], parts[W:]
+        # every column partition contributes its own ("ssd", column)... ("count", column)... run: split by label
+        row = parts_qc.to_pandas().iloc[0]
+        ssd = row["ssd"].reindex(mean.columns).to_numpy(dtype=np.float64)
+        cnt = row["count"].reindex(mean.columns).to_numpy(dtype=np.float64)
         with np.errstate(all="ignore"):
             out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
             if sqrt:

@@ -244,6 +244,18 @@ def test_wide_frames_use_the_2d_grid_everywhere(frames):
         "assign": (lambda: dw.assign(z=dw["w1"] * 2.0), lambda: wide.assign(z=wide["w1"] * 2.0)),
         "columns from both partitions": (lambda: dw[["w39", "w2"]], lambda: wide[["w39", "w2"]]),
     })  # fmt: skip
+    # reductions of a frame that IS two column partitions (ingested with 40 columns; selecting 40 columns on the device
+    # can come back as one partition, which is how var / std over two partitions went unnoticed): every partition
+    # gets the same functor, so the second pass of var / std has to find ITS columns' means by label
+    vals = wide[fcols]
+    dv = bpd.DataFrame(vals)
+    assert dv._query_compiler._modin_frame._partitions.shape[1] == 2
+    reductions = {}
+    for name, kw in (("sum", {}), ("sum", {"skipna": False}), ("sum", {"min_count": 1}), ("mean", {}), ("mean", {"skipna": False}),
+                     ("min", {}), ("max", {"skipna": False}), ("count", {}), ("var", {}), ("var", {"ddof": 0}),
+                     ("var", {"skipna": False}), ("std", {}), ("std", {"ddof": 0})):  # fmt: skip
+        reductions[f"{name} {kw}"] = ((lambda n=name, k=kw: getattr(dv, n)(**k)), (lambda n=name, k=kw: getattr(vals, n)(**k)))
+    _compare(reductions, check_dtypes=True)
 
 
 def test_frames_whose_labels_are_not_a_plain_range(frames):
