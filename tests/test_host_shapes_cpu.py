@@ -385,3 +385,50 @@ def test_binary_template_operand_shapes_are_bit_exact(cpu_device):
     assert not bad and len(cases) >= 60, bad
     with pytest.raises(ValueError, match="length must be 40"):
         (dw + roww[:-1])._to_pandas()
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_groupby_aggregations_across_key_kinds_and_shapes(cpu_device, dense):
+    """Every aggregation x (40 value columns, narrow, keys with gaps, one group, keys over the whole int64 range) x
+    (plain, filtered, concatenated input), through the dense-table path and the hash / regroup path; plus dictionary
+    and multi-key aggregation.  Keys, columns, dtypes and values against pandas."""
+    import modin_b200.pandas as bpd
+
+    rng = np.random.RandomState(5)
+    n = 907
+    wide = pandas.DataFrame(rng.randn(n, 40), columns=[f"w{i}" for i in range(40)])
+    wide.iloc[::13, 33] = np.nan
+    wide.iloc[::7, 2] = np.nan
+    wide.insert(0, "key", rng.randint(-4, 5, n).astype(np.int64))
+    wide.insert(1, "k2", (rng.randint(0, 3, n) * 100 - 100).astype(np.int64))
+    narrow = wide[["key", "k2", "w0", "w2", "w33"]]
+    frames = {
+        "wide": wide, "narrow": narrow, "keys with gaps": narrow.assign(key=narrow["key"] * 1000003),
+        "one group": narrow.assign(key=np.int64(7)),
+        "keys over the int64 range": narrow.assign(key=rng.randint(-(2**62), 2**62, n).astype(np.int64)),
+    }  # fmt: skip
+    spec = {"w2": "max", "w0": "sum", "w33": "count"}
+    config.GroupbyDenseKeys.put(dense)
+    try:
+        cases = {}
+        for fname, p in frames.items():
+            d = bpd.DataFrame(p)
+            cols = ["key"] + [c for c in p.columns if c not in ("key", "k2")]
+            variants = {
+                "plain": (d, p),
+                "filtered": (d[d["w0"] > 0.0], p[p["w0"] > 0.0]),
+                "concatenated": (bpd.concat([d, d.head(100)], ignore_index=True), pandas.concat([p, p.head(100)], ignore_index=True)),
+            }  # fmt: skip
+            for vname, (dd, pp) in variants.items():
+                for agg in ("sum", "count", "mean", "min", "max", "size"):
+                    cases[f"{fname} / {vname}: {agg}"] = ((lambda x=dd, a=agg: getattr(x[cols].groupby("key"), a)()),
+                                                          (lambda x=pp, a=agg: getattr(x[cols].groupby("key"), a)()))  # fmt: skip
+                if fname in ("wide", "narrow"):
+                    mk = ["key", "k2", "w0", "w2", "w33"]
+                    cases[f"{fname} / {vname}: dict"] = ((lambda x=dd: x.groupby("key").agg(spec)), (lambda x=pp: x.groupby("key").agg(spec)))
+                    cases[f"{fname} / {vname}: two keys"] = ((lambda x=dd: x[mk].groupby(["key", "k2"]).sum()),
+                                                             (lambda x=pp: x[mk].groupby(["key", "k2"]).sum()))  # fmt: skip
+        assert len(cases) == 5 * 3 * 6 + 2 * 3 * 2
+        _compare(cases, check_dtypes=True)
+    finally:
+        config.GroupbyDenseKeys.put(True)
