@@ -269,6 +269,9 @@ class JoinTable:
         for c in dim_cols:
             x = _np(c)
             null = np.nan if c.dtype == np.float64 else 0
+            if len(x) == 0:  # empty dim table: every row misses (the kernel never dereferences a dim row on a miss)
+                outs.append(_col(np.full(len(idx), null).astype(c.dtype)))
+                continue
             outs.append(_col(np.where(idx >= 0, x[np.maximum(idx, 0)], null).astype(c.dtype)))
         return outs, torch.tensor([int((idx >= 0).sum())])
 
@@ -282,6 +285,10 @@ def take_columns(cols, idx):
     for c in cols:
         x = _np(c)
         null = np.nan if c.dtype == np.float64 else 0
+        if len(x) == 0:  # empty source: only negative (null) positions are legal, nothing is dereferenced
+            assert not (i >= 0).any(), "take from an empty column with a non-negative position"
+            outs.append(_col(np.full(len(i), null).astype(c.dtype)))
+            continue
         outs.append(_col(np.where(i >= 0, x[np.maximum(i, 0)], null).astype(c.dtype)))
     return outs
 

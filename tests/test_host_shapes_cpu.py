@@ -432,3 +432,47 @@ def test_groupby_aggregations_across_key_kinds_and_shapes(cpu_device, dense):
         _compare(cases, check_dtypes=True)
     finally:
         config.GroupbyDenseKeys.put(True)
+
+
+def test_broadcast_merge_across_dim_and_fact_kinds(cpu_device):
+    """fact.merge(dim, on="key", how=left | inner): dim tables holding every key / some keys / one row / no key of the
+    fact / no rows at all, with a float payload that overlaps a fact column (suffixes) and an int64 payload (promoted
+    to float64 when a left join misses); facts plain, wider than one column partition, with gappy keys and keys near
+    the int64 range; inputs plain, filtered, concatenated.  Bit for bit, with dtypes, against pandas.  (The dense and
+    the hashed dim table differ only below the C ABI; the ``gpu`` merge tests cover both.)"""
+    import modin_b200.pandas as bpd
+
+    rng = np.random.RandomState(5)
+    n = 907
+    fact = pandas.DataFrame({"key": rng.randint(-4, 12, n).astype(np.int64), "x": rng.randn(n), "d0": rng.randn(n),
+                             "i": rng.randint(0, 9, n).astype(np.int64)})  # fmt: skip
+    fact.loc[::11, "x"] = np.nan
+    wide = pandas.concat([fact, pandas.DataFrame(rng.randn(n, 36), columns=[f"w{i}" for i in range(36)])], axis=1)
+
+    def dim_of(keys):
+        k = np.asarray(keys, dtype=np.int64)
+        return pandas.DataFrame({"key": k, "d0": rng.randn(len(k)), "p": np.arange(len(k), dtype=np.int64) * 3})
+
+    dims = {"every key": dim_of(rng.permutation(np.arange(-4, 12))), "some keys": dim_of(rng.permutation(np.arange(-4, 12))[:9]),
+            "one row": dim_of([3]), "no key of the fact": dim_of([100, 200]), "no rows": dim_of([])}  # fmt: skip
+    scale = {"plain": 1, "wide": 1, "keys with gaps": 1000003, "keys near the int64 range": 2**58}
+    facts = {"plain": fact, "wide": wide, "keys with gaps": fact.assign(key=fact["key"] * 1000003),
+             "keys near the int64 range": fact.assign(key=fact["key"] * (2**58))}  # fmt: skip
+    bad = {}
+    for fname, p in facts.items():
+        d = bpd.DataFrame(p)
+        variants = {"plain": (d, p), "filtered": (d[d["x"] > 0.0], p[p["x"] > 0.0]),
+                    "concatenated": (bpd.concat([d, d.head(50)], ignore_index=True), pandas.concat([p, p.head(50)], ignore_index=True))}  # fmt: skip
+        for vname, (dd, pp) in variants.items():
+            for dname, dim in dims.items():
+                dim = dim.assign(key=dim["key"] * scale[fname])
+                for how, suffixes in (("left", ("_x", "_y")), ("inner", ("_x", "_y")), ("left", ("_l", "_r"))):
+                    want = pp.merge(dim, on="key", how=how, suffixes=suffixes)
+                    g = dd.merge(bpd.DataFrame(dim), on="key", how=how, suffixes=suffixes)._to_pandas()
+                    gv, wv = np.asarray(g, dtype=np.float64), np.asarray(want, dtype=np.float64)
+                    ok = (list(g.columns) == list(want.columns) and list(g.index) == list(want.index) and gv.shape == wv.shape
+                          and bool(((gv == wv) | (np.isnan(gv) & np.isnan(wv))).all())
+                          and [str(t) for t in g.dtypes] == [str(t) for t in want.dtypes])  # fmt: skip
+                    if not ok:
+                        bad[f"{fname} / {vname} x {dname}, {how} {suffixes}"] = (gv.shape, wv.shape)
+    assert not bad, bad
