@@ -308,6 +308,12 @@ class DeviceBlock:
         out.replicated = self.replicated
         return out
 
+    def squeeze(self, axis=None) -> "DeviceBlock":
+        """A one-column block IS this package's Series, so squeezing changes nothing.  Modin's Binary template calls
+        ``right.squeeze()`` on the broadcast operand (``df.mul(series, axis=0)``, alg/binary.py:396-402) before handing
+        it to the block function; ``DevBinary`` pairs a one-column right operand with every left column."""
+        return self
+
     def select_columns(self, positions: Sequence[int]) -> "DeviceBlock":
         """Column subset sharing the buffers (mask along axis 1)."""
         return self.with_cols([self.cols[i] for i in positions], self.columns[list(positions)])

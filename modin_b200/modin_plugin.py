@@ -227,8 +227,10 @@ def register(shims: bool | None = None):
                 raise NotImplementedError("fillna(method=/limit=) is a Fold in the reference; not on the B200 path")
             if isinstance(value, type(self)):
                 return self.__constructor__(
+                    # PandasDataframe.n_ary_op takes the dtypes themselves: the "copy" shorthand is only understood by
+                    # the Binary template and broadcast_apply (it used to reach ModinDtypes as a string and fail)
                     self._modin_frame.n_ary_op(lambda x, y: fx.DevBinary("fillna")(x, y), [value._modin_frame],
-                                               join_type="left", dtypes="copy")
+                                               join_type="left", dtypes=self._modin_frame.copy_dtypes_cache())
                 )  # fmt: skip
             kw = {k: v for k, v in kwargs.items() if k in ("value",)}
             return self.__constructor__(self._modin_frame.map(lambda x: fx.DevFillna()(x, **kw), dtypes="copy"))

@@ -600,11 +600,12 @@ def test_pandas_method_on_a_block_is_a_clear_refusal(cpu_device):
 
     blk = DeviceBlock.from_pandas(pandas.DataFrame({"a": [1.0, 2.0]}))
     with pytest.raises(NotImplementedError, match="no device implementation"):
-        blk.squeeze(axis=1)
+        blk.cumsum(axis=0)
     with pytest.raises(AttributeError):
-        blk.cumsum
+        blk.rolling
     assert issubclass(NotOnDevicePath, NotImplementedError) and issubclass(NotOnDevicePath, AttributeError)
-    assert not hasattr(blk, "squeeze") and getattr(blk, "iloc", None) is None
+    assert not hasattr(blk, "cumsum") and getattr(blk, "iloc", None) is None
+    assert blk.squeeze(axis=1) is blk  # a one-column block is this package's Series (what Modin's broadcast branch asks)
     assert not hasattr(blk, "__array__") and not hasattr(blk, "__cuda_array_interface__")
     dup = copy.copy(blk)
     assert dup.nrows == 2 and dup.cols[0] is blk.cols[0] and list(dup.columns) == ["a"]

@@ -182,6 +182,24 @@ def _late_scenarios(mpd, ns):
     assert np.allclose(P(mdf[fcols].std()).to_numpy(), pdf[fcols].std().to_numpy(), rtol=1e-12, atol=0)
     with pytest.raises(NotImplementedError):
         mdf[fcols].var(axis=1)
+    # Binary template operand shapes through Modin's own dispatch: reflected scalars, positional / labelled row vectors
+    # (Modin applies those full-axis), a column along axis 0 (its broadcast branch squeezes the one-column block),
+    # co-partitioned frames, a frame-valued fillna
+    v, other = pdf[fcols], synth.host_frame(2003, 3, seed=13, nan_per_64k=2000)[fcols]
+    dv, do = mdf[fcols], mpd.DataFrame(other)
+    row3, srow = [0.5, -1.0, 2.0], pandas.Series([0.5, -1.0, 2.0], index=fcols)
+    for name, got, want in (
+        ("2 - df", 2.0 - dv, 2.0 - v), ("1 / df", 1.0 / dv, 1.0 / v), ("df.rsub", dv.rsub(1.0), v.rsub(1.0)),
+        ("df + list", dv + row3, v + row3), ("df * Series", dv * srow, v * srow), ("df < list", dv < row3, v < row3),
+        ("df.mul(col, 0)", dv.mul(dv["c1"], axis=0), v.mul(v["c1"], axis=0)),
+        ("df.rsub(col, 0)", dv.rsub(dv["c1"], axis=0), v.rsub(v["c1"], axis=0)),
+        ("df.lt(col, 0)", dv.lt(dv["c1"], axis=0), v.lt(v["c1"], axis=0)),
+        ("df - other", dv - do, v - other), ("df.rtruediv(other)", dv.rtruediv(do), v.rtruediv(other)),
+        ("a*b+c", dv * do + do, v * other + other), ("a*list+list", dv * row3 + row3, v * row3 + row3),
+        ("fillna(frame)", dv.fillna(do), v.fillna(other)), ("fillna(dict)", dv.fillna({"c0": 1.0}), v.fillna({"c0": 1.0})),
+        ("series - series", dv["c0"] - dv["c1"], v["c0"] - v["c1"]), ("2 - series", 2.0 - dv["c0"], 2.0 - v["c0"]),
+    ):  # fmt: skip
+        assert P(got).equals(want), name
     # sort_values: stable, NaN last (the reference's own range-partitioning sort returns an empty frame under pandas 3)
     for by, asc in (("c0", True), ("c0", False), ("key", True), ("k2", False)):
         assert P(mdf.sort_values(by, ascending=asc)).equals(pdf.sort_values(by, ascending=asc, kind="stable")), (by, asc)
