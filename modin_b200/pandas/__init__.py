@@ -465,6 +465,53 @@ class Series(BasePandasDataset):
     def _finish_host_stat(self, ser):
         return ser.iloc[0]
 
+    # ---- the frame surface that only re-wraps: a Series is a one-column frame, so these delegate to it -----------
+    @property
+    def dtype(self):
+        return self._query_compiler.dtypes.iloc[0]
+
+    def _as_frame(self) -> "DataFrame":
+        return DataFrame(query_compiler=self._query_compiler)
+
+    @staticmethod
+    def _of(frame: "DataFrame") -> "Series":
+        return Series(query_compiler=frame._query_compiler)
+
+    def head(self, n=5):
+        return self._of(self._as_frame().head(n))
+
+    def tail(self, n=5):
+        return self._of(self._as_frame().tail(n))
+
+    def copy(self, deep=True):
+        return self._of(self._as_frame().copy())
+
+    def dropna(self, *, axis=0, inplace=False, how=None, ignore_index=False):
+        if inplace or ignore_index or axis not in (0, "index"):
+            raise NotImplementedError("Series.dropna(inplace= / ignore_index= / axis=1) is not on the B200 path")
+        return self._of(self._as_frame().dropna())
+
+    def sort_values(self, *, axis=0, ascending=True, inplace=False, kind="quicksort", na_position="last",
+                    ignore_index=False, key=None):  # fmt: skip
+        if inplace:
+            raise NotImplementedError("sort_values(inplace=True) is not on the B200 path")
+        label = self._query_compiler.columns[0]
+        return self._of(self._as_frame().sort_values(label, axis=axis, ascending=ascending, kind=kind, na_position=na_position,
+                                                     ignore_index=ignore_index, key=key))  # fmt: skip
+
+    def rename(self, index=None, **kwargs):
+        """``Series.rename(name)``: a new name over the same buffer (relabelling the row labels is not on the path)."""
+        if kwargs or callable(index) or isinstance(index, dict):
+            raise NotImplementedError("Series.rename on the B200 path only changes the name")
+        label = MODIN_UNNAMED_SERIES_LABEL if index is None else index
+        return Series(query_compiler=self._query_compiler.relabel_columns([label]))
+
+    def __getitem__(self, key):
+        """``s[bool_series]``: boolean row selection, as on a frame."""
+        if isinstance(key, Series):
+            return self._of(self._as_frame()[key])
+        raise NotImplementedError("indexing a Series on the B200 path takes a bool Series")
+
     # ---- distinct values of an int64 Series, through the group tables (qc.py:1109-1142 nunique / unique; the
     # reference's range-partitioning variants are built on the same shuffle as sort_values) ----------------------
     def _as_key_frame(self):

@@ -612,6 +612,55 @@ def test_pandas_method_on_a_block_is_a_clear_refusal(cpu_device):
     assert np.asarray([[blk]], dtype=object).shape == (1, 1)  # still an opaque object to numpy, not a sequence
 
 
+def test_series_surface(cpu_device):
+    """A Series is a one-column frame: the whole surface against pandas -- values, row labels, NAME and dtype."""
+    import modin_b200.pandas as bpd
+
+    pa = synth.host_frame(1003, 3, seed=1, nan_per_64k=3000, key_modulus=11)
+    d = bpd.DataFrame(pa)
+    s, ws, k, wk = d["c0"], pa["c0"], d["key"], pa["key"]
+    assert s.name == "c0" and len(s) == len(ws) and s.dtype == ws.dtype and k.dtype == wk.dtype
+    series_cases = {
+        "abs": (lambda: s.abs(), lambda: ws.abs()), "neg": (lambda: -s, lambda: -ws), "round": (lambda: s.round(1), lambda: ws.round(1)),
+        "clip": (lambda: s.clip(-0.5, 0.5), lambda: ws.clip(-0.5, 0.5)), "fillna": (lambda: s.fillna(0.0), lambda: ws.fillna(0.0)),
+        "isna": (lambda: s.isna(), lambda: ws.isna()), "affine": (lambda: s * 2.0 + 1.0, lambda: ws * 2.0 + 1.0),
+        "reflected": (lambda: 2.0 - s, lambda: 2.0 - ws), "series / series": (lambda: s / d["c1"], lambda: ws / pa["c1"]),
+        "comparison": (lambda: s > 0.0, lambda: ws > 0.0), "series > series": (lambda: s > d["c1"], lambda: ws > pa["c1"]),
+        "mask and": (lambda: (s > 0.0) & (d["c1"] < 0.0), lambda: (ws > 0.0) & (pa["c1"] < 0.0)), "mask not": (lambda: ~(s > 0.0), lambda: ~(ws > 0.0)),
+        "s[mask]": (lambda: s[s > 0.0], lambda: ws[ws > 0.0]), "dropna": (lambda: s.dropna(), lambda: ws.dropna()),
+        "head": (lambda: s.head(7), lambda: ws.head(7)), "tail": (lambda: s.tail(7), lambda: ws.tail(7)), "copy": (lambda: s.copy(), lambda: ws.copy()),
+        "sort_values": (lambda: s.sort_values(), lambda: ws.sort_values(kind="stable")),
+        "sort_values descending": (lambda: s.sort_values(ascending=False), lambda: ws.sort_values(ascending=False, kind="stable")),
+        "rename": (lambda: s.rename("zz"), lambda: ws.rename("zz")), "rename(None)": (lambda: s.rename(None), lambda: ws.rename(None)),
+        "astype": (lambda: k.astype("float64"), lambda: wk.astype("float64")), "isin": (lambda: k.isin([1, 2]), lambda: wk.isin([1, 2])),
+        "drop_duplicates": (lambda: k.drop_duplicates(), lambda: wk.drop_duplicates()),
+        "drop_duplicates last": (lambda: k.drop_duplicates(keep="last"), lambda: wk.drop_duplicates(keep="last")),
+        "int == int": (lambda: k == 3, lambda: wk == 3), "int > float": (lambda: k > 2.5, lambda: wk > 2.5), "int * 2": (lambda: k * 2, lambda: wk * 2),
+    }  # fmt: skip
+    for name, (dev, host) in series_cases.items():
+        got, want = dev(), host()
+        assert isinstance(got, bpd.Series), name
+        g = got._to_pandas()
+        assert g.name == want.name and g.dtype == want.dtype and list(g.index) == list(want.index), name
+        assert _same(g.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64)), name
+    scalar_cases = {
+        "sum": (lambda: s.sum(), lambda: ws.sum()), "mean": (lambda: s.mean(), lambda: ws.mean()), "min": (lambda: s.min(), lambda: ws.min()),
+        "max": (lambda: s.max(), lambda: ws.max()), "count": (lambda: s.count(), lambda: ws.count()), "var": (lambda: s.var(), lambda: ws.var()),
+        "std": (lambda: s.std(), lambda: ws.std()), "prod": (lambda: s.head(20).prod(), lambda: ws.head(20).prod()),
+        "sum skipna=False": (lambda: s.sum(skipna=False), lambda: ws.sum(skipna=False)), "nunique": (lambda: k.nunique(), lambda: wk.nunique()),
+        "mask sum": (lambda: (s > 0.0).sum(), lambda: (ws > 0.0).sum()), "mask any": (lambda: (s > 0.0).any(), lambda: (ws > 0.0).any()),
+        "mask all": (lambda: (s > -100.0).all(), lambda: (ws > -100.0).all()), "mask mean": (lambda: (s > 0.0).mean(), lambda: (ws > 0.0).mean()),
+        "int sum": (lambda: k.sum(), lambda: wk.sum()), "int min": (lambda: k.min(), lambda: wk.min()), "int mean": (lambda: k.mean(), lambda: wk.mean()),
+    }  # fmt: skip
+    for name, (dev, host) in scalar_cases.items():
+        g, want = dev(), host()
+        assert np.ndim(g) == 0, name
+        assert (np.isnan(g) and np.isnan(want)) or np.isclose(g, want, rtol=1e-12, atol=1e-9), (name, g, want)
+    for refused in (lambda: s[0], lambda: s.dropna(inplace=True), lambda: s.rename({0: 1}), lambda: s.sort_values(inplace=True)):
+        with pytest.raises(NotImplementedError):
+            refused()
+
+
 def test_isin_is_a_join_probe(cpu_device):
     import modin_b200.pandas as bpd
 
