@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MB200_ABI_VERSION 1
+#define MB200_ABI_VERSION 2
 #define MB200_MAX_COLS 32 /* max columns per launch == Modin's MinColumnPartitionSize (envvars.py:1149-1190) */
 
 typedef void* mb200_stream_t;
@@ -220,6 +220,16 @@ int mb200_gb_hint_skew(mb200_gb_table* table, int skewed);
 int mb200_gb_create_dense(mb200_gb_table** table, int64_t key_min, int64_t key_max, int nvals,
                           int flags, void* acc, void* cnt, void* size, void* present,
                           mb200_stream_t stream);
+/* A dense table over caller-owned arrays that ALREADY hold accumulated state in the layout above -- the slice of
+ * the job-wide table this rank received from a reduce-scatter over the GPUs (NCCL SUM / MIN / MAX on acc, SUM on cnt
+ * and size, MAX on present).  Nothing is initialised; mb200_gb_ngroups / mb200_gb_emit then report the slice.  This
+ * is the reduce phase of GroupByReduce (alg/groupby.py:211-300) for dense keys across GPUs: each rank receives and
+ * emits only its own key range. */
+int mb200_gb_adopt_dense(mb200_gb_table** table, int64_t key_min, int64_t key_max, int nvals,
+                         int flags, void* acc, void* cnt, void* size, void* present,
+                         const mb200_gb_table* parent, mb200_stream_t stream);
+/* `parent` (may be NULL): the table whose arrays were scattered; its overflow flag (a key outside the declared range
+ * during accumulate) is inherited, so mb200_gb_ngroups on the slice reports it without a second host round trip. */
 /* Restrict what mb200_gb_ngroups / mb200_gb_emit report to group ids [gid_lo, gid_hi) (multiples of 4,
  * or gid_hi = R): after a cross-GPU merge each rank emits its own slice of the key range. */
 int mb200_gb_dense_window(mb200_gb_table* table, int64_t gid_lo, int64_t gid_hi);
@@ -281,12 +291,15 @@ int mb200_compact_hits(const int64_t* idx, int64_t n, int64_t* out_pos, int64_t*
  * values are NaN.  gen_i64: uniform integer in [0, modulus). */
 int mb200_gen_f64(double* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
                   int nan_per_64k, mb200_stream_t stream);
+/* stats_dev (may be NULL): DEVICE int64[4] that receives the generated column's key statistics {min, max, sampled,
+ * duplicated} (same quadruple as mb200_key_range) -- the producing kernel leaves them behind as column metadata,
+ * so a groupby on the column needs no 8 B/row pre-pass. */
 int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
-                  uint64_t modulus, mb200_stream_t stream);
+                  uint64_t modulus, int64_t* stats_dev, mb200_stream_t stream);
 /* Skewed keys in [0, modulus) (the Zipf-like variant of the groupby workload): mass per octave of the key
  * space grows towards small keys like k^-1.1 -- for modulus = 1e6 key 0 takes ~11 % of the rows. */
 int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
-                       uint64_t modulus, mb200_stream_t stream);
+                       uint64_t modulus, int64_t* stats_dev, mb200_stream_t stream);
 
 /* ======================= utilities ========================================= */
 /* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.

@@ -20,6 +20,8 @@ class B200Error(RuntimeError):
     """Raised when a libmodin_b200 call fails (message from mb200_last_error)."""
 
 
+ABI_VERSION = 2
+
 # enums (keep in sync with include/modin_b200.h)
 F64, I64, U8 = 0, 1, 2
 
@@ -68,6 +70,7 @@ _SIGNATURES = {
     "mb200_gb_create": (C.c_int, [_vpp, _i64, C.c_int, C.c_int, _vp]),
     "mb200_key_range": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp]),
     "mb200_gb_create_dense": (C.c_int, [_vpp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "mb200_gb_adopt_dense": (C.c_int, [_vpp, _i64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mb200_gb_dense_window": (C.c_int, [_vp, _i64, _i64]),
     "mb200_gb_hint_skew": (C.c_int, [_vp, C.c_int]),
     "mb200_gb_destroy": (C.c_int, [_vp, _vp]),
@@ -84,8 +87,8 @@ _SIGNATURES = {
     "mb200_take": (C.c_int, [C.c_int, C.c_int, _vpp, _vp, _i64, _vpp, _vp]),
     "mb200_compact_hits": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
-    "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp]),
-    "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp]),
+    "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
+    "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_sort_pairs_i64": (C.c_int, [_vp, _vp, _i64, _vp, C.c_size_t, _vp]),
     "mb200_l2_persist_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -116,7 +119,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.mb200_abi_version() != 1:
+        if lib.mb200_abi_version() != ABI_VERSION:
             raise B200Error("libmodin_b200 ABI version mismatch")
         _lib = lib
         return lib

@@ -86,14 +86,49 @@ def _torch_dtype(np_dtype):
     raise TypeError(f"dtype {np_dtype} is not supported on the B200 partition path")
 
 
+class KeyStats:
+    """Key statistics of an int64 column -- ``{min, max, sampled, duplicated}`` as ``mb200_key_range`` defines them
+    -- carried as immutable column METADATA.  The kernel that produces a column leaves them behind (the synthetic
+    generators, the ingest pass after an H2D copy); a column of unknown origin pays one 8 B/row pass the first time
+    a groupby asks, never again.  The quadruple stays on the device until somebody needs the numbers
+    (``host()``: one 32-byte D2H, memoised).  ``exact`` is False for bounds inherited from a parent column (row
+    slices): still a valid range for a direct-addressed table, possibly wider than the slice's own."""
+
+    __slots__ = ("_dev", "_host", "exact", "job")
+
+    def __init__(self, dev=None, host=None, exact=True):
+        self._dev, self._host, self.exact = dev, (tuple(int(v) for v in host) if host is not None else None), exact
+        self.job = None  # job-wide (all ranks) statistics of a group of key columns, cached by the first of them
+
+    def pending(self):
+        """Device quadruple not read back yet (None once ``host()`` has run)."""
+        return self._dev if self._host is None else None
+
+    def resolve(self, values):
+        self._host, self._dev = tuple(int(v) for v in values), None
+
+    def host(self):
+        if self._host is None:
+            self.resolve(self._dev.tolist())
+        return self._host
+
+    def as_bounds(self) -> "KeyStats":
+        if self._host is not None:
+            return KeyStats(host=self._host, exact=False)
+        ks = KeyStats(dev=self._dev, exact=False)
+        return ks
+
+
 class DeviceColumn:
-    """One fixed-width column: a 1-D device tensor plus the pandas dtype it stands for."""
+    """One fixed-width column: a 1-D device tensor plus the pandas dtype it stands for (and, for int64 columns
+    that have been or may become group keys, their ``KeyStats``)."""
 
-    __slots__ = ("data", "dtype")
+    __slots__ = ("data", "dtype", "stats")
 
-    def __init__(self, data, dtype):
+    def __init__(self, data, dtype, stats=None):
         self.data = data  # torch tensor, 1-D, contiguous
         self.dtype = np.dtype(dtype)
+        self.stats = stats
 
     def __len__(self):
         return int(self.data.shape[0])
@@ -123,7 +158,14 @@ class DeviceColumn:
             # pandas copy-on-write hands out read-only arrays; they are only read for the H2D copy
             warnings.simplefilter("ignore", UserWarning)
             dev = t.from_numpy(host).to(target, non_blocking=False)
-        return cls(dev, dtype)
+        col = cls(dev, dtype)
+        if dtype == np.int64 and len(col) >= _INGEST_STATS_MIN_ROWS:
+            # ingest is the producing step of this column: leave its key statistics behind (one device pass over
+            # data the PCIe copy has just delivered) so that a later groupby on it needs no pre-pass
+            from . import ops
+
+            col.stats = KeyStats(dev=ops.key_range_device([col]))
+        return col
 
     def to_numpy(self) -> np.ndarray:
         host = self.data.cpu().numpy()
@@ -132,7 +174,12 @@ class DeviceColumn:
         return host
 
     def slice(self, start: int, stop: int) -> "DeviceColumn":
-        return DeviceColumn(self.data[start:stop], self.dtype)
+        whole = start <= 0 and stop >= len(self)
+        stats = self.stats if whole or self.stats is None else self.stats.as_bounds()
+        return DeviceColumn(self.data[start:stop], self.dtype, stats)
+
+
+_INGEST_STATS_MIN_ROWS = 1 << 16  # below this a groupby's own pass over the keys is noise
 
 
 class NotOnDevicePath(NotImplementedError, AttributeError):

@@ -166,6 +166,60 @@ __device__ __forceinline__ uint32_t hash_key(long long k) {
   return (uint32_t)z;
 }
 
+// ---------------------------------------------------------------- key statistics {min, max, sampled, duplicated}
+// The statistics a groupby needs about its int64 key column to pick a table (dense range? skewed?).  They are
+// column METADATA: computed by whichever kernel produces the column (gen_i64*, the ingest pass after an H2D
+// copy) or, for a column of unknown origin, once by key_range_kernel -- never per query.
+//   stats[0] = min, stats[1] = max, stats[2] = keys sampled, stats[3] = of those, how many shared their value
+//   with another of the 32 keys sampled in the same warp instruction.
+struct KeyStatsAcc {
+  long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000ULL;
+  unsigned int sampled = 0, dups = 0;
+  __device__ __forceinline__ void add(long long k) {
+    lo = k < lo ? k : lo;
+    hi = k > hi ? k : hi;
+  }
+  // all 32 lanes of the warp must call this together
+  __device__ __forceinline__ void sample_warp(long long k) {
+    const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
+    dups += __popc(__ballot_sync(0xffffffffu, __popc(peers) > 1));
+    sampled += 32;
+  }
+  // block-wide fold + one atomic quadruple per block; blockDim.x <= 1024, every thread of the block calls it
+  __device__ __forceinline__ void flush(long long* stats) {
+    __shared__ long long s_min[32], s_max[32];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const long long a = __shfl_xor_sync(0xffffffffu, lo, m), b = __shfl_xor_sync(0xffffffffu, hi, m);
+      lo = a < lo ? a : lo;
+      hi = b > hi ? b : hi;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+      s_min[warp] = lo;
+      s_max[warp] = hi;
+      if (sampled) {  // every lane of a warp holds the same two counters
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats[2]), (unsigned long long)sampled);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&stats[3]), (unsigned long long)dups);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < nwarps; ++w) {
+        lo = s_min[w] < lo ? s_min[w] : lo;
+        hi = s_max[w] > hi ? s_max[w] : hi;
+      }
+      if (lo <= hi) {
+        atomicMin(&stats[0], lo);
+        atomicMax(&stats[1], hi);
+      }
+    }
+  }
+};
+
+// stats_dev[4] <- {INT64_MAX, INT64_MIN, 0, 0} (groupby.cu)
+int key_stats_init(long long* stats_dev, cudaStream_t st);
+
 inline bool aligned32(const void* p) { return (((uintptr_t)p) & 31u) == 0; }
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 

@@ -798,16 +798,17 @@ __global__ void gb_emit_kernel(const __grid_constant__ EmitParams p) {
 }
 
 // ---------------------------------------------------------------- dense tables: key range, ordered emit
-// min / max of an int64 key column (the pre-pass that decides between a dense and a hashed table):
-// 4 x 256-bit streaming loads in flight per thread, one atomic pair per block.
+// min / max (+ skew sample) of an int64 key column whose statistics are not known yet (a column that no
+// stats-producing kernel of this library wrote): 4 x 256-bit streaming loads in flight per thread, one atomic
+// quadruple per block.  The result is cached on the column by the caller (column metadata), so a column pays
+// this 8 B/row pass at most once, not once per query.
 __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restrict__ keys, long long n,
                                                         long long* minmax) {
-  __shared__ long long s_min[8], s_max[8];
-  long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000ULL;
+  KeyStatsAcc st;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long head = (((uintptr_t)keys & 31u) == 0) ? (n & ~15LL) : 0;  // 16 keys per thread-iteration
-  unsigned int sampled = 0, dups = 0, iter = 0;
+  unsigned int iter = 0;
   for (long long i = tid * 4; i + 3 < head; i += nthreads * 16, ++iter) {
     i64x4 v[4];
     bool ok[4];
@@ -819,52 +820,18 @@ __global__ void __launch_bounds__(256) key_range_kernel(const long long* __restr
     }
     // skew statistic (every 4th iteration, whole warps only): how many of 32 sampled keys share their value
     // with another lane's.  Uniform keys over G values: ~ 496 / G of them; a heavy hitter at 10 %: > 80 %.
-    if ((iter & 3u) == 0 && __activemask() == 0xffffffffu) {
-      const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)v[0].x);
-      dups += __popc(__ballot_sync(0xffffffffu, __popc(peers) > 1));
-      sampled += 32;
-    }
+    if ((iter & 3u) == 0 && __activemask() == 0xffffffffu) st.sample_warp(v[0].x);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (!ok[u]) continue;
-      const long long a = v[u].x < v[u].y ? v[u].x : v[u].y, b = v[u].z < v[u].w ? v[u].z : v[u].w;
-      const long long c = v[u].x > v[u].y ? v[u].x : v[u].y, d = v[u].z > v[u].w ? v[u].z : v[u].w;
-      const long long mn = a < b ? a : b, mx = c > d ? c : d;
-      lo = mn < lo ? mn : lo;
-      hi = mx > hi ? mx : hi;
+      st.add(v[u].x);
+      st.add(v[u].y);
+      st.add(v[u].z);
+      st.add(v[u].w);
     }
   }
-  for (long long i = head + tid; i < n; i += nthreads) {
-    const long long k = keys[i];
-    lo = k < lo ? k : lo;
-    hi = k > hi ? k : hi;
-  }
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const long long a = __shfl_xor_sync(0xffffffffu, lo, m), b = __shfl_xor_sync(0xffffffffu, hi, m);
-    lo = a < lo ? a : lo;
-    hi = b > hi ? b : hi;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    s_min[warp] = lo;
-    s_max[warp] = hi;
-    if (sampled) {  // every lane of a warp holds the same two counters
-      atomicAdd(reinterpret_cast<unsigned long long*>(&minmax[2]), (unsigned long long)sampled);
-      atomicAdd(reinterpret_cast<unsigned long long*>(&minmax[3]), (unsigned long long)dups);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
-      lo = s_min[w] < lo ? s_min[w] : lo;
-      hi = s_max[w] > hi ? s_max[w] : hi;
-    }
-    if (lo <= hi) {
-      atomicMin(&minmax[0], lo);
-      atomicMax(&minmax[1], hi);
-    }
-  }
+  for (long long i = head + tid; i < n; i += nthreads) st.add(keys[i]);
+  st.flush(minmax);
 }
 
 __global__ void key_range_init_kernel(long long* minmax) {
@@ -872,6 +839,13 @@ __global__ void key_range_init_kernel(long long* minmax) {
   minmax[1] = (long long)0x8000000000000000ULL;
   minmax[2] = 0;  // keys sampled for the skew statistic
   minmax[3] = 0;  // ... of which shared their value with another of the 32 keys sampled with them
+}
+
+// shared with synth.cu (the generators that produce key columns fill the same quadruple)
+int key_stats_init(long long* stats_dev, cudaStream_t st) {
+  key_range_init_kernel<<<1, 1, 0, st>>>(stats_dev);
+  MB_LAUNCH_CHECK("key_range_init_kernel");
+  return 0;
 }
 
 // presence of a dense key = its byte was marked (rows that changed nothing) OR its accumulators moved
@@ -1172,7 +1146,7 @@ struct DenseArrays {  // caller-owned arrays of a dense table (all NULL: the lib
 };
 
 static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags, bool dense,
-                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream);
+                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream, bool init_arrays = true);
 
 extern "C" int mb200_gb_create(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags,
                                mb200_stream_t stream) {
@@ -1195,6 +1169,33 @@ extern "C" int mb200_gb_create_dense(mb200_gb_table** table, int64_t key_min, in
     return fail("mb200_gb_create_dense", "caller-owned arrays need the presence array too");
   }
   return gb_create_impl(table, (int64_t)range, nvals, flags, true, key_min, ext, stream);
+}
+
+namespace mb200 {
+__global__ void gb_inherit_overflow_kernel(GbMeta* child, const GbMeta* parent) {
+  if (parent->overflow) child->overflow = 1;
+}
+}  // namespace mb200
+
+extern "C" int mb200_gb_adopt_dense(mb200_gb_table** table, int64_t key_min, int64_t key_max, int nvals, int flags,
+                                    void* acc, void* cnt, void* size, void* present, const mb200_gb_table* parent,
+                                    mb200_stream_t stream) {
+  if (key_max < key_min) return fail("mb200_gb_adopt_dense", "empty key range");
+  const unsigned long long range = (unsigned long long)key_max - (unsigned long long)key_min + 1ULL;
+  if (range == 0 || range > (1ULL << 29)) return fail("mb200_gb_adopt_dense", "key range above 2^29");
+  const bool need_acc = flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX);
+  if (!present || (need_acc && !acc) || ((flags & MB200_GB_COUNT) && !cnt) || ((flags & MB200_GB_SIZE) && !size))
+    return fail("mb200_gb_adopt_dense", "every array the flags need must be given");
+  if (!aligned16(acc) || !aligned16(cnt) || !aligned16(size) || !aligned16(present))
+    return fail("mb200_gb_adopt_dense", "arrays must be 16-byte aligned");
+  DenseArrays ext{acc, cnt, size, present};
+  if (int rc = gb_create_impl(table, (int64_t)range, nvals, flags, true, key_min, ext, stream, /*init_arrays=*/false))
+    return rc;
+  if (parent) {
+    gb_inherit_overflow_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((*table)->meta, parent->meta);
+    MB_LAUNCH_CHECK("gb_inherit_overflow_kernel");
+  }
+  return 0;
 }
 
 extern "C" int mb200_gb_hint_skew(mb200_gb_table* t, int skewed) {
@@ -1220,10 +1221,8 @@ extern "C" int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* minm
   DevProps dp;
   if (int rc = dev_props(&dp)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (init) {
-    key_range_init_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long*>(minmax_dev));
-    MB_LAUNCH_CHECK("key_range_init_kernel");
-  }
+  if (init)
+    if (int rc = key_stats_init(reinterpret_cast<long long*>(minmax_dev), st)) return rc;
   if (nrows == 0) return 0;
   long long grid = (long long)dp.sm_count * 8;
   const long long need = (nrows + 256 * 16 - 1) / (256 * 16);
@@ -1235,7 +1234,7 @@ extern "C" int mb200_key_range(const int64_t* keys, int64_t nrows, int64_t* minm
 }
 
 static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nvals, int flags, bool dense,
-                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream) {
+                          int64_t kbase, const DenseArrays& ext, mb200_stream_t stream, bool init_arrays) {
   if (!table) return fail("mb200_gb_create", "null out pointer");
   if (nvals < 0 || nvals > MB200_MAX_COLS) return fail("mb200_gb_create", "nvals out of range (0..32)");
   if (group_capacity < 1) group_capacity = 1;
@@ -1272,13 +1271,15 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
   }
   if (dense) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->present, (size_t)t->nwords * 4, st));
-    MB_TRY(cudaMemsetAsync(t->present, 0, (size_t)t->nwords * 4, st));
+    if (init_arrays) MB_TRY(cudaMemsetAsync(t->present, 0, (size_t)t->nwords * 4, st));
     MB_TRY(cudaMallocAsync((void**)&t->blockoff, (size_t)((t->nwords + 255) / 256 + 1) * 4, st));
   } else {
     MB_TRY(cudaMallocAsync((void**)&t->slots, (size_t)t->cap * sizeof(Slot), st));
   }
   MB_TRY(cudaMallocAsync((void**)&t->meta, sizeof(GbMeta), st));
-  if (flags & MB200_GB_SUM) {
+  if (!init_arrays) {
+    // adopted arrays (mb200_gb_adopt_dense): already hold a merged table, nothing to initialise
+  } else if (flags & MB200_GB_SUM) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     if (dense) {  // -0.0: the one value no sum can end on (x + -0.0 = x, and sums start from +0.0 in the emit)
       gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
@@ -1298,11 +1299,11 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
     MB_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
   }
-  if (flags & MB200_GB_COUNT) {
+  if ((flags & MB200_GB_COUNT) && init_arrays) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
     MB_TRY(cudaMemsetAsync(t->cnt, 0, accb, st));
   }
-  if (flags & MB200_GB_SIZE) {
+  if ((flags & MB200_GB_SIZE) && init_arrays) {
     if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->size, (size_t)t->gcap * 8, st));
     MB_TRY(cudaMemsetAsync(t->size, 0, (size_t)t->gcap * 8, st));
   }

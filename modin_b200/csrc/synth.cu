@@ -38,13 +38,25 @@ __global__ void gen_f64_kernel(double* __restrict__ out, long long n, unsigned l
     out[i] = synth_f64(seed, col, row_offset + i, nan_per_64k);
 }
 
+// STATS: the generator also leaves the column's key statistics {min, max, sampled, duplicated} in stats[4]
+// (KeyStatsAcc, common.cuh) -- a groupby on a generated key column then needs no pre-pass over it.
+template <bool STATS>
 __global__ void gen_i64_kernel(long long* __restrict__ out, long long n, unsigned long long seed,
-                               unsigned long long col, long long row_offset, unsigned long long modulus) {
+                               unsigned long long col, long long row_offset, unsigned long long modulus,
+                               long long* stats) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  KeyStatsAcc st;
+  unsigned int iter = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride, ++iter) {
     const unsigned long long z1 = mix64(seed * K1 + col * K2 + (unsigned long long)(row_offset + i) + 1ULL);
-    out[i] = (long long)(((z1 >> 32) * modulus) >> 32);
+    const long long k = (long long)(((z1 >> 32) * modulus) >> 32);
+    out[i] = k;
+    if (STATS) {
+      st.add(k);
+      if ((iter & 15u) == 0 && __activemask() == 0xffffffffu) st.sample_warp(k);
+    }
   }
+  if (STATS) st.flush(stats);
 }
 
 // Skewed keys (the Zipf-like variant of SURVEY 8d): level t in [0, T] is drawn with weight w_t, w_0 = 2^20,
@@ -56,12 +68,15 @@ struct SkewLevels {
   int nlevels;                 // T + 1
 };
 
+template <bool STATS>
 __global__ void gen_i64_skew_kernel(long long* __restrict__ out, long long n, unsigned long long seed,
                                     unsigned long long col, long long row_offset, unsigned long long modulus,
-                                    const __grid_constant__ SkewLevels lv) {
+                                    const __grid_constant__ SkewLevels lv, long long* stats) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const unsigned long long total = lv.cum[lv.nlevels];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  KeyStatsAcc st;
+  unsigned int iter = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride, ++iter) {
     const unsigned long long z1 = mix64(seed * K1 + col * K2 + (unsigned long long)(row_offset + i) + 1ULL);
     const unsigned long long z2 = mix64(z1 + K3);
     // pick in [0, total): total < 2^31, so (32-bit piece * total) >> 32 is exact in 64 bits
@@ -70,8 +85,14 @@ __global__ void gen_i64_skew_kernel(long long* __restrict__ out, long long n, un
     while (t + 1 < lv.nlevels && lv.cum[t + 1] <= pick) ++t;
     unsigned long long range = modulus >> t;
     if (range == 0) range = 1;
-    out[i] = (long long)(((z1 >> 32) * range) >> 32);
+    const long long k = (long long)(((z1 >> 32) * range) >> 32);
+    out[i] = k;
+    if (STATS) {
+      st.add(k);
+      if ((iter & 15u) == 0 && __activemask() == 0xffffffffu) st.sample_warp(k);
+    }
   }
+  if (STATS) st.flush(stats);
 }
 
 __global__ void flush_kernel(unsigned long long* __restrict__ buf, long long n) {
@@ -98,25 +119,33 @@ extern "C" int mb200_gen_f64(double* out, int64_t nrows, uint64_t seed, uint64_t
 }
 
 extern "C" int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
-                             uint64_t modulus, mb200_stream_t stream) {
+                             uint64_t modulus, int64_t* stats_dev, mb200_stream_t stream) {
   if (nrows < 0) return fail("mb200_gen_i64", "negative nrows");
   if (modulus == 0 || modulus > 0xffffffffULL) return fail("mb200_gen_i64", "modulus must be in [1, 2^32)");
+  if (stats_dev)
+    if (int rc = key_stats_init(reinterpret_cast<long long*>(stats_dev), (cudaStream_t)stream)) return rc;
   if (nrows == 0) return 0;
   if (!out) return fail("mb200_gen_i64", "null output");
   DevProps dp;
   if (int rc = dev_props(&dp)) return rc;
   long long grid = (nrows + 255) / 256;
   if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
-  gen_i64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, seed, col,
-                                                                   row_offset, modulus);
+  if (stats_dev)
+    gen_i64_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<long long*>(out), nrows, seed, col, row_offset, modulus, reinterpret_cast<long long*>(stats_dev));
+  else
+    gen_i64_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows,
+                                                                            seed, col, row_offset, modulus, nullptr);
   MB_LAUNCH_CHECK("gen_i64_kernel");
   return 0;
 }
 
 extern "C" int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
-                                  uint64_t modulus, mb200_stream_t stream) {
+                                  uint64_t modulus, int64_t* stats_dev, mb200_stream_t stream) {
   if (nrows < 0) return fail("mb200_gen_i64_skew", "negative nrows");
   if (modulus == 0 || modulus > 0xffffffffULL) return fail("mb200_gen_i64_skew", "modulus must be in [1, 2^32)");
+  if (stats_dev)
+    if (int rc = key_stats_init(reinterpret_cast<long long*>(stats_dev), (cudaStream_t)stream)) return rc;
   if (nrows == 0) return 0;
   if (!out) return fail("mb200_gen_i64_skew", "null output");
   DevProps dp;
@@ -135,8 +164,13 @@ extern "C" int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, ui
   lv.nlevels = T + 1;
   long long grid = (nrows + 255) / 256;
   if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
-  gen_i64_skew_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, seed,
-                                                                        col, row_offset, modulus, lv);
+  if (stats_dev)
+    gen_i64_skew_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<long long*>(out), nrows, seed, col, row_offset, modulus, lv,
+        reinterpret_cast<long long*>(stats_dev));
+  else
+    gen_i64_skew_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<long long*>(out), nrows, seed, col, row_offset, modulus, lv, nullptr);
   MB_LAUNCH_CHECK("gen_i64_skew_kernel");
   return 0;
 }

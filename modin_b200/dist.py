@@ -135,6 +135,21 @@ def dense_split(nkeys: int, r: int | None = None, ws: int | None = None):
     return lo, min(lo + chunk, int(nkeys))
 
 
+def dense_chunk(nkeys: int, ws: int | None = None) -> int:
+    """Keys per rank when a dense key range of ``nkeys`` is reduce-scattered: equal chunks, a multiple of 4 (the
+    presence map is scanned in 4-byte words); ``ws * chunk >= nkeys`` (the table is padded to that)."""
+    ws = world_size() if ws is None else ws
+    chunk = -(-int(nkeys) // ws)
+    return max(4, (chunk + 3) & ~3)
+
+
+def reduce_scatter(out, inp, op: str) -> None:
+    """``out`` <- this rank's equal slice of the element-wise reduction of ``inp`` over the ranks (NCCL
+    reduce-scatter over NVLink: each rank receives (W-1)/W of ONE slice instead of the all_reduce's whole array)."""
+    d = _dist()
+    d.reduce_scatter_tensor(out, inp, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
+
+
 def all_reduce_values(tensors: Sequence, ops: Sequence[str]) -> None:
     """In-place all_reduce of many 1-element tensors: one collective per (dtype, op) bucket.
 

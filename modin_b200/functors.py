@@ -1081,35 +1081,48 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
         items.append((key, vals))
     if len(labels) > _lib_max_cols():
         return None
-    mm = ops.key_range_device([k for k, _ in items])
-    total_rows = sum(len(k) for k, _ in items)
+    key_cols = [k for k, _ in items]
+    lo, hi, sampled, dup = ops.key_stats(key_cols)  # column metadata: no pass over the keys, no sync, once known
+    total_rows = sum(len(k) for k in key_cols)
     if dist.is_distributed():
-        # one small all_gather ([min, max, sampled, duplicated, rows] per rank) + one D2H
-        trip = dist.all_gather_small(mm, extra=total_rows)
-        lo, hi, total_rows = min(r[0] for r in trip), max(r[1] for r in trip), sum(r[4] for r in trip)
-        sampled, dup = trip[dist.rank()][2:4]  # the hot-group cache is a local choice
-    else:
-        lo, hi, sampled, dup = (int(v) for v in mm.tolist())
+        # every rank must take the same decision: job-wide range and row count, agreed on ONCE per set of key
+        # columns (one small all_gather + one D2H) and then remembered on the first of them -- columns are
+        # immutable and so is the job
+        sig = (dist.world_size(), tuple(id(k.data) for k in key_cols))
+        anchor = key_cols[0].stats
+        if anchor.job is None or anchor.job[0] != sig:
+            t = ops.torch_mod()
+            mine = t.tensor([lo, hi, total_rows], dtype=t.int64, device=ops.current_device())
+            trip = dist.all_gather_small(mine)
+            anchor.job = (sig, (min(r[0] for r in trip), max(r[1] for r in trip), sum(r[2] for r in trip)))
+        lo, hi, total_rows = anchor.job[1]  # `sampled` / `dup` stay local: the hot-group cache is a local choice
     if lo > hi:
         return None  # no rows anywhere
     cap = max(1024, min(map_fn.capacity_hint, total_rows))
     if not ops.dense_range_ok(lo, hi, cap, total_rows, len(labels), flags):
         return None
-    table = ops.GroupTable.dense(lo, hi, len(labels), flags)
+    ws = dist.world_size() if dist.is_distributed() else 1
+    # across GPUs the table spans the job-wide range padded to ws equal chunks, so that it can be reduce-scattered
+    chunk = dist.dense_chunk(hi - lo + 1, ws) if ws > 1 else 0
+    table = ops.GroupTable.dense(lo, lo + ws * chunk - 1 if ws > 1 else hi, len(labels), flags)
     table.hint_skew(ops.keys_are_skewed(sampled, dup))
+    mine = None
     try:
         for key, vals in items:
             table.accumulate(key, vals)
-        if dist.is_distributed():
-            for arr, op in table.collective_arrays():
-                dist.all_reduce_inplace(arr, op)
-            table.window(*dist.dense_split(hi - lo + 1))
-        ng, overflow = table.ngroups()
+        if ws > 1:
+            # the reduce phase: rank r receives the merged accumulators of ITS key slice only (no keys move,
+            # no sort, no pivots) and emits it; the rank-ordered results are the reference's key-sorted frame
+            mine = table.reduce_scatter(chunk, dist.reduce_scatter, dist.rank())
+        emitter = mine if mine is not None else table
+        ng, overflow = emitter.ngroups()
         if overflow:
             raise _lib.B200Error("dense group table saw a key outside its measured range")
-        keys, sums, cnts, sizes = table.emit(ng, sort=False)
+        keys, sums, cnts, sizes = emitter.emit(ng, sort=False)
     finally:
         table.close()
+        if mine is not None:
+            mine.close()
     part = _partial_block(agg, keys, key_label, sums, cnts, sizes, labels)
     return reduce_fn._finalize(part.index_cols[0], list(part.cols), part.columns, key_label)
 

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .block import DeviceColumn, current_device, current_stream, torch_mod
+from .block import DeviceColumn, KeyStats, current_device, current_stream, torch_mod
 
 _scratch_cache = {}
 
@@ -184,6 +184,7 @@ class GroupTable:
         self.lib = _lib.load()
         self.handle = C.c_void_p()
         self.capacity = R = int(key_max) - int(key_min) + 1
+        self.kbase = int(key_min)
         self.nvals, self.flags = int(nvals), int(flags)
         # the arrays live in torch's allocator (layout: include/modin_b200.h) so that the multi-GPU
         # reduce can run NCCL collectives on them in place
@@ -202,10 +203,38 @@ class GroupTable:
         return self
 
     def collective_arrays(self):
-        """(tensor, reduce-op) pairs whose element-wise reduction over ranks merges dense tables."""
+        """(tensor, reduce-op, elements per key) triples whose element-wise reduction over ranks merges dense tables."""
         acc_op = "sum" if self.flags & _lib.GB_SUM else ("min" if self.flags & _lib.GB_MIN else "max")
-        out = [(self.acc, acc_op), (self.cnt, "sum"), (self.size, "sum"), (self.present, "max")]
-        return [(x, op) for x, op in out if x is not None]
+        vs = max(4, (self.nvals + 3) & ~3)
+        out = [(self.acc, acc_op, vs), (self.cnt, "sum", vs), (self.size, "sum", 1), (self.present, "max", 1)]
+        return [(x, op, per) for x, op, per in out if x is not None]
+
+    def reduce_scatter(self, chunk: int, reduce_scatter_fn, r: int):
+        """Cross-GPU reduce phase for dense keys: every array of this table (job-wide key range, padded to
+        ``ws * chunk`` keys) is reduce-scattered over the ranks -- rank ``r`` receives keys
+        ``[r * chunk, (r + 1) * chunk)`` fully merged -- and a table over just that slice is returned
+        (``mb200_gb_adopt_dense``; it inherits this table's overflow flag).  Half the traffic of an all_reduce,
+        and each rank counts and emits only what it owns."""
+        t = torch_mod()
+        if self.capacity % chunk or chunk % 4:
+            raise ValueError("dense table is not padded to equal, 4-key-aligned chunks")
+        sl = GroupTable.__new__(GroupTable)
+        sl.lib, sl.handle = self.lib, C.c_void_p()
+        sl.capacity, sl.nvals, sl.flags = int(chunk), self.nvals, self.flags
+        sl.kbase = self.kbase + r * chunk
+        sl.acc = sl.cnt = sl.size = sl.present = None
+        for name, (x, op, per) in zip(self._array_names(), self.collective_arrays()):
+            out = t.empty(chunk * per, dtype=x.dtype, device=x.device)
+            reduce_scatter_fn(out, x[: self.capacity * per], op)
+            setattr(sl, name, out)
+        ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
+        _lib.check(self.lib.mb200_gb_adopt_dense(C.byref(sl.handle), sl.kbase, sl.kbase + chunk - 1, sl.nvals,
+                                                 sl.flags, ptr(sl.acc), ptr(sl.cnt), ptr(sl.size), ptr(sl.present),
+                                                 self.handle, current_stream()))  # fmt: skip
+        return sl
+
+    def _array_names(self):
+        return [n for n in ("acc", "cnt", "size", "present") if getattr(self, n) is not None]
 
     def window(self, gid_lo: int, gid_hi: int):
         _lib.check(self.lib.mb200_gb_dense_window(self.handle, int(gid_lo), int(gid_hi)))
@@ -293,9 +322,39 @@ def key_range_device(key_cols: Sequence[DeviceColumn]):
     return mm
 
 
+_I64_MAX, _I64_MIN = (1 << 63) - 1, -(1 << 63)
+key_stats_passes = 0  # how many columns had to be scanned because nothing had left their statistics behind
+
+
+def key_stats(key_cols: Sequence[DeviceColumn]):
+    """Host ``(min, max, sampled, duplicated)`` over int64 key columns, from the columns' cached ``KeyStats``.
+    Columns without statistics are scanned once (``mb200_key_range``) and remember the result; all pending device
+    quadruples are read back in ONE D2H.  Steady state (statistics already on the host): no launch, no sync."""
+    global key_stats_passes
+    t = torch_mod()
+    for k in key_cols:
+        if k.dtype != np.int64:
+            raise TypeError("device groupby needs an int64 key column")
+        if k.stats is None:
+            if len(k):
+                key_stats_passes += 1
+                k.stats = KeyStats(dev=key_range_device([k]))
+            else:
+                k.stats = KeyStats(host=(_I64_MAX, _I64_MIN, 0, 0))
+    pending = [k.stats for k in key_cols if k.stats.pending() is not None]
+    if pending:
+        for st, vals in zip(pending, t.stack([st.pending() for st in pending]).tolist()):
+            st.resolve(vals)
+    lo, hi, sampled, dup = _I64_MAX, _I64_MIN, 0, 0
+    for k in key_cols:
+        a, b, s_, d_ = k.stats.host()
+        lo, hi, sampled, dup = min(lo, a), max(hi, b), sampled + s_, dup + d_
+    return lo, hi, sampled, dup
+
+
 def key_range(key_cols: Sequence[DeviceColumn]):
     """(min, max) over int64 key columns -- one streaming pass, one 16-byte D2H.  None when empty."""
-    lo, hi = (int(v) for v in key_range_device(key_cols).tolist()[:2])
+    lo, hi = key_stats(key_cols)[:2]
     return None if lo > hi else (lo, hi)
 
 
@@ -322,7 +381,7 @@ def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool 
     total_rows = sum(len(item[0]) for item in key_cols_vals)
     skewed = False
     if GroupbyDenseKeys.get() and total_rows > 0:
-        lo, hi, sampled, dup = (int(v) for v in key_range_device([item[0] for item in key_cols_vals]).tolist())
+        lo, hi, sampled, dup = key_stats([item[0] for item in key_cols_vals])
         kr = None if lo > hi else (lo, hi)
         skewed = not partial and keys_are_skewed(sampled, dup)
         if kr is not None and dense_range_ok(kr[0], kr[1], cap, total_rows, nvals, flags):
@@ -468,10 +527,14 @@ def gen_f64(nrows: int, seed: int, col: int, row_offset: int = 0, nan_per_64k: i
 
 
 def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0, skew: bool = False) -> DeviceColumn:
+    """Synthetic int64 column; the generator kernel also leaves the column's key statistics behind (KeyStats)."""
     lib = _lib.load()
+    t = torch_mod()
     c = DeviceColumn.empty(nrows, np.int64)
+    stats = t.empty(4, dtype=t.int64, device=current_device())
     fn = lib.mb200_gen_i64_skew if skew else lib.mb200_gen_i64
-    _lib.check(fn(c.ptr, nrows, seed, col, row_offset, modulus, current_stream()))
+    _lib.check(fn(c.ptr, nrows, seed, col, row_offset, modulus, stats.data_ptr(), current_stream()))
+    c.stats = KeyStats(dev=stats)
     return c
 
 

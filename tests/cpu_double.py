@@ -210,8 +210,21 @@ class GroupTable:
 
     def collective_arrays(self):
         acc_op = "sum" if self.flags & _lib.GB_SUM else ("min" if self.flags & _lib.GB_MIN else "max")
-        out = [(self.acc, acc_op), (self.cnt, "sum"), (self.size, "sum"), (self.present, "max")]
-        return [(x, op) for x, op in out if x is not None]
+        out = [(self.acc, acc_op, self.vs), (self.cnt, "sum", self.vs), (self.size, "sum", 1), (self.present, "max", 1)]
+        return [(x, op, per) for x, op, per in out if x is not None]
+
+    def reduce_scatter(self, chunk, reduce_scatter_fn, r):
+        assert self.R % chunk == 0 and chunk % 4 == 0
+        sl = GroupTable()
+        sl.kbase, sl.R, sl.nvals, sl.flags, sl.vs = self.kbase + r * chunk, chunk, self.nvals, self.flags, self.vs
+        sl.acc = sl.cnt = sl.size = None
+        sl.win = (0, chunk)
+        names = [n for n in ("acc", "cnt", "size", "present") if getattr(self, n) is not None]
+        for name, (x, op, per) in zip(names, self.collective_arrays()):
+            out = torch.empty(chunk * per, dtype=x.dtype)
+            reduce_scatter_fn(out, x[: self.R * per], op)
+            setattr(sl, name, out)
+        return sl
 
     def hint_skew(self, skewed):
         pass
@@ -325,7 +338,8 @@ def installed():
     ops.JoinTable, ops.take_columns, ops.compact_hits, ops.cast_columns_f64 = JoinTable, take_columns, compact_hits, \
         cast_columns_f64  # fmt: skip
     ops.gen_f64 = lambda n, seed, col, row_offset=0, nan_per_64k=0: _col(synth.gen_f64(n, seed, col, row_offset, nan_per_64k))
-    ops.gen_i64 = lambda n, seed, col, modulus, row_offset=0: _col(synth.gen_i64(n, seed, col, modulus, row_offset))
+    ops.gen_i64 = lambda n, seed, col, modulus, row_offset=0, skew=False: _col(
+        (synth.gen_i64_skew if skew else synth.gen_i64)(n, seed, col, modulus, row_offset))
     try:
         yield
     finally:

@@ -44,7 +44,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_binding_loads_and_reports_abi():
     lib = _lib.load()
-    assert lib.mb200_abi_version() == 1
+    assert lib.mb200_abi_version() == _lib.ABI_VERSION
     assert lib.mb200_launch_count() >= 0
     assert lib.mb200_reduce_scratch_bytes(8) > 0
     assert lib.mb200_sort_scratch_bytes(1000) >= 16000
