@@ -88,6 +88,10 @@ struct mb200_gb_table {
   int persisted;           // holds a reference on the persisting L2 carve-out (accumulators pinned)
   size_t carve_bytes, window_bytes;
   long long win_lo, win_hi;  // gid window that ngroups / emit report (default: the whole range)
+  // hashed tables: slots | acc | cnt | size live in ONE allocation so that one persisting-L2 access window
+  // can cover the probe slots AND the accumulators (a stream carries a single window)
+  void* arena;
+  size_t arena_bytes;
 };
 
 namespace mb200 {
@@ -1042,10 +1046,14 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   {
     const char* e = getenv("MB200_GB_PERSIST");
     const size_t acc_bytes = (size_t)t->gcap * t->vstride * 8;
-    const bool forced = e && e[0] == '2';
-    const bool want = t->dense ? (!(e && e[0] == '0') && (acc_bytes >= ((size_t)8 << 20) || forced))
-                               : ((e && e[0] == '1' && table_bytes * 2 > dp.l2_bytes) || forced);
-    if (want && t->acc) {
+    const bool off = e && e[0] == '0';
+    // dense: the accumulators are the table.  hashed: the whole arena (slots | acc | cnt | size) -- with more
+    // table than carve-out the window's hit ratio pins a random carve/arena share of its lines, which still turns
+    // most probe and RED misses into hits (the streamed input is evict-first and cannot displace pinned lines).
+    void* win_base = t->dense ? (void*)t->acc : t->arena;
+    const size_t win_bytes = t->dense ? acc_bytes : t->arena_bytes;
+    const bool want = !off && win_base && win_bytes >= ((size_t)8 << 20);
+    if (want) {
       if (!t->persisted) {  // one carve-out reference per table, dropped in mb200_gb_destroy
         size_t mw = 0;
         const size_t mp = l2_carveout_acquire(&mw);
@@ -1058,8 +1066,8 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
       if (t->persisted) {
         cudaStreamAttrValue v;
         memset(&v, 0, sizeof(v));
-        v.accessPolicyWindow.base_ptr = t->acc;
-        v.accessPolicyWindow.num_bytes = acc_bytes < t->window_bytes ? acc_bytes : t->window_bytes;
+        v.accessPolicyWindow.base_ptr = win_base;
+        v.accessPolicyWindow.num_bytes = win_bytes < t->window_bytes ? win_bytes : t->window_bytes;
         const double fit = (double)t->carve_bytes / (double)v.accessPolicyWindow.num_bytes;
         v.accessPolicyWindow.hitRatio = fit >= 1.0 ? 1.0f : (float)fit;
         v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -1274,13 +1282,31 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
     if (init_arrays) MB_TRY(cudaMemsetAsync(t->present, 0, (size_t)t->nwords * 4, st));
     MB_TRY(cudaMallocAsync((void**)&t->blockoff, (size_t)((t->nwords + 255) / 256 + 1) * 4, st));
   } else {
-    MB_TRY(cudaMallocAsync((void**)&t->slots, (size_t)t->cap * sizeof(Slot), st));
+    const size_t slot_b = ((size_t)t->cap * sizeof(Slot) + 255) & ~(size_t)255;
+    const size_t acc_b = (accb + 255) & ~(size_t)255;
+    const bool has_acc = flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX);
+    const size_t size_b = (((size_t)t->gcap * 8) + 255) & ~(size_t)255;
+    t->arena_bytes = slot_b + (has_acc ? acc_b : 0) + ((flags & MB200_GB_COUNT) ? acc_b : 0) +
+                     ((flags & MB200_GB_SIZE) ? size_b : 0);
+    MB_TRY(cudaMallocAsync(&t->arena, t->arena_bytes, st));
+    char* a = static_cast<char*>(t->arena);
+    t->slots = reinterpret_cast<Slot*>(a);
+    a += slot_b;
+    if (has_acc) {
+      t->acc = reinterpret_cast<double*>(a);
+      a += acc_b;
+    }
+    if (flags & MB200_GB_COUNT) {
+      t->cnt = reinterpret_cast<long long*>(a);
+      a += acc_b;
+    }
+    if (flags & MB200_GB_SIZE) t->size = reinterpret_cast<long long*>(a);
   }
   MB_TRY(cudaMallocAsync((void**)&t->meta, sizeof(GbMeta), st));
   if (!init_arrays) {
     // adopted arrays (mb200_gb_adopt_dense): already hold a merged table, nothing to initialise
   } else if (flags & MB200_GB_SUM) {
-    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
+    if (!t->borrowed && dense) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     if (dense) {  // -0.0: the one value no sum can end on (x + -0.0 = x, and sums start from +0.0 in the emit)
       gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
                                                                (long long)(accb / 8), (long long)0x8000000000000000ULL);
@@ -1290,7 +1316,7 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
       MB_TRY(cudaMemsetAsync(t->acc, 0, accb, st));
     }
   } else if (flags & (MB200_GB_MIN | MB200_GB_MAX)) {
-    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
+    if (!t->borrowed && dense) MB_TRY(cudaMallocAsync((void**)&t->acc, accb, st));
     // "no value yet": INT64_MAX = bytes ff..ff 7f for min is not a byte pattern; use the fill kernel
     gb_fill_kernel<<<(unsigned)dp.sm_count * 4, 256, 0, st>>>(reinterpret_cast<long long*>(t->acc),
                                                              (long long)(accb / 8),
@@ -1300,11 +1326,11 @@ static int gb_create_impl(mb200_gb_table** table, int64_t group_capacity, int nv
     g_launches.fetch_add(1);
   }
   if ((flags & MB200_GB_COUNT) && init_arrays) {
-    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
+    if (!t->borrowed && dense) MB_TRY(cudaMallocAsync((void**)&t->cnt, accb, st));
     MB_TRY(cudaMemsetAsync(t->cnt, 0, accb, st));
   }
   if ((flags & MB200_GB_SIZE) && init_arrays) {
-    if (!t->borrowed) MB_TRY(cudaMallocAsync((void**)&t->size, (size_t)t->gcap * 8, st));
+    if (!t->borrowed && dense) MB_TRY(cudaMallocAsync((void**)&t->size, (size_t)t->gcap * 8, st));
     MB_TRY(cudaMemsetAsync(t->size, 0, (size_t)t->gcap * 8, st));
   }
 #undef MB_TRY
@@ -1322,9 +1348,9 @@ bad:
 extern "C" int mb200_gb_destroy(mb200_gb_table* t, mb200_stream_t stream) {
   if (!t) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (t->slots) cudaFreeAsync(t->slots, st);
+  if (t->arena) cudaFreeAsync(t->arena, st);
   if (t->meta) cudaFreeAsync(t->meta, st);
-  if (!t->borrowed) {
+  if (!t->borrowed && !t->arena) {
     if (t->acc) cudaFreeAsync(t->acc, st);
     if (t->cnt) cudaFreeAsync(t->cnt, st);
     if (t->size) cudaFreeAsync(t->size, st);

@@ -380,11 +380,12 @@ def hash_aggregate(key_cols_vals, flags: int, capacity_hint: int, partial: bool 
     nvals = len(key_cols_vals[0][1]) if key_cols_vals[0][1] else 0
     total_rows = sum(len(item[0]) for item in key_cols_vals)
     skewed = False
-    if GroupbyDenseKeys.get() and total_rows > 0:
+    if total_rows > 0:
+        # key statistics are column metadata (KeyStats): free once known, one pass for a column of unknown origin
         lo, hi, sampled, dup = key_stats([item[0] for item in key_cols_vals])
         kr = None if lo > hi else (lo, hi)
         skewed = not partial and keys_are_skewed(sampled, dup)
-        if kr is not None and dense_range_ok(kr[0], kr[1], cap, total_rows, nvals, flags):
+        if GroupbyDenseKeys.get() and kr is not None and dense_range_ok(kr[0], kr[1], cap, total_rows, nvals, flags):
             table = GroupTable.dense(kr[0], kr[1], nvals, flags)
             table.hint_skew(skewed)
             try:
