@@ -373,7 +373,8 @@ class DeviceBlock:
         icols = [c.slice(start, stop) for c in self.index_cols] if self.index_cols else None
         ihost = self.index_host[start:stop] if self.index_host is not None else None
         return DeviceBlock(cols, self.columns, nrows=stop - start, range_start=self.range_start + start,
-                           index_cols=icols, index_names=self.index_names, index_host=ihost)  # fmt: skip
+                           index_cols=icols, index_names=self.index_names, index_host=ihost,
+                           replicated=self.replicated)  # fmt: skip
 
     @property
     def T(self) -> "DeviceBlock":

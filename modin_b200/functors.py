@@ -38,6 +38,17 @@ _BINARY_TO_FRAME = {
 _REFLECTED_FRAME = {"rsub": "sub", "rtruediv": "div"}
 
 
+def _spans_ranks(block) -> bool:
+    """True when ``block`` is this rank's part of a frame whose rows are sharded over several GPUs: the reduce phase
+    of a template then has to finish with a collective.  The reference gathers every block of the axis into ONE task
+    (axis_partition.py:445-452); here the other ranks hold the rest of the axis, so the reduce-phase functors issue
+    the collective themselves -- also when Modin's own templates call them through an opaque lambda
+    (``lambda y: reduce_function(y, *args, **kwargs)``, alg/tree_reduce.py:77-80)."""
+    from . import dist
+
+    return dist.is_distributed() and not getattr(block, "replicated", False)
+
+
 class DevFn:
     """Base of all device functors."""
 
@@ -623,6 +634,8 @@ class DevBoolReduce(DevFn):
         _check_block(block, f"DevBoolReduce({self.op})")
         if axis not in (0, "index", None):
             raise NotImplementedError("row-wise any / all is not on the B200 path")
+        if self.phase == "reduce" and _spans_ranks(block):
+            return self.run_distributed(block, *args, axis=axis, skipna=skipna, **kwargs)
         if not block.cols:
             return _reduced_block([], block.columns)
         vals, _ = ops.reduce_columns(self.kop, self._ints(block), skipna=True, variant=1)
@@ -726,6 +739,9 @@ class DevReduce(DevFn):
 
     def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
         self._check(block, axis, min_count)
+        if self.phase == "reduce" and _spans_ranks(block):
+            return self.run_distributed(block, *args, axis=axis, skipna=skipna, numeric_only=numeric_only,
+                                        min_count=min_count, **kwargs)  # fmt: skip
         if not block.cols:
             return _reduced_block([], block.columns)
         kop = self._kernel_op()
@@ -850,6 +866,8 @@ class DevMeanReduce(DevFn):
 
     def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
         _check_block(block, "DevMeanReduce")
+        if _spans_ranks(block):
+            return self.run_distributed(block, *args, axis=axis, skipna=skipna, **kwargs)
         return self._divide(*self._local(block))
 
     def run_distributed(self, block, *args, axis=0, skipna=True, **kwargs):
@@ -1029,6 +1047,8 @@ class DevGroupbyReduce(DevFn):
         return self._merge(keys, block.cols)
 
     def __call__(self, block, *args, partition_idx=0, **kwargs):
+        if _spans_ranks(block):
+            return self.run_distributed(block, *args, partition_idx=partition_idx, **kwargs)
         keys, key_label = self._unpack(block)
         k, cols = self._local_merge(block, keys)
         return self._finalize(k, cols, block.columns, key_label)

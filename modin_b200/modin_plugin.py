@@ -101,6 +101,12 @@ def register(shims: bool | None = None):
         _row_partition_class = bp.B200RowPartition
         _execution_wrapper = bp.B200Wrapper
 
+        @classmethod
+        def from_pandas(cls, df, return_dims=False):
+            """The frame (``B200OnModinDataframe.from_pandas``) cuts this rank's row shard itself, together with the
+            shard's row labels, so the partition manager must not cut again."""
+            return cls.from_pandas_local(df, return_dims)
+
     # ---------------------------------------------------------------- core dataframe
     class B200OnModinDataframe(PandasDataframe):
         _partition_mgr_cls = B200OnModinPartitionManager
@@ -112,6 +118,54 @@ def register(shims: bool | None = None):
         @property
         def storage_format(self) -> str:  # df.py:125-135
             return "Arrow"
+
+        # ---- one process per GPU: every rank holds its own row shard (labels included) ----------------------
+        @classmethod
+        def from_pandas(cls, df):
+            """df.py:4592-4620 pairs ``df.index`` with the partitions of ``df``; under torch.distributed the
+            partitions hold this rank's contiguous row shard only, so index, dtypes and row lengths are the
+            shard's (the same split ``B200Dataframe.from_pandas`` makes)."""
+            if bdist.is_distributed():
+                lo, hi = bdist.shard_bounds(len(df))
+                df = df.iloc[lo:hi]
+            return super().from_pandas(df)
+
+        @classmethod
+        def from_pandas_replicated(cls, df):
+            """A small host frame that every rank holds in full (reduction results computed on the host from
+            all-reduced numbers): no sharding, and ``to_pandas`` must not gather it again."""
+            frame = super().from_pandas(df)
+            for p in frame._partitions.flatten():
+                p.get().replicated = True
+            return frame
+
+        @classmethod
+        def from_arrow(cls, at):
+            """df.py:4622-4654.  Single process: Modin's own path (the partition manager copies the Arrow buffers
+            H2D directly).  Under torch.distributed the rows are sharded like ``from_pandas`` (zero-copy pandas
+            view of the table, then this rank's slice of it)."""
+            if not bdist.is_distributed():
+                return super().from_arrow(at)
+            cols = {}
+            for name, col in zip(at.column_names, at.columns):
+                arr = col.combine_chunks() if hasattr(col, "combine_chunks") else col
+                if arr.null_count:
+                    arr = arr.fill_null(float("nan"))
+                cols[name] = arr.to_numpy(zero_copy_only=False)
+            return cls.from_pandas(pandas.DataFrame(cols, copy=False))
+
+        def to_pandas(self):
+            """df.py:4691-4722.  Under torch.distributed the partition manager all-gathers the row shards (unless
+            the blocks are replicated results), so the host frame carries the JOB-wide rows while ``self.index``
+            is this rank's: labels come from the blocks, after the deferred external labels have been pushed
+            into them."""
+            if not bdist.is_distributed():
+                return super().to_pandas()
+            self._propagate_index_objs(axis=None)
+            df = self._partition_mgr_cls.to_pandas(self._partitions)
+            if len(df.columns) == 0 and len(self.columns):
+                df = pandas.DataFrame(columns=self.columns, index=df.index)
+            return df
 
         def _build_treereduce_func(self, axis, func):
             """df.py:2081-2123: device reduce functors already return the 1 x W block labelled
@@ -154,10 +208,9 @@ def register(shims: bool | None = None):
                     raise NotImplementedError("device groupby: one key column of the same frame, axis=0")
                 if not groupby_kwargs.get("as_index", True) or groupby_kwargs.get("level") is not None:
                     raise NotImplementedError("device groupby: as_index=True, no level=")
-                new_frame = query_compiler._modin_frame.groupby_reduce(
-                    axis, by._modin_frame, lambda df, other=None, **kw: map_f(df, other),
-                    lambda df, **kw: red_f(df, **kw),
-                )
+                # the functors themselves, not lambdas around them: the partition manager recognises them and fuses
+                # map + reduce into one direct-addressed table per GPU when the key range allows (pm.groupby_reduce)
+                new_frame = query_compiler._modin_frame.groupby_reduce(axis, by._modin_frame, map_f, red_f)
                 return query_compiler.__constructor__(new_frame)
 
             return caller
@@ -249,6 +302,8 @@ def register(shims: bool | None = None):
             """qc.py:2231-2270 -- what ``drop_duplicates`` (modin/pandas/base.py:1600-1623) and ``Series.unique``
             ask for.  One full-axis application of the device functor instead of duplicated() + row selection."""
             pos = fx.DevDropDuplicates.resolve(self.columns, subset, keep)
+            if bdist.is_distributed():  # every rank refuses together: a duplicate's first occurrence may live elsewhere
+                raise NotImplementedError("drop_duplicates / unique through the Modin plug-in is single-process")
             frame = self._modin_frame
             if frame._partitions.shape[1] != 1:
                 raise NotImplementedError("device drop_duplicates: frames of one column partition (up to 32 columns)")
@@ -281,10 +336,6 @@ def register(shims: bool | None = None):
             the answer is its number of groups.  The W counts go back as a 1 x W frame like the other reductions."""
             if axis != 0:
                 raise NotImplementedError("nunique(axis=1) is not on the B200 path")
-            if bdist.is_distributed():
-                # each rank would count only its own key range of the group table; the multi-GPU path is the
-                # standalone front door (modin_b200.pandas), the plug-in has not been run under torch.distributed
-                raise NotImplementedError("nunique through the Modin plug-in is single-process")
             bad = [c for c, dt in zip(self.columns, self.dtypes) if np.dtype(dt) != np.int64]
             if bad:
                 raise NotImplementedError(f"nunique on the B200 path counts int64 columns only (got {bad!r})")
@@ -292,11 +343,17 @@ def register(shims: bool | None = None):
             for label in self.columns:
                 key = self.getitem_column_array([label])
                 sizes = key.groupby_size(by=key, axis=0, groupby_kwargs={}, agg_args=(), agg_kwargs={})
-                counts.append(len(sizes.index))
+                counts.append(sum(sizes._modin_frame.row_lengths))  # across GPUs: this rank's key range of the table
+            if bdist.is_distributed():
+                import torch
+
+                t = torch.tensor(counts, dtype=torch.int64, device=self._modin_frame._partitions[0, 0].get().cols[0].data.device)
+                bdist.all_reduce_values([t], ["sum"])
+                counts = [int(v) for v in t.tolist()]
             from modin.utils import MODIN_UNNAMED_SERIES_LABEL
 
             host = pandas.DataFrame([counts], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.int64)
-            return self.from_pandas(host, type(self._modin_frame))
+            return self.__constructor__(type(self._modin_frame).from_pandas_replicated(host))
 
         def getitem_array(self, key):
             """qc.py:3072-3103.  A one-column bool query compiler is boolean row selection: the reference registers
@@ -369,7 +426,7 @@ def register(shims: bool | None = None):
                 out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
                 out = np.sqrt(out) if sqrt else out
             host = pandas.DataFrame([out], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.float64)
-            return self.from_pandas(host, type(self._modin_frame))
+            return self.__constructor__(type(self._modin_frame).from_pandas_replicated(host))
 
         def var(self, axis=0, **kwargs):  # qc.py:1152 (a Reduce over pandas.DataFrame.var in the reference)
             return self._var(False, axis, **kwargs)

@@ -641,6 +641,12 @@ class B200PartitionManager:
         if dist.is_distributed():
             lo, hi = dist.shard_bounds(len(df))
             df = df.iloc[lo:hi]
+        return cls.from_pandas_local(df, return_dims)
+
+    @classmethod
+    def from_pandas_local(cls, df, return_dims=False):
+        """The grid split + H2D of ``from_pandas`` for a frame that is already this rank's own (a shard cut by the
+        caller, or a small frame every rank holds in full)."""
         num_splits = NPartitions.get()
         row_chunksize = compute_chunksize(df.shape[0], num_splits, MinRowPartitionSize.get())
         col_chunksize = compute_chunksize(df.shape[1], num_splits, MinColumnPartitionSize.get())

@@ -312,6 +312,17 @@ class B200QueryCompiler:
         return self.__constructor__(_reset_row_index(new_frame))
 
 
+def _frame_device(frame):
+    """Device of the frame's first non-empty block (works for the mirror frame and for Modin's ``PandasDataframe``)."""
+    from .block import current_device
+
+    for p in frame._partitions.flatten():
+        b = p.get()
+        if b.cols:
+            return b.cols[0].data.device
+    return current_device()
+
+
 def _reset_row_index(frame: B200Dataframe) -> B200Dataframe:
     """``reset_index(drop=True)`` on range-indexed device blocks: renumber ``range_start`` so that
     the row partitions of this rank form one contiguous RangeIndex (metadata only, no kernel)."""
@@ -323,7 +334,7 @@ def _reset_row_index(frame: B200Dataframe) -> B200Dataframe:
     if dist.is_distributed():
         import torch
 
-        dev = frame._any_device()
+        dev = _frame_device(frame)
         mine = torch.zeros(dist.world_size(), dtype=torch.int64, device=dev)
         mine[dist.rank()] = sum(lengths)
         dist.all_reduce_values([mine], ["sum"])

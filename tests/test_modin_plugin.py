@@ -366,3 +366,111 @@ def test_hot_path_under_real_modin_on_b200(modin_b200_execution):
     before = lib.mb200_launch_count()
     _scenarios(mpd, ns)
     assert lib.mb200_launch_count() > before
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The plug-in under torch.distributed (one process per GPU; here 2 gloo ranks on the numpy device double): every
+# rank activates the execution, ingests ITS row shard of the same host frame through ``modin.pandas`` and runs the
+# hot path; results are compared with whole-frame pandas / the oracle.
+def _plugin_rank_job(rank, ws):
+    import sys
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import cpu_double
+    from modin_b200 import config, modin_plugin
+
+    out = {}
+    with cpu_double.installed():
+        ns = modin_plugin.activate()
+        import modin.config as cfg
+        import modin.pandas as mpd
+
+        cfg.NPartitions.put(2)
+        config.NPartitions.put(2)
+        pdf = synth.host_frame(2003, 4, seed=11, nan_per_64k=3000, key_modulus=23)
+        vals = pdf.drop(columns="key")
+        mdf, mfull = mpd.DataFrame(vals), mpd.DataFrame(pdf)
+        fr = mdf._query_compiler._modin_frame
+        assert type(fr) is ns.Dataframe
+        lo, hi = (rank * 2003) // ws, ((rank + 1) * 2003) // ws  # shard_bounds for an even-ish split
+        out["local_rows"] = (len(mdf), int(mdf.index[0]), int(mdf.index[-1]))
+        P = lambda x: x._to_pandas()  # noqa: E731
+        out["affine"] = P(mdf * 1.5 + 0.25)
+        out["abs"] = P(mdf.abs())
+        out["lt"] = P(mdf < 0.0)
+        other = mpd.DataFrame(synth.host_frame(2003, 4, seed=12))
+        out["fma3"] = P(mdf * other + other)
+        out["fillna_frame"] = P(mdf.fillna(other))
+        for name in ("sum", "mean", "count", "min", "max", "var", "std"):
+            out[name] = P(getattr(mdf, name)())
+        g = mfull.groupby("key")
+        for agg in ("sum", "count", "mean", "size", "min", "max"):
+            r = getattr(g, agg)()
+            out["gb_" + agg] = P(r)
+            out["gb_local_" + agg] = len(r)
+        rng = np.random.RandomState(1)
+        dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
+        out["merge_left"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="left"))
+        out["merge_inner"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="inner"))
+        out["filter"] = P(mdf[mdf["c0"] > 0.0])
+        out["dropna"] = P(mdf.dropna())
+        out["nunique"] = P(mfull[["key"]].nunique())
+        for what, call in (("drop_duplicates", lambda: mfull[["key"]].drop_duplicates()),
+                           ("sort_values", lambda: mfull.sort_values("key"))):  # fmt: skip
+            try:
+                call()
+                out["refused_" + what] = False
+            except NotImplementedError:
+                out["refused_" + what] = True
+    return out
+
+
+def test_plugin_under_two_gloo_ranks():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tools/dist_check.py covers the plug-in under NCCL")
+    from tests.test_dist_gloo import _run
+
+    outs = _run(_plugin_rank_job, ws=2)
+    pdf = synth.host_frame(2003, 4, seed=11, nan_per_64k=3000, key_modulus=23)
+    vals = pdf.drop(columns="key")
+    other = synth.host_frame(2003, 4, seed=12)
+    rows = [o["local_rows"] for o in outs]
+    assert sum(r[0] for r in rows) == 2003 and rows[0][1] == 0 and rows[1][2] == 2002 and rows[0][2] + 1 == rows[1][1]
+    rng = np.random.RandomState(1)
+    dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
+    for o in outs:  # every rank gathers the job-wide result
+        assert _same(o["affine"].to_numpy(), orc.a_mul_b_add_c(vals, 1.5, 0.25, 4).to_numpy())
+        assert list(o["affine"].index) == list(vals.index)
+        assert _same(o["abs"].to_numpy(), vals.abs().to_numpy())
+        assert _same(o["lt"].to_numpy().astype(float), (vals < 0.0).to_numpy().astype(float))
+        assert _same(o["fma3"].to_numpy(), orc.a_mul_b_add_c(vals, other, other, 4).to_numpy())
+        assert _same(o["fillna_frame"].to_numpy(), vals.fillna(other).to_numpy())
+        assert np.allclose(o["sum"].to_numpy(), vals.sum().to_numpy(), rtol=0, atol=1e-9)
+        assert np.allclose(o["mean"].to_numpy(), vals.mean().to_numpy(), rtol=0, atol=1e-12)
+        assert _same(o["count"].to_numpy(), vals.count().to_numpy())
+        assert _same(o["min"].to_numpy(), vals.min().to_numpy()) and _same(o["max"].to_numpy(), vals.max().to_numpy())
+        assert np.allclose(o["var"].to_numpy(), vals.var().to_numpy(), rtol=1e-12, atol=0)
+        assert np.allclose(o["std"].to_numpy(), vals.std().to_numpy(), rtol=1e-12, atol=0)
+        for agg in ("sum", "count", "mean", "size", "min", "max"):
+            want = orc.groupby_reduce(pdf, "key", agg, 4)
+            got = o["gb_" + agg]
+            assert list(got.index) == list(want.index), agg
+            assert np.allclose(np.asarray(got, dtype=np.float64).reshape(len(want), -1),
+                               np.asarray(want, dtype=np.float64).reshape(len(want), -1), rtol=0, atol=1e-9, equal_nan=True), agg  # fmt: skip
+        wl = orc.broadcast_merge(pdf, dim, "key", "left", 4)
+        assert list(o["merge_left"].columns) == list(wl.columns) and _same(o["merge_left"].to_numpy(), wl.to_numpy())
+        assert _same(o["merge_inner"].to_numpy(), orc.broadcast_merge(pdf, dim, "key", "inner", 4).to_numpy())
+        wf = vals[vals["c0"] > 0.0]
+        assert list(o["filter"].index) == list(wf.index) and _same(o["filter"].to_numpy(), wf.to_numpy())
+        wd = vals.dropna()
+        assert list(o["dropna"].index) == list(wd.index) and _same(o["dropna"].to_numpy(), wd.to_numpy())
+        assert int(np.asarray(o["nunique"]).ravel()[0]) == pdf["key"].nunique()
+        assert o["refused_drop_duplicates"] and o["refused_sort_values"]
+    # the group table is split by key range: both ranks own a part, together all 23 groups
+    assert sum(o["gb_local_sum"] for o in outs) == pdf["key"].nunique() and all(o["gb_local_sum"] > 0 for o in outs)

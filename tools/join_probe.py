@@ -37,7 +37,7 @@ def main():
     n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 28)
     nd = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, nd, st))
+    _lib.check(lib.mb200_gen_i64(keys.data_ptr(), n, 43, 0, 0, nd, None, st))
     rng = np.random.RandomState(5)
     dk = torch.from_numpy(rng.permutation(nd).astype(np.int64)).to(dev)
     pay = torch.randn(nd, dtype=torch.float64, device=dev)
