@@ -411,6 +411,37 @@ class DeviceBlock:
         return f"DeviceBlock(nrows={self.nrows}, columns={list(self.columns)!r})"
 
 
+class HostBlock:
+    """A pandas block that was NOT copied to the device at ingest (large float64 / int64 frames,
+    ``config.HostStreamMinBytes``).  Two things can happen to it: a fusable elementwise call queue followed by
+    ``to_pandas`` streams it through the device chunk by chunk (``mb200_map_host``: H2D / kernel / D2H overlapped on
+    three streams, the frame never resident as a whole -- partitioning.stream_to_pandas); anything else calls
+    ``materialize()`` first, which is the plain H2D ingest.  The host arrays are only read."""
+
+    __slots__ = ("frame", "nrows", "ncols", "_device")
+
+    def __init__(self, frame: pandas.DataFrame):
+        self.frame, self.nrows, self.ncols = frame, len(frame), frame.shape[1]
+        self._device = None  # the H2D copy, made once and shared by every partition derived from this block
+
+    @staticmethod
+    def eligible(df, min_bytes: int) -> bool:
+        if min_bytes <= 0 or not isinstance(df, pandas.DataFrame) or df.shape[1] == 0 or df.shape[1] > 32:
+            return False
+        if df.shape[0] * df.shape[1] * 8 < min_bytes:
+            return False
+        return all(dt in (np.dtype("float64"), np.dtype("int64")) for dt in df.dtypes)
+
+    def columns_numpy(self):
+        """Contiguous 1-D numpy views of the columns (no copy for frames built column by column)."""
+        return [np.ascontiguousarray(self.frame.iloc[:, j].to_numpy()) for j in range(self.ncols)]
+
+    def materialize(self) -> "DeviceBlock":
+        if self._device is None:
+            self._device = DeviceBlock.from_pandas(self.frame)
+        return self._device
+
+
 def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
     """Row-wise concatenation of blocks with identical columns (pandas.concat in
     deploy_axis_func, axpart.py:445-452) -- a D2D copy into fresh column buffers."""

@@ -95,9 +95,20 @@ class ReduceVariant(Parameter):
     default = 0
 
 
+class HostStreamMinBytes(Parameter):
+    """Host frames whose blocks are at least this large stay on the HOST at ingest (``HostBlock``): a fusable
+    elementwise call queue followed by ``to_pandas`` is then streamed chunk by chunk through the device
+    (``mb200_map_host``: H2D / kernel / D2H overlapped), and anything else copies the block to the device first.
+    0 disables (every ingest is an immediate H2D copy)."""
+
+    varname = "MB200_HOST_STREAM_MIN_BYTES"
+    default = 64 << 20
+
+
 class GroupbyDenseKeys(Parameter):
     """Use a direct-addressed (dense) group table when the key range is narrow (default on);
-    off = always hash.  The decision costs one 8 B/row min/max pre-pass over the key column."""
+    off = always hash.  The choice reads the key column's cached statistics (``KeyStats``: left behind by the kernel
+    that produced the column; one 8 B/row pass, once, for a column of unknown origin)."""
 
     varname = "MB200_GB_DENSE"
     default = True

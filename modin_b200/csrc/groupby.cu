@@ -43,6 +43,18 @@
 // (cp.reduce.async.bulk .add.f64 / UBLKRED) 34.7 G rows/s -- no gain, dropped; L2 eviction-priority
 // hints on the table accesses and L2 prefetch of the next tile's probe slots -- no gain either.
 // Fresh table per pass (what a real groupby pays): 30 G rows/s at G = 1e6, 39 G rows/s at G = 65536.
+//
+// Round 2 (same shape; profiles/r02_summary.md):
+//   * hashed table, persisting-L2 window over the whole arena (slots | sums, hit ratio = carve-out / arena): DRAM
+//     traffic 17.8 -> 13.8 GB per 9.66 GB of input, time unchanged (4.60 ms) -- kept, it is free;
+//   * hashed table, first probe bucket of the NEXT tile loaded one tile ahead into registers (+14 registers): 4.58 ->
+//     4.50 ms, and the HOT variant of the same kernel lost 12 % to the register pressure -- removed.  ncu on the hash
+//     kernel: 555 warp-instructions per 32 rows at 45 % issue utilisation, 8.6 warps per issue slot waiting on the
+//     bucket load, DRAM 37 % busy with 32-byte random sectors: neither latency nor bandwidth alone, a 96 MB random
+//     footprint against a 126 MB L2 that also has 9.7 GB streaming through it;
+//   * HOT variant, rows of a cached group that owns several of a warp's 32 rows summed per column before the
+//     shared-memory atomic (quarter warp per group): 5.34 -> 6.23 ms -- the extra match / ballot / shuffle work costs
+//     more than the CAS retries it saves -- removed.
 #include "common.cuh"
 
 namespace mb200 {
@@ -127,8 +139,7 @@ struct GbParams {
   long long kbase;
   unsigned int* present;  // dense: one byte per key of [kbase, kbase + gcap)
   int policy_mode;  // unused (kept for experiments)
-  int prefetch;     // TMA kernel, hashed tables: load the next tile's first probe buckets one tile ahead
-  int hot_combine;  // HOT kernel: pre-combine the rows of multi-row cached groups per warp (MB200_GB_HOT_COMBINE=0 disables)
+  int prefetch;     // TMA kernel: L2-prefetch the next tile's probe slots (MB200_GB_PREFETCH=0 disables)
 };
 
 // ---- table accesses: relaxed GPU-scope.  L2 eviction-priority hints on these (evict_last / evict_normal
@@ -333,34 +344,6 @@ __device__ __forceinline__ int resolve_gid(const GbParams& p, long long k, uint6
   return __shfl_sync(0xffffffffu, gid, leader);
 }
 
-// Probe-ahead form (TMA kernel, hashed tables): the first bucket of every lane's key was loaded one tile EARLIER
-// (k0/g0/k1/g1), so its DRAM / L2 latency overlapped the previous tile's accumulate phase instead of sitting at the
-// head of this tile's dependency chain (ncu, round 2: 8.6 warps stalled on that load per issue slot, DRAM at 37 %).
-// Slots never change once published, so a stale bucket can only say "not there yet": those leaders re-probe with a
-// fresh load (and insert if the key really is new) exactly as resolve_gid does.
-__device__ __forceinline__ int resolve_gid_pre(const GbParams& p, long long k, unsigned int bucket, long long k0, int g0,
-                                               long long k1, int g1) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
-  const int leader = __ffs(peers) - 1;
-  const bool is_leader = (lane == leader);
-  int gid = -1;
-  bool chain = false;  // both slots of the first bucket hold other keys: the chain goes on
-  if (g0 >= 0 && k0 == k) gid = g0;
-  else if (g0 >= 0) {
-    if (g1 >= 0 && k1 == k) gid = g1;
-    else if (g1 >= 0) chain = true;
-  }
-  const bool need = is_leader && gid < 0;
-  if (__any_sync(0xffffffffu, need)) {
-    unsigned int b = chain ? ((bucket + 1) & (p.mask >> 1)) : bucket;
-    const int found = probe_find(p, k, need, b);
-    if (need) gid = found;
-    if (__any_sync(0xffffffffu, is_leader && gid < 0)) gid = insert_rounds(p, k, is_leader, gid, b);
-  }
-  return __shfl_sync(0xffffffffu, gid, leader);
-}
-
 // ---------------------------------------------------------------- fallback: direct loads
 template <int VARIANT, bool PARTIAL>
 __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __grid_constant__ GbParams p) {
@@ -529,44 +512,22 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
   // ---------------- consumers: warp w owns rows [32w, 32w + 32) of every tile
   const uint64_t keep = table_policy(p.policy_mode);
   const int c = lane & 7;
-  const bool ahead = !p.dense && p.prefetch;  // hashed table: probe one tile ahead (MB200_GB_PROBE_AHEAD=0 disables)
-  const unsigned int bmask = p.mask >> 1;
-  long long key = 0, a_k0 = 0, a_k1 = 0;
-  int a_g0 = -1, a_g1 = -1;
-  unsigned int a_bucket = 0;
-  if (nmine > 0) {
-    mbar_wait(&full[0], 0u);
-    key = reinterpret_cast<const long long*>(smem_raw)[warp * 32 + lane];
-    if (ahead) {
-      a_bucket = hash_key(key) & bmask;
-      ld_bucket(p.slots + 2 * (size_t)a_bucket, a_k0, a_g0, a_k1, a_g1);
-    }
-  }
   for (long long k = 0; k < nmine; ++k) {
     const int s = (int)(k % kGbStages);
     mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
     const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
-    // the next tile's keys are (normally) already in shared memory: issue the first probe load of each of this
-    // warp's next 32 rows NOW, so that it is in flight during this tile's accumulate phase
-    long long nkey = 0, n_k0 = 0, n_k1 = 0;
-    int n_g0 = -1, n_g1 = -1;
-    unsigned int n_bucket = 0;
-    if (k + 1 < nmine) {
+    const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
+    if (p.prefetch && k + 1 < nmine) {
+      // the next tile's keys are (normally) already in shared memory: pull the first probe slot of each of
+      // this warp's next 32 rows into L2 now, one tile ahead of the dependent 128-bit slot load
       const int s1 = (int)((k + 1) % kGbStages);
       mbar_wait(&full[s1], (uint32_t)(((k + 1) / kGbStages) & 1));
-      nkey = reinterpret_cast<const long long*>(smem_raw + (size_t)s1 * kStageBytes)[warp * 32 + lane];
-      if (ahead) {
-        n_bucket = hash_key(nkey) & bmask;
-        ld_bucket(p.slots + 2 * (size_t)n_bucket, n_k0, n_g0, n_k1, n_g1);
-      }
+      const long long nk =
+          reinterpret_cast<const long long*>(smem_raw + (size_t)s1 * kStageBytes)[warp * 32 + lane];
+      const Slot* ns = &p.slots[hash_key(nk) & p.mask];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ns));
     }
-    int gid = ahead ? resolve_gid_pre(p, key, a_bucket, a_k0, a_g0, a_k1, a_g1) : resolve_gid(p, key, keep);
-    key = nkey;
-    a_bucket = n_bucket;
-    a_k0 = n_k0;
-    a_g0 = n_g0;
-    a_k1 = n_k1;
-    a_g1 = n_g1;
+    int gid = resolve_gid(p, key, keep);
     if ((p.flags & MB200_GB_SIZE) && gid < gcap) red_add_u64(p.size + gid, 1LL, keep);
     if (HOT && gid < gcap) {  // is this row's group in the CTA's hot cache (or can it claim its slot)?
       const int slot = gid & (kHotSlots - 1);
@@ -578,46 +539,6 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
       if (tag == gid) gid |= kHotBit;
     }
     const double* vt = stage + kTileColStride + warp * 32;  // value column 0, this warp's rows
-    unsigned int combined = 0;  // HOT: rows of this warp tile whose updates were pre-combined below
-    if (HOT && p.hot_combine) {
-      // Cached groups that own SEVERAL of this warp's 32 rows (under Zipf-like keys ~9 of 32 rows sit in ~3 such
-      // groups, the hottest key alone in 4-5) are summed per column BEFORE they touch shared memory: 64-bit
-      // shared-memory atomics are CAS loops, and every row of a hot key spins on the same 8 words.  Each quarter
-      // warp takes one such group per round: lane c of the quarter adds up column c over the group's rows straight
-      // from the tile and issues ONE atomic for them.
-      const unsigned int hp = __match_any_sync(0xffffffffu, gid);
-      const bool multi = (gid & kHotBit) && __popc(hp) >= 2;
-      combined = __ballot_sync(0xffffffffu, multi);
-      unsigned int leaders = __ballot_sync(0xffffffffu, multi && lane == __ffs(hp) - 1);
-      while (leaders) {  // warp-uniform
-        int L = -1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (leaders) {
-            if (i == (lane >> 3)) L = __ffs(leaders) - 1;
-            leaders &= leaders - 1;
-          }
-        }
-        const unsigned int P = __shfl_sync(0xffffffffu, hp, L < 0 ? 0 : L);
-        const int g = __shfl_sync(0xffffffffu, gid, L < 0 ? 0 : L) & ~kHotBit;
-        if (L >= 0 && c < nv) {
-          double acc = 0.0;
-          unsigned int n = 0;
-          for (unsigned int m = P; m; m &= m - 1) {
-            const double xv = vt[c * kTileColStride + (__ffs(m) - 1)];
-            if (xv == xv) {
-              acc += xv;
-              ++n;
-            }
-          }
-          if (n) {
-            const int o = (g & (kHotSlots - 1)) * kHotStride + c;
-            if (p.flags & MB200_GB_SUM) atomicAdd(&s_hot[o], acc);
-            if (p.flags & MB200_GB_COUNT) atomicAdd(&s_hcnt[o], n);
-          }
-        }
-      }
-    }
     unsigned int seen = 0;  // bit kk: this lane's (row 4 kk + lane / 8, column c) update leaves a trace
     int gs[8];
 #pragma unroll
@@ -629,7 +550,7 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
       if (c < nv && g < gcap) {
         const double xv = vt[c * kTileColStride + r];
         if (dense_visible(p, xv)) seen |= 1u << kk;
-        if (xv == xv && !(HOT && ((combined >> r) & 1u))) {
+        if (xv == xv) {
           if (HOT && (pg & kHotBit)) {
             const int o = (g & (kHotSlots - 1)) * kHotStride + c;
             if (p.flags & MB200_GB_SUM) atomicAdd(&s_hot[o], xv);
@@ -1106,10 +1027,8 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   {
     const char* e = getenv("MB200_GB_POLICY");  // none | last | normal
     p.policy_mode = (e && e[0] == 'l') ? 1 : ((e && e[0] == 'n' && e[1] == 'o' && e[2] == 'r') ? 2 : ((e && e[0] == 'u') ? 3 : 0));
-    const char* hc = getenv("MB200_GB_HOT_COMBINE");
-    p.hot_combine = (hc && hc[0] == '0') ? 0 : 1;
-    const char* pf = getenv("MB200_GB_PROBE_AHEAD");
-    p.prefetch = (pf && pf[0] == '0') ? 0 : 1;  // hashed tables: first probe load issued one tile ahead
+    const char* pf = getenv("MB200_GB_PREFETCH");
+    p.prefetch = (pf && pf[0] == '1') ? 1 : 0;  // measured: no gain (the limiter is random-sector DRAM traffic)
   }
   const size_t table_bytes = (size_t)t->cap * sizeof(Slot) + (size_t)t->gcap * t->vstride * 8 *
                                                                   (((t->flags & (MB200_GB_SUM | MB200_GB_MIN | MB200_GB_MAX)) ? 1 : 0) +

@@ -507,6 +507,30 @@ def register(shims: bool | None = None):
     return ns
 
 
+def from_device_blocks(blocks):
+    """``modin.pandas.DataFrame`` over device blocks that already sit in this rank's HBM, one row partition per block
+    -- the from_map-style ingest (modin/core/io/io.py:184-209; what
+    ``modin.distributed.dataframe.pandas.from_partitions`` does for Ray object refs, partitions.py:154-264): no host
+    frame is built and nothing is copied.  Blocks must share their column labels and carry RangeIndex labels that
+    run on from each other (``synth.device_blocks``)."""
+    ns = register()
+    import modin.pandas as mpd
+
+    blocks = list(blocks)
+    if not blocks:
+        raise ValueError("from_device_blocks needs at least one block")
+    for b in blocks:
+        if not b.has_range_index() or list(b.columns) != list(blocks[0].columns):
+            raise NotImplementedError("from_device_blocks: range-indexed blocks with identical columns")
+    pc = ns.PartitionManager._partition_class
+    parts = np.array([[pc.put(b)] for b in blocks], dtype=object).reshape(len(blocks), 1)
+    start = blocks[0].range_start
+    index = pandas.RangeIndex(start, start + sum(b.nrows for b in blocks))
+    frame = ns.Dataframe(parts, index, blocks[0].columns, [b.nrows for b in blocks], [len(blocks[0].cols)],
+                         dtypes=blocks[0].dtypes)  # fmt: skip
+    return mpd.DataFrame(query_compiler=ns.QueryCompiler(frame))
+
+
 def activate():
     """``register()`` + ``modin.set_execution(engine="B200", storage_format="Arrow")``."""
     ns = register()

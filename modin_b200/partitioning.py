@@ -23,8 +23,8 @@ import numpy as np
 import pandas
 
 from . import dist
-from .block import DeviceBlock, concat_cols, concat_rows, torch_mod
-from .config import BenchmarkMode, MinColumnPartitionSize, MinRowPartitionSize, NPartitions
+from .block import DeviceBlock, HostBlock, concat_cols, concat_rows, torch_mod
+from .config import BenchmarkMode, HostStreamMinBytes, MinColumnPartitionSize, MinRowPartitionSize, NPartitions
 from .functors import DevAffine, DevBinary, DevFma3, DevFn, DevGroupbyMap, DevGroupbyReduce, fused_dense_groupby
 
 
@@ -63,9 +63,20 @@ class Bound:
 
 
 def unwrap(func):
-    """(functor, bound_args, bound_kwargs) of a possibly Bound callable."""
+    """(functor, bound_args, bound_kwargs) of a possibly Bound callable.
+
+    Modin's own templates hand the partition manager closures, not functors: the Binary template wraps the
+    registered function as ``lambda x, y: func(x, y, *args, **kwargs)`` (alg/binary.py:421).  When such a closure's
+    free variables are exactly a device functor plus its ``args`` / ``kwargs``, it is read back into the same
+    (functor, args, kwargs) triple, so that the call queue can still fuse ``a * b`` with the ``+ c`` that follows
+    under the real ``modin.pandas``."""
     if isinstance(func, Bound):
         return func.fn, func.args, func.kwargs
+    code, cells = getattr(func, "__code__", None), getattr(func, "__closure__", None)
+    if code is not None and cells and code.co_name == "<lambda>" and set(code.co_freevars) == {"func", "args", "kwargs"}:
+        free = {name: cell.cell_contents for name, cell in zip(code.co_freevars, cells)}
+        if isinstance(free["func"], DevFn) and code.co_argcount == 2 and isinstance(free["args"], tuple):
+            return free["func"], free["args"], dict(free["kwargs"])
     return func, (), {}
 
 
@@ -182,6 +193,73 @@ def _run_queue(data, queue):
     return data
 
 
+# ------------------------------------------------------------------ host-resident blocks: streamed execution
+def _streamable_step(queue):
+    """``(op, s0, s1)`` when the (fused) call queue of a host-resident partition is ONE elementwise sweep that
+    ``mb200_map_host`` can stream -- ``x * s + t`` (AFFINE), ``abs`` / ``neg``, or one arithmetic op against a scalar
+    or row vector -- over float64 columns; else None.  ``s0`` / ``s1`` are scalars or per-column lists."""
+    from .functors import DevMap
+
+    fused = fuse_call_queue(queue)
+    if len(fused) != 1:
+        return None
+    func, args, kwargs = fused[0]
+    fn, bargs, bkw = unwrap(func)
+    if isinstance(fn, DevAffine) and not args and not bargs:
+        return "affine", fn.mul, fn.add
+    if isinstance(fn, DevMap) and fn.op in ("abs", "neg") and not args and not bargs:
+        return fn.op, None, None
+    sc = _scalar_operand(fused[0])
+    if sc is not None:
+        op = {"add": "add_s", "radd": "add_s", "mul": "mul_s", "rmul": "mul_s", "sub": "sub_s", "rsub": "rsub_s",
+              "truediv": "div_s", "rtruediv": "rdiv_s"}.get(sc[0])  # fmt: skip
+        if op is not None:
+            return op, sc[1], None
+    return None
+
+
+def stream_to_pandas(row_partitions):
+    """``to_pandas`` of row partitions that still live on the host (``HostBlock``) and carry a streamable call queue:
+    every block is pushed through the device in chunks (H2D copy, one fused sweep, D2H copy, overlapped on three
+    streams by ``mb200_map_host``) straight into the columns of the result frame -- pinned buffers from the pool, so
+    both copies run as plain DMA.  Returns None when the partitions do not qualify (the caller then takes the
+    device-resident path).  This is what ``pd.DataFrame(host) * b + c -> to_pandas()`` costs end to end."""
+    from . import _lib, hostpath
+
+    if not row_partitions or dist.is_distributed():
+        return None
+    steps = []
+    for p in row_partitions:
+        if not isinstance(p._data, HostBlock) or not p.call_queue:
+            return None
+        st = _streamable_step(p.call_queue)
+        if st is None:
+            return None
+        steps.append(st)
+    first = row_partitions[0]._data
+    W = first.ncols
+    if any(p._data.ncols != W or list(p._data.frame.columns) != list(first.frame.columns) for p in row_partitions):
+        return None
+    if any(dt != np.dtype("float64") for p in row_partitions for dt in p._data.frame.dtypes):
+        return None  # int64 columns would need pandas' promotion rules per op: device-resident path
+    total = sum(p._data.nrows for p in row_partitions)
+    out = [hostpath.pinned_array(total, np.float64) for _ in range(W)]
+    pos = 0
+    for p, (op, s0, s1) in zip(row_partitions, steps):
+        n = p._data.nrows
+        vec = lambda v: None if v is None else ([float(x) for x in v] if isinstance(v, (list, tuple, np.ndarray)) else [float(v)] * W)  # noqa: E731
+        a, b = vec(s0), vec(s1)
+        if (a is not None and len(a) != W) or (b is not None and len(b) != W):
+            return None
+        if n:
+            hostpath.stream_map(op, _lib.F64, p._data.columns_numpy(), [o[pos : pos + n] for o in out], s0=a, s1=b)
+        pos += n
+    index = row_partitions[0]._data.frame.index
+    for p in row_partitions[1:]:
+        index = index.append(p._data.frame.index)
+    return pandas.DataFrame(dict(zip(range(W), out)), index=index, copy=False).set_axis(first.frame.columns, axis=1)
+
+
 # ------------------------------------------------------------------ block partition
 class B200Partition:
     """One block partition holding a DeviceBlock (immutable value semantics)."""
@@ -199,21 +277,27 @@ class B200Partition:
         return type(self)
 
     # -- execution -------------------------------------------------------------------------------
+    def _on_device(self):
+        """The payload as a DeviceBlock: a block left on the host at ingest (HostBlock) is copied H2D now."""
+        if isinstance(self._data, HostBlock):
+            self._data = self._data.materialize()
+        return self._data
+
     def get(self):
         self.drain_call_queue()
-        return self._data
+        return self._on_device()
 
     @property
     def list_of_blocks(self):
         self.drain_call_queue()
-        return [self._data]
+        return [self._on_device()]
 
     def apply(self, func: Callable, *args, **kwargs):
         """Run the call queue, then ``func`` (pandas_on_python/partitioning/partition.py:76-123);
         no defensive copies: blocks are immutable and device functors never write in place."""
         queue = self.call_queue + [[func, args, kwargs]]
         try:
-            data = _run_queue(self._data, queue)
+            data = _run_queue(self._on_device(), queue)
         except Exception:
             raise
         return self.__constructor__(data)
@@ -228,7 +312,7 @@ class B200Partition:
             return
         queue, self.call_queue = self.call_queue, []
         try:
-            self._data = _run_queue(self._data, queue)
+            self._data = _run_queue(self._on_device(), queue)
         except Exception:
             self.call_queue = []  # reference clears the queue on failure (partition.py:111-116)
             raise
@@ -244,6 +328,11 @@ class B200Partition:
         """pandas.DataFrame -> device partition (H2D); a DeviceBlock is wrapped as is."""
         if isinstance(obj, DeviceBlock):
             return cls(obj, length=obj.nrows, width=len(obj.cols))
+        if HostBlock.eligible(obj, HostStreamMinBytes.get()) and not dist.is_distributed():
+            from .block import current_device
+
+            current_device()  # no device, no ingest: fail here like the eager H2D path would
+            return cls(HostBlock(obj), length=len(obj), width=obj.shape[1])
         block = DeviceBlock.from_pandas(obj)
         return cls(block, length=block.nrows, width=len(block.cols))
 
@@ -258,17 +347,20 @@ class B200Partition:
     # -- metadata --------------------------------------------------------------------------------
     def length(self, materialize=True):
         if self._length_cache is None:
-            self._length_cache = self.get().nrows
+            self._length_cache = self._data.nrows if isinstance(self._data, HostBlock) and not self.call_queue \
+                else self.get().nrows  # fmt: skip
         return self._length_cache
 
     def width(self, materialize=True):
         if self._width_cache is None:
-            self._width_cache = len(self.get().cols)
+            self._width_cache = self._data.ncols if isinstance(self._data, HostBlock) and not self.call_queue \
+                else len(self.get().cols)  # fmt: skip
         return self._width_cache
 
     # -- egress / structure ----------------------------------------------------------------------
     def to_pandas(self):
-        return self.get().to_pandas()
+        streamed = stream_to_pandas([self])
+        return streamed if streamed is not None else self.get().to_pandas()
 
     def to_numpy(self, **kwargs):
         return self.get().to_numpy()
@@ -690,6 +782,10 @@ class B200PartitionManager:
     def to_pandas(cls, partitions):
         """pm.py:989-1005: D2H every block and assemble the host frame (all ranks' shards when
         distributed)."""
+        if len(partitions) and np.asarray(partitions).shape[1] == 1:
+            streamed = stream_to_pandas([row[0] for row in partitions])
+            if streamed is not None:
+                return streamed
         rows = []
         for row in partitions:
             blocks = [p.get() for p in row]
