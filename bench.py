@@ -4,28 +4,39 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's arm
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): Map / Binary template, ``a * b + c`` over a synthetic
-1e9-row x 8-column float64 frame (``a`` device resident, ``b``, ``c`` scalars -> one fused AFFINE
-sweep, two IEEE roundings), issued through the public API (``modin_b200.pandas``: ``df * b + c``
-then ``execute()``).  N > 1 (torchrun, one rank per GPU, NCCL): the SAME 1e9 rows are sharded
-row-wise over the ranks ("strong" scaling, as the north-star's ">= 6x at 8 GPUs" is phrased); the
-map path needs no collective.
+Front door: the REAL ``modin.pandas`` with this repo's execution plugged in (``modin_b200.modin_plugin``;
+Modin itself comes from ``baseline/_ref``, pip-installed from the read-only reference) -- ``config.api`` says so.
+``--api mirror`` (and the automatic fallback when Modin is not importable) uses the repo's own Modin-free mirror
+of the same class protocol, ``modin_b200.pandas``.
 
-One JSON line on rank 0.  ``value`` = rows/s with inputs resident in HBM; ``e2e`` = rows/s through
-the host-buffer entry point (pinned host in -> H2D -> kernel -> D2H -> pinned host out, all inside
-the timed region); ``roofline`` = algorithmic bytes / kernel time against MEASURED_PEAKS.json;
-``cpu_baseline`` = the oracle port of the reference path on this box's host cores (bounded sample);
-``also`` = the other hot-path templates (TreeReduce sum, GroupByReduce sum) measured the same way.
+Workload of the headline (BASELINE.json configs[1]): Map / Binary template, ``a * b + c`` over a synthetic
+1e9-row x 8-column float64 frame (``a`` device resident, ``b``, ``c`` scalars -> one fused AFFINE sweep, two
+IEEE roundings).  N > 1 (torchrun, one rank per GPU, NCCL): the SAME 1e9 rows are sharded row-wise over the
+ranks ("strong" scaling, as the north-star's ">= 6x at 8 GPUs" is phrased).
 
-``--impl reference`` times the reference's CPU implementation of the path (oracle port of
-Modin-on-pandas: same partition grid logic, pandas per block, all host threads) on a bounded
-sample of the same workload; rank 0 only.
+One JSON line on rank 0:
+  value            rows/s, inputs resident in HBM (CUDA events, max over ranks)
+  roofline         algorithmic bytes / launch time against MEASURED_PEAKS.json (map kernel)
+  roofline_groupby the same for ``groupby('key').sum()`` (BASELINE.json's other half of the metric)
+  e2e              rows/s through the public API with HOST buffers: ``pd.DataFrame(host) * b + c -> _to_pandas()``
+                   (pinned host in, H2D, kernel, D2H, pinned host out, all inside the timed call)
+  e2e_groupby      ``pd.DataFrame(host).groupby('key').sum()._to_pandas()`` the same way (72 B/row H2D, result D2H)
+  cpu_baseline     the reference's own CPU path on this box's host cores (bounded sample)
+  also             the other hot-path templates measured the same way (C3 sum / mean at 16 columns, three-frame
+                   a*b+c, groupby on dense / hashed / skewed keys, broadcast merge)
+  every leg carries ``checked`` (its result was verified OUTSIDE the timed region); N > 1 adds ``parity_ok``
+  (the hot path checked against pandas on a small job-wide frame over the NCCL group before anything is timed).
+
+``--impl reference`` times the UNMODIFIED reference (``modin.pandas`` from ``baseline/_ref``, its own
+PandasOnPython engine -- PandasOnRay when ``ray`` is importable) on a bounded sample of the same workload; rank 0
+only.
 """
 
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -35,10 +46,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "baseline", "_ref")
 
 METRIC = "rows/sec elementwise map (a*b+c) on 1e9x8 f64"
 UNIT = "rows/s"
 B_SCALAR, C_SCALAR = 1.000000119, 0.5
+EPS = 2.0**-53
 
 
 def parse_args():
@@ -47,11 +60,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--api", default="auto", choices=["auto", "modin", "mirror"])
     ap.add_argument("--rows", type=float, default=1e9, help="global rows of the synthetic frame")
     ap.add_argument("--cols", type=int, default=8)
     ap.add_argument("--groups", type=int, default=1_000_000)
-    ap.add_argument("--cpu-rows", type=float, default=2e7, help="rows of the bounded CPU sample")
-    ap.add_argument("--e2e-rows", type=float, default=1e8, help="rows of the host-buffer e2e sample")
+    ap.add_argument("--cpu-rows", type=float, default=0, help="rows of the bounded CPU sample (0 = sized to a time budget)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the reference arm's map leg may take")
+    ap.add_argument("--e2e-rows", type=float, default=1e8, help="rows of the host-buffer e2e sample (all ranks together)")
     ap.add_argument("--skip-also", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -69,49 +84,21 @@ def measured_peaks():
 
 
 def traffic_for(kernel: str, rows_local: int = 0):
-    """DRAM bytes per launch of `kernel`, from the committed `ncu --set full` capture
-    (profiles/traffic.json, taken at 2^27 rows) scaled linearly to this run's local row count;
-    None when no capture exists for the kernel."""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+    """DRAM bytes per launch of `kernel`, from the committed `ncu --set full` capture (profiles/traffic.json, taken at
+    2^27 rows) scaled linearly to this run's local row count; None when no capture exists for the kernel."""
     try:
-        t = json.load(open(path))
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         ent = t.get(kernel)
-        if not ent:
-            return None
-        return float(ent["dram_bytes"]) * (rows_local / float(t["rows"]))
+        return float(ent["dram_bytes"]) * (rows_local / float(t["rows"])) if ent else None
     except Exception:
         return None
 
 
-# ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_pass(rows: int, cols: int, threads: int):
-    """One pass of the reference path (oracle port) over `rows` x `cols`: returns seconds."""
-    from modin_b200 import synth
-    from oracle import reference_path as orc
-
-    pdf = synth.host_frame(rows, cols, seed=42)
-    t0 = time.perf_counter()
-    out = orc.a_mul_b_add_c(pdf, B_SCALAR, C_SCALAR, npartitions=threads, threads=threads)
-    dt = time.perf_counter() - t0
-    assert out.shape == pdf.shape
-    return dt
+def modin_importable() -> bool:
+    return os.path.isdir(os.path.join(REF, "modin"))
 
 
-def best_thread_count(cols: int) -> int:
-    """The reference uses one partition per core (NPartitions = CpuCount, envvars.py:837-885).  On a
-    128-core host the port's per-partition overhead can make fewer workers faster, so the CPU arm is
-    not sandbagged: a quick scan picks the fastest worker count and reports it as `cores`."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 16), min(ncpu, 8)}, reverse=True)
-    best, best_t = ncpu, float("inf")
-    for th in cands:
-        cpu_reference_pass(2_000_000, cols, th)
-        t = min(cpu_reference_pass(2_000_000, cols, th) for _ in range(2))
-        if t < best_t:
-            best, best_t = th, t
-    return best
-
-
+# ------------------------------------------------------------------------------------ reference arm (CPU)
 _MALLOC_ENV = {
     # keep big numpy buffers inside the heap and never trim it: without this every pandas temporary is a
     # fresh mmap whose first touch page-faults, which would sandbag the CPU arm by 2-10x
@@ -121,6 +108,28 @@ _MALLOC_ENV = {
 }
 
 
+def _reference_modin():
+    """``modin.pandas`` of the UNMODIFIED reference (baseline/_ref) on its own CPU engine; (module, engine name)."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from modin_b200.modin_plugin import apply_pandas3_shims
+
+    apply_pandas3_shims()  # the image ships pandas 3; the reference pins < 2.4 (SURVEY 8c: five removed names)
+    engine = "python"
+    try:
+        import ray  # noqa: F401
+
+        engine = "ray"
+    except Exception:
+        pass
+    os.environ["MODIN_ENGINE"] = engine
+    import modin.config as cfg
+    import modin.pandas as mpd
+
+    cfg.Engine.put(engine.capitalize() if engine != "python" else "Python")
+    return mpd, ("PandasOnRay" if engine == "ray" else "PandasOnPython"), int(cfg.NPartitions.get())
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -128,23 +137,84 @@ def run_reference_arm(args):
     if os.environ.get("MB200_REF_CHILD") != "1":
         env = dict(os.environ, MB200_REF_CHILD="1", **_MALLOC_ENV)
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
-    threads = best_thread_count(args.cols)
-    rows = int(args.cpu_rows)
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from modin_b200 import synth
+
+    ncpu = os.cpu_count() or 1
+    if not modin_importable():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/modin is not installed on this box"}), flush=True)
+        return
+    mpd, engine, nparts = _reference_modin()
+    cores = 1 if engine == "PandasOnPython" else ncpu
+    W = args.cols
+
+    def modin_map_pass(mdf):
+        t0 = time.perf_counter()
+        out = mdf * B_SCALAR + C_SCALAR
+        out._query_compiler.execute()
+        dt = time.perf_counter() - t0
+        assert out.shape == mdf.shape
+        return dt
+
+    # size the sample to the time budget: probe at 2e7 rows (large enough that every pandas temporary is a fresh
+    # mmap, as at the real size), then scale
+    probe_n = 20_000_000
+    probe = mpd.DataFrame(synth.host_frame(probe_n, W, seed=42))
+    probe._query_compiler.execute()
+    modin_map_pass(probe)
+    rate = probe_n / modin_map_pass(probe)
+    del probe
+    total_steps = args.steps + max(args.warmup, 1)
+    rows = int(args.cpu_rows) if args.cpu_rows else int(min(1e8, max(1e7, rate * args.cpu_budget / total_steps)))
+    pdf = synth.host_frame(rows, W, seed=42)
+    mdf = mpd.DataFrame(pdf)
+    mdf._query_compiler.execute()
     for _ in range(max(args.warmup, 1)):
-        cpu_reference_pass(rows, args.cols, threads)
-    times = [cpu_reference_pass(rows, args.cols, threads) for _ in range(args.steps)]
+        modin_map_pass(mdf)
+    times = [modin_map_pass(mdf) for _ in range(args.steps)]
     ms = statistics.mean(times) * 1e3
     value = rows / (ms / 1e3)
+    # alongside: plain pandas on the same frame (one core), and the groupby half of the metric on a smaller sample
+    t0 = time.perf_counter()
+    _ = pdf * B_SCALAR + C_SCALAR
+    pandas_map = rows / (time.perf_counter() - t0)
+    del _, mdf, pdf
+    grows = int(min(rows, 1e7))
+    gpdf = synth.host_frame(grows, W, seed=42, key_modulus=args.groups)
+    gm = mpd.DataFrame(gpdf)
+    gm._query_compiler.execute()
+
+    def modin_gb_pass():
+        t0 = time.perf_counter()
+        r = gm.groupby("key").sum()
+        r._query_compiler.execute()
+        return time.perf_counter() - t0, r
+
+    modin_gb_pass()
+    gdt, gres = modin_gb_pass()
+    t0 = time.perf_counter()
+    pres = gpdf.groupby("key").sum()
+    pandas_gb = grows / (time.perf_counter() - t0)
+    gb_checked = bool(len(gres) == len(pres))
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"map_partitions elementwise a*b+c, {rows}x{args.cols} f64 sample per step "
-                               "(reference path: Modin partition grid + pandas per block, two passes)",
-                   "npartitions": threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows} rows x {args.cols} cols per step, {args.steps} steps"},
+        "config": {"workload": f"map_partitions elementwise a*b+c (b,c scalars) on {int(args.rows)}x{W} f64 -- reference "
+                               f"arm: a {rows}x{W} sample of it per step",
+                   "rows": int(args.rows), "cols": W, "sample_rows": rows,
+                   "api": f"modin.pandas ({engine}, unmodified reference from baseline/_ref, pandas-3 import shims)",
+                   "npartitions": nparts},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "engine": engine,
+                         "host_cores": ncpu,
+                         "sample": f"{rows} rows x {W} cols per step, {args.steps} steps",
+                         "alongside": {"plain_pandas_1core_rows_s": pandas_map,
+                                       "groupby_sum": {"rows": grows, "groups": args.groups,
+                                                       "modin_rows_s": grows / gdt, "plain_pandas_rows_s": pandas_gb,
+                                                       "checked": gb_checked}}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
@@ -200,14 +270,138 @@ class ClockSampler:
             for name, val in zip(names, r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the median over samples taken while the GPU was actually clocked up (idle samples sit at the floor)
+        busy = [v for v in sm if mx and v >= 0.5 * max(mx)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(rows)}  # fmt: skip
 
 
+class Api:
+    """The front door the legs are driven through: real ``modin.pandas`` with the B200 execution plugged in, or the
+    repo's Modin-free mirror.  Both hand out pandas-style frames with ``_query_compiler`` / ``_to_pandas()``."""
+
+    def __init__(self, which: str):
+        from modin_b200 import synth
+
+        self.synth = synth
+        if which == "auto":
+            which = "modin" if modin_importable() else "mirror"
+        self.which = which
+        if which == "modin":
+            if REF not in sys.path:
+                sys.path.insert(0, REF)
+            import warnings
+
+            warnings.filterwarnings("ignore")
+            from modin_b200 import modin_plugin
+
+            self.plugin = modin_plugin
+            modin_plugin.activate()
+            import modin.config as cfg
+            import modin.pandas as mpd
+
+            cfg.NPartitions.put(1)
+            self.pd = mpd
+            self.name = "modin.pandas (ArrowOnB200: real Modin from baseline/_ref + modin_b200.modin_plugin)"
+        else:
+            import modin_b200.pandas as bpd
+
+            self.pd = bpd
+            self.name = "modin_b200.pandas (Modin-free mirror of the class protocol)"
+
+    def device_frame(self, rows, W, **kw):
+        """This rank's shard of the synthetic frame, generated in HBM (from_map-style ingest: no host frame)."""
+        if self.which == "modin":
+            return self.plugin.from_device_blocks(self.synth.device_blocks(rows, W, npartitions=1, **kw))
+        return self.synth.device_frame(rows, W, npartitions=1, **kw)
+
+    @staticmethod
+    def execute(obj):
+        qc = getattr(obj, "_query_compiler", None)
+        if qc is not None:
+            qc.execute()
+        return obj
+
+    @staticmethod
+    def to_pandas(obj):
+        return obj._to_pandas() if hasattr(obj, "_to_pandas") else obj
+
+    @staticmethod
+    def blocks(obj):
+        """This rank's device blocks of a frame, one per row partition (first column partition)."""
+        return [row[0].get() for row in obj._query_compiler._modin_frame._partitions]
+
+
+def _bits_equal(a, b):
+    import numpy as np
+
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def _sum_close(got, want, abs_sum, n):
+    import numpy as np
+
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    tol = 4.0 * max(1.0, math.log2(max(n, 2))) * EPS * np.asarray(abs_sum, dtype=np.float64) + 1e-300
+    return got.shape == want.shape and bool((np.abs(got - want) <= tol).all())
+
+
+def parity_over_ranks(api: Api):
+    """The hot path on a small JOB-WIDE frame (every rank ingests its shard of the same seeded host frame), gathered
+    and compared with pandas on the whole frame: bit-exact for elementwise / count / min / max / keys / merge, the
+    stated sum tolerance for sums and means.  Returns (ok, failed check names).  Runs before anything is timed."""
+    import numpy as np
+    import pandas
+
+    from modin_b200 import config as _cfg
+    from modin_b200 import synth
+
+    fails = []
+
+    def check(name, ok):
+        if not ok:
+            fails.append(name)
+
+    n, W, G = 100_003, 4, 2_003
+    pdf = synth.host_frame(n, W, seed=42, nan_per_64k=700, key_modulus=G)
+    vals = pdf.drop(columns="key")
+    P = api.to_pandas
+    df, dv = api.pd.DataFrame(pdf), api.pd.DataFrame(vals)
+    check("map abs", _bits_equal(P(dv.abs()).to_numpy(), vals.abs().to_numpy()))
+    check("fused a*b+c", _bits_equal(P(dv * 1.25 + 0.5).to_numpy(), (vals * 1.25 + 0.5).to_numpy()))
+    abs_sum = np.nansum(np.abs(vals.to_numpy()), axis=0)
+    check("tree_reduce sum", _sum_close(np.asarray(P(dv.sum())), vals.sum().to_numpy(), abs_sum, n))
+    check("tree_reduce count", np.array_equal(np.asarray(P(dv.count())), vals.count().to_numpy()))
+    check("tree_reduce min", _bits_equal(np.asarray(P(dv.min())), vals.min().to_numpy()))
+    check("tree_reduce mean", _sum_close(np.asarray(P(dv.mean())), vals.mean().to_numpy(),
+                                         abs_sum / np.maximum(vals.count().to_numpy(), 1), n))  # fmt: skip
+    gabs = vals.abs().groupby(pdf["key"]).sum().to_numpy()
+    want = pdf.groupby("key").sum()
+    for dense in (True, False):
+        _cfg.GroupbyDenseKeys.put(dense)
+        tag = "dense" if dense else "hash"
+        got = P(df.groupby("key").sum())
+        check(f"groupby[{tag}] keys", np.array_equal(got.index.to_numpy(), want.index.to_numpy()))
+        check(f"groupby[{tag}] sum", got.shape == want.shape and _sum_close(got.to_numpy(), want.to_numpy(), gabs, n))
+        check(f"groupby[{tag}] count", np.array_equal(P(df.groupby("key").count()).to_numpy(), pdf.groupby("key").count().to_numpy()))
+    _cfg.GroupbyDenseKeys.put(True)
+    rng = np.random.RandomState(5)
+    dim = pandas.DataFrame({"key": rng.permutation(G).astype(np.int64)[: int(G * 0.9)]})
+    dim["d0"] = synth.gen_f64(len(dim), 11, 0)
+    left = P(df.merge(api.pd.DataFrame(dim), on="key", how="left"))
+    wl = pdf.merge(dim, on="key", how="left")
+    check("merge left", list(left.columns) == list(wl.columns) and _bits_equal(left.to_numpy(dtype=np.float64), wl.to_numpy(dtype=np.float64)))
+    return (not fails), fails
+
+
 def run_b200_arm(args):
+    import numpy as np
+    import pandas
     import torch
 
     from modin_b200 import _lib, dist, synth
+    from modin_b200 import config as _cfg
     from modin_b200.config import NPartitions
 
     if not torch.cuda.is_available():
@@ -220,8 +414,9 @@ def run_b200_arm(args):
     _lib.check(lib.mb200_device_check(local))
     NPartitions.put(1)
     hbm_peak, peak_src = measured_peaks()
+    api = Api(args.api)
 
-    rows, W = int(args.rows), args.cols
+    rows, W, G = int(args.rows), args.cols, args.groups
     lo, hi = dist.shard_bounds(rows)
     rows_local = hi - lo
 
@@ -237,6 +432,13 @@ def run_b200_arm(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
+
+    def all_ranks_ok(ok: bool) -> bool:
+        if not distributed:
+            return bool(ok)
+        t = torch.tensor([0 if ok else 1], dtype=torch.int64, device="cuda")
+        torch.distributed.all_reduce(t)
+        return int(t.item()) == 0
 
     def timed(step_fn, steps, warmup):
         """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the launching
@@ -255,23 +457,45 @@ def run_b200_arm(args):
         sync_all()
         return max_over_ranks(total), per
 
+    def roof(kernel, bytes_per_launch_local, per_ms, traffic=None, **extra):
+        ach = bytes_per_launch_local / (statistics.mean(per_ms) / 1e3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch_local, "launch_ms": statistics.mean(per_ms), **extra}  # fmt: skip
+
+    def sample_rows(n):
+        return sorted({0, 1, min(4095, n - 1), min(4096, n - 1), n // 2, n - 1}) if n > 0 else []
+
+    def device_values(col, idx):
+        return col.data[torch.tensor(idx, dtype=torch.int64, device=col.data.device)].cpu().numpy()
+
+    # ---- multi-GPU parity before anything is timed ------------------------------------------------
+    parity_ok, parity_fails = None, []
+    if distributed:
+        try:
+            ok, parity_fails = parity_over_ranks(api)
+        except Exception as exc:  # a crash is a failed check, on every rank
+            ok, parity_fails = False, [f"{type(exc).__name__}: {exc}"[:300]]
+        parity_ok = all_ranks_ok(ok)
+
     # ---- headline: fused a*b+c through the public API ---------------------------------------
-    a = synth.device_frame(rows, W, seed=42, npartitions=1)  # this rank's shard, generated in HBM
-    a.execute()
+    a = api.device_frame(rows, W, seed=42)
+    api.execute(a)
+    last = [None]
 
     def step_map():
         out = a * B_SCALAR + C_SCALAR  # Binary template x2 -> call queue -> one AFFINE sweep
-        out.execute()
-        del out
+        api.execute(out)
+        last[0] = out
 
     sampler = ClockSampler(local)
-    launches0 = lib.mb200_launch_count()
     if rank == 0:
         sampler.start()
+    step_map()
+    launches0 = lib.mb200_launch_count()
     total_ms, per = timed(step_map, args.steps, args.warmup)
+    launches = lib.mb200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    launches = lib.mb200_launch_count() - launches0 - 0
-    # launches counted over warmup+timed; keep only the timed share
     launches_timed = round(launches * args.steps / max(args.steps + args.warmup, 1))
     if distributed:
         t = torch.tensor([launches_timed], dtype=torch.int64, device="cuda")
@@ -279,126 +503,165 @@ def run_b200_arm(args):
         launches_timed = int(t.item())
     ms_per_step = total_ms / args.steps
     value = rows / (ms_per_step / 1e3)
-    alg_bytes_local = rows_local * W * 16
-    kernel_ms = statistics.mean(per)
-    achieved = alg_bytes_local / (kernel_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "map_kernel<AFFINE,f64> (256-bit column sweep)",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic_for("map_affine", rows_local), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_local, "launch_ms": kernel_ms}  # fmt: skip
+    roofline = roof("map_kernel<AFFINE,f64> (256-bit column sweep)", rows_local * W * 16, per,
+                    traffic_for("map_affine", rows_local))  # fmt: skip
+    # check (outside the timed region): sampled rows against the numpy twin of the generator, bit for bit
+    blk = api.blocks(last[0])[0]
+    idx = sample_rows(blk.nrows)
+    ok = blk.nrows == rows_local
+    for j in (0, W - 1):
+        ref = np.array([synth.gen_f64(1, 42, j, lo + r)[0] for r in idx]) * B_SCALAR + C_SCALAR
+        ok = ok and _bits_equal(device_values(blk.cols[j], idx), ref)
+    map_checked = all_ranks_ok(ok)
+    last[0] = None
 
     also = []
+    roofline_groupby = None
 
     def _secondary_legs():
-        nonlocal a
-        # ---- TreeReduce: df.sum() over this frame (C3 uses 16 columns: two sweeps of 8 are one launch each)
-        def step_sum():
-            s = a.sum()
-            return s
+        nonlocal a, roofline_groupby
+        ksteps = max(3, args.steps // 2)
+        cols8 = [f"c{j}" for j in range(W)]
+        # sums of the headline frame with the direct-load reduce kernel: the cross-check value for the TMA kernel below
+        _cfg.ReduceVariant.put(1)
+        sum8_ldg = np.asarray(api.to_pandas(a.sum()), dtype=np.float64)
+        _cfg.ReduceVariant.put(0)
+        abs8 = np.asarray(api.to_pandas(a.abs().sum()), dtype=np.float64)
+        a = None
+        torch.cuda.empty_cache()
 
-        total_s, per_s = timed(step_sum, max(3, args.steps // 2), 2)
-        ms_s = total_s / max(3, args.steps // 2)
-        ach = rows_local * W * 8 / (statistics.mean(per_s) / 1e3) / 1e9
-        also.append({"metric": "rows/sec TreeReduce df.sum() on 1e9x8 f64 (incl. result D2H)", "value": rows / (ms_s / 1e3),
-                     "unit": UNIT, "ms_per_step": ms_s,
-                     "roofline": {"bound": "hbm", "kernel": "reduce_tma_kernel<SUM,f64>", "achieved": ach,
-                                  "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                  "traffic": traffic_for("reduce_sum", rows_local)}})  # fmt: skip
+        # ---- TreeReduce (C3): df.sum() / df.mean() over 16 float64 columns.  1e9 x 16 f64 = 128 GB: the whole frame
+        # on one 180 GB B200, 16 GB per GPU at 8
+        W3 = 16
+        c3 = api.device_frame(rows, W3, seed=42)
+        api.execute(c3)
+        res = {}
+
+        def step_sum():
+            res["sum"] = api.execute(c3.sum())
+
+        def step_mean():
+            res["mean"] = api.execute(c3.mean())
+
+        for name, fn in (("sum", step_sum), ("mean", step_mean)):
+            total_s, per_s = timed(fn, ksteps, 2)
+            got = np.asarray(api.to_pandas(res[name]), dtype=np.float64)
+            if name == "sum":
+                sum16 = got
+                ok = _sum_close(got[:W], sum8_ldg, abs8, rows)  # same first 8 columns, other reduce kernel
+            else:
+                ok = _sum_close(got, sum16 / rows, np.concatenate([abs8, abs8])[:W3] / rows + np.abs(sum16) / rows, rows)
+            also.append({"metric": f"rows/sec TreeReduce df.{name}() on 1e9x16 f64 (C3; result stays on the device)",
+                         "value": rows / (total_s / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_s / ksteps,
+                         "checked": bool(ok),
+                         "roofline": roof("reduce_tma_kernel<SUM,f64> + reduce_finalize" + (" (+ count, divide)" if name == "mean" else ""),
+                                          rows_local * W3 * 8, per_s, traffic_for("reduce_sum", rows_local * 2))})  # fmt: skip
+        del c3, res
+        torch.cuda.empty_cache()
+
         # ---- Binary template on three frames: a*b+c with b, c frames (C2 secondary form; 256 B/row fused).
         # Four n x 8 frames are resident, so n = rows/4 (2.5e8 per 1e9: 64 GB on one GPU)
-        del a
-        torch.cuda.empty_cache()
         rows3 = max(rows // 4, 1024)
-        fa, fb, fc = (synth.device_frame(rows3, W, seed=s, npartitions=1) for s in (42, 44, 45))
+        lo3, _hi3 = dist.shard_bounds(rows3)
+        fa, fb, fc = (api.device_frame(rows3, W, seed=s) for s in (42, 44, 45))
         for f in (fa, fb, fc):
-            f.execute()
+            api.execute(f)
 
         def step_fma3():
             out = fa * fb + fc  # two n_ary_op calls -> call queue -> one FMA3 sweep (two roundings)
-            out.execute()
-            del out
+            api.execute(out)
+            last[0] = out
 
-        fsteps = max(3, args.steps // 2)
-        total_f, per_f = timed(step_fma3, fsteps, 2)
-        ms_f = total_f / fsteps
-        ach = (rows3 // ws) * W * 32 / (statistics.mean(per_f) / 1e3) / 1e9
+        total_f, per_f = timed(step_fma3, ksteps, 2)
+        blk = api.blocks(last[0])[0]
+        idx = sample_rows(blk.nrows)
+        j = W - 1
+        ref = (np.array([synth.gen_f64(1, 42, j, lo3 + r)[0] for r in idx]) * np.array([synth.gen_f64(1, 44, j, lo3 + r)[0] for r in idx])
+               + np.array([synth.gen_f64(1, 45, j, lo3 + r)[0] for r in idx]))  # fmt: skip
+        ok = all_ranks_ok(_bits_equal(device_values(blk.cols[j], idx), ref))
+        last[0] = None
         also.append({"metric": f"rows/sec a*b+c on three frames ({rows3}x8 f64 each), Binary template x2 fused",
-                     "value": rows3 / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f,
-                     "roofline": {"bound": "hbm", "kernel": "map_kernel<FMA3,f64>", "achieved": ach, "peak": hbm_peak,
-                                  "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None}})  # fmt: skip
-        del fa, fb, fc
+                     "value": rows3 / (total_f / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_f / ksteps, "checked": ok,
+                     "roofline": roof("map_kernel<FMA3,f64>", blk.nrows * W * 32, per_f)})  # fmt: skip
+        del fa, fb, fc, blk
         torch.cuda.empty_cache()
-        # ---- GroupByReduce: groupby('key').sum(), G = 1e6 int64 keys, 8 float64 values (C4)
-        g = synth.device_frame(rows, W, seed=42, key_modulus=args.groups, npartitions=1)
-        g.execute()
-        ngroups = [0]
 
-        def step_gb():
-            r = g.groupby("key").sum()
-            r.execute()
-            ngroups[0] = len(r)
-            del r
-
-        from modin_b200 import config as _cfg
-
-        ksteps = max(3, args.steps // 2)
-        # default engine behaviour: one 8 B/row key min/max pre-pass (inside the timed step) picks the dense
-        # (direct-addressed) table because the synthetic keys span [0, G); then the same query with the hash
-        # table forced -- what keys spread over a wide range get
-        for dense_on, label, kern in (
-            (True, "", "key_range_kernel + gb_accumulate_tma_kernel on a dense (direct-addressed) table"),
-            (False, " [hash table forced]", "gb_accumulate_tma_kernel (open-addressed hash aggregate)"),
-        ):
+        # ---- GroupByReduce: groupby('key').sum(), G int64 keys, 8 float64 values (C4)
+        def groupby_leg(skew, dense_on, label, kern, traffic_key):
+            nonlocal roofline_groupby
+            g = api.device_frame(rows, W, seed=42, key_modulus=G, key_skew=skew)
+            api.execute(g)
             _cfg.GroupbyDenseKeys.put(dense_on)
-            total_g, per_g = timed(step_gb, ksteps, 2)
-            ms_g = total_g / ksteps
-            ach = rows_local * (8 + 8 * W) / (statistics.mean(per_g) / 1e3) / 1e9
-            also.append({"metric": f"rows/sec groupby('key').sum() 1e9 rows, 1e6 int64 keys, 8 f64 vals{label}",
-                         "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
-                         "roofline": {"bound": "hbm", "kernel": kern,
-                                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                      "traffic": traffic_for("groupby_sum" if not dense_on else "groupby_sum_dense",
-                                                             rows_local)}})  # fmt: skip
-        _cfg.GroupbyDenseKeys.put(True)
-        del g
-        torch.cuda.empty_cache()
-        # ---- the same query on SKEWED keys (Zipf-like, SURVEY 8d: key 0 takes ~11 % of the rows): the pre-pass flags
-        # the skew and the accumulate kernel keeps a per-CTA cache of hot groups in shared memory
-        g = synth.device_frame(rows, W, seed=42, key_modulus=args.groups, npartitions=1, key_skew=True)
-        g.execute()
-        total_g, per_g = timed(step_gb, ksteps, 2)
-        ms_g = total_g / ksteps
-        ach = rows_local * (8 + 8 * W) / (statistics.mean(per_g) / 1e3) / 1e9
-        also.append({"metric": "rows/sec groupby('key').sum() 1e9 rows, 1e6 int64 keys SKEWED (Zipf-like), 8 f64 vals",
-                     "value": rows / (ms_g / 1e3), "unit": UNIT, "ms_per_step": ms_g, "groups_local": ngroups[0],
-                     "roofline": {"bound": "hbm", "kernel": "key_range_kernel + gb_accumulate_tma_kernel<HOT> (dense table, "
-                                  "per-CTA hot-group cache)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                  "frac": ach / hbm_peak, "traffic": None}})  # fmt: skip
-        del g
-        torch.cuda.empty_cache()
+
+            def step_gb():
+                last[0] = api.execute(g.groupby("key").sum())
+
+            try:
+                total_g, per_g = timed(step_gb, ksteps, 2)
+                # ---- checks, outside the timed region
+                res = api.to_pandas(last[0])  # gathers every rank's key range: G x 8 (72 MB at G = 1e6)
+                last[0] = None
+                vals = g[cols8]
+                col_sum = np.asarray(api.to_pandas(vals.sum()), dtype=np.float64)
+                col_abs = np.asarray(api.to_pandas(vals.abs().sum()), dtype=np.float64)
+                keys = res.index.to_numpy()
+                ok = bool(len(keys) > 0 and (np.diff(keys) > 0).all() and keys[0] >= 0 and keys[-1] < G)
+                if not skew:
+                    ok = ok and len(keys) == min(G, rows)  # 1e9 uniform rows over 1e6 keys: every key occurs
+                ok = ok and _sum_close(res.to_numpy().sum(axis=0), col_sum, col_abs, rows)
+                # sampled groups against an independent device path: boolean row selection + TreeReduce
+                for k in ([0, int(keys[len(keys) // 2]), int(keys[-1])] if len(keys) else []):
+                    sel = g[g["key"] == k][cols8]
+                    want = np.asarray(api.to_pandas(sel.sum()), dtype=np.float64)
+                    wabs = np.asarray(api.to_pandas(sel.abs().sum()), dtype=np.float64)
+                    pos = int(np.searchsorted(keys, k))
+                    ok = ok and pos < len(keys) and keys[pos] == k and _sum_close(res.to_numpy()[pos], want, wabs, rows)
+                ok = all_ranks_ok(ok)
+            finally:
+                _cfg.GroupbyDenseKeys.put(True)
+            rf = roof(kern, rows_local * (8 + 8 * W), per_g, traffic_for(traffic_key, rows_local) if traffic_key else None)
+            entry = {"metric": f"rows/sec groupby('key').sum() {rows} rows, {G} int64 keys{label}, 8 f64 vals",
+                     "value": rows / (total_g / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_g / ksteps,
+                     "groups": int(len(keys)), "checked": ok, "roofline": rf}  # fmt: skip
+            also.append(entry)
+            if not skew and dense_on:
+                roofline_groupby = dict(rf, value=entry["value"], ms_per_step=entry["ms_per_step"], checked=ok,
+                                        note="key range and skew flag come from statistics the generator kernel left "
+                                             "on the key column (column metadata): no pre-pass over the keys")  # fmt: skip
+            del g
+            torch.cuda.empty_cache()
+
+        groupby_leg(False, True, "", "gb_accumulate_tma_kernel on a dense (direct-addressed) table pinned in L2", "groupby_sum_dense")
+        groupby_leg(False, False, " [hash table forced]", "gb_accumulate_tma_kernel (open-addressed hash aggregate)", "groupby_sum")
+        groupby_leg(True, True, " SKEWED (Zipf-like)", "gb_accumulate_tma_kernel<HOT> (dense table, per-CTA hot-group cache)", None)
+        # what a key column of UNKNOWN origin pays once: the 8 B/row statistics pass (mb200_key_range)
+        from modin_b200 import ops as _ops
+
+        kc = _ops.gen_i64(min(rows_local, 1 << 28), 43, 0, G, lo)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _ops.key_range_device([kc])
+        e0.record()
+        _ops.key_range_device([kc])
+        e1.record()
+        torch.cuda.synchronize()
+        if roofline_groupby is not None:
+            roofline_groupby["key_stats_pass_ms_per_1e9_rows_unknown_column"] = e0.elapsed_time(e1) * (1e9 / len(kc))
+        del kc
+
         # ---- broadcast merge: fact (rows x (key + 8 f64)) LEFT JOIN dim (1e7 x (key + 1 f64)) on int64 key (C5)
-        import numpy as np
-        import pandas
-
-        import modin_b200.pandas as bpd
-
         ndim = int(min(10_000_000, max(1000, rows // 100)))
-        fact = synth.device_frame(rows, W, seed=42, key_modulus=ndim, npartitions=1)
-        fact.execute()
+        fact = api.device_frame(rows, W, seed=42, key_modulus=ndim)
+        api.execute(fact)
         rng = np.random.RandomState(5)
-        dim_host = pandas.DataFrame({"key": rng.permutation(ndim).astype(np.int64), "d0": synth.gen_f64(ndim, 11, 0)})
-        dim = bpd.DataFrame(dim_host)  # sharded by rank; merge() all-gathers it (combine)
-        nout = [0]
+        dim_keys = rng.permutation(ndim).astype(np.int64)
+        d0 = synth.gen_f64(ndim, 11, 0)
+        dim = api.pd.DataFrame(pandas.DataFrame({"key": dim_keys, "d0": d0}))  # sharded by rank; merge() all-gathers it
+        row_of = np.empty(ndim, dtype=np.int64)
+        row_of[dim_keys] = np.arange(ndim)
 
         def step_merge():
-            r = fact.merge(dim, on="key", how="left")
-            r.execute()
-            nout[0] = len(r)
-            del r
+            last[0] = api.execute(fact.merge(dim, on="key", how="left"))
 
-        msteps = max(3, args.steps // 2)
-        moved = rows_local * 16  # 8 B key read + 8 B payload written per fact row; fact columns are shared, not copied
-        # default: the dim keys span [0, ndim) so the build picks the direct-addressed table; then the hash table forced
         for dense_on, label, kern in (
             (True, "", "join_dense_build + join_dense_probe (direct-addressed dim table, fused payload gather)"),
             (False, " [hash table forced]", "join_build + join_probe_gather (open-addressed hash table)"),
@@ -407,18 +670,28 @@ def run_b200_arm(args):
                 os.environ.pop("MB200_JOIN_DENSE", None)
             else:
                 os.environ["MB200_JOIN_DENSE"] = "0"
-            total_m, per_m = timed(step_merge, msteps, 2)
-            ms_m = total_m / msteps
-            ach = moved / (statistics.mean(per_m) / 1e3) / 1e9
+            try:
+                total_m, per_m = timed(step_merge, ksteps, 2)
+            finally:
+                os.environ.pop("MB200_JOIN_DENSE", None)
+            blk = api.blocks(last[0])[0]
+            idx = sample_rows(blk.nrows)
+            fk = np.array([synth.gen_i64(1, 43, 0, ndim, lo + r)[0] for r in idx])
+            ok = blk.nrows == rows_local and list(blk.columns) == ["key"] + cols8 + ["d0"]
+            ok = ok and np.array_equal(device_values(blk.cols[0], idx), fk)
+            ok = ok and _bits_equal(device_values(blk.cols[-1], idx), d0[row_of[fk]])
+            ok = all_ranks_ok(ok)
+            last[0] = None
+            ms_m = total_m / ksteps
+            moved16, moved152 = rows_local * 16, rows_local * 152
+            rf = roof(kern, moved16, per_m)
+            rf["note"] = ("algorithmic bytes = 16 B/row: key read + payload written -- the fact columns of the result are "
+                          "shared by reference, never copied; SURVEY 8(d) counts the reference's materialised output, "
+                          "152 B/row: see frac_vs_152B_row")
+            rf["frac_vs_152B_row"] = moved152 / (statistics.mean(per_m) / 1e3) / 1e9 / hbm_peak
             also.append({"metric": f"rows/sec fact.merge(dim, on='key', how='left'), {rows} fact rows x {ndim} dim rows{label}",
-                         "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "rows_out_local": nout[0],
-                         "roofline": {"bound": "hbm", "kernel": kern,
-                                      "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                      "traffic": None,
-                                      "note": "algorithmic bytes here = 16 B/row (key read + payload written); the "
-                                              "reference materialises the whole 152 B/row output, this backend shares "
-                                              "the fact columns by reference"}})  # fmt: skip
-        os.environ.pop("MB200_JOIN_DENSE", None)
+                         "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "checked": ok, "roofline": rf})  # fmt: skip
+            del blk
         del fact, dim
         torch.cuda.empty_cache()
 
@@ -426,59 +699,106 @@ def run_b200_arm(args):
         try:
             _secondary_legs()
         except Exception as exc:  # a secondary leg must never cost the headline line
-            also.append({"metric": "secondary legs aborted", "error": f"{type(exc).__name__}: {exc}"[:400]})
+            import traceback
+
+            also.append({"metric": "secondary legs aborted", "error": f"{type(exc).__name__}: {exc}"[:400],
+                         "where": traceback.format_exc().strip().splitlines()[-3:]})
             os.environ.pop("MB200_JOIN_DENSE", None)
+            _cfg.GroupbyDenseKeys.put(True)
+            _cfg.ReduceVariant.put(0)
     a = None
+    last[0] = None
     torch.cuda.empty_cache()
 
-    # ---- e2e: host buffers in, host buffers out (rank-local sample) ---------------------------
-    e2e = None
+    # ---- e2e: host frames in, host frames out, through the public API (rank-local sample) ----------------
+    e2e = e2e_groupby = None
     if not args.skip_e2e:
         from modin_b200 import hostpath
 
         er = int(args.e2e_rows) // ws
-        hin = [hostpath.PinnedColumn(er) for _ in range(W)]
-        hout = [hostpath.PinnedColumn(er) for _ in range(W)]
-        for j, c in enumerate(hin):
-            c.array[:] = synth.gen_f64(min(er, 1 << 20), 42, j).repeat(-(-er // min(er, 1 << 20)))[:er]
-        s0, s1 = [B_SCALAR] * W, [C_SCALAR] * W
 
-        def step_e2e():
-            hostpath.map_host("affine", hin, hout, s0=s0, s1=s1)
+        def fill(arr, seed, col):
+            m = min(len(arr), 1 << 20)
+            arr[:] = np.resize(synth.gen_f64(m, seed, col), len(arr))
 
-        step_e2e()
-        sync_all()
-        t0 = time.perf_counter()
-        ke = 3
-        for _ in range(ke):
-            step_e2e()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / ke * 1e3
-        dt = max_over_ranks(dt)
-        ref = hin[0].array[:1000] * B_SCALAR + C_SCALAR
-        assert (hout[0].array[:1000] == ref).all(), "e2e result check failed"
-        e2e = {"value": er * ws / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": er * W * 8,
-               "d2h_bytes_per_step": er * W * 8, "rows_per_step": er * ws, "ms_per_step": dt,
-               "path": "mb200_map_host: pinned host -> H2D -> AFFINE sweep -> D2H -> pinned host, 3-stream ring"}  # fmt: skip
-        for c in hin + hout:
-            c.free()
+        def host_timed(step_fn, reps=3):
+            step_fn()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                step_fn()
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t0) / reps * 1e3)
 
-    # ---- CPU baseline (rank 0, bounded sample) --------------------------------------------------
+        with dist.local_frames():  # every rank runs the same host-to-host pipeline on ITS OWN host frame
+            try:
+                host = hostpath.pinned_frame({f"c{j}": (er, np.float64) for j in range(W)})
+                for j in range(W):
+                    fill(host[f"c{j}"].to_numpy(), 42, j)
+                out = [None]
+
+                def step_e2e():
+                    df = api.pd.DataFrame(host)  # ingest: the block stays on the host (HostBlock)
+                    out[0] = api.to_pandas(df * B_SCALAR + C_SCALAR)  # streamed: H2D / AFFINE sweep / D2H per chunk
+
+                dt = host_timed(step_e2e)
+                got = out[0]
+                ref = host["c0"].to_numpy()[:1000] * B_SCALAR + C_SCALAR
+                ok = got.shape == (er, W) and bool((got["c0"].to_numpy()[:1000] == ref).all()) and \
+                    bool((got[f"c{W - 1}"].to_numpy()[-1000:] == host[f"c{W - 1}"].to_numpy()[-1000:] * B_SCALAR + C_SCALAR).all())
+                e2e = {"value": er * ws / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": er * W * 8,
+                       "d2h_bytes_per_step": er * W * 8, "rows_per_step": er * ws, "ms_per_step": dt, "checked": bool(ok),
+                       "path": f"{api.name}: pd.DataFrame(host) * b + c -> _to_pandas(); pinned host frame in, pooled "
+                               "pinned columns out; HostBlock -> mb200_map_host (H2D / AFFINE / D2H on three streams)"}  # fmt: skip
+                del got, out, host
+            except Exception as exc:
+                e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "error": f"{type(exc).__name__}: {exc}"[:300]}
+            try:
+                data = {"key": (er, np.int64), **{f"c{j}": (er, np.float64) for j in range(W)}}
+                host = hostpath.pinned_frame(data)
+                host["key"].to_numpy()[:] = np.resize(synth.gen_i64(min(er, 1 << 22), 43, 0, G), er)
+                for j in range(W):
+                    fill(host[f"c{j}"].to_numpy(), 42, j)
+                out = [None]
+
+                def step_e2e_gb():
+                    df = api.pd.DataFrame(host)
+                    out[0] = api.to_pandas(df.groupby("key").sum())  # H2D 72 B/row, device groupby, result D2H
+
+                dt = host_timed(step_e2e_gb, reps=2)
+                got = out[0]
+                keys = host["key"].to_numpy()
+                ok = len(got) == len(np.unique(keys[: 1 << 22])) if er >= (1 << 22) else True
+                want0 = np.bincount(keys, weights=host["c0"].to_numpy(), minlength=G)[got.index.to_numpy()]
+                wabs0 = np.bincount(keys, weights=np.abs(host["c0"].to_numpy()), minlength=G)[got.index.to_numpy()]
+                ok = bool(ok) and _sum_close(got["c0"].to_numpy(), want0, wabs0, er)
+                e2e_groupby = {"value": er * ws / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": er * (8 + 8 * W),
+                               "d2h_bytes_per_step": int(len(got)) * (8 + 8 * W), "rows_per_step": er * ws,
+                               "ms_per_step": dt, "checked": bool(ok),
+                               "path": f"{api.name}: pd.DataFrame(host).groupby('key').sum()._to_pandas()"}  # fmt: skip
+                del got, out, host
+            except Exception as exc:
+                e2e_groupby = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        if distributed:
+            torch.distributed.barrier()
+
+    # ---- CPU baseline (rank 0, bounded sample): the reference arm itself, in its own process ---------------
     cpu = None
     if rank == 0 and not args.skip_cpu and ws == 1:
-        # the CPU leg runs in its own process (own malloc tuning, no CUDA context): the reference arm itself
         env = dict(os.environ, RANK="0", WORLD_SIZE="1")
         for k in ("LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "MB200_REF_CHILD"):
             env.pop(k, None)
         try:
             res = subprocess.run(
                 [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                 "--cpu-rows", str(int(args.cpu_rows)), "--cols", str(W)],
-                capture_output=True, text=True, timeout=600, env=env)  # fmt: skip
+                 "--cpu-budget", "20", "--cols", str(W), "--groups", str(G), "--rows", str(rows)]
+                + (["--cpu-rows", str(int(args.cpu_rows))] if args.cpu_rows else []),
+                capture_output=True, text=True, timeout=900, env=env)  # fmt: skip
             ref = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
             cpu = ref["cpu_baseline"]
         except Exception as e:  # the GPU numbers stand on their own; say why the CPU leg is missing
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e!r}"[:300]}
 
     if rank == 0:
         line = {
@@ -488,8 +808,10 @@ def run_b200_arm(args):
             "config": {"workload": f"map_partitions elementwise a*b+c (b,c scalars, fused AFFINE, 2 roundings) on "
                                    f"{rows}x{W} f64, row-sharded over {ws} GPU(s)", "rows": rows, "cols": W,
                        "l2_policy": "inputs_larger_than_l2 (64 GB streamed per step)", "npartitions_per_gpu": 1,
-                       "api": "modin_b200.pandas: (df * b + c).execute()"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_timed,
+                       "api": api.name + ": (df * b + c)._query_compiler.execute()"},
+            "checked": map_checked, "parity_ok": parity_ok, "parity_failed": parity_fails,
+            "roofline": roofline, "roofline_groupby": roofline_groupby, "cpu_baseline": cpu,
+            "e2e": e2e, "e2e_groupby": e2e_groupby, "gpu_launches": launches_timed,
             "clocks": clocks, "also": also,
         }  # fmt: skip
         print(json.dumps(line), flush=True)

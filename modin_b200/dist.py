@@ -39,9 +39,29 @@ def _dist():
     return dist
 
 
+_LOCAL_DEPTH = 0
+
+
+class local_frames:
+    """Context manager: frames created and used inside belong to THIS rank alone (not row shards of a job-wide
+    frame), so ingest does not cut them by rank and nothing issues a collective -- N ranks then run N independent
+    single-GPU pipelines (the per-rank host-to-host legs of ``bench.py``).  Every rank must leave the block before
+    the next job-wide operation."""
+
+    def __enter__(self):
+        global _LOCAL_DEPTH
+        _LOCAL_DEPTH += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _LOCAL_DEPTH
+        _LOCAL_DEPTH -= 1
+        return False
+
+
 def is_distributed() -> bool:
     d = _dist()
-    return d.is_available() and d.is_initialized() and d.get_world_size() > 1
+    return _LOCAL_DEPTH == 0 and d.is_available() and d.is_initialized() and d.get_world_size() > 1
 
 
 def world_size() -> int:
