@@ -160,14 +160,17 @@ def run_reference_arm(args):
 
     # size the sample to the time budget: probe at 2e7 rows (large enough that every pandas temporary is a fresh
     # mmap, as at the real size), then scale
-    probe_n = 20_000_000
-    probe = mpd.DataFrame(synth.host_frame(probe_n, W, seed=42))
-    probe._query_compiler.execute()
-    modin_map_pass(probe)
-    rate = probe_n / modin_map_pass(probe)
-    del probe
     total_steps = args.steps + max(args.warmup, 1)
-    rows = int(args.cpu_rows) if args.cpu_rows else int(min(1e8, max(1e7, rate * args.cpu_budget / total_steps)))
+    if args.cpu_rows:
+        rows = int(args.cpu_rows)
+    else:
+        probe_n = 20_000_000
+        probe = mpd.DataFrame(synth.host_frame(probe_n, W, seed=42))
+        probe._query_compiler.execute()
+        modin_map_pass(probe)
+        rate = probe_n / modin_map_pass(probe)
+        del probe
+        rows = int(min(1e8, max(1e7, rate * args.cpu_budget / total_steps)))
     pdf = synth.host_frame(rows, W, seed=42)
     mdf = mpd.DataFrame(pdf)
     mdf._query_compiler.execute()
@@ -484,6 +487,7 @@ def run_b200_arm(args):
     last = [None]
 
     def step_map():
+        last[0] = None  # the previous result (64 GB at 1e9 rows) goes back to the allocator first
         out = a * B_SCALAR + C_SCALAR  # Binary template x2 -> call queue -> one AFFINE sweep
         api.execute(out)
         last[0] = out
@@ -568,6 +572,7 @@ def run_b200_arm(args):
             api.execute(f)
 
         def step_fma3():
+            last[0] = None
             out = fa * fb + fc  # two n_ary_op calls -> call queue -> one FMA3 sweep (two roundings)
             api.execute(out)
             last[0] = out
@@ -594,6 +599,7 @@ def run_b200_arm(args):
             _cfg.GroupbyDenseKeys.put(dense_on)
 
             def step_gb():
+                last[0] = None
                 last[0] = api.execute(g.groupby("key").sum())
 
             try:
@@ -660,6 +666,7 @@ def run_b200_arm(args):
         row_of[dim_keys] = np.arange(ndim)
 
         def step_merge():
+            last[0] = None
             last[0] = api.execute(fact.merge(dim, on="key", how="left"))
 
         for dense_on, label, kern in (

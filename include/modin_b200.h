@@ -284,6 +284,25 @@ int mb200_take(int dtype, int ncols, const void* const* src, const int64_t* idx,
 int mb200_compact_hits(const int64_t* idx, int64_t n, int64_t* out_pos, int64_t* out_count_dev,
                        void* scratch, size_t scratch_bytes, mb200_stream_t stream);
 
+/* ---- many-to-many merge (duplicate keys on the broadcast side; merge.py:139-168 is plain pandas.merge per block) ----
+ * The right keys are sorted with their row ids (mb200_sort_pairs_i64); mb200_run_heads marks the first row of every
+ * run of equal keys (idx_out[i] = i at a run head, else -1; feed it to mb200_compact_hits to get starts[U]); the U
+ * distinct keys go into a join table, so the probe stays many-to-one and returns u[i] = run of fact row i or -1. */
+int mb200_run_heads(const int64_t* sorted_keys, int64_t n, int64_t* idx_out, mb200_stream_t stream);
+/* Per left row: cnt[i] = rows it produces (length of run u[i]; 1 for a miss when keep_misses, the LEFT join; else 0),
+ * first[i] = start of its run in the sorted right rows (or -1). */
+int mb200_expand_counts(const int64_t* u, int64_t n, const int64_t* starts, int64_t nuniq, int64_t nright,
+                        int keep_misses, int64_t* cnt, int64_t* first, mb200_stream_t stream);
+/* Exclusive prefix sum of int64 values: out_offsets[i] = values[0] + ... + values[i - 1]; *out_total_dev = the sum
+ * (device).  scratch_bytes >= mb200_scan_scratch_bytes(n). */
+size_t mb200_scan_scratch_bytes(int64_t n);
+int mb200_scan_i64(const int64_t* values, int64_t n, int64_t* out_offsets, int64_t* out_total_dev, void* scratch,
+                   size_t scratch_bytes, mb200_stream_t stream);
+/* Left row i writes its cnt[i] output pairs at offsets[i]: out_left = i, out_right = order[first[i] + j] (the right
+ * row ids in key-sorted order) or -1 for a miss.  The result columns are mb200_take gathers of the two. */
+int mb200_expand_rows(const int64_t* offsets, const int64_t* cnt, const int64_t* first, const int64_t* order,
+                      int64_t n, int64_t* out_left, int64_t* out_right, mb200_stream_t stream);
+
 /* ======================= synthetic data (from_map-style generators) ======== */
 /* Counter-based generators, reproducible for any row range; the numpy twin lives in
  * modin_b200/synth.py.  value(row, col) depends only on (seed, col, row_offset + i).
@@ -300,6 +319,13 @@ int mb200_gen_i64(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int6
  * space grows towards small keys like k^-1.1 -- for modulus = 1e6 key 0 takes ~11 % of the rows. */
 int mb200_gen_i64_skew(int64_t* out, int64_t nrows, uint64_t seed, uint64_t col, int64_t row_offset,
                        uint64_t modulus, int64_t* stats_dev, mb200_stream_t stream);
+
+/* Row labels of a RangeIndex block as a device column: out[i] = start + i.  The labels a block needs on the device
+ * when it is re-indexed against another frame's labels (PandasDataframe._copartition, df.py:3799-3840). */
+int mb200_iota_i64(int64_t* out, int64_t nrows, int64_t start, mb200_stream_t stream);
+/* Constant column of 8-byte elements: out[i] = bits (a float64 / int64 bit pattern; NaN columns for labels that
+ * re-indexing adds). */
+int mb200_fill_u64(void* out, int64_t n, uint64_t bits, mb200_stream_t stream);
 
 /* ======================= utilities ========================================= */
 /* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.

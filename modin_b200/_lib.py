@@ -86,9 +86,16 @@ _SIGNATURES = {
     "mb200_join_probe_gather": (C.c_int, [_vp, _vp, _i64, C.c_int, _vpp, C.c_int, _vpp, _vp, _vp]),
     "mb200_take": (C.c_int, [C.c_int, C.c_int, _vpp, _vp, _i64, _vpp, _vp]),
     "mb200_compact_hits": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mb200_run_heads": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "mb200_expand_counts": (C.c_int, [_vp, _i64, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp]),
+    "mb200_scan_scratch_bytes": (C.c_size_t, [_i64]),
+    "mb200_scan_i64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "mb200_expand_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
     "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
+    "mb200_iota_i64": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "mb200_fill_u64": (C.c_int, [_vp, _i64, C.c_uint64, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_sort_pairs_i64": (C.c_int, [_vp, _vp, _i64, _vp, C.c_size_t, _vp]),
     "mb200_l2_persist_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),

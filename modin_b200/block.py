@@ -355,6 +355,45 @@ class DeviceBlock:
         out.replicated = self.replicated
         return out
 
+    def reindex(self, labels=None, index=None, columns=None, axis=None, fill_value=None, copy=None, **kwargs):
+        """``df.reindex(joined_index, axis=axis, fill_value=fill_value)``: what ``PandasDataframe._copartition``
+        applies to the gathered blocks of a frame whose labels differ from the joined index (``make_reindexer``,
+        df.py:2058-2073).  Answered on the device by ``functors.DevReindex``."""
+        from .functors import DevReindex
+
+        if kwargs.get("method") is not None or kwargs.get("level") is not None:
+            raise NotImplementedError("reindex(method= / level=) is not on the B200 path")
+        out = self
+        if labels is not None:
+            out = DevReindex()(out, labels, axis=0 if axis is None else axis, fill_value=fill_value)
+        if index is not None:
+            out = DevReindex()(out, index, axis=0, fill_value=fill_value)
+        if columns is not None:
+            out = DevReindex()(out, columns, axis=1, fill_value=fill_value)
+        return out
+
+    def _reindex_with_indexers(self, reindexers, fill_value=None, copy=None, allow_dups=False, **kwargs):
+        """pandas' internal ``NDFrame._reindex_with_indexers``, which ``_copartition`` calls when some frame's labels
+        repeat (df.py:2064-2072): ``reindexers = {axis: [new_labels, positional_indexer_or_None]}``."""
+        from .functors import DevReindex
+
+        if fill_value is not None and not (isinstance(fill_value, float) and np.isnan(fill_value)):
+            raise NotImplementedError("reindex(fill_value=) is not on the B200 path")
+        out = self
+        for axis, (labels, indexer) in reindexers.items():
+            if axis in (0, "index"):
+                out = DevReindex.with_indexer(out, labels, indexer)
+            else:
+                labels = labels if isinstance(labels, pandas.Index) else pandas.Index(labels)
+                if indexer is None:
+                    out = out.with_cols(out.cols, labels)
+                else:
+                    from . import ops
+
+                    cols = [out.cols[p] if p >= 0 else ops.full_column(out.nrows, np.float64, float("nan")) for p in indexer]
+                    out = out.with_cols(cols, labels)
+        return out
+
     def squeeze(self, axis=None) -> "DeviceBlock":
         """A one-column block IS this package's Series, so squeezing changes nothing.  Modin's Binary template calls
         ``right.squeeze()`` on the broadcast operand (``df.mul(series, axis=0)``, alg/binary.py:396-402) before handing
@@ -498,6 +537,8 @@ def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
 def concat_cols(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
     """Column-wise concatenation (shares buffers; no copy)."""
     first = blocks[0]
+    if len(blocks) == 1:
+        return first
     cols = []
     labels = []
     for b in blocks:

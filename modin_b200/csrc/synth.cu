@@ -95,6 +95,16 @@ __global__ void gen_i64_skew_kernel(long long* __restrict__ out, long long n, un
   if (STATS) st.flush(stats);
 }
 
+// out[i] = start + i (row labels of a RangeIndex block as a device column) / out[i] = bits (constant column)
+__global__ void iota_i64_kernel(long long* __restrict__ out, long long n, long long start) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = start + i;
+}
+__global__ void fill_u64_kernel(unsigned long long* __restrict__ out, long long n, unsigned long long bits) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = bits;
+}
+
 __global__ void flush_kernel(unsigned long long* __restrict__ buf, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = (unsigned long long)i;
@@ -182,5 +192,31 @@ extern "C" int mb200_flush_l2(void* buf, size_t bytes, mb200_stream_t stream) {
   flush_kernel<<<dp.sm_count * 8, 256, 0, (cudaStream_t)stream>>>(static_cast<unsigned long long*>(buf),
                                                                   (long long)(bytes / 8));
   MB_LAUNCH_CHECK("flush_kernel");
+  return 0;
+}
+
+extern "C" int mb200_iota_i64(int64_t* out, int64_t nrows, int64_t start, mb200_stream_t stream) {
+  if (nrows < 0) return fail("mb200_iota_i64", "negative nrows");
+  if (nrows == 0) return 0;
+  if (!out) return fail("mb200_iota_i64", "null output");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long grid = (nrows + 255) / 256;
+  if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
+  iota_i64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(out), nrows, start);
+  MB_LAUNCH_CHECK("iota_i64_kernel");
+  return 0;
+}
+
+extern "C" int mb200_fill_u64(void* out, int64_t n, uint64_t bits, mb200_stream_t stream) {
+  if (n < 0) return fail("mb200_fill_u64", "negative n");
+  if (n == 0) return 0;
+  if (!out) return fail("mb200_fill_u64", "null output");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long grid = (n + 255) / 256;
+  if (grid > (long long)dp.sm_count * 16) grid = (long long)dp.sm_count * 16;
+  fill_u64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(static_cast<unsigned long long*>(out), n, bits);
+  MB_LAUNCH_CHECK("fill_u64_kernel");
   return 0;
 }

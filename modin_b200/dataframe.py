@@ -201,10 +201,7 @@ class B200Dataframe:
         Buffers are shared; up to 32 columns stay one column partition."""
         from .block import concat_cols
 
-        if sum(self.row_lengths) != sum(other.row_lengths):
-            raise ValueError("Length of values does not match length of index")
-        if other.row_lengths != self.row_lengths:
-            other = other._repartition_rows(self.row_lengths)
+        other = self._align_rows_like(other, "column assignment")  # pandas aligns on the frame's row labels
         if len(set(self.columns) & set(other.columns)):
             raise ValueError("hstack needs distinct column labels")
         pc = self._partition_mgr_cls._partition_class
@@ -284,10 +281,14 @@ class B200Dataframe:
 
         if len(mask.columns) != 1:
             raise NotImplementedError("row selection takes a one-column bool mask")
-        if sum(mask.row_lengths) != sum(self.row_lengths):
-            raise ValueError("Item wrong length: the mask has to cover the rows of the frame one to one")
-        if mask.row_lengths != self.row_lengths:
-            mask = mask._repartition_rows(self.row_lengths)
+        if not self.index.equals(mask.index):
+            # pandas (check_bool_indexer): the mask is re-indexed on the frame's labels and must cover all of them
+            if not mask.index.is_unique or not self.index.isin(mask.index).all():
+                raise pandas.errors.IndexingError(
+                    "Unalignable boolean Series provided as indexer (index of the boolean Series and of the indexed "
+                    "object do not match)."
+                )
+        mask = self._align_rows_like(mask, "boolean mask")
         from .block import concat_cols
 
         pc = self._partition_mgr_cls._partition_class
@@ -404,6 +405,59 @@ class B200Dataframe:
         return self.__constructor__(parts, self._index_cache, self._columns_cache, list(lengths), self._column_widths_cache,
                                     self._dtypes)  # fmt: skip
 
+    def _reindex_rows(self, labels: pandas.Index, lengths: List[int]) -> "B200Dataframe":
+        """This frame's rows re-labelled to ``labels`` (missing labels -> NaN rows) and cut at ``lengths``: the
+        ``map_axis_partitions(0, parts, make_reindexer(...), lengths=base_lengths)`` step of
+        ``PandasDataframe._copartition`` (df.py:3799-3840) -- every column partition is gathered along the rows,
+        re-indexed on the device (``DevReindex``) and split again."""
+        from .functors import DevReindex
+        from .partitioning import Bound
+
+        if dist.is_distributed() and not self._is_replicated():
+            # the labels to align against live on the other ranks too; every rank refuses together
+            raise NotImplementedError("label alignment between row-sharded frames is not on the B200 path")
+        parts = self._partition_mgr_cls.map_axis_partitions(
+            0, self._partitions, Bound(DevReindex(), (labels,), {"axis": 0}), lengths=list(lengths))
+        return self.__constructor__(parts, labels, self._columns_cache, list(lengths), self._column_widths_cache, None)
+
+    def _copartition_rows(self, others: list, how: str = "outer", sort=None):
+        """``_copartition(axis=0, ...)`` (df.py:3709-3848): join the row labels of ``self`` and ``others``
+        (``how`` = "outer" for binary operators, "left" for assignments / masks / group keys; pandas sorts the joined
+        index when the labels differ, df.py:3759-3760) and bring every frame to the joined labels and to the same
+        row cuts.  Returns ``(self', others')``; frames whose labels already equal the joined index are only re-cut."""
+        if all(self._check_if_axes_identical(o, 0) for o in others):
+            return self, list(others)
+        if sort is None:
+            sort = not all(self.index.equals(o.index) for o in others)
+        joined = self.index
+        for o in others:
+            if not joined.equals(o.index):
+                joined = joined.join(o.index, how=how, sort=sort)
+        base = self if self.index.equals(joined) else None
+        lengths = self.row_lengths if base is not None else None
+        if lengths is None:
+            from .partitioning import get_length_list
+            from .config import MinRowPartitionSize, NPartitions
+
+            lengths = [n for n in get_length_list(len(joined), NPartitions.get(), MinRowPartitionSize.get()) if n] or [0]
+        new_self = self if base is not None else self._reindex_rows(joined, lengths)
+        out = []
+        for o in others:
+            if o.index.equals(joined):
+                out.append(o if o.row_lengths == list(lengths) else o._repartition_rows(list(lengths)))
+            else:
+                out.append(o._reindex_rows(joined, lengths))
+        return new_self, out
+
+    def _align_rows_like(self, other: "B200Dataframe", what: str) -> "B200Dataframe":
+        """``other`` brought to THIS frame's row labels and cuts (pandas aligns an assigned Series, a boolean mask or
+        a group-key Series on the frame's index -- a left join of the labels)."""
+        if self.index.equals(other.index):
+            return other if other.row_lengths == self.row_lengths else other._repartition_rows(self.row_lengths)
+        if not other.index.is_unique:
+            raise ValueError("cannot reindex on an axis with duplicate labels")
+        return other._reindex_rows(self.index, self.row_lengths)
+
     def _check_if_axes_identical(self, other: "B200Dataframe", axis: int = 0) -> bool:
         """df.py:3678-3707."""
         if axis == 0:
@@ -412,23 +466,25 @@ class B200Dataframe:
 
     def n_ary_op(self, op, right_frames: list, join_type="outer", copartition_along_columns=True, labels="replace",
                  dtypes=None, sort=None):  # fmt: skip
-        """df.py:3851-3950, fast path only: operands must already be co-partitioned (identical labels
-        and partition lengths, df.py:3750-3758 -- no data movement).  The general ``_copartition``
-        reindex (df.py:3799-3840) is a "next" row."""
-        aligned = []
+        """df.py:3851-3950.  Row labels go through ``_copartition`` (df.py:3709-3848): identical labels and cuts are
+        the no-op fast path (df.py:3750-3758), equal labels with other cuts are re-cut (views), different labels are
+        joined (outer, sorted -- pandas' alignment of binary operators) and every frame is re-indexed on the device
+        (``DevReindex``).  Column labels must already agree."""
+        left = self
         for other in right_frames:
-            if not (self._check_if_axes_identical(other, 0) and self._check_if_axes_identical(other, 1)):
-                # the part of _copartition (df.py:3709-3848) that needs no reindex: same labels, same column
-                # grid, only the row partition lengths differ -> re-cut the right operand along the left's cuts
-                if (self.columns.equals(other.columns) and self.column_widths == other.column_widths
-                        and sum(self.row_lengths) == sum(other.row_lengths) and self.index.equals(other.index)):  # fmt: skip
-                    other = other._repartition_rows(self.row_lengths)
-                else:
-                    raise NotImplementedError(
-                        "binary op between differently labelled frames needs the reindexing half of _copartition, "
-                        "which is not on the B200 path"
-                    )
-            aligned.append(other)
+            if not (self.columns.equals(other.columns) and self.column_widths == other.column_widths):
+                raise NotImplementedError(
+                    "binary op between frames with different COLUMN labels is not on the B200 path "
+                    "(row labels are aligned; select / rename the columns first)"
+                )
+        # row labels: identical -> no-op; same labels, other cuts -> re-cut; different labels -> the join + reindex
+        # of _copartition (df.py:3709-3848)
+        left, aligned = self._copartition_rows(list(right_frames), how=join_type if join_type in ("outer", "left", "inner") else "outer",
+                                               sort=sort)  # fmt: skip
+        if left is not self:
+            new_frame = left._partition_mgr_cls.n_ary_operation(left._partitions, op, [o._partitions for o in aligned])
+            return self.__constructor__(new_frame, left._index_cache, left._columns_cache, left._row_lengths_cache,
+                                        left._column_widths_cache, None)  # fmt: skip
         new_frame = self._partition_mgr_cls.n_ary_operation(
             self._partitions, op, [other._partitions for other in aligned]
         )
@@ -463,9 +519,12 @@ class B200Dataframe:
     # ---- GroupByReduce ----------------------------------------------------------------------------
     def groupby_reduce(self, axis, by, map_func, reduce_func, new_index=None, new_columns=None, apply_indices=None):
         """df.py:4530-4589."""
+        if by is not None and not (self.index.equals(by.index) and self.row_lengths == by.row_lengths):
+            if not self.index.equals(by.index) and not self.index.isin(by.index).all():
+                # pandas would group the uncovered rows under NaN keys and drop them: float keys are not on the path
+                raise NotImplementedError("group keys that do not cover every row label are not on the B200 path")
+            by = self._align_rows_like(by, "group keys")
         by_parts = by if by is None else by._partitions
-        if by is not None and self.row_lengths != by.row_lengths:
-            raise NotImplementedError("`by` must be co-partitioned with the frame on the B200 path")
         new_partitions = self._partition_mgr_cls.groupby_reduce(axis, self._partitions, by_parts, map_func, reduce_func,
                                                                 apply_indices)  # fmt: skip
         return self.__constructor__(new_partitions, new_index, new_columns)

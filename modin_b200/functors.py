@@ -926,6 +926,108 @@ class DevSsdMap(DevFn):
         return _reduced_block(out, labels)
 
 
+# ------------------------------------------------------------------ label alignment (the reindexing half of _copartition)
+def _labels_block(block, cols, labels: pandas.Index, replicated=False):
+    """``cols`` under new row ``labels`` (RangeIndex -> O(1) metadata, numeric -> device index column, else host)."""
+    n = len(labels)
+    if isinstance(labels, pandas.RangeIndex) and labels.step == 1 and labels.name is None:
+        out = DeviceBlock(cols, block.columns, nrows=n, range_start=labels.start)
+    elif not isinstance(labels, pandas.MultiIndex) and labels.dtype.kind in "if" and n > 0:
+        arr = labels.to_numpy()
+        arr = arr.astype(np.int64) if arr.dtype.kind == "i" else arr.astype(np.float64)
+        out = DeviceBlock(cols, block.columns, nrows=n, index_cols=[DeviceColumn.from_numpy(arr)], index_names=[labels.name])
+    else:
+        out = DeviceBlock(cols, block.columns, nrows=n, index_host=labels)
+    out.replicated = replicated
+    return out
+
+
+class DevReindex(DevFn):
+    """``df.reindex(labels, axis=axis)`` of one full-axis block -- the function ``PandasDataframe._copartition``
+    ships to ``map_axis_partitions`` for every frame whose labels differ from the joined index (df.py:3799-3840,
+    ``make_reindexer`` df.py:2058-2073).  Rows: a join table over the block's own labels is probed with the target
+    labels and the columns are gathered (``mb200_join_build`` / ``probe`` / ``take``); labels that the block does not
+    have become NaN rows, which promotes int64 columns to float64 exactly as pandas does.  Columns: buffers are
+    re-ordered by reference, missing labels become NaN columns."""
+
+    op = "reindex"
+
+    def __call__(self, block, labels, axis=0, fill_value=None, **kwargs):
+        _check_block(block, "DevReindex")
+        if fill_value is not None and not (isinstance(fill_value, float) and np.isnan(fill_value)):
+            raise NotImplementedError("reindex(fill_value=) is not on the B200 path")
+        labels = labels if isinstance(labels, pandas.Index) else pandas.Index(labels)
+        if axis in (1, "columns"):
+            return self._columns(block, labels)
+        if axis not in (0, "index"):
+            raise ValueError(f"No axis named {axis}")
+        return self._rows(block, labels)
+
+    @staticmethod
+    def with_indexer(block, labels, indexer):
+        """Rows gathered by a HOST-computed positional indexer (-1 = no such row -> NaN): what
+        ``df._reindex_with_indexers({0: [joined_index, indexer]}, allow_dups=True)`` does for frames whose labels
+        repeat (``make_reindexer``, df.py:2064-2072 -- the reference computes those indexers on the host too)."""
+        labels = labels if isinstance(labels, pandas.Index) else pandas.Index(labels)
+        if indexer is None:
+            return _labels_block(block, list(block.cols), labels, replicated=block.replicated)
+        pos = np.asarray(indexer, dtype=np.int64)
+        misses = int((pos < 0).sum())
+        cols = []
+        for c in block.cols:
+            if misses and c.dtype == np.bool_:
+                raise NotImplementedError("re-indexing would put NaN into a bool column (object dtype in pandas)")
+            cols.append(ops.cast_columns_f64([c])[0] if misses and c.dtype == np.int64 else c)
+        idx = DeviceColumn.from_numpy(pos) if len(pos) else DeviceColumn.empty(0, np.int64)
+        out = ops.take_columns(cols, idx) if cols else []
+        return _labels_block(block, out, labels, replicated=block.replicated)
+
+    @staticmethod
+    def _columns(block, labels):
+        if not block.columns.is_unique:
+            raise ValueError("cannot reindex on an axis with duplicate labels")
+        pos = block.columns.get_indexer(labels)
+        cols = [block.cols[p] if p >= 0 else ops.full_column(block.nrows, np.float64, float("nan")) for p in pos]
+        return block.with_cols(cols, labels)
+
+    @staticmethod
+    def _rows(block, labels):
+        n_t = len(labels)
+        numeric = (not isinstance(labels, pandas.MultiIndex) and labels.dtype.kind in "if"
+                   and block.index_host is None and (not block.index_cols or len(block.index_cols) == 1))  # fmt: skip
+        if n_t == 0 or block.nrows == 0 or not numeric:
+            src = block.index  # host labels (small blocks, non-numeric labels): the indexer is computed on the host
+            if not src.is_unique:
+                raise ValueError("cannot reindex on an axis with duplicate labels")
+            pos = src.get_indexer(labels).astype(np.int64)
+            misses = int((pos < 0).sum())
+            idx = DeviceColumn.from_numpy(pos) if n_t else DeviceColumn.empty(0, np.int64)
+        else:
+            src = block.index_cols[0] if block.index_cols else ops.iota(block.range_start, block.nrows)
+            tgt_np = labels.to_numpy()
+            if src.dtype == np.float64 or tgt_np.dtype.kind == "f":
+                # float labels (or int against float): compare through the order-preserving int64 image
+                tgt = ops.map_columns("ordered_s", [DeviceColumn.from_numpy(tgt_np.astype(np.float64))], s0=[0])[0]
+                src = ops.map_columns("ordered_s", ops.cast_columns_f64([src]), s0=[0])[0]
+            else:
+                tgt = DeviceColumn.from_numpy(tgt_np.astype(np.int64))
+            table = ops.JoinTable(src)
+            try:
+                if not table.is_unique():
+                    raise ValueError("cannot reindex on an axis with duplicate labels")
+                idx, nmatch = table.probe(tgt)
+                misses = n_t - int(nmatch.item())
+            finally:
+                table.close()
+        cols = []
+        for c in block.cols:
+            if misses and c.dtype == np.bool_:
+                raise NotImplementedError("re-indexing would put NaN into a bool column (object dtype in pandas)")
+            cols.append(ops.cast_columns_f64([c])[0] if misses and c.dtype == np.int64 else c)
+        out = ops.take_columns(cols, idx) if cols else []
+        return _labels_block(block, out, labels, replicated=block.replicated)
+
+
 # ------------------------------------------------------------------ GroupByReduce functors
 _GB_FLAGS = {
     "min": _lib.GB_MIN,
@@ -1153,50 +1255,93 @@ def _lib_max_cols() -> int:
 
 # ------------------------------------------------------------------ broadcast merge functor
 class DevMerge(DevFn):
-    """Per-row-partition ``pandas.merge(left_block, right, how, on, sort=False)`` of
-    MergeImpl.row_axis_merge (merge.py:139-168) as a hash-join probe + payload gather."""
+    """Per-row-partition ``pandas.merge(left_block, right, how, on / left_on / right_on, sort=False)`` of
+    MergeImpl.row_axis_merge (merge.py:139-168) as a join-table probe + payload gather.
+
+    * distinct right keys (many-to-one): probe + fused payload gather, the fact columns of a left join shared by
+      reference;
+    * repeated right keys (many-to-many): every left row yields one row per matching right row, left order kept, the
+      matches in their order on the right (``ops.expand_matches``), then two gathers;
+    * ``left_on != right_on``: both key columns appear in the result, like pandas.
+
+    ``promote_ints``: whether int64 payload columns of a LEFT join become float64 (pandas does that when some left
+    row finds no match, for the NaN).  The caller decides it ONCE for the whole job (all row partitions, all ranks:
+    ``count_misses`` + all_reduce), so that every partition of the result carries the same dtypes; ``None`` = decide
+    per block (single-partition callers)."""
 
     op = "merge"
 
-    def __init__(self, on, how="left", suffixes=("_x", "_y")):
+    def __init__(self, on=None, how="left", suffixes=("_x", "_y"), left_on=None, right_on=None, promote_ints=None,
+                 table_cache=None):  # fmt: skip
         if how not in ("left", "inner"):
             raise NotImplementedError("device merge supports how='left' and how='inner'")
-        self.on, self.how, self.suffixes = on, how, suffixes
-        self._cache = {}
+        self.left_on = on if left_on is None else left_on
+        self.right_on = on if right_on is None else right_on
+        if self.left_on is None or self.right_on is None:
+            raise NotImplementedError("device merge needs `on` (or `left_on` and `right_on`)")
+        self.on, self.how, self.suffixes, self.promote_ints = self.left_on, how, suffixes, promote_ints
+        # {right key label: (right block, table, unique)}.  Handed in by ``merge.row_axis_merge`` it lives on the
+        # combined (broadcast) right frame, so that a dim frame is built into a table ONCE however often it is merged
+        self._cache = table_cache if table_cache is not None else {}
 
     def _table(self, right: DeviceBlock):
-        key = id(right)
-        ent = self._cache.get(key)
-        if ent is None or ent[0] is not right:
-            table = ops.JoinTable(right.column(self.on))
-            if not table.is_unique():
-                table.close()
-                raise NotImplementedError("device merge needs distinct keys on the right (many-to-one join)")
-            ent = (right, table)
-            self._cache.clear()
-            self._cache[key] = ent
-        return ent[1]
+        """(join table over the right keys, are they distinct) -- built once per right block and kept (the library
+        also keeps the key-ordered payload copies of a dense table with it)."""
+        keys = right.column(self.right_on)
+        ident = (keys.ptr, len(keys))  # the key BUFFER identifies the table: blocks are re-wrapped freely, buffers are immutable
+        ent = self._cache.get(self.right_on)
+        if ent is None or ent[0] != ident:
+            if ent is not None:
+                ent[1].close()
+            table = ops.JoinTable(keys)
+            ent = (ident, table, table.is_unique())
+            self._cache[self.right_on] = ent
+        return ent[1], ent[2]
+
+    def result_labels(self, left_columns, right_columns):
+        """(positions of the right columns that enter the result, left labels, right labels) with pandas' suffixes."""
+        same = self.left_on == self.right_on
+        pay_pos = [i for i, lab in enumerate(right_columns) if not (same and lab == self.right_on)]
+        pay_labels = [right_columns[i] for i in pay_pos]
+        left_labels = list(left_columns)
+        overlap = set(left_labels) & set(pay_labels)
+        ll = [f"{x}{self.suffixes[0]}" if x in overlap else x for x in left_labels]
+        rl = [f"{x}{self.suffixes[1]}" if x in overlap else x for x in pay_labels]
+        return pay_pos, ll, rl
+
+    def count_misses(self, left: DeviceBlock, right: DeviceBlock) -> int:
+        """Left rows of this block whose key is not on the right (host int; one probe pass, one sync)."""
+        table, _ = self._table(right)
+        _, nmatch = table.probe(left.column(self.left_on))
+        return left.nrows - int(nmatch.item())
 
     def __call__(self, left, right, *args, **kwargs):
         _check_block(left, "DevMerge")
         _check_block(right, "DevMerge")
-        table = self._table(right)
-        fact_keys = left.column(self.on)
-        pay_pos = [i for i, lab in enumerate(right.columns) if lab != self.on]
+        table, unique = self._table(right)
+        fact_keys = left.column(self.left_on)
+        pay_pos, ll, rl = self.result_labels(left.columns, right.columns)
         pay_cols = [right.cols[i] for i in pay_pos]
-        pay_labels = [right.columns[i] for i in pay_pos]
-        left_labels = list(left.columns)
-        # suffixes for overlapping non-key labels (pandas.merge semantics)
-        overlap = set(left_labels) & set(pay_labels)
-        ll = [f"{x}{self.suffixes[0]}" if x in overlap else x for x in left_labels]
-        rl = [f"{x}{self.suffixes[1]}" if x in overlap else x for x in pay_labels]
+        has_int = any(c.dtype == np.int64 for c in pay_cols)
+        if not unique:
+            lrows, rrows, misses = ops.expand_matches(fact_keys, right.column(self.right_on), keep_misses=self.how == "left")
+            promote = self.how == "left" and has_int and (self.promote_ints if self.promote_ints is not None else misses > 0)
+            pay = ops.cast_columns_f64(pay_cols) if promote else pay_cols
+            cols = ops.take_columns(left.cols, lrows) + ops.take_columns(pay, rrows)
+            return DeviceBlock(cols, pandas.Index(ll + rl), nrows=len(lrows), range_start=0)
         if self.how == "left":
-            gathered, nmatch = table.probe_gather(fact_keys, pay_cols)
-            if any(c.dtype == np.int64 for c in pay_cols):
-                if int(nmatch.item()) != left.nrows:  # misses: pandas promotes int payload to float64 NaN
-                    idx, _ = table.probe(fact_keys)
-                    pay_f = ops.cast_columns_f64(pay_cols)
-                    gathered = ops.take_columns(pay_f, idx)
+            promote = self.promote_ints
+            if has_int and promote is None:
+                gathered, nmatch = table.probe_gather(fact_keys, pay_cols)
+                promote = int(nmatch.item()) != left.nrows  # misses: pandas promotes int payload to float64 NaN
+                if not promote:
+                    return DeviceBlock(list(left.cols) + gathered, pandas.Index(ll + rl), nrows=left.nrows,
+                                       range_start=left.range_start)  # fmt: skip
+            if has_int and promote:
+                idx, _ = table.probe(fact_keys)
+                gathered = ops.take_columns(ops.cast_columns_f64(pay_cols), idx)
+            else:
+                gathered, _ = table.probe_gather(fact_keys, pay_cols)
             cols = list(left.cols) + gathered  # fact columns shared by reference
             return DeviceBlock(cols, pandas.Index(ll + rl), nrows=left.nrows, range_start=left.range_start)
         idx, _ = table.probe(fact_keys)

@@ -444,36 +444,13 @@ def register(shims: bool | None = None):
             return self.__constructor__(_reset_row_index(self._modin_frame))
 
         def merge(self, right, **kwargs):
-            """qc.py:657-667 -> MergeImpl.row_axis_merge (merge.py:104-252) with the per-block
-            ``pandas.merge`` replaced by the device hash-join functor."""
-            how = kwargs.get("how", "inner")
-            on = kwargs.get("on")
-            if kwargs.get("left_index") or kwargs.get("right_index") or how not in ("left", "inner"):
-                raise NotImplementedError("device merge: how in {left, inner}, no index joins")
-            if isinstance(on, (list, tuple)):
-                if len(on) != 1:
-                    raise NotImplementedError("device merge joins on exactly one int64 key column")
-                on = on[0]
-            if on is None:
-                raise NotImplementedError("device merge needs `on`")
-            suffixes = kwargs.get("suffixes", ("_x", "_y"))
-            right_to_broadcast = right._modin_frame.combine()  # merge.py:178
-            func = fx.DevMerge(on=on, how=how, suffixes=suffixes)
-            right_labels = [c for c in right.columns if c != on]
-            overlap = set(self.columns) & set(right_labels)
-            new_columns = pandas.Index(
-                [f"{c}{suffixes[0]}" if c in overlap else c for c in self.columns]
-                + [f"{c}{suffixes[1]}" if c in overlap else c for c in right_labels]
-            )
-            new_frame = self._modin_frame.broadcast_apply_full_axis(
-                axis=1, func=func, other=right_to_broadcast, keep_partitioning=True, num_splits=1,
-                new_columns=new_columns, sync_labels=False,
-            )  # fmt: skip
-            # merge.py:236-250 resets the index with a pandas lambda per block; on range-indexed device
-            # blocks that is a renumbering of `range_start` (metadata only)
+            """qc.py:657-667 -> MergeImpl.row_axis_merge (merge.py:104-252) with the per-block ``pandas.merge``
+            replaced by the device join functor (``modin_b200.merge``): many-to-one and many-to-many keys,
+            ``on`` or ``left_on`` / ``right_on``, how in {left, inner}."""
+            from .merge import row_axis_merge
             from .query_compiler import _reset_row_index
 
-            return self.__constructor__(_reset_row_index(new_frame))
+            return self.__constructor__(row_axis_merge(self, right, _reset_row_index, **kwargs))
 
     # ---------------------------------------------------------------- IO + factory
     class B200IO(BaseIO):

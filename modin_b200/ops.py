@@ -486,6 +486,41 @@ class JoinTable:
             pass
 
 
+def expand_matches(fact_keys: DeviceColumn, dim_keys: DeviceColumn, keep_misses: bool):
+    """Row pairs of a merge whose broadcast side has DUPLICATE keys (many-to-many): ``(left_rows, right_rows,
+    misses)`` -- int64 device columns of equal length, left order preserved, a left row's matches in their order of
+    appearance on the right, ``right_rows`` = -1 where a left row found nothing (kept only when ``keep_misses``, the
+    left join); ``misses`` = number of such left rows (host int).  Sort + run heads + a many-to-one probe of the
+    distinct keys + prefix sum + expansion, all on the device (csrc/expand.cu)."""
+    lib = _lib.load()
+    t = torch_mod()
+    st = current_stream()
+    nd, nf = len(dim_keys), len(fact_keys)
+    ks = map_columns("copy", [dim_keys])[0] if nd else dim_keys
+    order = iota(0, nd)
+    if nd:
+        sort_pairs(ks, order)
+    heads = DeviceColumn.empty(nd, np.int64)
+    _lib.check(lib.mb200_run_heads(ks.ptr, nd, heads.ptr, st))
+    starts, nuniq = compact_hits(heads)
+    uniq = take_columns([ks], starts)[0] if nuniq else DeviceColumn.empty(0, np.int64)
+    table = JoinTable(uniq)
+    try:
+        u, nmatch = table.probe(fact_keys)
+    finally:
+        table.close()
+    cnt, first, offsets = (DeviceColumn.empty(nf, np.int64) for _ in range(3))
+    _lib.check(lib.mb200_expand_counts(u.ptr, nf, starts.ptr, nuniq, nd, 1 if keep_misses else 0, cnt.ptr, first.ptr, st))
+    total = t.zeros(1, dtype=t.int64, device=current_device())
+    sb = lib.mb200_scan_scratch_bytes(nf)
+    scratch = _scratch(sb, "scan")
+    _lib.check(lib.mb200_scan_i64(cnt.ptr, nf, offsets.ptr, total.data_ptr(), scratch.data_ptr(), sb, st))
+    n_out, n_hit = (int(v) for v in t.cat([total, nmatch.reshape(1)]).tolist())  # one D2H sizes the result
+    left_rows, right_rows = DeviceColumn.empty(n_out, np.int64), DeviceColumn.empty(n_out, np.int64)
+    _lib.check(lib.mb200_expand_rows(offsets.ptr, cnt.ptr, first.ptr, order.ptr, nf, left_rows.ptr, right_rows.ptr, st))
+    return left_rows, right_rows, nf - n_hit
+
+
 def take_columns(cols: Sequence[DeviceColumn], idx: DeviceColumn) -> List[DeviceColumn]:
     lib = _lib.load()
     n = len(idx)
@@ -536,6 +571,26 @@ def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0, 
     fn = lib.mb200_gen_i64_skew if skew else lib.mb200_gen_i64
     _lib.check(fn(c.ptr, nrows, seed, col, row_offset, modulus, stats.data_ptr(), current_stream()))
     c.stats = KeyStats(dev=stats)
+    return c
+
+
+def iota(start: int, nrows: int) -> DeviceColumn:
+    """int64 column ``start, start + 1, ...``: the labels of a RangeIndex block as device data."""
+    lib = _lib.load()
+    c = DeviceColumn.empty(nrows, np.int64)
+    _lib.check(lib.mb200_iota_i64(c.ptr, nrows, int(start), current_stream()))
+    return c
+
+
+def full_column(nrows: int, dtype, value) -> DeviceColumn:
+    """Constant float64 / int64 column (NaN columns that re-indexing adds)."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype("float64"), np.dtype("int64")):
+        raise TypeError("constant device columns are float64 or int64")
+    c = DeviceColumn.empty(nrows, dtype)
+    bits = f64_bits(value) if dtype == np.float64 else i64_bits(value)
+    _lib.check(lib.mb200_fill_u64(c.ptr, nrows, bits, current_stream()))
     return c
 
 

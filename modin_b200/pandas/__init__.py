@@ -735,9 +735,15 @@ def concat(objs, *, axis=0, join="outer", ignore_index=False, **kwargs):
     if not objs or not all(isinstance(o, DataFrame) for o in objs):
         raise NotImplementedError("concat on the B200 path takes a list of device DataFrames")
     if axis in (1, "columns"):
-        frame = objs[0]._query_compiler._modin_frame
-        for o in objs[1:]:
-            frame = frame.hstack(o._query_compiler._modin_frame)
+        # PandasDataframe.concat(axis=1) (df.py:3952-4096) co-partitions the frames along the rows first: the row
+        # labels are joined (outer, in order of appearance -- pandas.concat does not sort) and frames whose labels
+        # differ are re-indexed on the device
+        if join != "outer":
+            raise NotImplementedError("concat(axis=1, join='inner') is not on the B200 path")
+        frames = [o._query_compiler._modin_frame for o in objs]
+        frame, rest = frames[0]._copartition_rows(frames[1:], how="outer", sort=False)
+        for o in rest:
+            frame = frame.hstack(o)
         return DataFrame(query_compiler=type(objs[0]._query_compiler)(frame))
     if axis not in (0, "index"):
         raise ValueError(f"No axis named {axis}")

@@ -281,35 +281,9 @@ class B200QueryCompiler:
 
     # ---- merge (qc.py:657-667 -> MergeImpl.row_axis_merge merge.py:104-252) --------------------------
     def merge(self, right, **kwargs):
-        how = kwargs.get("how", "inner")
-        on = kwargs.get("on")
-        left_on, right_on = kwargs.get("left_on"), kwargs.get("right_on")
-        if kwargs.get("left_index") or kwargs.get("right_index"):
-            raise NotImplementedError("index joins default to pandas in the reference (merge.py:129-136)")
-        if how not in ("left", "inner"):
-            raise NotImplementedError(f"merge(how={how!r}) defaults to pandas in the reference; not on the B200 path")
-        if on is None and left_on is not None and left_on == right_on:
-            on = left_on
-        if on is None or isinstance(on, (list, tuple)) and len(on) != 1:
-            raise NotImplementedError("device merge joins on exactly one int64 key column given by `on`")
-        if isinstance(on, (list, tuple)):
-            on = on[0]
-        suffixes = kwargs.get("suffixes", ("_x", "_y"))
-        # merge.py:178 -- all dim partitions collapsed into one and broadcast to every row partition
-        right_to_broadcast = right._modin_frame.combine()
-        func = DevMerge(on=on, how=how, suffixes=suffixes)
-        right_labels = [c for c in right.columns if c != on]
-        overlap = set(self.columns) & set(right_labels)
-        new_columns = pandas.Index(
-            [f"{c}{suffixes[0]}" if c in overlap else c for c in self.columns]
-            + [f"{c}{suffixes[1]}" if c in overlap else c for c in right_labels]
-        )
-        new_frame = self._modin_frame.broadcast_apply_full_axis(
-            axis=1, func=func, other=right_to_broadcast, keep_partitioning=True, new_columns=new_columns,
-            sync_labels=False,
-        )  # fmt: skip
-        # merge.py:236-250: the result index is reset to a fresh RangeIndex
-        return self.__constructor__(_reset_row_index(new_frame))
+        from .merge import row_axis_merge
+
+        return self.__constructor__(row_axis_merge(self, right, _reset_row_index, **kwargs))
 
 
 def _frame_device(frame):

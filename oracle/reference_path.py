@@ -408,3 +408,66 @@ def df_nunique(df, npartitions: int) -> pandas.Series:
     """qc.nunique (qc.py:1109-1113, range partitioning off): ``Reduce.register(pandas.DataFrame.nunique)`` -- a
     full-axis reduce, every column partition sees whole columns."""
     return reduce_full_axis(df, lambda full: full.nunique(), npartitions)
+
+
+# ------------------------------------------------------------------ _copartition with reindex (df.py:3709-3848)
+def copartition_rows(frames: Sequence[pandas.DataFrame], how: str, sort: Optional[bool], npartitions: int):
+    """``PandasDataframe._copartition(axis=0, ...)``: join the row labels (``_join_index_objects``, df.py:1984-2075:
+    ``left.join(right, how=how, sort=sort)`` pairwise; ``sort`` defaults to "the labels differ", df.py:3759-3760), then
+    every frame whose labels differ from the joined index is gathered along the rows, re-indexed
+    (``df.reindex(joined_index, axis=0)``, df.py:2073) and split at the base frame's row lengths (df.py:3799-3840).
+    Returns the aligned frames as partition grids plus the joined index."""
+    base = frames[0]
+    if all(base.index.equals(f.index) for f in frames[1:]):
+        return [split_into_partitions(f, npartitions) for f in frames], base.index
+    if sort is None:
+        sort = not all(base.index.equals(f.index) for f in frames[1:])
+    joined = base.index
+    for f in frames[1:]:
+        joined = joined.join(f.index, how=how, sort=sort)
+    aligned = [f if f.index.equals(joined) else f.reindex(joined, axis=0) for f in frames]
+    return [split_into_partitions(f, npartitions) for f in aligned], joined
+
+
+def n_ary_op_aligned(frames: Sequence[pandas.DataFrame], func: Callable, npartitions: int, join_type: str = "outer"):
+    """``PandasDataframe.n_ary_op`` (df.py:3851-3950) with the general ``_copartition``: align the rows, then
+    ``out[i, j] = func(left[i, j], *right[i, j])`` block by block."""
+    grids, _ = copartition_rows(list(frames), join_type, None, npartitions)
+    left = grids[0]
+    out = [[func(*[g[i][j].copy() for g in grids]) for j in range(len(row))] for i, row in enumerate(left)]
+    return to_pandas(out)
+
+
+def setitem_aligned(df: pandas.DataFrame, label, value: pandas.Series, npartitions: int) -> pandas.DataFrame:
+    """``df[label] = series`` (modin/pandas/dataframe.py ``__setitem__`` -> ``qc.insert`` / ``setitem``,
+    qc.py:3161-3247): the value is re-indexed on the frame's row labels (a LEFT join of the labels) and appended
+    as a column of every row partition."""
+    aligned = value if df.index.equals(value.index) else value.reindex(df.index)
+    blocks = split_into_partitions(df, npartitions)
+    vparts = split_into_partitions(aligned.to_frame(label), npartitions)
+    rows = [pandas.concat([pandas.concat(r, axis=1) if len(r) > 1 else r[0], v[0]], axis=1) for r, v in zip(blocks, vparts)]
+    return pandas.concat(rows, axis=0)
+
+
+def filter_rows_aligned(df: pandas.DataFrame, mask: pandas.Series, npartitions: int) -> pandas.DataFrame:
+    """``df[bool_series]`` with a mask on other row labels (qc.getitem_array -> ``__getitem_bool``, qc.py:3021-3103:
+    ``broadcast_apply(..., join_type="left")``): the mask is brought to the frame's labels first."""
+    return filter_rows(df, mask.reindex(df.index) if not df.index.equals(mask.index) else mask, npartitions)
+
+
+def concat_columns_aligned(frames: Sequence[pandas.DataFrame], npartitions: int) -> pandas.DataFrame:
+    """``concat(axis=1)`` of frames with different row labels (``PandasDataframe.concat``, df.py:3952-4096): rows
+    co-partitioned with an OUTER, unsorted join of the labels, then the column partitions are lined up."""
+    grids, joined = copartition_rows(list(frames), "outer", False, npartitions)
+    return pandas.concat([to_pandas(g) for g in grids], axis=1)
+
+
+def broadcast_merge_general(left, right, how: str, npartitions: int, on=None, left_on=None, right_on=None,
+                            suffixes=("_x", "_y")) -> pandas.DataFrame:  # fmt: skip
+    """``MergeImpl.row_axis_merge`` (merge.py:104-252) with everything ``pandas.merge`` accepts for the key: ``on`` or
+    ``left_on`` / ``right_on``; repeated right keys give one output row per match (many-to-many)."""
+    grid = split_into_partitions(left, npartitions)
+    row_blocks = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
+    kw = dict(on=on) if on is not None else dict(left_on=left_on, right_on=right_on)
+    outs = [pandas.merge(b.copy(), right.copy(), how=how, sort=False, suffixes=suffixes, **kw) for b in row_blocks]
+    return pandas.concat(outs, axis=0).reset_index(drop=True)

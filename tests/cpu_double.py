@@ -270,7 +270,14 @@ class JoinTable:
         return bool(self.index.is_unique)
 
     def _idx(self, fact_keys):
-        return self.index.get_indexer(_np(fact_keys)).astype(np.int64)
+        if self.index.is_unique:
+            return self.index.get_indexer(_np(fact_keys)).astype(np.int64)
+        # repeated dim keys: the device table keeps ONE row per key (hit / miss is what callers use it for)
+        uniq, first = np.unique(self.keys, return_index=True)
+        fk = _np(fact_keys)
+        pos = np.searchsorted(uniq, fk)
+        pos_c = np.minimum(pos, len(uniq) - 1)
+        return np.where(uniq[pos_c] == fk, first[pos_c], -1).astype(np.int64)
 
     def probe(self, fact_keys):
         idx = self._idx(fact_keys)
@@ -319,6 +326,30 @@ def cast_columns_i64(cols):
     return [_col(_np(c).astype(np.int64)) if c.dtype == np.bool_ else c for c in cols]
 
 
+def expand_matches(fact_keys, dim_keys, keep_misses):
+    fk, dk = _np(fact_keys), _np(dim_keys)
+    order = np.argsort(dk, kind="stable")
+    ks = dk[order]
+    lo, hi = np.searchsorted(ks, fk, side="left"), np.searchsorted(ks, fk, side="right")
+    cnt = hi - lo
+    out_cnt = np.where(cnt > 0, cnt, 1 if keep_misses else 0)
+    left = np.repeat(np.arange(len(fk), dtype=np.int64), out_cnt)
+    offs = np.concatenate([[0], np.cumsum(out_cnt)[:-1]]) if len(fk) else np.zeros(0, dtype=np.int64)
+    within = np.arange(len(left), dtype=np.int64) - np.repeat(offs, out_cnt)
+    src = np.repeat(lo, out_cnt) + within
+    hit = np.repeat(cnt > 0, out_cnt)
+    right = np.where(hit, order[np.minimum(src, max(len(order) - 1, 0))] if len(order) else -1, -1).astype(np.int64)
+    return _col(left), _col(right), int((cnt == 0).sum())
+
+
+def iota(start, nrows):
+    return _col(np.arange(start, start + nrows, dtype=np.int64))
+
+
+def full_column(nrows, dtype, value):
+    return _col(np.full(nrows, value, dtype=np.dtype(dtype)))
+
+
 @contextlib.contextmanager
 def installed():
     """Swap the device for the double (context manager used by the ``cpu_device`` fixture)."""
@@ -328,9 +359,10 @@ def installed():
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
                                         "compact_hits", "cast_columns_f64", "cast_columns_i64", "gen_f64", "gen_i64", "GroupTable",
-                                        "key_range_device", "sort_pairs")},
+                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches")},
     }  # fmt: skip
     ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
+    ops.iota, ops.full_column, ops.expand_matches = iota, full_column, expand_matches
     ops.cast_columns_i64 = cast_columns_i64
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device

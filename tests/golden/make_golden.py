@@ -66,6 +66,25 @@ def third_batch_frames(synth, n, nb, nan, G):
     return frames
 
 
+def fourth_batch_frames(synth):
+    """Inputs of the ``ext4`` cases (label alignment and many-to-many merge; shared with the tests): ``A`` on labels
+    0..n-1; ``B`` on a permutation of labels 300..300+n2-1 (partly overlapping ``A``); ``Bp`` on a permutation of
+    ``A``'s own labels; a fact / dim pair whose dim keys repeat."""
+    n, n2 = 2003, 1801
+    rng = np.random.RandomState(7)
+    A = synth.host_frame(n, 3, seed=51, nan_per_64k=2000)
+    B = synth.host_frame(n2, 3, seed=52, nan_per_64k=2000)
+    B.index = rng.permutation(np.arange(300, 300 + n2))
+    Bp = synth.host_frame(n, 3, seed=53)
+    Bp.index = rng.permutation(n)
+    fact = synth.host_frame(3000, 2, seed=42, key_modulus=200, key_seed=43)
+    dim = pandas.DataFrame({"key": np.concatenate([rng.permutation(200)[:150], rng.permutation(200)[:80]]).astype(np.int64)})
+    dim["d0"] = synth.gen_f64(len(dim), 11, 0)
+    dim["d1"] = np.arange(len(dim), dtype=np.int64) * 3 + 1
+    dim_u = dim.drop_duplicates("key").rename(columns={"key": "k"})
+    return A, B, Bp, fact, dim, dim_u
+
+
 def main():
     os.environ["MODIN_ENGINE"] = "python"
     apply_pandas3_shims()
@@ -209,6 +228,28 @@ def main():
         r = P(mdf[["key", "k2", "big"]].nunique())
         arrays["nunique"], arrays["nunique_cols"] = r.to_numpy(), np.array(list(r.index))
         save(f"ext3_n{n}_nan{nan}", meta=np.array([n, nb, nan, G]), **arrays)
+
+    # ---- fourth batch: row-label alignment (_copartition with reindex, df.py:3709-3848) and many-to-many merge
+    A, B, Bp, fact, dim, dim_u = fourth_batch_frames(synth)
+    mA, mB, mBp = mpd.DataFrame(A), mpd.DataFrame(B), mpd.DataFrame(Bp)
+    arrays = {}
+    for name, r in (("add", mA + mB), ("mul_add", mA * mB + mA), ("lt", mA < mBp)):
+        r = P(r)
+        arrays[name + "_index"], arrays[name] = r.index.to_numpy(), r.to_numpy(dtype=np.float64)
+    x = mA.copy()
+    x["d"] = mB["c0"]
+    arrays["setitem"] = P(x).to_numpy()
+    r = P(mA[mBp["c0"] > 0])
+    arrays["mask_index"], arrays["mask"] = r.index.to_numpy(), r.to_numpy()
+    r = P(mpd.concat([mA, mBp.rename(columns={"c0": "x", "c1": "y", "c2": "z"})], axis=1))
+    arrays["cat1_index"], arrays["cat1"] = r.index.to_numpy(), r.to_numpy()
+    mf = mpd.DataFrame(fact)
+    for how in ("left", "inner"):
+        r = P(mf.merge(mpd.DataFrame(dim), on="key", how=how))
+        arrays[f"m2m_{how}"], arrays[f"m2m_{how}_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
+    r = P(mf.merge(mpd.DataFrame(dim_u), left_on="key", right_on="k", how="left"))
+    arrays["lr_on"], arrays["lr_on_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
+    save("ext4_align_m2m", meta=np.array([2003, 1801]), **arrays)
 
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):

@@ -206,5 +206,6 @@ def test_reference_arm_prints_the_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "dtype", "data", "config", "cpu_baseline", "e2e"):  # fmt: skip
         assert key in j, key
-    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "reference"
+    assert "modin.pandas" in j["config"]["api"] and j["cpu_baseline"]["alongside"]["groupby_sum"]["checked"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0

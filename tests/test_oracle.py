@@ -253,3 +253,39 @@ def test_third_batch_against_reference(golden_dir):
         r = orc.df_nunique(df[["key", "k2", "big"]], NP)
         assert list(r.index) == list(z["nunique_cols"])
         assert_bit_equal(r.to_numpy(), z["nunique"], f"{name}:nunique")
+
+
+def test_fourth_batch_against_reference(golden_dir):
+    """Row-label alignment (``_copartition`` with reindex) and the general merge: restatements pinned to the
+    unmodified reference (tests/golden/ext4_align_m2m.npz)."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from make_golden import fourth_batch_frames
+
+    z = dict(np.load(os.path.join(golden_dir, "ext4_align_m2m.npz"), allow_pickle=False))
+    A, B, Bp, fact, dim, dim_u = fourth_batch_frames(synth)
+    add = lambda x, y: x + y  # noqa: E731
+    r = orc.n_ary_op_aligned([A, B], add, NP)
+    assert_bit_equal(r.index.to_numpy(), z["add_index"], "a + b labels (outer join, sorted)")
+    assert_bit_equal(r.to_numpy(), z["add"], "a + b")
+    r = orc.n_ary_op_aligned([orc.n_ary_op_aligned([A, B], lambda x, y: x * y, NP), A], add, NP)
+    assert_bit_equal(r.index.to_numpy(), z["mul_add_index"], "a * b + a labels")
+    assert_bit_equal(r.to_numpy(), z["mul_add"], "a * b + a")
+    r = orc.n_ary_op_aligned([A, Bp], lambda x, y: x < y, NP)
+    assert_bit_equal(r.index.to_numpy(), z["lt_index"], "a < b' labels")
+    assert_bit_equal(r.to_numpy(dtype=np.float64), z["lt"], "a < b'")
+    assert_bit_equal(orc.setitem_aligned(A, "d", B["c0"], NP).to_numpy(), z["setitem"], "df[d] = other series")
+    r = orc.filter_rows_aligned(A, Bp["c0"] > 0, NP)
+    assert_bit_equal(r.index.to_numpy(), z["mask_index"], "mask labels")
+    assert_bit_equal(r.to_numpy(), z["mask"], "df[mask on permuted labels]")
+    r = orc.concat_columns_aligned([A, Bp.rename(columns={"c0": "x", "c1": "y", "c2": "z"})], NP)
+    assert_bit_equal(r.index.to_numpy(), z["cat1_index"], "concat(axis=1) labels")
+    assert_bit_equal(r.to_numpy(), z["cat1"], "concat(axis=1)")
+    for how in ("left", "inner"):
+        r = orc.broadcast_merge_general(fact, dim, how, NP, on="key")
+        assert list(r.columns) == list(z[f"m2m_{how}_cols"])
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z[f"m2m_{how}"], f"many-to-many merge {how}")
+    r = orc.broadcast_merge_general(fact, dim_u, "left", NP, left_on="key", right_on="k")
+    assert list(r.columns) == list(z["lr_on_cols"])
+    assert_bit_equal(r.to_numpy(dtype=np.float64), z["lr_on"], "merge left_on / right_on")
