@@ -667,7 +667,9 @@ class DevAffine(DevFn):
         mul = list(self.mul) if isinstance(self.mul, (list, tuple, np.ndarray)) else [self.mul] * W
         add = list(self.add) if isinstance(self.add, (list, tuple, np.ndarray)) else [self.add] * W
         if block.nrows == 0 or not block.cols:
-            return block
+            # nothing to sweep, but the RESULT DTYPES still follow pandas (int64 * 2 + 1.5 is float64 on an empty frame
+            # too): the two un-fused steps know how to answer for empty blocks
+            return DevBinary("add")(DevBinary("mul")(block, self.mul), self.add)
         is_int = lambda v: isinstance(v, (int, np.integer)) and not isinstance(v, bool)  # noqa: E731
         cols, s0, s1 = [], [], []
         for c, m, a in zip(block.cols, mul, add):

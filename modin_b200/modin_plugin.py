@@ -60,11 +60,24 @@ def apply_pandas3_shims() -> None:
         if getattr(cls.groupby, "_mb200_shim", False):
             continue
         g = cls.groupby
-        wrapped = functools.wraps(g)(lambda self, *a, axis=0, _g=g, **k: _g(self, *a, **k))
+
+        def _groupby(self, *a, axis=0, _g=g, **k):
+            # pandas 3 removed ``axis=``; Modin still passes the default -- anything else must fail, not be ignored
+            if axis not in (0, "index"):
+                raise TypeError("groupby() got an unexpected keyword argument 'axis' (removed in pandas 3)")
+            return _g(self, *a, **k)
+
+        wrapped = functools.wraps(g)(_groupby)
         wrapped._mb200_shim = True
         cls.groupby = wrapped
         f = cls.fillna
-        cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: _f(self, *a, **k))
+
+        def _fillna(self, *a, method=None, downcast=None, _f=f, **k):
+            if method is not None or downcast is not None:
+                raise TypeError("fillna() got an unexpected keyword argument 'method' / 'downcast' (removed in pandas 3)")
+            return _f(self, *a, **k)
+
+        cls.fillna = functools.wraps(f)(_fillna)
 
 
 def register(shims: bool | None = None):

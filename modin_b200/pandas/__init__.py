@@ -569,12 +569,12 @@ def _multi_key_groupby(df: "DataFrame", by: list, groupby_kwargs: dict) -> "Data
     # global [min, max] of every key column (one all_gather across ranks so that every rank packs alike)
     mins, maxs = [], []
     for p in pos:
-        st = ops.key_range_device([b.cols[p] for b in rows])
+        lo, hi = ops.key_stats([b.cols[p] for b in rows])[:2]  # column metadata (cached after the first query)
         if dist.is_distributed():
-            per_rank = dist.all_gather_small(st[:2])
+            import torch
+
+            per_rank = dist.all_gather_small(torch.tensor([lo, hi], dtype=torch.int64, device=ops.current_device()))
             lo, hi = min(r[0] for r in per_rank), max(r[1] for r in per_rank)
-        else:
-            lo, hi = (int(v) for v in st[:2].tolist())
         if lo > hi:
             lo = hi = 0  # no rows anywhere
         mins.append(lo)
@@ -590,7 +590,9 @@ def _multi_key_groupby(df: "DataFrame", by: list, groupby_kwargs: dict) -> "Data
     for b in rows:
         packed = None
         for p, lo, s in zip(pos, mins, strides):
-            term = ops.map_columns("affine", [b.cols[p]], s0=[s], s1=[-lo * s])[0] if b.nrows else b.cols[p]
+            # (key - lo) * stride, in that order: -lo * stride alone need not fit int64 (epoch-ns keys next to a
+            # second key), the difference always does
+            term = ops.map_columns("mul_s", ops.map_columns("sub_s", [b.cols[p]], s0=[lo]), s0=[s])[0] if b.nrows else b.cols[p]
             packed = term if packed is None else ops.map_columns("add", [packed], [term])[0]
         cols = [b.cols[j] for j in keep] + [packed]
         labels = pandas.Index([df.columns[j] for j in keep] + [_PACKED_KEY])

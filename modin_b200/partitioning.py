@@ -145,6 +145,11 @@ def _block_operand(entry):
     return fn.op, allargs[0]
 
 
+def _entry_kwargs(entry):
+    func, _args, kwargs = entry
+    return {**unwrap(func)[2], **kwargs}
+
+
 def fuse_call_queue(queue: list) -> list:
     """Peephole fusion over adjacent queue entries:
     ``x * s`` ; ``+ t``   -> AFFINE(s, t)   (one sweep, two roundings)
@@ -162,7 +167,7 @@ def fuse_call_queue(queue: list) -> list:
                 continue
             fa, fb = _block_operand(cur), _block_operand(nxt)
             if fa and fb and fa[0] in ("mul", "rmul") and fb[0] in ("add", "radd"):
-                out.append([_Fma3Entry(fa[1], fb[1]), (), {}])
+                out.append([_Fma3Entry(fa[1], fb[1], _entry_kwargs(cur), _entry_kwargs(nxt)), (), {}])
                 i += 2
                 continue
         out.append(cur)
@@ -171,13 +176,27 @@ def fuse_call_queue(queue: list) -> list:
 
 
 class _Fma3Entry(DevFn):
+    """``a * b`` then ``+ c`` between blocks, met next to each other in a call queue.  One FMA3 sweep (two roundings)
+    when the three operands are float64 throughout, non-empty, identically shaped and labelled; anything else (int64
+    or mixed columns, empty blocks, a one-column operand to broadcast) runs the two ``DevBinary`` steps one after the
+    other, with their dtype promotion, label checks and empty-frame handling."""
+
     op = "fma3"
 
-    def __init__(self, b, c):
+    def __init__(self, b, c, kw_mul=None, kw_add=None):
         self.b, self.c = b, c
+        self.kw_mul, self.kw_add = dict(kw_mul or {}), dict(kw_add or {})
 
     def __call__(self, a):
-        return DevFma3()(a, _payload(self.b), _payload(self.c))
+        b, c = _payload(self.b), _payload(self.c)
+        fusable = (
+            a.nrows > 0 and a.nrows == b.nrows == c.nrows and len(a.cols) == len(b.cols) == len(c.cols)
+            and a.columns.equals(b.columns) and a.columns.equals(c.columns)
+            and all(x.dtype == np.float64 for blk in (a, b, c) for x in blk.cols)
+        )  # fmt: skip
+        if fusable:
+            return DevFma3()(a, b, c)
+        return DevBinary("add")(DevBinary("mul")(a, b, **self.kw_mul), c, **self.kw_add)
 
 
 def _payload(x):
