@@ -326,6 +326,17 @@ class Api:
         return obj
 
     @staticmethod
+    def launch(obj):
+        """Run the frame's pending work WITHOUT waiting for the device: ``qc.finalize()`` drains the call queues
+        (= launches the kernels on the rank's stream); ``qc.execute()`` would add ``wait_computations``.  The timed
+        region is bracketed by device synchronisations, the steps inside it are not -- the host prepares step i + 1
+        while the GPU runs step i, as any asynchronous engine is used."""
+        qc = getattr(obj, "_query_compiler", None)
+        if qc is not None:
+            qc.finalize()
+        return obj
+
+    @staticmethod
     def to_pandas(obj):
         return obj._to_pandas() if hasattr(obj, "_to_pandas") else obj
 
@@ -460,11 +471,28 @@ def run_b200_arm(args):
         sync_all()
         return max_over_ranks(total), per
 
-    def roof(kernel, bytes_per_launch_local, per_ms, traffic=None, **extra):
-        ach = bytes_per_launch_local / (statistics.mean(per_ms) / 1e3) / 1e9
+    from modin_b200 import ops as _ops
+
+    def kernel_ms(step_fn, tag, reps=3):
+        """Average duration of ONE launch of the dominant kernel (CUDA events around the C call on the launching
+        stream, ops.KernelTimer), over `reps` extra steps run after the timed region; max over ranks."""
+        with _ops.KernelTimer() as kt:
+            for _ in range(reps):
+                step_fn()
+            ms = kt.mean_ms(tag)
+        sync_all()
+        return max_over_ranks(ms) if ms is not None else None
+
+    def roof(kernel, bytes_per_launch_local, per_ms, traffic=None, launch_ms=None, **extra):
+        """`achieved` = algorithmic bytes of one launch / that kernel's own duration (`launch_ms`, CUDA events around
+        the launch); `step_frac` is the same bytes over the WHOLE step (API layer, small kernels, collectives)."""
+        step = statistics.mean(per_ms)
+        lm = launch_ms if launch_ms else step
+        ach = bytes_per_launch_local / (lm / 1e3) / 1e9
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch_local, "launch_ms": statistics.mean(per_ms), **extra}  # fmt: skip
+                "algorithmic_bytes_per_launch": bytes_per_launch_local, "launch_ms": lm, "step_ms": step,
+                "step_frac": bytes_per_launch_local / (step / 1e3) / 1e9 / hbm_peak, **extra}  # fmt: skip
 
     def sample_rows(n):
         return sorted({0, 1, min(4095, n - 1), min(4096, n - 1), n // 2, n - 1}) if n > 0 else []
@@ -489,7 +517,7 @@ def run_b200_arm(args):
     def step_map():
         last[0] = None  # the previous result (64 GB at 1e9 rows) goes back to the allocator first
         out = a * B_SCALAR + C_SCALAR  # Binary template x2 -> call queue -> one AFFINE sweep
-        api.execute(out)
+        api.launch(out)
         last[0] = out
 
     sampler = ClockSampler(local)
@@ -508,7 +536,7 @@ def run_b200_arm(args):
     ms_per_step = total_ms / args.steps
     value = rows / (ms_per_step / 1e3)
     roofline = roof("map_kernel<AFFINE,f64> (256-bit column sweep)", rows_local * W * 16, per,
-                    traffic_for("map_affine", rows_local))  # fmt: skip
+                    traffic_for("map_affine", rows_local), launch_ms=kernel_ms(step_map, "map_affine"))  # fmt: skip
     # check (outside the timed region): sampled rows against the numpy twin of the generator, bit for bit
     blk = api.blocks(last[0])[0]
     idx = sample_rows(blk.nrows)
@@ -542,10 +570,10 @@ def run_b200_arm(args):
         res = {}
 
         def step_sum():
-            res["sum"] = api.execute(c3.sum())
+            res["sum"] = api.launch(c3.sum())
 
         def step_mean():
-            res["mean"] = api.execute(c3.mean())
+            res["mean"] = api.launch(c3.mean())
 
         for name, fn in (("sum", step_sum), ("mean", step_mean)):
             total_s, per_s = timed(fn, ksteps, 2)
@@ -559,7 +587,8 @@ def run_b200_arm(args):
                          "value": rows / (total_s / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_s / ksteps,
                          "checked": bool(ok),
                          "roofline": roof("reduce_tma_kernel<SUM,f64> + reduce_finalize" + (" (+ count, divide)" if name == "mean" else ""),
-                                          rows_local * W3 * 8, per_s, traffic_for("reduce_sum", rows_local * 2))})  # fmt: skip
+                                          rows_local * W3 * 8, per_s, traffic_for("reduce_sum", rows_local * 2),
+                                          launch_ms=kernel_ms(fn, "reduce_sum"))})  # fmt: skip
         del c3, res
         torch.cuda.empty_cache()
 
@@ -574,7 +603,7 @@ def run_b200_arm(args):
         def step_fma3():
             last[0] = None
             out = fa * fb + fc  # two n_ary_op calls -> call queue -> one FMA3 sweep (two roundings)
-            api.execute(out)
+            api.launch(out)
             last[0] = out
 
         total_f, per_f = timed(step_fma3, ksteps, 2)
@@ -587,7 +616,7 @@ def run_b200_arm(args):
         last[0] = None
         also.append({"metric": f"rows/sec a*b+c on three frames ({rows3}x8 f64 each), Binary template x2 fused",
                      "value": rows3 / (total_f / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_f / ksteps, "checked": ok,
-                     "roofline": roof("map_kernel<FMA3,f64>", blk.nrows * W * 32, per_f)})  # fmt: skip
+                     "roofline": roof("map_kernel<FMA3,f64>", blk.nrows * W * 32, per_f, launch_ms=kernel_ms(step_fma3, "map_fma3"))})  # fmt: skip
         del fa, fb, fc, blk
         torch.cuda.empty_cache()
 
@@ -600,10 +629,11 @@ def run_b200_arm(args):
 
             def step_gb():
                 last[0] = None
-                last[0] = api.execute(g.groupby("key").sum())
+                last[0] = api.launch(g.groupby("key").sum())
 
             try:
                 total_g, per_g = timed(step_gb, ksteps, 2)
+                k_ms = kernel_ms(step_gb, "gb_accumulate")
                 # ---- checks, outside the timed region
                 res = api.to_pandas(last[0])  # gathers every rank's key range: G x 8 (72 MB at G = 1e6)
                 last[0] = None
@@ -625,7 +655,8 @@ def run_b200_arm(args):
                 ok = all_ranks_ok(ok)
             finally:
                 _cfg.GroupbyDenseKeys.put(True)
-            rf = roof(kern, rows_local * (8 + 8 * W), per_g, traffic_for(traffic_key, rows_local) if traffic_key else None)
+            rf = roof(kern, rows_local * (8 + 8 * W), per_g, traffic_for(traffic_key, rows_local) if traffic_key else None,
+                      launch_ms=k_ms)
             entry = {"metric": f"rows/sec groupby('key').sum() {rows} rows, {G} int64 keys{label}, 8 f64 vals",
                      "value": rows / (total_g / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_g / ksteps,
                      "groups": int(len(keys)), "checked": ok, "roofline": rf}  # fmt: skip
@@ -667,7 +698,7 @@ def run_b200_arm(args):
 
         def step_merge():
             last[0] = None
-            last[0] = api.execute(fact.merge(dim, on="key", how="left"))
+            last[0] = api.launch(fact.merge(dim, on="key", how="left"))
 
         for dense_on, label, kern in (
             (True, "", "join_dense_build + join_dense_probe (direct-addressed dim table, fused payload gather)"),
@@ -679,6 +710,7 @@ def run_b200_arm(args):
                 os.environ["MB200_JOIN_DENSE"] = "0"
             try:
                 total_m, per_m = timed(step_merge, ksteps, 2)
+                km_ms = kernel_ms(step_merge, "join_probe_gather")
             finally:
                 os.environ.pop("MB200_JOIN_DENSE", None)
             blk = api.blocks(last[0])[0]
@@ -691,11 +723,11 @@ def run_b200_arm(args):
             last[0] = None
             ms_m = total_m / ksteps
             moved16, moved152 = rows_local * 16, rows_local * 152
-            rf = roof(kern, moved16, per_m)
+            rf = roof(kern, moved16, per_m, launch_ms=km_ms)
             rf["note"] = ("algorithmic bytes = 16 B/row: key read + payload written -- the fact columns of the result are "
                           "shared by reference, never copied; SURVEY 8(d) counts the reference's materialised output, "
                           "152 B/row: see frac_vs_152B_row")
-            rf["frac_vs_152B_row"] = moved152 / (statistics.mean(per_m) / 1e3) / 1e9 / hbm_peak
+            rf["frac_vs_152B_row"] = moved152 / (rf["launch_ms"] / 1e3) / 1e9 / hbm_peak
             also.append({"metric": f"rows/sec fact.merge(dim, on='key', how='left'), {rows} fact rows x {ndim} dim rows{label}",
                          "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "checked": ok, "roofline": rf})  # fmt: skip
             del blk
@@ -739,9 +771,10 @@ def run_b200_arm(args):
 
         with dist.local_frames():  # every rank runs the same host-to-host pipeline on ITS OWN host frame
             try:
-                host = hostpath.pinned_frame({f"c{j}": (er, np.float64) for j in range(W)})
+                arrs = {f"c{j}": hostpath.pinned_array(er, np.float64) for j in range(W)}
                 for j in range(W):
-                    fill(host[f"c{j}"].to_numpy(), 42, j)
+                    fill(arrs[f"c{j}"], 42, j)
+                host = pandas.DataFrame(arrs, copy=False)  # columns stay the pinned buffers (no consolidation)
                 out = [None]
 
                 def step_e2e():
@@ -757,16 +790,16 @@ def run_b200_arm(args):
                        "d2h_bytes_per_step": er * W * 8, "rows_per_step": er * ws, "ms_per_step": dt, "checked": bool(ok),
                        "path": f"{api.name}: pd.DataFrame(host) * b + c -> _to_pandas(); pinned host frame in, pooled "
                                "pinned columns out; HostBlock -> mb200_map_host (H2D / AFFINE / D2H on three streams)"}  # fmt: skip
-                del got, out, host
+                del got, out, host, arrs
             except Exception as exc:
                 e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "error": f"{type(exc).__name__}: {exc}"[:300]}
             try:
-                data = {"key": (er, np.int64), **{f"c{j}": (er, np.float64) for j in range(W)}}
-                host = hostpath.pinned_frame(data)
-                host["key"].to_numpy()[:] = np.resize(synth.gen_i64(min(er, 1 << 22), 43, 0, G), er)
+                arrs = {"key": hostpath.pinned_array(er, np.int64), **{f"c{j}": hostpath.pinned_array(er, np.float64) for j in range(W)}}
+                arrs["key"][:] = np.resize(synth.gen_i64(min(er, 1 << 22), 43, 0, G), er)
                 for j in range(W):
-                    fill(host[f"c{j}"].to_numpy(), 42, j)
+                    fill(arrs[f"c{j}"], 42, j)
+                host = pandas.DataFrame(arrs, copy=False)
                 out = [None]
 
                 def step_e2e_gb():
@@ -784,7 +817,7 @@ def run_b200_arm(args):
                                "d2h_bytes_per_step": int(len(got)) * (8 + 8 * W), "rows_per_step": er * ws,
                                "ms_per_step": dt, "checked": bool(ok),
                                "path": f"{api.name}: pd.DataFrame(host).groupby('key').sum()._to_pandas()"}  # fmt: skip
-                del got, out, host
+                del got, out, host, arrs
             except Exception as exc:
                 e2e_groupby = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
         if distributed:

@@ -256,6 +256,15 @@ int mb200_gb_emit(mb200_gb_table* table, int64_t ngroups, int sort, int64_t* out
                   void* const* out_sums, void* const* out_cnts, int64_t* out_sizes,
                   void* scratch, mb200_stream_t stream);
 
+/* Sync-free emit of a DENSE table: the outputs have room for `capacity` groups (>= the table's window), the number of
+ * groups actually written (ascending keys, first entries of every output) is decided on the device and left, with the
+ * table's overflow flag, in count_overflow_dev[2] (device int64) -- no host round trip sits between the accumulate
+ * and the emit, so a stream of groupby queries keeps the GPU busy while the host prepares the next one.  Scratch as
+ * for mb200_gb_emit(capacity). */
+int mb200_gb_emit_dense_async(mb200_gb_table* table, int64_t capacity, int64_t* out_keys,
+                              void* const* out_sums, void* const* out_cnts, int64_t* out_sizes,
+                              void* scratch, int64_t* count_overflow_dev, mb200_stream_t stream);
+
 /* ======================= broadcast hash join =============================== */
 typedef struct mb200_join_table mb200_join_table;
 /* Build a hash table over the (broadcast) right/dim key column.

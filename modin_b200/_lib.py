@@ -79,6 +79,7 @@ _SIGNATURES = {
     "mb200_gb_ngroups": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(C.c_int), _vp]),
     "mb200_gb_emit_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_gb_emit": (C.c_int, [_vp, _i64, C.c_int, _vp, _vpp, _vpp, _vp, _vp, _vp]),
+    "mb200_gb_emit_dense_async": (C.c_int, [_vp, _i64, _vp, _vpp, _vpp, _vp, _vp, _vp, _vp]),
     "mb200_join_build": (C.c_int, [_vpp, _vp, _i64, _vp]),
     "mb200_join_destroy": (C.c_int, [_vp, _vp]),
     "mb200_join_is_unique": (C.c_int, [_vp, C.POINTER(C.c_int), _vp]),

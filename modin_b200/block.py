@@ -192,8 +192,8 @@ class NotOnDevicePath(NotImplementedError, AttributeError):
 class DeviceBlock:
     """Columnar device block = payload of one block partition."""
 
-    __slots__ = ("cols", "columns", "index_cols", "index_names", "range_start", "nrows", "index_host", "replicated",
-                 "keys_sorted_unique")
+    __slots__ = ("cols", "columns", "index_cols", "index_names", "range_start", "_nrows", "_pending", "index_host",
+                 "replicated", "keys_sorted_unique")
 
     def __init__(
         self,
@@ -224,14 +224,49 @@ class DeviceBlock:
                 nrows = len(index_host)
             else:
                 nrows = 0
-        self.nrows = int(nrows)
+        self._nrows = int(nrows)
+        self._pending = None
         for c in self.cols:
-            if len(c) != self.nrows:
+            if len(c) != self._nrows:
                 raise ValueError("ragged device block")
         self.range_start = int(range_start)
         self.index_cols = list(index_cols) if index_cols else None
         self.index_names = list(index_names) if index_names else None
         self.index_host = index_host  # only for small blocks (reduction results etc.)
+
+    # ---- row count: normally a host integer; a block whose size is decided ON THE DEVICE (the emit of a group table)
+    # carries buffers of the largest possible size plus the device-side count, and learns its row count -- one 16-byte
+    # D2H, the buffers trimmed to views -- only when somebody asks.  Until then nothing waits for the GPU.
+    @property
+    def nrows(self) -> int:
+        if self._pending is not None:
+            self._resolve()
+        return self._nrows
+
+    @nrows.setter
+    def nrows(self, value):
+        self._nrows = int(value)
+
+    @classmethod
+    def with_device_count(cls, cols, columns, count_dev, index_cols=None, index_names=None, check=None):
+        """Block over buffers of CAPACITY rows of which the first ``count_dev[0]`` (a device int64) are valid;
+        ``check(values: list)`` is called with ``count_dev.tolist()`` when the count is read back (to raise on flags
+        stored behind the count)."""
+        cap = len(cols[0]) if cols else (len(index_cols[0]) if index_cols else 0)
+        blk = cls(cols, columns, nrows=cap, index_cols=index_cols, index_names=index_names)
+        blk._pending = (count_dev, check)
+        return blk
+
+    def _resolve(self):
+        count_dev, check = self._pending
+        self._pending = None
+        vals = [int(v) for v in count_dev.tolist()]
+        if check is not None:
+            check(vals)
+        n = vals[0]
+        for c in list(self.cols) + list(self.index_cols or []):
+            c.data = c.data[:n]
+        self._nrows = n
 
     def __getattr__(self, name):
         # only reached when normal lookup fails (every slot is set in __init__)

@@ -113,3 +113,12 @@ class GroupbyDenseKeys(Parameter):
     varname = "MB200_GB_DENSE"
     default = True
     type = bool
+
+
+class GroupbyAsyncEmit(Parameter):
+    """Dense group tables are emitted without a host round trip (the result block is sized on the device and reads
+    its row count back lazily); off = count first, then emit exactly that many rows."""
+
+    varname = "MB200_GB_ASYNC_EMIT"
+    default = True
+    type = bool

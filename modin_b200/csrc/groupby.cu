@@ -776,6 +776,7 @@ __global__ void __launch_bounds__(256) gb_collect_kernel(const Slot* __restrict_
 }
 
 struct EmitParams {
+  const int* count_dev;  // when set: the number of valid groups lives on the device (sync-free dense emit)
   const long long* keys_sorted;
   const long long* perm;
   const double* acc;
@@ -794,6 +795,7 @@ struct EmitParams {
 __global__ void gb_emit_kernel(const __grid_constant__ EmitParams p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.ngroups) return;
+  if (p.count_dev && i >= (long long)*p.count_dev) return;
   const long long g = p.perm[i];
   if (p.out_keys) p.out_keys[i] = p.keys_sorted[i];
   if (p.out_sizes && p.size) p.out_sizes[i] = p.size[g];
@@ -1442,9 +1444,35 @@ extern "C" size_t mb200_gb_emit_scratch_bytes(int64_t ngroups) {
   return (size_t)ngroups * 16 + 512 + sort_scratch_bytes(ngroups);
 }
 
+namespace mb200 {
+__global__ void gb_export_meta_kernel(const GbMeta* meta, long long* out2) {
+  out2[0] = meta->ngroups;
+  out2[1] = meta->overflow;
+}
+}  // namespace mb200
+
+static int gb_emit_impl(mb200_gb_table* t, int64_t ngroups, int sort, int64_t* out_keys, void* const* out_sums,
+                        void* const* out_cnts, int64_t* out_sizes, void* scratch, int64_t* count_overflow_dev,
+                        mb200_stream_t stream);
+
 extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64_t* out_keys,
                              void* const* out_sums, void* const* out_cnts, int64_t* out_sizes, void* scratch,
                              mb200_stream_t stream) {
+  return gb_emit_impl(t, ngroups, sort, out_keys, out_sums, out_cnts, out_sizes, scratch, nullptr, stream);
+}
+
+extern "C" int mb200_gb_emit_dense_async(mb200_gb_table* t, int64_t capacity, int64_t* out_keys, void* const* out_sums,
+                                         void* const* out_cnts, int64_t* out_sizes, void* scratch,
+                                         int64_t* count_overflow_dev, mb200_stream_t stream) {
+  if (!t || !t->dense) return fail("mb200_gb_emit_dense_async", "not a dense table");
+  if (!count_overflow_dev) return fail("mb200_gb_emit_dense_async", "null count output");
+  if (capacity < t->win_hi - t->win_lo) return fail("mb200_gb_emit_dense_async", "capacity below the window size");
+  return gb_emit_impl(t, capacity, 0, out_keys, out_sums, out_cnts, out_sizes, scratch, count_overflow_dev, stream);
+}
+
+static int gb_emit_impl(mb200_gb_table* t, int64_t ngroups, int sort, int64_t* out_keys, void* const* out_sums,
+                        void* const* out_cnts, int64_t* out_sizes, void* scratch, int64_t* count_overflow_dev,
+                        mb200_stream_t stream) {
   if (!t) return fail("mb200_gb_emit", "null table");
   if (ngroups < 0 || ngroups > t->gcap) return fail("mb200_gb_emit", "ngroups out of range");
   if (ngroups == 0) return 0;
@@ -1492,6 +1520,13 @@ extern "C" int mb200_gb_emit(mb200_gb_table* t, int64_t ngroups, int sort, int64
   }
   EmitParams p;
   memset(&p, 0, sizeof(p));
+  if (count_overflow_dev) {
+    // the group count stays on the device: dense_scan_kernel left it in meta->ngroups; export {count, overflow}
+    // for the caller (the table may be destroyed before anybody reads them) and bound the emit by it
+    gb_export_meta_kernel<<<1, 1, 0, st>>>(t->meta, reinterpret_cast<long long*>(count_overflow_dev));
+    MB_LAUNCH_CHECK("gb_export_meta_kernel");
+    p.count_dev = &t->meta->ngroups;
+  }
   p.keys_sorted = keys_by_gid;
   p.perm = perm;
   p.acc = t->acc;

@@ -66,6 +66,8 @@ def _is_scalar(x) -> bool:
 def _check_block(x, who):
     if not isinstance(x, DeviceBlock):
         raise TypeError(f"{who} expects a DeviceBlock partition payload, got {type(x).__name__}")
+    if x._pending is not None:
+        x.nrows  # sized on the device: read the count back (and trim the buffers) before any kernel sees the block
 
 
 class DevMap(DevFn):
@@ -1084,7 +1086,7 @@ class DevGroupbyMap(DevFn):
         return _partial_block(self.agg, keys, key_label, sums, cnts, sizes, labels)
 
 
-def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels):
+def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels, count_dev=None, check=None):
     if agg in ("sum", "min", "max"):
         cols, cl = sums, labels
     elif agg == "count":
@@ -1094,7 +1096,10 @@ def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels):
     else:  # mean: sums then counts
         cols = list(sums) + list(cnts)
         cl = pandas.MultiIndex.from_tuples([("sum", c) for c in labels] + [("count", c) for c in labels])
-    blk = DeviceBlock(cols, cl, nrows=len(keys), index_cols=[keys], index_names=[key_label])
+    if count_dev is not None:
+        blk = DeviceBlock.with_device_count(cols, cl, count_dev, index_cols=[keys], index_names=[key_label], check=check)
+    else:
+        blk = DeviceBlock(cols, cl, nrows=len(keys), index_cols=[keys], index_names=[key_label])
     blk.keys_sorted_unique = True
     return blk
 
@@ -1186,7 +1191,7 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
     the general map -> exchange -> reduce path).  Every rank takes the same decision: it is made on the
     all-reduced key range and row count."""
     from . import dist
-    from .config import GroupbyDenseKeys
+    from .config import GroupbyAsyncEmit, GroupbyDenseKeys
 
     if not GroupbyDenseKeys.get() or map_fn.agg != reduce_fn.agg or not blocks or len(blocks) != len(by_blocks):
         return None
@@ -1239,6 +1244,17 @@ def fused_dense_groupby(map_fn: "DevGroupbyMap", reduce_fn: "DevGroupbyReduce", 
             # no sort, no pivots) and emits it; the rank-ordered results are the reference's key-sorted frame
             mine = table.reduce_scatter(chunk, dist.reduce_scatter, dist.rank())
         emitter = mine if mine is not None else table
+        if agg != "mean" and GroupbyAsyncEmit.get():
+            # no host round trip: the result block is sized on the device and learns its row count when somebody
+            # asks (DeviceBlock.with_device_count) -- the host is free to prepare the next query meanwhile
+            keys, sums, cnts, sizes, count = emitter.emit_async()
+
+            def check(vals):
+                if vals[1]:
+                    raise _lib.B200Error("dense group table saw a key outside its measured range")
+
+            part = _partial_block(agg, keys, key_label, sums, cnts, sizes, labels, count_dev=count, check=check)
+            return part
         ng, overflow = emitter.ngroups()
         if overflow:
             raise _lib.B200Error("dense group table saw a key outside its measured range")

@@ -18,6 +18,52 @@ from .block import DeviceColumn, KeyStats, current_device, current_stream, torch
 _scratch_cache = {}
 
 
+class KernelTimer:
+    """Measurement hook (bench.py): while installed, the wrappers of the dominant kernels bracket their C call with
+    CUDA events on the launching stream, so that a kernel's own duration can be read apart from the step around it.
+    ``with KernelTimer() as kt: ...; kt.mean_ms("gb_accumulate")`` (synchronises when read)."""
+
+    active = None
+
+    def __init__(self):
+        self.events = {}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+        return False
+
+    def mean_ms(self, tag):
+        torch_mod().cuda.synchronize()
+        ev = self.events.get(tag, [])
+        return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else None
+
+    def launches(self, tag):
+        return len(self.events.get(tag, []))
+
+
+class _timed:
+    """Bracket one C call with events when a KernelTimer is installed (no-op otherwise)."""
+
+    def __init__(self, tag):
+        self.tag, self.kt = tag, KernelTimer.active
+
+    def __enter__(self):
+        if self.kt is not None:
+            t = torch_mod()
+            self.a, self.b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.kt is not None:
+            self.b.record()
+            self.kt.events.setdefault(self.tag, []).append((self.a, self.b))
+        return False
+
+
 def _scratch(nbytes: int, tag: str = "default"):
     """Per-device reusable scratch buffer (grown geometrically)."""
     t = torch_mod()
@@ -86,7 +132,8 @@ def map_columns(
             o = _lib.ptr_array([x.ptr for x in outs])
             s0a = _scalar_bits([s0[j] for j in sel], code) if s0 is not None else None
             s1a = _scalar_bits([s1[j] for j in sel], code) if s1 is not None else None
-            _lib.check(lib.mb200_map(_lib.OP[op], code, len(sel), a, b, c, o, n, s0a, s1a, current_stream()))
+            with _timed("map_" + op):
+                _lib.check(lib.mb200_map(_lib.OP[op], code, len(sel), a, b, c, o, n, s0a, s1a, current_stream()))
             for j, x in zip(sel, outs):
                 out[j] = x
     return out  # type: ignore[return-value]
@@ -152,12 +199,13 @@ def reduce_columns(op: str, cols: Sequence[DeviceColumn], skipna: bool = True, v
                     )
                 )  # fmt: skip
             else:
-                _lib.check(
-                    lib.mb200_reduce_columns(
-                        _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, oval.data_ptr(), ocnt.data_ptr(),
-                        scratch.data_ptr(), variant, current_stream(),
-                    )
-                )  # fmt: skip
+                with _timed("reduce_" + op):
+                    _lib.check(
+                        lib.mb200_reduce_columns(
+                            _lib.RED[op], code, len(sel), ptrs, n, 1 if skipna else 0, oval.data_ptr(), ocnt.data_ptr(),
+                            scratch.data_ptr(), variant, current_stream(),
+                        )
+                    )  # fmt: skip
             for pos, j in enumerate(sel):
                 vals[j] = oval[pos : pos + 1]
                 cnts[j] = ocnt[pos : pos + 1]
@@ -250,7 +298,8 @@ class GroupTable:
             if v.dtype != np.float64:
                 raise TypeError("device groupby aggregates float64 value columns")
         ptrs = _lib.ptr_array([v.ptr for v in vals])
-        _lib.check(self.lib.mb200_gb_accumulate(self.handle, keys.ptr, ptrs, len(keys), current_stream()))
+        with _timed("gb_accumulate"):
+            _lib.check(self.lib.mb200_gb_accumulate(self.handle, keys.ptr, ptrs, len(keys), current_stream()))
 
     def merge_partial(self, keys: DeviceColumn, sums, cnts=None, sizes: Optional[DeviceColumn] = None):
         ps = _lib.ptr_array([v.ptr for v in sums]) if sums else None
@@ -282,6 +331,30 @@ class GroupTable:
             )
         )  # fmt: skip
         return keys, sums, cnts, sizes
+
+    def emit_async(self):
+        """Dense tables: emit WITHOUT asking the device how many groups there are -- the outputs have room for every
+        key of the table's range, the count is left in a device int64[2] ``{groups, overflow}``
+        (``mb200_gb_emit_dense_async``).  Returns ``(keys, sums, cnts, sizes, count_dev)``; the columns are valid up
+        to ``count_dev[0]``."""
+        t = torch_mod()
+        cap = self.capacity
+        keys = DeviceColumn.empty(cap, np.int64)
+        has_acc = self.flags & (_lib.GB_SUM | _lib.GB_MIN | _lib.GB_MAX)
+        sums = [DeviceColumn.empty(cap, np.float64) for _ in range(self.nvals)] if has_acc else None
+        cnts = [DeviceColumn.empty(cap, np.int64) for _ in range(self.nvals)] if self.flags & _lib.GB_COUNT else None
+        sizes = DeviceColumn.empty(cap, np.int64) if self.flags & _lib.GB_SIZE else None
+        count = t.empty(2, dtype=t.int64, device=current_device())
+        scratch = _scratch(self.lib.mb200_gb_emit_scratch_bytes(cap), "gb_emit")
+        _lib.check(
+            self.lib.mb200_gb_emit_dense_async(
+                self.handle, cap, keys.ptr,
+                _lib.ptr_array([c.ptr for c in sums]) if sums else None,
+                _lib.ptr_array([c.ptr for c in cnts]) if cnts else None,
+                sizes.ptr if sizes is not None else None, scratch.data_ptr(), count.data_ptr(), current_stream(),
+            )
+        )  # fmt: skip
+        return keys, sums, cnts, sizes, count
 
     def close(self):
         if self.handle:
@@ -463,13 +536,14 @@ class JoinTable:
             if code == _lib.U8:
                 raise TypeError("bool payload columns are not on the device merge path")
             sel_out = [DeviceColumn.empty(n, dim_cols[j].dtype) for j in idxs]
-            _lib.check(
-                self.lib.mb200_join_probe_gather(
-                    self.handle, fact_keys.ptr, n, len(idxs), _lib.ptr_array([dim_cols[j].ptr for j in idxs]), code,
-                    _lib.ptr_array([c.ptr for c in sel_out]), nm.data_ptr() if code == count_code else None,
-                    current_stream(),
-                )
-            )  # fmt: skip
+            with _timed("join_probe_gather"):
+                _lib.check(
+                    self.lib.mb200_join_probe_gather(
+                        self.handle, fact_keys.ptr, n, len(idxs), _lib.ptr_array([dim_cols[j].ptr for j in idxs]), code,
+                        _lib.ptr_array([c.ptr for c in sel_out]), nm.data_ptr() if code == count_code else None,
+                        current_stream(),
+                    )
+                )  # fmt: skip
             for j, c in zip(idxs, sel_out):
                 outs[j] = c
         return outs, nm

@@ -304,7 +304,10 @@ class B200Partition:
 
     def get(self):
         self.drain_call_queue()
-        return self._on_device()
+        block = self._on_device()
+        if getattr(block, "_pending", None) is not None:
+            block.nrows  # a block sized on the device learns its row count (and trims its buffers) before anyone reads it
+        return block
 
     @property
     def list_of_blocks(self):

@@ -257,6 +257,21 @@ class GroupTable:
             sizes = _col(self.size.numpy()[g])
         return _col((g + self.kbase).astype(np.int64)), sums, cnts, sizes
 
+    def emit_async(self):
+        ng, _ = self.ngroups()
+        keys, sums, cnts, sizes = self.emit(ng, sort=False)
+        lo, hi = self.win
+        cap = hi - lo
+
+        def pad(col):
+            if col is None:
+                return None
+            a = _np(col)
+            return _col(np.concatenate([a, np.zeros(cap - len(a), dtype=a.dtype)]))
+
+        return (pad(keys), [pad(c) for c in sums] if sums else None, [pad(c) for c in cnts] if cnts else None, pad(sizes),
+                torch.tensor([ng, 0], dtype=torch.int64))
+
     def close(self):
         pass
 
