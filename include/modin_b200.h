@@ -312,6 +312,12 @@ int mb200_scan_i64(const int64_t* values, int64_t n, int64_t* out_offsets, int64
 int mb200_expand_rows(const int64_t* offsets, const int64_t* cnt, const int64_t* first, const int64_t* order,
                       int64_t n, int64_t* out_left, int64_t* out_right, mb200_stream_t stream);
 
+/* Range-partitioning shuffle, split step (ShuffleSortFunctions.split_partitions, dfutils.py:355-475: np.digitize of
+ * the key column against the sampled pivots): out_bins[i] = number of pivots <= values[i]; pivots_dev ascending,
+ * npivots <= 1023.  Keys go in as their order-preserving int64 image (MB200_OP_ORDERED_S). */
+int mb200_digitize_i64(const int64_t* values, int64_t n, const int64_t* pivots_dev, int npivots,
+                       int64_t* out_bins, mb200_stream_t stream);
+
 /* ======================= synthetic data (from_map-style generators) ======== */
 /* Counter-based generators, reproducible for any row range; the numpy twin lives in
  * modin_b200/synth.py.  value(row, col) depends only on (seed, col, row_offset + i).

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "mb200_scan_scratch_bytes": (C.c_size_t, [_i64]),
     "mb200_scan_i64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "mb200_expand_rows": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mb200_digitize_i64": (C.c_int, [_vp, _i64, _vp, C.c_int, _vp, _vp]),
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
     "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),

@@ -143,6 +143,28 @@ __global__ void __launch_bounds__(256) expand_rows_kernel(const long long* __res
   }
 }
 
+// bins[i] = number of pivots <= values[i] (np.digitize(values, pivots, right=False) for ascending pivots): the split
+// step of the range-partitioning shuffle (ShuffleSortFunctions.split_partitions, dfutils.py:355-475).  Up to 1023
+// pivots live in shared memory; binary search per row.
+__global__ void __launch_bounds__(256) digitize_kernel(const long long* __restrict__ values, long long n,
+                                                       const long long* __restrict__ pivots, int npivots,
+                                                       long long* __restrict__ bins) {
+  __shared__ long long s_piv[1024];
+  for (int i = threadIdx.x; i < npivots; i += blockDim.x) s_piv[i] = pivots[i];
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long v = values[i];
+    int lo = 0, hi = npivots;  // first pivot > v
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_piv[mid] <= v) lo = mid + 1;
+      else hi = mid;
+    }
+    bins[i] = lo;
+  }
+}
+
 static int grid_for(long long n, const DevProps& dp) {
   long long g = (n + 255) / 256;
   const long long cap = (long long)dp.sm_count * 16;
@@ -218,5 +240,19 @@ extern "C" int mb200_expand_rows(const int64_t* offsets, const int64_t* cnt, con
       reinterpret_cast<const long long*>(first), reinterpret_cast<const long long*>(order), n,
       reinterpret_cast<long long*>(out_left), reinterpret_cast<long long*>(out_right));
   MB_LAUNCH_CHECK("expand_rows_kernel");
+  return 0;
+}
+
+extern "C" int mb200_digitize_i64(const int64_t* values, int64_t n, const int64_t* pivots_dev, int npivots,
+                                  int64_t* out_bins, mb200_stream_t stream) {
+  if (n < 0 || npivots < 0 || npivots > 1023) return fail("mb200_digitize_i64", "bad sizes (0 <= npivots <= 1023)");
+  if (n == 0) return 0;
+  if (!values || !out_bins || (npivots > 0 && !pivots_dev)) return fail("mb200_digitize_i64", "null argument");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  digitize_kernel<<<grid_for(n, dp), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(values), n, reinterpret_cast<const long long*>(pivots_dev), npivots,
+      reinterpret_cast<long long*>(out_bins));
+  MB_LAUNCH_CHECK("digitize_kernel");
   return 0;
 }

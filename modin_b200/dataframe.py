@@ -305,61 +305,51 @@ class B200Dataframe:
         ``PandasDataframe.sort_by`` (df.py:2741-2791), which range-partitions the rows by sampled pivots
         (``_apply_func_to_range_partitioning`` df.py:2565-2739) and sorts every range with pandas.
 
-        Here: per GPU, key -> order-preserving int64 image (MB200_OP_ORDERED_S), stable LSD radix sort of
-        (image, row id), one gather of every column by the permutation.  Across GPUs the locally sorted rows are
-        range-partitioned by sampled pivots and exchanged with ONE all_to_all (``dist.exchange_by_key_range``,
-        the raw-row shuffle of SURVEY 8f-2), then the received runs are merged by the same stable sort; rank r ends
-        up with the r-th key range, ties in original row order.  Row labels travel as a device index column."""
-        from . import ops
-        from .block import DeviceBlock, DeviceColumn, concat_cols, concat_rows
+        Here the same shuffle on the device (``partition manager.shuffle_partitions`` with ``DevShuffleFunctions``):
+        sample the key's order-preserving int64 image, pivots from the pooled samples, every row partition split by
+        ``digitize`` + stable radix sort + one gather, and each key range sorted by ``DevSortBlock`` (stable LSD radix
+        sort of (image, row id), one gather per column).  Across GPUs there is one range per rank and the transpose
+        is ONE all_to_all of raw rows over NVLink; rank r ends up with the r-th key range, ties in original row
+        order.  Row labels travel as a device index column."""
+        from .block import DeviceBlock, concat_cols
+        from .config import NPartitions
+        from .shuffle import DevShuffleFunctions, DevSortBlock
 
-        t = torch_mod()
-        rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
-        block = concat_rows(rows) if len(rows) > 1 else rows[0]
-        key = block.cols[col_position]
-        if key.dtype not in (np.float64, np.int64):
-            raise NotImplementedError("device sort_values needs a float64 or int64 key column")
-        if block.index_host is not None and not ignore_index:
-            raise NotImplementedError("sort_values keeps host-resident (non-numeric) row labels only with ignore_index=True")
-        n = block.nrows
-        cols = list(block.cols)
-        if dist.is_distributed() and any(c.dtype == np.bool_ for c in cols):
-            raise NotImplementedError("multi-GPU sort_values moves 8-byte columns only (bool columns are not packed)")
-        if not ignore_index:  # row labels ride along as one more int64 / float64 column
-            if block.index_cols:
-                if len(block.index_cols) != 1:
-                    raise NotImplementedError("sort_values with a MultiIndex is not on the B200 path")
-                cols.append(block.index_cols[0])
-            else:
-                cols.append(DeviceColumn(t.arange(block.range_start, block.range_start + n, dtype=t.int64,
-                                                  device=key.data.device), np.int64))  # fmt: skip
-
-        def sort_local(key_image, columns):
-            perm = DeviceColumn(t.arange(len(key_image), dtype=t.int64, device=key_image.data.device), np.int64)
-            ops.sort_pairs(key_image, perm)  # in place, stable
-            return key_image, ops.take_columns(columns, perm)
-
-        if n:
-            image = ops.map_columns("ordered_s", [key], s0=[(1.0 if key.dtype == np.float64 else 1) if not ascending else 0])[0]
-            image, cols = sort_local(image, cols)
-        else:
-            image = DeviceColumn.empty(0, np.int64)
-        if dist.is_distributed():
-            rk, rcols = dist.exchange_by_key_range(image.data, [c.data for c in cols])
-            image = DeviceColumn(rk, np.int64)
-            cols = [DeviceColumn(x, c.dtype) for x, c in zip(rcols, cols)]
-            if len(image):
-                image, cols = sort_local(image, cols)  # merge of the W sorted runs that arrived (rank order = tie order)
-            n = len(image)
-        if ignore_index:
-            lo = dist.exclusive_row_offset(n) if dist.is_distributed() else 0
-            out = DeviceBlock(cols, block.columns, nrows=n, range_start=lo)
-        else:
-            names = block.index_names if block.index_cols else [None]
-            out = DeviceBlock(cols[:-1], block.columns, nrows=n, index_cols=[cols[-1]], index_names=names)
+        # one column partition per row (a row block spans every column partition on the device path: zero-copy)
         pc = self._partition_mgr_cls._partition_class
-        return self.__constructor__(np.array([[pc(out)]], dtype=object), None, self._columns_cache, [n],
-                                    [len(out.cols)], self._dtypes)  # fmt: skip
+        parts = self._partitions
+        if parts.shape[1] > 1:
+            parts = np.array([[pc(concat_cols([p.get() for p in row]))] for row in parts], dtype=object)
+        first = parts[0, 0].get()
+        if first.cols[col_position].dtype not in (np.float64, np.int64):
+            raise NotImplementedError("device sort_values needs a float64 or int64 key column")
+        if any(row[0].get().index_host is not None for row in parts) and not ignore_index:
+            raise NotImplementedError("sort_values keeps host-resident (non-numeric) row labels only with ignore_index=True")
+        if ignore_index:  # labels are dropped anyway: give every block a throw-away range so that none is host-resident
+            parts = np.array([[pc(DeviceBlock(row[0].get().cols, row[0].get().columns, nrows=row[0].get().nrows))]
+                              for row in parts], dtype=object)  # fmt: skip
+        nbins = 1 if dist.is_distributed() else min(NPartitions.get(), max(1, len(self) // (1 << 16)))
+        if nbins == 1 and len(parts) > 1 and not dist.is_distributed():
+            # one new partition wanted, several held: gather the rows and apply the function once
+            # (``combine_and_apply``, df.py:2565-2739 ``_apply_func_to_range_partitioning``)
+            from .block import concat_rows
+            from .shuffle import _with_label_column
+
+            parts = np.array([[pc(concat_rows([_with_label_column(row[0].get()) for row in parts]))]], dtype=object)
+        shuffle = DevShuffleFunctions(col_position, ascending, ideal_num_new_partitions=max(1, nbins))
+        new_parts = self._partition_mgr_cls.shuffle_partitions(parts, 0, shuffle, DevSortBlock(col_position, ascending))
+        if len(new_parts) > 1 and all(len(row) == 1 for row in new_parts):
+            pass
+        lengths = [row[0].get().nrows for row in new_parts]
+        if ignore_index:
+            offset = dist.exclusive_row_offset(sum(lengths)) if dist.is_distributed() else 0
+            rows = []
+            for row, n in zip(new_parts, lengths):
+                b = row[0].get()
+                rows.append([pc(DeviceBlock(b.cols, b.columns, nrows=n, range_start=offset))])
+                offset += n
+            new_parts = np.array(rows, dtype=object)
+        return self.__constructor__(new_parts, None, self._columns_cache, lengths, [len(first.cols)], self._dtypes)
 
     def drop_duplicate_rows(self, col_position: int, keep: str = "first", ignore_index: bool = False) -> "B200Dataframe":
         """Rows holding the first / last occurrence of every value of one int64 column, in row order

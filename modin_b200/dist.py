@@ -218,6 +218,33 @@ def all_gather_rows(cols: Sequence) -> List:
     return out
 
 
+def exchange_rows(columns: Sequence, send_counts: Sequence[int]) -> List:
+    """all_to_all of raw rows: ``columns`` are 1-D tensors of equal length (8-byte dtypes) laid out destination by
+    destination (``send_counts[r]`` consecutive rows go to rank r).  Returns the received columns: the pieces of
+    rank 0, 1, ... in that order.  One collective for the counts, one for the packed rows."""
+    if not is_distributed():
+        return list(columns)
+    t = _torch()
+    d = _dist()
+    dev = columns[0].device
+    sc = t.as_tensor([int(c) for c in send_counts], dtype=t.int64).to(dev)
+    rc = t.empty_like(sc)
+    d.all_to_all_single(rc, sc)
+    rcl = [int(x) for x in rc.tolist()]
+    scl = [int(c) for c in send_counts]
+    n = int(columns[0].shape[0])
+    packed = t.empty((n, len(columns)), dtype=t.int64, device=dev)
+    for j, c in enumerate(columns):
+        packed[:, j] = c.view(t.int64) if c.dtype != t.int64 else c
+    recv = t.empty((sum(rcl), len(columns)), dtype=t.int64, device=dev)
+    d.all_to_all_single(recv, packed, output_split_sizes=rcl, input_split_sizes=scl)
+    outs = []
+    for j, c in enumerate(columns):
+        col = recv[:, j].contiguous()
+        outs.append(col.view(c.dtype) if c.dtype != t.int64 else col)
+    return outs
+
+
 def choose_pivots(sorted_keys, nsamples: int = 256):
     """ws-1 range pivots, identical on every rank, from evenly spaced samples of each rank's
     ascending unique keys (TeraSort-style; reference: pick_pivots_from_samples_for_sort,

@@ -648,6 +648,31 @@ def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0, 
     return c
 
 
+def run_starts(sorted_keys: DeviceColumn):
+    """Runs of equal values in a SORTED int64 column: ``(start positions, value of each run)`` as small host arrays
+    (``mb200_run_heads`` + compaction + gather; meant for few runs -- bin ids, not row keys)."""
+    lib = _lib.load()
+    n = len(sorted_keys)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    heads = DeviceColumn.empty(n, np.int64)
+    _lib.check(lib.mb200_run_heads(sorted_keys.ptr, n, heads.ptr, current_stream()))
+    starts, nruns = compact_hits(heads)
+    vals = take_columns([sorted_keys], starts)[0]
+    return starts.to_numpy(), vals.to_numpy()
+
+
+def digitize(values: DeviceColumn, pivots) -> DeviceColumn:
+    """``np.digitize(values, pivots)`` on the device: bin id = number of (ascending int64) pivots <= value."""
+    lib = _lib.load()
+    t = torch_mod()
+    out = DeviceColumn.empty(len(values), np.int64)
+    piv = t.as_tensor(list(pivots), dtype=t.int64).to(current_device()) if len(pivots) else None
+    _lib.check(lib.mb200_digitize_i64(values.ptr, len(values), piv.data_ptr() if piv is not None else None, len(pivots),
+                                      out.ptr, current_stream()))  # fmt: skip
+    return out
+
+
 def iota(start: int, nrows: int) -> DeviceColumn:
     """int64 column ``start, start + 1, ...``: the labels of a RangeIndex block as device data."""
     lib = _lib.load()

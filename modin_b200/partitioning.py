@@ -527,6 +527,15 @@ class B200AxisPartition:
             )  # fmt: skip
         return [self.partition_type(o) for o in outs]
 
+    def split(self, split_func, num_splits, *args, extract_metadata=False):
+        """axpart.py:321-366: gather the blocks of this axis partition, split them with ``split_func`` into
+        ``num_splits`` pieces (the range-partitioning split step), one new block partition per piece."""
+        fn, bargs, bkw = unwrap(split_func)
+        pieces = fn(self._gathered(), *bargs, *args, **bkw)
+        if len(pieces) != num_splits:
+            raise ValueError(f"split function returned {len(pieces)} pieces, expected {num_splits}")
+        return [self.partition_type(b) for b in pieces]
+
     def wait(self):
         for p in self._list_of_block_partitions:
             p.wait()
@@ -713,6 +722,45 @@ class B200PartitionManager:
         num_splits = min(len(partitions), NPartitions.get())
         return cls.map_axis_partitions(axis, mapped_partitions, reduce_func, enumerate_partitions=True,
                                        num_splits=num_splits)  # fmt: skip
+
+    # -- range-partitioning shuffle -------------------------------------------------------------
+    @classmethod
+    @wait_computations_if_benchmark_mode
+    def shuffle_partitions(cls, partitions, index, shuffle_functions, final_shuffle_func, right_partitions=None):
+        """pm.py:1937-2052: sample the key column of every row partition, let ``shuffle_functions`` pick the pivots,
+        split every row partition into one piece per key range, transpose, and run ``final_shuffle_func`` over the
+        pieces of each range.  Returns ``num_bins`` row partitions in key order (one column partition each).
+
+        Across GPUs (``shuffle_functions.pivot_fn`` then answers one range per rank) the transpose is an
+        ``all_to_all`` of raw rows over NVLink (``shuffle.exchange_pieces``): rank r ends up with range r."""
+        from .shuffle import exchange_pieces
+
+        if right_partitions is not None:
+            raise NotImplementedError("range-partition shuffle with a broadcast right side is not on the B200 path")
+        masked = partitions[:, index]
+        sample_func = cls.preprocess_func(shuffle_functions.sample_fn)
+        if masked.ndim == 1:
+            samples = [part.apply(sample_func) for part in masked]
+        else:
+            samples = [cls._row_partition_class(row, full_axis=False).apply(sample_func)[0] for row in masked]
+        samples = [s._data for s in samples]  # small device tensors, not blocks
+        num_bins = shuffle_functions.pivot_fn(samples)
+        row_partitions = cls.row_partitions(partitions)
+        if num_bins <= 1:
+            return np.array([[row_part.apply(final_shuffle_func, num_splits=1)[0]] for row_part in row_partitions])
+        split_row_partitions = np.array(
+            [part.split(shuffle_functions.split_fn, num_splits=num_bins) for part in row_partitions], dtype=object
+        ).reshape(len(row_partitions), num_bins).T  # [bin][source row partition]
+        if dist.is_distributed():
+            # pieces of bin r from all local row partitions -> rank r
+            send = [concat_rows([p.get() for p in pieces]) if len(pieces) > 1 else pieces[0].get() for pieces in split_row_partitions]
+            mine = exchange_pieces(send)
+            fn, bargs, bkw = unwrap(cls.preprocess_func(final_shuffle_func))
+            return np.array([[cls._partition_class(fn(mine, *bargs, **bkw))]])
+        return np.array(
+            [[cls._column_partitions_class(list(pieces), full_axis=False).apply(final_shuffle_func, num_splits=1)[0]]
+             for pieces in split_row_partitions]
+        )  # fmt: skip
 
     # -- n-ary -----------------------------------------------------------------------------------
     @classmethod

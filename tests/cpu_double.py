@@ -357,6 +357,18 @@ def expand_matches(fact_keys, dim_keys, keep_misses):
     return _col(left), _col(right), int((cnt == 0).sum())
 
 
+def run_starts(sorted_keys):
+    b = _np(sorted_keys)
+    if len(b) == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    starts = np.nonzero(np.concatenate([[True], b[1:] != b[:-1]]))[0].astype(np.int64)
+    return starts, b[starts]
+
+
+def digitize(values, pivots):
+    return _col(np.searchsorted(np.asarray(list(pivots), dtype=np.int64), _np(values), side="right").astype(np.int64))
+
+
 def iota(start, nrows):
     return _col(np.arange(start, start + nrows, dtype=np.int64))
 
@@ -374,10 +386,11 @@ def installed():
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
                                         "compact_hits", "cast_columns_f64", "cast_columns_i64", "gen_f64", "gen_i64", "GroupTable",
-                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches")},
+                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches", "digitize", "run_starts")},
     }  # fmt: skip
     ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
-    ops.iota, ops.full_column, ops.expand_matches = iota, full_column, expand_matches
+    ops.iota, ops.full_column, ops.expand_matches, ops.digitize = iota, full_column, expand_matches, digitize
+    ops.run_starts = run_starts
     ops.cast_columns_i64 = cast_columns_i64
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device

@@ -174,3 +174,59 @@ def test_many_to_many_expansion_at_scale():
         src = np.repeat(lo, out_cnt) + (np.arange(len(left)) - np.repeat(offs, out_cnt))
         right = np.where(np.repeat(cnt > 0, out_cnt), order[np.minimum(src, len(order) - 1)], -1)
         assert np.array_equal(lr.to_numpy(), left) and np.array_equal(rr.to_numpy(), right)
+
+
+# ---- range-partitioning shuffle (pm.shuffle_partitions, partition_manager.py:1937-2052) --------------------------
+def _shuffle_checks(bpd, n):
+    from modin_b200 import config
+    from modin_b200.shuffle import DevShuffleFunctions, DevSortBlock
+
+    old = config.NPartitions.get()
+    config.NPartitions.put(4)
+    try:
+        pdf = synth.host_frame(n, 3, seed=5, nan_per_64k=3000, key_modulus=777)
+        df = bpd.DataFrame(pdf)
+        frame = df._query_compiler._modin_frame
+        pm = frame._partition_mgr_cls
+        # the classmethod itself: 4 key ranges, disjoint and in key order, every row exactly once
+        sf = DevShuffleFunctions(1, ascending=True, ideal_num_new_partitions=4)  # column 1 = c0
+        parts = pm.shuffle_partitions(frame._partitions, 0, sf, DevSortBlock(1, True))
+        assert parts.shape == (4, 1) and len(sf.pivots) == 3
+        blocks = [p[0].get() for p in parts]
+        assert sum(b.nrows for b in blocks) == n
+        pieces = [b.to_pandas() for b in blocks]
+        keys = [p["c0"].to_numpy() for p in pieces]
+        tops = [np.nanmax(k) for k in keys if len(k) and not np.isnan(k).all()]
+        lows = [np.nanmin(k) for k in keys if len(k) and not np.isnan(k).all()]
+        assert all(t <= l for t, l in zip(tops[:-1], lows[1:])), "key ranges overlap"
+        got = pandas.concat(pieces)
+        want = pdf.sort_values("c0", kind="stable")
+        assert got.index.equals(want.index), "rows out of stable key order"
+        assert np.array_equal(got.to_numpy().view(np.uint64), want.to_numpy().view(np.uint64))
+        # through the API, both directions, float and int keys, labels kept or renumbered
+        for by, asc in (("c1", False), ("key", True), ("key", False)):
+            got = df.sort_values(by, ascending=asc)._to_pandas()
+            want = pdf.sort_values(by, ascending=asc, kind="stable")
+            assert got.index.equals(want.index) and np.array_equal(got.to_numpy().view(np.uint64), want.to_numpy().view(np.uint64)), (by, asc)
+        got = df.sort_values("c0", ignore_index=True)._to_pandas()
+        want = pdf.sort_values("c0", ignore_index=True, kind="stable")
+        assert got.index.equals(want.index) and np.array_equal(got.to_numpy().view(np.uint64), want.to_numpy().view(np.uint64))
+    finally:
+        config.NPartitions.put(old)
+
+
+def test_shuffle_partitions_on_the_double(cpu_device):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    import modin_b200.pandas as bpd
+
+    _shuffle_checks(bpd, 300_000)
+
+
+@pytest.mark.gpu
+def test_shuffle_partitions_on_b200():
+    import modin_b200.pandas as bpd
+
+    _shuffle_checks(bpd, 1 << 21)
