@@ -479,9 +479,11 @@ def run_b200_arm(args):
         with _ops.KernelTimer() as kt:
             for _ in range(reps):
                 step_fn()
-            ms = kt.mean_ms(tag)
+            ms = kt.total_ms(tag)
         sync_all()
-        return max_over_ranks(ms) if ms is not None else None
+        # per step: a template may launch the kernel more than once (map phase + the tiny reduce phase over the
+        # partials); the step's launches are added up, so the figure is the time the step spends in this kernel
+        return max_over_ranks(ms / reps) if ms is not None else None
 
     def roof(kernel, bytes_per_launch_local, per_ms, traffic=None, launch_ms=None, **extra):
         """`achieved` = algorithmic bytes of one launch / that kernel's own duration (`launch_ms`, CUDA events around
@@ -546,6 +548,7 @@ def run_b200_arm(args):
         ok = ok and _bits_equal(device_values(blk.cols[j], idx), ref)
     map_checked = all_ranks_ok(ok)
     last[0] = None
+    del blk  # the block is the 64 GB result: drop the last reference before the next leg allocates
 
     also = []
     roofline_groupby = None
@@ -778,6 +781,7 @@ def run_b200_arm(args):
                 out = [None]
 
                 def step_e2e():
+                    out[0] = None  # the previous result's pinned buffers go back to the pool (and are taken again below)
                     df = api.pd.DataFrame(host)  # ingest: the block stays on the host (HostBlock)
                     out[0] = api.to_pandas(df * B_SCALAR + C_SCALAR)  # streamed: H2D / AFFINE sweep / D2H per chunk
 
@@ -803,6 +807,7 @@ def run_b200_arm(args):
                 out = [None]
 
                 def step_e2e_gb():
+                    out[0] = None
                     df = api.pd.DataFrame(host)
                     out[0] = api.to_pandas(df.groupby("key").sum())  # H2D 72 B/row, device groupby, result D2H
 

@@ -342,6 +342,11 @@ int mb200_iota_i64(int64_t* out, int64_t nrows, int64_t start, mb200_stream_t st
  * re-indexing adds). */
 int mb200_fill_u64(void* out, int64_t n, uint64_t bits, mb200_stream_t stream);
 
+/* Row-wise concatenation of column pieces: dst = src[0] | src[1] | ... (src_bytes[i] bytes each; HOST arrays of
+ * device pointers / sizes), one launch per 64 sources.  Replaces the pandas.concat of the gathered blocks of an axis
+ * partition (PandasDataframeAxisPartition.deploy_axis_func, axpart.py:445-452) and pm.combine (pm.py:1328-1373). */
+int mb200_concat(int nsrc, const void* const* src, const int64_t* src_bytes, void* dst, mb200_stream_t stream);
+
 /* ======================= utilities ========================================= */
 /* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.
  * scratch_bytes >= mb200_sort_scratch_bytes(n). */

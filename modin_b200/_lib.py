@@ -96,6 +96,7 @@ _SIGNATURES = {
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
     "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
+    "mb200_concat": (C.c_int, [C.c_int, _vpp, C.POINTER(C.c_int64), _vp, _vp]),
     "mb200_iota_i64": (C.c_int, [_vp, _i64, _i64, _vp]),
     "mb200_fill_u64": (C.c_int, [_vp, _i64, C.c_uint64, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),

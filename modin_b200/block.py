@@ -519,7 +519,8 @@ class HostBlock:
 def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
     """Row-wise concatenation of blocks with identical columns (pandas.concat in
     deploy_axis_func, axpart.py:445-452) -- a D2D copy into fresh column buffers."""
-    t = torch_mod()
+    from . import ops
+
     blocks = [b for b in blocks]
     if len(blocks) == 1:
         return blocks[0]
@@ -531,16 +532,16 @@ def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
         dtype = first.cols[j].dtype
         if len(dts) > 1:  # int + float partials (count next to sum) promote like pandas.concat
             dtype = np.result_type(*dts)
-            parts = [b.cols[j].data.to(_torch_dtype(dtype)) if b.cols[j].dtype != dtype else b.cols[j].data
-                     for b in blocks]  # fmt: skip
+            if dtype != np.float64:
+                raise TypeError(f"row-wise concat of {sorted(str(d) for d in dts)} columns is not on the B200 path")
+            pieces = [ops.cast_columns_f64([b.cols[j]])[0] if b.cols[j].dtype != dtype else b.cols[j] for b in blocks]
         else:
-            parts = [b.cols[j].data for b in blocks]
-        cols.append(DeviceColumn(t.cat(parts), dtype))
+            pieces = [b.cols[j] for b in blocks]
+        cols.append(ops.concat_columns(pieces))
     nrows = sum(b.nrows for b in blocks)
     if all(b.index_cols for b in blocks):
         k = len(first.index_cols)
-        icols = [DeviceColumn(t.cat([b.index_cols[i].data for b in blocks]), first.index_cols[i].dtype)
-                 for i in range(k)]  # fmt: skip
+        icols = [ops.concat_columns([b.index_cols[i] for b in blocks]) for i in range(k)]
         return DeviceBlock(cols, first.columns, nrows=nrows, index_cols=icols, index_names=first.index_names)
     if all(b.index_host is not None for b in blocks):
         ih = blocks[0].index_host
@@ -560,9 +561,8 @@ def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
     if all(b.has_range_index() for b in blocks) and cols:
         # ranges that do not run on from each other (row-wise concat of frames, shard-local slices): still numeric
         # labels, so they stay on the device as an int64 index column instead of becoming a host index
-        dev = cols[0].data.device
-        labels = t.cat([t.arange(b.range_start, b.range_start + b.nrows, dtype=t.int64, device=dev) for b in blocks])
-        return DeviceBlock(cols, first.columns, nrows=nrows, index_cols=[DeviceColumn(labels, np.int64)], index_names=[None])
+        labels = ops.concat_columns([ops.iota(b.range_start, b.nrows) for b in blocks])
+        return DeviceBlock(cols, first.columns, nrows=nrows, index_cols=[labels], index_names=[None])
     ih = blocks[0].index
     for b in blocks[1:]:
         ih = ih.append(b.index)

@@ -165,6 +165,48 @@ __global__ void __launch_bounds__(256) digitize_kernel(const long long* __restri
   }
 }
 
+// Row-wise concatenation of column pieces (pandas.concat of the blocks of an axis partition, axpart.py:445-452; the
+// gather before a full-axis function): up to 64 source buffers are copied into ONE destination by one launch.  Work
+// is cut into 64 KiB chunks over all sources; a CTA finds the source of its chunk in the (<= 64-entry) prefix table in
+// kernel parameters and copies 16 bytes per thread per step (bytes for ragged heads / tails).
+constexpr int kConcatMax = 64;
+constexpr long long kConcatChunk = 64 << 10;
+struct ConcatParams {
+  const char* src[kConcatMax];
+  long long dst_off[kConcatMax];    // byte offset of the source in the destination
+  long long chunk_lo[kConcatMax + 1];  // first chunk id of every source
+  long long bytes[kConcatMax];
+  int nsrc;
+};
+
+__global__ void __launch_bounds__(256) concat_kernel(const __grid_constant__ ConcatParams p, char* __restrict__ dst,
+                                                     long long nchunks) {
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    int s = 0;
+    while (s + 1 < p.nsrc && p.chunk_lo[s + 1] <= ch) ++s;
+    const long long off = (ch - p.chunk_lo[s]) * kConcatChunk;
+    long long n = p.bytes[s] - off;
+    if (n > kConcatChunk) n = kConcatChunk;
+    const char* in = p.src[s] + off;
+    char* out = dst + p.dst_off[s] + off;
+    if ((((uintptr_t)in | (uintptr_t)out) & 15u) == 0) {
+      const long long nv = n >> 4;
+      const int4* vi = reinterpret_cast<const int4*>(in);
+      int4* vo = reinterpret_cast<int4*>(out);
+      for (long long i = threadIdx.x; i < nv; i += blockDim.x) vo[i] = vi[i];
+      for (long long i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+    } else if ((((uintptr_t)in | (uintptr_t)out) & 7u) == 0) {
+      const long long nv = n >> 3;
+      const long long* vi = reinterpret_cast<const long long*>(in);
+      long long* vo = reinterpret_cast<long long*>(out);
+      for (long long i = threadIdx.x; i < nv; i += blockDim.x) vo[i] = vi[i];
+      for (long long i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+    } else {
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+    }
+  }
+}
+
 static int grid_for(long long n, const DevProps& dp) {
   long long g = (n + 255) / 256;
   const long long cap = (long long)dp.sm_count * 16;
@@ -254,5 +296,44 @@ extern "C" int mb200_digitize_i64(const int64_t* values, int64_t n, const int64_
       reinterpret_cast<const long long*>(values), n, reinterpret_cast<const long long*>(pivots_dev), npivots,
       reinterpret_cast<long long*>(out_bins));
   MB_LAUNCH_CHECK("digitize_kernel");
+  return 0;
+}
+
+extern "C" int mb200_concat(int nsrc, const void* const* src, const int64_t* src_bytes, void* dst,
+                            mb200_stream_t stream) {
+  if (nsrc < 0) return fail("mb200_concat", "negative nsrc");
+  if (nsrc == 0) return 0;
+  if (!src || !src_bytes || !dst) return fail("mb200_concat", "null argument");
+  DevProps dp;
+  if (int rc = dev_props(&dp)) return rc;
+  long long dst_off = 0;
+  for (int base = 0; base < nsrc; base += kConcatMax) {
+    ConcatParams p;
+    memset(&p, 0, sizeof(p));
+    const int m = (nsrc - base) < kConcatMax ? (nsrc - base) : kConcatMax;
+    long long chunks = 0;
+    int k = 0;
+    for (int i = 0; i < m; ++i) {
+      const long long b = src_bytes[base + i];
+      if (b < 0) return fail("mb200_concat", "negative source size");
+      if (b == 0) continue;
+      if (!src[base + i]) return fail("mb200_concat", "null source");
+      p.src[k] = static_cast<const char*>(src[base + i]);
+      p.bytes[k] = b;
+      p.dst_off[k] = dst_off;
+      p.chunk_lo[k] = chunks;
+      chunks += (b + kConcatChunk - 1) / kConcatChunk;
+      dst_off += b;
+      ++k;
+    }
+    if (k == 0) continue;
+    p.chunk_lo[k] = chunks;
+    p.nsrc = k;
+    long long grid = chunks;
+    const long long cap = (long long)dp.sm_count * 16;
+    if (grid > cap) grid = cap;
+    concat_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p, static_cast<char*>(dst), chunks);
+    MB_LAUNCH_CHECK("concat_kernel");
+  }
   return 0;
 }

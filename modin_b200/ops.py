@@ -41,6 +41,11 @@ class KernelTimer:
         ev = self.events.get(tag, [])
         return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else None
 
+    def total_ms(self, tag):
+        torch_mod().cuda.synchronize()
+        ev = self.events.get(tag, [])
+        return sum(a.elapsed_time(b) for a, b in ev) if ev else None
+
     def launches(self, tag):
         return len(self.events.get(tag, []))
 
@@ -646,6 +651,23 @@ def gen_i64(nrows: int, seed: int, col: int, modulus: int, row_offset: int = 0, 
     _lib.check(fn(c.ptr, nrows, seed, col, row_offset, modulus, stats.data_ptr(), current_stream()))
     c.stats = KeyStats(dev=stats)
     return c
+
+
+def concat_columns(pieces: Sequence[DeviceColumn]) -> DeviceColumn:
+    """Row-wise concatenation of column pieces of one dtype into a fresh buffer: ONE ``mb200_concat`` launch (per 64
+    pieces) instead of a framework concatenation."""
+    pieces = [p for p in pieces]
+    if len(pieces) == 1:
+        return pieces[0]
+    lib = _lib.load()
+    dtype = pieces[0].dtype
+    if any(p.dtype != dtype for p in pieces):
+        raise TypeError("concat_columns needs pieces of one dtype")
+    out = DeviceColumn.empty(sum(len(p) for p in pieces), dtype)
+    item = 1 if dtype == np.bool_ else 8
+    sizes = (C.c_int64 * len(pieces))(*[len(p) * item for p in pieces])
+    _lib.check(lib.mb200_concat(len(pieces), _lib.ptr_array([p.ptr for p in pieces]), sizes, out.ptr, current_stream()))
+    return out
 
 
 def run_starts(sorted_keys: DeviceColumn):

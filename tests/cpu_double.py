@@ -357,6 +357,11 @@ def expand_matches(fact_keys, dim_keys, keep_misses):
     return _col(left), _col(right), int((cnt == 0).sum())
 
 
+def concat_columns(pieces):
+    pieces = list(pieces)
+    return pieces[0] if len(pieces) == 1 else _col(np.concatenate([_np(p) for p in pieces]))
+
+
 def run_starts(sorted_keys):
     b = _np(sorted_keys)
     if len(b) == 0:
@@ -386,11 +391,11 @@ def installed():
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
                                         "compact_hits", "cast_columns_f64", "cast_columns_i64", "gen_f64", "gen_i64", "GroupTable",
-                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches", "digitize", "run_starts")},
+                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches", "digitize", "run_starts", "concat_columns")},
     }  # fmt: skip
     ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
     ops.iota, ops.full_column, ops.expand_matches, ops.digitize = iota, full_column, expand_matches, digitize
-    ops.run_starts = run_starts
+    ops.run_starts, ops.concat_columns = run_starts, concat_columns
     ops.cast_columns_i64 = cast_columns_i64
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device
