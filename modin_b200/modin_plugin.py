@@ -329,19 +329,18 @@ def register(shims: bool | None = None):
 
         def sort_rows_by_column_values(self, columns, ascending=True, **kwargs):
             """qc.py ``sort_rows_by_column_values`` -> PandasDataframe.sort_by (df.py:2741-2791), a range-partitioning
-            shuffle that samples the blocks with pandas code.  Here one full-axis application of the device sort
-            (stable, NaN last; one float64 / int64 key column)."""
+            shuffle whose sampling / pivot / split callbacks run pandas code on the blocks.  Here the same shuffle
+            with device callbacks (``B200PartitionManager.shuffle_partitions`` + ``shuffle.DevShuffleFunctions``):
+            stable, NaN last, one float64 / int64 key column; across GPUs one key range per rank."""
+            from .dataframe import B200Dataframe
+
             pos, asc = fx.DevSortRows.resolve(self.columns, columns, ascending, **kwargs)
             frame = self._modin_frame
-            if frame._partitions.shape[1] != 1:
-                raise NotImplementedError("device sort_values: frames of one column partition (up to 32 columns)")
-            if bdist.is_distributed():
-                raise NotImplementedError("sort_values through the Modin plug-in is single-process")
-            fn, ignore = fx.DevSortRows(), bool(kwargs.get("ignore_index", False))
-            new_frame = frame.apply_full_axis(
-                0, lambda blk: fn(blk, pos, asc, ignore), new_columns=self.columns, dtypes="copy",
-                keep_partitioning=True, num_splits=1, sync_labels=False,
-            )  # fmt: skip
+            frame._propagate_index_objs(axis=0)  # deferred external row labels go into the blocks first
+            mirror = B200Dataframe(frame._partitions, None, self.columns, None, None, None)
+            done = mirror.sort_by(pos, asc, bool(kwargs.get("ignore_index", False)))
+            new_frame = type(frame)(done._partitions, None, self.columns, done.row_lengths, done.column_widths,
+                                    dtypes=frame.copy_dtypes_cache())  # fmt: skip
             return self.__constructor__(new_frame)
 
         def nunique(self, axis=0, dropna=True):

@@ -419,8 +419,8 @@ def _plugin_rank_job(rank, ws):
         out["filter"] = P(mdf[mdf["c0"] > 0.0])
         out["dropna"] = P(mdf.dropna())
         out["nunique"] = P(mfull[["key"]].nunique())
-        for what, call in (("drop_duplicates", lambda: mfull[["key"]].drop_duplicates()),
-                           ("sort_values", lambda: mfull.sort_values("key"))):  # fmt: skip
+        out["sort"] = P(mdf.sort_values("c1"))
+        for what, call in (("drop_duplicates", lambda: mfull[["key"]].drop_duplicates()),):  # fmt: skip
             try:
                 call()
                 out["refused_" + what] = False
@@ -471,6 +471,8 @@ def test_plugin_under_two_gloo_ranks():
         wd = vals.dropna()
         assert list(o["dropna"].index) == list(wd.index) and _same(o["dropna"].to_numpy(), wd.to_numpy())
         assert int(np.asarray(o["nunique"]).ravel()[0]) == pdf["key"].nunique()
-        assert o["refused_drop_duplicates"] and o["refused_sort_values"]
+        assert o["refused_drop_duplicates"]
+        wsrt = vals.sort_values("c1", kind="stable")
+        assert list(o["sort"].index) == list(wsrt.index) and _same(o["sort"].to_numpy(), wsrt.to_numpy())
     # the group table is split by key range: both ranks own a part, together all 23 groups
     assert sum(o["gb_local_sum"] for o in outs) == pdf["key"].nunique() and all(o["gb_local_sum"] > 0 for o in outs)

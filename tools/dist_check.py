@@ -6,6 +6,10 @@
 Every rank builds the SAME seeded host frame, ingests only its row shard (pm.from_pandas shards by
 rank), runs the hot-path templates through the public API and compares the gathered results with
 the CPU oracle.  Exit code 0 = all checks passed on every rank.
+
+``--api mirror`` (default: both) drives ``modin_b200.pandas``; ``--api modin`` drives the REAL ``modin.pandas``
+(baseline/_ref) with the plug-in activated on every rank -- the same checks, plus the operations the plug-in refuses
+on all ranks together.
 """
 import math
 import os
@@ -19,8 +23,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from modin_b200 import config, dist, synth  # noqa: E402
-import modin_b200.pandas as bpd  # noqa: E402
 from oracle import reference_path as orc  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 EPS = 2.0**-53
 
@@ -36,13 +41,33 @@ def close(a, b, abs_sum, n):
     return a.shape == b.shape and bool(((np.abs(a - b) <= tol) | (a == b) | (np.isnan(a) & np.isnan(b))).all())
 
 
-def main():
-    assert dist.init_from_env("nccl"), "run under torchrun with WORLD_SIZE > 1"
-    rank, ws = dist.rank(), dist.world_size()
-    config.NPartitions.put(2)
-    fails = []
+def front_door(which):
+    if which == "mirror":
+        import modin_b200.pandas as bpd
+
+        return bpd
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from modin_b200 import modin_plugin
+
+    modin_plugin.activate()
+    import modin.config as cfg
+    import modin.pandas as mpd
+
+    cfg.NPartitions.put(2)
+    return mpd
+
+
+def run_checks(bpd, tag, rank, fails):
+    def P(x):
+        return x._to_pandas() if hasattr(x, "_to_pandas") else x
 
     def check(name, ok):
+        name = f"[{tag}] {name}"
         if not ok:
             fails.append(name)
         if rank == 0:
@@ -57,36 +82,36 @@ def main():
     dv = df[[f"c{i}" for i in range(W)]]
     NP = 4
 
-    check("map abs (gathered, bit-exact)", exact(dv.abs()._to_pandas().to_numpy(), orc.df_abs(vals, NP).to_numpy()))
+    check("map abs (gathered, bit-exact)", exact(P(dv.abs()).to_numpy(), orc.df_abs(vals, NP).to_numpy()))
     check("fused a*b+c (gathered, bit-exact)",
-          exact((dv * 1.25 + 0.5)._to_pandas().to_numpy(), orc.a_mul_b_add_c(vals, 1.25, 0.5, NP).to_numpy()))
+          exact(P(dv * 1.25 + 0.5).to_numpy(), orc.a_mul_b_add_c(vals, 1.25, 0.5, NP).to_numpy()))
     abs_sum = np.nansum(np.abs(vals.to_numpy()), axis=0)
-    check("tree_reduce sum (all_reduce)", close(dv.sum().to_numpy(), orc.df_sum(vals, NP).to_numpy(), abs_sum, n))
-    check("tree_reduce count", exact(dv.count().to_numpy(), orc.df_count(vals, NP).to_numpy()))
-    check("tree_reduce min", exact(dv.min().to_numpy(), orc.df_min(vals, NP).to_numpy()))
-    check("tree_reduce max", exact(dv.max().to_numpy(), orc.df_max(vals, NP).to_numpy()))
+    check("tree_reduce sum (all_reduce)", close(np.asarray(P(dv.sum())), orc.df_sum(vals, NP).to_numpy(), abs_sum, n))
+    check("tree_reduce count", exact(np.asarray(P(dv.count())), orc.df_count(vals, NP).to_numpy()))
+    check("tree_reduce min", exact(np.asarray(P(dv.min())), orc.df_min(vals, NP).to_numpy()))
+    check("tree_reduce max", exact(np.asarray(P(dv.max())), orc.df_max(vals, NP).to_numpy()))
     cnt = np.maximum(orc.df_count(vals, NP).to_numpy(), 1)
-    check("tree_reduce mean", close(dv.mean().to_numpy(), orc.df_mean(vals, NP).to_numpy(), abs_sum / cnt, n))
+    check("tree_reduce mean", close(np.asarray(P(dv.mean())), orc.df_mean(vals, NP).to_numpy(), abs_sum / cnt, n))
 
     from modin_b200 import config as _cfg
 
-    for dense, tag in ((True, "dense table + collectives"), (False, "hash tables + range exchange")):
+    for dense, kind in ((True, "dense table + reduce-scatter"), (False, "hash tables + range exchange")):
         _cfg.GroupbyDenseKeys.put(dense)
         g = df.groupby("key")
         want = orc.groupby_reduce(pdf, "key", "sum", NP)
         got_local = g.sum()
-        check(f"[{tag}] groupby: every rank owns a non-empty key range", len(got_local) > 0)
-        got = got_local._to_pandas()  # gathers the per-rank key ranges in rank order
+        check(f"[{kind}] groupby: every rank owns a non-empty key range", len(got_local) > 0)
+        got = P(got_local)  # gathers the per-rank key ranges in rank order
         gabs = vals.abs().groupby(pdf["key"]).sum().to_numpy()
-        check(f"[{tag}] groupby keys globally sorted & complete", np.array_equal(got.index.to_numpy(), want.index.to_numpy()))
-        check(f"[{tag}] groupby sum", close(got.to_numpy(), want.to_numpy(), gabs, n))
-        check(f"[{tag}] groupby count", exact(g.count()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "count", NP).to_numpy()))
-        check(f"[{tag}] groupby size", exact(g.size()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "size", NP).to_numpy()))
+        check(f"[{kind}] groupby keys globally sorted & complete", np.array_equal(got.index.to_numpy(), want.index.to_numpy()))
+        check(f"[{kind}] groupby sum", close(got.to_numpy(), want.to_numpy(), gabs, n))
+        check(f"[{kind}] groupby count", exact(P(g.count()).to_numpy(), orc.groupby_reduce(pdf, "key", "count", NP).to_numpy()))
+        check(f"[{kind}] groupby size", exact(np.asarray(P(g.size())).ravel(), orc.groupby_reduce(pdf, "key", "size", NP).to_numpy().ravel()))
         gc = np.maximum(orc.groupby_reduce(pdf, "key", "count", NP).to_numpy(), 1)
-        check(f"[{tag}] groupby mean", close(g.mean()._to_pandas().to_numpy(), orc.groupby_reduce(pdf, "key", "mean", NP).to_numpy(),
+        check(f"[{kind}] groupby mean", close(P(g.mean()).to_numpy(), orc.groupby_reduce(pdf, "key", "mean", NP).to_numpy(),
                                     gabs / gc, n))
         for agg in ("min", "max"):
-            check(f"[{tag}] groupby {agg}", exact(getattr(g, agg)()._to_pandas().to_numpy(),
+            check(f"[{kind}] groupby {agg}", exact(P(getattr(g, agg)()).to_numpy(),
                                                  orc.groupby_reduce(pdf, "key", agg, NP).to_numpy()))
     _cfg.GroupbyDenseKeys.put(True)
 
@@ -94,14 +119,48 @@ def main():
     dim_keys = rng.permutation(G).astype(np.int64)[: int(G * 0.9)]
     dim = pandas.DataFrame({"key": dim_keys, "d0": synth.gen_f64(len(dim_keys), 11, 0)})
     mdim = bpd.DataFrame(dim)  # sharded too; combine() all-gathers it
-    left = df.merge(mdim, on="key", how="left")._to_pandas()
+    left = P(df.merge(mdim, on="key", how="left"))
     wl = orc.broadcast_merge(pdf, dim, "key", "left", NP)
     check("merge left (dim all_gathered)", list(left.columns) == list(wl.columns) and
           exact(left.to_numpy(dtype=np.float64), wl.to_numpy(dtype=np.float64)))
-    inner = df.merge(mdim, on="key", how="inner")._to_pandas()
+    inner = P(df.merge(mdim, on="key", how="inner"))
     wi = orc.broadcast_merge(pdf, dim, "key", "inner", NP)
     check("merge inner", exact(inner.to_numpy(dtype=np.float64), wi.to_numpy(dtype=np.float64)))
 
+    # many-to-many merge (repeated dim keys) and the range-partitioning shuffle (sort_values) across ranks
+    dup = pandas.DataFrame({"key": np.concatenate([dim_keys[:300], dim_keys[:120]]), "d1": np.arange(420, dtype=np.int64)})
+    m2m = P(df.merge(bpd.DataFrame(dup), on="key", how="inner"))
+    wm = orc.broadcast_merge_general(pdf, dup, "inner", NP, on="key")
+    check("merge inner, repeated dim keys (many-to-many)", exact(m2m.to_numpy(dtype=np.float64), wm.to_numpy(dtype=np.float64)))
+    srt = P(dv.sort_values("c1"))
+    ws_ = vals.sort_values("c1", kind="stable")
+    check("sort_values (range shuffle, all_to_all of rows)", list(srt.index) == list(ws_.index) and exact(srt.to_numpy(), ws_.to_numpy()))
+
+
+def main():
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--api", default="both", choices=["mirror", "modin", "both"])
+    args = ap.parse_args()
+    assert dist.init_from_env("nccl"), "run under torchrun with WORLD_SIZE > 1"
+    rank, ws = dist.rank(), dist.world_size()
+    config.NPartitions.put(2)
+    fails = []
+    apis = ["mirror", "modin"] if args.api == "both" else [args.api]
+    if "modin" in apis and not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "modin")):
+        apis.remove("modin")
+        if rank == 0:
+            print("SKIP modin front door: baseline/_ref/modin is not installed", flush=True)
+    for which in apis:
+        try:
+            run_checks(front_door(which), which, rank, fails)
+        except Exception as exc:
+            import traceback
+
+            fails.append(f"[{which}] crashed: {type(exc).__name__}: {exc}")
+            if rank == 0:
+                traceback.print_exc()
     t = torch.tensor([len(fails)], dtype=torch.int64, device="cuda")
     torch.distributed.all_reduce(t)
     if rank == 0:
