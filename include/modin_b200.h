@@ -347,6 +347,34 @@ int mb200_fill_u64(void* out, int64_t n, uint64_t bits, mb200_stream_t stream);
  * partition (PandasDataframeAxisPartition.deploy_axis_func, axpart.py:445-452) and pm.combine (pm.py:1328-1373). */
 int mb200_concat(int nsrc, const void* const* src, const int64_t* src_bytes, void* dst, mb200_stream_t stream);
 
+/* ======================= collectives (NCCL over NVLink 5 / NVSwitch) ======= */
+/* The reference issues no collective: it gathers all blocks of an axis into one task (axis_partition.py:445-452),
+ * hands one object to many tasks (pm.py:443-494) or shuffles rows between partitions (pm.py:1937-2052).  With one
+ * process per GPU those steps are the calls below, issued on the caller's stream on device buffers.  NCCL is resolved
+ * at run time: mb200_comm_load(path or NULL) once per process; rank 0 calls mb200_comm_unique_id and the host side
+ * carries the 128 bytes to every rank (any control channel), then every rank calls mb200_comm_init_rank. */
+typedef struct mb200_comm mb200_comm;
+enum mb200_comm_op { MB200_COMM_SUM = 0, MB200_COMM_MIN = 1, MB200_COMM_MAX = 2 };
+int mb200_comm_load(const char* libnccl_path);
+int mb200_comm_unique_id(void* out128);
+int mb200_comm_init_rank(mb200_comm** comm, int nranks, const void* id128, int rank);
+int mb200_comm_destroy(mb200_comm* comm);
+/* TreeReduce combine (W-vector) and the element-wise merge of dense group tables. */
+int mb200_comm_allreduce(mb200_comm* comm, const void* send, void* recv, int64_t count, int dtype, int op,
+                         mb200_stream_t stream);
+/* Reduce phase of GroupByReduce for dense keys: rank r receives elements [r * recvcount, (r + 1) * recvcount). */
+int mb200_comm_reduce_scatter(mb200_comm* comm, const void* send, void* recv, int64_t recvcount, int dtype,
+                              int op, mb200_stream_t stream);
+/* Broadcast merge: every rank's (equal-length, padded) shard of a dim column -> the whole column everywhere. */
+int mb200_comm_allgather(mb200_comm* comm, const void* send, void* recv, int64_t sendcount, int dtype,
+                         mb200_stream_t stream);
+int mb200_comm_broadcast(mb200_comm* comm, void* buf, int64_t count, int dtype, int root, mb200_stream_t stream);
+/* Range-partitioning shuffle / exchange of partial group tables: counts and displacements in ELEMENTS of elem_bytes
+ * (HOST arrays of length nranks); grouped ncclSend / ncclRecv. */
+int mb200_comm_alltoallv(mb200_comm* comm, const void* send, const int64_t* sendcounts, const int64_t* sdispls,
+                         void* recv, const int64_t* recvcounts, const int64_t* rdispls, int elem_bytes,
+                         mb200_stream_t stream);
+
 /* ======================= utilities ========================================= */
 /* Stable LSD radix sort of (key, payload) pairs by key ascending (signed), in place.
  * scratch_bytes >= mb200_sort_scratch_bytes(n). */

@@ -96,6 +96,16 @@ _SIGNATURES = {
     "mb200_gen_f64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_int, _vp]),
     "mb200_gen_i64": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
     "mb200_gen_i64_skew": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint64, _i64, C.c_uint64, _vp, _vp]),
+    "mb200_comm_load": (C.c_int, [C.c_char_p]),
+    "mb200_comm_unique_id": (C.c_int, [_vp]),
+    "mb200_comm_init_rank": (C.c_int, [_vpp, C.c_int, _vp, C.c_int]),
+    "mb200_comm_destroy": (C.c_int, [_vp]),
+    "mb200_comm_allreduce": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp]),
+    "mb200_comm_reduce_scatter": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp]),
+    "mb200_comm_allgather": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp]),
+    "mb200_comm_broadcast": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp]),
+    "mb200_comm_alltoallv": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.c_int, _vp]),
     "mb200_concat": (C.c_int, [C.c_int, _vpp, C.POINTER(C.c_int64), _vp, _vp]),
     "mb200_iota_i64": (C.c_int, [_vp, _i64, _i64, _vp]),
     "mb200_fill_u64": (C.c_int, [_vp, _i64, C.c_uint64, _vp]),

@@ -110,11 +110,73 @@ def shard_bounds(nrows: int, r: int | None = None, ws: int | None = None):
 
 _REDUCE_OPS = {"sum": "SUM", "min": "MIN", "max": "MAX"}
 
+# ---- data-plane collectives through the C ABI (csrc/comm.cu: NCCL resolved at run time, this library's own
+# communicator, issued on the rank's CUDA stream).  torch.distributed stays the CONTROL plane: process bootstrap, the
+# 128-byte unique id, and the handful of host-side integers a decision needs; under gloo (CPU tests) it also carries
+# the data.
+_COMM = None
+_COMM_OPS = {"sum": 0, "min": 1, "max": 2}
+
+
+def _native():
+    """The mb200_comm handle when the job runs on NCCL (created on first use), else None."""
+    global _COMM
+    d = _dist()
+    if not (d.is_available() and d.is_initialized()) or d.get_backend() != "nccl":
+        return None
+    if _COMM is None:
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        path = None
+        try:
+            import nvidia.nccl as _n  # the copy PyTorch ships (already mapped into the process)
+
+            cand = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+            path = cand.encode() if os.path.exists(cand) else None
+        except Exception:
+            pass
+        _lib.check(lib.mb200_comm_load(path))
+        uid = (C.c_char * 128)()
+        payload = [None]
+        if d.get_rank() == 0:
+            _lib.check(lib.mb200_comm_unique_id(uid))
+            payload = [bytes(uid)]
+        d.broadcast_object_list(payload, src=0)
+        handle = C.c_void_p()
+        _lib.check(lib.mb200_comm_init_rank(C.byref(handle), d.get_world_size(), payload[0], d.get_rank()))
+        _COMM = (lib, handle)
+    return _COMM
+
+
+def _code(tensor):
+    t = _torch()
+    if tensor.dtype == t.float64:
+        return 0
+    if tensor.dtype == t.int64:
+        return 1
+    if tensor.dtype in (t.uint8, t.bool):
+        return 2
+    raise TypeError(f"collectives of the B200 path move float64 / int64 / uint8 buffers, not {tensor.dtype}")
+
+
+def _stream():
+    return _torch().cuda.current_stream().cuda_stream
+
 
 def all_reduce_inplace(tensor, op: str) -> None:
     """Element-wise all_reduce of one (large) device array in place -- the cross-GPU merge of dense
     group tables: NVSwitch carries 2 (W-1)/W x the table once, no keys move."""
     if is_distributed() and tensor.numel():
+        nat = _native()
+        if nat is not None:
+            from . import _lib
+
+            _lib.check(nat[0].mb200_comm_allreduce(nat[1], tensor.data_ptr(), tensor.data_ptr(), tensor.numel(),
+                                                   _code(tensor), _COMM_OPS[op], _stream()))  # fmt: skip
+            return
         d = _dist()
         d.all_reduce(tensor, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
 
@@ -166,6 +228,13 @@ def dense_chunk(nkeys: int, ws: int | None = None) -> int:
 def reduce_scatter(out, inp, op: str) -> None:
     """``out`` <- this rank's equal slice of the element-wise reduction of ``inp`` over the ranks (NCCL
     reduce-scatter over NVLink: each rank receives (W-1)/W of ONE slice instead of the all_reduce's whole array)."""
+    nat = _native()
+    if nat is not None:
+        from . import _lib
+
+        _lib.check(nat[0].mb200_comm_reduce_scatter(nat[1], inp.data_ptr(), out.data_ptr(), out.numel(), _code(out),
+                                                    _COMM_OPS[op], _stream()))  # fmt: skip
+        return
     d = _dist()
     d.reduce_scatter_tensor(out, inp, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
 
@@ -183,7 +252,7 @@ def all_reduce_values(tensors: Sequence, ops: Sequence[str]) -> None:
         buckets.setdefault((x.dtype, op), []).append(i)
     for (dtype, op), idxs in buckets.items():
         packed = t.cat([tensors[i].reshape(-1) for i in idxs])
-        d.all_reduce(packed, op=getattr(d.ReduceOp, _REDUCE_OPS[op]))
+        all_reduce_inplace(packed, op)
         off = 0
         for i in idxs:
             n = tensors[i].numel()
@@ -211,11 +280,42 @@ def all_gather_rows(cols: Sequence) -> List:
         # all_gather needs equal shapes: pad to the longest shard
         padded = t.zeros(m, dtype=c.dtype, device=c.device)
         padded[:n_local] = c
-        gathered = [t.empty(m, dtype=c.dtype, device=c.device) for _ in range(ws)]
-        d.all_gather(gathered, padded)
+        nat = _native()
+        if nat is not None and m:
+            from . import _lib
+
+            flat = t.empty(ws * m, dtype=c.dtype, device=c.device)
+            _lib.check(nat[0].mb200_comm_allgather(nat[1], padded.data_ptr(), flat.data_ptr(), m, _code(padded), _stream()))
+            gathered = [flat[r * m : (r + 1) * m] for r in range(ws)]
+        else:
+            gathered = [t.empty(m, dtype=c.dtype, device=c.device) for _ in range(ws)]
+            d.all_gather(gathered, padded)
         pieces = [g[:k] for g, k in zip(gathered, counts)]
         out.append(t.cat(pieces))
     return out
+
+
+def _all_to_all_rows(recv, packed, recv_rows, send_rows) -> None:
+    """all_to_all of a row-major [rows, ncols] int64 matrix split by rows: ``mb200_comm_alltoallv`` (grouped
+    ncclSend / ncclRecv on the rank's stream) under NCCL, ``all_to_all_single`` under gloo."""
+    nat = _native()
+    if nat is None:
+        _dist().all_to_all_single(recv, packed, output_split_sizes=list(recv_rows), input_split_sizes=list(send_rows))
+        return
+    import ctypes as C
+
+    from . import _lib
+
+    n = len(send_rows)
+
+    def arr(vals):
+        return (C.c_int64 * n)(*[int(v) for v in vals])
+
+    sd = [sum(send_rows[:i]) for i in range(n)]
+    rd = [sum(recv_rows[:i]) for i in range(n)]
+    row_bytes = int(packed.shape[1]) * 8 if packed.dim() == 2 else 8
+    _lib.check(nat[0].mb200_comm_alltoallv(nat[1], packed.data_ptr(), arr(send_rows), arr(sd), recv.data_ptr(),
+                                           arr(recv_rows), arr(rd), row_bytes, _stream()))  # fmt: skip
 
 
 def exchange_rows(columns: Sequence, send_counts: Sequence[int]) -> List:
@@ -237,7 +337,7 @@ def exchange_rows(columns: Sequence, send_counts: Sequence[int]) -> List:
     for j, c in enumerate(columns):
         packed[:, j] = c.view(t.int64) if c.dtype != t.int64 else c
     recv = t.empty((sum(rcl), len(columns)), dtype=t.int64, device=dev)
-    d.all_to_all_single(recv, packed, output_split_sizes=rcl, input_split_sizes=scl)
+    _all_to_all_rows(recv, packed, rcl, scl)
     outs = []
     for j, c in enumerate(columns):
         col = recv[:, j].contiguous()
@@ -301,7 +401,7 @@ def exchange_by_key_range(sorted_keys, columns: Sequence):
     for j, c in enumerate(columns):
         packed[:, j + 1] = c.view(t.int64) if c.dtype != t.int64 else c
     recv = t.empty((sum(rc), ncols), dtype=t.int64, device=dev)
-    d.all_to_all_single(recv, packed, output_split_sizes=rc, input_split_sizes=sc)
+    _all_to_all_rows(recv, packed, rc, sc)
     keys = recv[:, 0].contiguous()
     outs = []
     for j, c in enumerate(columns):
