@@ -46,6 +46,9 @@ int dev_props(DevProps* out);
 // unsupported) and the largest access-policy window; the last release hands the whole L2 back.
 size_t l2_carveout_acquire(size_t* max_window_bytes);
 void l2_carveout_release();
+// hand an unused carve-out back to normally managed L2 (a device-synchronising call: done lazily, by kernels that want
+// the whole L2 for themselves, never per group table)
+void l2_carveout_drop_idle();
 
 // ---------------------------------------------------------------- streaming loads/stores
 // 256-bit global accesses (LDG.E.256 / STG.E.256 on sm_100a).  Streaming data is read

@@ -412,6 +412,7 @@ using namespace mb200;
 extern "C" int mb200_join_build(mb200_join_table** table, const int64_t* dim_keys, int64_t ndim,
                                 mb200_stream_t stream) {
   if (!table) return fail("mb200_join_build", "null out pointer");
+  l2_carveout_drop_idle();  // a carve-out left behind by group tables: the dim table wants the whole L2
   if (ndim < 0 || ndim > 0x7fffffffLL) return fail("mb200_join_build", "dim rows must be in [0, 2^31)");
   if (ndim > 0 && !dim_keys) return fail("mb200_join_build", "null keys");
   DevProps dp;
@@ -553,6 +554,7 @@ struct JoinWindow {
 
 extern "C" int mb200_join_probe(mb200_join_table* t, const int64_t* fact_keys, int64_t nfact, int64_t* out_idx,
                                 int64_t* out_nmatch_dev, mb200_stream_t stream) {
+  l2_carveout_drop_idle();
   if (!t) return fail("mb200_join_probe", "null table");
   if (nfact < 0) return fail("mb200_join_probe", "negative nfact");
   if (nfact == 0) return 0;
@@ -578,6 +580,7 @@ extern "C" int mb200_join_probe(mb200_join_table* t, const int64_t* fact_keys, i
 extern "C" int mb200_join_probe_gather(mb200_join_table* t, const int64_t* fact_keys, int64_t nfact, int ncols,
                                        const void* const* dim_cols, int dim_dtype, void* const* out_cols,
                                        int64_t* out_nmatch_dev, mb200_stream_t stream) {
+  l2_carveout_drop_idle();
   if (!t) return fail("mb200_join_probe_gather", "null table");
   if (ncols < 0 || ncols > MB200_MAX_COLS) return fail("mb200_join_probe_gather", "ncols out of range (0..32)");
   if (nfact < 0) return fail("mb200_join_probe_gather", "negative nfact");
