@@ -162,11 +162,15 @@ class GroupByReduce(Operator):
             raise NotImplementedError("groupby along axis=1 defaults to pandas in the reference; not on the B200 path")
         if not isinstance(by, type(query_compiler)):
             raise NotImplementedError("`by` must resolve to a column of a frame on the B200 path")
-        for key, allowed in (("as_index", (True,)), ("level", (None,)), ("observed", (True, False, None))):
+        for key, allowed in (("as_index", (True, False)), ("level", (None,)), ("observed", (True, False, None))):
             if groupby_kwargs.get(key, allowed[0]) not in allowed:
                 raise NotImplementedError(f"groupby({key}={groupby_kwargs[key]!r}) is not on the B200 path")
         # alg/groupby.py:403-416: keys are sorted anyway
         map_fn = Bound(map_func, agg_args, agg_kwargs)
         reduce_fn = Bound(reduce_func, agg_args, agg_kwargs)
         new_modin_frame = query_compiler._modin_frame.groupby_reduce(axis, by._modin_frame, map_fn, reduce_fn)
+        if not groupby_kwargs.get("as_index", True):
+            from .query_compiler import group_keys_to_columns
+
+            new_modin_frame = group_keys_to_columns(new_modin_frame)  # alg/groupby.py:278-294
         return query_compiler.__constructor__(new_modin_frame)

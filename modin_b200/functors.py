@@ -1104,6 +1104,20 @@ def _partial_block(agg, keys, key_label, sums, cnts, sizes, labels, count_dev=No
     return blk
 
 
+def keys_to_columns(block: DeviceBlock, offset: int = 0) -> DeviceBlock:
+    """``groupby(..., as_index=False)``: the group keys (device index columns) become the leading columns and the rows
+    get a fresh RangeIndex starting at ``offset`` (``GroupBy.handle_as_index_for_dataframe``, alg/groupby.py:278-294)
+    -- buffers are shared, nothing is copied."""
+    if not block.index_cols:
+        return block
+    names = list(block.index_names or [None] * len(block.index_cols))
+    clash = [n for n in names if n in set(block.columns)]
+    if clash:
+        raise ValueError(f"cannot insert {clash[0]}, already exists")
+    labels = pandas.Index(names).append(block.columns)
+    return DeviceBlock(list(block.index_cols) + list(block.cols), labels, nrows=block.nrows, range_start=offset)
+
+
 class DevGroupbyReduce(DevFn):
     """GroupByReduce.reduce (alg/groupby.py:211-300): regroup the concatenated partial tables by
     key (level 0) with the reduce aggregation (sum of sums / counts / sizes; mean = sum/count)."""

@@ -219,11 +219,15 @@ def register(shims: bool | None = None):
             def caller(query_compiler, by, axis, groupby_kwargs, agg_args, agg_kwargs, drop=False, **kwargs):
                 if axis != 0 or not isinstance(by, type(query_compiler)) or len(by.columns) != 1:
                     raise NotImplementedError("device groupby: one key column of the same frame, axis=0")
-                if not groupby_kwargs.get("as_index", True) or groupby_kwargs.get("level") is not None:
-                    raise NotImplementedError("device groupby: as_index=True, no level=")
+                if groupby_kwargs.get("level") is not None:
+                    raise NotImplementedError("device groupby: no level=")
                 # the functors themselves, not lambdas around them: the partition manager recognises them and fuses
                 # map + reduce into one direct-addressed table per GPU when the key range allows (pm.groupby_reduce)
                 new_frame = query_compiler._modin_frame.groupby_reduce(axis, by._modin_frame, map_f, red_f)
+                if not groupby_kwargs.get("as_index", True):
+                    from .query_compiler import group_keys_to_columns
+
+                    new_frame = group_keys_to_columns(new_frame)  # alg/groupby.py:278-294
                 return query_compiler.__constructor__(new_frame)
 
             return caller
@@ -468,6 +472,24 @@ def register(shims: bool | None = None):
     class B200IO(BaseIO):
         frame_cls = B200OnModinDataframe
         query_compiler_cls = B200OnModinQueryCompiler
+
+        @classmethod
+        def read_parquet(cls, **kwargs):
+            """io.py:218-220 defaults to ``pandas.read_parquet`` + ``from_pandas``; here the file is decoded to an
+            Arrow table on the host (pyarrow) and its column buffers are copied to the device as they are
+            (``from_arrow``: no pandas frame in between).  ``path`` and ``columns`` only; filters, partitioned
+            datasets and storage options are the reference's ``parquet_dispatcher`` (962 lines), out of scope."""
+            import pyarrow.parquet as pq
+
+            path = kwargs.pop("path")
+            columns = kwargs.pop("columns", None)
+            from pandas._libs import lib as pandas_lib
+
+            extra = {k: v for k, v in kwargs.items() if v is not pandas_lib.no_default and v not in (None, False, "auto")
+                     and k not in ("engine", "dtype_backend", "filesystem")}  # fmt: skip
+            if extra:
+                raise NotImplementedError(f"read_parquet({', '.join(sorted(extra))}=...) is not on the B200 path")
+            return cls.from_arrow(pq.read_table(path, columns=columns))
 
     class ArrowOnB200Factory(factories.BaseFactory):
         @classmethod

@@ -634,8 +634,6 @@ class DataFrameGroupBy:
         self._by = by_qc
         self._drop = drop
         self._kwargs = groupby_kwargs
-        if not groupby_kwargs.get("as_index", True):
-            raise NotImplementedError("groupby(as_index=False) is not on the B200 path")
 
     def _wrap_aggregation(self, qc_method, numeric_only=False, agg_args=None, agg_kwargs=None):
         qc = self._query_compiler

@@ -286,6 +286,27 @@ class B200QueryCompiler:
         return self.__constructor__(row_axis_merge(self, right, _reset_row_index, **kwargs))
 
 
+def group_keys_to_columns(frame):
+    """Result frame of a device groupby with ``as_index=False``: keys as leading columns, rows renumbered 0..G-1 over
+    all row partitions (and ranks, in rank order = key order).  Metadata only."""
+    from . import dist
+    from .functors import keys_to_columns
+
+    lengths = [row[0].length() for row in frame._partitions]
+    offset = dist.exclusive_row_offset(sum(lengths)) if dist.is_distributed() else 0
+    pc = frame._partition_mgr_cls._partition_class
+    rows = []
+    for row, n in zip(frame._partitions, lengths):
+        if len(row) != 1:
+            raise NotImplementedError("groupby(as_index=False) results wider than one column partition")
+        rows.append([pc(keys_to_columns(row[0].get(), offset))])
+        offset += n
+    first = rows[0][0].get()
+    start = offset - sum(lengths)
+    return type(frame)(np.array(rows, dtype=object), pandas.RangeIndex(start, offset), first.columns, lengths,
+                       [len(first.cols)], None)  # fmt: skip
+
+
 def _frame_device(frame):
     """Device of the frame's first non-empty block (works for the mirror frame and for Modin's ``PandasDataframe``)."""
     from .block import current_device

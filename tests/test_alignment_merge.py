@@ -230,3 +230,51 @@ def test_shuffle_partitions_on_b200():
     import modin_b200.pandas as bpd
 
     _shuffle_checks(bpd, 1 << 21)
+
+
+# ---- groupby(as_index=False) (alg/groupby.py:278-294) and read_parquet -> Arrow -> device ---------------------------
+def _as_index_and_parquet_checks(pdm, tmp_path, real_modin):
+    pdf = synth.host_frame(5000, 3, seed=2, nan_per_64k=2000, key_modulus=37)
+    for agg in ("sum", "count", "max"):
+        got = getattr(pdm.DataFrame(pdf).groupby("key", as_index=False), agg)()._to_pandas()
+        want = getattr(pdf.groupby("key", as_index=False), agg)()
+        assert list(got.columns) == list(want.columns) and got.index.equals(want.index), agg
+        assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True), agg
+    if real_modin:
+        path = os.path.join(str(tmp_path), "frame.parquet")
+        pdf.to_parquet(path)
+        got = pdm.read_parquet(path, columns=["key", "c1"])
+        from modin_b200.block import DeviceBlock
+
+        assert all(isinstance(p.get(), DeviceBlock) for p in got._query_compiler._modin_frame._partitions.flatten())
+        assert got._to_pandas().equals(pdf[["key", "c1"]])
+        with pytest.raises(NotImplementedError):
+            pdm.read_parquet(path, filters=[("key", ">", 3)])
+
+
+def test_as_index_false_on_the_double(cpu_device, tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    import modin_b200.pandas as bpd
+
+    _as_index_and_parquet_checks(bpd, tmp_path, False)
+
+
+@needs_modin
+def test_as_index_false_and_read_parquet_under_real_modin_on_the_double(cpu_device, tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    _as_index_and_parquet_checks(_modin(), tmp_path, True)
+
+
+@needs_modin
+@pytest.mark.gpu
+def test_as_index_false_and_read_parquet_under_real_modin_on_b200(tmp_path):
+    import modin_b200.pandas as bpd
+
+    _as_index_and_parquet_checks(bpd, tmp_path, False)
+    _as_index_and_parquet_checks(_modin(), tmp_path, True)
