@@ -455,19 +455,26 @@ __global__ void __launch_bounds__(kGbThreads, 5) gb_accumulate_kernel(const __gr
 // a key with 10 % of 1e9 rows costs ~0.8 s).  SUM / COUNT tables only.
 constexpr int kHotSlots = 256;
 constexpr int kHotStride = 9;  // doubles per cached group (8 sums + 1 pad against bank conflicts)
-constexpr int kHotOffset = ((kGbStages * kStageBytes + 2 * kGbStages * 8 + 63) / 64) * 64;
-constexpr int kHotBytes = kHotSlots * 4 + kHotSlots * kHotStride * 8 + kHotSlots * kHotStride * 4;
+// The HOT variant runs a 2-stage ring (the plain one 3): its cache shares the SM's shared memory with the ring, and
+// at 3 stages only 2 CTAs fit per SM (ncu, round 2: 28 % of the warp slots occupied, issue 44 % busy) -- 2 stages
+// and no count array for pure sums fit 3-4.
+constexpr int kHotStages = 2;
+__host__ __device__ constexpr int hot_offset(int stages) {
+  return ((stages * kStageBytes + 2 * stages * 8 + 63) / 64) * 64;
+}
+constexpr int kHotBytesSum = kHotSlots * 4 + kHotSlots * kHotStride * 8;                 // tags + sums
+constexpr int kHotBytes = kHotBytesSum + kHotSlots * kHotStride * 4;                     // ... + counts
 constexpr int kHotBit = 1 << 30;  // group ids are < 2^29
 
-template <bool HOT>
+template <bool HOT, int STAGES>
 __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const __grid_constant__ GbParams p,
                                                                           long long ntiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kGbStages * kStageBytes);
-  uint64_t* empty = full + kGbStages;
-  int* s_tag = reinterpret_cast<int*>(smem_raw + kHotOffset);
-  double* s_hot = reinterpret_cast<double*>(smem_raw + kHotOffset + kHotSlots * 4);
-  unsigned int* s_hcnt = reinterpret_cast<unsigned int*>(smem_raw + kHotOffset + kHotSlots * 4 + kHotSlots * kHotStride * 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * kStageBytes);
+  uint64_t* empty = full + STAGES;
+  int* s_tag = reinterpret_cast<int*>(smem_raw + hot_offset(STAGES));
+  double* s_hot = reinterpret_cast<double*>(smem_raw + hot_offset(STAGES) + kHotSlots * 4);
+  unsigned int* s_hcnt = reinterpret_cast<unsigned int*>(smem_raw + hot_offset(STAGES) + kHotSlots * 4 + kHotSlots * kHotStride * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nv = p.nvals;
   const int gcap = (int)p.gcap;
@@ -478,12 +485,12 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     for (int i = tid; i < kHotSlots; i += kGbTmaThreads) s_tag[i] = -1;
     for (int i = tid; i < kHotSlots * kHotStride; i += kGbTmaThreads) {
       s_hot[i] = 0.0;
-      s_hcnt[i] = 0u;
+      if (p.flags & MB200_GB_COUNT) s_hcnt[i] = 0u;  // the count array exists only for COUNT tables
     }
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kGbStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kGbWarps);
     }
@@ -496,8 +503,8 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
       for (long long k = 0; k < nmine; ++k) {
-        const int s = (int)(k % kGbStages);
-        if (k >= kGbStages) mbar_wait(&empty[s], (uint32_t)(((k / kGbStages) - 1) & 1));
+        const int s = (int)(k % STAGES);
+        if (k >= STAGES) mbar_wait(&empty[s], (uint32_t)(((k / STAGES) - 1) & 1));
         const long long row0 = (first + k * gridDim.x) * kTileRows;
         double* stage = reinterpret_cast<double*>(smem_raw + (size_t)s * kStageBytes);
         mbar_expect_tx(&full[s], (uint32_t)((1 + nv) * kTileRows * 8));
@@ -513,15 +520,15 @@ __global__ void __launch_bounds__(kGbTmaThreads) gb_accumulate_tma_kernel(const 
   const uint64_t keep = table_policy(p.policy_mode);
   const int c = lane & 7;
   for (long long k = 0; k < nmine; ++k) {
-    const int s = (int)(k % kGbStages);
-    mbar_wait(&full[s], (uint32_t)((k / kGbStages) & 1));
+    const int s = (int)(k % STAGES);
+    mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
     const double* stage = reinterpret_cast<const double*>(smem_raw + (size_t)s * kStageBytes);
     const long long key = reinterpret_cast<const long long*>(stage)[warp * 32 + lane];
     if (p.prefetch && k + 1 < nmine) {
       // the next tile's keys are (normally) already in shared memory: pull the first probe slot of each of
       // this warp's next 32 rows into L2 now, one tile ahead of the dependent 128-bit slot load
-      const int s1 = (int)((k + 1) % kGbStages);
-      mbar_wait(&full[s1], (uint32_t)(((k + 1) / kGbStages) & 1));
+      const int s1 = (int)((k + 1) % STAGES);
+      mbar_wait(&full[s1], (uint32_t)(((k + 1) / STAGES) & 1));
       const long long nk =
           reinterpret_cast<const long long*>(smem_raw + (size_t)s1 * kStageBytes)[warp * 32 + lane];
       const Slot* ns = &p.slots[hash_key(nk) & p.mask];
@@ -1130,9 +1137,16 @@ static int gb_launch(mb200_gb_table* t, const long long* keys, const void* const
   if (variant == 0 && !partial && aligned && t->nvals <= 8 && nrows >= kTileRows) {
     const long long ntiles = nrows / kTileRows;
     const bool hot = t->skewed && !(t->flags & (MB200_GB_MIN | MB200_GB_MAX | MB200_GB_SIZE));
-    const size_t smem = hot ? (size_t)kHotOffset + kHotBytes
-                            : (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
-    auto kern = hot ? gb_accumulate_tma_kernel<true> : gb_accumulate_tma_kernel<false>;
+    // hashed tables: a 2-stage ring lets 5 CTAs share an SM instead of 4 (the probe chain wants warps, not staging
+    // depth); MB200_GB_STAGES=3 restores the 3-stage ring for comparison
+    const char* se = getenv("MB200_GB_STAGES");
+    const bool two = !hot && !t->dense && !(se && se[0] == '3');
+    const size_t smem = hot   ? (size_t)hot_offset(kHotStages) + ((t->flags & MB200_GB_COUNT) ? kHotBytes : kHotBytesSum)
+                        : two ? (size_t)2 * kStageBytes + 2 * 2 * sizeof(uint64_t)
+                              : (size_t)kGbStages * kStageBytes + 2 * kGbStages * sizeof(uint64_t);
+    auto kern = hot   ? gb_accumulate_tma_kernel<true, kHotStages>
+                : two ? gb_accumulate_tma_kernel<false, 2>
+                      : gb_accumulate_tma_kernel<false, kGbStages>;
     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGbTmaThreads, smem));

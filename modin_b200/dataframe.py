@@ -556,10 +556,13 @@ class B200Dataframe:
         new_columns = df.columns
         new_dtypes = df.dtypes
         parts, _, row_lengths, col_widths = cls._partition_mgr_cls.from_pandas(df, return_dims=True)
+        lo = 0
         if dist.is_distributed():
             lo, hi = dist.shard_bounds(len(df))
             new_index = new_index[lo:hi]
-        return cls(parts, new_index, new_columns, row_lengths, col_widths, dtypes=new_dtypes)
+        frame = cls(parts, new_index, new_columns, row_lengths, col_widths, dtypes=new_dtypes)
+        frame._b200_shard_offset = lo  # this rank's first global row position (a fresh ingest: rows are in job order)
+        return frame
 
     @classmethod
     def from_arrow(cls, at):

@@ -87,5 +87,15 @@ def row_axis_merge(left_qc, right_qc, reset_row_index, **kwargs):
         axis=1, func=func, other=right_to_broadcast, keep_partitioning=True, num_splits=1, new_columns=new_columns,
         sync_labels=False,
     )  # fmt: skip
-    # merge.py:236-250: the result index is reset to a fresh RangeIndex (metadata only on range-indexed blocks)
-    return reset_row_index(new_frame)
+    # merge.py:236-250: the result index is reset to a fresh RangeIndex (metadata only on range-indexed blocks).  A left
+    # join against distinct keys keeps the left rows one to one: when the left shard still carries its original
+    # job-wide range labels, their start is this rank's offset and no rank has to ask the others for their row counts
+    hint = None
+    if how == "left" and dist.is_distributed():
+        # `_b200_shard_offset` is set by the ingest paths on EVERY rank alike (from_pandas / from_arrow / from_blocks),
+        # so all ranks take the same branch -- a collective that only some ranks reach would hang
+        off = getattr(left_frame, "_b200_shard_offset", None)
+        rblock = right_to_broadcast._partitions[0, 0].get()
+        if off is not None and func._table(rblock)[1]:
+            hint = off
+    return reset_row_index(new_frame, hint) if hint is not None else reset_row_index(new_frame)

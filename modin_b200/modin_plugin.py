@@ -138,10 +138,13 @@ def register(shims: bool | None = None):
             """df.py:4592-4620 pairs ``df.index`` with the partitions of ``df``; under torch.distributed the
             partitions hold this rank's contiguous row shard only, so index, dtypes and row lengths are the
             shard's (the same split ``B200Dataframe.from_pandas`` makes)."""
+            lo = 0
             if bdist.is_distributed():
                 lo, hi = bdist.shard_bounds(len(df))
                 df = df.iloc[lo:hi]
-            return super().from_pandas(df)
+            frame = super().from_pandas(df)
+            frame._b200_shard_offset = lo  # this rank's first global row position (see merge.row_axis_merge)
+            return frame
 
         @classmethod
         def from_pandas_replicated(cls, df):
@@ -539,6 +542,7 @@ def from_device_blocks(blocks):
     index = pandas.RangeIndex(start, start + sum(b.nrows for b in blocks))
     frame = ns.Dataframe(parts, index, blocks[0].columns, [b.nrows for b in blocks], [len(blocks[0].cols)],
                          dtypes=blocks[0].dtypes)  # fmt: skip
+    frame._b200_shard_offset = start  # this rank's first global row position (see merge.row_axis_merge)
     return mpd.DataFrame(query_compiler=ns.QueryCompiler(frame))
 
 

@@ -318,15 +318,20 @@ def _frame_device(frame):
     return current_device()
 
 
-def _reset_row_index(frame: B200Dataframe) -> B200Dataframe:
+def _reset_row_index(frame: B200Dataframe, offset_hint=None) -> B200Dataframe:
     """``reset_index(drop=True)`` on range-indexed device blocks: renumber ``range_start`` so that
-    the row partitions of this rank form one contiguous RangeIndex (metadata only, no kernel)."""
+    the row partitions of this rank form one contiguous RangeIndex (metadata only, no kernel).
+    ``offset_hint``: this rank's first global row position when the caller already knows it (a left merge keeps
+    the left frame's rows, so the left shard's own range start is the answer) -- saves the collective + D2H that
+    counting the other ranks' rows costs."""
     from . import dist
     from .block import DeviceBlock
 
     lengths = frame.row_lengths
     offset = 0
-    if dist.is_distributed():
+    if offset_hint is not None:
+        offset = int(offset_hint)
+    elif dist.is_distributed():
         import torch
 
         dev = _frame_device(frame)

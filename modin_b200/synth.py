@@ -135,4 +135,7 @@ def device_frame(nrows: int, ncols: int, **kwargs):
     from .pandas import DataFrame
     from .query_compiler import B200QueryCompiler
 
-    return DataFrame(query_compiler=B200QueryCompiler(B200Dataframe.from_blocks(device_blocks(nrows, ncols, **kwargs))))
+    blocks = device_blocks(nrows, ncols, **kwargs)
+    frame = B200Dataframe.from_blocks(blocks)
+    frame._b200_shard_offset = blocks[0].range_start  # every rank generates its own contiguous shard of the job's rows
+    return DataFrame(query_compiler=B200QueryCompiler(frame))
