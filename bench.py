@@ -494,6 +494,7 @@ def run_b200_arm(args):
         return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch_local, "launch_ms": lm, "step_ms": step,
+                "per_step_ms": [round(x, 3) for x in per_ms],
                 "step_frac": bytes_per_launch_local / (step / 1e3) / 1e9 / hbm_peak, **extra}  # fmt: skip
 
     def sample_rows(n):

@@ -303,7 +303,13 @@ extern "C" int mb200_concat(int nsrc, const void* const* src, const int64_t* src
                             mb200_stream_t stream) {
   if (nsrc < 0) return fail("mb200_concat", "negative nsrc");
   if (nsrc == 0) return 0;
-  if (!src || !src_bytes || !dst) return fail("mb200_concat", "null argument");
+  if (!src || !src_bytes) return fail("mb200_concat", "null argument");
+  {
+    long long total = 0;
+    for (int i = 0; i < nsrc; ++i) total += src_bytes[i] > 0 ? src_bytes[i] : 0;
+    if (total == 0) return 0;  // nothing to copy: an empty destination has no buffer
+  }
+  if (!dst) return fail("mb200_concat", "null destination");
   DevProps dp;
   if (int rc = dev_props(&dp)) return rc;
   long long dst_off = 0;

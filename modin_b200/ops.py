@@ -668,6 +668,9 @@ def concat_columns(pieces: Sequence[DeviceColumn]) -> DeviceColumn:
     if any(p.dtype != dtype for p in pieces):
         raise TypeError("concat_columns needs pieces of one dtype")
     out = DeviceColumn.empty(sum(len(p) for p in pieces), dtype)
+    pieces = [p for p in pieces if len(p)]  # empty pieces have no buffer (and nothing to copy)
+    if not pieces:
+        return out
     item = 1 if dtype == np.bool_ else 8
     sizes = (C.c_int64 * len(pieces))(*[len(p) * item for p in pieces])
     _lib.check(lib.mb200_concat(len(pieces), _lib.ptr_array([p.ptr for p in pieces]), sizes, out.ptr, current_stream()))
