@@ -220,13 +220,42 @@ def register(shims: bool | None = None):
             map_f, red_f = fx.DevGroupbyMap(agg), fx.DevGroupbyReduce(agg)
 
             def caller(query_compiler, by, axis, groupby_kwargs, agg_args, agg_kwargs, drop=False, **kwargs):
-                if axis != 0 or not isinstance(by, type(query_compiler)) or len(by.columns) != 1:
-                    raise NotImplementedError("device groupby: one key column of the same frame, axis=0")
+                if axis != 0 or not isinstance(by, type(query_compiler)) or len(by.columns) < 1:
+                    raise NotImplementedError("device groupby: key columns of the same frame, axis=0")
                 if groupby_kwargs.get("level") is not None:
                     raise NotImplementedError("device groupby: no level=")
+                frame, by_frame = query_compiler._modin_frame, by._modin_frame
+                plan = names = None
+                if len(by.columns) > 1:
+                    # several int64 keys: packed into one order-preserving int64 on the device (groupkeys.py), the
+                    # single-key groupby runs on the image, the G result keys are unpacked into index columns
+                    from . import groupkeys as gk
+                    from .block import concat_cols
+
+                    names = list(by.columns)
+                    if drop:
+                        keep = [c for c in query_compiler.columns if c not in set(names)]
+                        frame = query_compiler.getitem_column_array(keep)._modin_frame
+                    rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in by_frame._partitions]
+                    plan = gk.packing_plan(rows)
+                    pc = by_frame._partition_mgr_cls._partition_class
+                    label = pandas.Index([gk.PACKED_KEY])
+                    parts = np.array([[pc(DeviceBlock([gk.pack(b, plan)], label, nrows=b.nrows, range_start=b.range_start))]
+                                      for b in rows], dtype=object)  # fmt: skip
+                    by_frame = type(by_frame)(parts, by_frame.copy_index_cache(), label, by_frame.row_lengths, [1])
                 # the functors themselves, not lambdas around them: the partition manager recognises them and fuses
                 # map + reduce into one direct-addressed table per GPU when the key range allows (pm.groupby_reduce)
-                new_frame = query_compiler._modin_frame.groupby_reduce(axis, by._modin_frame, map_f, red_f)
+                new_frame = frame.groupby_reduce(axis, by_frame, map_f, red_f)
+                if plan is not None:
+                    pc = new_frame._partition_mgr_cls._partition_class
+                    rows = []
+                    for row in new_frame._partitions:
+                        b = row[0].get()
+                        nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=gk.unpack(b.index_cols[0], plan),
+                                         index_names=names)  # fmt: skip
+                        nb.keys_sorted_unique = True
+                        rows.append([pc(nb)])
+                    new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)
                 if not groupby_kwargs.get("as_index", True):
                     from .query_compiler import group_keys_to_columns
 

@@ -240,6 +240,17 @@ def _as_index_and_parquet_checks(pdm, tmp_path, real_modin):
         want = getattr(pdf.groupby("key", as_index=False), agg)()
         assert list(got.columns) == list(want.columns) and got.index.equals(want.index), agg
         assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True), agg
+    # several int64 keys (packed into one order-preserving int64 on the device, groupkeys.py)
+    pdf["k2"] = synth.gen_i64(5000, 99, 1, 5) * 10 - 20
+    for agg in ("sum", "count", "min"):
+        got = getattr(pdm.DataFrame(pdf).groupby(["key", "k2"]), agg)()._to_pandas()
+        want = getattr(pdf.groupby(["key", "k2"]), agg)()
+        assert got.index.equals(want.index) and list(got.columns) == list(want.columns), agg
+        assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True), agg
+    if real_modin:
+        got = pdm.DataFrame(pdf).groupby(["key", "k2"], as_index=False).sum()._to_pandas()
+        want = pdf.groupby(["key", "k2"], as_index=False).sum()
+        assert list(got.columns) == list(want.columns) and np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9)
     if real_modin:
         path = os.path.join(str(tmp_path), "frame.parquet")
         pdf.to_parquet(path)
