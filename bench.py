@@ -737,6 +737,8 @@ def run_b200_arm(args):
             ms_m = total_m / ksteps
             moved16, moved152 = rows_local * 16, rows_local * 152
             rf = roof(kern, moved16, per_m, launch_ms=km_ms)
+            rf["traffic_note"] = ("no ncu capture of the key-ordered payload probe this leg runs; the rows[] + gather "
+                                  "variant moves 6.2x its algorithmic bytes (profiles/traffic.json: join_dense_gather)")
             rf["note"] = ("algorithmic bytes = 16 B/row: key read + payload written -- the fact columns of the result are "
                           "shared by reference, never copied; SURVEY 8(d) counts the reference's materialised output, "
                           "152 B/row: see frac_vs_152B_row")
