@@ -420,15 +420,25 @@ def run_b200_arm(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
-    distributed = dist.init_from_env("nccl")
+    # DEV / backend are "cuda" / "nccl" in every real run; tests/bench_dryrun.py swaps the device for the numpy double
+    # (and torch.cuda.* for stand-ins) to run this function's control flow under gloo at world sizes no CPU box has GPUs for
+    DEV = os.environ.get("MB200_BENCH_DEVICE", "cuda")
+    distributed = dist.init_from_env("nccl" if DEV == "cuda" else "gloo")
     ws, rank = dist.world_size(), dist.rank()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     lib = _lib.load()
-    _lib.check(lib.mb200_device_check(local))
+    if DEV == "cuda":
+        _lib.check(lib.mb200_device_check(local))
     NPartitions.put(1)
     hbm_peak, peak_src = measured_peaks()
     api = Api(args.api)
+
+    def progress(msg):
+        """One line per leg on stderr (rank 0): where a run is, should it ever stop making progress."""
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
 
     rows, W, G = int(args.rows), args.cols, args.groups
     lo, hi = dist.shard_bounds(rows)
@@ -443,14 +453,14 @@ def run_b200_arm(args):
     def max_over_ranks(ms: float) -> float:
         if not distributed:
             return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms], dtype=torch.float64, device=DEV)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
     def all_ranks_ok(ok: bool) -> bool:
         if not distributed:
             return bool(ok)
-        t = torch.tensor([0 if ok else 1], dtype=torch.int64, device="cuda")
+        t = torch.tensor([0 if ok else 1], dtype=torch.int64, device=DEV)
         torch.distributed.all_reduce(t)
         return int(t.item()) == 0
 
@@ -505,6 +515,7 @@ def run_b200_arm(args):
 
     # ---- multi-GPU parity before anything is timed ------------------------------------------------
     parity_ok, parity_fails = None, []
+    progress(f"start: {ws} rank(s), {rows} rows, front door {api.which}")
     if distributed:
         try:
             ok, parity_fails = parity_over_ranks(api)
@@ -513,6 +524,7 @@ def run_b200_arm(args):
         parity_ok = all_ranks_ok(ok)
 
     # ---- headline: fused a*b+c through the public API ---------------------------------------
+    progress(f"parity_ok={parity_ok}; headline map")
     a = api.device_frame(rows, W, seed=42)
     api.execute(a)
     last = [None]
@@ -533,7 +545,7 @@ def run_b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     launches_timed = round(launches * args.steps / max(args.steps + args.warmup, 1))
     if distributed:
-        t = torch.tensor([launches_timed], dtype=torch.int64, device="cuda")
+        t = torch.tensor([launches_timed], dtype=torch.int64, device=DEV)
         torch.distributed.all_reduce(t)
         launches_timed = int(t.item())
     ms_per_step = total_ms / args.steps
@@ -566,6 +578,7 @@ def run_b200_arm(args):
         a = None
         torch.cuda.empty_cache()
 
+        progress("leg: TreeReduce sum / mean, 16 columns")
         # ---- TreeReduce (C3): df.sum() / df.mean() over 16 float64 columns.  1e9 x 16 f64 = 128 GB: the whole frame
         # on one 180 GB B200, 16 GB per GPU at 8
         W3 = 16
@@ -598,6 +611,7 @@ def run_b200_arm(args):
 
         # ---- Binary template on three frames: a*b+c with b, c frames (C2 secondary form; 256 B/row fused).
         # Four n x 8 frames are resident, so n = rows/4 (2.5e8 per 1e9: 64 GB on one GPU)
+        progress("leg: three-frame a*b+c")
         rows3 = max(rows // 4, 1024)
         lo3, _hi3 = dist.shard_bounds(rows3)
         fa, fb, fc = (api.device_frame(rows3, W, seed=s) for s in (42, 44, 45))
@@ -627,6 +641,7 @@ def run_b200_arm(args):
         # ---- GroupByReduce: groupby('key').sum(), G int64 keys, 8 float64 values (C4)
         def groupby_leg(skew, dense_on, label, kern, traffic_key):
             nonlocal roofline_groupby
+            progress(f"leg: groupby{label or ' dense'}")
             g = api.device_frame(rows, W, seed=42, key_modulus=G, key_skew=skew)
             api.execute(g)
             _cfg.GroupbyDenseKeys.put(dense_on)
@@ -699,6 +714,7 @@ def run_b200_arm(args):
         del kc
 
         # ---- broadcast merge: fact (rows x (key + 8 f64)) LEFT JOIN dim (1e7 x (key + 1 f64)) on int64 key (C5)
+        progress("leg: broadcast merge")
         ndim = int(min(10_000_000, max(1000, rows // 100)))
         fact = api.device_frame(rows, W, seed=42, key_modulus=ndim)
         api.execute(fact)
@@ -766,6 +782,7 @@ def run_b200_arm(args):
 
     # ---- e2e: host frames in, host frames out, through the public API (rank-local sample) ----------------
     e2e = e2e_groupby = None
+    progress("legs done; e2e")
     if not args.skip_e2e:
         from modin_b200 import hostpath
 
@@ -857,6 +874,7 @@ def run_b200_arm(args):
         except Exception as e:  # the GPU numbers stand on their own; say why the CPU leg is missing
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e!r}"[:300]}
 
+    progress("done")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps,

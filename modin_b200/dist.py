@@ -99,6 +99,30 @@ def barrier():
         _dist().barrier()
 
 
+_CONTROL = None
+
+
+def _control_group():
+    """Process group for HOST-side integers every rank must agree on (is the job-wide frame empty? how many rows
+    are there?): gloo over CPU tensors, so that asking never waits for the GPU -- a NCCL all_reduce + ``.item()``
+    would drain the rank's stream and serialise an otherwise asynchronous pipeline.  Under a gloo job (CPU tests) it
+    is the default group.  Created collectively on first use (every rank reaches the first use together: SPMD)."""
+    global _CONTROL
+    d = _dist()
+    if _CONTROL is None:
+        _CONTROL = d.new_group(backend="gloo") if d.get_backend() != "gloo" else d.group.WORLD
+    return _CONTROL
+
+
+def control_sum(value: int) -> int:
+    """Sum of one host integer over the ranks, on the control group (no device synchronisation)."""
+    if not is_distributed():
+        return int(value)
+    t = _torch().tensor([int(value)], dtype=_torch().int64)
+    _dist().all_reduce(t, group=_control_group())
+    return int(t.item())
+
+
 def shard_bounds(nrows: int, r: int | None = None, ws: int | None = None):
     """Contiguous row range [lo, hi) owned by rank r: even split, remainder to the low ranks."""
     ws = world_size() if ws is None else ws

@@ -268,6 +268,26 @@ def register(shims: bool | None = None):
     _f64 = lambda *a, **k: np.dtype("float64")  # noqa: E731
 
     class B200OnModinQueryCompiler(PandasQueryCompiler):
+        def get_axis_len(self, axis):
+            """qc.py:411-427.  Under torch.distributed ``len(df)`` is the JOB-wide row count, not this rank's shard:
+            Modin's API layer decides from it whether a frame is ``empty`` -- and defaults every method call on an
+            empty frame to pandas (modin/pandas/base.py:4372) -- so a rank whose shard happens to be empty (a filter that
+            only matched rows elsewhere) would leave the device path, skip the collectives the other ranks issue, and
+            hang the job.  The count is agreed once per frame over the host-side control group (gloo: no device
+            synchronisation) and cached on the frame; results every rank holds in full answer locally."""
+            if axis == 0 and bdist.is_distributed():
+                frame = self._modin_frame
+                n = getattr(frame, "_b200_job_rows", None)
+                if n is None:
+                    local = len(frame)
+                    parts = frame._partitions.flatten()
+                    replicated = len(parts) > 0 and all(p._data is not None and getattr(p.get(), "replicated", False)
+                                                        for p in parts)  # fmt: skip
+                    n = local if replicated else bdist.control_sum(local)
+                    frame._b200_job_rows = n
+                return n
+            return super().get_axis_len(axis)
+
         # Map (qc.py:2036-2106)
         abs = Map.register(fx.DevMap("abs"), dtypes="copy")
         negative = Map.register(fx.DevMap("neg"), dtypes="copy")

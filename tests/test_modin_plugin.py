@@ -397,7 +397,15 @@ def _plugin_rank_job(rank, ws):
         fr = mdf._query_compiler._modin_frame
         assert type(fr) is ns.Dataframe
         lo, hi = (rank * 2003) // ws, ((rank + 1) * 2003) // ws  # shard_bounds for an even-ish split
-        out["local_rows"] = (len(mdf), int(mdf.index[0]), int(mdf.index[-1]))
+        out["local_rows"] = (len(fr), int(mdf.index[0]), int(mdf.index[-1]))
+        out["job_rows"] = len(mdf)  # Modin's API sees the job-wide row count (its emptiness test must agree on all ranks)
+        # a filter that leaves some ranks EMPTY must not make them leave the device path (Modin defaults every
+        # method of an empty frame to pandas, modin/pandas/base.py:4372): the reduction after it is a collective
+        withpos = vals.assign(pos=np.arange(len(vals), dtype=np.float64))
+        mpos = mpd.DataFrame(withpos)
+        first_rows = mpos[mpos["pos"] < 10.0]  # only rank 0 holds such rows
+        out["sum_after_one_sided_filter"] = first_rows.sum()._to_pandas()
+        out["len_after_one_sided_filter"] = len(first_rows)
         P = lambda x: x._to_pandas()  # noqa: E731
         out["affine"] = P(mdf * 1.5 + 0.25)
         out["abs"] = P(mdf.abs())
@@ -411,7 +419,8 @@ def _plugin_rank_job(rank, ws):
         for agg in ("sum", "count", "mean", "size", "min", "max"):
             r = getattr(g, agg)()
             out["gb_" + agg] = P(r)
-            out["gb_local_" + agg] = len(r)
+            out["gb_local_" + agg] = sum(r._query_compiler._modin_frame.row_lengths)  # this rank's key range
+            out["gb_job_" + agg] = len(r)  # len() of a frame is job-wide under torch.distributed
         rng = np.random.RandomState(1)
         dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
         out["merge_left"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="left"))
@@ -440,6 +449,11 @@ def test_plugin_under_two_gloo_ranks():
     pdf = synth.host_frame(2003, 4, seed=11, nan_per_64k=3000, key_modulus=23)
     vals = pdf.drop(columns="key")
     other = synth.host_frame(2003, 4, seed=12)
+    assert all(o["job_rows"] == 2003 for o in outs)
+    wpos = vals.assign(pos=np.arange(len(vals), dtype=np.float64))
+    for o in outs:
+        assert o["len_after_one_sided_filter"] == 10
+        assert np.allclose(o["sum_after_one_sided_filter"].to_numpy(), wpos[wpos["pos"] < 10.0].sum().to_numpy(), rtol=0, atol=1e-9)
     rows = [o["local_rows"] for o in outs]
     assert sum(r[0] for r in rows) == 2003 and rows[0][1] == 0 and rows[1][2] == 2002 and rows[0][2] + 1 == rows[1][1]
     rng = np.random.RandomState(1)
@@ -476,3 +490,4 @@ def test_plugin_under_two_gloo_ranks():
         assert list(o["sort"].index) == list(wsrt.index) and _same(o["sort"].to_numpy(), wsrt.to_numpy())
     # the group table is split by key range: both ranks own a part, together all 23 groups
     assert sum(o["gb_local_sum"] for o in outs) == pdf["key"].nunique() and all(o["gb_local_sum"] > 0 for o in outs)
+    assert all(o["gb_job_sum"] == pdf["key"].nunique() for o in outs)

@@ -78,7 +78,9 @@ def run_checks(bpd, tag, rank, fails):
     vals = pdf.drop(columns="key")
     df = bpd.DataFrame(pdf)  # this rank's shard only
     lo, hi = dist.shard_bounds(n)
-    check("local shard length", len(df) == hi - lo)
+    check("local shard length", len(df._query_compiler._modin_frame) == hi - lo)
+    check("len(df) is the job-wide row count" if tag == "modin" else "len(df) is this rank's shard",
+          len(df) == (n if tag == "modin" else hi - lo))
     dv = df[[f"c{i}" for i in range(W)]]
     NP = 4
 
