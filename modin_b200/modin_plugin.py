@@ -120,6 +120,21 @@ def register(shims: bool | None = None):
             shard's row labels, so the partition manager must not cut again."""
             return cls.from_pandas_local(df, return_dims)
 
+        # The grid walkers whose bodies are pure protocol (loop over the grid, call ``partition.apply`` /
+        # ``add_to_apply_calls`` / ``axis_partition.apply``) are Modin's OWN under the plug-in -- the standalone mirror
+        # carries restatements of them only because it must run without Modin.  What stays overridden above are the
+        # methods that do something different on a device: groupby_reduce (fused dense table), n_ary_operation (queued
+        # for fusion), shuffle_partitions, ingest / egress, combine, finalize / wait.
+        map_partitions = classmethod(PandasDataframePartitionManager.map_partitions.__func__)
+        lazy_map_partitions = classmethod(PandasDataframePartitionManager.lazy_map_partitions.__func__)
+        broadcast_axis_partitions = classmethod(PandasDataframePartitionManager.broadcast_axis_partitions.__func__)
+        map_axis_partitions = classmethod(PandasDataframePartitionManager.map_axis_partitions.__func__)
+        broadcast_apply = classmethod(PandasDataframePartitionManager.broadcast_apply.__func__)
+        base_broadcast_apply = classmethod(PandasDataframePartitionManager.base_broadcast_apply.__func__)
+        axis_partition = classmethod(PandasDataframePartitionManager.axis_partition.__func__)
+        column_partitions = classmethod(PandasDataframePartitionManager.column_partitions.__func__)
+        row_partitions = classmethod(PandasDataframePartitionManager.row_partitions.__func__)
+
     # ---------------------------------------------------------------- core dataframe
     class B200OnModinDataframe(PandasDataframe):
         _partition_mgr_cls = B200OnModinPartitionManager
