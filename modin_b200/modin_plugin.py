@@ -198,6 +198,16 @@ def register(shims: bool | None = None):
                 df = pandas.DataFrame(columns=self.columns, index=df.index)
             return df
 
+        def map(self, *args, **kwargs):
+            """df.py:2253-2322 hands the result this frame's row lengths -- a Map keeps the rows -- so the job-wide
+            row count (``get_axis_len``) is handed on with them: Modin's API asks ``.empty`` of every intermediate
+            frame, and an expression like ``df * b + c`` must not cost a control-plane collective per operator."""
+            out = super().map(*args, **kwargs)
+            rows = getattr(self, "_b200_job_rows", None)
+            if rows is not None:
+                out._b200_job_rows = rows
+            return out
+
         def _build_treereduce_func(self, axis, func):
             """df.py:2081-2123: device reduce functors already return the 1 x W block labelled
             ``__reduced__``; only pandas results need the Series -> frame conversion."""
@@ -295,9 +305,10 @@ def register(shims: bool | None = None):
                 n = getattr(frame, "_b200_job_rows", None)
                 if n is None:
                     local = len(frame)
+                    # the payloads as they are: asking must not run a partition's pending call queue (``get()`` would
+                    # launch a queued ``* b`` on its own and cost the fusion with the ``+ c`` that follows)
                     parts = frame._partitions.flatten()
-                    replicated = len(parts) > 0 and all(p._data is not None and getattr(p.get(), "replicated", False)
-                                                        for p in parts)  # fmt: skip
+                    replicated = len(parts) > 0 and all(getattr(p._data, "replicated", False) for p in parts)
                     n = local if replicated else bdist.control_sum(local)
                     frame._b200_job_rows = n
                 return n

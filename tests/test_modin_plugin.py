@@ -407,6 +407,9 @@ def _plugin_rank_job(rank, ws):
         out["sum_after_one_sided_filter"] = first_rows.sum()._to_pandas()
         out["len_after_one_sided_filter"] = len(first_rows)
         P = lambda x: x._to_pandas()  # noqa: E731
+        lazy = mdf * 1.5 + 0.25
+        out["len_of_lazy"] = len(lazy)  # asking for the length must not run the queued ops one by one
+        out["queued"] = [len(p.call_queue) for p in lazy._query_compiler._modin_frame._partitions.flatten()]
         out["affine"] = P(mdf * 1.5 + 0.25)
         out["abs"] = P(mdf.abs())
         out["lt"] = P(mdf < 0.0)
@@ -449,7 +452,8 @@ def test_plugin_under_two_gloo_ranks():
     pdf = synth.host_frame(2003, 4, seed=11, nan_per_64k=3000, key_modulus=23)
     vals = pdf.drop(columns="key")
     other = synth.host_frame(2003, 4, seed=12)
-    assert all(o["job_rows"] == 2003 for o in outs)
+    assert all(o["job_rows"] == 2003 and o["len_of_lazy"] == 2003 for o in outs)
+    assert all(q == 2 for o in outs for q in o["queued"]), "x * s + t must still be queued (-> one fused sweep)"
     wpos = vals.assign(pos=np.arange(len(vals), dtype=np.float64))
     for o in outs:
         assert o["len_after_one_sided_filter"] == 10
