@@ -467,14 +467,21 @@ def run_b200_arm(args):
     def timed(step_fn, steps, warmup):
         """W untimed steps, then exactly K steps between barrier+sync, CUDA events on the launching
         stream; returns (total ms max over ranks, per-step ms list on this rank)."""
+        import gc
+
         for _ in range(warmup):
             step_fn()
+        gc.collect()  # like timeit: a generation-2 collection (tens of ms with Modin's object graphs alive) must not
+        gc.disable()  # land inside a 3 ms step; the collector runs again as soon as the timed steps are launched
         sync_all()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         evs[0].record()
-        for i in range(steps):
-            step_fn()
-            evs[i + 1].record()
+        try:
+            for i in range(steps):
+                step_fn()
+                evs[i + 1].record()
+        finally:
+            gc.enable()
         torch.cuda.synchronize()
         per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
         total = evs[0].elapsed_time(evs[steps])
@@ -883,6 +890,8 @@ def run_b200_arm(args):
             "config": {"workload": f"map_partitions elementwise a*b+c (b,c scalars, fused AFFINE, 2 roundings) on "
                                    f"{rows}x{W} f64, row-sharded over {ws} GPU(s)", "rows": rows, "cols": W,
                        "l2_policy": "inputs_larger_than_l2 (64 GB streamed per step)", "npartitions_per_gpu": 1,
+                       "timing": "CUDA events on the launching stream, steps launched asynchronously, barrier + "
+                                 "synchronise either side, max over ranks; Python's cyclic GC paused for the K steps",
                        "api": api.name + ": (df * b + c)._query_compiler.execute()"},
             "checked": map_checked, "parity_ok": parity_ok, "parity_failed": parity_fails,
             "roofline": roofline, "roofline_groupby": roofline_groupby, "cpu_baseline": cpu,
