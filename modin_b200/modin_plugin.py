@@ -368,6 +368,70 @@ def register(shims: bool | None = None):
         groupby_min = B200GroupByReduce.register_agg("min")
         groupby_max = B200GroupByReduce.register_agg("max")
 
+        _DEVICE_AGGS = ("sum", "count", "size", "mean", "min", "max")
+
+        def groupby_agg(self, by, agg_func, axis, groupby_kwargs, agg_args, agg_kwargs, how="axis_wise", drop=False,
+                        series_groupby=False):  # fmt: skip
+            """qc.py:4236-4527.  The reference sends ``{column: function}`` dictionaries whose functions all have a
+            map / reduce form through ``_groupby_dict_reduce`` (qc.py:3876-3970: one map table and one reduce table
+            per function) and everything else through a full-axis ``groupby.agg`` on pandas blocks.  Here a dictionary
+            over the device aggregations becomes one device aggregation per DISTINCT function over the columns that
+            ask for it; every result carries the same ascending group keys, so the result blocks are zipped
+            column-wise (buffers shared) in the dictionary's order.  A function name alone goes to its registered
+            template.  Anything else has no device form and is refused -- there is no pandas block to fall back to."""
+            if how != "axis_wise" or agg_args or agg_kwargs:
+                raise NotImplementedError(f"groupby ({how}) with extra arguments is not on the B200 path")
+            if isinstance(agg_func, str) and agg_func in self._DEVICE_AGGS:
+                return getattr(self, f"groupby_{agg_func}")(
+                    by=by, axis=axis, groupby_kwargs=groupby_kwargs, agg_args=agg_args, agg_kwargs=agg_kwargs, drop=drop
+                )
+            if not isinstance(agg_func, dict) or not agg_func:
+                raise NotImplementedError(f"groupby.agg({agg_func!r}) is not on the B200 path")
+            if not isinstance(by, type(self)):
+                raise NotImplementedError("device groupby: key columns of the same frame, axis=0")
+            keys = set(by.columns) if drop else set()
+            by_func = {}
+            for col, fn in agg_func.items():
+                if isinstance(fn, (list, tuple)) and len(fn) == 1:
+                    fn = fn[0]
+                if not isinstance(fn, str) or fn not in self._DEVICE_AGGS or fn == "size":
+                    raise NotImplementedError(f"groupby.agg({{{col!r}: {fn!r}}}) is not on the B200 path")
+                if col not in self.columns or col in keys:
+                    raise KeyError(col)
+                by_func.setdefault(fn, []).append(col)
+            if any(isinstance(fn, (list, tuple)) for fn in agg_func.values()):
+                raise NotImplementedError("groupby.agg with lists of functions (two-level result columns)")
+            kw = dict(groupby_kwargs, as_index=True)
+            where, frames = {}, []
+            for fn, cols in by_func.items():
+                res = getattr(self.getitem_column_array(cols), f"groupby_{fn}")(
+                    by=by, axis=axis, groupby_kwargs=kw, agg_args=(), agg_kwargs={}, drop=False
+                )
+                frame = res._modin_frame
+                if frame._partitions.shape[1] != 1:
+                    raise NotImplementedError("dictionary aggregation over more than 32 columns per function")
+                for j, c in enumerate(cols):
+                    where[c] = (len(frames), j)
+                frames.append(frame)
+            if len({f._partitions.shape[0] for f in frames}) != 1:
+                raise NotImplementedError("per-function results are partitioned differently")
+            pc, rows = frames[0]._partition_mgr_cls._partition_class, []
+            for i in range(frames[0]._partitions.shape[0]):
+                blks = [f._partitions[i, 0].get() for f in frames]
+                if len({b.nrows for b in blks}) != 1:
+                    raise NotImplementedError("per-function results are partitioned differently")
+                nb = DeviceBlock([blks[where[c][0]].cols[where[c][1]] for c in agg_func], pandas.Index(list(agg_func)),
+                                 nrows=blks[0].nrows, index_cols=blks[0].index_cols, index_names=blks[0].index_names)  # fmt: skip
+                nb.keys_sorted_unique = True
+                nb.replicated = getattr(blks[0], "replicated", False)
+                rows.append([pc(nb)])
+            new_frame = type(frames[0])(np.array(rows, dtype=object), None, None, None, None)
+            if not groupby_kwargs.get("as_index", True):
+                from .query_compiler import group_keys_to_columns
+
+                new_frame = group_keys_to_columns(new_frame)  # alg/groupby.py:278-294
+            return self.__constructor__(new_frame)
+
         def fillna(self, **kwargs):
             """qc.py:2710-2813."""
             value = kwargs.get("value")

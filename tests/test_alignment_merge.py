@@ -251,6 +251,19 @@ def _as_index_and_parquet_checks(pdm, tmp_path, real_modin):
         got = pdm.DataFrame(pdf).groupby(["key", "k2"], as_index=False).sum()._to_pandas()
         want = pdf.groupby(["key", "k2"], as_index=False).sum()
         assert list(got.columns) == list(want.columns) and np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9)
+    # dictionary aggregations (qc._groupby_dict_reduce, qc.py:3876-3970): one device aggregation per distinct function
+    spec = {"c2": "mean", "c0": "sum", "c1": "max"}
+    for by, kw in (("key", {}), ("key", {"as_index": False}), (["key", "k2"], {})):
+        if not real_modin and kw:
+            continue
+        got = pdm.DataFrame(pdf).groupby(by, **kw).agg(spec)._to_pandas()
+        want = pdf.groupby(by, **kw).agg(spec)
+        assert list(got.columns) == list(want.columns) and got.index.equals(want.index), (by, kw)
+        assert np.allclose(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True), (by, kw)
+    fl = pdf[["key", "c0", "c1"]]  # min / max / sum aggregate float64 value columns
+    assert pdm.DataFrame(fl).groupby("key").agg("min")._to_pandas().equals(fl.groupby("key").agg("min"))
+    with pytest.raises(NotImplementedError):
+        pdm.DataFrame(pdf).groupby("key").agg({"c0": "median"})
     if real_modin:
         path = os.path.join(str(tmp_path), "frame.parquet")
         pdf.to_parquet(path)

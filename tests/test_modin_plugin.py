@@ -424,6 +424,7 @@ def _plugin_rank_job(rank, ws):
             out["gb_" + agg] = P(r)
             out["gb_local_" + agg] = sum(r._query_compiler._modin_frame.row_lengths)  # this rank's key range
             out["gb_job_" + agg] = len(r)  # len() of a frame is job-wide under torch.distributed
+        out["gb_dict"] = P(g.agg({"c2": "mean", "c0": "sum", "c3": "max"}))  # one device aggregation per function
         rng = np.random.RandomState(1)
         dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
         out["merge_left"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="left"))
@@ -481,6 +482,9 @@ def test_plugin_under_two_gloo_ranks():
             assert list(got.index) == list(want.index), agg
             assert np.allclose(np.asarray(got, dtype=np.float64).reshape(len(want), -1),
                                np.asarray(want, dtype=np.float64).reshape(len(want), -1), rtol=0, atol=1e-9, equal_nan=True), agg  # fmt: skip
+        wd_ = pdf.groupby("key").agg({"c2": "mean", "c0": "sum", "c3": "max"})
+        assert list(o["gb_dict"].columns) == list(wd_.columns) and list(o["gb_dict"].index) == list(wd_.index)
+        assert np.allclose(o["gb_dict"].to_numpy(), wd_.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
         wl = orc.broadcast_merge(pdf, dim, "key", "left", 4)
         assert list(o["merge_left"].columns) == list(wl.columns) and _same(o["merge_left"].to_numpy(), wl.to_numpy())
         assert _same(o["merge_inner"].to_numpy(), orc.broadcast_merge(pdf, dim, "key", "inner", 4).to_numpy())
