@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MB200_ABI_VERSION 2
+#define MB200_ABI_VERSION 3
 #define MB200_MAX_COLS 32 /* max columns per launch == Modin's MinColumnPartitionSize (envvars.py:1149-1190) */
 
 typedef void* mb200_stream_t;
@@ -311,6 +311,28 @@ int mb200_scan_i64(const int64_t* values, int64_t n, int64_t* out_offsets, int64
  * row ids in key-sorted order) or -1 for a miss.  The result columns are mb200_take gathers of the two. */
 int mb200_expand_rows(const int64_t* offsets, const int64_t* cnt, const int64_t* first, const int64_t* order,
                       int64_t n, int64_t* out_left, int64_t* out_right, mb200_stream_t stream);
+
+/* ---- Fold template: cumulative functions down the rows (alg/fold.py:32-95 -> PandasDataframe.fold, df.py:2357-2400;
+ * registrations qc.py:2429-2431 cummax / cummin / cumsum, and fillna(method="ffill"), qc.py:2809-2810).  pandas skips
+ * NaN: the running value ignores them, the output keeps NaN where the input has it (FFILL: the running value goes
+ * everywhere).  Two phases so that a frame sharded over ranks (or cut into several row partitions) needs one pass:
+ *   mb200_cum_partials  per 4096-row tile aggregates, scanned per column into `scratch`; totals_dev[j] (may be NULL)
+ *                       = the aggregate of the whole column j -- what the ranks exchange;
+ *   mb200_cum_carry     carry_dev[j] = totals of ranks 0 .. rank-1 combined in rank order, from the all-gathered
+ *                       totals [nranks][ncols];
+ *   mb200_cum_apply     out[j][i] = carry (+) rows 0 .. i of column j  (carry_dev may be NULL; out may alias in).
+ * in / out: HOST arrays of ncols device column pointers (8-byte aligned; any ncols, 32 per launch); dtype MB200_F64
+ * or MB200_I64 (FFILL: float64 only); scratch_bytes >= mb200_cum_scratch_bytes(ncols, nrows); the same scratch goes
+ * from partials to apply.  Sums re-associate (tile tree instead of pandas' sequential loop); max / min / ffill and
+ * int64 results are exact. */
+enum mb200_cum_op { MB200_CUM_SUM = 0, MB200_CUM_MAX = 1, MB200_CUM_MIN = 2, MB200_CUM_FFILL = 3 };
+size_t mb200_cum_scratch_bytes(int ncols, int64_t nrows);
+int mb200_cum_partials(int op, int dtype, int ncols, const void* const* in, int64_t nrows, void* scratch,
+                       size_t scratch_bytes, void* totals_dev, mb200_stream_t stream);
+int mb200_cum_carry(int op, int dtype, int ncols, const void* gathered_totals_dev, int rank, void* carry_dev,
+                    mb200_stream_t stream);
+int mb200_cum_apply(int op, int dtype, int ncols, const void* const* in, void* const* out, int64_t nrows,
+                    const void* scratch, const void* carry_dev, mb200_stream_t stream);
 
 /* Range-partitioning shuffle, split step (ShuffleSortFunctions.split_partitions, dfutils.py:355-475: np.digitize of
  * the key column against the sampled pivots): out_bins[i] = number of pivots <= values[i]; pivots_dev ascending,

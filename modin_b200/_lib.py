@@ -20,7 +20,7 @@ class B200Error(RuntimeError):
     """Raised when a libmodin_b200 call fails (message from mb200_last_error)."""
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums (keep in sync with include/modin_b200.h)
 F64, I64, U8 = 0, 1, 2
@@ -37,6 +37,7 @@ OP = {
 }  # fmt: skip
 PREDICATES = {"isna", "notna", "eq_s", "ne_s", "lt_s", "le_s", "gt_s", "ge_s", "eq", "ne", "lt", "le", "gt", "ge"}
 RED = {"sum": 0, "min": 1, "max": 2, "count": 3, "prod": 4, "ssd": 5}
+CUM = {"sum": 0, "max": 1, "min": 2, "ffill": 3}
 GB_SUM, GB_COUNT, GB_SIZE, GB_MIN, GB_MAX = 1, 2, 4, 8, 16
 
 _vp = C.c_void_p
@@ -107,6 +108,10 @@ _SIGNATURES = {
     "mb200_comm_alltoallv": (C.c_int, [_vp, _vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64), C.c_int, _vp]),
     "mb200_concat": (C.c_int, [C.c_int, _vpp, C.POINTER(C.c_int64), _vp, _vp]),
+    "mb200_cum_scratch_bytes": (C.c_size_t, [C.c_int, _i64]),
+    "mb200_cum_partials": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _i64, _vp, C.c_size_t, _vp, _vp]),
+    "mb200_cum_carry": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "mb200_cum_apply": (C.c_int, [C.c_int, C.c_int, C.c_int, _vpp, _vpp, _i64, _vp, _vp, _vp]),
     "mb200_iota_i64": (C.c_int, [_vp, _i64, _i64, _vp]),
     "mb200_fill_u64": (C.c_int, [_vp, _i64, C.c_uint64, _vp]),
     "mb200_sort_scratch_bytes": (C.c_size_t, [_i64]),

@@ -83,6 +83,38 @@ class TreeReduce(Operator):
         return caller
 
 
+class Reduce(Operator):
+    """alg/reduce.py:32-71: one function over FULL column partitions (``PandasDataframe.reduce``, df.py:2171-2205) --
+    for reductions that have no map / combine split (var, std: two dependent sweeps)."""
+
+    @classmethod
+    def register(cls, reduce_function, axis=None, shape_hint=None):
+        def caller(query_compiler, *args, **kwargs):
+            _axis = kwargs.get("axis") if axis is None else axis
+            return query_compiler.__constructor__(
+                query_compiler._modin_frame.reduce(cls.validate_axis(_axis), Bound(reduce_function, args, kwargs))
+            )
+
+        return caller
+
+
+class Fold(Operator):
+    """alg/fold.py:32-95: one shape-preserving function over FULL column partitions (``PandasDataframe.fold``,
+    df.py:2357-2400) -- cumulative functions and forward fill."""
+
+    @classmethod
+    def register(cls, fold_function, shape_preserved=False):
+        def caller(query_compiler, fold_axis=None, *args, new_index=None, new_columns=None, **kwargs):
+            return query_compiler.__constructor__(
+                query_compiler._modin_frame.fold(
+                    cls.validate_axis(fold_axis), Bound(fold_function, args, kwargs), new_index=new_index,
+                    new_columns=new_columns, shape_preserved=shape_preserved,
+                )  # fmt: skip
+            )
+
+        return caller
+
+
 class Binary(Operator):
     """alg/binary.py:296-460 (dtype inference is per device block, so `infer_dtypes` hints are
     accepted for signature parity and the result dtypes are read off the produced blocks)."""

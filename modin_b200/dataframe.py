@@ -194,6 +194,27 @@ class B200Dataframe:
         reduce_parts = self._partition_mgr_cls.map_axis_partitions(axis, map_parts, reduce_func, num_splits=1)
         return self._compute_tree_reduce_metadata(axis, reduce_parts, dtypes=dtypes)
 
+    def reduce(self, axis, function: Callable, dtypes=None):
+        """df.py:2171-2205: ``function`` over every FULL column partition -> 1 x W (the Reduce template).  The
+        device functor sees this rank's blocks of the axis and finishes with its own collective."""
+        if axis != 0:
+            raise NotImplementedError("reduce along axis=1 is not on the B200 path")
+        function = self._build_treereduce_func(axis, function)
+        new_parts = self._partition_mgr_cls.map_axis_partitions(axis, self._partitions, function, num_splits=1)
+        return self._compute_tree_reduce_metadata(axis, new_parts, dtypes=dtypes)
+
+    def fold(self, axis, func: Callable, new_index=None, new_columns=None, shape_preserved=False):
+        """df.py:2357-2400: ``func`` over every FULL column partition, partitioning kept (the Fold template)."""
+        if axis != 0:
+            raise NotImplementedError("fold along axis=1 is not on the B200 path")
+        row_lengths = column_widths = None
+        if shape_preserved:
+            new_index = self.copy_index_cache(copy_lengths=True) if new_index is None else new_index
+            new_columns = self.copy_columns_cache(copy_lengths=True) if new_columns is None else new_columns
+            row_lengths, column_widths = self._row_lengths_cache, self._column_widths_cache
+        new_parts = self._partition_mgr_cls.map_axis_partitions(axis, self._partitions, func, keep_partitioning=True)
+        return self.__constructor__(new_parts, new_index, new_columns, row_lengths, column_widths)
+
     # ---- Binary -----------------------------------------------------------------------------------
     def hstack(self, other: "B200Dataframe") -> "B200Dataframe":
         """Columns of ``self`` followed by the columns of ``other`` (same rows, same row labels): the column half of

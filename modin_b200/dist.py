@@ -218,6 +218,24 @@ def all_gather_small(values, extra: int | None = None):
     return out.reshape(world_size(), v.numel()).tolist()
 
 
+def all_gather_fixed(vec):
+    """all_gather of a device vector that has the SAME length on every rank -> one flat device vector, rank-major
+    (no host round trip: the carries of a cumulative function, W numbers per rank)."""
+    t = _torch()
+    v = vec.reshape(-1).contiguous()
+    out = t.empty(world_size() * v.numel(), dtype=v.dtype, device=v.device)
+    if not v.numel():
+        return out
+    nat = _native()
+    if nat is not None:
+        from . import _lib
+
+        _lib.check(nat[0].mb200_comm_allgather(nat[1], v.data_ptr(), out.data_ptr(), v.numel(), _code(v), _stream()))
+        return out
+    _dist().all_gather_into_tensor(out, v)
+    return out
+
+
 def exclusive_row_offset(nrows_local: int) -> int:
     """Global position of this rank's first row when every rank holds ``nrows_local`` rows in rank order."""
     if not is_distributed():

@@ -930,7 +930,105 @@ class DevSsdMap(DevFn):
         return _reduced_block(out, labels)
 
 
+class DevVar(DevFn):
+    """``pandas.DataFrame.var / std`` of one FULL column partition -> 1 x W block: the device body of the Reduce
+    template (alg/reduce.py:32-71 -> PandasDataframe.reduce, df.py:2171-2205; qc.py:1155-1156 registers
+    ``Reduce.register(pandas.DataFrame.std / var)``, i.e. pandas' two-pass nanops.nanvar over the gathered column).
+
+    Two sweeps over the block, nothing leaves the device: (sum, count) -> means -> sums of squared deviations from
+    those means (``mb200_reduce_columns_centered``) -> ``ssd / (count - ddof)``.  When the rows are sharded over
+    ranks the W sums / counts and the W sums of squares are all-reduced in between -- the Reduce template's
+    "gather the whole axis into one task" (axis_partition.py:445-452) becomes two packed W-vector collectives."""
+
+    def __init__(self, sqrt: bool = False):
+        self.sqrt = bool(sqrt)
+        self.op = "std" if sqrt else "var"
+
+    def __call__(self, block, *args, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
+        from . import dist
+
+        _check_block(block, f"DevVar({self.op})")
+        if axis not in (0, "index", None) or args:
+            raise NotImplementedError("row-wise var / std is not on the B200 path")
+        if not block.cols:
+            return _reduced_block([], block.columns)
+        spans = _spans_ranks(block)
+        t = ops.torch_mod()
+        W = len(block.cols)
+        cols = ops.cast_columns_f64(block.cols)
+        sums, cnts = ops.reduce_columns("sum", cols, skipna=bool(skipna), variant=ReduceVariant.get())
+        if spans:
+            dist.all_reduce_values(list(sums) + list(cnts), ["sum"] * (2 * W))
+        n = t.cat([c.reshape(1) for c in cnts]).to(t.float64)
+        centers = t.cat([v.reshape(1) for v in sums]) / n
+        ssd, _ = ops.reduce_columns("ssd", cols, skipna=bool(skipna), variant=ReduceVariant.get(), centers=centers)
+        if spans:
+            dist.all_reduce_values(list(ssd), ["sum"] * W)
+        d = n - float(ddof)
+        out = t.where(d > 0, t.cat([v.reshape(1) for v in ssd]) / d, t.full_like(d, float("nan")))
+        if self.sqrt:
+            out = t.sqrt(out)
+        res = _reduced_block([DeviceColumn(out[j : j + 1], np.float64) for j in range(W)], block.columns)
+        res.replicated = spans
+        return res
+
+    def run_distributed(self, block, *args, **kwargs):
+        return self(block, *args, **kwargs)
+
+
 # ------------------------------------------------------------------ label alignment (the reindexing half of _copartition)
+class DevCumulative(DevFn):
+    """``pandas.DataFrame.cumsum / cummax / cummin`` (qc.py:2429-2431) and ``DataFrame.ffill`` (``fillna(method=
+    "ffill")``, qc.py:2809-2810) of one full column partition: the device body of the Fold template
+    (alg/fold.py:32-95 -> PandasDataframe.fold, df.py:2357-2400).
+
+    The reference gathers every row block of the column partition into one pandas frame and runs the sequential
+    function over it.  Here the block is scanned by tiles (csrc/cum.cu: tile aggregates -> per-column scan of the
+    aggregates -> tiles with their prefix); when the rows are sharded over ranks each rank scans its own shard and the
+    rows before it arrive as ONE number per column: the ranks all-gather their column totals (W x 8 bytes each) and
+    combine those of the lower ranks in rank order into the carry of the second pass.  NaN are skipped like pandas
+    does (``skipna=True`` only); bool columns are refused (pandas returns object / int columns for them)."""
+
+    def __init__(self, op: str):
+        if op not in ("sum", "max", "min", "ffill"):
+            raise ValueError(op)
+        self.op = op
+
+    def __call__(self, block, *args, axis=0, skipna=True, **kwargs):
+        _check_block(block, f"DevCumulative({self.op})")
+        if axis not in (0, "index", None) or args:
+            raise NotImplementedError("row-wise (axis=1) cumulative functions are not on the B200 path")
+        if not skipna:
+            raise NotImplementedError("cumulative functions with skipna=False are not on the B200 path")
+        if self.op == "ffill" and (kwargs.get("limit") is not None or kwargs.get("limit_area") is not None):
+            raise NotImplementedError("ffill(limit=) is not on the B200 path")
+        return self._run(block, _spans_ranks(block))
+
+    def run_distributed(self, block, *args, **kwargs):
+        return self(block, *args, **kwargs)
+
+    def _run(self, block, distributed: bool):
+        from . import dist
+
+        if any(c.dtype == np.bool_ for c in block.cols):
+            raise NotImplementedError(f"cumulative {self.op} over bool columns is not on the B200 path")
+        # forward fill leaves integer columns as they are (they hold no NaN)
+        sel = [j for j, c in enumerate(block.cols) if not (self.op == "ffill" and c.dtype != np.float64)]
+        if not sel or (block.nrows == 0 and not distributed):
+            return block
+        cols = [block.cols[j] for j in sel]
+        state = ops.cum_partials(self.op, cols)
+        carries = None
+        if distributed:
+            gathered = [dist.all_gather_fixed(g[3]) for g in state.groups]
+            carries = ops.cum_carry(state, gathered, dist.rank())
+        outs = ops.cum_apply(state, cols, carries)
+        new_cols = list(block.cols)
+        for j, c in zip(sel, outs):
+            new_cols[j] = c
+        return block.with_cols(new_cols)
+
+
 def _labels_block(block, cols, labels: pandas.Index, replicated=False):
     """``cols`` under new row ``labels`` (RangeIndex -> O(1) metadata, numeric -> device index column, else host)."""
     n = len(labels)

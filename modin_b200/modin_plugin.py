@@ -92,7 +92,7 @@ def register(shims: bool | None = None):
 
     import modin.config as cfg
     from modin.config.envvars import Execution
-    from modin.core.dataframe.algebra import Binary, GroupByReduce, Map, TreeReduce
+    from modin.core.dataframe.algebra import Binary, Fold, GroupByReduce, Map, Reduce, TreeReduce
     from modin.core.dataframe.pandas.dataframe.dataframe import PandasDataframe
     from modin.core.dataframe.pandas.partitioning.partition_manager import PandasDataframePartitionManager
     from modin.core.execution.dispatching.factories import factories
@@ -215,7 +215,17 @@ def register(shims: bool | None = None):
 
             def _tree_reduce_func(df, *args, **kwargs):
                 if isinstance(df, DeviceBlock):
-                    result = func(df, *args, **kwargs)
+                    try:
+                        result = func(df, *args, **kwargs)
+                    except TypeError as e:
+                        # an unbound pandas method (Reduce.register(pandas.DataFrame.median), qc.py:1107) handed a
+                        # device block fails inside pandas with "super(type, obj): obj must be an instance ..."
+                        if "super(type, obj)" not in str(e):
+                            raise
+                        raise NotImplementedError(
+                            "this reduction has no device implementation in modin_b200 (unsupported operations raise "
+                            "instead of falling back to pandas)"
+                        ) from e
                     if isinstance(result, DeviceBlock):
                         return result
                     raise NotImplementedError(
@@ -435,8 +445,13 @@ def register(shims: bool | None = None):
         def fillna(self, **kwargs):
             """qc.py:2710-2813."""
             value = kwargs.get("value")
-            if kwargs.get("method") is not None or kwargs.get("limit") is not None:
-                raise NotImplementedError("fillna(method=/limit=) is a Fold in the reference; not on the B200 path")
+            if kwargs.get("method") is not None:  # qc.py:2809-2810: a Fold
+                if kwargs["method"] not in ("ffill", "pad") or value is not None or kwargs.get("limit") is not None \
+                        or kwargs.get("axis") not in (0, "index", None):  # fmt: skip
+                    raise NotImplementedError("fillna(method=) on the B200 path: forward fill down the rows, no limit=")
+                return self._ffill(0)
+            if kwargs.get("limit") is not None:
+                raise NotImplementedError("fillna(limit=) is not on the B200 path")
             if isinstance(value, type(self)):
                 return self.__constructor__(
                     # PandasDataframe.n_ary_op takes the dtypes themselves: the "copy" shorthand is only understood by
@@ -560,37 +575,19 @@ def register(shims: bool | None = None):
             )  # fmt: skip
             return self.getitem_array(self.__constructor__(mask, shape_hint="column"))
 
-        def _var(self, sqrt, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
-            """Two TreeReduce passes like the standalone query compiler: the means, then the sums of squared deviations
-            from them (``DevSsdMap``); ``ssd / (count - ddof)`` on the W reduced numbers is host arithmetic, and the
-            result goes back as the 1 x W frame the API layer expects from a reduction."""
-            if axis not in (0, "index", None):
-                raise NotImplementedError("row-wise var / std is not on the B200 path")
-            from modin.utils import MODIN_UNNAMED_SERIES_LABEL
+        # qc.py:1155-1156: std / var = Reduce.register(pandas.DataFrame.std / var) -- same template, device functor
+        # (two sweeps over each full column partition, two packed all-reduces when the rows span ranks)
+        var = Reduce.register(fx.DevVar(sqrt=False))
+        std = Reduce.register(fx.DevVar(sqrt=True))
+        # qc.py:2429-2431: cumulative functions through the Fold template (csrc/cum.cu); forward fill rides the same
+        # scan (fillna(method="ffill"), qc.py:2809-2810)
+        cumsum = Fold.register(fx.DevCumulative("sum"), shape_preserved=True)
+        cummax = Fold.register(fx.DevCumulative("max"), shape_preserved=True)
+        cummin = Fold.register(fx.DevCumulative("min"), shape_preserved=True)
+        _ffill = Fold.register(fx.DevCumulative("ffill"), shape_preserved=True)
 
-            if self._modin_frame._partitions.shape[1] != 1:
-                raise NotImplementedError("device var / std: frames of one column partition (up to 32 columns)")
-            mean = self.mean(axis=0, skipna=skipna, numeric_only=numeric_only).to_pandas()
-            centers = np.asarray(mean, dtype=np.float64).ravel()
-            W = len(centers)
-            parts_qc = TreeReduce.register(fx.DevSsdMap(centers), fx.DevReduce("sum", phase="reduce"))(
-                self, axis=0, skipna=skipna, numeric_only=numeric_only
-            )  # fmt: skip
-            # the reduced block is 1 x 2W (sums of squares, then counts) while the template's metadata says W columns,
-            # so it is read from the partition directly instead of through PandasDataframe.to_pandas' shape check
-            parts = np.asarray(parts_qc._modin_frame._partitions[0, 0].get().to_numpy(), dtype=np.float64).ravel()
-            ssd, cnt = parts[:W], parts[W:]
-            with np.errstate(all="ignore"):
-                out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
-                out = np.sqrt(out) if sqrt else out
-            host = pandas.DataFrame([out], columns=self.columns, index=[MODIN_UNNAMED_SERIES_LABEL], dtype=np.float64)
-            return self.__constructor__(type(self._modin_frame).from_pandas_replicated(host))
-
-        def var(self, axis=0, **kwargs):  # qc.py:1152 (a Reduce over pandas.DataFrame.var in the reference)
-            return self._var(False, axis, **kwargs)
-
-        def std(self, axis=0, **kwargs):  # qc.py:1153
-            return self._var(True, axis, **kwargs)
+        def cumprod(self, *args, **kwargs):
+            raise NotImplementedError("cumprod is not on the B200 path")
 
         def reset_index(self, **kwargs):
             """qc.py ``reset_index``: only ``drop=True`` over all levels -- a renumbering of the blocks' range starts

@@ -677,6 +677,69 @@ def concat_columns(pieces: Sequence[DeviceColumn]) -> DeviceColumn:
     return out
 
 
+class CumState:
+    """What ``cum_partials`` leaves for ``cum_apply``: per dtype group the scanned tile aggregates (scratch) and the
+    column totals (device, one per column of the group)."""
+
+    __slots__ = ("op", "n", "groups")
+
+    def __init__(self, op, n):
+        self.op, self.n, self.groups = op, n, []  # (code, column positions, scratch tensor, totals tensor)
+
+
+def cum_partials(op: str, cols: Sequence[DeviceColumn]) -> CumState:
+    """Phase 1 of a cumulative function (``mb200_cum_partials``): per-tile aggregates of every column, scanned per
+    column; ``state.groups[k][3]`` holds the column totals -- what ranks / row partitions exchange."""
+    lib = _lib.load()
+    t = torch_mod()
+    n = len(cols[0]) if cols else 0
+    st = CumState(op, n)
+    by_code = {}
+    for j, c in enumerate(cols):
+        if c.code == _lib.U8 or (op == "ffill" and c.code != _lib.F64):
+            raise TypeError(f"cumulative {op} over {c.dtype} columns is not on the B200 path")
+        by_code.setdefault(c.code, []).append(j)
+    for code, idxs in by_code.items():
+        nbytes = lib.mb200_cum_scratch_bytes(len(idxs), n)
+        scratch = t.empty(nbytes, dtype=t.uint8, device=current_device())
+        totals = t.empty(len(idxs), dtype=t.float64 if code == _lib.F64 else t.int64, device=current_device())
+        with _timed("cum_partials"):
+            _lib.check(lib.mb200_cum_partials(_lib.CUM[op], code, len(idxs), _lib.ptr_array([cols[j].ptr for j in idxs]), n,
+                                              scratch.data_ptr(), nbytes, totals.data_ptr(), current_stream()))  # fmt: skip
+        st.groups.append((code, idxs, scratch, totals))
+    return st
+
+
+def cum_carry(state: CumState, gathered: Sequence, rank: int) -> list:
+    """Carry of this rank per dtype group from the all-gathered totals (``[nranks * ncols]`` device vectors, rank-major):
+    the totals of ranks ``0 .. rank-1`` combined in rank order (``mb200_cum_carry``)."""
+    lib = _lib.load()
+    t = torch_mod()
+    out = []
+    for (code, idxs, _s, totals), g in zip(state.groups, gathered):
+        carry = t.empty_like(totals)
+        _lib.check(lib.mb200_cum_carry(_lib.CUM[state.op], code, len(idxs), g.data_ptr(), int(rank), carry.data_ptr(),
+                                       current_stream()))  # fmt: skip
+        out.append(carry)
+    return out
+
+
+def cum_apply(state: CumState, cols: Sequence[DeviceColumn], carries=None) -> list:
+    """Phase 2 (``mb200_cum_apply``): ``out[j][i] = carry (+) rows 0 .. i`` of column j, into fresh columns."""
+    lib = _lib.load()
+    outs: list = [None] * len(cols)
+    for k, (code, idxs, scratch, _totals) in enumerate(state.groups):
+        fresh = [DeviceColumn.empty(state.n, cols[j].dtype) for j in idxs]
+        carry = carries[k] if carries is not None else None
+        with _timed("cum_apply"):
+            _lib.check(lib.mb200_cum_apply(_lib.CUM[state.op], code, len(idxs), _lib.ptr_array([cols[j].ptr for j in idxs]),
+                                           _lib.ptr_array([c.ptr for c in fresh]), state.n, scratch.data_ptr(),
+                                           carry.data_ptr() if carry is not None else None, current_stream()))  # fmt: skip
+        for j, c in zip(idxs, fresh):
+            outs[j] = c
+    return outs
+
+
 def run_starts(sorted_keys: DeviceColumn):
     """Runs of equal values in a SORTED int64 column: ``(start positions, value of each run)`` as small host arrays
     (``mb200_run_heads`` + compaction + gather; meant for few runs -- bin ids, not row keys)."""

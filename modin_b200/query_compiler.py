@@ -17,13 +17,14 @@ from __future__ import annotations
 import numpy as np
 import pandas
 
-from .algebra import Binary, GroupByReduce, Map, TreeReduce
+from .algebra import Binary, Fold, GroupByReduce, Map, Reduce, TreeReduce
 from .dataframe import B200Dataframe
 from .functors import (
     DevAstype,
     DevBinary,
     DevBoolReduce,
     DevClip,
+    DevCumulative,
     DevFillna,
     DevGroupbyMap,
     DevGroupbyReduce,
@@ -34,7 +35,7 @@ from .functors import (
     DevMerge,
     DevReduce,
     DevRound,
-    DevSsdMap,
+    DevVar,
 )
 from .partitioning import Bound
 
@@ -201,9 +202,12 @@ class B200QueryCompiler:
     def fillna(self, **kwargs):
         """qc.py:2710-2813: scalar / dict values are a Map; ``method``/``limit`` would be a Fold."""
         value = kwargs.get("value")
+        if kwargs.get("method") is not None:
+            if kwargs["method"] not in ("ffill", "pad") or value is not None or kwargs.get("limit") is not None \
+                    or kwargs.get("axis") not in (0, "index", None):  # fmt: skip
+                raise NotImplementedError("fillna(method=) on the B200 path: forward fill down the rows, no limit=")
+            return self._ffill(0)
         if isinstance(value, type(self)):
-            if kwargs.get("method") is not None:
-                raise NotImplementedError("fillna(method=) is not on the B200 path")
             return self.__constructor__(
                 self._modin_frame.n_ary_op(Bound(DevBinary("fillna")), [value._modin_frame], join_type="left")
             )
@@ -242,27 +246,15 @@ class B200QueryCompiler:
     all = TreeReduce.register(DevBoolReduce("all"), DevBoolReduce("all", phase="reduce"),
                               compute_dtypes=lambda *a, **k: np.dtype("bool"))  # qc.py:987
 
-    # ---- var / std (qc.py:1152-1153: Reduce.register(pandas.DataFrame.var / std), pandas' two-pass nanvar) ----
+    # ---- Reduce (qc.py:1155-1156: std / var = Reduce.register(pandas.DataFrame.std / var)) ---------------------------
+    _var_frame = Reduce.register(DevVar(sqrt=False))
+    _std_frame = Reduce.register(DevVar(sqrt=True))
+
     def _var(self, axis=0, skipna=True, ddof=1, numeric_only=False, sqrt=False, **kwargs):
-        """1 x W frame of variances (standard deviations when ``sqrt``): pass 1 = ``mean`` (sum, count), pass 2 =
-        sum of squared deviations from those means (``DevSsdMap``), both TreeReduce-shaped and all-reduced across
-        GPUs; the final ``ssd / (count - ddof)`` on W numbers is host arithmetic on the reduced frame."""
-        if axis not in (0, "index", None):
-            raise NotImplementedError("row-wise var / std is not on the B200 path")
-        mean = self.mean(axis=0, skipna=skipna, numeric_only=numeric_only).to_pandas()
-        # centres by column label: a frame wider than one column partition gives every partition the same functor
-        parts_qc = TreeReduce.register(DevSsdMap(mean.iloc[0].astype(np.float64)), DevReduce("sum", phase="reduce"))(
-            self, axis=0, skipna=skipna, numeric_only=numeric_only
-        )  # fmt: skip
-        # every column partition contributes its own ("ssd", column)... ("count", column)... run: split by label
-        row = parts_qc.to_pandas().iloc[0]
-        ssd = row["ssd"].reindex(mean.columns).to_numpy(dtype=np.float64)
-        cnt = row["count"].reindex(mean.columns).to_numpy(dtype=np.float64)
-        with np.errstate(all="ignore"):
-            out = np.where(cnt - ddof > 0, ssd / (cnt - ddof), np.nan)
-            if sqrt:
-                out = np.sqrt(out)
-        return pandas.Series(out, index=mean.columns, dtype="float64")
+        """The W variances (standard deviations when ``sqrt``) as a host Series: the API layer of the mirror takes
+        reductions of this kind as W host numbers (identical on every rank)."""
+        qc = (self._std_frame if sqrt else self._var_frame)(axis=axis, skipna=skipna, ddof=ddof, numeric_only=numeric_only)
+        return pandas.Series(qc.to_pandas().iloc[0].to_numpy(dtype=np.float64), index=self.columns, dtype="float64")
 
     def var(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
         """Reduced result as a host ``pandas.Series`` (W numbers; identical on every rank)."""
@@ -270,6 +262,12 @@ class B200QueryCompiler:
 
     def std(self, axis=0, skipna=True, ddof=1, numeric_only=False, **kwargs):
         return self._var(axis, skipna, ddof, numeric_only, sqrt=True)
+
+    # ---- Fold (qc.py:2429-2431; forward fill is fillna(method="ffill"), qc.py:2809-2810) ----------------------------
+    cumsum = Fold.register(DevCumulative("sum"), shape_preserved=True)
+    cummax = Fold.register(DevCumulative("max"), shape_preserved=True)
+    cummin = Fold.register(DevCumulative("min"), shape_preserved=True)
+    _ffill = Fold.register(DevCumulative("ffill"), shape_preserved=True)
 
     # ---- GroupByReduce (qc.py:3741-3748; impl table storage_formats/pandas/groupby.py:237-248) ------
     groupby_sum = GroupByReduce.register(DevGroupbyMap("sum"), DevGroupbyReduce("sum"))

@@ -11,9 +11,13 @@ reference does (the arithmetic itself is the third-party dependency ``pandas`` p
 the reference code it follows.  Parity is PINNED: ``tests/golden/*.npz`` were produced by running
 the unmodified reference (PandasOnPython engine, NPartitions=4, five pandas-3 import shims, see
 ``tests/golden/make_golden.py``) in the build container, and ``tests/test_oracle.py`` checks this
-restatement against them bit for bit.  ONE EXCEPTION -- ``sort_values`` is PARITY UNPINNED: under pandas 3 the
-reference's range-partitioning sort returns an empty frame (even for 40 rows), so no golden vectors could be
-produced; that restatement is checked against pandas' stable sort instead.
+restatement against them bit for bit.  ``sort_values`` is pinned since round 2 (tests/golden/ext5_sort_fold.npz):
+under pandas 3 the reference's range-partitioning split finds no group (``grp.get_group(scalar)`` after
+``groupby([codes])``, dataframe/utils.py:415-420 -- pandas < 2.4 semantics), so the generator restores exactly that
+one behaviour (make_golden.py) and the reference sorts again.  Rows with DISTINCT keys (and NaN keys, which keep
+their order) are pinned row for row; rows with EQUAL keys have no defined order in the reference (unseeded pivot
+sampling + pandas' default unstable kind per bin), so tie-heavy keys are pinned as "same keys, same rows per run of
+equal keys" and the restatement / device path fix the order to the stable one.
 """
 
 from __future__ import annotations
@@ -285,6 +289,31 @@ def df_var(df, npartitions: int, ddof: int = 1, skipna: bool = True):
 
 def df_std(df, npartitions: int, ddof: int = 1, skipna: bool = True):
     return reduce_full_axis(df, lambda x: x.std(axis=0, ddof=ddof, skipna=skipna), npartitions)
+
+
+def fold_full_axis(df, func: Callable, npartitions: int) -> pandas.DataFrame:
+    """Fold.register(func, shape_preserved=True) (alg/fold.py:32-95 -> PandasDataframe.fold, dataframe.py:2357-2400:
+    ``map_axis_partitions(axis, partitions, func, keep_partitioning=True)``): the function runs on whole COLUMN
+    partitions (every row block of the column partition concatenated, axis_partition.py:445-452) and the result is
+    cut back into the original row lengths -- only the column grid matters for the values."""
+    grid = split_into_partitions(df, npartitions)
+    ncol_parts = len(grid[0]) if grid else 0
+    outs = [func(pandas.concat([row[j] for row in grid], axis=0)) for j in range(ncol_parts)]
+    return pandas.concat(outs, axis=1) if outs else df.copy()
+
+
+def df_cumulative(df, which: str, npartitions: int, skipna: bool = True) -> pandas.DataFrame:
+    """qc.cumsum / cummax / cummin = Fold.register(pandas.DataFrame.cumsum / ..., shape_preserved=True)
+    (query_compiler.py:2429-2431)."""
+    if which not in ("cumsum", "cummax", "cummin"):
+        raise ValueError(which)
+    return fold_full_axis(df, lambda x: getattr(x, which)(axis=0, skipna=skipna), npartitions)
+
+
+def df_ffill(df, npartitions: int) -> pandas.DataFrame:
+    """qc.fillna(method="ffill") (query_compiler.py:2809-2810: ``self._modin_frame.fold(axis, fillna)``; the pinned
+    pandas spells it ``fillna(method="ffill")``, pandas 3 ``ffill()``)."""
+    return fold_full_axis(df, lambda x: x.ffill(axis=0), npartitions)
 
 
 # ------------------------------------------------------------------ sort_values (SURVEY 8f-2: range-partition shuffle)

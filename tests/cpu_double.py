@@ -362,6 +362,80 @@ def concat_columns(pieces):
     return pieces[0] if len(pieces) == 1 else _col(np.concatenate([_np(p) for p in pieces]))
 
 
+_CUM_ID = {"sum": 0.0, "max": -np.inf, "min": np.inf, "ffill": np.nan}
+
+
+def _cum_comb(op, a, b):
+    if op == "sum":
+        return a + b
+    if op == "max":
+        return np.maximum(a, b)
+    if op == "min":
+        return np.minimum(a, b)
+    return np.where(np.isnan(b), a, b)
+
+
+def _cum_ident(op, dtype):
+    if dtype == np.float64:
+        return np.float64(_CUM_ID[op])
+    return np.int64({"sum": 0, "max": np.iinfo(np.int64).min, "min": np.iinfo(np.int64).max}[op])
+
+
+def cum_partials(op, cols):
+    n = len(cols[0]) if cols else 0
+    st = ops.CumState(op, n)
+    by_code = {}
+    for j, c in enumerate(cols):
+        if c.dtype == np.bool_ or (op == "ffill" and c.dtype != np.float64):
+            raise TypeError(f"cumulative {op} over {c.dtype} columns is not on the B200 path")
+        by_code.setdefault(c.code, []).append(j)
+    for code, idxs in by_code.items():
+        tot = []
+        for j in idxs:
+            x = _np(cols[j])
+            v = x[~np.isnan(x)] if x.dtype == np.float64 else x
+            ident = _cum_ident(op, x.dtype)
+            with np.errstate(all="ignore"):
+                tot.append(ident if len(v) == 0 else {"sum": v.sum, "max": v.max, "min": v.min, "ffill": lambda: v[-1]}[op]())
+        st.groups.append((code, idxs, None, torch.from_numpy(np.asarray(tot, dtype=_np(cols[idxs[0]]).dtype))))
+    return st
+
+
+def cum_carry(state, gathered, rank):
+    out = []
+    for (code, idxs, _s, totals), g in zip(state.groups, gathered):
+        g = g.numpy().reshape(-1, len(idxs))
+        run = np.full(len(idxs), _cum_ident(state.op, g.dtype), dtype=g.dtype)
+        with np.errstate(all="ignore"):
+            for r in range(rank):
+                run = _cum_comb(state.op, run, g[r]).astype(g.dtype)
+        out.append(torch.from_numpy(run))
+    return out
+
+
+def cum_apply(state, cols, carries=None):
+    outs = [None] * len(cols)
+    op = state.op
+    for k, (code, idxs, _s, _t) in enumerate(state.groups):
+        for pos, j in enumerate(idxs):
+            x = _np(cols[j])
+            ident = _cum_ident(op, x.dtype)
+            carry = carries[k].numpy()[pos] if carries is not None else ident
+            nan = np.isnan(x) if x.dtype == np.float64 else np.zeros(len(x), dtype=bool)
+            with np.errstate(all="ignore"):
+                if op == "ffill":
+                    r = pandas.Series(x).ffill().to_numpy()
+                    r = np.where(np.isnan(r), carry, r)
+                else:
+                    v = np.where(nan, ident, x)
+                    acc = {"sum": np.cumsum, "max": np.maximum.accumulate, "min": np.minimum.accumulate}[op](v)
+                    r = _cum_comb(op, np.full(len(x), carry, dtype=x.dtype), acc).astype(x.dtype)
+                    if x.dtype == np.float64:
+                        r = np.where(nan, np.nan, r)
+            outs[j] = _col(r)
+    return outs
+
+
 def run_starts(sorted_keys):
     b = _np(sorted_keys)
     if len(b) == 0:
@@ -391,11 +465,12 @@ def installed():
         "current_device": block.current_device,
         **{n: getattr(ops, n) for n in ("map_columns", "reduce_columns", "hash_aggregate", "JoinTable", "take_columns",
                                         "compact_hits", "cast_columns_f64", "cast_columns_i64", "gen_f64", "gen_i64", "GroupTable",
-                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches", "digitize", "run_starts", "concat_columns")},
+                                        "key_range_device", "sort_pairs", "iota", "full_column", "expand_matches", "digitize", "run_starts", "concat_columns", "cum_partials", "cum_carry", "cum_apply")},
     }  # fmt: skip
     ops.GroupTable, ops.key_range_device, ops.sort_pairs = GroupTable, key_range_device, sort_pairs
     ops.iota, ops.full_column, ops.expand_matches, ops.digitize = iota, full_column, expand_matches, digitize
     ops.run_starts, ops.concat_columns = run_starts, concat_columns
+    ops.cum_partials, ops.cum_carry, ops.cum_apply = cum_partials, cum_carry, cum_apply
     ops.cast_columns_i64 = cast_columns_i64
     block.current_device = lambda: torch.device("cpu")
     ops.current_device = block.current_device

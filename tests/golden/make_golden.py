@@ -49,7 +49,28 @@ def apply_pandas3_shims():
         g = cls.groupby
         cls.groupby = functools.wraps(g)(lambda self, *a, axis=0, _g=g, **k: _g(self, *a, **k))
         f = cls.fillna
-        cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: _f(self, *a, **k))
+        cls.fillna = functools.wraps(f)(lambda self, *a, method=None, downcast=None, _f=f, **k: (
+            (self.ffill(**{kk: v for kk, v in k.items() if kk in ("axis", "limit", "inplace")}) if method in ("ffill", "pad")
+             else self.bfill(**{kk: v for kk, v in k.items() if kk in ("axis", "limit", "inplace")}))
+            if method is not None else _f(self, *a, **k)))
+    # pandas < 2.4 (the reference's pin, setup.py:49): a SCALAR names a group of a length-1 list of keys.  pandas 3
+    # wants a 1-tuple, so the reference's range-partitioning split (dataframe/utils.py:415-420 ``grp.get_group(key)``
+    # after ``groupby([codes])``) finds no group at all and every sort returns an empty frame.
+    from pandas.core.groupby.groupby import GroupBy
+
+    if not getattr(GroupBy.get_group, "_mb200_shim", False):
+        _gg = GroupBy.get_group
+
+        def get_group(self, name, *a, **k):
+            try:
+                return _gg(self, name, *a, **k)
+            except KeyError:
+                if not isinstance(name, tuple) and len(self._grouper.groupings) == 1:
+                    return _gg(self, (name,), *a, **k)
+                raise
+
+        get_group._mb200_shim = True
+        GroupBy.get_group = get_group
 
 
 def third_batch_frames(synth, n, nb, nan, G):
@@ -83,6 +104,19 @@ def fourth_batch_frames(synth):
     dim["d1"] = np.arange(len(dim), dtype=np.int64) * 3 + 1
     dim_u = dim.drop_duplicates("key").rename(columns={"key": "k"})
     return A, B, Bp, fact, dim, dim_u
+
+
+def fifth_batch_frame(synth):
+    """Input of the ``ext5`` cases (sort_values, Fold, Reduce; shared with the tests): float64 columns with NaN --
+    also at the very top, in a long run, and a column that is NaN from row 1500 on --, an int64 key with many ties and
+    an int64 column without ties."""
+    n = 2003
+    f = synth.host_frame(n, 4, seed=61, nan_per_64k=3000, key_modulus=23)
+    f.iloc[0:4, f.columns.get_loc("c1")] = np.nan
+    f.iloc[700:760, f.columns.get_loc("c2")] = np.nan
+    f.iloc[1500:, f.columns.get_loc("c3")] = np.nan
+    f["u"] = np.random.RandomState(3).permutation(n).astype(np.int64) * 7 - 5000
+    return f
 
 
 def main():
@@ -250,6 +284,33 @@ def main():
     r = P(mf.merge(mpd.DataFrame(dim_u), left_on="key", right_on="k", how="left"))
     arrays["lr_on"], arrays["lr_on_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
     save("ext4_align_m2m", meta=np.array([2003, 1801]), **arrays)
+
+    # ---- fifth batch: sort_values through the reference's range-partitioning shuffle (dataframe.py:2741-2791 ->
+    # 2565-2739), the Fold registrations (qc.py:2429-2431, 2809-2810) and the Reduce-registered var / std
+    # (qc.py:1155-1156).  The reference samples its pivots with an UNSEEDED ``df.sample`` and sorts every bin with
+    # pandas' default (unstable) kind, so the order of rows with EQUAL keys changes from run to run: tie-free keys
+    # are stored row for row, the tie-heavy key as (sorted keys, labels) to be compared per run of equal keys.
+    F = fifth_batch_frame(synth)
+    mF = mpd.DataFrame(F)
+    arrays = {}
+    for by in ("c0", "c2", "u"):
+        for asc in (True, False):
+            r = P(mF.sort_values(by, ascending=asc))
+            tag = f"sort_{by}_{'asc' if asc else 'desc'}"
+            arrays[tag + "_index"], arrays[tag] = r.index.to_numpy(), r.to_numpy(dtype=np.float64)
+    for asc in (True, False):
+        r = P(mF.sort_values("key", ascending=asc))
+        tag = f"sort_key_{'asc' if asc else 'desc'}"
+        arrays[tag + "_index"], arrays[tag + "_keys"] = r.index.to_numpy(), r["key"].to_numpy()
+    fl = ["c0", "c1", "c2", "c3"]
+    for name in ("cumsum", "cummax", "cummin", "ffill"):
+        arrays[name] = P(getattr(mF[fl], name)()).to_numpy()
+    arrays["cumsum_int"] = P(mF[["key", "u"]].cumsum()).to_numpy()
+    arrays["cummax_int"] = P(mF[["key", "u"]].cummax()).to_numpy()
+    for name in ("var", "std"):
+        for ddof in (1, 0):
+            arrays[f"{name}_ddof{ddof}"] = P(getattr(mF[fl], name)(ddof=ddof)).to_numpy()
+    save("ext5_sort_fold", meta=np.array([2003]), **arrays)
 
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):

@@ -216,7 +216,19 @@ def _late_scenarios(mpd, ns):
     # a query-compiler method the plug-in does not override reaches the blocks with Modin's pandas lambda: refused
     # with a message that says so (it used to be a bare AttributeError on the block)
     with pytest.raises(NotImplementedError, match="no device implementation"):
-        P(mdf[fcols].cumsum())
+        P(mdf[fcols].median())
+    # Fold template (alg/fold.py): cumulative functions and forward fill down the rows, NaN skipped like pandas does
+    got, want = P(mdf[fcols].cumsum()), pdf[fcols].cumsum()
+    assert got.index.equals(want.index) and np.allclose(got.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+    assert np.array_equal(np.isnan(got.to_numpy()), np.isnan(want.to_numpy()))
+    assert P(mdf[fcols].cummax()).equals(pdf[fcols].cummax()) and P(mdf[fcols].cummin()).equals(pdf[fcols].cummin())
+    assert P(mdf[["key", "k2"]].cumsum()).equals(pdf[["key", "k2"]].cumsum())  # int64: exact
+    assert P(mdf["c1"].cummax()).equals(pdf["c1"].cummax())
+    assert P(mdf.ffill()).equals(pdf.ffill())
+    with pytest.raises(NotImplementedError):
+        mdf[fcols].cumsum(skipna=False)
+    with pytest.raises(NotImplementedError):
+        mdf.ffill(limit=2)
 
 
 def test_odd_shapes_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
@@ -290,9 +302,11 @@ def test_odd_shapes_under_real_modin_cpu_double(modin_b200_execution, cpu_device
         if not ok:
             bad[name] = (got.shape, want.shape, list(got.index)[:3], list(want.index)[:3])
     assert not bad, bad
-    for refused in (lambda: dw.drop_duplicates(subset=["key"]), lambda: dw[fcols].var()):  # need one column partition
-        with pytest.raises(NotImplementedError, match="one column partition"):
-            refused()
+    with pytest.raises(NotImplementedError, match="one column partition"):
+        dw.drop_duplicates(subset=["key"])
+    # var / std are a device Reduce per column partition, so a frame wider than one partition works
+    gv, wv = dw[fcols].var()._to_pandas(), dw[fcols]._to_pandas().var()
+    assert list(gv.index) == list(wv.index) and np.allclose(gv.to_numpy(), wv.to_numpy(), rtol=1e-12, atol=0)
     # NOT covered, and not this package's doing: reductions / filters / groupby of an EMPTY frame make Modin's API
     # layer default to pandas, and that path builds ``pandas.Series(..., fastpath=...)`` (modin/pandas/series.py:166),
     # a keyword pandas 3 removed (the reference pins pandas < 2.4)
@@ -424,6 +438,15 @@ def _plugin_rank_job(rank, ws):
             out["gb_" + agg] = P(r)
             out["gb_local_" + agg] = sum(r._query_compiler._modin_frame.row_lengths)  # this rank's key range
             out["gb_job_" + agg] = len(r)  # len() of a frame is job-wide under torch.distributed
+        for name in ("cumsum", "cummax", "cummin", "ffill"):  # Fold: each rank scans its shard, carries cross the ranks
+            out[name] = P(getattr(mdf, name)())
+        edge = vals.copy()  # NaN runs across the shard boundary (row 1001) and at the very top
+        edge.iloc[995:1010, 0] = np.nan
+        edge.iloc[0:5, 1] = np.nan
+        edge.iloc[1001:, 2] = np.nan  # a shard with nothing valid in one column
+        medge = mpd.DataFrame(edge)
+        for name in ("cumsum", "cummax", "ffill"):
+            out["edge_" + name] = P(getattr(medge, name)())
         out["gb_dict"] = P(g.agg({"c2": "mean", "c0": "sum", "c3": "max"}))  # one device aggregation per function
         rng = np.random.RandomState(1)
         dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
@@ -482,6 +505,16 @@ def test_plugin_under_two_gloo_ranks():
             assert list(got.index) == list(want.index), agg
             assert np.allclose(np.asarray(got, dtype=np.float64).reshape(len(want), -1),
                                np.asarray(want, dtype=np.float64).reshape(len(want), -1), rtol=0, atol=1e-9, equal_nan=True), agg  # fmt: skip
+        assert np.allclose(o["cumsum"].to_numpy(), vals.cumsum().to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+        assert list(o["cumsum"].index) == list(vals.index)
+        for name in ("cummax", "cummin", "ffill"):
+            assert o[name].equals(getattr(vals, name)()), name
+        edge = vals.copy()
+        edge.iloc[995:1010, 0] = np.nan
+        edge.iloc[0:5, 1] = np.nan
+        edge.iloc[1001:, 2] = np.nan
+        assert np.allclose(o["edge_cumsum"].to_numpy(), edge.cumsum().to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+        assert o["edge_cummax"].equals(edge.cummax()) and o["edge_ffill"].equals(edge.ffill())
         wd_ = pdf.groupby("key").agg({"c2": "mean", "c0": "sum", "c3": "max"})
         assert list(o["gb_dict"].columns) == list(wd_.columns) and list(o["gb_dict"].index) == list(wd_.index)
         assert np.allclose(o["gb_dict"].to_numpy(), wd_.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)

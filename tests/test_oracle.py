@@ -289,3 +289,42 @@ def test_fourth_batch_against_reference(golden_dir):
     r = orc.broadcast_merge_general(fact, dim_u, "left", NP, left_on="key", right_on="k")
     assert list(r.columns) == list(z["lr_on_cols"])
     assert_bit_equal(r.to_numpy(dtype=np.float64), z["lr_on"], "merge left_on / right_on")
+
+
+def _same_rows_per_key_run(keys, labels, want_keys, want_labels):
+    """Tie-heavy sort: identical key column, and every run of equal keys holds the same set of row labels."""
+    if not np.array_equal(keys, want_keys):
+        return False
+    cuts = np.nonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))[0].tolist() + [len(keys)]
+    return all(sorted(labels[a:b]) == sorted(want_labels[a:b]) for a, b in zip(cuts[:-1], cuts[1:]))
+
+
+def test_fifth_batch_against_reference(golden_dir):
+    """sort_values (the reference's range-partitioning sort), the Fold registrations and Reduce-registered var / std:
+    restatements pinned to the unmodified reference (tests/golden/ext5_sort_fold.npz)."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from make_golden import fifth_batch_frame
+
+    z = dict(np.load(os.path.join(golden_dir, "ext5_sort_fold.npz"), allow_pickle=False))
+    F = fifth_batch_frame(synth)
+    for by in ("c0", "c2", "u"):  # distinct keys (NaN keys keep their order): row for row
+        for asc in (True, False):
+            tag = f"sort_{by}_{'asc' if asc else 'desc'}"
+            r = orc.sort_values(F, by, asc, NP)
+            assert_bit_equal(r.index.to_numpy(), z[tag + "_index"], tag + " labels")
+            assert_bit_equal(r.to_numpy(dtype=np.float64), z[tag], tag)
+    for asc in (True, False):  # 23 distinct keys over 2003 rows: the reference's order inside a run is not defined
+        tag = f"sort_key_{'asc' if asc else 'desc'}"
+        r = orc.sort_values(F, "key", asc, NP)
+        assert _same_rows_per_key_run(r["key"].to_numpy(), r.index.to_numpy(), z[tag + "_keys"], z[tag + "_index"]), tag
+    fl = ["c0", "c1", "c2", "c3"]
+    for name in ("cumsum", "cummax", "cummin"):
+        assert_bit_equal(orc.df_cumulative(F[fl], name, NP).to_numpy(), z[name], name)
+    assert_bit_equal(orc.df_ffill(F[fl], NP).to_numpy(), z["ffill"], "ffill")
+    assert_bit_equal(orc.df_cumulative(F[["key", "u"]], "cumsum", NP).to_numpy(), z["cumsum_int"], "cumsum int64")
+    assert_bit_equal(orc.df_cumulative(F[["key", "u"]], "cummax", NP).to_numpy(), z["cummax_int"], "cummax int64")
+    for ddof in (1, 0):
+        assert_bit_equal(orc.df_var(F[fl], NP, ddof=ddof).to_numpy(), z[f"var_ddof{ddof}"], f"var ddof={ddof}")
+        assert_bit_equal(orc.df_std(F[fl], NP, ddof=ddof).to_numpy(), z[f"std_ddof{ddof}"], f"std ddof={ddof}")
