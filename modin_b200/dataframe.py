@@ -603,6 +603,25 @@ class B200Dataframe:
             index = pandas.RangeIndex(first.range_start, first.range_start + sum(b.nrows for b in blocks))
         return cls(parts, index, first.columns, [b.nrows for b in blocks], [len(first.cols)], dtypes=first.dtypes)
 
+    def __dataframe__(self, nan_as_null: bool = False, allow_copy: bool = True):
+        """df.py:4803-4824: the interchange-protocol view of this frame -- device buffers, one chunk per row
+        partition (``modin_b200.interchange``)."""
+        from .block import concat_cols
+        from .interchange import B200ProtocolDataframe
+
+        blocks = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
+        return B200ProtocolDataframe(blocks, self.index, nan_as_null, allow_copy)
+
+    @classmethod
+    def from_interchange_dataframe(cls, df):
+        """df.py:4826-4867 -- without the detour through pandas: CUDA buffers are adopted through DLPack, host
+        buffers are copied H2D."""
+        if type(df) is cls:
+            return df
+        from .interchange import blocks_from_dataframe
+
+        return cls.from_blocks(blocks_from_dataframe(df))
+
     def to_pandas(self) -> pandas.DataFrame:
         """df.py:4691-4722."""
         df = self._partition_mgr_cls.to_pandas(self._partitions)

@@ -198,6 +198,32 @@ def register(shims: bool | None = None):
                 df = pandas.DataFrame(columns=self.columns, index=df.index)
             return df
 
+        def __dataframe__(self, nan_as_null: bool = False, allow_copy: bool = True):
+            """df.py:4803-4824, over the device blocks (``modin_b200.interchange``): buffers stay in HBM and say so
+            (``__dlpack_device__`` = CUDA), one chunk per row partition."""
+            from .block import concat_cols
+            from .interchange import B200ProtocolDataframe
+
+            self._propagate_index_objs(axis=None)
+            blocks = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
+            return B200ProtocolDataframe(blocks, self.index, nan_as_null, allow_copy)
+
+        @classmethod
+        def from_interchange_dataframe(cls, df):
+            """df.py:4826-4867 converts through pandas; here CUDA buffers are adopted through DLPack (no copy) and
+            host buffers are copied H2D, one row partition per chunk of the producer."""
+            if type(df) is cls:
+                return df
+            from .interchange import blocks_from_dataframe
+
+            blocks = blocks_from_dataframe(df)
+            pc = cls._partition_mgr_cls._partition_class
+            parts = np.array([[pc.put(b)] for b in blocks], dtype=object).reshape(len(blocks), 1)
+            index = None
+            if all(b.has_range_index() for b in blocks):
+                index = pandas.RangeIndex(blocks[0].range_start, blocks[0].range_start + sum(b.nrows for b in blocks))
+            return cls(parts, index, blocks[0].columns, [b.nrows for b in blocks], [len(blocks[0].cols)])
+
         def map(self, *args, **kwargs):
             """df.py:2253-2322 hands the result this frame's row lengths -- a Map keeps the rows -- so the job-wide
             row count (``get_axis_len``) is handed on with them: Modin's API asks ``.empty`` of every intermediate
