@@ -645,6 +645,45 @@ def run_b200_arm(args):
         del fa, fb, fc, blk
         torch.cuda.empty_cache()
 
+        # ---- Fold template: df.cumsum() down the rows (qc.py:2431; csrc/cum.cu).  Input + output resident, so
+        # n = rows/2 (32 + 32 GB per 1e9 on one GPU); rows sharded over ranks scan locally, carries cross the ranks
+        progress("leg: Fold cumsum")
+        try:
+            rowsf = max(rows // 2, 8192)
+            lof, hif = dist.shard_bounds(rowsf)
+            ff = api.device_frame(rowsf, W, seed=42)
+            api.execute(ff)
+
+            def step_cumsum():
+                last[0] = None
+                last[0] = api.launch(ff.cumsum())  # qc.cumsum -> Fold template -> frame.fold -> DevCumulative
+
+            total_c, per_c = timed(step_cumsum, ksteps, 2)
+            blk = api.blocks(last[0])[0]
+            j = W - 1
+            ok = True
+            if rank == 0:  # the top of the frame against numpy's sequential cumsum of the same generated rows
+                m = min(blk.nrows, 10000)
+                x = synth.gen_f64(m, 42, j, 0)
+                got = blk.cols[j].data[:m].cpu().numpy()
+                ok = _sum_close(got, np.cumsum(x), np.cumsum(np.abs(x)), max(m, 2))
+            fsum = np.asarray(api.to_pandas(ff.sum()), dtype=np.float64)
+            fabs = np.asarray(api.to_pandas(ff.abs().sum()), dtype=np.float64)
+            if rank == ws - 1 and blk.nrows:  # the last row of the job holds the column sums (TreeReduce kernel)
+                ok = ok and _sum_close(device_values(blk.cols[j], [blk.nrows - 1]), fsum[j : j + 1], fabs[j : j + 1], rowsf)
+            ok = all_ranks_ok(ok)
+            last[0] = None
+            also.append({"metric": f"rows/sec df.cumsum() on {rowsf}x{W} f64, Fold template",
+                         "value": rowsf / (total_c / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_c / ksteps, "checked": ok,
+                         "roofline": roof("cum_tile_scan_kernel<f64,SUM> (after cum_tile_reduce + cum_scan_tiles: the input is read twice, 24 B moved per 16 B algorithmic)",
+                                          (hif - lof) * W * 16, per_c, launch_ms=kernel_ms(step_cumsum, "cum_apply"),
+                                          partials_ms=kernel_ms(step_cumsum, "cum_partials"))})  # fmt: skip
+            del ff, blk
+        except Exception as exc:  # a leg added late in round 2: a failure here must not take the other legs with it
+            also.append({"metric": "rows/sec df.cumsum(), Fold template", "error": f"{type(exc).__name__}: {exc}"[:300]})
+        last[0] = None
+        torch.cuda.empty_cache()
+
         # ---- GroupByReduce: groupby('key').sum(), G int64 keys, 8 float64 values (C4)
         def groupby_leg(skew, dense_on, label, kern, traffic_key):
             nonlocal roofline_groupby

@@ -44,7 +44,7 @@ def test_bench_control_flow_on_the_double(ws):
     assert j["n_gpus"] == ws and j["checked"] is True
     assert j["parity_ok"] is (True if ws > 1 else None), j.get("parity_failed")
     legs = j["also"]
-    assert len(legs) == 8 and all(a.get("checked") is True for a in legs), [(a["metric"][:40], a.get("checked"), a.get("error")) for a in legs]
+    assert len(legs) == 9 and all(a.get("checked") is True for a in legs), [(a["metric"][:40], a.get("checked"), a.get("error")) for a in legs]
     assert j["roofline_groupby"]["checked"] is True
     assert j["e2e"]["checked"] is True and j["e2e_groupby"]["checked"] is True
     for key in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",

@@ -57,8 +57,11 @@ def _protocol_checks(pdm, on_gpu):
     k = proto.num_chunks()
     sub = list(proto.get_chunks(2 * k))
     assert len(sub) == 2 * k and sum(ch.num_rows() for ch in sub) == len(pdf)
+    if k > 1:
+        with pytest.raises(RuntimeError):
+            list(proto.get_chunks(2 * k + 1))  # not a multiple of the number of row partitions
     with pytest.raises(RuntimeError):
-        list(proto.get_chunks(2 * k + 1))
+        list(proto.get_chunks(0))
     sel = proto.select_columns_by_name(["c2", "key"])
     assert list(sel.column_names()) == ["c2", "key"] and sel.num_rows() == len(pdf)
     # our consumer on our producer: buffers adopted, values and labels intact
