@@ -532,3 +532,47 @@ def test_plugin_under_two_gloo_ranks():
     # the group table is split by key range: both ranks own a part, together all 23 groups
     assert sum(o["gb_local_sum"] for o in outs) == pdf["key"].nunique() and all(o["gb_local_sum"] > 0 for o in outs)
     assert all(o["gb_job_sum"] == pdf["key"].nunique() for o in outs)
+
+
+def test_results_are_released_without_the_cycle_collector(modin_b200_execution, cpu_device):
+    """A result frame must give its device buffers back when the last user reference goes -- not at the next run of
+    Python's cycle collector.  The reference's frames reference themselves when their labels or dtypes are lazy
+    (``ModinIndex(self, axis)``, df.py:526 / 542; ``DtypesDescriptor(parent_df=self)``, df.py:428-431); on the
+    CPU engines that only delays the release of host memory, here it pinned 32 GB of HBM per ``df.cumsum()`` call
+    (bench run of round 2: out of memory after five steps with the collector paused)."""
+    import gc
+    import weakref
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: host-logic check for the CPU device double")
+    _ns, mpd = modin_b200_execution
+    pdf = synth.host_frame(3000, 4, seed=1, nan_per_64k=2000, key_modulus=10)
+    df = mpd.DataFrame(pdf)
+    vals = df[["c0", "c1", "c2", "c3"]]
+    dim = mpd.DataFrame(pandas.DataFrame({"key": np.arange(10, dtype=np.int64), "w": np.arange(10) * 0.5}))
+    gb = df.groupby("key")
+    cases = {
+        "x * s + t": lambda: vals * 2.0 + 1.0, "abs": lambda: vals.abs(), "cumsum": lambda: vals.cumsum(),
+        "ffill": lambda: vals.ffill(), "groupby.sum": lambda: gb.sum(), "groupby.agg(dict)": lambda: gb.agg({"c0": "sum", "c1": "max"}),
+        "merge": lambda: df.merge(dim, on="key", how="left"), "filter": lambda: vals[vals["c0"] > 0.0],
+        "sort_values": lambda: vals.sort_values("c1"), "a + b": lambda: vals + vals, "dropna": lambda: vals.dropna(),
+    }  # fmt: skip
+    for call in cases.values():  # first use: caches (join tables, key statistics) may legitimately keep things alive
+        call()._query_compiler.finalize()
+    gc.collect()
+    gc.disable()
+    try:
+        kept = []
+        for name, call in cases.items():
+            r = call()
+            r._query_compiler.finalize()
+            blk = r._query_compiler._modin_frame._partitions[0, 0].get()
+            probe = weakref.ref(blk.cols[-1].data)  # the last column is always a fresh buffer of this result
+            del r, blk
+            if probe() is not None:
+                kept.append(name)
+        assert not kept, f"still allocated after the last reference went: {kept}"
+    finally:
+        gc.enable()
