@@ -886,50 +886,6 @@ class DevMeanReduce(DevFn):
         return res
 
 
-class DevSsdMap(DevFn):
-    """Second pass of var / std: per-column sum of squared deviations from the column means of the WHOLE frame
-    plus non-NaN counts, as a 1 x 2W partial (W float64 sums, W int64 counts) that
-    ``DevReduce("sum", "reduce")`` adds up across partitions and GPUs.
-
-    The reference registers var / std as full-axis ``Reduce`` of ``pandas.DataFrame.var`` (qc.py:1152-1153), i.e.
-    pandas' two-pass nanops.nanvar on a whole column; the two passes here are ``mean()`` and this functor, so the
-    result does not depend on the partitioning either."""
-
-    op = "ssd_map"
-
-    def __init__(self, centers):
-        """``centers``: a ``pandas.Series`` of column means indexed by column label (each block picks the centres of
-        ITS columns -- a frame wider than one column partition hands every partition the same functor), or a plain
-        sequence holding one centre per column of the block."""
-        if isinstance(centers, pandas.Series):
-            self.by_label, self.centers = {k: float(v) for k, v in centers.items()}, None
-        else:
-            self.by_label, self.centers = None, [float(c) for c in centers]
-
-    def _centers_for(self, block):
-        if self.by_label is not None:
-            missing = [c for c in block.columns if c not in self.by_label]
-            if missing:
-                raise ValueError(f"var / std: no centre for columns {missing!r}")
-            return [self.by_label[c] for c in block.columns]
-        if len(self.centers) != len(block.cols):
-            raise ValueError("var / std: one centre per column expected")
-        return self.centers
-
-    def __call__(self, block, *args, axis=0, skipna=True, numeric_only=False, **kwargs):
-        _check_block(block, "DevSsdMap")
-        if axis not in (0, "index", None):
-            raise NotImplementedError("row-wise var / std is not on the B200 path")
-        block_centers = self._centers_for(block)
-        cols = ops.cast_columns_f64(block.cols)
-        t = ops.torch_mod()
-        centers = t.tensor(block_centers, dtype=t.float64).to(cols[0].data.device) if cols else None
-        vals, cnts = ops.reduce_columns("ssd", cols, skipna=bool(skipna), variant=ReduceVariant.get(), centers=centers)
-        out = [DeviceColumn(v, np.float64) for v in vals] + [DeviceColumn(c, np.int64) for c in cnts]
-        labels = pandas.MultiIndex.from_tuples([("ssd", c) for c in block.columns] + [("count", c) for c in block.columns])
-        return _reduced_block(out, labels)
-
-
 class DevVar(DevFn):
     """``pandas.DataFrame.var / std`` of one FULL column partition -> 1 x W block: the device body of the Reduce
     template (alg/reduce.py:32-71 -> PandasDataframe.reduce, df.py:2171-2205; qc.py:1155-1156 registers
@@ -976,7 +932,7 @@ class DevVar(DevFn):
         return self(block, *args, **kwargs)
 
 
-# ------------------------------------------------------------------ label alignment (the reindexing half of _copartition)
+# ------------------------------------------------------------------ Fold functor
 class DevCumulative(DevFn):
     """``pandas.DataFrame.cumsum / cummax / cummin`` (qc.py:2429-2431) and ``DataFrame.ffill`` (``fillna(method=
     "ffill")``, qc.py:2809-2810) of one full column partition: the device body of the Fold template
@@ -1029,6 +985,7 @@ class DevCumulative(DevFn):
         return block.with_cols(new_cols)
 
 
+# ------------------------------------------------------------------ label alignment (the reindexing half of _copartition)
 def _labels_block(block, cols, labels: pandas.Index, replicated=False):
     """``cols`` under new row ``labels`` (RangeIndex -> O(1) metadata, numeric -> device index column, else host)."""
     n = len(labels)
