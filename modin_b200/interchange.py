@@ -22,7 +22,7 @@ from typing import Any, Dict, Iterable, Optional, Sequence, Tuple
 import numpy as np
 import pandas
 
-from .block import DeviceBlock, DeviceColumn, current_device, torch_mod
+from .block import DeviceBlock, DeviceColumn, torch_mod
 
 
 class DTypeKind(enum.IntEnum):  # dataframe_protocol/utils.py:29-56
@@ -298,4 +298,4 @@ def blocks_from_dataframe(df, allow_copy: bool = True):
     return blocks
 
 
-__all__ = ["B200Buffer", "B200Column", "B200ProtocolDataframe", "blocks_from_dataframe", "current_device"]
+__all__ = ["B200Buffer", "B200Column", "B200ProtocolDataframe", "blocks_from_dataframe"]
