@@ -380,6 +380,10 @@ class DeviceBlock:
             if self.has_range_index() and labels.start == self.range_start:
                 return self
             out = DeviceBlock(self.cols, self.columns, nrows=self.nrows, range_start=labels.start)
+        elif len(labels) == 0 and not isinstance(labels, pandas.MultiIndex) and labels.name is None:
+            # no rows, no labels to keep: an empty range (an empty ``Index([], dtype=object)`` would otherwise make
+            # this a host-labelled block, which row-shard gathers refuse -- a rank whose shard of a result is empty)
+            out = DeviceBlock(self.cols, self.columns, nrows=0, range_start=0)
         elif not isinstance(labels, pandas.MultiIndex) and labels.dtype.kind in "if" and len(labels) > 0:
             arr = labels.to_numpy()
             arr = arr.astype(np.int64) if arr.dtype.kind == "i" else arr.astype(np.float64)
@@ -519,11 +523,17 @@ class HostBlock:
 def concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
     """Row-wise concatenation of blocks with identical columns (pandas.concat in
     deploy_axis_func, axpart.py:445-452) -- a D2D copy into fresh column buffers."""
-    from . import ops
-
     blocks = [b for b in blocks]
     if len(blocks) == 1:
         return blocks[0]
+    out = _concat_rows(blocks)
+    out.replicated = all(b.replicated for b in blocks)  # pieces every rank holds in full stay that
+    return out
+
+
+def _concat_rows(blocks: Sequence[DeviceBlock]) -> DeviceBlock:
+    from . import ops
+
     first = blocks[0]
     ncols = len(first.cols)
     cols = []

@@ -374,13 +374,11 @@ class B200Dataframe:
 
     def drop_duplicate_rows(self, col_position: int, keep: str = "first", ignore_index: bool = False) -> "B200Dataframe":
         """Rows holding the first / last occurrence of every value of one int64 column, in row order
-        (``DevDropDuplicates``).  Single process: equal keys on different GPUs would need the key-range exchange
-        of ``sort_by`` first, which is not wired up for this operation."""
+        (``DevDropDuplicates``).  Across GPUs the keys of every rank's own survivors are all-gathered in rank order,
+        the same pass names the job-wide winners and every rank keeps its own: the result stays row-sharded."""
         from .block import concat_cols, concat_rows
         from .functors import DevDropDuplicates
 
-        if dist.is_distributed():
-            raise NotImplementedError("multi-GPU drop_duplicates is not on the B200 path")
         rows = [concat_cols([p.get() for p in row]) if len(row) > 1 else row[0].get() for row in self._partitions]
         block = concat_rows(rows) if len(rows) > 1 else rows[0]
         out = DevDropDuplicates()(block, col_position, keep=keep, ignore_index=ignore_index)

@@ -556,18 +556,52 @@ class DevDropDuplicates(DevFn):
         return int(columns.get_loc(cols[0]))
 
     def __call__(self, block, key_position=0, keep="first", ignore_index=False, **kwargs):
-        from .block import torch_mod
-
         _check_block(block, "DevDropDuplicates")
+        if _spans_ranks(block):
+            return self.run_distributed(block, key_position, keep=keep, ignore_index=ignore_index)
+        self._validate(block, key_position, keep, ignore_index)
+        if block.nrows <= 1:
+            return DeviceBlock(block.cols, block.columns, nrows=block.nrows, range_start=0) if ignore_index else block
+        return self._rows(block, self._winners(block.cols[key_position], keep), ignore_index, 0)
+
+    def run_distributed(self, block, key_position=0, keep="first", ignore_index=False, **kwargs):
+        """Rows sharded over ranks: equal keys may sit on different GPUs, so a shard-local answer is not the answer.
+        Every rank finds its own first / last occurrence per key; only the KEYS of those survivors (one int64 per
+        rank and distinct key) are all-gathered, in rank order -- which is row order, shards are contiguous; the
+        same pass over the gathered keys names the job-wide winners, and every rank keeps the winners that came
+        from its own survivors.  The result stays row-sharded and in row order like any other frame; no row moves."""
         from . import dist
 
-        if dist.is_distributed() and not block.replicated:
-            # equal keys on different GPUs: a shard-local answer would be wrong, and both front doors end up here
-            raise NotImplementedError("multi-GPU drop_duplicates is not on the B200 path")
+        _check_block(block, "DevDropDuplicates")
+        self._validate(block, key_position, keep, ignore_index)
+        t = ops.torch_mod()
+        key = block.cols[key_position]
+        mine = self._winners(key, keep)  # positions inside this shard, ascending
+        dev = key.data.device
+        counts = [c[0] for c in dist.all_gather_small(t.tensor([len(mine)], dtype=t.int64, device=dev))]
+        surv_keys = ops.take_columns([key], mine)[0] if len(mine) else DeviceColumn.empty(0, np.int64)
+        all_keys = DeviceColumn(dist.all_gather_rows([surv_keys.data])[0], np.int64)
+        win = self._winners(all_keys, keep)  # positions inside the gathered survivors, ascending
+        start = int(sum(counts[: dist.rank()]))
+        stop = start + int(counts[dist.rank()])
+        keep_ids = DeviceColumn.empty(0, np.int64)
+        if len(win) and stop > start:
+            # winners that are this rank's survivors: positions in [start, stop) (digitize against the two bounds)
+            bins = ops.digitize(win, [start, stop])
+            hit = ops.map_columns("eq_s", [bins], s0=[1])[0]
+            idx = ops.map_columns("add_s", ops.cast_columns_i64([hit]), s0=[-1])[0]  # 0 -> -1 (skip), 1 -> 0 (hit)
+            pos, k = ops.compact_hits(idx)
+            if k:
+                local = ops.map_columns("add_s", ops.take_columns([win], pos), s0=[-start])[0]
+                keep_ids = ops.take_columns([mine], local)[0]
+        offset = dist.exclusive_row_offset(len(keep_ids)) if ignore_index else 0
+        return self._rows(block, keep_ids, ignore_index, offset)
+
+    @staticmethod
+    def _validate(block, key_position, keep, ignore_index):
         if keep not in ("first", "last"):
             raise NotImplementedError("drop_duplicates(keep=False) is not on the B200 path")
-        key = block.cols[key_position]
-        if key.dtype != np.int64:
+        if block.cols[key_position].dtype != np.int64:
             raise NotImplementedError("device drop_duplicates needs an int64 subset column")
         if any(c.dtype == np.bool_ for c in block.cols):
             raise NotImplementedError("drop_duplicates of frames with bool columns is not on the B200 path")
@@ -575,12 +609,14 @@ class DevDropDuplicates(DevFn):
             raise NotImplementedError("drop_duplicates keeps numeric / range row labels only (or ignore_index=True)")
         if block.index_cols and len(block.index_cols) != 1 and not ignore_index:
             raise NotImplementedError("drop_duplicates of a frame with a MultiIndex is not on the B200 path")
-        t = torch_mod()
-        n = block.nrows
+
+    @staticmethod
+    def _winners(key: DeviceColumn, keep: str) -> DeviceColumn:
+        """Row positions holding the first / last occurrence of every key value, ascending (steps 1-4 above)."""
+        t = ops.torch_mod()
+        n = len(key)
         if n <= 1:
-            if ignore_index:
-                return DeviceBlock(block.cols, block.columns, nrows=n, range_start=0)
-            return block
+            return DeviceColumn(t.arange(n, dtype=t.int64, device=key.data.device), np.int64)
         image = ops.map_columns("ordered_s", [key], s0=[0])[0]  # fresh buffer: the sort is in place
         perm = DeviceColumn(t.arange(n, dtype=t.int64, device=key.data.device), np.int64)
         ops.sort_pairs(image, perm)
@@ -596,14 +632,20 @@ class DevDropDuplicates(DevFn):
         picked = [ops.take_columns([perm], pos)[0].data] if k else []
         rid = DeviceColumn(t.cat([always.data] + picked), np.int64)  # K = k + 1 row ids, in key order
         ops.sort_pairs(rid, DeviceColumn.empty(k + 1, np.int64))  # back into row order (payload unused)
+        return rid
+
+    @staticmethod
+    def _rows(block, rid: DeviceColumn, ignore_index: bool, new_start: int) -> DeviceBlock:
+        """The rows ``rid`` of ``block`` with their labels (or renumbered from ``new_start``)."""
+        k = len(rid)
         cols = ops.take_columns(block.cols, rid) if block.cols else []
         if ignore_index:
-            return DeviceBlock(cols, block.columns, nrows=k + 1, range_start=0)
+            return DeviceBlock(cols, block.columns, nrows=k, range_start=int(new_start))
         if block.index_cols:
             labels, names = ops.take_columns(block.index_cols, rid)[0], block.index_names
         else:
             labels, names = ops.map_columns("add_s", [rid], s0=[int(block.range_start)])[0], [None]
-        return DeviceBlock(cols, block.columns, nrows=k + 1, index_cols=[labels], index_names=names)
+        return DeviceBlock(cols, block.columns, nrows=k, index_cols=[labels], index_names=names)
 
 
 class DevBoolReduce(DevFn):
@@ -761,7 +803,9 @@ class DevReduce(DevFn):
                 out.append(_nan_where_empty(vals[j], cnts[j]))
             else:
                 out.append(DeviceColumn(vals[j], c.dtype))
-        return _reduced_block(out, block.columns)
+        res = _reduced_block(out, block.columns)
+        res.replicated = block.replicated  # a partial of rows every rank holds in full is such a partial too
+        return res
 
     def run_distributed(self, block, *args, axis=0, skipna=True, numeric_only=False, min_count=0, **kwargs):
         """Reduce-phase body when rows are sharded over several GPUs: local reduction of this rank's

@@ -549,9 +549,7 @@ def register(shims: bool | None = None):
             """qc.py:2231-2270 -- what ``drop_duplicates`` (modin/pandas/base.py:1600-1623) and ``Series.unique``
             ask for.  One full-axis application of the device functor instead of duplicated() + row selection."""
             pos = fx.DevDropDuplicates.resolve(self.columns, subset, keep)
-            if bdist.is_distributed():  # every rank refuses together: a duplicate's first occurrence may live elsewhere
-                raise NotImplementedError("drop_duplicates / unique through the Modin plug-in is single-process")
-            frame = self._modin_frame
+            frame = self._modin_frame  # under torch.distributed the functor exchanges the per-rank survivors itself
             if frame._partitions.shape[1] != 1:
                 raise NotImplementedError("device drop_duplicates: frames of one column partition (up to 32 columns)")
             fn = fx.DevDropDuplicates()

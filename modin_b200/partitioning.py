@@ -203,12 +203,22 @@ def _payload(x):
     return x.get() if isinstance(x, B200Partition) else x
 
 
+def _inherit_replicated(result, inputs):
+    """A function of blocks that EVERY rank holds in full (results of collectives: reductions, gathered frames)
+    gives every rank the same block again -- the flag that keeps later reduce phases from combining it across ranks
+    once more is handed on, whatever functor built the result."""
+    blocks = [b for b in inputs if isinstance(b, DeviceBlock)]
+    if isinstance(result, DeviceBlock) and not result.replicated and blocks and all(b.replicated for b in blocks):
+        result.replicated = True
+    return result
+
+
 def _run_queue(data, queue):
     for func, args, kwargs in fuse_call_queue(queue):
         args = tuple(_payload(a) for a in args)
         fn, bargs, bkw = unwrap(func)
         bargs = tuple(_payload(a) for a in bargs)
-        data = fn(data, *bargs, *args, **{**bkw, **kwargs})
+        data = _inherit_replicated(fn(data, *bargs, *args, **{**bkw, **kwargs}), (data, *bargs, *args))
     return data
 
 
@@ -473,10 +483,10 @@ class B200AxisPartition:
         fn, bargs, bkw = unwrap(func)
         args = tuple(bargs) + tuple(f_args or ())
         kwargs = {**bkw, **(f_kwargs or {})}
-        if dist.is_distributed() and axis == 0 and hasattr(fn, "run_distributed"):
+        if dist.is_distributed() and axis == 0 and hasattr(fn, "run_distributed") and not gathered.replicated:
             result = fn.run_distributed(gathered, *args, **kwargs)
         else:
-            result = fn(gathered, *args, **kwargs)
+            result = _inherit_replicated(fn(gathered, *args, **kwargs), (gathered, *args))
         if manual_partition:
             lengths_ = lengths
         elif num_splits == 1:
@@ -502,7 +512,7 @@ class B200AxisPartition:
             rows.append(concat_cols(right_blocks[other_shape[i - 1] : other_shape[i]]))
         rt = concat_rows(rows) if len(rows) > 1 else rows[0]
         fn, bargs, bkw = unwrap(func)
-        result = fn(lt, rt, *bargs, *(f_args or ()), **{**bkw, **(f_kwargs or {})})
+        result = _inherit_replicated(fn(lt, rt, *bargs, *(f_args or ()), **{**bkw, **(f_kwargs or {})}), (lt, rt))
         if num_splits == 1:
             return [result]
         return split_block(axis, result, num_splits, None, min_block_size)

@@ -276,15 +276,20 @@ def _full_stack_late_ops_job(rank, ws):
         out["series_nunique"] = df["key"].nunique()
         # a shard-local answer would be wrong for these: refused on every rank
         out["concat_rows_refused"] = refused(lambda: bpd.concat([df, df]))
-        out["drop_duplicates_refused"] = refused(lambda: df.drop_duplicates(subset=["key"]))
+        # equal keys sit on different ranks: every rank keeps its survivors, they are gathered, the same pass picks
+        # the job-wide first / last -- the result is the whole-frame answer, identical on every rank
+        for keep in ("first", "last"):
+            out["dd_" + keep] = df.drop_duplicates(subset=["key"], keep=keep)._to_pandas()
+        out["dd_ignore"] = df.drop_duplicates(subset=["k2"], ignore_index=True)._to_pandas()
+        out["dd_filtered"] = df[df["c0"] > 0.25].drop_duplicates(subset=["key"], keep="last")._to_pandas()
         out["local_rows"] = len(df._query_compiler._modin_frame)
     return out
 
 
 def test_full_stack_late_ops_across_ranks():
     """astype / row selection / dropna / isin / column concat / head / tail work shard by shard and gather to the
-    whole-frame pandas answer; nunique counts groups job-wide; row concat and drop_duplicates refuse under
-    torch.distributed instead of answering per shard."""
+    whole-frame pandas answer; nunique counts groups job-wide; drop_duplicates exchanges the per-rank survivors; row
+    concat refuses under torch.distributed instead of answering per shard."""
     import pandas
 
     out = _run(_full_stack_late_ops_job)
@@ -301,6 +306,10 @@ def test_full_stack_late_ops_across_ranks():
         "tail": pdf.tail(4000),
         "shifted": pdf.set_axis(pandas.RangeIndex(1000, 1000 + len(pdf)), axis=0),
         "sliced": pandas.concat([pdf.iloc[lo + 10 : lo + 100] for lo, _ in (bdist.shard_bounds(len(pdf), r, 2) for r in range(2))]),
+        "dd_first": pdf.drop_duplicates(subset=["key"], keep="first"),
+        "dd_last": pdf.drop_duplicates(subset=["key"], keep="last"),
+        "dd_ignore": pdf.drop_duplicates(subset=["k2"], ignore_index=True),
+        "dd_filtered": pdf[pdf["c0"] > 0.25].drop_duplicates(subset=["key"], keep="last"),
     }
     for o in out:  # the gathered frame is the same on every rank
         for name, w in want.items():
@@ -310,7 +319,7 @@ def test_full_stack_late_ops_across_ranks():
             assert np.array_equal(g.to_numpy(dtype=np.float64), w.to_numpy(dtype=np.float64), equal_nan=True), name
         assert list(o["nunique"].index) == ["key", "k2"] and list(o["nunique"]) == list(pdf[["key", "k2"]].nunique())
         assert o["series_nunique"] == pdf["key"].nunique()
-        assert o["concat_rows_refused"] and o["drop_duplicates_refused"]
+        assert o["concat_rows_refused"]
 
 
 def _full_stack_api_sweep_job(rank, ws):

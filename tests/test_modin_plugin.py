@@ -456,12 +456,15 @@ def _plugin_rank_job(rank, ws):
         out["dropna"] = P(mdf.dropna())
         out["nunique"] = P(mfull[["key"]].nunique())
         out["sort"] = P(mdf.sort_values("c1"))
-        for what, call in (("drop_duplicates", lambda: mfull[["key"]].drop_duplicates()),):  # fmt: skip
-            try:
-                call()
-                out["refused_" + what] = False
-            except NotImplementedError:
-                out["refused_" + what] = True
+        # results every rank holds in full (reductions) stay that through maps and further reductions: they must not
+        # be combined across the ranks a second time
+        out["sum_of_scaled_sums"] = float((mdf.sum() * 2.0).sum())
+        out["max_of_means"] = float(mdf.mean().max())
+        out["count_positive_sums"] = int((mdf.sum() > 0).sum())
+        # equal keys on different ranks: the functor exchanges the keys of the per-rank survivors (sharded result)
+        out["dd_last"] = P(mfull.drop_duplicates(subset=["key"], keep="last"))
+        out["dd_series"] = P(mfull["key"].drop_duplicates())
+        out["dd_then_sum"] = P(mfull.drop_duplicates(subset=["key"])[["c0", "c1"]].sum())  # the result is row-sharded like any frame
     return out
 
 
@@ -526,7 +529,12 @@ def test_plugin_under_two_gloo_ranks():
         wd = vals.dropna()
         assert list(o["dropna"].index) == list(wd.index) and _same(o["dropna"].to_numpy(), wd.to_numpy())
         assert int(np.asarray(o["nunique"]).ravel()[0]) == pdf["key"].nunique()
-        assert o["refused_drop_duplicates"]
+        assert np.isclose(o["sum_of_scaled_sums"], (vals.sum() * 2.0).sum(), rtol=1e-12, atol=0)
+        assert np.isclose(o["max_of_means"], vals.mean().max(), rtol=1e-12, atol=0)
+        assert o["count_positive_sums"] == int((vals.sum() > 0).sum())
+        assert o["dd_last"].equals(pdf.drop_duplicates(subset=["key"], keep="last"))
+        assert o["dd_series"].equals(pdf["key"].drop_duplicates())
+        assert np.allclose(o["dd_then_sum"].to_numpy(), pdf.drop_duplicates(subset=["key"])[["c0", "c1"]].sum().to_numpy(), rtol=0, atol=1e-9)
         wsrt = vals.sort_values("c1", kind="stable")
         assert list(o["sort"].index) == list(wsrt.index) and _same(o["sort"].to_numpy(), wsrt.to_numpy())
     # the group table is split by key range: both ranks own a part, together all 23 groups
