@@ -137,6 +137,28 @@ def run_checks(bpd, tag, rank, fails):
     srt = P(dv.sort_values("c1"))
     ws_ = vals.sort_values("c1", kind="stable")
     check("sort_values (range shuffle, all_to_all of rows)", list(srt.index) == list(ws_.index) and exact(srt.to_numpy(), ws_.to_numpy()))
+    # drop_duplicates: the keys of each rank's own survivors are all-gathered, the result stays row-sharded
+    for keep in ("first", "last"):
+        dd, wdd = P(df.drop_duplicates(subset=["key"], keep=keep)), pdf.drop_duplicates(subset=["key"], keep=keep)
+        check(f"drop_duplicates keep={keep} (survivor keys all_gathered)",
+              list(dd.index) == list(wdd.index) and exact(dd.to_numpy(dtype=np.float64), wdd.to_numpy(dtype=np.float64)))
+    if tag == "modin":  # the templates added late in round 2 are reached through Modin's own API
+        # Fold: every rank scans its shard, the W column totals are all-gathered, carries are combined on the device
+        cs, wcs = P(dv.cumsum()).to_numpy(), vals.cumsum().to_numpy()
+        run_abs = np.cumsum(np.abs(np.nan_to_num(vals.to_numpy())), axis=0)
+        check("Fold cumsum (carries across ranks)", bool((np.isnan(cs) == np.isnan(wcs)).all()) and
+              bool((np.isnan(wcs) | (np.abs(cs - wcs) <= 4 * math.log2(n) * EPS * run_abs + 1e-300)).all()))
+        check("Fold cummax", exact(P(dv.cummax()).to_numpy(), vals.cummax().to_numpy()))
+        check("Fold ffill", exact(P(dv.ffill()).to_numpy(), vals.ffill().to_numpy()))
+        # Reduce: var / std, two packed all-reduces
+        check("Reduce var", bool(np.allclose(np.asarray(P(dv.var())), vals.var().to_numpy(), rtol=16 * math.log2(n) * EPS, atol=0)))
+        check("Reduce std(ddof=0)", bool(np.allclose(np.asarray(P(dv.std(ddof=0))), vals.std(ddof=0).to_numpy(),
+                                                     rtol=16 * math.log2(n) * EPS, atol=0)))
+        spec = {"c1": "mean", "c0": "sum"}
+        ga, wa = P(df.groupby("key").agg(spec)), pdf.groupby("key").agg(spec)
+        check("groupby.agg(dict)", list(ga.index) == list(wa.index) and list(ga.columns) == list(wa.columns) and
+              bool(np.allclose(ga.to_numpy(), wa.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)))
+        check("reduction of a reduction stays local", bool(np.isclose(float((dv.sum() * 2.0).sum()), (vals.sum() * 2.0).sum(), rtol=1e-12)))
 
 
 def main():
