@@ -375,6 +375,27 @@ def register(shims: bool | None = None):
     # ---------------------------------------------------------------- query compiler
     _f64 = lambda *a, **k: np.dtype("float64")  # noqa: E731
 
+    def _arith(op):
+        """``Binary.register(DevBinary(op), infer_dtypes="common_cast")`` (qc.py:535-566) with one shortcut in front:
+        a float64 frame against a real SCALAR keeps its dtypes, so the template's dtype inference (a pandas concat of
+        two dtype Series per operator, ~0.5 ms of host time: as much as the kernel needs for 2e7 rows) is skipped and
+        the scalar branch of the template (alg/binary.py:444-455: a lazy ``frame.map``) is taken directly."""
+        generic = Binary.register(fx.DevBinary(op), infer_dtypes="common_cast")
+        functor = fx.DevBinary(op)
+
+        def caller(query_compiler, other, broadcast=False, *args, dtypes=None, **kwargs):
+            frame = query_compiler._modin_frame
+            if (dtypes is None and not broadcast and not args and isinstance(other, (float, int, np.floating, np.integer))
+                    and not isinstance(other, (bool, np.bool_)) and kwargs.get("level") is None
+                    and kwargs.get("fill_value") is None and kwargs.get("axis", 0) in (0, 1, "index", "columns", None)
+                    and frame.has_materialized_dtypes and all(dt == np.float64 for dt in frame.dtypes)):  # fmt: skip
+                shape_hint = "column" if frame.has_materialized_columns and len(frame.columns) == 1 else None
+                new_frame = frame.map(functor, func_args=(other,), func_kwargs=kwargs, dtypes="copy", lazy=True)
+                return query_compiler.__constructor__(new_frame, shape_hint=shape_hint)
+            return generic(query_compiler, other, broadcast, *args, dtypes=dtypes, **kwargs)
+
+        return caller
+
     class B200OnModinQueryCompiler(PandasQueryCompiler):
         def get_axis_len(self, axis):
             """qc.py:411-427.  Under torch.distributed ``len(df)`` is the JOB-wide row count, not this rank's shard:
@@ -405,14 +426,14 @@ def register(shims: bool | None = None):
         round = Map.register(fx.DevRound(), dtypes="copy")  # qc.py:2438
         clip = Map.register(fx.DevClip(), dtypes="copy")
         # Binary (qc.py:535-624)
-        add = Binary.register(fx.DevBinary("add"), infer_dtypes="common_cast")
-        radd = Binary.register(fx.DevBinary("radd"), infer_dtypes="common_cast")
-        sub = Binary.register(fx.DevBinary("sub"), infer_dtypes="common_cast")
-        rsub = Binary.register(fx.DevBinary("rsub"), infer_dtypes="common_cast")
-        mul = Binary.register(fx.DevBinary("mul"), infer_dtypes="common_cast")
-        rmul = Binary.register(fx.DevBinary("rmul"), infer_dtypes="common_cast")
-        truediv = Binary.register(fx.DevBinary("truediv"), infer_dtypes="common_cast")
-        rtruediv = Binary.register(fx.DevBinary("rtruediv"), infer_dtypes="common_cast")
+        add = _arith("add")
+        radd = _arith("radd")
+        sub = _arith("sub")
+        rsub = _arith("rsub")
+        mul = _arith("mul")
+        rmul = _arith("rmul")
+        truediv = _arith("truediv")
+        rtruediv = _arith("rtruediv")
         eq = Binary.register(fx.DevBinary("eq"), infer_dtypes="bool")
         ne = Binary.register(fx.DevBinary("ne"), infer_dtypes="bool")
         lt = Binary.register(fx.DevBinary("lt"), infer_dtypes="bool")
