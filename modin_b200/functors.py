@@ -889,8 +889,27 @@ class DevMeanMap(DevFn):
             n = block.nrows
             out += [DeviceColumn(torch.full((1,), n, dtype=torch.int64, device=vals[0].device), np.int64)
                     for _ in cnts]  # fmt: skip
-        labels = pandas.MultiIndex.from_tuples([("sum", c) for c in block.columns] + [("count", c) for c in block.columns])
-        return _reduced_block(out, labels)
+        return _reduced_block(out, _mean_partial_labels(block.columns))
+
+
+_MEAN_LABELS: dict = {}
+
+
+def _mean_partial_labels(columns: pandas.Index) -> pandas.MultiIndex:
+    """("sum", c) ... ("count", c) ... for the 1 x 2W partial of a mean.  Building a MultiIndex costs the host more
+    than the launch it labels (~0.6 ms), and a frame asks for the same one on every call: remembered per column set."""
+    try:
+        key = tuple(columns)
+        hit = _MEAN_LABELS.get(key)
+    except TypeError:  # unhashable labels: build, do not remember
+        key = hit = None
+    if hit is None:
+        hit = pandas.MultiIndex.from_tuples([("sum", c) for c in columns] + [("count", c) for c in columns])
+        if key is not None:
+            if len(_MEAN_LABELS) >= 64:
+                _MEAN_LABELS.clear()
+            _MEAN_LABELS[key] = hit
+    return hit
 
 
 class DevMeanReduce(DevFn):
