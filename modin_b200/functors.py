@@ -1161,6 +1161,24 @@ _GB_FLAGS = {
 }
 
 
+_VALUE_POSITIONS: dict = {}
+
+
+def _value_positions(columns: pandas.Index, key_label):
+    """Positions and labels of the columns other than ``key_label``.  Iterating and slicing a pandas Index (Arrow-backed
+    strings under pandas 3) costs ~0.15 ms of host time per query; a frame asks the same question on every query, so the
+    answer is remembered per Index object (identity + the label; Index objects are immutable)."""
+    memo = _VALUE_POSITIONS.get(id(columns))
+    if memo is not None and memo[0] is columns and memo[1] == key_label:
+        return memo[2], memo[3]
+    keep = [i for i, lab in enumerate(columns) if lab != key_label]
+    labels = columns[keep]
+    if len(_VALUE_POSITIONS) >= 64:
+        _VALUE_POSITIONS.clear()
+    _VALUE_POSITIONS[id(columns)] = (columns, key_label, keep, labels)  # holding `columns` keeps the id from being reused
+    return keep, labels
+
+
 def _split_key_values(block: DeviceBlock, by_block: Optional[DeviceBlock]):
     """Key column + value columns of one row block (alg/groupby.py:186-206: with drop=True the
     `by` column is taken out of the data, or concatenated in when it lives in another frame)."""
@@ -1170,9 +1188,8 @@ def _split_key_values(block: DeviceBlock, by_block: Optional[DeviceBlock]):
         raise NotImplementedError("multi-column `by` is not on the B200 path yet")
     key = by_block.cols[0]
     key_label = by_block.columns[0]
-    keep = [i for i, lab in enumerate(block.columns) if lab != key_label]
+    keep, labels = _value_positions(block.columns, key_label)
     vals = [block.cols[i] for i in keep]
-    labels = block.columns[keep]
     if key.dtype != np.int64:
         raise NotImplementedError("device groupby needs an int64 key column")
     return key, key_label, vals, labels
@@ -1448,8 +1465,28 @@ class DevMerge(DevFn):
             self._cache[self.right_on] = ent
         return ent[1], ent[2]
 
+    _LABELS: dict = {}
+
     def result_labels(self, left_columns, right_columns):
-        """(positions of the right columns that enter the result, left labels, right labels) with pandas' suffixes."""
+        """(positions of the right columns that enter the result, left labels, right labels) with pandas' suffixes.
+        Asked twice per merge (frame metadata, then the block functor) with the same two Index objects on every query
+        of a stream: remembered per (Index identities, keys, suffixes) -- iterating pandas Indexes is host time the
+        probe kernel does not have at 8 GPUs."""
+        key = (id(left_columns), id(right_columns), self.left_on, self.right_on, tuple(self.suffixes))
+        try:
+            memo = DevMerge._LABELS.get(key)
+        except TypeError:
+            key = memo = None
+        if memo is not None and memo[0] is left_columns and memo[1] is right_columns:
+            return memo[2]
+        out = self._result_labels(left_columns, right_columns)
+        if key is not None:
+            if len(DevMerge._LABELS) >= 64:
+                DevMerge._LABELS.clear()
+            DevMerge._LABELS[key] = (left_columns, right_columns, out)  # the references keep the ids from being reused
+        return out
+
+    def _result_labels(self, left_columns, right_columns):
         same = self.left_on == self.right_on
         pay_pos = [i for i, lab in enumerate(right_columns) if not (same and lab == self.right_on)]
         pay_labels = [right_columns[i] for i in pay_pos]

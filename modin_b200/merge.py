@@ -33,6 +33,9 @@ def _combined(right_frame):
     return comb
 
 
+_RESULT_COLUMNS: dict = {}  # id(labels tuple) -> (labels tuple, result column Index): built once per pair of frames
+
+
 def row_axis_merge(left_qc, right_qc, reset_row_index, **kwargs):
     """``left_qc.merge(right_qc, **kwargs)`` -> new frame (the caller wraps it in its query compiler)."""
     how = kwargs.get("how", "inner")
@@ -63,8 +66,14 @@ def row_axis_merge(left_qc, right_qc, reset_row_index, **kwargs):
     right_to_broadcast = _combined(right_qc._modin_frame)  # merge.py:178
     func = DevMerge(how=how, suffixes=suffixes, left_on=left_on, right_on=right_on,
                     table_cache=right_to_broadcast._b200_join_tables)  # fmt: skip
-    pay_pos, ll, rl = func.result_labels(left_qc.columns, right_qc.columns)
-    new_columns = pandas.Index(ll + rl)
+    labels = func.result_labels(left_qc.columns, right_qc.columns)  # the same tuple object for the same two Indexes
+    pay_pos, ll, rl = labels
+    memo = _RESULT_COLUMNS.get(id(labels))
+    if memo is None or memo[0] is not labels:
+        if len(_RESULT_COLUMNS) >= 64:
+            _RESULT_COLUMNS.clear()
+        memo = _RESULT_COLUMNS[id(labels)] = (labels, pandas.Index(ll + rl))
+    new_columns = memo[1]
     right_dtypes = [np.dtype(right_qc.dtypes.iloc[i]) for i in pay_pos]
     if how == "left" and any(dt == np.int64 for dt in right_dtypes):
         # pandas turns int64 payload into float64 when ANY left row misses; every row partition on every GPU has to
