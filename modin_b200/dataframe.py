@@ -22,7 +22,7 @@ import numpy as np
 import pandas
 
 from . import dist
-from .block import DeviceBlock, torch_mod
+from .block import DeviceBlock
 from .functors import MODIN_UNNAMED_SERIES_LABEL
 from .partitioning import B200PartitionManager
 

@@ -32,7 +32,6 @@ from .functors import (
     DevMap,
     DevMeanMap,
     DevMeanReduce,
-    DevMerge,
     DevReduce,
     DevRound,
     DevVar,

@@ -11,7 +11,6 @@ import os
 
 import numpy as np
 import pandas
-import pytest
 
 from modin_b200 import synth
 from oracle import reference_path as orc
