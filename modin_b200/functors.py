@@ -1537,3 +1537,38 @@ class DevMerge(DevFn):
         hit_idx = ops.take_columns([idx], pos)[0]
         rcols = ops.take_columns(pay_cols, hit_idx)
         return DeviceBlock(lcols + rcols, pandas.Index(ll + rl), nrows=k, range_start=0)
+
+
+class DevMergePacked(DevMerge):
+    """``DevMerge`` on SEVERAL int64 key columns (pandas.merge(on=[k1, k2, ...]), merge.py:139-168 per block): the
+    left block's key tuples are packed into one order-preserving int64 (``groupkeys.pack``: one subtract + multiply
+    per key column and k - 1 adds per row) with the plan that also packed the right frame, the single-key join runs
+    on that image, and the image column is dropped from the result."""
+
+    op = "merge_packed"
+
+    def __init__(self, left_keys, plan, how="left", suffixes=("_x", "_y"), promote_ints=None, table_cache=None):
+        from .groupkeys import PACKED_KEY
+
+        super().__init__(how=how, suffixes=suffixes, left_on=PACKED_KEY, right_on=PACKED_KEY, promote_ints=promote_ints,
+                         table_cache=table_cache)  # fmt: skip
+        self.left_keys, self.plan = list(left_keys), plan
+
+    def _with_image(self, left: DeviceBlock) -> DeviceBlock:
+        from . import groupkeys as gk
+
+        keys = DeviceBlock([left.column(k) for k in self.left_keys], pandas.Index(range(len(self.left_keys))), nrows=left.nrows)
+        if any(c.dtype != np.int64 for c in keys.cols):
+            raise NotImplementedError("device merge joins on int64 key columns")
+        return left.with_cols(list(left.cols) + [gk.pack(keys, self.plan)], left.columns.append(pandas.Index([gk.PACKED_KEY])))
+
+    def count_misses(self, left: DeviceBlock, right: DeviceBlock) -> int:
+        return super().count_misses(self._with_image(left), right)
+
+    def __call__(self, left, right, *args, **kwargs):
+        from .groupkeys import PACKED_KEY
+
+        _check_block(left, "DevMergePacked")
+        out = super().__call__(self._with_image(left), right, *args, **kwargs)
+        return out.select_columns([i for i, lab in enumerate(out.columns) if lab != PACKED_KEY])
+

@@ -119,6 +119,26 @@ def fifth_batch_frame(synth):
     return f
 
 
+def sixth_batch_frames(synth):
+    """Inputs of the ``ext6`` cases (merge on SEVERAL key columns; shared with the tests): a fact frame with two int64
+    key columns (one with negative values) and a dim frame holding a subset of the key pairs, some of them twice, with
+    a float column whose label collides with the fact's, and an int64 column (promoted to float64 by left-join misses)."""
+    n = 4001
+    rng = np.random.RandomState(17)
+    fact = synth.host_frame(n, 2, seed=71, nan_per_64k=1500)
+    fact.insert(0, "b", synth.gen_i64(n, 72, 1, 9) - 4)
+    fact.insert(0, "a", synth.gen_i64(n, 73, 0, 31))
+    pairs = [(a, b) for a in range(0, 34) for b in range(-5, 4)]
+    rng.shuffle(pairs)
+    pairs = pairs[:170]
+    dim = pandas.DataFrame({"a": np.array([p[0] for p in pairs], dtype=np.int64), "b": np.array([p[1] for p in pairs], dtype=np.int64)})
+    dim["c0"] = synth.gen_f64(len(dim), 74, 0)
+    dim["d"] = synth.gen_f64(len(dim), 75, 0)
+    dim["i"] = np.arange(len(dim), dtype=np.int64) * 5 - 7
+    dim_dups = pandas.concat([dim, dim.iloc[:45].assign(d=lambda x: x["d"] + 1.0)], ignore_index=True)
+    return fact, dim, dim_dups
+
+
 def main():
     os.environ["MODIN_ENGINE"] = "python"
     apply_pandas3_shims()
@@ -311,6 +331,20 @@ def main():
         for ddof in (1, 0):
             arrays[f"{name}_ddof{ddof}"] = P(getattr(mF[fl], name)(ddof=ddof)).to_numpy()
     save("ext5_sort_fold", meta=np.array([2003]), **arrays)
+
+    # ---- sixth batch: merge on several key columns (merge.py:139-168 is pandas.merge per block, whatever the key is)
+    fact, dim, dim_dups = sixth_batch_frames(synth)
+    mf = mpd.DataFrame(fact)
+    arrays = {}
+    for how in ("left", "inner"):
+        r = P(mf.merge(mpd.DataFrame(dim), on=["a", "b"], how=how))
+        arrays[f"on_{how}"], arrays[f"on_{how}_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
+        arrays[f"on_{how}_dtypes"] = np.array([str(t) for t in r.dtypes])
+        r = P(mf.merge(mpd.DataFrame(dim_dups), on=["a", "b"], how=how))
+        arrays[f"m2m_{how}"] = r.to_numpy(dtype=np.float64)
+    r = P(mf.merge(mpd.DataFrame(dim.rename(columns={"a": "k"})), left_on=["a", "b"], right_on=["k", "b"], how="left"))
+    arrays["lr_on"], arrays["lr_on_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
+    save("ext6_multikey_merge", meta=np.array([4001, 170]), **arrays)
 
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):

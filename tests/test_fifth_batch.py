@@ -69,6 +69,32 @@ def _fifth_batch_checks(pdm, real_modin):
             assert np.allclose(got, z[f"{name}_ddof{ddof}"], rtol=rtol, atol=0), (name, ddof)
 
 
+def _sixth_batch_checks(pdm):
+    """Merge on several int64 key columns (packed into one order-preserving int64, ``groupkeys`` / ``DevMergePacked``)
+    against the unmodified reference's result: bit for bit, column labels and dtypes included."""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import sixth_batch_frames
+
+    z = dict(np.load(os.path.join(GOLDEN, "ext6_multikey_merge.npz"), allow_pickle=False))
+    fact, dim, dim_dups = sixth_batch_frames(synth)
+    P = lambda x: x._to_pandas()  # noqa: E731
+    mf = pdm.DataFrame(fact)
+    for how in ("left", "inner"):
+        r = P(mf.merge(pdm.DataFrame(dim), on=["a", "b"], how=how))
+        assert list(r.columns) == list(z[f"on_{how}_cols"]) and [str(t) for t in r.dtypes] == list(z[f"on_{how}_dtypes"]), how
+        assert np.array_equal(r.to_numpy(dtype=np.float64), z[f"on_{how}"], equal_nan=True), how
+        assert isinstance(r.index, type(fact.index)) and len(r.index) == len(r) and r.index[0] == 0  # fresh RangeIndex
+        r = P(mf.merge(pdm.DataFrame(dim_dups), on=["a", "b"], how=how))
+        assert np.array_equal(r.to_numpy(dtype=np.float64), z[f"m2m_{how}"], equal_nan=True), f"repeated pairs, {how}"
+    r = P(mf.merge(pdm.DataFrame(dim.rename(columns={"a": "k"})), left_on=["a", "b"], right_on=["k", "b"], how="left"))
+    assert list(r.columns) == list(z["lr_on_cols"])
+    assert np.array_equal(r.to_numpy(dtype=np.float64), z["lr_on"], equal_nan=True)
+    with pytest.raises(KeyError):
+        mf.merge(pdm.DataFrame(dim), on=["a", "nope"])
+    with pytest.raises(NotImplementedError):  # float key columns have no order-preserving int64 packing here
+        mf.merge(pdm.DataFrame(dim), left_on=["a", "c0"], right_on=["a", "d"])
+
+
 def test_fifth_batch_through_the_mirror_on_the_double(cpu_device):
     import torch
 
@@ -77,6 +103,7 @@ def test_fifth_batch_through_the_mirror_on_the_double(cpu_device):
     import modin_b200.pandas as bpd
 
     _fifth_batch_checks(bpd, False)
+    _sixth_batch_checks(bpd)
 
 
 @needs_modin
@@ -86,6 +113,7 @@ def test_fifth_batch_under_real_modin_on_the_double(cpu_device):
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu-marked test")
     _fifth_batch_checks(_modin(), True)
+    _sixth_batch_checks(_modin())
 
 
 @pytest.mark.gpu

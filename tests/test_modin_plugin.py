@@ -452,6 +452,11 @@ def _plugin_rank_job(rank, ws):
         dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
         out["merge_left"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="left"))
         out["merge_inner"] = P(mfull.merge(mpd.DataFrame(dim), on="key", how="inner"))
+        # two key columns: packed into one int64 over the key ranges of both frames, agreed across the ranks
+        two = pdf.assign(k2=(np.arange(len(pdf), dtype=np.int64) * 7) % 5 - 2)
+        dim2 = pandas.DataFrame({"key": np.repeat(np.arange(23, dtype=np.int64), 5)[:100],
+                                 "k2": np.tile(np.arange(-2, 3, dtype=np.int64), 23)[:100], "d1": rng.randn(100)})
+        out["merge_two_keys"] = P(mpd.DataFrame(two).merge(mpd.DataFrame(dim2), on=["key", "k2"], how="left"))
         out["filter"] = P(mdf[mdf["c0"] > 0.0])
         out["dropna"] = P(mdf.dropna())
         out["nunique"] = P(mfull[["key"]].nunique())
@@ -524,6 +529,13 @@ def test_plugin_under_two_gloo_ranks():
         wl = orc.broadcast_merge(pdf, dim, "key", "left", 4)
         assert list(o["merge_left"].columns) == list(wl.columns) and _same(o["merge_left"].to_numpy(), wl.to_numpy())
         assert _same(o["merge_inner"].to_numpy(), orc.broadcast_merge(pdf, dim, "key", "inner", 4).to_numpy())
+        two = pdf.assign(k2=(np.arange(len(pdf), dtype=np.int64) * 7) % 5 - 2)
+        rng2 = np.random.RandomState(1)
+        rng2.permutation(23), rng2.randn(20)  # the draws the rank job made before building dim2
+        dim2 = pandas.DataFrame({"key": np.repeat(np.arange(23, dtype=np.int64), 5)[:100],
+                                 "k2": np.tile(np.arange(-2, 3, dtype=np.int64), 23)[:100], "d1": rng2.randn(100)})
+        w2 = orc.broadcast_merge_general(two, dim2, "left", 4, on=["key", "k2"])
+        assert list(o["merge_two_keys"].columns) == list(w2.columns) and _same(o["merge_two_keys"].to_numpy(), w2.to_numpy())
         wf = vals[vals["c0"] > 0.0]
         assert list(o["filter"].index) == list(wf.index) and _same(o["filter"].to_numpy(), wf.to_numpy())
         wd = vals.dropna()

@@ -327,3 +327,23 @@ def test_fifth_batch_against_reference(golden_dir):
     for ddof in (1, 0):
         assert_bit_equal(orc.df_var(F[fl], NP, ddof=ddof).to_numpy(), z[f"var_ddof{ddof}"], f"var ddof={ddof}")
         assert_bit_equal(orc.df_std(F[fl], NP, ddof=ddof).to_numpy(), z[f"std_ddof{ddof}"], f"std ddof={ddof}")
+
+
+def test_sixth_batch_against_reference(golden_dir):
+    """Merge on several key columns: the restatement pinned to the unmodified reference (ext6_multikey_merge.npz)."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from make_golden import sixth_batch_frames
+
+    z = dict(np.load(os.path.join(golden_dir, "ext6_multikey_merge.npz"), allow_pickle=False))
+    fact, dim, dim_dups = sixth_batch_frames(synth)
+    for how in ("left", "inner"):
+        r = orc.broadcast_merge_general(fact, dim, how, NP, on=["a", "b"])
+        assert list(r.columns) == list(z[f"on_{how}_cols"]) and [str(t) for t in r.dtypes] == list(z[f"on_{how}_dtypes"])
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z[f"on_{how}"], f"merge on two keys, {how}")
+        r = orc.broadcast_merge_general(fact, dim_dups, how, NP, on=["a", "b"])
+        assert_bit_equal(r.to_numpy(dtype=np.float64), z[f"m2m_{how}"], f"merge on two keys, repeated pairs, {how}")
+    r = orc.broadcast_merge_general(fact, dim.rename(columns={"a": "k"}), "left", NP, left_on=["a", "b"], right_on=["k", "b"])
+    assert list(r.columns) == list(z["lr_on_cols"])
+    assert_bit_equal(r.to_numpy(dtype=np.float64), z["lr_on"], "merge left_on / right_on lists")

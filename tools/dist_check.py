@@ -134,6 +134,12 @@ def run_checks(bpd, tag, rank, fails):
     m2m = P(df.merge(bpd.DataFrame(dup), on="key", how="inner"))
     wm = orc.broadcast_merge_general(pdf, dup, "inner", NP, on="key")
     check("merge inner, repeated dim keys (many-to-many)", exact(m2m.to_numpy(dtype=np.float64), wm.to_numpy(dtype=np.float64)))
+    two = pdf.assign(k2=(np.arange(n, dtype=np.int64) * 7) % 5 - 2)
+    dim2 = pandas.DataFrame({"key": np.repeat(np.arange(G, dtype=np.int64), 5)[: 4 * G],
+                             "k2": np.tile(np.arange(-2, 3, dtype=np.int64), G)[: 4 * G], "d1": rng.randn(4 * G)})
+    mk, wmk = P(bpd.DataFrame(two).merge(bpd.DataFrame(dim2), on=["key", "k2"], how="left")), two.merge(dim2, on=["key", "k2"], how="left")
+    check("merge on two key columns (packed keys)", list(mk.columns) == list(wmk.columns) and
+          exact(mk.to_numpy(dtype=np.float64), wmk.to_numpy(dtype=np.float64)))
     srt = P(dv.sort_values("c1"))
     ws_ = vals.sort_values("c1", kind="stable")
     check("sort_values (range shuffle, all_to_all of rows)", list(srt.index) == list(ws_.index) and exact(srt.to_numpy(), ws_.to_numpy()))
