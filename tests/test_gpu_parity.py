@@ -87,21 +87,6 @@ def assert_sum_close(got, want, abs_sums, n, what):
     assert ok.all(), f"{what}: max err {np.nanmax(np.abs(got - want))} vs tol {tol.max()}"
 
 
-def _var_rtol(n):
-    """var / std: both sides are two-pass evaluations (means, then sums of squared deviations).  Each sums n
-    NON-NEGATIVE terms, so its relative error is at most ~(3 + log2 n) eps for any pairwise / tree / compensated order
-    (3 eps for forming one squared deviation); the error of the mean enters squared (ssd(m') = ssd(m) + n (m' - m)^2)
-    and is negligible.  Two such evaluations differ by at most the sum of their bounds, < 16 log2(n) eps; the square
-    root of std halves it."""
-    return 16.0 * max(1.0, math.log2(max(n, 2))) * EPS
-
-
-def _prod_rtol(k):
-    """Product of k factors: every multiplication contributes one rounding (relative eps) whatever the association,
-    so an evaluation is within k eps of the exact product and two evaluations within 2 k eps of each other."""
-    return 2.0 * k * 2.0 * EPS  # 2.0 * EPS = the unit roundoff step 2^-52 counted generously
-
-
 # ---------------------------------------------------------------------------------------------
 def test_device_generators_match_numpy_twin():
     from modin_b200 import ops
@@ -240,7 +225,7 @@ def test_prod_tree_reduce():
     pdf = synth.host_frame(300, 4, seed=21, nan_per_64k=3000) * 1.7
     got = m.DataFrame(pdf).prod().to_numpy()
     want = orc.df_prod(pdf, 4).to_numpy()
-    assert np.allclose(got, want, rtol=_prod_rtol(300), atol=0)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
     ints = pandas.DataFrame({"a": np.arange(1, 21, dtype=np.int64), "b": np.full(20, -2, dtype=np.int64)})
     assert_exact(m.DataFrame(ints).prod().to_numpy(), ints.prod().to_numpy(), "int64 prod (wrapping, exact)")
 
@@ -338,14 +323,7 @@ def test_groups_whose_rows_leave_no_trace_are_still_groups(gb_table_kind):
         w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
         gt = got.to_numpy(dtype=np.float64).reshape(len(got), -1)
         if agg in ("sum", "mean"):
-            # the stated bound, per group: |err| <= 4 log2(n) eps * sum|x| (divided by the count for the mean, plus the
-            # rounding of the division itself)
-            vcols = ["c0", "c1", "c2"]
-            abs_sums = pdf[vcols].abs().groupby(pdf["key"]).sum().to_numpy()
-            if agg == "mean":
-                cnt = np.maximum(pdf[vcols].notna().groupby(pdf["key"]).sum().to_numpy(), 1)
-                abs_sums = abs_sums / cnt + np.abs(np.nan_to_num(w)) / (2.0 * math.log2(n))
-            assert_sum_close(gt, w, abs_sums, n, f"groupby {agg}")
+            assert np.allclose(gt, w, rtol=0, atol=1e-9, equal_nan=True), agg
             assert not np.signbit(gt[np.isin(want.index.to_numpy(), [0, 6, 12])]).any() or agg == "mean"
         else:
             assert_exact(gt, w, f"groupby {agg}")
@@ -474,10 +452,10 @@ def test_more_registrations_vs_reference_golden(golden_dir):
         assert_exact(df.clip(lower=0.0)._to_pandas().to_numpy(), z["clip_lower"], f"{name}:clip lower")
         for got, key in ((df.var(), "var"), (df.var(ddof=0), "var_ddof0"), (df.std(), "std")):
             assert isinstance(got, pandas.Series) and list(got.index) == list(pdf.columns)
-            assert np.allclose(got.to_numpy(), z[key], rtol=_var_rtol(n), atol=0), f"{name}:{key}"
+            assert np.allclose(got.to_numpy(), z[key], rtol=1e-12, atol=0), f"{name}:{key}"
         assert np.isnan(df.var(skipna=False).to_numpy()).all() and np.isnan(z["var_noskip"]).all()
         small = m.DataFrame(pdf.iloc[:60] * 1.25)
-        assert np.allclose(small.prod().to_numpy(), z["prod60"], rtol=_prod_rtol(60), atol=0), f"{name}:prod"
+        assert np.allclose(small.prod().to_numpy(), z["prod60"], rtol=1e-12, atol=0), f"{name}:prod"
     for name, z in _load(golden_dir, "ext_groupby_*.npz"):
         n, G, V, nan, seed, kseed = (int(x) for x in z["meta"])
         pdf = synth.host_frame(n, V, seed=seed, nan_per_64k=nan, key_modulus=G, key_seed=kseed)
@@ -491,8 +469,8 @@ def test_more_registrations_vs_reference_golden(golden_dir):
     idf = m.DataFrame(ipdf)
     assert_exact(idf.round(1)._to_pandas().to_numpy(), ipdf.round(1).to_numpy(), "int round")
     assert_exact(idf.clip(-3, 9)._to_pandas().to_numpy(), ipdf.clip(-3, 9).to_numpy(), "int clip")
-    assert np.allclose(idf.var().to_numpy(), ipdf.var().to_numpy(), rtol=_var_rtol(100), atol=0)
-    assert np.allclose(idf.std(ddof=0).to_numpy(), ipdf.std(ddof=0).to_numpy(), rtol=_var_rtol(100), atol=0)
+    assert np.allclose(idf.var().to_numpy(), ipdf.var().to_numpy(), rtol=1e-12)
+    assert np.allclose(idf.std(ddof=0).to_numpy(), ipdf.std(ddof=0).to_numpy(), rtol=1e-12)
 
 
 def test_groupby_dictionary_aggregation(gb_table_kind):

@@ -1,0 +1,79 @@
+"""The DERIVED error bounds for the assertions VERDICT r1 called looser than stated (``atol=1e-9`` on group sums /
+means of ``test_groups_whose_rows_leave_no_trace_are_still_groups``; ``rtol=1e-12`` on var / std / prod with no
+derivation), as tests of their own.
+
+They live in a file that sorts LAST because the bounds were tightened after the round's GPU minutes were spent: the
+loose assertions in tests/test_gpu_parity.py are the ones that have passed on a B200, these have run on the numpy
+device double only, and a ``pytest -x`` run must not stop at an untried bound before the verified tests.
+
+Derivations
+-----------
+* group sum: ``|err| <= 4 log2(n) eps * sum|x|`` per group (float atomics in any order);
+  group mean: that bound divided by the group's count, plus the rounding of the division (``2 eps |mean|``).
+* var / std: both sides are two-pass evaluations (means, then sums of squared deviations).  Each sums n NON-NEGATIVE
+  terms, so its relative error is at most ~(3 + log2 n) eps for any pairwise / tree / compensated order (3 eps for
+  forming one squared deviation); the error of the mean enters squared (``ssd(m') = ssd(m) + n (m' - m)^2``) and is
+  negligible.  Two such evaluations differ by at most the sum of their bounds, ``< 16 log2(n) eps``; the square root
+  of std halves it.
+* prod of k factors: every multiplication contributes one rounding whatever the association, so an evaluation is
+  within ``k eps`` of the exact product and two evaluations within ``2 k eps`` of each other (asserted: ``4 k eps``).
+"""
+
+import math
+
+import numpy as np
+import pandas
+import pytest
+
+from modin_b200 import synth
+from oracle import reference_path as orc
+from tests.test_gpu_parity import EPS, _load, assert_sum_close, bpd
+
+pytestmark = pytest.mark.gpu
+
+
+def _var_rtol(n):
+    return 16.0 * max(1.0, math.log2(max(n, 2))) * EPS
+
+
+def _prod_rtol(k):
+    return 4.0 * k * EPS
+
+
+def test_group_sums_and_means_within_the_stated_bound():
+    m = bpd()
+    n = 4096 + 37
+    pdf = synth.host_frame(n, 3, seed=17, nan_per_64k=3000, key_modulus=10)
+    pdf.loc[pdf["key"] == 3, ["c0", "c1", "c2"]] = np.nan
+    pdf.loc[pdf["key"] == 5, ["c0", "c1", "c2"]] = -0.0
+    pdf["key"] = pdf["key"] * 3 - 9
+    g = m.DataFrame(pdf).groupby("key")
+    vcols = ["c0", "c1", "c2"]
+    for agg in ("sum", "mean"):
+        got = getattr(g, agg)()._to_pandas()
+        want = orc.groupby_reduce(pdf, "key", agg, 4)
+        w = want.to_numpy(dtype=np.float64).reshape(len(want), -1)
+        gt = got.to_numpy(dtype=np.float64).reshape(len(got), -1)
+        abs_sums = pdf[vcols].abs().groupby(pdf["key"]).sum().to_numpy()
+        if agg == "mean":
+            cnt = np.maximum(pdf[vcols].notna().groupby(pdf["key"]).sum().to_numpy(), 1)
+            abs_sums = abs_sums / cnt + np.abs(np.nan_to_num(w)) / (2.0 * math.log2(n))
+        assert_sum_close(gt, w, abs_sums, n, f"groupby {agg}")
+
+
+def test_var_std_prod_within_the_derived_bounds(golden_dir):
+    m = bpd()
+    for name, z in _load(golden_dir, "ext_n*.npz"):
+        n, W, seed, nan = (int(x) for x in z["meta"])
+        pdf = synth.host_frame(n, W, seed=seed, nan_per_64k=nan)
+        df = m.DataFrame(pdf)
+        for got, key in ((df.var(), "var"), (df.var(ddof=0), "var_ddof0"), (df.std(), "std")):
+            assert np.allclose(got.to_numpy(), z[key], rtol=_var_rtol(n), atol=0), f"{name}:{key}"
+        small = m.DataFrame(pdf.iloc[:60] * 1.25)
+        assert np.allclose(small.prod().to_numpy(), z["prod60"], rtol=_prod_rtol(60), atol=0), f"{name}:prod"
+    ipdf = pandas.DataFrame({"a": np.arange(-50, 50, dtype=np.int64), "b": (np.arange(100, dtype=np.int64) * 7) % 13})
+    idf = m.DataFrame(ipdf)
+    assert np.allclose(idf.var().to_numpy(), ipdf.var().to_numpy(), rtol=_var_rtol(100), atol=0)
+    assert np.allclose(idf.std(ddof=0).to_numpy(), ipdf.std(ddof=0).to_numpy(), rtol=_var_rtol(100), atol=0)
+    pdf = synth.host_frame(300, 4, seed=21, nan_per_64k=3000) * 1.7
+    assert np.allclose(m.DataFrame(pdf).prod().to_numpy(), orc.df_prod(pdf, 4).to_numpy(), rtol=_prod_rtol(300), atol=0)
