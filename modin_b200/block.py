@@ -380,10 +380,16 @@ class DeviceBlock:
             if self.has_range_index() and labels.start == self.range_start:
                 return self
             out = DeviceBlock(self.cols, self.columns, nrows=self.nrows, range_start=labels.start)
-        elif len(labels) == 0 and not isinstance(labels, pandas.MultiIndex) and labels.name is None:
-            # no rows, no labels to keep: an empty range (an empty ``Index([], dtype=object)`` would otherwise make
-            # this a host-labelled block, which row-shard gathers refuse -- a rank whose shard of a result is empty)
-            out = DeviceBlock(self.cols, self.columns, nrows=0, range_start=0)
+        elif len(labels) == 0 and not isinstance(labels, pandas.MultiIndex):
+            # no rows, no labels to keep: an empty range, or an empty device label column when the labels carry a name
+            # (an empty ``Index([], dtype=object)`` would otherwise make this a host-labelled block, which row-shard
+            # gathers refuse -- a rank whose shard of a result is empty)
+            if labels.name is None:
+                out = DeviceBlock(self.cols, self.columns, nrows=0, range_start=0)
+            else:
+                kind = np.float64 if labels.dtype.kind == "f" else np.int64
+                out = DeviceBlock(self.cols, self.columns, nrows=0, index_cols=[DeviceColumn.empty(0, kind)],
+                                  index_names=[labels.name])  # fmt: skip
         elif not isinstance(labels, pandas.MultiIndex) and labels.dtype.kind in "if" and len(labels) > 0:
             arr = labels.to_numpy()
             arr = arr.astype(np.int64) if arr.dtype.kind == "i" else arr.astype(np.float64)

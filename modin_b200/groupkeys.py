@@ -66,3 +66,29 @@ def unpack(packed: DeviceColumn, plan) -> List[DeviceColumn]:
     mins, ranges, strides = plan
     host = packed.to_numpy().astype(np.int64)
     return [DeviceColumn.from_numpy(((host // s) % r + lo).astype(np.int64)) for lo, r, s in zip(mins, ranges, strides)]
+
+
+# ---- float64 group keys ------------------------------------------------------------------------------------------
+_I64_MAX = np.iinfo(np.int64).max
+_MAG = np.int64(0x7FFFFFFFFFFFFFFF)
+
+
+def float_image(key: DeviceColumn) -> DeviceColumn:
+    """Order-preserving int64 image of a float64 key column: ``-0.0`` folded into ``0.0`` first (pandas groups them
+    together), then the total order of IEEE doubles as a signed integer (``MB200_OP_ORDERED_S``, the map the device
+    sort uses); every NaN becomes INT64_MAX, i.e. ONE group that sorts last -- where ``dropna`` finds it."""
+    if key.dtype != np.float64:
+        raise TypeError("float_image takes a float64 column")
+    if not len(key):
+        return DeviceColumn.empty(0, np.int64)
+    return ops.map_columns("ordered_s", ops.map_columns("add_s", [key], s0=[0.0]), s0=[0])[0]
+
+
+def float_keys(image: DeviceColumn) -> np.ndarray:
+    """The float64 keys behind G image values (host arithmetic on G numbers: the image map is its own inverse)."""
+    img = image.to_numpy().astype(np.int64)
+    bits = img ^ ((img >> np.int64(63)) & _MAG)
+    keys = bits.view(np.float64).copy()
+    keys[img == _I64_MAX] = np.nan
+    return keys
+

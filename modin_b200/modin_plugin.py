@@ -103,7 +103,7 @@ def register(shims: bool | None = None):
     from . import dist as bdist
     from . import functors as fx
     from . import partitioning as bp
-    from .block import DeviceBlock
+    from .block import DeviceBlock, DeviceColumn
     from .query_compiler import _dtypes_sum
 
     # ---------------------------------------------------------------- partition manager
@@ -334,6 +334,20 @@ def register(shims: bool | None = None):
                     raise NotImplementedError("device groupby: no level=")
                 frame, by_frame = query_compiler._modin_frame, by._modin_frame
                 plan = names = None
+                float_key = len(by.columns) == 1 and by_frame.has_materialized_dtypes and by.dtypes.iloc[0] == np.float64
+                if float_key:
+                    # a float64 key: the single-key groupby runs on its order-preserving int64 image (NaN = one group
+                    # that sorts last), the G result keys are mapped back afterwards (groupkeys.float_image / float_keys)
+                    from . import groupkeys as gk
+
+                    if by_frame._partitions.shape[1] != 1:
+                        raise NotImplementedError("device groupby: one key column partition")
+                    pc = by_frame._partition_mgr_cls._partition_class
+                    rows = [row[0].get() for row in by_frame._partitions]
+                    parts = np.array([[pc(DeviceBlock([gk.float_image(b.cols[0])], b.columns, nrows=b.nrows,
+                                                      range_start=b.range_start))] for b in rows], dtype=object)  # fmt: skip
+                    by_frame = type(by_frame)(parts, by_frame.copy_index_cache(), by_frame.copy_columns_cache(),
+                                              by_frame.row_lengths, [1])  # fmt: skip
                 if len(by.columns) > 1:
                     # several int64 keys: packed into one order-preserving int64 on the device (groupkeys.py), the
                     # single-key groupby runs on the image, the G result keys are unpacked into index columns
@@ -361,6 +375,19 @@ def register(shims: bool | None = None):
                         b = row[0].get()
                         nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=gk.unpack(b.index_cols[0], plan),
                                          index_names=names)  # fmt: skip
+                        nb.keys_sorted_unique = True
+                        rows.append([pc(nb)])
+                    new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)
+                if float_key:
+                    pc = new_frame._partition_mgr_cls._partition_class
+                    rows = []
+                    for row in new_frame._partitions:
+                        b = row[0].get()
+                        keys = gk.float_keys(b.index_cols[0]) if b.nrows else np.zeros(0, dtype=np.float64)
+                        if groupby_kwargs.get("dropna", True) and b.nrows and np.isnan(keys[-1]):
+                            b, keys = b.slice_rows(0, b.nrows - 1), keys[:-1]  # the NaN group is the last row, if any
+                        nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=[DeviceColumn.from_numpy(keys)],
+                                         index_names=b.index_names)  # fmt: skip
                         nb.keys_sorted_unique = True
                         rows.append([pc(nb)])
                     new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)

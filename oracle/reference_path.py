@@ -207,7 +207,7 @@ def df_mean(df, npartitions, skipna=True, threads: int = 1):
 
 
 # ------------------------------------------------------------------ GroupByReduce (alg/groupby.py)
-def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) -> pandas.DataFrame:
+def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1, dropna: bool = True) -> pandas.DataFrame:
     """``df.groupby(by).<agg>()`` through GroupByReduce: map = per row block
     ``df.groupby(by, as_index=True, sort=True).<map_agg>()`` (alg/groupby.py:124-208); reduce =
     concat of the partial tables + ``groupby(level=0).<reduce_agg>()`` (alg/groupby.py:211-300).
@@ -217,7 +217,7 @@ def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) ->
     row_blocks = [pandas.concat(row, axis=1) if len(row) > 1 else row[0] for row in grid]
 
     def map_fn(block):
-        g = block.groupby(by, as_index=True, sort=True, observed=True)
+        g = block.groupby(by, as_index=True, sort=True, observed=True, dropna=dropna)  # groupby_kwargs reach both phases
         if agg == "sum":
             return g.sum()
         if agg == "count":
@@ -234,8 +234,8 @@ def groupby_reduce(df, by: str, agg: str, npartitions: int, threads: int = 1) ->
     stacked = pandas.concat(partials, axis=0)
     levels = list(range(len(by))) if isinstance(by, (list, tuple)) else 0  # several key columns -> MultiIndex levels
     if agg in ("min", "max"):  # impl table storage_formats/pandas/groupby.py:237-248: ("min","min"), ("max","max")
-        return getattr(stacked.groupby(level=levels, sort=True), agg)()
-    regrouped = stacked.groupby(level=levels, sort=True).sum()
+        return getattr(stacked.groupby(level=levels, sort=True, dropna=dropna), agg)()
+    regrouped = stacked.groupby(level=levels, sort=True, dropna=dropna).sum()
     if agg == "mean":
         return regrouped["sum"] / regrouped["count"]
     if agg == "size":

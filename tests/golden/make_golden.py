@@ -139,6 +139,19 @@ def sixth_batch_frames(synth):
     return fact, dim, dim_dups
 
 
+def seventh_batch_frame(synth):
+    """Input of the ``ext7`` cases (float64 group keys; shared with the tests): ~25 distinct half-integers of both
+    signs, both zeros, 5 % NaN keys; float64 values with NaN."""
+    n = 6007
+    rng = np.random.RandomState(23)
+    f = synth.host_frame(n, 3, seed=81, nan_per_64k=2500)
+    fk = np.round(rng.randn(n) * 3.0, 0) / 2.0
+    fk[rng.rand(n) < 0.05] = np.nan
+    fk[:4] = [0.0, -0.0, 0.0, -0.0]
+    f.insert(0, "fk", fk)
+    return f
+
+
 def main():
     os.environ["MODIN_ENGINE"] = "python"
     apply_pandas3_shims()
@@ -345,6 +358,19 @@ def main():
     r = P(mf.merge(mpd.DataFrame(dim.rename(columns={"a": "k"})), left_on=["a", "b"], right_on=["k", "b"], how="left"))
     arrays["lr_on"], arrays["lr_on_cols"] = r.to_numpy(dtype=np.float64), np.array(list(r.columns))
     save("ext6_multikey_merge", meta=np.array([4001, 170]), **arrays)
+
+    # ---- seventh batch: groupby on a float64 key (alg/groupby.py:124-300 is pandas' groupby per block, whatever the key)
+    F7 = seventh_batch_frame(synth)
+    m7 = mpd.DataFrame(F7)
+    arrays = {}
+    for agg in ("sum", "count", "mean", "min", "max", "size"):
+        r = P(getattr(m7.groupby("fk"), agg)())
+        arrays[agg + "_keys"], arrays[agg] = r.index.to_numpy(), np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+    r = P(m7.groupby("fk", dropna=False).sum())
+    arrays["sum_keepna_keys"], arrays["sum_keepna"] = r.index.to_numpy(), r.to_numpy()
+    r = P(m7.groupby("fk", as_index=False).mean())
+    arrays["mean_flat"], arrays["mean_flat_cols"] = r.to_numpy(), np.array(list(r.columns))
+    save("ext7_float_keys", meta=np.array([6007]), **arrays)
 
     # ---- C4-like: groupby on int64 key, float64 values (with NaNs)
     for n, G, V, nan in ((5000, 37, 3, 0), (20011, 1500, 8, 3000)):

@@ -95,6 +95,37 @@ def _sixth_batch_checks(pdm):
         mf.merge(pdm.DataFrame(dim), left_on=["a", "c0"], right_on=["a", "d"])
 
 
+def _seventh_batch_checks(pdm):
+    """groupby on a float64 key through the real Modin front door (the key runs as its order-preserving int64 image,
+    ``groupkeys.float_image``) against the unmodified reference: keys bit for bit -- NaN keys dropped or kept as one
+    last group --, counts / sizes / min / max exact, sums and means within the per-group bound."""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import seventh_batch_frame
+
+    z = dict(np.load(os.path.join(GOLDEN, "ext7_float_keys.npz"), allow_pickle=False))
+    F = seventh_batch_frame(synth)
+    n = len(F)
+    P = lambda x: x._to_pandas()  # noqa: E731
+    df = pdm.DataFrame(F)
+    vcols = ["c0", "c1", "c2"]
+    abs_sums = F[vcols].abs().groupby(F["fk"]).sum().to_numpy()
+    counts = np.maximum(F[vcols].notna().groupby(F["fk"]).sum().to_numpy(), 1)
+    for agg in ("sum", "count", "mean", "min", "max", "size"):
+        r = P(getattr(df.groupby("fk"), agg)())
+        assert np.array_equal(r.index.to_numpy(), z[agg + "_keys"]) and r.index.name == "fk", agg
+        got = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+        if agg in ("sum", "mean"):
+            tol = 4.0 * math.log2(n) * EPS * (abs_sums if agg == "sum" else abs_sums / counts + np.abs(np.nan_to_num(z[agg])) / (2.0 * math.log2(n))) + 1e-300
+            assert ((np.isnan(got) & np.isnan(z[agg])) | (np.abs(got - z[agg]) <= tol)).all(), agg
+        else:
+            assert np.array_equal(got, z[agg], equal_nan=True), agg
+    r = P(df.groupby("fk", dropna=False).sum())
+    assert np.array_equal(r.index.to_numpy(), z["sum_keepna_keys"], equal_nan=True)
+    assert np.allclose(r.to_numpy(), z["sum_keepna"], rtol=0, atol=1e-9, equal_nan=True)
+    r = P(df.groupby("fk", as_index=False).mean())
+    assert list(r.columns) == list(z["mean_flat_cols"]) and np.allclose(r.to_numpy(), z["mean_flat"], rtol=0, atol=1e-9, equal_nan=True)
+
+
 def test_fifth_batch_through_the_mirror_on_the_double(cpu_device):
     import torch
 
@@ -114,6 +145,7 @@ def test_fifth_batch_under_real_modin_on_the_double(cpu_device):
         pytest.skip("GPU present: covered by the gpu-marked test")
     _fifth_batch_checks(_modin(), True)
     _sixth_batch_checks(_modin())
+    _seventh_batch_checks(_modin())
 
 
 @pytest.mark.gpu

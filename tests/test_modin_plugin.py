@@ -447,6 +447,10 @@ def _plugin_rank_job(rank, ws):
         medge = mpd.DataFrame(edge)
         for name in ("cumsum", "cummax", "ffill"):
             out["edge_" + name] = P(getattr(medge, name)())
+        fkey = pdf.assign(fk=np.where(np.arange(len(pdf)) % 17 == 0, np.nan, np.round(pdf["c0"].fillna(0.0) * 2.0, 0) / 2.0))
+        mfk = mpd.DataFrame(fkey.drop(columns="key"))
+        out["gb_float_key"] = P(mfk.groupby("fk").sum())  # the key runs as its int64 image; NaN keys are dropped
+        out["gb_float_key_keepna"] = P(mfk.groupby("fk", dropna=False).count())
         out["gb_dict"] = P(g.agg({"c2": "mean", "c0": "sum", "c3": "max"}))  # one device aggregation per function
         rng = np.random.RandomState(1)
         dim = pandas.DataFrame({"key": rng.permutation(23)[:20].astype(np.int64), "d0": rng.randn(20)})
@@ -523,6 +527,13 @@ def test_plugin_under_two_gloo_ranks():
         edge.iloc[1001:, 2] = np.nan
         assert np.allclose(o["edge_cumsum"].to_numpy(), edge.cumsum().to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
         assert o["edge_cummax"].equals(edge.cummax()) and o["edge_ffill"].equals(edge.ffill())
+        fkey = pdf.assign(fk=np.where(np.arange(len(pdf)) % 17 == 0, np.nan, np.round(pdf["c0"].fillna(0.0) * 2.0, 0) / 2.0))
+        wfk = fkey.drop(columns="key").groupby("fk").sum()
+        assert np.array_equal(o["gb_float_key"].index.to_numpy(), wfk.index.to_numpy())
+        assert np.allclose(o["gb_float_key"].to_numpy(), wfk.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)
+        wfk = fkey.drop(columns="key").groupby("fk", dropna=False).count()
+        assert np.array_equal(o["gb_float_key_keepna"].index.to_numpy(), wfk.index.to_numpy(), equal_nan=True)
+        assert np.array_equal(o["gb_float_key_keepna"].to_numpy(), wfk.to_numpy())
         wd_ = pdf.groupby("key").agg({"c2": "mean", "c0": "sum", "c3": "max"})
         assert list(o["gb_dict"].columns) == list(wd_.columns) and list(o["gb_dict"].index) == list(wd_.index)
         assert np.allclose(o["gb_dict"].to_numpy(), wd_.to_numpy(), rtol=0, atol=1e-9, equal_nan=True)

@@ -347,3 +347,22 @@ def test_sixth_batch_against_reference(golden_dir):
     r = orc.broadcast_merge_general(fact, dim.rename(columns={"a": "k"}), "left", NP, left_on=["a", "b"], right_on=["k", "b"])
     assert list(r.columns) == list(z["lr_on_cols"])
     assert_bit_equal(r.to_numpy(dtype=np.float64), z["lr_on"], "merge left_on / right_on lists")
+
+
+def test_seventh_batch_against_reference(golden_dir):
+    """groupby on a float64 key (NaN keys dropped, or kept as one group): the restatement pinned to the unmodified
+    reference (ext7_float_keys.npz)."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from make_golden import seventh_batch_frame
+
+    z = dict(np.load(os.path.join(golden_dir, "ext7_float_keys.npz"), allow_pickle=False))
+    F = seventh_batch_frame(synth)
+    for agg in ("sum", "count", "mean", "min", "max", "size"):
+        r = orc.groupby_reduce(F, "fk", agg, NP)
+        assert_bit_equal(r.index.to_numpy(), z[agg + "_keys"], f"float keys {agg}: keys")
+        assert_bit_equal(np.asarray(r, dtype=np.float64).reshape(len(r), -1), z[agg], f"float keys {agg}")
+    r = orc.groupby_reduce(F, "fk", "sum", NP, dropna=False)
+    assert_bit_equal(r.index.to_numpy(), z["sum_keepna_keys"], "float keys, dropna=False: keys")
+    assert_bit_equal(r.to_numpy(), z["sum_keepna"], "float keys, dropna=False")

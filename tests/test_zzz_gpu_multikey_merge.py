@@ -1,5 +1,6 @@
-"""GPU variant of the multi-key merge checks (``tests/test_fifth_batch.py::_sixth_batch_checks``: both front doors
-against ``tests/golden/ext6_multikey_merge.npz`` from the unmodified reference).
+"""GPU variants of the multi-key merge checks (``tests/test_fifth_batch.py::_sixth_batch_checks``: both front doors
+against ``tests/golden/ext6_multikey_merge.npz`` from the unmodified reference) and of the float-key groupby checks
+(``_seventh_batch_checks``: the Modin front door against ``ext7_float_keys.npz``).
 
 Kept in a file of its own that sorts LAST: the feature was written after the round's GPU minutes were spent, so unlike
 everything else under ``-m gpu`` it has run on the numpy device double only (it is composed from kernels that are
@@ -12,7 +13,7 @@ import os
 import pytest
 
 from tests.test_alignment_merge import REF, _modin
-from tests.test_fifth_batch import _sixth_batch_checks
+from tests.test_fifth_batch import _seventh_batch_checks, _sixth_batch_checks
 
 
 @pytest.mark.gpu
@@ -22,3 +23,10 @@ def test_multi_key_merge_on_b200():
     _sixth_batch_checks(bpd)
     if os.path.isdir(os.path.join(REF, "modin")):
         _sixth_batch_checks(_modin())
+
+
+@pytest.mark.gpu
+def test_float_key_groupby_on_b200():
+    if not os.path.isdir(os.path.join(REF, "modin")):
+        pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")
+    _seventh_batch_checks(_modin())
