@@ -318,6 +318,39 @@ def register(shims: bool | None = None):
                 dtypes = dtypes.loc[list(columns)]
             return dtypes
 
+    _LEVEL_KEY = "__b200_index_level__"
+
+    def _labels_as_by(query_compiler, level):
+        """(query compiler of ONE key column holding the row labels, the level's name) for ``groupby(level=...)`` on a
+        single-level index."""
+        from . import ops
+
+        frame = query_compiler._modin_frame
+        levels = level if isinstance(level, (list, tuple)) else [level]
+        if len(levels) != 1 or frame._partitions.shape[1] < 1:
+            raise NotImplementedError("device groupby: one index level")
+        frame._propagate_index_objs(axis=0)  # deferred labels go into the blocks first
+        pc = frame._partition_mgr_cls._partition_class
+        rows, name = [], None
+        for row in frame._partitions:
+            b = row[0].get()
+            if b.index_host is not None or (b.index_cols and len(b.index_cols) != 1):
+                raise NotImplementedError("device groupby(level=): numeric single-level row labels")
+            if b.index_cols:
+                col, name = b.index_cols[0], (b.index_names or [None])[0]
+            else:
+                col = ops.iota(b.range_start, b.nrows)
+            rows.append([pc(DeviceBlock([col], pandas.Index([_LEVEL_KEY]), nrows=b.nrows, range_start=b.range_start))])
+        lv = levels[0]
+        if isinstance(lv, (int, np.integer)) and not isinstance(lv, bool):
+            if lv not in (0, -1):  # pandas' own errors (core/groupby/grouper.py)
+                raise ValueError("level > 0 or level < -1 only valid with MultiIndex")
+        elif lv != name:
+            raise ValueError(f"level name {lv} is not the name of the index")
+        by_frame = type(frame)(np.array(rows, dtype=object), frame.copy_index_cache(), pandas.Index([_LEVEL_KEY]),
+                               frame.row_lengths, [1])  # fmt: skip
+        return query_compiler.__constructor__(by_frame), name
+
     # ---------------------------------------------------------------- GroupByReduce over device blocks
     class B200GroupByReduce(GroupByReduce):
         """alg/groupby.py: same template, but the per-block map / reduce bodies are the device functors
@@ -328,10 +361,17 @@ def register(shims: bool | None = None):
             map_f, red_f = fx.DevGroupbyMap(agg), fx.DevGroupbyReduce(agg)
 
             def caller(query_compiler, by, axis, groupby_kwargs, agg_args, agg_kwargs, drop=False, **kwargs):
+                level = groupby_kwargs.get("level")
+                level_name = None
+                if by is None and level is not None and axis == 0:
+                    # groupby(level=0): the row labels are the key (alg/groupby.py:355-390 hands ``level`` to pandas per
+                    # block).  They already sit on the device (an index column) or are a range (materialised with
+                    # mb200_iota); the frame of one key column built from them goes down the ordinary path
+                    by, level_name = _labels_as_by(query_compiler, level)
+                elif level is not None:
+                    raise NotImplementedError("device groupby: `level=` together with `by` is not on the B200 path")
                 if axis != 0 or not isinstance(by, type(query_compiler)) or len(by.columns) < 1:
                     raise NotImplementedError("device groupby: key columns of the same frame, axis=0")
-                if groupby_kwargs.get("level") is not None:
-                    raise NotImplementedError("device groupby: no level=")
                 frame, by_frame = query_compiler._modin_frame, by._modin_frame
                 plan = names = None
                 float_key = len(by.columns) == 1 and by_frame.has_materialized_dtypes and by.dtypes.iloc[0] == np.float64
@@ -378,6 +418,15 @@ def register(shims: bool | None = None):
                         nb.keys_sorted_unique = True
                         rows.append([pc(nb)])
                     new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)
+                if level is not None and not float_key and plan is None:
+                    pc = new_frame._partition_mgr_cls._partition_class
+                    rows = []
+                    for row in new_frame._partitions:  # the private key label gives way to the index level's own name
+                        b = row[0].get()
+                        nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=b.index_cols, index_names=[level_name])
+                        nb.keys_sorted_unique = True
+                        rows.append([pc(nb)])
+                    new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)
                 if float_key:
                     pc = new_frame._partition_mgr_cls._partition_class
                     rows = []
@@ -387,7 +436,7 @@ def register(shims: bool | None = None):
                         if groupby_kwargs.get("dropna", True) and b.nrows and np.isnan(keys[-1]):
                             b, keys = b.slice_rows(0, b.nrows - 1), keys[:-1]  # the NaN group is the last row, if any
                         nb = DeviceBlock(b.cols, b.columns, nrows=b.nrows, index_cols=[DeviceColumn.from_numpy(keys)],
-                                         index_names=b.index_names)  # fmt: skip
+                                         index_names=[level_name] if level is not None else b.index_names)  # fmt: skip
                         nb.keys_sorted_unique = True
                         rows.append([pc(nb)])
                     new_frame = type(new_frame)(np.array(rows, dtype=object), None, None, None, None)

@@ -314,6 +314,28 @@ def test_odd_shapes_under_real_modin_cpu_double(modin_b200_execution, cpu_device
         emp[f].sum()
 
 
+def _level_scenarios(mpd):
+    """``groupby(level=0)`` through real ``modin.pandas``: the row labels are the key (a device label column, or a range
+    materialised on the device); written after the round's last GPU run, so kept out of the scenario set whose
+    ``gpu``-marked variant has passed on a B200."""
+    pdf = synth.host_frame(2003, 3, seed=11, nan_per_64k=3000)
+    fcols = ["c0", "c1", "c2"]
+    P = lambda x: x._to_pandas()  # noqa: E731
+    for idx in (pandas.Index(np.arange(len(pdf)) % 37 - 5, name="lab"), pandas.RangeIndex(len(pdf)),
+                pandas.Index(np.round(np.sin(np.arange(len(pdf))) * 4) / 2, name="f")):
+        lp = pdf[fcols].set_axis(idx, axis=0)
+        ldf = mpd.DataFrame(lp)
+        for agg in ("sum", "count", "max", "size"):
+            got, want = P(getattr(ldf.groupby(level=0), agg)()), getattr(lp.groupby(level=0), agg)()
+            assert np.array_equal(got.index.to_numpy(), want.index.to_numpy()) and got.index.name == want.index.name, (idx.name, agg)
+            assert np.allclose(np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64), rtol=0, atol=1e-9, equal_nan=True)
+    assert P(ldf.groupby(level="f").sum()).index.name == "f"
+    with pytest.raises(ValueError, match="only valid with MultiIndex"):
+        ldf.groupby(level=1).sum()
+    with pytest.raises(ValueError, match="not the name of the index"):
+        ldf.groupby(level="nope").sum()
+
+
 def test_late_additions_under_real_modin_cpu_double(modin_b200_execution, cpu_device):
     import torch
 
@@ -321,6 +343,7 @@ def test_late_additions_under_real_modin_cpu_double(modin_b200_execution, cpu_de
         pytest.skip("GPU present: covered by the gpu-marked test")
     ns, mpd = modin_b200_execution
     _late_scenarios(mpd, ns)
+    _level_scenarios(mpd)
 
 
 def test_late_gpu_plugin_test_is_sound_on_the_double(modin_b200_execution, cpu_device, monkeypatch):

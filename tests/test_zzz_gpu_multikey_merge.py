@@ -30,3 +30,12 @@ def test_float_key_groupby_on_b200():
     if not os.path.isdir(os.path.join(REF, "modin")):
         pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")
     _seventh_batch_checks(_modin())
+
+
+@pytest.mark.gpu
+def test_groupby_level_on_b200():
+    if not os.path.isdir(os.path.join(REF, "modin")):
+        pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")
+    from tests.test_modin_plugin import _level_scenarios
+
+    _level_scenarios(_modin())
