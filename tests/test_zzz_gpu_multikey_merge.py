@@ -15,8 +15,12 @@ import pytest
 from tests.test_alignment_merge import REF, _modin
 from tests.test_fifth_batch import _seventh_batch_checks, _sixth_batch_checks
 
+UNTRIED = pytest.mark.xfail(strict=False, reason="written after the round's last GPU minute: has run on the numpy "
+                           "device double only, never on a B200 (an XPASS is the first hardware evidence)")
+
 
 @pytest.mark.gpu
+@UNTRIED
 def test_multi_key_merge_on_b200():
     import modin_b200.pandas as bpd
 
@@ -26,6 +30,7 @@ def test_multi_key_merge_on_b200():
 
 
 @pytest.mark.gpu
+@UNTRIED
 def test_float_key_groupby_on_b200():
     if not os.path.isdir(os.path.join(REF, "modin")):
         pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")
@@ -33,6 +38,7 @@ def test_float_key_groupby_on_b200():
 
 
 @pytest.mark.gpu
+@UNTRIED
 def test_groupby_level_on_b200():
     if not os.path.isdir(os.path.join(REF, "modin")):
         pytest.skip("baseline/_ref (the unmodified reference) is not installed on this box")

@@ -29,7 +29,9 @@ from modin_b200 import synth
 from oracle import reference_path as orc
 from tests.test_gpu_parity import EPS, _load, assert_sum_close, bpd
 
-pytestmark = pytest.mark.gpu
+UNTRIED = pytest.mark.xfail(strict=False, reason="written after the round's last GPU minute: has run on the numpy "
+                           "device double only, never on a B200 (an XPASS is the first hardware evidence)")
+pytestmark = [pytest.mark.gpu, UNTRIED]
 
 
 def _var_rtol(n):
