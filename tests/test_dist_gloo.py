@@ -561,3 +561,61 @@ def test_full_stack_sort_values_across_ranks():
     want = pdf.sort_values("c1", kind="stable", ignore_index=True)
     assert np.array_equal(np.concatenate([o["ignore"][0] for o in out]), want.index.to_numpy())
     assert np.array_equal(np.concatenate([o["ignore"][1] for o in out]), want.to_numpy(dtype=np.float64), equal_nan=True)
+
+
+def _dedupe_and_packed_merge_sweep_job(rank, ws):
+    """Random shapes for the two exchanges written late in round 2: drop_duplicates across ranks (keys of the per-rank
+    survivors all-gathered) and the merge on two key columns (keys packed over the ranges of BOTH frames, agreed across
+    ranks).  Shards of 0 / 1 / a few rows, all duplicates in one shard, keys of both signs."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_double
+    import modin_b200.pandas as bpd
+    from modin_b200 import config
+
+    out = []
+    with cpu_double.installed():
+        config.NPartitions.put(2)
+        for case, (n, modulus) in enumerate(((0, 5), (1, 5), (2, 1), (7, 3), (50, 4), (333, 40), (2003, 7), (2003, 1500))):
+            rng = np.random.RandomState(100 + case)
+            pdf = pandas.DataFrame({"key": rng.randint(0, modulus, n).astype(np.int64) * 3 - modulus,
+                                    "k2": rng.randint(-2, 3, n).astype(np.int64), "v": rng.randn(n)})
+            if n >= 50:
+                pdf.loc[: n // 3, "key"] = pdf["key"].iloc[0]  # a long run of one key inside the first shard
+            df = bpd.DataFrame(pdf)
+            res = {"n": n, "modulus": modulus}
+            for keep in ("first", "last"):
+                res["dd_" + keep] = df.drop_duplicates(subset=["key"], keep=keep)._to_pandas()
+            res["dd_ignore"] = df.drop_duplicates(subset=["k2"], keep="last", ignore_index=True)._to_pandas()
+            pairs = sorted({(int(a), int(b)) for a, b in zip(rng.randint(0, modulus, 40) * 3 - modulus, rng.randint(-2, 3, 40))})
+            dim = pandas.DataFrame({"key": np.array([p[0] for p in pairs], dtype=np.int64),
+                                    "k2": np.array([p[1] for p in pairs], dtype=np.int64), "w": rng.randn(len(pairs))})
+            res["dim"] = dim
+            if n:
+                for how in ("left", "inner"):
+                    res["merge_" + how] = df.merge(bpd.DataFrame(dim), on=["key", "k2"], how=how)._to_pandas()
+            out.append((pdf, res))
+    return out
+
+
+def test_dedupe_and_packed_merge_sweep_across_three_ranks():
+    import pandas
+
+    outs = _run(_dedupe_and_packed_merge_sweep_job, ws=3)
+    for rank_out in outs:  # every rank gathers the same job-wide answers
+        for pdf, res in rank_out:
+            tag = (res["n"], res["modulus"])
+            for keep in ("first", "last"):
+                want = pdf.drop_duplicates(subset=["key"], keep=keep)
+                got = res["dd_" + keep]
+                assert list(got.index) == list(want.index) and np.array_equal(got.to_numpy(), want.to_numpy()), (tag, keep)
+            want = pdf.drop_duplicates(subset=["k2"], keep="last", ignore_index=True)
+            assert list(res["dd_ignore"].index) == list(want.index), tag
+            assert np.array_equal(res["dd_ignore"].to_numpy(), want.to_numpy()), tag
+            for how in ("left", "inner"):
+                if res["n"]:
+                    want = pandas.merge(pdf, res["dim"], on=["key", "k2"], how=how)
+                    got = res["merge_" + how]
+                    assert list(got.columns) == list(want.columns) and got.shape == want.shape, (tag, how)
+                    assert np.array_equal(got.to_numpy(dtype=np.float64), want.to_numpy(dtype=np.float64), equal_nan=True), (tag, how)

@@ -630,3 +630,68 @@ def test_results_are_released_without_the_cycle_collector(modin_b200_execution, 
         assert not kept, f"still allocated after the last reference went: {kept}"
     finally:
         gc.enable()
+
+
+def _fold_and_keys_sweep_job(rank, ws):
+    """Tiny and empty shards for what was written late in round 2 and crosses ranks: the Fold carries, float-key and
+    ``level=`` groupby, dictionary aggregation -- through real ``modin.pandas`` on the numpy device double."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    import cpu_double
+    from modin_b200 import config, modin_plugin
+
+    out = []
+    with cpu_double.installed():
+        modin_plugin.activate()
+        import modin.config as cfg
+        import modin.pandas as mpd
+
+        cfg.NPartitions.put(2)
+        config.NPartitions.put(2)
+        P = lambda x: x._to_pandas()  # noqa: E731
+        for case, n in enumerate((1, 2, 5, 64, 2003)):  # 1, 2 and 5 rows over 3 ranks: some shards are empty
+            rng = np.random.RandomState(40 + case)
+            pdf = pandas.DataFrame({"a": rng.randn(n), "b": rng.randn(n), "i": rng.randint(-9, 9, n).astype(np.int64)})
+            pdf.loc[rng.rand(n) < 0.3, "a"] = np.nan
+            pdf.iloc[: max(1, n // 2), 1] = np.nan  # the first half of "b" has nothing valid: carries of "nothing yet"
+            df = mpd.DataFrame(pdf)
+            res = {"n": n}
+            for name in ("cumsum", "cummax", "cummin", "ffill"):
+                res[name] = P(getattr(df, name)())
+            fvals = pdf[["a", "b"]]  # group sums / maxima aggregate float64 value columns
+            fk = fvals.assign(fk=np.where(rng.rand(n) < 0.2, np.nan, np.round(rng.randn(n), 0) / 2.0))
+            res["fk_frame"] = fk
+            res["fk_sum"] = P(mpd.DataFrame(fk).groupby("fk").sum())
+            lab = fvals.set_axis(pandas.Index(rng.randint(0, 4, n).astype(np.int64), name="lab"), axis=0)
+            res["lab_frame"] = lab
+            res["lab_max"] = P(mpd.DataFrame(lab).groupby(level=0).max())
+            out.append((pdf, res))
+    return out
+
+
+def test_fold_and_key_kinds_sweep_across_three_ranks():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tools/dist_check.py covers the plug-in under NCCL")
+    from tests.test_dist_gloo import _run
+
+    for rank_out in _run(_fold_and_keys_sweep_job, ws=3):
+        for pdf, res in rank_out:
+            n = res["n"]
+            got, want = res["cumsum"], pdf.cumsum()
+            assert list(got.index) == list(want.index) and np.allclose(got.to_numpy(), want.to_numpy(), rtol=0, atol=1e-9, equal_nan=True), n
+            for name in ("cummax", "cummin", "ffill"):
+                assert res[name].equals(getattr(pdf, name)()), (n, name)
+            want = res["fk_frame"].groupby("fk").sum()
+            assert np.array_equal(res["fk_sum"].index.to_numpy(), want.index.to_numpy()), n
+            assert np.allclose(res["fk_sum"].to_numpy(), want.to_numpy(), rtol=0, atol=1e-9, equal_nan=True), n
+            want = res["lab_frame"].groupby(level=0).max()
+            assert np.array_equal(res["lab_max"].index.to_numpy(), want.index.to_numpy()) and res["lab_max"].index.name == "lab", n
+            assert np.array_equal(res["lab_max"].to_numpy(), want.to_numpy(), equal_nan=True), n
