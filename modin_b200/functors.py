@@ -616,9 +616,9 @@ class DevDropDuplicates(DevFn):
         t = ops.torch_mod()
         n = len(key)
         if n <= 1:
-            return DeviceColumn(t.arange(n, dtype=t.int64, device=key.data.device), np.int64)
+            return ops.iota(0, n)
         image = ops.map_columns("ordered_s", [key], s0=[0])[0]  # fresh buffer: the sort is in place
-        perm = DeviceColumn(t.arange(n, dtype=t.int64, device=key.data.device), np.int64)
+        perm = ops.iota(0, n)  # mb200_iota_i64: the row ids the sort carries along
         ops.sort_pairs(image, perm)
         edge = ops.map_columns("ne", [image.slice(1, n)], [image.slice(0, n - 1)])[0]  # edge[i]: run ends at i
         idx = ops.map_columns("add_s", ops.cast_columns_i64([edge]), s0=[-1])[0]  # 0 -> -1 (skip), 1 -> 0 (hit)

@@ -962,7 +962,12 @@ def gather_block(block: DeviceBlock) -> DeviceBlock:
     if nlabel == 1 and not icols:  # explicit labels elsewhere: this rank's range becomes explicit too, in their dtype
         as_float = any(m[0] and m[4] for m in meta)
         ldt, ndt = (t.float64, np.float64) if as_float else (t.int64, np.int64)
-        icols = [DeviceColumn(t.arange(block.range_start, block.range_start + block.nrows, dtype=ldt, device=dev), ndt)]
+        if as_float:
+            icols = [DeviceColumn(t.arange(block.range_start, block.range_start + block.nrows, dtype=ldt, device=dev), ndt)]
+        else:
+            from . import ops
+
+            icols = [ops.iota(block.range_start, block.nrows)]
     tensors += [c.data for c in icols]
     gathered = dist.all_gather_rows(tensors)
     ncol = len(block.cols)
