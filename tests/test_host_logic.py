@@ -209,3 +209,29 @@ def test_reference_arm_prints_the_contract_line():
     assert j["impl"] == "reference" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "reference"
     assert "modin.pandas" in j["config"]["api"] and j["cpu_baseline"]["alongside"]["groupby_sum"]["checked"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_cum_entry_points_validate_arguments_before_touching_a_device():
+    """The Fold kernels' entry points (csrc/cum.cu): scratch sizing is host arithmetic (one 8-byte aggregate per column
+    and 4096-row tile), and bad arguments are refused with a message before any device is looked for -- so this runs in
+    a container without a GPU."""
+    import ctypes as C
+
+    lib = _lib.load()
+    assert lib.mb200_cum_scratch_bytes(8, 10**9) == 8 * ((10**9 + 4095) // 4096) * 8 + 256
+    assert lib.mb200_cum_scratch_bytes(3, 0) == 3 * 8 + 256 and lib.mb200_cum_scratch_bytes(1, 4096) == 8 + 256
+    none = _lib.ptr_array([None])
+    for args, needle in (
+        ((99, _lib.F64, 1, none, 10, None, 0, None, None), b"op must be"),
+        ((_lib.CUM["ffill"], _lib.I64, 1, none, 10, None, 0, None, None), b"op must be"),
+        ((_lib.CUM["sum"], _lib.U8, 1, none, 10, None, 0, None, None), b"dtype must be"),
+        ((_lib.CUM["sum"], _lib.F64, -1, none, 10, None, 0, None, None), b"negative"),
+        ((_lib.CUM["sum"], _lib.F64, 1, none, 10, None, 0, None, None), b"null or misaligned column"),
+    ):
+        assert lib.mb200_cum_partials(*args) != 0 and needle in lib.mb200_last_error(), (args[:3], lib.mb200_last_error())
+    buf = (C.c_double * 4)()
+    misaligned = _lib.ptr_array([C.addressof(buf) + 4])
+    assert lib.mb200_cum_partials(_lib.CUM["max"], _lib.F64, 1, misaligned, 2, None, 0, None, None) != 0
+    assert b"misaligned" in lib.mb200_last_error()
+    assert lib.mb200_cum_carry(_lib.CUM["sum"], _lib.F64, 2, None, 1, None, None) != 0 and b"null argument" in lib.mb200_last_error()
+    assert lib.mb200_cum_carry(_lib.CUM["sum"], _lib.F64, 0, None, 0, None, None) == 0  # nothing to do is not an error
