@@ -440,6 +440,14 @@ def run_b200_arm(args):
             print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+    def release():
+        """Between legs: collect cyclic garbage first (Modin's API objects reference themselves; a dead 32 GB result
+        held by such a cycle would survive ``empty_cache``), then hand the cached blocks back to the driver."""
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+
     rows, W, G = int(args.rows), args.cols, args.groups
     lo, hi = dist.shard_bounds(rows)
     rows_local = hi - lo
@@ -583,7 +591,7 @@ def run_b200_arm(args):
         _cfg.ReduceVariant.put(0)
         abs8 = np.asarray(api.to_pandas(a.abs().sum()), dtype=np.float64)
         a = None
-        torch.cuda.empty_cache()
+        release()
 
         progress("leg: TreeReduce sum / mean, 16 columns")
         # ---- TreeReduce (C3): df.sum() / df.mean() over 16 float64 columns.  1e9 x 16 f64 = 128 GB: the whole frame
@@ -614,7 +622,7 @@ def run_b200_arm(args):
                                           rows_local * W3 * 8, per_s, traffic_for("reduce_sum", rows_local * 2),
                                           launch_ms=kernel_ms(fn, "reduce_sum"))})  # fmt: skip
         del c3, res
-        torch.cuda.empty_cache()
+        release()
 
         # ---- Binary template on three frames: a*b+c with b, c frames (C2 secondary form; 256 B/row fused).
         # Four n x 8 frames are resident, so n = rows/4 (2.5e8 per 1e9: 64 GB on one GPU)
@@ -643,7 +651,7 @@ def run_b200_arm(args):
                      "value": rows3 / (total_f / ksteps / 1e3), "unit": UNIT, "ms_per_step": total_f / ksteps, "checked": ok,
                      "roofline": roof("map_kernel<FMA3,f64>", blk.nrows * W * 32, per_f, launch_ms=kernel_ms(step_fma3, "map_fma3"))})  # fmt: skip
         del fa, fb, fc, blk
-        torch.cuda.empty_cache()
+        release()
 
         # ---- Fold template: df.cumsum() down the rows (qc.py:2431; csrc/cum.cu).  Input + output resident, so
         # n = rows/2 (32 + 32 GB per 1e9 on one GPU); rows sharded over ranks scan locally, carries cross the ranks
@@ -685,7 +693,7 @@ def run_b200_arm(args):
         except Exception as exc:  # a leg added late in round 2: a failure here must not take the other legs with it
             also.append({"metric": "rows/sec df.cumsum(), Fold template", "error": f"{type(exc).__name__}: {exc}"[:300]})
         last[0] = None
-        torch.cuda.empty_cache()
+        release()
 
         # ---- GroupByReduce: groupby('key').sum(), G int64 keys, 8 float64 values (C4)
         def groupby_leg(skew, dense_on, label, kern, traffic_key):
@@ -743,7 +751,7 @@ def run_b200_arm(args):
                                         note="key range and skew flag come from statistics the generator kernel left "
                                              "on the key column (column metadata): no pre-pass over the keys")  # fmt: skip
             del g
-            torch.cuda.empty_cache()
+            release()
 
         groupby_leg(False, True, "", "gb_accumulate_tma_kernel on a dense (direct-addressed) table pinned in L2", "groupby_sum_dense")
         groupby_leg(False, False, " [hash table forced]", "gb_accumulate_tma_kernel (open-addressed hash aggregate)", "groupby_sum")
@@ -812,7 +820,7 @@ def run_b200_arm(args):
                          "value": rows / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m, "checked": ok, "roofline": rf})  # fmt: skip
             del blk
         del fact, dim
-        torch.cuda.empty_cache()
+        release()
 
     if not args.skip_also:
         try:
@@ -827,7 +835,7 @@ def run_b200_arm(args):
             _cfg.ReduceVariant.put(0)
     a = None
     last[0] = None
-    torch.cuda.empty_cache()
+    release()
 
     # ---- e2e: host frames in, host frames out, through the public API (rank-local sample) ----------------
     e2e = e2e_groupby = None
