@@ -37,6 +37,8 @@
 extern "C" {
 #endif
 
+/* 2: round 2 (key statistics, async dense emit, expand / concat / comm entry points); 3: + the Fold template's
+ * cumulative scans (mb200_cum_*).  Checked by the binding at load time (modin_b200/_lib.py). */
 #define MB200_ABI_VERSION 3
 #define MB200_MAX_COLS 32 /* max columns per launch == Modin's MinColumnPartitionSize (envvars.py:1149-1190) */
 
